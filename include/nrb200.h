@@ -1,0 +1,207 @@
+/*
+ * nrb200.h -- C ABI of libnrb200, the B200 (sm_100a) engine behind nullranges::bootRanges().
+ *
+ * The reference (nullranges 1.7.10) is pure R: it has NO foreign-function boundary
+ * (NAMESPACE has no useDynLib; R/ has no .Call).  This header therefore DEFINES the
+ * boundary an R `.Call` shim (r-package/src/r_shim.c) binds; each entry
+ * point names the reference code it replaces.  The same ABI is driven from Python
+ * (nullranges_b200/_lib.py, ctypes) because R is not installed in the build image.
+ *
+ * Conventions
+ *   - plain C types only; every pointer is caller-owned HOST memory unless a name ends in
+ *     `_dev`; the library never keeps a host pointer after a call returns;
+ *   - coordinates are R `integer` (int32), 1-based closed intervals [start, end];
+ *   - seqname ids are 0-based indices into seqlevels(y); strand codes 0 '*', 1 '+', 2 '-'
+ *     (strand pointers may be NULL = all '*');
+ *   - every function returns NRB200_OK (0) or a negative code; the text is in
+ *     nrb200_last_error().  Nothing is thrown across the boundary, so an R shim can free
+ *     its resources and only then call Rf_error();
+ *   - a handle is bound to ONE GPU and is not thread-safe (R is single-threaded); use one
+ *     handle per GPU / per process rank.
+ */
+#ifndef NRB200_H
+#define NRB200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+#if defined(__GNUC__)
+#pragma GCC visibility push(default) /* the library itself is built with -fvisibility=hidden */
+#endif
+
+#define NRB200_OK 0
+#define NRB200_ERR_INVALID (-1)     /* bad argument (mirrors a stopifnot() of the reference) */
+#define NRB200_ERR_CUDA (-2)        /* CUDA runtime failure / no device */
+#define NRB200_ERR_STATE (-3)       /* call order: ranges / plan not set */
+#define NRB200_ERR_UNSUPPORTED (-4) /* valid in the reference, not (yet) on the device */
+#define NRB200_ERR_NOMEM (-5)
+
+typedef struct nrb200_handle nrb200_handle;
+
+typedef struct nrb200_config {
+    int32_t device;     /* CUDA ordinal */
+    uint32_t flags;     /* reserved, 0 */
+    void *stream;       /* cudaStream_t to launch on, or NULL = a private stream */
+} nrb200_config;
+
+int nrb200_create(const nrb200_config *cfg, nrb200_handle **out);
+void nrb200_destroy(nrb200_handle *h);
+/* h may be NULL: error of the last failed nrb200_create() on this thread. */
+const char *nrb200_last_error(const nrb200_handle *h);
+const char *nrb200_version(void);
+
+/* ---- inputs ------------------------------------------------------------------------ */
+
+/* y of bootRanges(y, ...) plus seqlengths(y) (R/bootRanges.R:80-81: all must be known).
+ * Any order is accepted; the engine canonicalises to (seqname, start, end) and remembers
+ * the permutation, so src_idx in results always refers to the caller's order. */
+int nrb200_set_ranges(nrb200_handle *h, int64_t n, int32_t n_seq, const int64_t *seqlengths,
+                      const int32_t *seqid, const int32_t *start, const int32_t *end,
+                      const int8_t *strand);
+
+/* x of countOverlaps(x, boots) / join_overlap_inner(x, boots)
+ * (vignettes/bootRanges.Rmd:482-483, 497-503, 749).  n = 0 clears. */
+int nrb200_set_query(nrb200_handle *h, int64_t n, const int32_t *seqid, const int32_t *start,
+                     const int32_t *end, const int8_t *strand);
+
+/* exclude of bootRanges(..., exclude, excludeOption = "drop") (R/bootRanges.R:106-109).
+ * n = 0 clears. */
+int nrb200_set_exclude(nrb200_handle *h, int64_t n, const int32_t *seqid, const int32_t *start,
+                       const int32_t *end, const int8_t *strand);
+
+/* Which sampler of the reference runs (dispatch at R/bootRanges.R:91-104 and
+ * R/bootUnsegmented.R:15-40). */
+enum {
+    NRB200_UNSEG_ACROSS = 0,   /* unseg_bootstrap_across_chrom  R/bootUnsegmented.R:116-143 */
+    NRB200_UNSEG_WITHIN = 1,   /* unseg_bootstrap_within_chrom  R/bootUnsegmented.R:50-75   */
+    NRB200_SEG_PROP = 2,       /* seg_bootstrap_prop            R/bootRanges.R:179-253      */
+    NRB200_SEG_NOPROP = 3,     /* seg_bootstrap_noprop          R/bootRanges.R:256-331      */
+    NRB200_PERMUTE_WITHIN = 4, /* unseg_permute_within_chrom    R/bootUnsegmented.R:83-109  */
+    NRB200_PERMUTE_ACROSS = 5  /* unseg_permute_across_chrom    R/bootUnsegmented.R:150-165 */
+};
+
+typedef struct nrb200_plan_spec {
+    int32_t kind;            /* one of the enum above */
+    int64_t block_length;    /* blockLength (L_b) */
+    /* seg of bootRanges(..., seg): ranges(seg), seqnames(seg), seg$state (>= 1). */
+    int64_t n_seg;
+    const int32_t *seg_seqid;
+    const int32_t *seg_start;
+    const int32_t *seg_end;
+    const int32_t *seg_state;
+} nrb200_plan_spec;
+
+/* Builds the iteration-invariant block tables: the tiles blocks are moved TO
+ * (tileGenome / successiveIRanges / seq(by = L_bs)) and the bait width of each block.
+ * Requires nrb200_set_ranges() first (it needs seqlengths).  Block order: unsegmented =
+ * seqlevel-major; segmented = state 1..S, then segments of that state in `seg` order,
+ * then tiles left to right -- the order the reference concatenates them in. */
+int nrb200_set_plan(nrb200_handle *h, const nrb200_plan_spec *spec, int64_t *n_blocks);
+
+/* Copies out the block tables ([n_blocks] each; any pointer may be NULL). */
+int nrb200_get_tiles(const nrb200_handle *h, int32_t *tile_seqid, int32_t *tile_start,
+                     int32_t *bait_width);
+
+/* ---- block draws ------------------------------------------------------------------- */
+
+#define NRB200_RNG_HOST 0   /* validation mode: the caller drew the blocks (R: sample()/runif()
+                               under set.seed, in the order of R/bootUnsegmented.R:122-124,
+                               :60, R/bootRanges.R:202-209, :263-267, :296) */
+#define NRB200_RNG_PHILOX 1 /* production mode: Philox4x32-10 on the device, counter =
+                               (global iteration, block), key = seed */
+
+typedef struct nrb200_draws {
+    int64_t n_iter;            /* R */
+    int64_t iter0;             /* global index of the first iteration (multi-GPU shards) */
+    int32_t rng_mode;
+    uint64_t seed;             /* NRB200_RNG_PHILOX */
+    /* NRB200_RNG_HOST, [n_iter x n_blocks] row-major: */
+    const int32_t *bait_seqid; /* seqname id the block is sampled FROM */
+    const int32_t *bait_start; /* its start */
+    const int32_t *dst_tile;   /* permute kinds: tile index the block moves TO; else NULL */
+} nrb200_draws;
+
+typedef struct nrb200_stats {
+    double kernel_ms;      /* device time of the bootstrap kernels (CUDA events) */
+    double total_ms;       /* device time incl. uploads, memsets and result copies */
+    int64_t n_launches;    /* kernels launched by the call */
+    int64_t n_hits;        /* sum over iterations of ranges sampled (H of the byte model) */
+    int64_t h2d_bytes;
+    int64_t d2h_bytes;
+} nrb200_stats;
+
+/* ---- fused path: bootstrap -> countOverlaps, the R x N table is never built -------- */
+
+/* Replaces, per iteration, the body of replicate() at R/bootRanges.R:90-118
+ * (sampler + findOverlaps + shift_and_swap_chrom + exclude drop) AND the user-side
+ * countOverlaps / group_by(x_id, iter) of vignettes/bootRanges.Rmd:497-503.
+ * Outputs (host, any may be NULL):
+ *   iter_nranges   [n_iter]          rows the reference's BootRanges would hold for iter r
+ *   iter_totals    [n_iter]          sum over features of the overlap counts
+ *   feature_counts [n_iter x n_query] countOverlaps(x, boots[iter == r]) in the caller's
+ *                                     query order */
+int nrb200_run_counts(nrb200_handle *h, const nrb200_draws *draws, int64_t *iter_nranges,
+                      int64_t *iter_totals, int32_t *feature_counts, nrb200_stats *stats);
+
+/* Same computation, results left in device memory owned by the handle (valid until the next
+ * run or destroy).  want_feature_counts = 0 skips the [n_iter x n_query] matrix. */
+int nrb200_run_counts_resident(nrb200_handle *h, const nrb200_draws *draws,
+                               int32_t want_feature_counts, nrb200_stats *stats);
+int nrb200_resident_pointers(const nrb200_handle *h, void **iter_nranges_dev,
+                             void **iter_totals_dev, void **feature_counts_dev);
+
+/* Per-feature bootstrap moments without the n_iter x n_query matrix (BASELINE config 4):
+ * sum_r c[r,g], sum_r c[r,g]^2, and #{r : c[r,g] >= observed[g]} (observed may be NULL).
+ * Accumulates over calls until nrb200_moments_reset(). Iterations are processed in batches
+ * of `batch_iter` (0 = pick). */
+int nrb200_moments_reset(nrb200_handle *h);
+int nrb200_run_moments(nrb200_handle *h, const nrb200_draws *draws, int64_t batch_iter,
+                       const int32_t *observed, int64_t *iter_nranges, int64_t *iter_totals,
+                       nrb200_stats *stats);
+int nrb200_moments_fetch(nrb200_handle *h, int64_t *feat_sum, int64_t *feat_sumsq,
+                         int64_t *feat_n_ge_observed);
+
+/* countOverlaps(x, y) on the ORIGINAL ranges (the observed statistic,
+ * vignettes/bootRanges.Rmd:482-483). */
+int nrb200_count_observed(nrb200_handle *h, int32_t *feature_counts, int64_t *total);
+
+/* ---- materialising path: the literal BootRanges table ------------------------------ */
+
+/* Phase 1: runs the bootstrap, keeps the rows on the device, returns iter_offsets
+ * [n_iter + 1] (rows of iteration r are [iter_offsets[r], iter_offsets[r+1]) -- this is
+ * `lens`/`iter` of R/bootRanges.R:120-122).  Rows are ordered (iter, block, canonical y
+ * order). */
+int nrb200_run_materialize(nrb200_handle *h, const nrb200_draws *draws, int64_t *iter_offsets,
+                           nrb200_stats *stats);
+/* Phase 2: copies rows [row0, row0 + n) to the caller.  src_idx is the 0-based index into
+ * the caller's y (gather strand(y)/mcols(y) with it); block is the 0-based block index
+ * (the reference's internal `block` column, R/bootRanges.R:126). Pointers may be NULL. */
+int nrb200_fetch_rows(nrb200_handle *h, int64_t row0, int64_t n, int32_t *seqid,
+                      int32_t *start, int32_t *end, int32_t *src_idx, int32_t *block);
+
+/* ---- base-R RNG for hosts that are not R ------------------------------------------- */
+/* In R the wrapper draws blocks with R's own sample()/runif().  A non-R host (the Python
+ * mirror) needs the same stream under set.seed(): Mersenne-Twister / Inversion / Rejection,
+ * R >= 3.6 defaults. */
+typedef struct nrb200_rrng nrb200_rrng;
+nrb200_rrng *nrb200_rrng_create(uint32_t seed);                 /* set.seed(seed) */
+void nrb200_rrng_destroy(nrb200_rrng *g);
+double nrb200_rrng_unif_rand(nrb200_rrng *g);
+/* runif(n, min, max) with recycled bounds; min == max consumes no draw. */
+int nrb200_rrng_runif(nrb200_rrng *g, int64_t n, const double *min, int64_t n_min,
+                      const double *max, int64_t n_max, double *out);
+/* sample.int(n, size, replace, prob): 1-based results. prob may be NULL. Weighted sampling
+ * without replacement is not used by the reference path and returns NRB200_ERR_UNSUPPORTED. */
+int nrb200_rrng_sample(nrb200_rrng *g, int32_t n, int64_t size, int32_t replace,
+                       const double *prob, int32_t *out);
+double nrb200_r_round(double x); /* round(x): half to even */
+
+#if defined(__GNUC__)
+#pragma GCC visibility pop
+#endif
+#ifdef __cplusplus
+}
+#endif
+#endif /* NRB200_H */

@@ -1,0 +1,171 @@
+"""bootRanges(): the reference's front end (R/bootRanges.R:72-128), served by the B200 engine.
+
+Same arguments, same checks, same result columns.  New, default-off arguments:
+``rng`` ("R" = draw blocks on R's stream under set_seed(), bit-comparable with the
+reference; "philox" = draw on the GPU), ``seed``/``iter0`` for Philox, ``device``.
+``bootCounts()`` is the fused path: bootstrap and countOverlaps(x, boots) per iteration
+without ever building the R x N table (vignettes/bootRanges.Rmd:497-503).
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+
+import numpy as np
+
+from . import _lib, samplers
+from .engine import Draws, Engine, get_engine
+from .granges import BootRanges, GRanges
+from .rrng import RRng, global_rng
+
+
+def _match_arg(value, choices, name):
+    if isinstance(value, (tuple, list)):  # R's match.arg(): the default is the first choice
+        value = value[0]
+    if value not in choices:
+        raise ValueError(f"'{name}' should be one of {', '.join(repr(c) for c in choices)}")
+    return value
+
+
+def _plan_kind(seg, proportionLength, type_, withinChrom):
+    if seg is not None:  # type / withinChrom are ignored when seg is given (R/bootRanges.R:91-98)
+        return _lib.SEG_PROP if proportionLength else _lib.SEG_NOPROP
+    if type_ == "bootstrap":
+        return _lib.UNSEG_WITHIN if withinChrom else _lib.UNSEG_ACROSS
+    return _lib.PERMUTE_WITHIN if withinChrom else _lib.PERMUTE_ACROSS
+
+
+def _seg_arrays(seg: GRanges, y: GRanges):
+    if "state" not in seg.mcols:
+        raise ValueError('"state" %in% names(mcols(seg)) is not TRUE')  # R/bootRanges.R:87
+    state = np.asarray(seg.mcols["state"])
+    if not np.all(state == np.round(state)):
+        raise ValueError("seg$state must be integer valued")
+    lut = {s: i for i, s in enumerate(y.seqlevels)}
+    try:
+        seqid = np.array([lut[s] for s in seg.seqnames.tolist()], dtype=np.int32)
+    except KeyError as e:  # factor(levels = seqlevels(y)) would give NA (R/bootRanges.R:161-163)
+        raise ValueError(f"seqnames(seg) {e} not in seqlevels(y)") from None
+    return {"seqid": seqid, "start": seg.start, "end": seg.end, "state": state.astype(np.int32)}
+
+
+def _side_arrays(x: GRanges, y: GRanges, what: str):
+    lut = {s: i for i, s in enumerate(y.seqlevels)}
+    ids = np.array([lut.get(s, -1) for s in x.seqlevels], dtype=np.int32)[x.seqid]
+    keep = ids >= 0  # ranges on sequences y does not have can never be hit
+    return ids[keep], x.start[keep], x.end[keep], x.strand[keep], np.flatnonzero(keep)
+
+
+def _draw_host(kind, rng: RRng, R: int, y: GRanges, L_b: int, seg, eng: Engine):
+    L_s = y.seqlengths.astype(np.float64)
+    tile_seq, tile_start, _ = eng.tiles()
+    out = []
+    for _ in range(R):
+        if kind == _lib.UNSEG_ACROSS:
+            d = samplers.unseg_bootstrap_across_chrom(rng, L_s, L_b)
+        elif kind == _lib.UNSEG_WITHIN:
+            d = samplers.unseg_bootstrap_within_chrom(rng, L_s, L_b)
+        elif kind == _lib.PERMUTE_WITHIN:
+            d = samplers.unseg_permute_within_chrom(rng, L_s, L_b, tile_start)
+        elif kind == _lib.PERMUTE_ACROSS:
+            d = samplers.unseg_permute_across_chrom(rng, tile_seq, tile_start)
+        elif kind == _lib.SEG_PROP:
+            d = samplers.seg_bootstrap_prop(rng, seg["seqid"], seg["start"], seg["end"], seg["state"], L_b, L_s)
+        else:
+            d = samplers.seg_bootstrap_noprop(rng, seg["seqid"], seg["start"], seg["end"], seg["state"], L_b)
+        out.append(d)
+    bait_seq = np.stack([d[0] for d in out]) if R else np.empty((0, eng.n_blocks), np.int32)
+    bait_start = np.stack([d[1] for d in out]) if R else np.empty((0, eng.n_blocks), np.int32)
+    dst = np.stack([d[2] for d in out]) if (R and out[0][2] is not None) else None
+    return bait_seq, bait_start, dst
+
+
+def _setup(y: GRanges, blockLength, seg, exclude, excludeOption, proportionLength, type_, withinChrom, device):
+    chr_lens = y.seqlengths
+    if np.any(chr_lens < 0):
+        raise ValueError("all(!is.na(chr_lens)) is not TRUE")  # R/bootRanges.R:81
+    excludeOption = _match_arg(excludeOption, ("drop", "trim"), "excludeOption")
+    type_ = _match_arg(type_, ("bootstrap", "permute"), "type")
+    if excludeOption == "trim":
+        if exclude is None:
+            raise ValueError("excludeOption='trim' needs exclude")  # strand(NULL) errors in the reference (:84)
+        if np.any(exclude.strand != 0):
+            raise ValueError('all(strand(exclude) == "*") is not TRUE')
+        raise NotImplementedError("excludeOption='trim' is not on the device yet (SURVEY 8f rank 2)")
+    if float(blockLength) != int(blockLength):
+        raise ValueError("blockLength must be integer valued")
+    L_b = int(blockLength)
+    kind = _plan_kind(seg, proportionLength, type_, withinChrom)
+    if kind in (_lib.UNSEG_ACROSS, _lib.PERMUTE_ACROSS) and not y.is_sorted():
+        raise ValueError("all(y == GenomicRanges::sort(y)) is not TRUE")  # R/bootUnsegmented.R:31
+    segd = _seg_arrays(seg, y) if seg is not None else None
+    eng = get_engine(device)
+    eng.set_ranges(chr_lens, y.seqid, y.start, y.end, y.strand if np.any(y.strand) else None)
+    if exclude is not None:
+        xi, xs, xe, xstr, _ = _side_arrays(exclude, y, "exclude")
+        eng.set_exclude(xi, xs, xe, xstr if np.any(xstr) else None)
+    else:
+        eng.clear_exclude()
+    eng.set_plan(kind, L_b, segd)
+    return eng, kind, L_b, segd
+
+
+def _make_draws(eng, kind, R, y, L_b, segd, rng, seed, iter0):
+    rng = _match_arg(rng, ("R", "philox"), "rng")
+    if rng == "philox":
+        return Draws(n_iter=R, rng_mode=_lib.RNG_PHILOX, seed=int(seed or 0), iter0=int(iter0))
+    stream = global_rng() if seed is None else RRng(seed)
+    bs, bt, dt = _draw_host(kind, stream, R, y, L_b, segd, eng)
+    return Draws(n_iter=R, rng_mode=_lib.RNG_HOST, bait_seqid=bs, bait_start=bt, dst_tile=dt)
+
+
+def bootRanges(y: GRanges, blockLength, R: int = 1, seg: GRanges | None = None, exclude: GRanges | None = None,
+               excludeOption=("drop", "trim"), proportionLength: bool = True, type=("bootstrap", "permute"),
+               withinChrom: bool = False, storeBlockLength: bool = False, *, rng="R", seed=None, iter0: int = 0,
+               storeBlockStart: bool = False, device: int = 0) -> BootRanges:
+    """Block bootstrap of genomic ranges; returns all iterations concatenated with an ``iter`` column."""
+    eng, kind, L_b, segd = _setup(y, blockLength, seg, exclude, excludeOption, proportionLength, type, withinChrom, device)
+    draws = _make_draws(eng, kind, int(R), y, L_b, segd, rng, seed, iter0)
+    rows = eng.run_materialize(draws)
+    src = rows["src"]
+    lens = np.diff(rows["iter_offsets"])
+    br = object.__new__(BootRanges)
+    br.seqlevels, br.seqlengths = y.seqlevels, y.seqlengths
+    br.seqid, br.start, br.end = rows["seqid"], rows["start"], rows["end"]
+    br.strand = y.strand[src]
+    br.mcols = {k: v[src] for k, v in y.mcols.items() if k != "block"}
+    # mcols(br)$iter <- Rle(factor(rep(seq_len(R), lens), levels = seq_len(R)))   R/bootRanges.R:122
+    br.mcols["iter"] = np.repeat(np.arange(1, int(R) + 1, dtype=np.int32), lens)
+    if storeBlockLength:
+        br.mcols["blockLength"] = np.full(src.size, L_b, dtype=np.int32)  # :123-125
+    if storeBlockStart:
+        _, tile_start, _ = eng.tiles()
+        dst = rows["block"] if draws.dst_tile is None else draws.dst_tile[br.mcols["iter"] - 1, rows["block"]]
+        br.mcols["blockStart"] = tile_start[dst]
+    return br
+
+
+@dataclass
+class BootCounts:
+    """Per-iteration results of the fused bootstrap -> countOverlaps path."""
+    iter_totals: np.ndarray            # [R] sum over features of the overlap counts
+    iter_nranges: np.ndarray           # [R] length of the iteration's bootstrap sample
+    feature_counts: np.ndarray | None  # [R, length(x)] countOverlaps(x, boots[iter == r])
+    stats: dict
+
+
+def bootCounts(y: GRanges, x: GRanges, blockLength, R: int = 1, seg: GRanges | None = None,
+               exclude: GRanges | None = None, excludeOption=("drop", "trim"), proportionLength: bool = True,
+               type=("bootstrap", "permute"), withinChrom: bool = False, *, rng="philox", seed=None, iter0: int = 0,
+               perFeature: bool = True, device: int = 0) -> BootCounts:
+    """countOverlaps(x, bootRanges(y, ...)) per iteration, fused on the GPU."""
+    eng, kind, L_b, segd = _setup(y, blockLength, seg, exclude, excludeOption, proportionLength, type, withinChrom, device)
+    qi, qs, qe, qstr, qkeep = _side_arrays(x, y, "x")
+    eng.set_query(qi, qs, qe, qstr if np.any(qstr) else None)
+    draws = _make_draws(eng, kind, int(R), y, L_b, segd, rng, seed, iter0)
+    res = eng.run_counts(draws, want_counts=perFeature)
+    fc = res["feature_counts"]
+    if fc is not None and qkeep.size != len(x):  # features on sequences y lacks count 0
+        full = np.zeros((int(R), len(x)), np.int32)
+        full[:, qkeep] = fc
+        fc = full
+    return BootCounts(res["iter_totals"], res["iter_nranges"], fc, res["stats"])

@@ -1,0 +1,772 @@
+// libnrb200: host side of the C ABI (include/nrb200.h) and the kernel launches.
+//
+// Memory layout in HBM (all int32 unless noted, canonical = sorted by (seqname, start, end)):
+//   y        : start[N] end[N] pmax[N] src[N] (+ strand[N] int8 when stranded), seq_off[C+1],
+//              two direct-address rank tables (start, running-max end), ~N/4 entries each
+//   query    : start[G] end[G] pmax[G] src[G] (+strand) + per-tile window lo/hi [B]
+//   exclude  : same shape as query
+//   plan     : tile_seq[B] tile_start[B] bait_width[B], sampler tables (int64, a few KB)
+//   draws    : validation mode only, bait_seq/bait_start(/dst_tile) [R x B]
+//   results  : iter_nranges[R] iter_totals[R] (uint64), counts[R x G]
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <numeric>
+#include <string>
+#include <vector>
+
+#include "../../include/nrb200.h"
+#include "kernels.cuh"
+#include "plan.h"
+
+namespace nrb {
+
+static thread_local std::string g_create_error;
+
+// Growth-only device buffer.
+struct DevMem {
+    void *p = nullptr;
+    size_t cap = 0;
+    ~DevMem() { release(); }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+    cudaError_t reserve(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        release();
+        cudaError_t e = cudaMalloc(&p, bytes ? bytes : 1);
+        if (e == cudaSuccess) cap = bytes;
+        return e;
+    }
+    template <class T> T *as() const { return static_cast<T *>(p); }
+};
+
+// One set of ranges in canonical order, host mirror + device copy.
+struct RangeSet {
+    int64_t n = 0;
+    bool stranded = false;
+    int32_t wmax = 0;
+    std::vector<int32_t> h_start, h_end, h_pmax, h_src, h_seq_off;  // host mirror (kept for query/exclude)
+    std::vector<int8_t> h_strand;
+    DevMem start, end, pmax, src, strand, seq_off, seqid;
+};
+
+}  // namespace nrb
+
+using namespace nrb;
+
+struct nrb200_handle {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    std::string error;
+    int sm_count = 148;
+
+    int n_seq = 0;
+    std::vector<int64_t> seqlen;
+    DevMem seqlen_dev;
+
+    RangeSet y, query, excl;
+    bool have_y = false, have_plan = false;
+    // rank tables of y
+    int rank_shift = 0;
+    std::vector<int64_t> rank_off;
+    DevMem rank_off_dev, max_pos_dev, rank_start, rank_pmax;
+
+    Plan plan;
+    DevMem tile_seq, tile_start, bait_width, sampler_i64, sampler_i32;
+    SamplerView sampler_view{};
+    bool slices_dirty = true;
+    DevMem q_tile_lo, q_tile_hi, x_tile_lo, x_tile_hi;
+
+    // run scratch / results
+    DevMem d_bait_seq, d_bait_start, d_dst_tile;
+    DevMem d_iter_nranges, d_iter_totals, d_counts, d_n_hits;
+    int64_t res_iter = 0;
+    bool res_has_counts = false;
+    // moments
+    DevMem m_sum, m_sumsq, m_nge, m_observed;
+    bool moments_ready = false;
+    // rows
+    DevMem item_rows, within_off, iter_off_dev, row_seq, row_start, row_end, row_src, row_block;
+    int64_t n_rows = 0;
+};
+
+namespace {
+
+int fail(nrb200_handle *h, int code, const std::string &msg) {
+    if (h) h->error = msg; else g_create_error = msg;
+    return code;
+}
+
+#define NRB_CUDA(h, call)                                                                          \
+    do {                                                                                           \
+        cudaError_t err__ = (call);                                                                \
+        if (err__ != cudaSuccess)                                                                  \
+            return fail((h), NRB200_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(err__)); \
+    } while (0)
+
+template <class T>
+int upload(nrb200_handle *h, DevMem &dst, const T *src, size_t n) {
+    NRB_CUDA(h, dst.reserve(n * sizeof(T)));
+    if (n) NRB_CUDA(h, cudaMemcpyAsync(dst.p, src, n * sizeof(T), cudaMemcpyHostToDevice, h->stream));
+    return NRB200_OK;
+}
+
+// Canonicalise one set of ranges on the host and mirror it to the device.
+int load_range_set(nrb200_handle *h, RangeSet &rs, const char *what, int64_t n, const int32_t *seqid,
+                   const int32_t *start, const int32_t *end, const int8_t *strand, bool keep_seqid_dev) {
+    if (n < 0 || n > (int64_t)INT32_MAX - 64) return fail(h, NRB200_ERR_INVALID, std::string(what) + ": length out of range");
+    if (n > 0 && (!seqid || !start || !end)) return fail(h, NRB200_ERR_INVALID, std::string(what) + ": null coordinate pointer");
+    const int C = h->n_seq;
+    bool sorted = true, stranded = false;
+    int32_t wmax = 0;
+    for (int64_t i = 0; i < n; ++i) {
+        if (seqid[i] < 0 || seqid[i] >= C) return fail(h, NRB200_ERR_INVALID, std::string(what) + ": seqname not in seqlevels(y)");
+        if (start[i] < 1) return fail(h, NRB200_ERR_UNSUPPORTED, std::string(what) + ": ranges must start at position >= 1");
+        if (end[i] < start[i]) return fail(h, NRB200_ERR_UNSUPPORTED, std::string(what) + ": zero-width ranges are not supported");
+        if (end[i] >= (1 << 30)) return fail(h, NRB200_ERR_UNSUPPORTED, std::string(what) + ": coordinates must be below 2^30");
+        if (strand) {
+            if (strand[i] < 0 || strand[i] > 2) return fail(h, NRB200_ERR_INVALID, std::string(what) + ": strand codes are 0 '*', 1 '+', 2 '-'");
+            stranded |= strand[i] != 0;
+        }
+        wmax = std::max(wmax, end[i] - start[i] + 1);
+        if (i > 0) {
+            const int64_t j = i - 1;
+            if (seqid[i] < seqid[j] || (seqid[i] == seqid[j] && (start[i] < start[j] || (start[i] == start[j] && end[i] < end[j]))))
+                sorted = false;
+        }
+    }
+    rs.n = n;
+    rs.stranded = stranded;
+    rs.wmax = wmax;
+    rs.h_src.resize(n);
+    std::iota(rs.h_src.begin(), rs.h_src.end(), 0);
+    if (!sorted)
+        std::sort(rs.h_src.begin(), rs.h_src.end(), [&](int32_t a, int32_t b) {
+            if (seqid[a] != seqid[b]) return seqid[a] < seqid[b];
+            if (start[a] != start[b]) return start[a] < start[b];
+            if (end[a] != end[b]) return end[a] < end[b];
+            return a < b;
+        });
+    rs.h_start.resize(n);
+    rs.h_end.resize(n);
+    rs.h_pmax.resize(n);
+    rs.h_strand.clear();
+    if (stranded) rs.h_strand.resize(n);
+    rs.h_seq_off.assign(C + 1, 0);
+    std::vector<int32_t> h_seqid(keep_seqid_dev ? n : 0);
+    for (int64_t k = 0; k < n; ++k) {
+        const int32_t i = rs.h_src[k];
+        rs.h_start[k] = start[i];
+        rs.h_end[k] = end[i];
+        if (stranded) rs.h_strand[k] = strand[i];
+        if (keep_seqid_dev) h_seqid[k] = seqid[i];
+        rs.h_seq_off[seqid[i] + 1]++;
+    }
+    for (int c = 0; c < C; ++c) rs.h_seq_off[c + 1] += rs.h_seq_off[c];
+    for (int c = 0; c < C; ++c) {
+        int32_t m = INT32_MIN;
+        for (int32_t k = rs.h_seq_off[c]; k < rs.h_seq_off[c + 1]; ++k) {
+            m = std::max(m, rs.h_end[k]);
+            rs.h_pmax[k] = m;
+        }
+    }
+    int rc;
+    if ((rc = upload(h, rs.start, rs.h_start.data(), n))) return rc;
+    if ((rc = upload(h, rs.end, rs.h_end.data(), n))) return rc;
+    if ((rc = upload(h, rs.pmax, rs.h_pmax.data(), n))) return rc;
+    if ((rc = upload(h, rs.src, rs.h_src.data(), n))) return rc;
+    if ((rc = upload(h, rs.seq_off, rs.h_seq_off.data(), (size_t)C + 1))) return rc;
+    if (stranded && (rc = upload(h, rs.strand, rs.h_strand.data(), n))) return rc;
+    if (keep_seqid_dev && (rc = upload(h, rs.seqid, h_seqid.data(), n))) return rc;
+    NRB_CUDA(h, cudaStreamSynchronize(h->stream));  // host vectors above may go out of scope
+    return NRB200_OK;
+}
+
+int build_rank_tables(nrb200_handle *h) {
+    const int C = h->n_seq;
+    RangeSet &y = h->y;
+    // ~4 ranges per bucket on average keeps both tables near N entries in total.
+    int64_t genome = 0;
+    std::vector<int32_t> max_pos(C);
+    for (int c = 0; c < C; ++c) {
+        int64_t m = h->seqlen[c];
+        if (y.h_seq_off[c + 1] > y.h_seq_off[c]) m = std::max<int64_t>(m, y.h_pmax[y.h_seq_off[c + 1] - 1]);
+        max_pos[c] = (int32_t)std::min<int64_t>(m, INT32_MAX - 1);
+        genome += max_pos[c];
+    }
+    int shift = 0;
+    const int64_t want = std::max<int64_t>(y.n / 4, 1024);
+    while (shift < 30 && (genome >> shift) > want) ++shift;
+    h->rank_shift = shift;
+    h->rank_off.assign(C + 1, 0);
+    for (int c = 0; c < C; ++c) h->rank_off[c + 1] = h->rank_off[c] + ((int64_t)max_pos[c] >> shift) + 2;
+    const int64_t entries = h->rank_off[C];
+    int rc;
+    if ((rc = upload(h, h->rank_off_dev, h->rank_off.data(), (size_t)C + 1))) return rc;
+    if ((rc = upload(h, h->max_pos_dev, max_pos.data(), (size_t)C))) return rc;
+    NRB_CUDA(h, h->rank_start.reserve(entries * sizeof(int32_t)));
+    NRB_CUDA(h, h->rank_pmax.reserve(entries * sizeof(int32_t)));
+    const int threads = 256;
+    const unsigned grid = (unsigned)((entries + threads - 1) / threads);
+    build_rank_table_kernel<<<grid, threads, 0, h->stream>>>(y.start.as<int32_t>(), y.seq_off.as<int32_t>(),
+                                                             h->rank_off_dev.as<int64_t>(), C, shift, h->rank_start.as<int32_t>());
+    build_rank_table_kernel<<<grid, threads, 0, h->stream>>>(y.pmax.as<int32_t>(), y.seq_off.as<int32_t>(),
+                                                             h->rank_off_dev.as<int64_t>(), C, shift, h->rank_pmax.as<int32_t>());
+    NRB_CUDA(h, cudaGetLastError());
+    NRB_CUDA(h, cudaStreamSynchronize(h->stream));
+    return NRB200_OK;
+}
+
+// Per-tile candidate window of a query/exclude set: everything that can overlap a range
+// landing on the tile.  A shifted range overlaps [tile_start, tile_start + width - 1] before
+// trimming, so it lies within (wmax - 1) of it on either side.
+int build_slices(nrb200_handle *h, const RangeSet &rs, DevMem &lo_dev, DevMem &hi_dev) {
+    const Plan &p = h->plan;
+    const int64_t B = p.n_blocks();
+    std::vector<int32_t> lo(B), hi(B);
+    const int64_t reach = std::max<int32_t>(h->y.wmax, 1) - 1;
+    for (int64_t t = 0; t < B; ++t) {
+        const int c = p.tile_seq[t];
+        const int64_t r_lo = (int64_t)p.tile_start[t] - reach;
+        const int64_t r_hi = (int64_t)p.tile_start[t] + p.bait_width[t] - 1 + reach;
+        const int32_t *sb = rs.h_start.data() + rs.h_seq_off[c], *se = rs.h_start.data() + rs.h_seq_off[c + 1];
+        const int32_t *pb = rs.h_pmax.data() + rs.h_seq_off[c], *pe = rs.h_pmax.data() + rs.h_seq_off[c + 1];
+        int32_t a = (int32_t)(std::lower_bound(pb, pe, r_lo, [](int32_t v, int64_t key) { return (int64_t)v < key; }) - rs.h_pmax.data());
+        int32_t b = (int32_t)(std::upper_bound(sb, se, r_hi, [](int64_t key, int32_t v) { return key < (int64_t)v; }) - rs.h_start.data());
+        if (a > b) a = b;
+        lo[t] = a;
+        hi[t] = b;
+    }
+    int rc;
+    if ((rc = upload(h, lo_dev, lo.data(), (size_t)B))) return rc;
+    if ((rc = upload(h, hi_dev, hi.data(), (size_t)B))) return rc;
+    NRB_CUDA(h, cudaStreamSynchronize(h->stream));
+    return NRB200_OK;
+}
+
+int prepare(nrb200_handle *h) {
+    if (!h->have_y) return fail(h, NRB200_ERR_STATE, "nrb200_set_ranges() has not been called");
+    if (!h->have_plan) return fail(h, NRB200_ERR_STATE, "nrb200_set_plan() has not been called");
+    if (h->slices_dirty) {
+        int rc;
+        if (h->query.n && (rc = build_slices(h, h->query, h->q_tile_lo, h->q_tile_hi))) return rc;
+        if (h->excl.n && (rc = build_slices(h, h->excl, h->x_tile_lo, h->x_tile_hi))) return rc;
+        h->slices_dirty = false;
+    }
+    return NRB200_OK;
+}
+
+int stage_draws(nrb200_handle *h, const nrb200_draws *d) {
+    if (!d || d->n_iter < 0) return fail(h, NRB200_ERR_INVALID, "draws: n_iter must be >= 0");
+    const Plan &p = h->plan;
+    const int64_t B = p.n_blocks();
+    if (d->rng_mode == NRB200_RNG_PHILOX) {
+        if (p.kind != NRB200_UNSEG_ACROSS && p.kind != NRB200_UNSEG_WITHIN && p.kind != NRB200_SEG_PROP)
+            return fail(h, NRB200_ERR_UNSUPPORTED,
+                        "device Philox draws cover the unsegmented and proportionLength=TRUE bootstraps; "
+                        "draw this sampler on the host (NRB200_RNG_HOST)");
+        return NRB200_OK;
+    }
+    if (d->rng_mode != NRB200_RNG_HOST) return fail(h, NRB200_ERR_INVALID, "draws: unknown rng_mode");
+    const int64_t n = d->n_iter * B;
+    if (n > 0 && (!d->bait_seqid || !d->bait_start)) return fail(h, NRB200_ERR_INVALID, "draws: bait_seqid/bait_start are required in host mode");
+    if (p.permute() && n > 0 && !d->dst_tile) return fail(h, NRB200_ERR_INVALID, "draws: permute kinds need dst_tile");
+    for (int64_t i = 0; i < n; ++i) {
+        if (d->bait_seqid[i] < 0 || d->bait_seqid[i] >= h->n_seq) return fail(h, NRB200_ERR_INVALID, "draws: bait_seqid out of range");
+        if (d->bait_start[i] < 1 || d->bait_start[i] >= (1 << 30)) return fail(h, NRB200_ERR_INVALID, "draws: bait_start out of range");
+        if (d->dst_tile && (d->dst_tile[i] < 0 || d->dst_tile[i] >= B)) return fail(h, NRB200_ERR_INVALID, "draws: dst_tile out of range");
+    }
+    int rc;
+    if ((rc = upload(h, h->d_bait_seq, d->bait_seqid, (size_t)n))) return rc;
+    if ((rc = upload(h, h->d_bait_start, d->bait_start, (size_t)n))) return rc;
+    if (d->dst_tile && (rc = upload(h, h->d_dst_tile, d->dst_tile, (size_t)n))) return rc;
+    return NRB200_OK;
+}
+
+BootParams make_params(nrb200_handle *h, const nrb200_draws *d) {
+    BootParams P{};
+    const RangeSet &y = h->y;
+    P.y = RangesView{y.start.as<int32_t>(), y.end.as<int32_t>(), y.pmax.as<int32_t>(),
+                     y.stranded ? y.strand.as<int8_t>() : nullptr, y.src.as<int32_t>(), y.seq_off.as<int32_t>(),
+                     h->rank_start.as<int32_t>(), h->rank_pmax.as<int32_t>(), h->rank_off_dev.as<int64_t>(),
+                     h->max_pos_dev.as<int32_t>(), h->rank_shift};
+    const RangeSet &q = h->query, &x = h->excl;
+    P.query = SliceView{q.start.as<int32_t>(), q.end.as<int32_t>(), q.stranded ? q.strand.as<int8_t>() : nullptr,
+                        q.src.as<int32_t>(), h->q_tile_lo.as<int32_t>(), h->q_tile_hi.as<int32_t>()};
+    P.excl = SliceView{x.start.as<int32_t>(), x.end.as<int32_t>(), x.stranded ? x.strand.as<int8_t>() : nullptr,
+                       x.src.as<int32_t>(), h->x_tile_lo.as<int32_t>(), h->x_tile_hi.as<int32_t>()};
+    P.sampler = h->sampler_view;
+    P.n_blocks = h->plan.n_blocks();
+    P.tile_seq = h->tile_seq.as<int32_t>();
+    P.tile_start = h->tile_start.as<int32_t>();
+    P.bait_width = h->bait_width.as<int32_t>();
+    P.seqlen = h->seqlen_dev.as<int64_t>();
+    P.permute = h->plan.permute();
+    P.drop_zero = h->plan.drop_zero_width();
+    P.rng_mode = d->rng_mode;
+    P.seed = d->seed;
+    P.iter0 = d->iter0;
+    if (d->rng_mode == NRB200_RNG_HOST) {
+        P.bait_seq = h->d_bait_seq.as<int32_t>();
+        P.bait_start = h->d_bait_start.as<int32_t>();
+        P.dst_tile = d->dst_tile ? h->d_dst_tile.as<int32_t>() : nullptr;
+    }
+    P.n_iter = d->n_iter;
+    P.n_query = q.n;
+    return P;
+}
+
+template <bool ST, bool HQ, bool HX>
+void launch_count_t(nrb200_handle *h, const BootParams &P, unsigned grid) {
+    boot_count_kernel<ST, HQ, HX><<<grid, 256, 0, h->stream>>>(P);
+}
+
+void launch_count(nrb200_handle *h, const BootParams &P, bool has_query) {
+    const int64_t items = P.n_iter * P.n_blocks;
+    if (items == 0) return;
+    const int64_t ctas = (items + 7) / 8;
+    const unsigned grid = (unsigned)std::min<int64_t>(ctas, (int64_t)h->sm_count * 64);
+    const bool st = h->y.stranded && ((has_query && h->query.stranded) || (h->excl.n && h->excl.stranded));
+    const bool hx = h->excl.n > 0;
+    const int key = (st ? 4 : 0) | (has_query ? 2 : 0) | (hx ? 1 : 0);
+    switch (key) {
+    case 0: launch_count_t<false, false, false>(h, P, grid); break;
+    case 1: launch_count_t<false, false, true>(h, P, grid); break;
+    case 2: launch_count_t<false, true, false>(h, P, grid); break;
+    case 3: launch_count_t<false, true, true>(h, P, grid); break;
+    case 4: launch_count_t<true, false, false>(h, P, grid); break;
+    case 5: launch_count_t<true, false, true>(h, P, grid); break;
+    case 6: launch_count_t<true, true, false>(h, P, grid); break;
+    default: launch_count_t<true, true, true>(h, P, grid); break;
+    }
+}
+
+// Core of every counting entry point: results stay on the device.
+int run_counts_core(nrb200_handle *h, const nrb200_draws *d, bool want_counts, int32_t *counts_dev_override,
+                    nrb200_stats *stats) {
+    int rc;
+    if ((rc = prepare(h))) return rc;
+    NRB_CUDA(h, cudaEventRecord(h->ev[0], h->stream));
+    if ((rc = stage_draws(h, d))) return rc;
+    const int64_t R = d->n_iter, G = h->query.n;
+    const bool has_query = G > 0;
+    want_counts = want_counts && has_query;
+    NRB_CUDA(h, h->d_iter_nranges.reserve(std::max<int64_t>(R, 1) * 8));
+    NRB_CUDA(h, h->d_iter_totals.reserve(std::max<int64_t>(R, 1) * 8));
+    NRB_CUDA(h, h->d_n_hits.reserve(8));
+    NRB_CUDA(h, cudaMemsetAsync(h->d_iter_nranges.p, 0, R * 8, h->stream));
+    NRB_CUDA(h, cudaMemsetAsync(h->d_iter_totals.p, 0, R * 8, h->stream));
+    NRB_CUDA(h, cudaMemsetAsync(h->d_n_hits.p, 0, 8, h->stream));
+    int32_t *counts = nullptr;
+    if (want_counts) {
+        if (counts_dev_override) {
+            counts = counts_dev_override;
+        } else {
+            NRB_CUDA(h, h->d_counts.reserve((size_t)R * G * sizeof(int32_t)));
+            counts = h->d_counts.as<int32_t>();
+        }
+        NRB_CUDA(h, cudaMemsetAsync(counts, 0, (size_t)R * G * sizeof(int32_t), h->stream));
+    }
+    BootParams P = make_params(h, d);
+    P.iter_nranges = h->d_iter_nranges.as<unsigned long long>();
+    P.iter_totals = h->d_iter_totals.as<unsigned long long>();
+    P.counts = counts;
+    P.n_hits = h->d_n_hits.as<unsigned long long>();
+    NRB_CUDA(h, cudaEventRecord(h->ev[1], h->stream));
+    launch_count(h, P, has_query);
+    NRB_CUDA(h, cudaGetLastError());
+    NRB_CUDA(h, cudaEventRecord(h->ev[2], h->stream));
+    h->res_iter = R;
+    h->res_has_counts = want_counts && !counts_dev_override;
+    if (stats) {
+        NRB_CUDA(h, cudaEventSynchronize(h->ev[2]));
+        float k_ms = 0, t_ms = 0;
+        cudaEventElapsedTime(&k_ms, h->ev[1], h->ev[2]);
+        cudaEventElapsedTime(&t_ms, h->ev[0], h->ev[2]);
+        unsigned long long hits = 0;
+        NRB_CUDA(h, cudaMemcpyAsync(&hits, h->d_n_hits.p, 8, cudaMemcpyDeviceToHost, h->stream));
+        NRB_CUDA(h, cudaStreamSynchronize(h->stream));
+        std::memset(stats, 0, sizeof *stats);
+        stats->kernel_ms = k_ms;
+        stats->total_ms = t_ms;
+        stats->n_launches = (R * h->plan.n_blocks() > 0) ? 1 : 0;
+        stats->n_hits = (int64_t)hits;
+        stats->h2d_bytes = d->rng_mode == NRB200_RNG_HOST ? R * h->plan.n_blocks() * (d->dst_tile ? 12 : 8) : 0;
+    }
+    return NRB200_OK;
+}
+
+int fetch_u64_as_i64(nrb200_handle *h, const DevMem &src, int64_t n, int64_t *dst) {
+    if (!dst || n == 0) return NRB200_OK;
+    NRB_CUDA(h, cudaMemcpyAsync(dst, src.p, n * 8, cudaMemcpyDeviceToHost, h->stream));
+    return NRB200_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char *nrb200_version(void) { return "nrb200 0.1.0 (sm_100a)"; }
+
+const char *nrb200_last_error(const nrb200_handle *h) { return h ? h->error.c_str() : g_create_error.c_str(); }
+
+int nrb200_create(const nrb200_config *cfg, nrb200_handle **out) {
+    if (!out) return fail(nullptr, NRB200_ERR_INVALID, "nrb200_create: out is NULL");
+    *out = nullptr;
+    const int dev = cfg ? cfg->device : 0;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+        return fail(nullptr, NRB200_ERR_CUDA, std::string("no CUDA device: ") + cudaGetErrorString(e) +
+                                                 " (libnrb200 has no CPU path)");
+    if (dev < 0 || dev >= count) return fail(nullptr, NRB200_ERR_INVALID, "nrb200_create: device ordinal out of range");
+    NRB_CUDA(nullptr, cudaSetDevice(dev));
+    nrb200_handle *h = new nrb200_handle();
+    h->device = dev;
+    if (cfg && cfg->stream) {
+        h->stream = (cudaStream_t)cfg->stream;
+    } else {
+        e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
+        if (e != cudaSuccess) {
+            delete h;
+            return fail(nullptr, NRB200_ERR_CUDA, std::string("cudaStreamCreate: ") + cudaGetErrorString(e));
+        }
+        h->own_stream = true;
+    }
+    for (auto &ev : h->ev) cudaEventCreate(&ev);
+    cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, dev);
+    *out = h;
+    return NRB200_OK;
+}
+
+void nrb200_destroy(nrb200_handle *h) {
+    if (!h) return;
+    cudaSetDevice(h->device);
+    cudaStreamSynchronize(h->stream);
+    for (auto &ev : h->ev)
+        if (ev) cudaEventDestroy(ev);
+    if (h->own_stream) cudaStreamDestroy(h->stream);
+    delete h;
+}
+
+int nrb200_set_ranges(nrb200_handle *h, int64_t n, int32_t n_seq, const int64_t *seqlengths, const int32_t *seqid,
+                      const int32_t *start, const int32_t *end, const int8_t *strand) {
+    if (!h) return NRB200_ERR_INVALID;
+    NRB_CUDA(h, cudaSetDevice(h->device));
+    if (n_seq <= 0 || !seqlengths) return fail(h, NRB200_ERR_INVALID, "seqlengths(y) must be known");
+    for (int c = 0; c < n_seq; ++c) {
+        // stopifnot(all(!is.na(chr_lens)))                          R/bootRanges.R:81
+        if (seqlengths[c] <= 0) return fail(h, NRB200_ERR_INVALID, "all(!is.na(seqlengths(y))) is not TRUE");
+        if (seqlengths[c] >= (1 << 30)) return fail(h, NRB200_ERR_UNSUPPORTED, "seqlengths must be below 2^30");
+    }
+    h->have_y = h->have_plan = false;
+    h->query.n = h->excl.n = 0;  // seqlevels may have changed
+    h->n_seq = n_seq;
+    h->seqlen.assign(seqlengths, seqlengths + n_seq);
+    int rc;
+    if ((rc = upload(h, h->seqlen_dev, seqlengths, (size_t)n_seq))) return rc;
+    if ((rc = load_range_set(h, h->y, "y", n, seqid, start, end, strand, true))) return rc;
+    if ((rc = build_rank_tables(h))) return rc;
+    // the large host mirror of y is not needed again
+    std::vector<int32_t>().swap(h->y.h_start);
+    std::vector<int32_t>().swap(h->y.h_end);
+    std::vector<int32_t>().swap(h->y.h_pmax);
+    std::vector<int32_t>().swap(h->y.h_src);
+    std::vector<int8_t>().swap(h->y.h_strand);
+    h->have_y = true;
+    h->slices_dirty = true;
+    return NRB200_OK;
+}
+
+static int set_side(nrb200_handle *h, RangeSet &rs, const char *what, int64_t n, const int32_t *seqid,
+                    const int32_t *start, const int32_t *end, const int8_t *strand) {
+    if (!h) return NRB200_ERR_INVALID;
+    NRB_CUDA(h, cudaSetDevice(h->device));
+    if (!h->have_y) return fail(h, NRB200_ERR_STATE, "call nrb200_set_ranges() first (it defines the seqlevels)");
+    h->slices_dirty = true;
+    if (n == 0) {
+        rs.n = 0;
+        return NRB200_OK;
+    }
+    return load_range_set(h, rs, what, n, seqid, start, end, strand, false);
+}
+
+int nrb200_set_query(nrb200_handle *h, int64_t n, const int32_t *seqid, const int32_t *start, const int32_t *end,
+                     const int8_t *strand) {
+    return set_side(h, h->query, "query", n, seqid, start, end, strand);
+}
+
+int nrb200_set_exclude(nrb200_handle *h, int64_t n, const int32_t *seqid, const int32_t *start, const int32_t *end,
+                       const int8_t *strand) {
+    return set_side(h, h->excl, "exclude", n, seqid, start, end, strand);
+}
+
+int nrb200_set_plan(nrb200_handle *h, const nrb200_plan_spec *spec, int64_t *n_blocks) {
+    if (!h || !spec) return NRB200_ERR_INVALID;
+    NRB_CUDA(h, cudaSetDevice(h->device));
+    if (!h->have_y) return fail(h, NRB200_ERR_STATE, "call nrb200_set_ranges() first (the plan needs seqlengths)");
+    Plan p;
+    const std::string msg = build_plan(*spec, h->seqlen, p);
+    if (!msg.empty()) return fail(h, NRB200_ERR_INVALID, msg);
+    if (p.n_blocks() > (int64_t)INT32_MAX / 2) return fail(h, NRB200_ERR_UNSUPPORTED, "too many blocks per iteration");
+    h->plan = std::move(p);
+    const Plan &pl = h->plan;
+    const size_t B = (size_t)pl.n_blocks();
+    int rc;
+    if ((rc = upload(h, h->tile_seq, pl.tile_seq.data(), B))) return rc;
+    if ((rc = upload(h, h->tile_start, pl.tile_start.data(), B))) return rc;
+    if ((rc = upload(h, h->bait_width, pl.bait_width.data(), B))) return rc;
+    // sampler tables packed into one int64 and one int32 buffer
+    std::vector<int64_t> i64;
+    std::vector<int32_t> i32;
+    auto put64 = [&](const std::vector<int64_t> &v) { size_t o = i64.size(); i64.insert(i64.end(), v.begin(), v.end()); return o; };
+    auto put32 = [&](const std::vector<int32_t> &v) { size_t o = i32.size(); i32.insert(i32.end(), v.begin(), v.end()); return o; };
+    const size_t o_cum = put64(pl.seq_cum), o_tps = put64(pl.tiles_per_seq), o_sbo = put64(pl.state_block_off),
+                 o_sso = put64(pl.state_seg_off), o_sl = put64(pl.state_len), o_sbl = put64(pl.state_block_len),
+                 o_sgc = put64(pl.sg_cum);
+    const size_t o_sq = put32(pl.sg_seq), o_ss = put32(pl.sg_start), o_st = put32(pl.sg_tiles);
+    if ((rc = upload(h, h->sampler_i64, i64.data(), i64.size()))) return rc;
+    if ((rc = upload(h, h->sampler_i32, i32.data(), i32.size()))) return rc;
+    NRB_CUDA(h, cudaStreamSynchronize(h->stream));
+    const int64_t *b64 = h->sampler_i64.as<int64_t>();
+    const int32_t *b32 = h->sampler_i32.as<int32_t>();
+    h->sampler_view = SamplerView{pl.kind, pl.n_seq, pl.n_states, pl.block_length, pl.genome_length,
+                                  b64 + o_cum, b64 + o_tps, b64 + o_sbo, b64 + o_sso, b64 + o_sl, b64 + o_sbl,
+                                  b64 + o_sgc, b32 + o_sq, b32 + o_ss, b32 + o_st};
+    h->have_plan = true;
+    h->slices_dirty = true;
+    if (n_blocks) *n_blocks = pl.n_blocks();
+    return NRB200_OK;
+}
+
+int nrb200_get_tiles(const nrb200_handle *h, int32_t *tile_seqid, int32_t *tile_start, int32_t *bait_width) {
+    if (!h || !h->have_plan) return NRB200_ERR_STATE;
+    const size_t bytes = (size_t)h->plan.n_blocks() * sizeof(int32_t);
+    if (tile_seqid) std::memcpy(tile_seqid, h->plan.tile_seq.data(), bytes);
+    if (tile_start) std::memcpy(tile_start, h->plan.tile_start.data(), bytes);
+    if (bait_width) std::memcpy(bait_width, h->plan.bait_width.data(), bytes);
+    return NRB200_OK;
+}
+
+int nrb200_run_counts_resident(nrb200_handle *h, const nrb200_draws *draws, int32_t want_feature_counts,
+                               nrb200_stats *stats) {
+    if (!h) return NRB200_ERR_INVALID;
+    NRB_CUDA(h, cudaSetDevice(h->device));
+    return run_counts_core(h, draws, want_feature_counts != 0, nullptr, stats);
+}
+
+int nrb200_resident_pointers(const nrb200_handle *h, void **iter_nranges_dev, void **iter_totals_dev,
+                             void **feature_counts_dev) {
+    if (!h) return NRB200_ERR_INVALID;
+    if (iter_nranges_dev) *iter_nranges_dev = h->d_iter_nranges.p;
+    if (iter_totals_dev) *iter_totals_dev = h->d_iter_totals.p;
+    if (feature_counts_dev) *feature_counts_dev = h->res_has_counts ? h->d_counts.p : nullptr;
+    return NRB200_OK;
+}
+
+int nrb200_run_counts(nrb200_handle *h, const nrb200_draws *draws, int64_t *iter_nranges, int64_t *iter_totals,
+                      int32_t *feature_counts, nrb200_stats *stats) {
+    if (!h) return NRB200_ERR_INVALID;
+    NRB_CUDA(h, cudaSetDevice(h->device));
+    int rc = run_counts_core(h, draws, feature_counts != nullptr, nullptr, stats);
+    if (rc) return rc;
+    const int64_t R = draws->n_iter, G = h->query.n;
+    if ((rc = fetch_u64_as_i64(h, h->d_iter_nranges, R, iter_nranges))) return rc;
+    if ((rc = fetch_u64_as_i64(h, h->d_iter_totals, R, iter_totals))) return rc;
+    if (feature_counts && G > 0 && R > 0)
+        NRB_CUDA(h, cudaMemcpyAsync(feature_counts, h->d_counts.p, (size_t)R * G * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+    NRB_CUDA(h, cudaStreamSynchronize(h->stream));
+    if (stats) stats->d2h_bytes = (iter_nranges ? R * 8 : 0) + (iter_totals ? R * 8 : 0) + (feature_counts ? R * G * 4 : 0);
+    return NRB200_OK;
+}
+
+int nrb200_moments_reset(nrb200_handle *h) {
+    if (!h) return NRB200_ERR_INVALID;
+    NRB_CUDA(h, cudaSetDevice(h->device));
+    const int64_t G = h->query.n;
+    if (G == 0) return fail(h, NRB200_ERR_STATE, "moments need a query (nrb200_set_query)");
+    NRB_CUDA(h, h->m_sum.reserve(G * 8));
+    NRB_CUDA(h, h->m_sumsq.reserve(G * 8));
+    NRB_CUDA(h, h->m_nge.reserve(G * 8));
+    NRB_CUDA(h, cudaMemsetAsync(h->m_sum.p, 0, G * 8, h->stream));
+    NRB_CUDA(h, cudaMemsetAsync(h->m_sumsq.p, 0, G * 8, h->stream));
+    NRB_CUDA(h, cudaMemsetAsync(h->m_nge.p, 0, G * 8, h->stream));
+    h->moments_ready = true;
+    return NRB200_OK;
+}
+
+int nrb200_run_moments(nrb200_handle *h, const nrb200_draws *draws, int64_t batch_iter, const int32_t *observed,
+                       int64_t *iter_nranges, int64_t *iter_totals, nrb200_stats *stats) {
+    if (!h || !draws) return NRB200_ERR_INVALID;
+    NRB_CUDA(h, cudaSetDevice(h->device));
+    const int64_t G = h->query.n;
+    if (G == 0) return fail(h, NRB200_ERR_STATE, "moments need a query (nrb200_set_query)");
+    int rc;
+    if (!h->moments_ready && (rc = nrb200_moments_reset(h))) return rc;
+    if (observed && (rc = upload(h, h->m_observed, observed, (size_t)G))) return rc;
+    if (batch_iter <= 0) batch_iter = std::max<int64_t>(1, std::min<int64_t>(draws->n_iter, ((int64_t)1 << 28) / std::max<int64_t>(G, 1)));
+    const int64_t B = h->plan.n_blocks();
+    nrb200_stats acc{};
+    for (int64_t r0 = 0; r0 < draws->n_iter; r0 += batch_iter) {
+        nrb200_draws d = *draws;
+        d.n_iter = std::min(batch_iter, draws->n_iter - r0);
+        d.iter0 = draws->iter0 + r0;
+        if (draws->rng_mode == NRB200_RNG_HOST) {
+            d.bait_seqid = draws->bait_seqid + r0 * B;
+            d.bait_start = draws->bait_start + r0 * B;
+            d.dst_tile = draws->dst_tile ? draws->dst_tile + r0 * B : nullptr;
+        }
+        nrb200_stats st{};
+        if ((rc = run_counts_core(h, &d, true, nullptr, &st))) return rc;
+        const int threads = 256;
+        accumulate_moments_kernel<<<(unsigned)((G + threads - 1) / threads), threads, 0, h->stream>>>(
+            h->d_counts.as<int32_t>(), d.n_iter, G, observed ? h->m_observed.as<int32_t>() : nullptr,
+            h->m_sum.as<long long>(), h->m_sumsq.as<long long>(), h->m_nge.as<long long>());
+        NRB_CUDA(h, cudaGetLastError());
+        if ((rc = fetch_u64_as_i64(h, h->d_iter_nranges, d.n_iter, iter_nranges ? iter_nranges + r0 : nullptr))) return rc;
+        if ((rc = fetch_u64_as_i64(h, h->d_iter_totals, d.n_iter, iter_totals ? iter_totals + r0 : nullptr))) return rc;
+        NRB_CUDA(h, cudaStreamSynchronize(h->stream));
+        acc.kernel_ms += st.kernel_ms;
+        acc.total_ms += st.total_ms;
+        acc.n_launches += st.n_launches + 1;
+        acc.n_hits += st.n_hits;
+        acc.h2d_bytes += st.h2d_bytes;
+    }
+    if (stats) *stats = acc;
+    return NRB200_OK;
+}
+
+int nrb200_moments_fetch(nrb200_handle *h, int64_t *feat_sum, int64_t *feat_sumsq, int64_t *feat_n_ge_observed) {
+    if (!h) return NRB200_ERR_INVALID;
+    if (!h->moments_ready) return fail(h, NRB200_ERR_STATE, "no moments accumulated");
+    NRB_CUDA(h, cudaSetDevice(h->device));
+    const size_t bytes = (size_t)h->query.n * 8;
+    if (feat_sum) NRB_CUDA(h, cudaMemcpyAsync(feat_sum, h->m_sum.p, bytes, cudaMemcpyDeviceToHost, h->stream));
+    if (feat_sumsq) NRB_CUDA(h, cudaMemcpyAsync(feat_sumsq, h->m_sumsq.p, bytes, cudaMemcpyDeviceToHost, h->stream));
+    if (feat_n_ge_observed) NRB_CUDA(h, cudaMemcpyAsync(feat_n_ge_observed, h->m_nge.p, bytes, cudaMemcpyDeviceToHost, h->stream));
+    NRB_CUDA(h, cudaStreamSynchronize(h->stream));
+    return NRB200_OK;
+}
+
+int nrb200_count_observed(nrb200_handle *h, int32_t *feature_counts, int64_t *total) {
+    if (!h) return NRB200_ERR_INVALID;
+    NRB_CUDA(h, cudaSetDevice(h->device));
+    if (!h->have_y) return fail(h, NRB200_ERR_STATE, "nrb200_set_ranges() has not been called");
+    const RangeSet &q = h->query;
+    if (q.n == 0) return fail(h, NRB200_ERR_STATE, "nrb200_set_query() has not been called");
+    DevMem counts, tot;
+    NRB_CUDA(h, counts.reserve(q.n * 4));
+    NRB_CUDA(h, tot.reserve(8));
+    NRB_CUDA(h, cudaMemsetAsync(counts.p, 0, q.n * 4, h->stream));
+    NRB_CUDA(h, cudaMemsetAsync(tot.p, 0, 8, h->stream));
+    const RangeSet &y = h->y;
+    RangesView yv{};
+    yv.start = y.start.as<int32_t>();
+    yv.end = y.end.as<int32_t>();
+    yv.strand = y.stranded ? y.strand.as<int8_t>() : nullptr;
+    const int threads = 256;
+    const unsigned grid = (unsigned)((y.n + threads - 1) / threads);
+    if (y.n > 0) {
+        if (y.stranded && q.stranded)
+            count_observed_kernel<true><<<grid, threads, 0, h->stream>>>(yv, y.n, y.seqid.as<int32_t>(), q.start.as<int32_t>(),
+                q.end.as<int32_t>(), q.pmax.as<int32_t>(), q.strand.as<int8_t>(), q.src.as<int32_t>(), q.seq_off.as<int32_t>(),
+                counts.as<int32_t>(), tot.as<unsigned long long>());
+        else
+            count_observed_kernel<false><<<grid, threads, 0, h->stream>>>(yv, y.n, y.seqid.as<int32_t>(), q.start.as<int32_t>(),
+                q.end.as<int32_t>(), q.pmax.as<int32_t>(), nullptr, q.src.as<int32_t>(), q.seq_off.as<int32_t>(),
+                counts.as<int32_t>(), tot.as<unsigned long long>());
+        NRB_CUDA(h, cudaGetLastError());
+    }
+    unsigned long long t = 0;
+    if (feature_counts) NRB_CUDA(h, cudaMemcpyAsync(feature_counts, counts.p, q.n * 4, cudaMemcpyDeviceToHost, h->stream));
+    NRB_CUDA(h, cudaMemcpyAsync(&t, tot.p, 8, cudaMemcpyDeviceToHost, h->stream));
+    NRB_CUDA(h, cudaStreamSynchronize(h->stream));
+    if (total) *total = (int64_t)t;
+    return NRB200_OK;
+}
+
+int nrb200_run_materialize(nrb200_handle *h, const nrb200_draws *draws, int64_t *iter_offsets, nrb200_stats *stats) {
+    if (!h || !draws) return NRB200_ERR_INVALID;
+    NRB_CUDA(h, cudaSetDevice(h->device));
+    int rc;
+    if ((rc = prepare(h))) return rc;
+    NRB_CUDA(h, cudaEventRecord(h->ev[0], h->stream));
+    if ((rc = stage_draws(h, draws))) return rc;
+    const int64_t R = draws->n_iter, B = h->plan.n_blocks(), items = R * B;
+    NRB_CUDA(h, h->d_iter_nranges.reserve(std::max<int64_t>(R, 1) * 8));
+    NRB_CUDA(h, h->d_n_hits.reserve(8));
+    NRB_CUDA(h, h->item_rows.reserve(std::max<int64_t>(items, 1) * 4));
+    NRB_CUDA(h, h->within_off.reserve(std::max<int64_t>(items, 1) * 4));
+    NRB_CUDA(h, h->iter_off_dev.reserve((R + 1) * 8));
+    NRB_CUDA(h, cudaMemsetAsync(h->d_iter_nranges.p, 0, R * 8, h->stream));
+    NRB_CUDA(h, cudaMemsetAsync(h->d_n_hits.p, 0, 8, h->stream));
+    BootParams P = make_params(h, draws);
+    P.n_query = 0;
+    P.iter_nranges = h->d_iter_nranges.as<unsigned long long>();
+    P.iter_totals = nullptr;
+    P.item_rows = h->item_rows.as<int32_t>();
+    P.n_hits = h->d_n_hits.as<unsigned long long>();
+    NRB_CUDA(h, cudaEventRecord(h->ev[1], h->stream));
+    launch_count(h, P, false);
+    NRB_CUDA(h, cudaGetLastError());
+    if (R > 0)
+        scan_iteration_kernel<<<(unsigned)R, 256, 0, h->stream>>>(h->item_rows.as<int32_t>(), B, h->within_off.as<int32_t>());
+    NRB_CUDA(h, cudaGetLastError());
+    std::vector<int64_t> per_iter(R), offs(R + 1, 0);
+    if ((rc = fetch_u64_as_i64(h, h->d_iter_nranges, R, per_iter.data()))) return rc;
+    NRB_CUDA(h, cudaStreamSynchronize(h->stream));
+    for (int64_t r = 0; r < R; ++r) offs[r + 1] = offs[r] + per_iter[r];
+    const int64_t rows = offs[R];
+    if ((rc = upload(h, h->iter_off_dev, offs.data(), (size_t)R + 1))) return rc;
+    for (DevMem *m : {&h->row_seq, &h->row_start, &h->row_end, &h->row_src, &h->row_block})
+        NRB_CUDA(h, m->reserve(std::max<int64_t>(rows, 1) * 4));
+    RowsOut O{h->row_seq.as<int32_t>(), h->row_start.as<int32_t>(), h->row_end.as<int32_t>(), h->row_src.as<int32_t>(),
+              h->row_block.as<int32_t>(), h->iter_off_dev.as<int64_t>(), h->within_off.as<int32_t>()};
+    if (items > 0) {
+        const unsigned grid = (unsigned)std::min<int64_t>((items + 7) / 8, (int64_t)h->sm_count * 64);
+        const bool st = h->y.stranded && h->excl.n && h->excl.stranded;
+        const bool hx = h->excl.n > 0;
+        if (st && hx) boot_fill_kernel<true, true><<<grid, 256, 0, h->stream>>>(P, O);
+        else if (hx) boot_fill_kernel<false, true><<<grid, 256, 0, h->stream>>>(P, O);
+        else boot_fill_kernel<false, false><<<grid, 256, 0, h->stream>>>(P, O);
+        NRB_CUDA(h, cudaGetLastError());
+    }
+    NRB_CUDA(h, cudaEventRecord(h->ev[2], h->stream));
+    NRB_CUDA(h, cudaStreamSynchronize(h->stream));
+    h->n_rows = rows;
+    if (iter_offsets) std::memcpy(iter_offsets, offs.data(), (size_t)(R + 1) * 8);
+    if (stats) {
+        float k_ms = 0, t_ms = 0;
+        cudaEventElapsedTime(&k_ms, h->ev[1], h->ev[2]);
+        cudaEventElapsedTime(&t_ms, h->ev[0], h->ev[2]);
+        unsigned long long hits = 0;
+        cudaMemcpy(&hits, h->d_n_hits.p, 8, cudaMemcpyDeviceToHost);
+        std::memset(stats, 0, sizeof *stats);
+        stats->kernel_ms = k_ms;
+        stats->total_ms = t_ms;
+        stats->n_launches = items > 0 ? 3 : 0;
+        stats->n_hits = (int64_t)hits;
+    }
+    return NRB200_OK;
+}
+
+int nrb200_fetch_rows(nrb200_handle *h, int64_t row0, int64_t n, int32_t *seqid, int32_t *start, int32_t *end,
+                      int32_t *src_idx, int32_t *block) {
+    if (!h) return NRB200_ERR_INVALID;
+    NRB_CUDA(h, cudaSetDevice(h->device));
+    if (row0 < 0 || n < 0 || row0 + n > h->n_rows) return fail(h, NRB200_ERR_INVALID, "fetch_rows: range outside the materialised table");
+    struct { int32_t *dst; DevMem *src; } cols[] = {{seqid, &h->row_seq}, {start, &h->row_start}, {end, &h->row_end},
+                                                     {src_idx, &h->row_src}, {block, &h->row_block}};
+    for (auto &c : cols)
+        if (c.dst && n)
+            NRB_CUDA(h, cudaMemcpyAsync(c.dst, c.src->as<int32_t>() + row0, n * 4, cudaMemcpyDeviceToHost, h->stream));
+    NRB_CUDA(h, cudaStreamSynchronize(h->stream));
+    return NRB200_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,397 @@
+// Device side of the stream engine: one warp per (iteration, block) work item.
+//
+//   bait block (sampled or supplied)  ->  locate its hits in the start-sorted ranges
+//   -> stream the hits, shift to the destination tile, trim, drop, exclude
+//   -> count overlaps against the tile's slice of the query index.
+//
+// Reference code this replaces, per iteration: R/bootUnsegmented.R:116-143 / :50-75 /
+// R/bootRanges.R:141-176 (sampler + findOverlaps + gather), R/bootUnsegmented.R:175-191
+// (shift_and_swap_chrom), R/bootRanges.R:106-109 (exclude drop) and the user-side
+// countOverlaps of vignettes/bootRanges.Rmd:497-503.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#include "../../include/nrb200.h"
+#include "philox.cuh"
+
+namespace nrb {
+
+constexpr int kWarp = 32;
+constexpr unsigned kFull = 0xffffffffu;
+
+// ---- device views ---------------------------------------------------------------------
+
+struct RangesView {            // canonical (seqname, start, end) order
+    const int32_t *start;
+    const int32_t *end;
+    const int32_t *pmax;       // running max of end within the sequence
+    const int8_t *strand;      // nullptr when every strand is '*'
+    const int32_t *src;        // index in the caller's order
+    const int32_t *seq_off;    // [n_seq + 1]
+    // direct-address rank tables: first index whose value is >= (bucket << shift)
+    const int32_t *rank_start;
+    const int32_t *rank_pmax;
+    const int64_t *rank_off;   // [n_seq + 1] first table entry of each sequence
+    const int32_t *max_pos;    // [n_seq] largest coordinate a table covers
+    int rank_shift;
+};
+
+struct SliceView {             // query or exclude, canonical order, plus a per-tile window
+    const int32_t *start;
+    const int32_t *end;
+    const int8_t *strand;
+    const int32_t *src;
+    const int32_t *tile_lo;    // [n_blocks] first candidate of the tile
+    const int32_t *tile_hi;    // [n_blocks] one past the last
+};
+
+struct SamplerView {
+    int kind, n_seq, n_states;
+    int64_t block_length, genome_length;
+    const int64_t *seq_cum, *tiles_per_seq;
+    const int64_t *state_block_off, *state_seg_off, *state_len, *state_block_len;
+    const int64_t *sg_cum;
+    const int32_t *sg_seq, *sg_start, *sg_tiles;
+};
+
+struct BootParams {
+    RangesView y;
+    SliceView query, excl;
+    SamplerView sampler;
+    // iteration-invariant block tables
+    int64_t n_blocks;
+    const int32_t *tile_seq, *tile_start, *bait_width;
+    const int64_t *seqlen;
+    int permute, drop_zero;
+    // draws
+    int rng_mode;
+    uint64_t seed;
+    int64_t iter0;            // global index of local iteration 0 (Philox counter)
+    const int32_t *bait_seq, *bait_start, *dst_tile;  // [n_iter x n_blocks] (host draws)
+    // outputs
+    int64_t n_iter, n_query;
+    unsigned long long *iter_nranges, *iter_totals;  // [n_iter]
+    int32_t *counts;          // [n_iter x n_query], caller's query order, or nullptr
+    int32_t *item_rows;       // [n_iter x n_blocks] surviving rows per item, or nullptr
+    unsigned long long *n_hits;  // total ranges streamed (byte-model H)
+};
+
+// ---- searches -------------------------------------------------------------------------
+
+// first index in [a, b) with v[idx] > key
+__device__ __forceinline__ int32_t first_gt(const int32_t *__restrict__ v, int32_t a, int32_t b, int32_t key) {
+    while (a < b) {
+        const int32_t m = (a + b) >> 1;
+        if (__ldg(v + m) <= key) a = m + 1; else b = m;
+    }
+    return a;
+}
+// first index in [a, b) with v[idx] >= key
+__device__ __forceinline__ int32_t first_ge(const int32_t *__restrict__ v, int32_t a, int32_t b, int32_t key) {
+    while (a < b) {
+        const int32_t m = (a + b) >> 1;
+        if (__ldg(v + m) < key) a = m + 1; else b = m;
+    }
+    return a;
+}
+
+// Hits of the bait block [s, e] on sequence c are a window [lo, hi) of the canonical order:
+// hi = #{start <= e}, lo = first index whose running-max end reaches s.  Both come from one
+// rank-table probe plus a search confined to a single bucket.
+__device__ __forceinline__ void locate_block(const RangesView &y, int c, int32_t s, int64_t e,
+                                             int32_t &lo, int32_t &hi) {
+    const int32_t seq_end = __ldg(y.seq_off + c + 1);
+    const int32_t max_pos = __ldg(y.max_pos + c);
+    const int64_t base = __ldg(y.rank_off + c);
+    if (e >= max_pos) {
+        hi = seq_end;
+    } else {
+        const int32_t pe = e < 0 ? 0 : (int32_t)e;
+        const int64_t u = base + (pe >> y.rank_shift);
+        hi = first_gt(y.start, __ldg(y.rank_start + u), __ldg(y.rank_start + u + 1), pe);
+    }
+    if (s > max_pos) {
+        lo = seq_end;
+    } else {
+        const int32_t ps = s < 0 ? 0 : s;
+        const int64_t u = base + (ps >> y.rank_shift);
+        lo = first_ge(y.pmax, __ldg(y.rank_pmax + u), __ldg(y.rank_pmax + u + 1), ps);
+    }
+    if (lo > hi) lo = hi;
+}
+
+__device__ __forceinline__ bool strands_match(int a, int b) { return a == 0 || b == 0 || a == b; }
+
+// ---- block draws ----------------------------------------------------------------------
+
+// Production-mode draw of block b of global iteration `iter` (same arithmetic on the host:
+// philox.cuh).  Returns the sequence and start the block is sampled from.
+__device__ __forceinline__ void draw_block(const BootParams &P, uint64_t iter, int64_t b, int &c, int32_t &s) {
+    const SamplerView &S = P.sampler;
+    const Philox128 u = philox_draw(P.seed, iter, (uint32_t)b, 0u);
+    if (S.kind == NRB200_UNSEG_ACROSS) {
+        const int64_t pos = (int64_t)mul_hi_u64(u.lo, (uint64_t)S.genome_length);
+        c = pick_by_length(S.seq_cum, S.n_seq, pos);
+        s = (int32_t)rounded_uniform(u.hi, 1, (S.tiles_per_seq[c] - 1) * S.block_length);
+    } else if (S.kind == NRB200_UNSEG_WITHIN) {
+        c = __ldg(P.tile_seq + b);
+        s = (int32_t)rounded_uniform(u.hi, 1, (S.tiles_per_seq[c] - 1) * S.block_length);
+    } else {  // NRB200_SEG_PROP
+        int st = 1;
+        while (st < S.n_states && b >= S.state_block_off[st + 1]) ++st;
+        const int64_t first = S.state_seg_off[st];
+        const int n = (int)(S.state_seg_off[st + 1] - first);
+        const int64_t pos = (int64_t)mul_hi_u64(u.lo, (uint64_t)S.state_len[st]);
+        const int64_t j = first + pick_by_length(S.sg_cum + first, n, pos);
+        c = S.sg_seq[j];
+        s = (int32_t)rounded_uniform(u.hi, S.sg_start[j], (int64_t)(S.sg_tiles[j] - 1) * S.state_block_len[st]);
+    }
+}
+
+// ---- the fused kernel -----------------------------------------------------------------
+
+struct Item {
+    int bait_seq, tile;        // sampled-from sequence; destination tile index
+    int32_t bait_start;
+    int64_t bait_end;
+    int tile_seq;
+    int32_t shift;             // tile_start - bait_start       (block_shift, :179)
+    int32_t seq_len;           // seqlengths[tile_seq]
+    int32_t lo, hi;            // hit window in canonical y
+};
+
+__device__ __forceinline__ Item load_item(const BootParams &P, int64_t r, int64_t b) {
+    Item it;
+    const int64_t flat = r * P.n_blocks + b;
+    if (P.rng_mode == NRB200_RNG_PHILOX) {
+        draw_block(P, (uint64_t)(P.iter0 + r), b, it.bait_seq, it.bait_start);
+        it.tile = (int)b;
+    } else {
+        it.bait_seq = __ldg(P.bait_seq + flat);
+        it.bait_start = __ldg(P.bait_start + flat);
+        it.tile = P.dst_tile ? __ldg(P.dst_tile + flat) : (int)b;
+    }
+    it.bait_end = (int64_t)it.bait_start + __ldg(P.bait_width + b) - 1;
+    it.tile_seq = __ldg(P.tile_seq + it.tile);
+    it.shift = __ldg(P.tile_start + it.tile) - it.bait_start;
+    it.seq_len = (int32_t)__ldg(P.seqlen + it.tile_seq);
+    locate_block(P.y, it.bait_seq, it.bait_start, it.bait_end, it.lo, it.hi);
+    return it;
+}
+
+// shift() + trim() + the width filter for one candidate.  Returns false when the range is
+// not a hit or is dropped.  (s2, e2) is the trimmed range; e2 < s2 marks a zero-width
+// survivor of the within-chromosome variants.
+__device__ __forceinline__ bool transform(const BootParams &P, const Item &it, int32_t st, int32_t en,
+                                          int32_t &s2, int32_t &e2) {
+    // bootstrap: any overlap with the bait block; permute: the tile that holds the start
+    const bool hit = P.permute ? (st >= it.bait_start) : (en >= it.bait_start);
+    if (!hit) return false;
+    s2 = st + it.shift;
+    e2 = en + it.shift;
+    if (s2 > it.seq_len) {       // wholly beyond the sequence end -> [L + 1, L]
+        if (P.drop_zero) return false;
+        s2 = it.seq_len + 1;
+        e2 = it.seq_len;
+    } else {
+        s2 = max(s2, 1);
+        e2 = min(e2, it.seq_len);
+    }
+    return true;
+}
+
+template <bool STRANDED>
+__device__ __forceinline__ bool excluded(const SliceView &X, int tile, int32_t s2, int32_t e2, int strand) {
+    if (e2 < s2) return false;
+    const int32_t a = __ldg(X.tile_lo + tile), b = __ldg(X.tile_hi + tile);
+    for (int32_t k = a; k < b; ++k) {
+        if (s2 <= __ldg(X.end + k) && e2 >= __ldg(X.start + k)) {
+            if (!STRANDED || !X.strand || strands_match(strand, __ldg(X.strand + k))) return true;
+        }
+    }
+    return false;
+}
+
+template <bool STRANDED, bool HAS_QUERY, bool HAS_EXCL>
+__global__ void __launch_bounds__(256) boot_count_kernel(const BootParams P) {
+    const int lane = threadIdx.x & (kWarp - 1);
+    const int64_t warps_total = (int64_t)gridDim.x * (blockDim.x / kWarp);
+    const int64_t warp0 = (int64_t)blockIdx.x * (blockDim.x / kWarp) + (threadIdx.x / kWarp);
+    const int64_t n_items = P.n_iter * P.n_blocks;
+
+    for (int64_t item = warp0; item < n_items; item += warps_total) {
+        const int64_t r = item / P.n_blocks, b = item - r * P.n_blocks;
+        const Item it = load_item(P, r, b);
+
+        int32_t q_lo = 0, q_hi = 0;
+        if (HAS_QUERY) {
+            q_lo = __ldg(P.query.tile_lo + it.tile);
+            q_hi = __ldg(P.query.tile_hi + it.tile);
+        }
+        int rows = 0;
+        int overlaps = 0;
+        for (int32_t i = it.lo + lane; i < it.hi; i += kWarp) {
+            const int32_t st = __ldg(P.y.start + i), en = __ldg(P.y.end + i);
+            int32_t s2, e2;
+            if (!transform(P, it, st, en, s2, e2)) continue;
+            const int strand = (STRANDED && P.y.strand) ? __ldg(P.y.strand + i) : 0;
+            if (HAS_EXCL && excluded<STRANDED>(P.excl, it.tile, s2, e2, strand)) continue;
+            ++rows;
+            if (HAS_QUERY && e2 >= s2) {
+                for (int32_t k = q_lo; k < q_hi; ++k) {
+                    if (s2 <= __ldg(P.query.end + k) && e2 >= __ldg(P.query.start + k)) {
+                        if (STRANDED && P.query.strand && !strands_match(strand, __ldg(P.query.strand + k))) continue;
+                        ++overlaps;
+                        if (P.counts) atomicAdd(P.counts + r * P.n_query + __ldg(P.query.src + k), 1);
+                    }
+                }
+            }
+        }
+        rows = __reduce_add_sync(kFull, rows);
+        if (HAS_QUERY) overlaps = __reduce_add_sync(kFull, overlaps);
+        if (lane == 0) {
+            if (rows) atomicAdd(P.iter_nranges + r, (unsigned long long)rows);
+            if (HAS_QUERY && overlaps) atomicAdd(P.iter_totals + r, (unsigned long long)overlaps);
+            if (P.item_rows) P.item_rows[item] = rows;
+            if (P.n_hits) atomicAdd(P.n_hits, (unsigned long long)(it.hi - it.lo));
+        }
+    }
+}
+
+// ---- materialising path ---------------------------------------------------------------
+
+// One CTA per iteration: exclusive scan of the rows-per-block of that iteration.
+__global__ void __launch_bounds__(256) scan_iteration_kernel(const int32_t *__restrict__ item_rows, int64_t n_blocks,
+                                                             int32_t *__restrict__ within_off) {
+    __shared__ int warp_sums[8];
+    __shared__ int carry;
+    const int64_t r = blockIdx.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (int64_t base = 0; base < n_blocks; base += blockDim.x) {
+        const int64_t b = base + threadIdx.x;
+        const int v = b < n_blocks ? item_rows[r * n_blocks + b] : 0;
+        int x = v;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int t = __shfl_up_sync(kFull, x, d);
+            if (lane >= d) x += t;
+        }
+        if (lane == 31) warp_sums[warp] = x;
+        __syncthreads();
+        int before = carry;
+        for (int w = 0; w < warp; ++w) before += warp_sums[w];
+        if (b < n_blocks) within_off[r * n_blocks + b] = before + x - v;
+        __syncthreads();
+        if (threadIdx.x == blockDim.x - 1) carry = before + x;
+        __syncthreads();
+    }
+}
+
+struct RowsOut {
+    int32_t *seq, *start, *end, *src, *block;
+    const int64_t *iter_off;      // [n_iter + 1]
+    const int32_t *within_off;    // [n_iter x n_blocks]
+};
+
+template <bool STRANDED, bool HAS_EXCL>
+__global__ void __launch_bounds__(256) boot_fill_kernel(const BootParams P, const RowsOut O) {
+    const int lane = threadIdx.x & (kWarp - 1);
+    const int64_t warps_total = (int64_t)gridDim.x * (blockDim.x / kWarp);
+    const int64_t warp0 = (int64_t)blockIdx.x * (blockDim.x / kWarp) + (threadIdx.x / kWarp);
+    const int64_t n_items = P.n_iter * P.n_blocks;
+    for (int64_t item = warp0; item < n_items; item += warps_total) {
+        const int64_t r = item / P.n_blocks, b = item - r * P.n_blocks;
+        const Item it = load_item(P, r, b);
+        int64_t out = O.iter_off[r] + O.within_off[item];
+        for (int32_t base = it.lo; base < it.hi; base += kWarp) {
+            const int32_t i = base + lane;
+            bool keep = false;
+            int32_t s2 = 0, e2 = 0;
+            if (i < it.hi) {
+                keep = transform(P, it, __ldg(P.y.start + i), __ldg(P.y.end + i), s2, e2);
+                if (keep && HAS_EXCL) {
+                    const int strand = (STRANDED && P.y.strand) ? __ldg(P.y.strand + i) : 0;
+                    keep = !excluded<STRANDED>(P.excl, it.tile, s2, e2, strand);
+                }
+            }
+            const unsigned m = __ballot_sync(kFull, keep);
+            if (keep) {
+                const int64_t pos = out + __popc(m & ((1u << lane) - 1u));
+                O.seq[pos] = it.tile_seq;
+                O.start[pos] = s2;
+                O.end[pos] = e2;
+                O.src[pos] = __ldg(P.y.src + i);
+                O.block[pos] = (int32_t)b;
+            }
+            out += __popc(m);
+        }
+    }
+}
+
+// ---- index construction ---------------------------------------------------------------
+
+// entry t of a rank table: first index of its sequence whose value is >= (bucket << shift)
+__global__ void build_rank_table_kernel(const int32_t *__restrict__ values, const int32_t *__restrict__ seq_off,
+                                        const int64_t *__restrict__ rank_off, int n_seq, int shift,
+                                        int32_t *__restrict__ table) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= rank_off[n_seq]) return;
+    int c = 0, hi = n_seq;  // sequence that owns entry t
+    while (hi - c > 1) {
+        const int m = (c + hi) >> 1;
+        if (rank_off[m] <= t) c = m; else hi = m;
+    }
+    const int64_t bucket = t - rank_off[c];
+    const int64_t key = bucket << shift;
+    const int32_t a = seq_off[c], b = seq_off[c + 1];
+    table[t] = key > INT32_MAX ? b : first_ge(values, a, b, (int32_t)key);
+}
+
+// countOverlaps(query, y) on the original ranges: one thread per y range.
+template <bool STRANDED>
+__global__ void count_observed_kernel(const RangesView y, int64_t n, const int32_t *__restrict__ y_seq,
+                                      const int32_t *__restrict__ q_start, const int32_t *__restrict__ q_end,
+                                      const int32_t *__restrict__ q_pmax, const int8_t *__restrict__ q_strand,
+                                      const int32_t *__restrict__ q_src, const int32_t *__restrict__ q_seq_off,
+                                      int32_t *__restrict__ counts, unsigned long long *__restrict__ total) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int found = 0;
+    if (i < n) {
+        const int c = y_seq[i];
+        const int32_t s = y.start[i], e = y.end[i];
+        const int strand = (STRANDED && y.strand) ? y.strand[i] : 0;
+        const int32_t a = q_seq_off[c];
+        for (int32_t k = first_gt(q_start, a, q_seq_off[c + 1], e) - 1; k >= a && q_pmax[k] >= s; --k) {
+            if (q_end[k] >= s && (!STRANDED || !q_strand || strands_match(strand, q_strand[k]))) {
+                ++found;
+                atomicAdd(counts + q_src[k], 1);
+            }
+        }
+    }
+    found = __reduce_add_sync(kFull, found);
+    if ((threadIdx.x & 31) == 0 && found) atomicAdd(total, (unsigned long long)found);
+}
+
+// Per-feature moments over a batch of iterations: thread per feature, coalesced over g.
+__global__ void accumulate_moments_kernel(const int32_t *__restrict__ counts, int64_t n_iter, int64_t n_query,
+                                          const int32_t *__restrict__ observed, long long *__restrict__ sum,
+                                          long long *__restrict__ sumsq, long long *__restrict__ n_ge) {
+    const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= n_query) return;
+    long long s = 0, q = 0, ge = 0;
+    const int32_t obs = observed ? observed[g] : 0;
+    for (int64_t r = 0; r < n_iter; ++r) {
+        const long long v = counts[r * n_query + g];
+        s += v;
+        q += v * v;
+        ge += (observed && v >= obs) ? 1 : 0;
+    }
+    sum[g] += s;
+    sumsq[g] += q;
+    n_ge[g] += ge;
+}
+
+}  // namespace nrb

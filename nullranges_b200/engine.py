@@ -1,0 +1,175 @@
+"""Handle-level wrapper of the C ABI: one Engine = one GPU = one nrb200_handle."""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+
+import numpy as np
+
+from . import _lib
+from ._lib import ptr
+
+
+class EngineError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"libnrb200 error {code}: {msg}")
+        self.code = code
+
+
+def _i32(a):
+    return None if a is None else np.ascontiguousarray(a, dtype=np.int32)
+
+
+def _i8(a):
+    return None if a is None else np.ascontiguousarray(a, dtype=np.int8)
+
+
+@dataclass
+class Draws:
+    """Block draws for a run: Philox (device) or host arrays of shape [n_iter, n_blocks]."""
+    n_iter: int
+    rng_mode: int = _lib.RNG_PHILOX
+    seed: int = 0
+    iter0: int = 0
+    bait_seqid: np.ndarray | None = None
+    bait_start: np.ndarray | None = None
+    dst_tile: np.ndarray | None = None
+
+    def to_c(self):
+        self._keep = (_i32(self.bait_seqid), _i32(self.bait_start), _i32(self.dst_tile))
+        return _lib.Draws(int(self.n_iter), int(self.iter0), int(self.rng_mode), C.c_uint64(int(self.seed) & (2**64 - 1)),
+                          ptr(self._keep[0], C.c_int32), ptr(self._keep[1], C.c_int32), ptr(self._keep[2], C.c_int32))
+
+
+class Engine:
+    def __init__(self, device: int = 0, stream: int | None = None):
+        self._lib = _lib.load()
+        self._h = C.c_void_p()
+        cfg = _lib.Config(int(device), 0, C.c_void_p(stream) if stream else None)
+        rc = self._lib.nrb200_create(C.byref(cfg), C.byref(self._h))
+        if rc:
+            raise EngineError(rc, self._lib.nrb200_last_error(None).decode())
+        self.device = device
+        self.n_blocks = 0
+        self.n_query = 0
+        self.n_seq = 0
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.nrb200_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def _check(self, rc: int):
+        if rc:
+            raise EngineError(rc, self._lib.nrb200_last_error(self._h).decode())
+
+    # ---- inputs
+    def set_ranges(self, seqlengths, seqid, start, end, strand=None):
+        sl = np.ascontiguousarray(seqlengths, dtype=np.int64)
+        a, b, c, d = _i32(seqid), _i32(start), _i32(end), _i8(strand)
+        self._check(self._lib.nrb200_set_ranges(self._h, a.size, sl.size, ptr(sl, C.c_int64), ptr(a, C.c_int32),
+                                                ptr(b, C.c_int32), ptr(c, C.c_int32), ptr(d, C.c_int8)))
+        self.n_seq = sl.size
+        self.n_query = 0
+        self.n_blocks = 0
+
+    def set_query(self, seqid, start, end, strand=None):
+        a, b, c, d = _i32(seqid), _i32(start), _i32(end), _i8(strand)
+        self._check(self._lib.nrb200_set_query(self._h, a.size, ptr(a, C.c_int32), ptr(b, C.c_int32), ptr(c, C.c_int32), ptr(d, C.c_int8)))
+        self.n_query = a.size
+
+    def set_exclude(self, seqid, start, end, strand=None):
+        a, b, c, d = _i32(seqid), _i32(start), _i32(end), _i8(strand)
+        self._check(self._lib.nrb200_set_exclude(self._h, a.size, ptr(a, C.c_int32), ptr(b, C.c_int32), ptr(c, C.c_int32), ptr(d, C.c_int8)))
+
+    def clear_exclude(self):
+        self._check(self._lib.nrb200_set_exclude(self._h, 0, None, None, None, None))
+
+    def clear_query(self):
+        self._check(self._lib.nrb200_set_query(self._h, 0, None, None, None, None))
+        self.n_query = 0
+
+    def set_plan(self, kind: int, block_length: int, seg=None) -> int:
+        """seg: dict(seqid, start, end, state) for the segmented kinds."""
+        if seg is not None:
+            keep = tuple(_i32(seg[k]) for k in ("seqid", "start", "end", "state"))
+            spec = _lib.PlanSpec(kind, int(block_length), keep[0].size, *(ptr(k, C.c_int32) for k in keep))
+        else:
+            spec = _lib.PlanSpec(kind, int(block_length), 0, None, None, None, None)
+        nb = C.c_int64()
+        self._check(self._lib.nrb200_set_plan(self._h, C.byref(spec), C.byref(nb)))
+        self.n_blocks = nb.value
+        return nb.value
+
+    def tiles(self):
+        B = self.n_blocks
+        ts, tt, bw = (np.empty(B, np.int32) for _ in range(3))
+        self._check(self._lib.nrb200_get_tiles(self._h, ptr(ts, C.c_int32), ptr(tt, C.c_int32), ptr(bw, C.c_int32)))
+        return ts, tt, bw
+
+    # ---- fused counting
+    def run_counts(self, draws: Draws, want_counts: bool = True) -> dict:
+        R, G = int(draws.n_iter), self.n_query
+        nr, tot = np.zeros(R, np.int64), np.zeros(R, np.int64)
+        cnt = np.zeros((R, G), np.int32) if (want_counts and G) else None
+        st = _lib.Stats()
+        d = draws.to_c()
+        self._check(self._lib.nrb200_run_counts(self._h, C.byref(d), ptr(nr, C.c_int64), ptr(tot, C.c_int64), ptr(cnt, C.c_int32), C.byref(st)))
+        return {"iter_nranges": nr, "iter_totals": tot, "feature_counts": cnt, "stats": st.as_dict()}
+
+    def run_counts_resident(self, draws: Draws, want_counts: bool = True, want_stats: bool = True) -> dict | None:
+        st = _lib.Stats()
+        d = draws.to_c()
+        self._check(self._lib.nrb200_run_counts_resident(self._h, C.byref(d), int(want_counts), C.byref(st) if want_stats else None))
+        return st.as_dict() if want_stats else None
+
+    def resident_pointers(self):
+        a, b, c = C.c_void_p(), C.c_void_p(), C.c_void_p()
+        self._check(self._lib.nrb200_resident_pointers(self._h, C.byref(a), C.byref(b), C.byref(c)))
+        return a.value, b.value, c.value
+
+    def run_moments(self, draws: Draws, observed=None, batch_iter: int = 0, reset: bool = True) -> dict:
+        if reset:
+            self._check(self._lib.nrb200_moments_reset(self._h))
+        R, G = int(draws.n_iter), self.n_query
+        nr, tot = np.zeros(R, np.int64), np.zeros(R, np.int64)
+        obs = _i32(observed)
+        st = _lib.Stats()
+        d = draws.to_c()
+        self._check(self._lib.nrb200_run_moments(self._h, C.byref(d), int(batch_iter), ptr(obs, C.c_int32), ptr(nr, C.c_int64), ptr(tot, C.c_int64), C.byref(st)))
+        s, q, ge = (np.zeros(G, np.int64) for _ in range(3))
+        self._check(self._lib.nrb200_moments_fetch(self._h, ptr(s, C.c_int64), ptr(q, C.c_int64), ptr(ge, C.c_int64)))
+        return {"iter_nranges": nr, "iter_totals": tot, "sum": s, "sumsq": q, "n_ge_observed": ge, "stats": st.as_dict()}
+
+    def count_observed(self):
+        cnt = np.zeros(self.n_query, np.int32)
+        tot = C.c_int64()
+        self._check(self._lib.nrb200_count_observed(self._h, ptr(cnt, C.c_int32), C.byref(tot)))
+        return cnt, tot.value
+
+    # ---- materialising
+    def run_materialize(self, draws: Draws) -> dict:
+        R = int(draws.n_iter)
+        offs = np.zeros(R + 1, np.int64)
+        st = _lib.Stats()
+        d = draws.to_c()
+        self._check(self._lib.nrb200_run_materialize(self._h, C.byref(d), ptr(offs, C.c_int64), C.byref(st)))
+        n = int(offs[-1])
+        cols = {k: np.empty(n, np.int32) for k in ("seqid", "start", "end", "src", "block")}
+        self._check(self._lib.nrb200_fetch_rows(self._h, 0, n, *(ptr(cols[k], C.c_int32) for k in ("seqid", "start", "end", "src", "block"))))
+        cols["iter_offsets"] = offs
+        cols["stats"] = st.as_dict()
+        return cols
+
+
+_engines: dict[int, Engine] = {}
+
+
+def get_engine(device: int = 0) -> Engine:
+    """Process-wide engine per GPU (device buffers are reused across calls)."""
+    e = _engines.get(device)
+    if e is None or e._h is None:
+        e = _engines[device] = Engine(device)
+    return e

@@ -1,0 +1,115 @@
+"""GPU parity: the CUDA engine through the C ABI vs the CPU oracle, bit-exact (integer work)."""
+import numpy as np
+import pytest
+
+from nullranges_b200 import Draws
+from nullranges_b200 import _lib
+from oracle import oracle as O
+from tests import helpers as H
+
+pytestmark = pytest.mark.gpu
+
+BOOT_KINDS = [0, 1, 2, 3]
+ALL_KINDS = [0, 1, 2, 3, 4, 5]
+
+
+def _check_counts(eng, case, kind, R, seed, philox):
+    plan, y, q, x = H.oracle_objects(case, kind)
+    B = H.load_engine(eng, case, kind)
+    assert B == plan.B
+    ts, tt, bw = eng.tiles()
+    assert np.array_equal(ts, plan.tile_chrom) and np.array_equal(tt, plan.tile_start) and np.array_equal(bw, plan.bait_width)
+    if philox:
+        draws = Draws(n_iter=R, rng_mode=_lib.RNG_PHILOX, seed=seed, iter0=5)
+        ref = O.boot_counts(plan, y, q, R, exclude=x, seed=seed, iter0=5)
+    else:
+        d = plan.draw_R(O.RRng(seed), R)
+        draws = Draws(n_iter=R, rng_mode=_lib.RNG_HOST, bait_seqid=d[0], bait_start=d[1], dst_tile=d[2] if kind >= 4 else None)
+        ref = O.boot_counts(plan, y, q, R, exclude=x, draws=d)
+    got = eng.run_counts(draws)
+    assert np.array_equal(got["iter_nranges"], ref["iter_nranges"])
+    assert np.array_equal(got["iter_totals"], ref["iter_totals"])
+    if q is not None:
+        assert np.array_equal(got["feature_counts"], ref["feature_counts"])
+        assert np.array_equal(got["feature_counts"].sum(axis=1), got["iter_totals"])
+    return got, ref
+
+
+@pytest.mark.parametrize("kind", ALL_KINDS)
+@pytest.mark.parametrize("stranded", [False, True])
+@pytest.mark.parametrize("n_excl", [0, 25])
+def test_counts_validation_mode(engine, kind, stranded, n_excl):
+    case = H.random_case(seed=10 + kind, n=600, n_seq=4, n_query=80, n_excl=n_excl, stranded=stranded, n_seg=12,
+                         sort=True)
+    _check_counts(engine, case, kind, R=6, seed=3, philox=False)
+
+
+@pytest.mark.parametrize("kind", [0, 1, 2])
+@pytest.mark.parametrize("n_excl", [0, 25])
+def test_counts_philox_mode(engine, kind, n_excl):
+    case = H.random_case(seed=20 + kind, n=700, n_seq=5, n_query=90, n_excl=n_excl, n_seg=15)
+    _check_counts(engine, case, kind, R=7, seed=2024, philox=True)
+
+
+@pytest.mark.parametrize("kind", [1, 2, 3, 4])
+def test_unsorted_y(engine, kind):
+    case = H.random_case(seed=30 + kind, n=500, n_seq=3, n_query=50, stranded=True, n_seg=9, sort=False)
+    _check_counts(engine, case, kind, R=4, seed=9, philox=False)
+
+
+@pytest.mark.parametrize("kind", ALL_KINDS)
+@pytest.mark.parametrize("n_excl", [0, 20])
+def test_rows_match_oracle(engine, kind, n_excl):
+    case = H.random_case(seed=40 + kind, n=500, n_seq=3, n_query=0, n_excl=n_excl, stranded=bool(n_excl), n_seg=9)
+    plan, y, q, x = H.oracle_objects(case, kind)
+    H.load_engine(engine, case, kind)
+    R = 5
+    d = plan.draw_R(O.RRng(77), R)
+    draws = Draws(n_iter=R, rng_mode=_lib.RNG_HOST, bait_seqid=d[0], bait_start=d[1], dst_tile=d[2] if kind >= 4 else None)
+    rows = engine.run_materialize(draws)
+    it = np.repeat(np.arange(R), np.diff(rows["iter_offsets"]))
+    got = H.canon_rows(rows["seqid"], rows["start"], rows["end"], rows["src"], rows["block"], it)
+    want = H.oracle_rows(plan, y, x, d, R)
+    assert np.array_equal(got, want)
+    # emitted order is already (iter, block, canonical y order) = (iter, block, src) for sorted y
+    assert np.array_equal(rows["block"][np.argsort(it, kind="stable")], rows["block"])
+
+
+def test_points_and_long_ranges(engine):
+    for pts, wmax in ((True, 1), (False, 2500)):
+        case = H.random_case(seed=51, n=800, n_seq=3, n_query=70, points=pts, wmax=wmax)
+        for kind in (0, 1):
+            _check_counts(engine, case, kind, R=5, seed=1, philox=False)
+
+
+def test_edge_cases(engine):
+    # empty y
+    case = H.random_case(seed=60, n=0, n_query=10)
+    got, _ = _check_counts(engine, case, 0, R=3, seed=1, philox=False)
+    assert got["iter_nranges"].sum() == 0
+    # no query: only iter_nranges
+    case = H.random_case(seed=61, n=300, n_query=0)
+    _check_counts(engine, case, 0, R=3, seed=1, philox=False)
+    # a chromosome without ranges, single range, R = 0
+    case = H.random_case(seed=62, n=1, n_seq=4, n_query=5)
+    _check_counts(engine, case, 1, R=4, seed=1, philox=False)
+    got, _ = _check_counts(engine, case, 0, R=0, seed=1, philox=True)
+    assert got["iter_totals"].size == 0
+
+
+def test_moments_and_observed(engine):
+    case = H.random_case(seed=70, n=900, n_seq=4, n_query=120, stranded=True)
+    plan, y, q, x = H.oracle_objects(case, 0)
+    H.load_engine(engine, case, 0)
+    R = 23
+    ref = O.boot_counts(plan, y, q, R, seed=5, iter0=0)
+    obs, tot = engine.count_observed()
+    cy = case["y"]
+    want_obs = H.brute_counts(case, (cy[0], cy[1], cy[2], cy[3]))
+    assert np.array_equal(obs, want_obs) and tot == want_obs.sum()
+    m = engine.run_moments(Draws(n_iter=R, seed=5), observed=obs, batch_iter=7)
+    fc = ref["feature_counts"].astype(np.int64)
+    assert np.array_equal(m["sum"], fc.sum(0))
+    assert np.array_equal(m["sumsq"], (fc * fc).sum(0))
+    assert np.array_equal(m["n_ge_observed"], (fc >= obs[None, :]).sum(0))
+    assert np.array_equal(m["iter_totals"], ref["iter_totals"])
