@@ -156,13 +156,15 @@ class BootCounts:
 def bootCounts(y: GRanges, x: GRanges, blockLength, R: int = 1, seg: GRanges | None = None,
                exclude: GRanges | None = None, excludeOption=("drop", "trim"), proportionLength: bool = True,
                type=("bootstrap", "permute"), withinChrom: bool = False, *, rng="philox", seed=None, iter0: int = 0,
-               perFeature: bool = True, device: int = 0) -> BootCounts:
+               perFeature: bool = True, device: int = 0, out: dict | None = None) -> BootCounts:
     """countOverlaps(x, bootRanges(y, ...)) per iteration, fused on the GPU."""
     eng, kind, L_b, segd = _setup(y, blockLength, seg, exclude, excludeOption, proportionLength, type, withinChrom, device)
     qi, qs, qe, qstr, qkeep = _side_arrays(x, y, "x")
     eng.set_query(qi, qs, qe, qstr if np.any(qstr) else None)
     draws = _make_draws(eng, kind, int(R), y, L_b, segd, rng, seed, iter0)
-    res = eng.run_counts(draws, want_counts=perFeature)
+    if out is not None and qkeep.size != len(x):
+        raise ValueError("out= needs every seqlevel of x to be a seqlevel of y")
+    res = eng.run_counts(draws, want_counts=perFeature, out=out)
     fc = res["feature_counts"]
     if fc is not None and qkeep.size != len(x):  # features on sequences y lacks count 0
         full = np.zeros((int(R), len(x)), np.int32)

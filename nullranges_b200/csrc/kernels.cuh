@@ -229,11 +229,12 @@ __global__ void __launch_bounds__(256) boot_count_kernel(const BootParams P) {
             q_lo = __ldg(P.query.tile_lo + it.tile);
             q_hi = __ldg(P.query.tile_hi + it.tile);
         }
-        int rows = 0;
+        int rows = 0, hits = 0;
         int overlaps = 0;
         for (int32_t i = it.lo + lane; i < it.hi; i += kWarp) {
             const int32_t st = __ldg(P.y.start + i), en = __ldg(P.y.end + i);
             int32_t s2, e2;
+            hits += (P.permute ? (st >= it.bait_start) : (en >= it.bait_start)) ? 1 : 0;
             if (!transform(P, it, st, en, s2, e2)) continue;
             const int strand = (STRANDED && P.y.strand) ? __ldg(P.y.strand + i) : 0;
             if (HAS_EXCL && excluded<STRANDED>(P.excl, it.tile, s2, e2, strand)) continue;
@@ -249,12 +250,13 @@ __global__ void __launch_bounds__(256) boot_count_kernel(const BootParams P) {
             }
         }
         rows = __reduce_add_sync(kFull, rows);
+        hits = __reduce_add_sync(kFull, hits);
         if (HAS_QUERY) overlaps = __reduce_add_sync(kFull, overlaps);
         if (lane == 0) {
             if (rows) atomicAdd(P.iter_nranges + r, (unsigned long long)rows);
             if (HAS_QUERY && overlaps) atomicAdd(P.iter_totals + r, (unsigned long long)overlaps);
             if (P.item_rows) P.item_rows[item] = rows;
-            if (P.n_hits) atomicAdd(P.n_hits, (unsigned long long)(it.hi - it.lo));
+            if (P.n_hits && hits) atomicAdd(P.n_hits, (unsigned long long)hits);
         }
     }
 }

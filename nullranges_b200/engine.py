@@ -110,10 +110,24 @@ class Engine:
         return ts, tt, bw
 
     # ---- fused counting
-    def run_counts(self, draws: Draws, want_counts: bool = True) -> dict:
+    def run_counts(self, draws: Draws, want_counts: bool = True, out: dict | None = None) -> dict:
+        """out: optional preallocated (e.g. pinned) C-contiguous result arrays keyed iter_nranges /
+        iter_totals [R] int64 and feature_counts [R, G] int32; every element is overwritten."""
         R, G = int(draws.n_iter), self.n_query
-        nr, tot = np.zeros(R, np.int64), np.zeros(R, np.int64)
-        cnt = np.zeros((R, G), np.int32) if (want_counts and G) else None
+        out = out or {}
+
+        def buf(key, shape, dtype):
+            a = out.get(key)
+            if a is None:
+                return np.empty(shape, dtype)
+            if a.shape != shape or a.dtype != dtype or not a.flags.c_contiguous:
+                raise ValueError(f"out[{key!r}] must be C-contiguous {dtype.__name__}{list(shape)}")
+            return a
+
+        nr, tot = buf("iter_nranges", (R,), np.int64), buf("iter_totals", (R,), np.int64)
+        cnt = buf("feature_counts", (R, G), np.int32) if (want_counts and G) else None
+        if not G:
+            tot[:] = 0
         st = _lib.Stats()
         d = draws.to_c()
         self._check(self._lib.nrb200_run_counts(self._h, C.byref(d), ptr(nr, C.c_int64), ptr(tot, C.c_int64), ptr(cnt, C.c_int32), C.byref(st)))

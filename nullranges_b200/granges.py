@@ -86,10 +86,20 @@ class GRanges:
         return self[self.sort_order()]
 
     def is_sorted(self) -> bool:
-        """all(y == sort(y)): equal ranges may be in any order."""
-        o = self.sort_order()
-        return bool(np.array_equal(self.seqid[o], self.seqid) and np.array_equal(self.strand[o], self.strand)
-                    and np.array_equal(self.start[o], self.start) and np.array_equal(self.end[o], self.end))
+        """all(y == sort(y)): equal ranges may be in any order.  One O(N) pass over neighbours."""
+        if len(self) < 2:
+            return True
+        keys = [self.seqid]
+        if np.any(self.strand):
+            keys.append(_STRAND_RANK[self.strand])
+        keys += [self.start, self.end]
+        undecided = np.ones(len(self) - 1, dtype=bool)  # pairs equal on every key so far
+        for k in keys:
+            a, b = k[:-1], k[1:]
+            if np.any(undecided & (a > b)):
+                return False
+            undecided &= a == b
+        return True
 
     def __repr__(self) -> str:
         return f"{type(self).__name__} with {len(self)} ranges on {len(self.seqlevels)} sequences, mcols={list(self.mcols)}"

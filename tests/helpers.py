@@ -69,6 +69,20 @@ def load_engine(eng, case, kind):
     return eng.set_plan(kind, case["L_b"], segd)
 
 
+def draw_R(plan, seed, R):
+    """R-RNG block draws for R iterations.  seg_bootstrap_noprop legitimately fails (in the reference
+    too: R/bootRanges.R:303) when a state draws no segment; such seeds are skipped."""
+    last = None
+    for k in range(50):
+        try:
+            return plan.draw_R(O.RRng(seed + 1000 * k), R)
+        except ValueError as e:
+            if "drew no segments" not in str(e):
+                raise
+            last = e
+    raise last
+
+
 def canon_rows(seqid, start, end, src, block, it):
     """Sort rows on (iter, block, src) -- the contract order made explicit."""
     o = np.lexsort((src, block, it))

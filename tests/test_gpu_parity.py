@@ -23,7 +23,7 @@ def _check_counts(eng, case, kind, R, seed, philox):
         draws = Draws(n_iter=R, rng_mode=_lib.RNG_PHILOX, seed=seed, iter0=5)
         ref = O.boot_counts(plan, y, q, R, exclude=x, seed=seed, iter0=5)
     else:
-        d = plan.draw_R(O.RRng(seed), R)
+        d = H.draw_R(plan, seed, R)
         draws = Draws(n_iter=R, rng_mode=_lib.RNG_HOST, bait_seqid=d[0], bait_start=d[1], dst_tile=d[2] if kind >= 4 else None)
         ref = O.boot_counts(plan, y, q, R, exclude=x, draws=d)
     got = eng.run_counts(draws)
@@ -53,7 +53,7 @@ def test_counts_philox_mode(engine, kind, n_excl):
 
 @pytest.mark.parametrize("kind", [1, 2, 3, 4])
 def test_unsorted_y(engine, kind):
-    case = H.random_case(seed=30 + kind, n=500, n_seq=3, n_query=50, stranded=True, n_seg=9, sort=False)
+    case = H.random_case(seed=130 + kind, n=500, n_seq=3, n_query=50, stranded=True, n_seg=6, n_states=2, sort=False)
     _check_counts(engine, case, kind, R=4, seed=9, philox=False)
 
 
@@ -64,7 +64,7 @@ def test_rows_match_oracle(engine, kind, n_excl):
     plan, y, q, x = H.oracle_objects(case, kind)
     H.load_engine(engine, case, kind)
     R = 5
-    d = plan.draw_R(O.RRng(77), R)
+    d = H.draw_R(plan, 77, R)
     draws = Draws(n_iter=R, rng_mode=_lib.RNG_HOST, bait_seqid=d[0], bait_start=d[1], dst_tile=d[2] if kind >= 4 else None)
     rows = engine.run_materialize(draws)
     it = np.repeat(np.arange(R), np.diff(rows["iter_offsets"]))
