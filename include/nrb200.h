@@ -40,9 +40,14 @@ extern "C" {
 
 typedef struct nrb200_handle nrb200_handle;
 
+/* config flags */
+#define NRB200_FLAG_FORCE_STREAM 1u /* always stream the sampled ranges (boot_count_kernel), even where
+                                       the rank path (counting by rank differences) applies; for tests
+                                       and for measuring the streaming kernel */
+
 typedef struct nrb200_config {
     int32_t device;     /* CUDA ordinal */
-    uint32_t flags;     /* reserved, 0 */
+    uint32_t flags;     /* NRB200_FLAG_* */
     void *stream;       /* cudaStream_t to launch on, or NULL = a private stream */
 } nrb200_config;
 

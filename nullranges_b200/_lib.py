@@ -16,6 +16,7 @@ i32p, i64p, i8p, dp, vp = (C.POINTER(C.c_int32), C.POINTER(C.c_int64), C.POINTER
 OK, ERR_INVALID, ERR_CUDA, ERR_STATE, ERR_UNSUPPORTED, ERR_NOMEM = 0, -1, -2, -3, -4, -5
 UNSEG_ACROSS, UNSEG_WITHIN, SEG_PROP, SEG_NOPROP, PERMUTE_WITHIN, PERMUTE_ACROSS = range(6)
 RNG_HOST, RNG_PHILOX = 0, 1
+FLAG_FORCE_STREAM = 1
 
 
 class Config(C.Structure):

@@ -2,8 +2,10 @@
 //
 // Memory layout in HBM (all int32 unless noted, canonical = sorted by (seqname, start, end)):
 //   y        : start[N] end[N] pmax[N] src[N] (+ strand[N] int8 when stranded), seq_off[C+1],
-//              two direct-address rank tables (start, running-max end), ~N/4 entries each
+//              end_sorted[N] (ends ascending within each sequence), three direct-address rank
+//              tables (start, running-max end, sorted end), ~N entries each
 //   query    : start[G] end[G] pmax[G] src[G] (+strand) + per-tile window lo/hi [B]
+//              + feature -> tiles-within-reach lists (pair_off[G+1], pair_tile[])
 //   exclude  : same shape as query
 //   plan     : tile_seq[B] tile_start[B] bait_width[B], sampler tables (int64, a few KB)
 //   draws    : validation mode only, bait_seq/bait_start(/dst_tile) [R x B]
@@ -14,6 +16,8 @@
 #include <numeric>
 #include <string>
 #include <vector>
+
+#include <cub/device/device_radix_sort.cuh>
 
 #include "../../include/nrb200.h"
 #include "kernels.cuh"
@@ -74,13 +78,16 @@ struct nrb200_handle {
     // rank tables of y
     int rank_shift = 0;
     std::vector<int64_t> rank_off;
-    DevMem rank_off_dev, max_pos_dev, rank_start, rank_pmax;
+    DevMem rank_off_dev, max_pos_dev, rank_start, rank_pmax, rank_end, end_sorted, sort_keys_a, sort_keys_b, sort_tmp;
+    uint32_t flags = 0;
 
     Plan plan;
     DevMem tile_seq, tile_start, bait_width, sampler_i64, sampler_i32;
     SamplerView sampler_view{};
     bool slices_dirty = true;
-    DevMem q_tile_lo, q_tile_hi, x_tile_lo, x_tile_hi;
+    DevMem q_tile_lo, q_tile_hi, x_tile_lo, x_tile_hi, pair_off, pair_tile;
+    int64_t n_pairs = 0;
+    bool tiles_in_bounds = false;
 
     // run scratch / results
     DevMem d_bait_seq, d_bait_start, d_dst_tile;
@@ -190,7 +197,8 @@ int load_range_set(nrb200_handle *h, RangeSet &rs, const char *what, int64_t n, 
 int build_rank_tables(nrb200_handle *h) {
     const int C = h->n_seq;
     RangeSet &y = h->y;
-    // ~4 ranges per bucket on average keeps both tables near N entries in total.
+    // ~1 range per bucket on average (2 above 4M ranges): a rank query is one table probe plus a
+    // search that rarely leaves one cache sector.
     int64_t genome = 0;
     std::vector<int32_t> max_pos(C);
     for (int c = 0; c < C; ++c) {
@@ -200,7 +208,7 @@ int build_rank_tables(nrb200_handle *h) {
         genome += max_pos[c];
     }
     int shift = 0;
-    const int64_t want = std::max<int64_t>(y.n / 4, 1024);
+    const int64_t want = std::max<int64_t>(y.n > (4 << 20) ? y.n / 2 : y.n, 1024);
     while (shift < 30 && (genome >> shift) > want) ++shift;
     h->rank_shift = shift;
     h->rank_off.assign(C + 1, 0);
@@ -211,12 +219,33 @@ int build_rank_tables(nrb200_handle *h) {
     if ((rc = upload(h, h->max_pos_dev, max_pos.data(), (size_t)C))) return rc;
     NRB_CUDA(h, h->rank_start.reserve(entries * sizeof(int32_t)));
     NRB_CUDA(h, h->rank_pmax.reserve(entries * sizeof(int32_t)));
+    NRB_CUDA(h, h->rank_end.reserve(entries * sizeof(int32_t)));
+    // ends in ascending order within each sequence: radix sort of (seqid << 32 | end)
+    NRB_CUDA(h, h->end_sorted.reserve(std::max<int64_t>(y.n, 1) * sizeof(int32_t)));
+    if (y.n > 0) {
+        int seq_bits = 1;
+        while ((1 << seq_bits) < C) ++seq_bits;
+        NRB_CUDA(h, h->sort_keys_a.reserve(y.n * 8));
+        NRB_CUDA(h, h->sort_keys_b.reserve(y.n * 8));
+        const unsigned g = (unsigned)((y.n + 255) / 256);
+        pack_end_keys_kernel<<<g, 256, 0, h->stream>>>(y.seqid.as<int32_t>(), y.end.as<int32_t>(), y.n,
+                                                       h->sort_keys_a.as<unsigned long long>());
+        size_t tmp_bytes = 0;
+        NRB_CUDA(h, cub::DeviceRadixSort::SortKeys(nullptr, tmp_bytes, h->sort_keys_a.as<unsigned long long>(),
+                                                   h->sort_keys_b.as<unsigned long long>(), y.n, 0, 32 + seq_bits, h->stream));
+        NRB_CUDA(h, h->sort_tmp.reserve(tmp_bytes));
+        NRB_CUDA(h, cub::DeviceRadixSort::SortKeys(h->sort_tmp.p, tmp_bytes, h->sort_keys_a.as<unsigned long long>(),
+                                                   h->sort_keys_b.as<unsigned long long>(), y.n, 0, 32 + seq_bits, h->stream));
+        unpack_end_keys_kernel<<<g, 256, 0, h->stream>>>(h->sort_keys_b.as<unsigned long long>(), y.n, h->end_sorted.as<int32_t>());
+    }
     const int threads = 256;
     const unsigned grid = (unsigned)((entries + threads - 1) / threads);
     build_rank_table_kernel<<<grid, threads, 0, h->stream>>>(y.start.as<int32_t>(), y.seq_off.as<int32_t>(),
                                                              h->rank_off_dev.as<int64_t>(), C, shift, h->rank_start.as<int32_t>());
     build_rank_table_kernel<<<grid, threads, 0, h->stream>>>(y.pmax.as<int32_t>(), y.seq_off.as<int32_t>(),
                                                              h->rank_off_dev.as<int64_t>(), C, shift, h->rank_pmax.as<int32_t>());
+    build_rank_table_kernel<<<grid, threads, 0, h->stream>>>(h->end_sorted.as<int32_t>(), y.seq_off.as<int32_t>(),
+                                                             h->rank_off_dev.as<int64_t>(), C, shift, h->rank_end.as<int32_t>());
     NRB_CUDA(h, cudaGetLastError());
     NRB_CUDA(h, cudaStreamSynchronize(h->stream));
     return NRB200_OK;
@@ -249,6 +278,64 @@ int build_slices(nrb200_handle *h, const RangeSet &rs, DevMem &lo_dev, DevMem &h
     return NRB200_OK;
 }
 
+// Feature -> tiles lists of the rank path: tile t is listed for feature k when the feature comes
+// within (wmax - 1) of the tile, i.e. when a range landing on the tile can overlap it.  Features
+// that start beyond their sequence end get no tiles (trim() leaves nothing there).
+int build_pairs(nrb200_handle *h) {
+    const Plan &p = h->plan;
+    const RangeSet &q = h->query;
+    const int C = h->n_seq;
+    const int64_t B = p.n_blocks(), G = q.n;
+    const int64_t reach = std::max<int32_t>(h->y.wmax, 1) - 1;
+    // tiles of each sequence in ascending start order with the running max of their ends
+    std::vector<std::vector<int32_t>> by_seq(C);
+    for (int64_t t = 0; t < B; ++t) by_seq[p.tile_seq[t]].push_back((int32_t)t);
+    std::vector<int32_t> off(G + 1, 0), tiles;
+    tiles.reserve((size_t)G + G / 4);
+    std::vector<int64_t> ts, te_max;
+    for (int c = 0; c < C; ++c) {
+        auto &v = by_seq[c];
+        std::sort(v.begin(), v.end(), [&](int32_t a, int32_t b) {
+            return p.tile_start[a] != p.tile_start[b] ? p.tile_start[a] < p.tile_start[b] : a < b;
+        });
+        ts.resize(v.size());
+        te_max.resize(v.size());
+        int64_t m = INT64_MIN;
+        for (size_t j = 0; j < v.size(); ++j) {
+            ts[j] = p.tile_start[v[j]];
+            m = std::max<int64_t>(m, ts[j] + p.bait_width[v[j]] - 1);
+            te_max[j] = m;
+        }
+        for (int32_t k = q.h_seq_off[c]; k < q.h_seq_off[c + 1]; ++k) {
+            const int64_t gs = q.h_start[k], ge = q.h_end[k];
+            if (gs <= h->seqlen[c]) {
+                int64_t j = (int64_t)(std::upper_bound(ts.begin(), ts.end(), ge + reach) - ts.begin()) - 1;
+                const size_t first = tiles.size();
+                for (; j >= 0 && te_max[j] + reach >= gs; --j)
+                    if (ts[j] + p.bait_width[v[j]] - 1 + reach >= gs) tiles.push_back(v[j]);
+                std::reverse(tiles.begin() + first, tiles.end());
+            }
+            if (tiles.size() > (size_t)INT32_MAX) return fail(h, NRB200_ERR_UNSUPPORTED, "too many (feature, tile) pairs");
+            off[k + 1] = (int32_t)tiles.size();
+        }
+    }
+    h->n_pairs = (int64_t)tiles.size();
+    int rc;
+    if ((rc = upload(h, h->pair_off, off.data(), (size_t)G + 1))) return rc;
+    if ((rc = upload(h, h->pair_tile, tiles.data(), tiles.size()))) return rc;
+    NRB_CUDA(h, cudaStreamSynchronize(h->stream));
+    return NRB200_OK;
+}
+
+// The rank path covers the bootstrap samplers without exclusion, as long as strand cannot matter
+// (y or the query is all '*').  Everything else streams the hits (boot_count_kernel).
+bool rank_path_ok(const nrb200_handle *h, bool with_query) {
+    if (h->flags & NRB200_FLAG_FORCE_STREAM) return false;
+    if (h->plan.permute() || h->excl.n > 0 || !h->tiles_in_bounds) return false;
+    if (with_query && h->y.stranded && h->query.stranded) return false;
+    return true;
+}
+
 int prepare(nrb200_handle *h) {
     if (!h->have_y) return fail(h, NRB200_ERR_STATE, "nrb200_set_ranges() has not been called");
     if (!h->have_plan) return fail(h, NRB200_ERR_STATE, "nrb200_set_plan() has not been called");
@@ -256,6 +343,10 @@ int prepare(nrb200_handle *h) {
         int rc;
         if (h->query.n && (rc = build_slices(h, h->query, h->q_tile_lo, h->q_tile_hi))) return rc;
         if (h->excl.n && (rc = build_slices(h, h->excl, h->x_tile_lo, h->x_tile_hi))) return rc;
+        h->tiles_in_bounds = true;
+        for (int64_t t = 0; t < h->plan.n_blocks(); ++t)
+            if (h->plan.tile_start[t] > h->seqlen[h->plan.tile_seq[t]]) h->tiles_in_bounds = false;
+        if (h->query.n && rank_path_ok(h, true) && (rc = build_pairs(h))) return rc;
         h->slices_dirty = false;
     }
     return NRB200_OK;
@@ -293,7 +384,8 @@ BootParams make_params(nrb200_handle *h, const nrb200_draws *d) {
     const RangeSet &y = h->y;
     P.y = RangesView{y.start.as<int32_t>(), y.end.as<int32_t>(), y.pmax.as<int32_t>(),
                      y.stranded ? y.strand.as<int8_t>() : nullptr, y.src.as<int32_t>(), y.seq_off.as<int32_t>(),
-                     h->rank_start.as<int32_t>(), h->rank_pmax.as<int32_t>(), h->rank_off_dev.as<int64_t>(),
+                     h->end_sorted.as<int32_t>(), h->rank_start.as<int32_t>(), h->rank_pmax.as<int32_t>(),
+                     h->rank_end.as<int32_t>(), h->rank_off_dev.as<int64_t>(),
                      h->max_pos_dev.as<int32_t>(), h->rank_shift};
     const RangeSet &q = h->query, &x = h->excl;
     P.query = SliceView{q.start.as<int32_t>(), q.end.as<int32_t>(), q.stranded ? q.strand.as<int8_t>() : nullptr,
@@ -326,9 +418,31 @@ void launch_count_t(nrb200_handle *h, const BootParams &P, unsigned grid) {
     boot_count_kernel<ST, HQ, HX><<<grid, 256, 0, h->stream>>>(P);
 }
 
-void launch_count(nrb200_handle *h, const BootParams &P, bool has_query) {
+constexpr int kRpt = 4;  // iterations per thread on the rank path
+
+// Returns the number of kernels launched.
+int launch_rank(nrb200_handle *h, const BootParams &P, bool has_query) {
+    if (P.n_iter == 0) return 0;
+    int launches = 0;
+    const unsigned gy = (unsigned)((P.n_iter + kRpt - 1) / kRpt);
+    if (P.n_blocks > 0) {
+        boot_block_rows_kernel<kRpt><<<dim3((unsigned)((P.n_blocks + 255) / 256), gy), 256, 0, h->stream>>>(P);
+        ++launches;
+    }
+    if (has_query) {
+        const RangeSet &q = h->query;
+        const FeatView F{q.start.as<int32_t>(), q.end.as<int32_t>(), q.src.as<int32_t>(), h->pair_off.as<int32_t>(),
+                         h->pair_tile.as<int32_t>()};
+        boot_rank_count_kernel<kRpt><<<dim3((unsigned)((P.n_query + 255) / 256), gy), 256, 0, h->stream>>>(P, F);
+        ++launches;
+    }
+    return launches;
+}
+
+int launch_count(nrb200_handle *h, const BootParams &P, bool has_query) {
+    if (rank_path_ok(h, has_query)) return launch_rank(h, P, has_query);
     const int64_t items = P.n_iter * P.n_blocks;
-    if (items == 0) return;
+    if (items == 0) return 0;
     const int64_t ctas = (items + 7) / 8;
     const unsigned grid = (unsigned)std::min<int64_t>(ctas, (int64_t)h->sm_count * 64);
     const bool st = h->y.stranded && ((has_query && h->query.stranded) || (h->excl.n && h->excl.stranded));
@@ -344,6 +458,7 @@ void launch_count(nrb200_handle *h, const BootParams &P, bool has_query) {
     case 6: launch_count_t<true, true, false>(h, P, grid); break;
     default: launch_count_t<true, true, true>(h, P, grid); break;
     }
+    return 1;
 }
 
 // Core of every counting entry point: results stay on the device.
@@ -370,7 +485,8 @@ int run_counts_core(nrb200_handle *h, const nrb200_draws *d, bool want_counts, i
             NRB_CUDA(h, h->d_counts.reserve((size_t)R * G * sizeof(int32_t)));
             counts = h->d_counts.as<int32_t>();
         }
-        NRB_CUDA(h, cudaMemsetAsync(counts, 0, (size_t)R * G * sizeof(int32_t), h->stream));
+        // the rank path writes every element; the streaming path accumulates with atomics
+        if (!rank_path_ok(h, true)) NRB_CUDA(h, cudaMemsetAsync(counts, 0, (size_t)R * G * sizeof(int32_t), h->stream));
     }
     BootParams P = make_params(h, d);
     P.iter_nranges = h->d_iter_nranges.as<unsigned long long>();
@@ -378,7 +494,8 @@ int run_counts_core(nrb200_handle *h, const nrb200_draws *d, bool want_counts, i
     P.counts = counts;
     P.n_hits = h->d_n_hits.as<unsigned long long>();
     NRB_CUDA(h, cudaEventRecord(h->ev[1], h->stream));
-    launch_count(h, P, has_query);
+    if (R > 65535LL * kRpt) return fail(h, NRB200_ERR_UNSUPPORTED, "more than 262140 iterations per call: split the run (iter0)");
+    const int launches = launch_count(h, P, has_query);
     NRB_CUDA(h, cudaGetLastError());
     NRB_CUDA(h, cudaEventRecord(h->ev[2], h->stream));
     h->res_iter = R;
@@ -394,7 +511,7 @@ int run_counts_core(nrb200_handle *h, const nrb200_draws *d, bool want_counts, i
         std::memset(stats, 0, sizeof *stats);
         stats->kernel_ms = k_ms;
         stats->total_ms = t_ms;
-        stats->n_launches = (R * h->plan.n_blocks() > 0) ? 1 : 0;
+        stats->n_launches = launches;
         stats->n_hits = (int64_t)hits;
         stats->h2d_bytes = d->rng_mode == NRB200_RNG_HOST ? R * h->plan.n_blocks() * (d->dst_tile ? 12 : 8) : 0;
     }
@@ -428,6 +545,7 @@ int nrb200_create(const nrb200_config *cfg, nrb200_handle **out) {
     NRB_CUDA(nullptr, cudaSetDevice(dev));
     nrb200_handle *h = new nrb200_handle();
     h->device = dev;
+    h->flags = cfg ? cfg->flags : 0;
     if (cfg && cfg->stream) {
         h->stream = (cudaStream_t)cfg->stream;
     } else {
@@ -712,7 +830,8 @@ int nrb200_run_materialize(nrb200_handle *h, const nrb200_draws *draws, int64_t 
     P.item_rows = h->item_rows.as<int32_t>();
     P.n_hits = h->d_n_hits.as<unsigned long long>();
     NRB_CUDA(h, cudaEventRecord(h->ev[1], h->stream));
-    launch_count(h, P, false);
+    if (R > 65535LL * kRpt) return fail(h, NRB200_ERR_UNSUPPORTED, "more than 262140 iterations per call: split the run (iter0)");
+    const int count_launches = launch_count(h, P, false);
     NRB_CUDA(h, cudaGetLastError());
     if (R > 0)
         scan_iteration_kernel<<<(unsigned)R, 256, 0, h->stream>>>(h->item_rows.as<int32_t>(), B, h->within_off.as<int32_t>());
@@ -749,7 +868,7 @@ int nrb200_run_materialize(nrb200_handle *h, const nrb200_draws *draws, int64_t 
         std::memset(stats, 0, sizeof *stats);
         stats->kernel_ms = k_ms;
         stats->total_ms = t_ms;
-        stats->n_launches = items > 0 ? 3 : 0;
+        stats->n_launches = items > 0 ? count_launches + 2 : 0;
         stats->n_hits = (int64_t)hits;
     }
     return NRB200_OK;

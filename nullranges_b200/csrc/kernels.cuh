@@ -30,8 +30,10 @@ struct RangesView {            // canonical (seqname, start, end) order
     const int32_t *src;        // index in the caller's order
     const int32_t *seq_off;    // [n_seq + 1]
     // direct-address rank tables: first index whose value is >= (bucket << shift)
+    const int32_t *end_sorted; // ends of the sequence in ascending order (rank queries)
     const int32_t *rank_start;
     const int32_t *rank_pmax;
+    const int32_t *rank_end;
     const int64_t *rank_off;   // [n_seq + 1] first table entry of each sequence
     const int32_t *max_pos;    // [n_seq] largest coordinate a table covers
     int rank_shift;
@@ -119,6 +121,24 @@ __device__ __forceinline__ void locate_block(const RangesView &y, int c, int32_t
         lo = first_ge(y.pmax, __ldg(y.rank_pmax + u), __ldg(y.rank_pmax + u + 1), ps);
     }
     if (lo > hi) lo = hi;
+}
+
+// First index of sequence c (canonical order) whose value in `vals` is >= key, for a per-sequence
+// ascending array with its direct-address table: one table probe + a search inside one bucket.
+__device__ __forceinline__ int32_t first_ge_ranked(const RangesView &y, const int32_t *__restrict__ vals,
+                                                   const int32_t *__restrict__ table, int c, int64_t key) {
+    if (key <= 0) return __ldg(y.seq_off + c);
+    if (key > __ldg(y.max_pos + c)) return __ldg(y.seq_off + c + 1);
+    const int64_t u = __ldg(y.rank_off + c) + ((int32_t)key >> y.rank_shift);
+    return first_ge(vals, __ldg(table + u), __ldg(table + u + 1), (int32_t)key);
+}
+// #{start <= a} and #{end < b} on sequence c, both as canonical-order indices (their difference
+// is the number of ranges overlapping [b, a] when b <= a).
+__device__ __forceinline__ int32_t idx_start_le(const RangesView &y, int c, int64_t a) {
+    return first_ge_ranked(y, y.start, y.rank_start, c, a + 1);
+}
+__device__ __forceinline__ int32_t idx_end_lt(const RangesView &y, int c, int64_t b) {
+    return first_ge_ranked(y, y.end_sorted, y.rank_end, c, b);
 }
 
 __device__ __forceinline__ bool strands_match(int a, int b) { return a == 0 || b == 0 || a == b; }
@@ -331,6 +351,165 @@ __global__ void __launch_bounds__(256) boot_fill_kernel(const BootParams P, cons
             out += __popc(m);
         }
     }
+}
+
+// ---- rank path: counting without streaming the ranges ------------------------------------
+//
+// For a bootstrap block sampled at [bs, be] on sequence c and moved by sh = tile_start - bs, the
+// ranges that land on feature [gs, ge] of the tile's sequence (length L) are exactly
+//     { i on c : start_i <= A  and  end_i >= Bv },   A = min(be, ge - sh, L - sh),  Bv = max(bs, gs - sh)
+// (hit of the bait block, overlap after shift(), and start + sh <= L so trim() leaves a positive
+// width; trim() never changes whether a positive-width range overlaps a feature inside [1, L]).
+// When Bv <= A that set has  #{start <= A} - #{end < Bv}  members: two rank queries.  When A < Bv
+// (the feature lies beside the tile, reached only by ranges hanging over the block edge) the
+// members all contain [A, Bv]; they are enumerated backwards from #{start <= A} under the
+// running-max-of-end bound.  Same arithmetic as the reference's findOverlaps + shift + trim +
+// countOverlaps (R/bootUnsegmented.R:133-139, :175-191; vignettes/bootRanges.Rmd:497-503).
+
+struct FeatView {              // query features in canonical order + the tiles within reach
+    const int32_t *start, *end, *src;
+    const int32_t *pair_off;   // [n_query + 1]
+    const int32_t *pair_tile;  // tile (= block) indices
+};
+
+struct Draw {
+    int seq;
+    int32_t start;
+};
+
+__device__ __forceinline__ Draw get_draw(const BootParams &P, int64_t r, int64_t b) {
+    Draw d;
+    if (P.rng_mode == NRB200_RNG_PHILOX) {
+        draw_block(P, (uint64_t)(P.iter0 + r), b, d.seq, d.start);
+    } else {
+        d.seq = __ldg(P.bait_seq + r * P.n_blocks + b);
+        d.start = __ldg(P.bait_start + r * P.n_blocks + b);
+    }
+    return d;
+}
+
+__device__ __forceinline__ int count_pair(const RangesView &y, int c, int32_t bs, int32_t width, int32_t ts,
+                                          int32_t seq_len, int32_t gs, int32_t ge) {
+    const int64_t sh = (int64_t)ts - bs;
+    const int64_t be = (int64_t)bs + width - 1;
+    const int64_t A = min(be, min((int64_t)ge, (int64_t)seq_len) - sh);
+    const int64_t Bv = max((int64_t)bs, (int64_t)gs - sh);
+    if (A < 1) return 0;
+    const int32_t ia = idx_start_le(y, c, A);
+    if (Bv <= A) return ia - idx_end_lt(y, c, Bv);
+    if (Bv > __ldg(y.max_pos + c)) return 0;
+    int n = 0;
+    const int32_t first = __ldg(y.seq_off + c);
+    for (int32_t k = ia - 1; k >= first && __ldg(y.pmax + k) >= Bv; --k) n += __ldg(y.end + k) >= Bv;
+    return n;
+}
+
+// Thread = (feature, RPT consecutive iterations).  No atomics on the count matrix, no memset: every
+// element is written exactly once.
+template <int RPT>
+__global__ void __launch_bounds__(256) boot_rank_count_kernel(const BootParams P, const FeatView F) {
+    __shared__ int warp_tot[8][RPT];
+    const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t r0 = (int64_t)blockIdx.y * RPT;
+    int cnt[RPT];
+#pragma unroll
+    for (int j = 0; j < RPT; ++j) cnt[j] = 0;
+    int32_t src = 0;
+    if (g < P.n_query) {
+        const int32_t gs = __ldg(F.start + g), ge = __ldg(F.end + g);
+        src = __ldg(F.src + g);
+        const int32_t p1 = __ldg(F.pair_off + g + 1);
+        for (int32_t p = __ldg(F.pair_off + g); p < p1; ++p) {
+            const int32_t t = __ldg(F.pair_tile + p);
+            const int32_t ts = __ldg(P.tile_start + t), width = __ldg(P.bait_width + t);
+            const int32_t seq_len = (int32_t)__ldg(P.seqlen + __ldg(P.tile_seq + t));
+#pragma unroll
+            for (int j = 0; j < RPT; ++j) {
+                if (r0 + j < P.n_iter) {
+                    const Draw d = get_draw(P, r0 + j, t);
+                    cnt[j] += count_pair(P.y, d.seq, d.start, width, ts, seq_len, gs, ge);
+                }
+            }
+        }
+        if (P.counts) {
+#pragma unroll
+            for (int j = 0; j < RPT; ++j)
+                if (r0 + j < P.n_iter) P.counts[(r0 + j) * P.n_query + src] = cnt[j];
+        }
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int j = 0; j < RPT; ++j) {
+        const int s = __reduce_add_sync(kFull, cnt[j]);
+        if (lane == 0) warp_tot[warp][j] = s;
+    }
+    __syncthreads();
+    if (threadIdx.x < RPT && r0 + threadIdx.x < P.n_iter) {
+        unsigned long long s = 0;
+        for (int w = 0; w < 8; ++w) s += (unsigned)warp_tot[w][threadIdx.x];
+        if (s) atomicAdd(P.iter_totals + r0 + threadIdx.x, s);
+    }
+}
+
+// Rows the reference's table would hold per (iteration, block), by ranks: hits of the bait block
+// minus (where the variant filters width > 0, R/bootUnsegmented.R:189) the hits shifted wholly
+// beyond the sequence end.  Requires tile_start <= seqlength for every tile (checked on the host).
+template <int RPT>
+__global__ void __launch_bounds__(256) boot_block_rows_kernel(const BootParams P) {
+    __shared__ int warp_rows[8][RPT];
+    __shared__ unsigned long long cta_hits;
+    const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t r0 = (int64_t)blockIdx.y * RPT;
+    if (threadIdx.x == 0) cta_hits = 0;
+    int rows[RPT];
+    int hits_sum = 0;
+#pragma unroll
+    for (int j = 0; j < RPT; ++j) rows[j] = 0;
+    if (b < P.n_blocks) {
+        const int32_t ts = __ldg(P.tile_start + b), width = __ldg(P.bait_width + b);
+        const int32_t seq_len = (int32_t)__ldg(P.seqlen + __ldg(P.tile_seq + b));
+#pragma unroll
+        for (int j = 0; j < RPT; ++j) {
+            if (r0 + j < P.n_iter) {
+                const Draw d = get_draw(P, r0 + j, b);
+                const int64_t be = (int64_t)d.start + width - 1;
+                const int32_t ie = idx_start_le(P.y, d.seq, be);
+                const int hits = ie - idx_end_lt(P.y, d.seq, d.start);
+                int dropped = 0;
+                if (P.drop_zero) dropped = max(0, ie - idx_start_le(P.y, d.seq, (int64_t)seq_len - ((int64_t)ts - d.start)));
+                rows[j] = hits - dropped;
+                hits_sum += hits;
+                if (P.item_rows) P.item_rows[(r0 + j) * P.n_blocks + b] = rows[j];
+            }
+        }
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int j = 0; j < RPT; ++j) {
+        const int s = __reduce_add_sync(kFull, rows[j]);
+        if (lane == 0) warp_rows[warp][j] = s;
+    }
+    hits_sum = __reduce_add_sync(kFull, hits_sum);
+    __syncthreads();
+    if (lane == 0 && hits_sum) atomicAdd(&cta_hits, (unsigned long long)hits_sum);
+    if (threadIdx.x < RPT && r0 + threadIdx.x < P.n_iter) {
+        unsigned long long s = 0;
+        for (int w = 0; w < 8; ++w) s += (unsigned)warp_rows[w][threadIdx.x];
+        if (s) atomicAdd(P.iter_nranges + r0 + threadIdx.x, s);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0 && P.n_hits && cta_hits) atomicAdd(P.n_hits, cta_hits);
+}
+
+// (seqid << 32 | end) sort keys and their unpacking: the sorted-ends array of the rank path
+__global__ void pack_end_keys_kernel(const int32_t *__restrict__ seqid, const int32_t *__restrict__ end, int64_t n,
+                                     unsigned long long *__restrict__ keys) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) keys[i] = ((unsigned long long)(unsigned)seqid[i] << 32) | (unsigned)end[i];
+}
+__global__ void unpack_end_keys_kernel(const unsigned long long *__restrict__ keys, int64_t n, int32_t *__restrict__ end_sorted) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) end_sorted[i] = (int32_t)(unsigned)keys[i];
 }
 
 // ---- index construction ---------------------------------------------------------------

@@ -42,10 +42,11 @@ class Draws:
 
 
 class Engine:
-    def __init__(self, device: int = 0, stream: int | None = None):
+    def __init__(self, device: int = 0, stream: int | None = None, force_stream: bool = False):
+        """force_stream: always stream the sampled ranges instead of counting by ranks (tests, profiling)."""
         self._lib = _lib.load()
         self._h = C.c_void_p()
-        cfg = _lib.Config(int(device), 0, C.c_void_p(stream) if stream else None)
+        cfg = _lib.Config(int(device), _lib.FLAG_FORCE_STREAM if force_stream else 0, C.c_void_p(stream) if stream else None)
         rc = self._lib.nrb200_create(C.byref(cfg), C.byref(self._h))
         if rc:
             raise EngineError(rc, self._lib.nrb200_last_error(None).decode())

@@ -17,6 +17,7 @@ def random_case(seed, n=400, n_seq=3, max_len=5000, n_query=60, n_excl=0, strand
     def ranges(m, wmax):
         sid = rng.integers(0, n_seq, m).astype(np.int32)
         w = np.ones(m, np.int64) if points else rng.integers(1, wmax + 1, m)
+        w = np.minimum(w, seqlen[sid] - 1)
         st = 1 + (rng.random(m) * (seqlen[sid] - w)).astype(np.int64)
         strand = rng.integers(0, 3, m).astype(np.int8) if stranded else None
         return sid, st.astype(np.int32), (st + w - 1).astype(np.int32), strand

@@ -113,3 +113,63 @@ def test_moments_and_observed(engine):
     assert np.array_equal(m["sumsq"], (fc * fc).sum(0))
     assert np.array_equal(m["n_ge_observed"], (fc >= obs[None, :]).sum(0))
     assert np.array_equal(m["iter_totals"], ref["iter_totals"])
+
+
+def test_features_beyond_sequence_end(engine):
+    """Query features that start or end past seqlengths: trim() keeps ranges inside [1, L]."""
+    case = H.random_case(seed=81, n=900, n_seq=3, n_query=40, wmax=400)
+    sid, st, en, sd = case["query"]
+    L = case["seqlen"][sid]
+    st = st.copy(); en = en.copy()
+    st[::4] = (L[::4] - 5).astype(np.int32); en[::4] = (L[::4] + 300).astype(np.int32)     # straddles the end
+    st[1::4] = (L[1::4] + 1).astype(np.int32); en[1::4] = (L[1::4] + 50).astype(np.int32)  # wholly beyond
+    case["query"] = (sid, st, en, sd)
+    for kind in (0, 1):
+        _check_counts(engine, case, kind, R=6, seed=4, philox=False)
+
+
+def _synth_case(y, x):
+    return {"seqlen": y.seqlengths, "y": (y.seqid, y.start, y.end, None), "query": (x.seqid, x.start, x.end, None),
+            "excl": None, "seg": None, "L_b": 500_000}
+
+
+def test_cfg1_validation_mode_full(engine):
+    """BASELINE configs[0]: 10k ranges, hg38 seqlengths, blockLength 5e5, R = 50, 20k genes; block draws
+    from R's RNG under set.seed(1): totals, [50 x 20k] counts and the whole table, bit-exact."""
+    from nullranges_b200 import synth
+    y, x = synth.uniform_ranges(10_000, seed=1), synth.genes(20_000, seed=2)
+    case = _synth_case(y, x)
+    got, ref = _check_counts(engine, case, 0, R=50, seed=1, philox=False)
+    assert got["iter_nranges"].sum() > 400_000
+    plan, yi, _, _ = H.oracle_objects(case, 0)
+    d = H.draw_R(plan, 1, 50)
+    rows = engine.run_materialize(Draws(n_iter=50, rng_mode=_lib.RNG_HOST, bait_seqid=d[0], bait_start=d[1]))
+    it = np.repeat(np.arange(50), np.diff(rows["iter_offsets"]))
+    assert np.array_equal(np.diff(rows["iter_offsets"]), got["iter_nranges"])
+    assert np.array_equal(H.canon_rows(rows["seqid"], rows["start"], rows["end"], rows["src"], rows["block"], it),
+                          H.oracle_rows(plan, yi, None, d, 50))
+
+
+def test_cfg2_full_size(engine):
+    """BASELINE configs[1] at full size: 1M ATAC-like peaks vs 20k genes, blockLength 5e5; 64 Philox
+    iterations against the oracle, then R = 1000 through size-independent properties."""
+    from nullranges_b200 import synth
+    y, x = synth.atac_peaks(1_000_000, seed=3), synth.genes(20_000, seed=2)
+    case = _synth_case(y, x)
+    plan, yi, qi, _ = H.oracle_objects(case, 0)
+    H.load_engine(engine, case, 0)
+    R = 64
+    got = engine.run_counts(Draws(n_iter=R, rng_mode=_lib.RNG_PHILOX, seed=2024, iter0=0))
+    ref = O.boot_counts(plan, yi, qi, R, seed=2024, iter0=0, nthreads=O.max_threads())
+    for k in ("iter_nranges", "iter_totals", "feature_counts"):
+        assert np.array_equal(got[k], ref[k]), k
+    # R = 1000: the sharded result equals the one-shot result (counter-based draws), row sums = totals
+    big = engine.run_counts(Draws(n_iter=1000, rng_mode=_lib.RNG_PHILOX, seed=2024, iter0=0))
+    assert np.array_equal(big["feature_counts"][:R], got["feature_counts"])
+    assert np.array_equal(big["feature_counts"].sum(axis=1), big["iter_totals"])
+    part = engine.run_counts(Draws(n_iter=300, rng_mode=_lib.RNG_PHILOX, seed=2024, iter0=700))
+    assert np.array_equal(part["feature_counts"], big["feature_counts"][700:])
+    assert np.array_equal(part["iter_nranges"], big["iter_nranges"][700:])
+    # bootstrap mean of the total tracks the observed total (block bootstrap preserves density)
+    obs, tot = engine.count_observed()
+    assert abs(big["iter_totals"].mean() / tot - 1.0) < 0.05
