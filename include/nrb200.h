@@ -66,6 +66,11 @@ int nrb200_set_ranges(nrb200_handle *h, int64_t n, int32_t n_seq, const int64_t 
                       const int32_t *seqid, const int32_t *start, const int32_t *end,
                       const int8_t *strand);
 
+/* What set_ranges found: is_sorted = the caller's order was already (seqname, start, end) -- for
+ * an unstranded y that is the all(y == sort(y)) check of R/bootUnsegmented.R:31, so the wrapper
+ * need not sort again; is_stranded = some strand is '+' or '-'; max_width = widest range. */
+int nrb200_ranges_info(const nrb200_handle *h, int32_t *is_sorted, int32_t *is_stranded, int32_t *max_width);
+
 /* x of countOverlaps(x, boots) / join_overlap_inner(x, boots)
  * (vignettes/bootRanges.Rmd:482-483, 497-503, 749).  n = 0 clears. */
 int nrb200_set_query(nrb200_handle *h, int64_t n, const int32_t *seqid, const int32_t *start,

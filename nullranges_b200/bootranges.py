@@ -95,11 +95,15 @@ def _setup(y: GRanges, blockLength, seg, exclude, excludeOption, proportionLengt
         raise ValueError("blockLength must be integer valued")
     L_b = int(blockLength)
     kind = _plan_kind(seg, proportionLength, type_, withinChrom)
-    if kind in (_lib.UNSEG_ACROSS, _lib.PERMUTE_ACROSS) and not y.is_sorted():
-        raise ValueError("all(y == GenomicRanges::sort(y)) is not TRUE")  # R/bootUnsegmented.R:31
     segd = _seg_arrays(seg, y) if seg is not None else None
     eng = get_engine(device)
-    eng.set_ranges(chr_lens, y.seqid, y.start, y.end, y.strand if np.any(y.strand) else None)
+    stranded = bool(np.any(y.strand))
+    eng.set_ranges(chr_lens, y.seqid, y.start, y.end, y.strand if stranded else None)
+    if kind in (_lib.UNSEG_ACROSS, _lib.PERMUTE_ACROSS):
+        # stopifnot(all(y == GenomicRanges::sort(y)))  R/bootUnsegmented.R:31.  For an unstranded y the
+        # engine's canonical-order test (made on the GPU while loading) is that check.
+        if not (eng.ranges_info()["sorted"] if not stranded else y.is_sorted()):
+            raise ValueError("all(y == GenomicRanges::sort(y)) is not TRUE")
     if exclude is not None:
         xi, xs, xe, xstr, _ = _side_arrays(exclude, y, "exclude")
         eng.set_exclude(xi, xs, xe, xstr if np.any(xstr) else None)

@@ -18,6 +18,7 @@
 #include <vector>
 
 #include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
 
 #include "../../include/nrb200.h"
 #include "kernels.cuh"
@@ -54,6 +55,8 @@ struct RangeSet {
     int32_t wmax = 0;
     std::vector<int32_t> h_start, h_end, h_pmax, h_src, h_seq_off;  // host mirror (kept for query/exclude)
     std::vector<int8_t> h_strand;
+    std::vector<int32_t> max_end;  // [n_seq] largest end on the sequence (INT32_MIN when empty)
+    bool sorted_input = false;     // the caller's order was already canonical
     DevMem start, end, pmax, src, strand, seq_off, seqid;
 };
 
@@ -66,6 +69,8 @@ struct nrb200_handle {
     cudaStream_t stream = nullptr;
     bool own_stream = false;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t chunk_ev[16] = {};
     std::string error;
     int sm_count = 148;
 
@@ -78,6 +83,7 @@ struct nrb200_handle {
     // rank tables of y
     int rank_shift = 0;
     std::vector<int64_t> rank_off;
+    DevMem inspect_dev;
     DevMem rank_off_dev, max_pos_dev, rank_start, rank_pmax, rank_end, end_sorted, sort_keys_a, sort_keys_b, sort_tmp;
     uint32_t flags = 0;
 
@@ -182,6 +188,10 @@ int load_range_set(nrb200_handle *h, RangeSet &rs, const char *what, int64_t n, 
             rs.h_pmax[k] = m;
         }
     }
+    rs.sorted_input = sorted;
+    rs.max_end.assign(C, INT32_MIN);
+    for (int c = 0; c < C; ++c)
+        if (rs.h_seq_off[c + 1] > rs.h_seq_off[c]) rs.max_end[c] = rs.h_pmax[rs.h_seq_off[c + 1] - 1];
     int rc;
     if ((rc = upload(h, rs.start, rs.h_start.data(), n))) return rc;
     if ((rc = upload(h, rs.end, rs.h_end.data(), n))) return rc;
@@ -194,6 +204,62 @@ int load_range_set(nrb200_handle *h, RangeSet &rs, const char *what, int64_t n, 
     return NRB200_OK;
 }
 
+// y on the fast path: the caller's arrays go to the device as they are and ONE kernel does the
+// argument checks and finds out whether they are already in canonical order (the usual case:
+// the reference insists on sort(y) for the across-chromosome samplers, R/bootUnsegmented.R:31).
+// Unsorted input falls back to the host canonicalisation above.  Returns 1 for "fall back".
+int load_y_device(nrb200_handle *h, int64_t n, const int32_t *seqid, const int32_t *start, const int32_t *end,
+                  const int8_t *strand) {
+    RangeSet &y = h->y;
+    const int C = h->n_seq;
+    if (n <= 0 || n > (int64_t)INT32_MAX - 64 || !seqid || !start || !end) return 1;  // host path words the errors
+    int rc;
+    if ((rc = upload(h, y.seqid, seqid, (size_t)n))) return rc;
+    if ((rc = upload(h, y.start, start, (size_t)n))) return rc;
+    if ((rc = upload(h, y.end, end, (size_t)n))) return rc;
+    if (strand && (rc = upload(h, y.strand, strand, (size_t)n))) return rc;
+    // scratch: InspectOut | seq_count[C] | seq_max_end[C]
+    const size_t words = 4 + 2 * (size_t)C;
+    NRB_CUDA(h, h->inspect_dev.reserve(words * 4));
+    std::vector<int32_t> init(words, 0);
+    for (int c = 0; c < C; ++c) init[4 + C + c] = INT32_MIN;
+    NRB_CUDA(h, cudaMemcpyAsync(h->inspect_dev.p, init.data(), words * 4, cudaMemcpyHostToDevice, h->stream));
+    int32_t *base = h->inspect_dev.as<int32_t>();
+    const unsigned grid = (unsigned)std::min<int64_t>((n + 255) / 256, (int64_t)h->sm_count * 8);
+    inspect_ranges_kernel<<<grid, 256, 0, h->stream>>>(y.seqid.as<int32_t>(), y.start.as<int32_t>(), y.end.as<int32_t>(),
+                                                       strand ? y.strand.as<int8_t>() : nullptr, n, C,
+                                                       reinterpret_cast<InspectOut *>(base), reinterpret_cast<unsigned *>(base + 4),
+                                                       base + 4 + C);
+    NRB_CUDA(h, cudaGetLastError());
+    std::vector<int32_t> res(words);
+    NRB_CUDA(h, cudaMemcpyAsync(res.data(), base, words * 4, cudaMemcpyDeviceToHost, h->stream));
+    NRB_CUDA(h, cudaStreamSynchronize(h->stream));
+    if (res[0] != 0 || res[1] != 0) return 1;  // invalid (host path names the problem) or unsorted
+    y.n = n;
+    y.sorted_input = true;
+    y.stranded = res[2] != 0;
+    y.wmax = res[3];
+    y.h_seq_off.assign(C + 1, 0);
+    y.max_end.assign(C, INT32_MIN);
+    for (int c = 0; c < C; ++c) {
+        y.h_seq_off[c + 1] = y.h_seq_off[c] + res[4 + c];
+        y.max_end[c] = res[4 + C + c];
+    }
+    if ((rc = upload(h, y.seq_off, y.h_seq_off.data(), (size_t)C + 1))) return rc;
+    NRB_CUDA(h, y.src.reserve(n * 4));
+    NRB_CUDA(h, y.pmax.reserve(n * 4));
+    iota_kernel<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(y.src.as<int32_t>(), n);
+    // running max of end within each sequence
+    size_t tmp_bytes = 0;
+    NRB_CUDA(h, cub::DeviceScan::InclusiveScanByKey(nullptr, tmp_bytes, y.seqid.as<int32_t>(), y.end.as<int32_t>(),
+                                                    y.pmax.as<int32_t>(), MaxOp(), n, cub::Equality(), h->stream));
+    NRB_CUDA(h, h->sort_tmp.reserve(tmp_bytes));
+    NRB_CUDA(h, cub::DeviceScan::InclusiveScanByKey(h->sort_tmp.p, tmp_bytes, y.seqid.as<int32_t>(), y.end.as<int32_t>(),
+                                                    y.pmax.as<int32_t>(), MaxOp(), n, cub::Equality(), h->stream));
+    NRB_CUDA(h, cudaStreamSynchronize(h->stream));  // seq_off upload reads y.h_seq_off
+    return NRB200_OK;
+}
+
 int build_rank_tables(nrb200_handle *h) {
     const int C = h->n_seq;
     RangeSet &y = h->y;
@@ -202,8 +268,7 @@ int build_rank_tables(nrb200_handle *h) {
     int64_t genome = 0;
     std::vector<int32_t> max_pos(C);
     for (int c = 0; c < C; ++c) {
-        int64_t m = h->seqlen[c];
-        if (y.h_seq_off[c + 1] > y.h_seq_off[c]) m = std::max<int64_t>(m, y.h_pmax[y.h_seq_off[c + 1] - 1]);
+        const int64_t m = std::max<int64_t>(h->seqlen[c], y.max_end[c]);
         max_pos[c] = (int32_t)std::min<int64_t>(m, INT32_MAX - 1);
         genome += max_pos[c];
     }
@@ -341,12 +406,15 @@ int prepare(nrb200_handle *h) {
     if (!h->have_plan) return fail(h, NRB200_ERR_STATE, "nrb200_set_plan() has not been called");
     if (h->slices_dirty) {
         int rc;
-        if (h->query.n && (rc = build_slices(h, h->query, h->q_tile_lo, h->q_tile_hi))) return rc;
-        if (h->excl.n && (rc = build_slices(h, h->excl, h->x_tile_lo, h->x_tile_hi))) return rc;
         h->tiles_in_bounds = true;
         for (int64_t t = 0; t < h->plan.n_blocks(); ++t)
             if (h->plan.tile_start[t] > h->seqlen[h->plan.tile_seq[t]]) h->tiles_in_bounds = false;
-        if (h->query.n && rank_path_ok(h, true) && (rc = build_pairs(h))) return rc;
+        if (h->excl.n && (rc = build_slices(h, h->excl, h->x_tile_lo, h->x_tile_hi))) return rc;
+        if (h->query.n) {
+            if (rank_path_ok(h, true)) rc = build_pairs(h);
+            else rc = build_slices(h, h->query, h->q_tile_lo, h->q_tile_hi);
+            if (rc) return rc;
+        }
         h->slices_dirty = false;
     }
     return NRB200_OK;
@@ -418,7 +486,8 @@ void launch_count_t(nrb200_handle *h, const BootParams &P, unsigned grid) {
     boot_count_kernel<ST, HQ, HX><<<grid, 256, 0, h->stream>>>(P);
 }
 
-constexpr int kRpt = 4;  // iterations per thread on the rank path
+constexpr int kRpt = 4;     // iterations per thread on the rank path
+constexpr int kChunks = 8;  // pipeline depth of nrb200_run_counts (compute chunk k+1 while chunk k copies out)
 
 // Returns the number of kernels launched.
 int launch_rank(nrb200_handle *h, const BootParams &P, bool has_query) {
@@ -461,8 +530,25 @@ int launch_count(nrb200_handle *h, const BootParams &P, bool has_query) {
     return 1;
 }
 
-// Core of every counting entry point: results stay on the device.
-int run_counts_core(nrb200_handle *h, const nrb200_draws *d, bool want_counts, int32_t *counts_dev_override,
+// P restricted to local iterations [r0, r0 + n).
+BootParams slice_params(const BootParams &P, int64_t r0, int64_t n) {
+    BootParams Q = P;
+    Q.n_iter = n;
+    Q.iter0 = P.iter0 + r0;
+    if (P.bait_seq) Q.bait_seq = P.bait_seq + r0 * P.n_blocks;
+    if (P.bait_start) Q.bait_start = P.bait_start + r0 * P.n_blocks;
+    if (P.dst_tile) Q.dst_tile = P.dst_tile + r0 * P.n_blocks;
+    if (P.iter_nranges) Q.iter_nranges = P.iter_nranges + r0;
+    if (P.iter_totals) Q.iter_totals = P.iter_totals + r0;
+    if (P.counts) Q.counts = P.counts + r0 * P.n_query;
+    if (P.item_rows) Q.item_rows = P.item_rows + r0 * P.n_blocks;
+    return Q;
+}
+
+// Core of every counting entry point: results stay on the device.  With host_counts set, the
+// iterations run in chunks and each chunk of the [R x G] matrix starts its way to the host
+// (copy stream) while the next chunk computes.
+int run_counts_core(nrb200_handle *h, const nrb200_draws *d, bool want_counts, int32_t *host_counts,
                     nrb200_stats *stats) {
     int rc;
     if ((rc = prepare(h))) return rc;
@@ -471,6 +557,7 @@ int run_counts_core(nrb200_handle *h, const nrb200_draws *d, bool want_counts, i
     const int64_t R = d->n_iter, G = h->query.n;
     const bool has_query = G > 0;
     want_counts = want_counts && has_query;
+    if (R > 65535LL * kRpt) return fail(h, NRB200_ERR_UNSUPPORTED, "more than 262140 iterations per call: split the run (iter0)");
     NRB_CUDA(h, h->d_iter_nranges.reserve(std::max<int64_t>(R, 1) * 8));
     NRB_CUDA(h, h->d_iter_totals.reserve(std::max<int64_t>(R, 1) * 8));
     NRB_CUDA(h, h->d_n_hits.reserve(8));
@@ -479,12 +566,8 @@ int run_counts_core(nrb200_handle *h, const nrb200_draws *d, bool want_counts, i
     NRB_CUDA(h, cudaMemsetAsync(h->d_n_hits.p, 0, 8, h->stream));
     int32_t *counts = nullptr;
     if (want_counts) {
-        if (counts_dev_override) {
-            counts = counts_dev_override;
-        } else {
-            NRB_CUDA(h, h->d_counts.reserve((size_t)R * G * sizeof(int32_t)));
-            counts = h->d_counts.as<int32_t>();
-        }
+        NRB_CUDA(h, h->d_counts.reserve((size_t)R * G * sizeof(int32_t)));
+        counts = h->d_counts.as<int32_t>();
         // the rank path writes every element; the streaming path accumulates with atomics
         if (!rank_path_ok(h, true)) NRB_CUDA(h, cudaMemsetAsync(counts, 0, (size_t)R * G * sizeof(int32_t), h->stream));
     }
@@ -494,12 +577,30 @@ int run_counts_core(nrb200_handle *h, const nrb200_draws *d, bool want_counts, i
     P.counts = counts;
     P.n_hits = h->d_n_hits.as<unsigned long long>();
     NRB_CUDA(h, cudaEventRecord(h->ev[1], h->stream));
-    if (R > 65535LL * kRpt) return fail(h, NRB200_ERR_UNSUPPORTED, "more than 262140 iterations per call: split the run (iter0)");
-    const int launches = launch_count(h, P, has_query);
-    NRB_CUDA(h, cudaGetLastError());
+    int launches = 0;
+    const bool pipelined = host_counts && counts && R > 0;
+    if (!pipelined) {
+        launches = launch_count(h, P, has_query);
+        NRB_CUDA(h, cudaGetLastError());
+    } else {
+        if (!h->copy_stream) NRB_CUDA(h, cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+        int64_t chunk = (R + kChunks - 1) / kChunks;
+        chunk = std::max<int64_t>((chunk + kRpt - 1) / kRpt * kRpt, 64);
+        int k = 0;
+        for (int64_t r0 = 0; r0 < R; r0 += chunk, ++k) {
+            const int64_t n = std::min(chunk, R - r0);
+            launches += launch_count(h, slice_params(P, r0, n), has_query);
+            NRB_CUDA(h, cudaGetLastError());
+            if (!h->chunk_ev[k]) NRB_CUDA(h, cudaEventCreateWithFlags(&h->chunk_ev[k], cudaEventDisableTiming));
+            NRB_CUDA(h, cudaEventRecord(h->chunk_ev[k], h->stream));
+            NRB_CUDA(h, cudaStreamWaitEvent(h->copy_stream, h->chunk_ev[k], 0));
+            NRB_CUDA(h, cudaMemcpyAsync(host_counts + r0 * G, counts + r0 * G, (size_t)n * G * sizeof(int32_t),
+                                        cudaMemcpyDeviceToHost, h->copy_stream));
+        }
+    }
     NRB_CUDA(h, cudaEventRecord(h->ev[2], h->stream));
     h->res_iter = R;
-    h->res_has_counts = want_counts && !counts_dev_override;
+    h->res_has_counts = want_counts;
     if (stats) {
         NRB_CUDA(h, cudaEventSynchronize(h->ev[2]));
         float k_ms = 0, t_ms = 0;
@@ -568,6 +669,12 @@ void nrb200_destroy(nrb200_handle *h) {
     cudaStreamSynchronize(h->stream);
     for (auto &ev : h->ev)
         if (ev) cudaEventDestroy(ev);
+    for (auto &ev : h->chunk_ev)
+        if (ev) cudaEventDestroy(ev);
+    if (h->copy_stream) {
+        cudaStreamSynchronize(h->copy_stream);
+        cudaStreamDestroy(h->copy_stream);
+    }
     if (h->own_stream) cudaStreamDestroy(h->stream);
     delete h;
 }
@@ -588,7 +695,9 @@ int nrb200_set_ranges(nrb200_handle *h, int64_t n, int32_t n_seq, const int64_t 
     h->seqlen.assign(seqlengths, seqlengths + n_seq);
     int rc;
     if ((rc = upload(h, h->seqlen_dev, seqlengths, (size_t)n_seq))) return rc;
-    if ((rc = load_range_set(h, h->y, "y", n, seqid, start, end, strand, true))) return rc;
+    rc = load_y_device(h, n, seqid, start, end, strand);
+    if (rc < 0) return rc;
+    if (rc == 1 && (rc = load_range_set(h, h->y, "y", n, seqid, start, end, strand, true))) return rc;
     if ((rc = build_rank_tables(h))) return rc;
     // the large host mirror of y is not needed again
     std::vector<int32_t>().swap(h->y.h_start);
@@ -598,6 +707,14 @@ int nrb200_set_ranges(nrb200_handle *h, int64_t n, int32_t n_seq, const int64_t 
     std::vector<int8_t>().swap(h->y.h_strand);
     h->have_y = true;
     h->slices_dirty = true;
+    return NRB200_OK;
+}
+
+int nrb200_ranges_info(const nrb200_handle *h, int32_t *is_sorted, int32_t *is_stranded, int32_t *max_width) {
+    if (!h || !h->have_y) return NRB200_ERR_STATE;
+    if (is_sorted) *is_sorted = h->y.sorted_input;
+    if (is_stranded) *is_stranded = h->y.stranded;
+    if (max_width) *max_width = h->y.wmax;
     return NRB200_OK;
 }
 
@@ -691,14 +808,13 @@ int nrb200_run_counts(nrb200_handle *h, const nrb200_draws *draws, int64_t *iter
                       int32_t *feature_counts, nrb200_stats *stats) {
     if (!h) return NRB200_ERR_INVALID;
     NRB_CUDA(h, cudaSetDevice(h->device));
-    int rc = run_counts_core(h, draws, feature_counts != nullptr, nullptr, stats);
+    int rc = run_counts_core(h, draws, feature_counts != nullptr, feature_counts, stats);
     if (rc) return rc;
     const int64_t R = draws->n_iter, G = h->query.n;
     if ((rc = fetch_u64_as_i64(h, h->d_iter_nranges, R, iter_nranges))) return rc;
     if ((rc = fetch_u64_as_i64(h, h->d_iter_totals, R, iter_totals))) return rc;
-    if (feature_counts && G > 0 && R > 0)
-        NRB_CUDA(h, cudaMemcpyAsync(feature_counts, h->d_counts.p, (size_t)R * G * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
     NRB_CUDA(h, cudaStreamSynchronize(h->stream));
+    if (h->copy_stream) NRB_CUDA(h, cudaStreamSynchronize(h->copy_stream));
     if (stats) stats->d2h_bytes = (iter_nranges ? R * 8 : 0) + (iter_totals ? R * 8 : 0) + (feature_counts ? R * G * 4 : 0);
     return NRB200_OK;
 }

@@ -514,6 +514,76 @@ __global__ void unpack_end_keys_kernel(const unsigned long long *__restrict__ ke
 
 // ---- index construction ---------------------------------------------------------------
 
+// One pass over the caller's y: argument checks of nrb200_set_ranges, canonical-order test,
+// strandedness, widest range, and per-sequence counts / largest end (warp-aggregated atomics).
+struct InspectOut {
+    int32_t err;       // bit mask: 1 seqid, 2 start < 1, 4 end < start, 8 end >= 2^30, 16 strand code
+    int32_t unsorted;  // some neighbour pair is out of (seqid, start, end) order
+    int32_t stranded;  // some strand is '+' or '-'
+    int32_t wmax;      // widest range
+};
+
+__global__ void __launch_bounds__(256) inspect_ranges_kernel(const int32_t *__restrict__ seqid, const int32_t *__restrict__ start,
+                                                             const int32_t *__restrict__ end, const int8_t *__restrict__ strand,
+                                                             int64_t n, int n_seq, InspectOut *__restrict__ out,
+                                                             unsigned *__restrict__ seq_count, int32_t *__restrict__ seq_max_end) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    int err = 0, unsorted = 0, stranded = 0, wmax = 0;
+    for (int64_t base = (int64_t)blockIdx.x * blockDim.x; base < n; base += stride) {  // warp-uniform trip count
+        const int64_t i = base + threadIdx.x;
+        const bool live = i < n;
+        int c = -1;
+        int32_t e = 0;
+        if (live) {
+            c = seqid[i];
+            const int32_t s = start[i];
+            e = end[i];
+            if (c < 0 || c >= n_seq) { err |= 1; c = -1; }
+            if (s < 1) err |= 2;
+            if (e < s) err |= 4;
+            if (e >= (1 << 30)) err |= 8;
+            if (strand) {
+                const int t = strand[i];
+                if (t < 0 || t > 2) err |= 16;
+                stranded |= t != 0;
+            }
+            wmax = max(wmax, e - s + 1);
+            if (i > 0) {
+                const int32_t pc = seqid[i - 1], ps = start[i - 1], pe = end[i - 1];
+                if (c < pc || (c == pc && (s < ps || (s == ps && e < pe)))) unsorted = 1;
+            }
+        }
+        const unsigned active = __ballot_sync(kFull, c >= 0);
+        if (c >= 0) {
+            const unsigned peers = __match_any_sync(active, c);
+            const int32_t m = __reduce_max_sync(peers, e);
+            if ((threadIdx.x & 31) == __ffs(peers) - 1) {
+                atomicAdd(seq_count + c, (unsigned)__popc(peers));
+                atomicMax(seq_max_end + c, m);
+            }
+        }
+    }
+    err = __reduce_or_sync(kFull, err);
+    unsorted = __reduce_or_sync(kFull, unsorted);
+    stranded = __reduce_or_sync(kFull, stranded);
+    wmax = __reduce_max_sync(kFull, wmax);
+    if ((threadIdx.x & 31) == 0) {
+        if (err) atomicOr(&out->err, err);
+        if (unsorted) atomicOr(&out->unsorted, 1);
+        if (stranded) atomicOr(&out->stranded, 1);
+        atomicMax(&out->wmax, wmax);
+    }
+}
+
+__global__ void iota_kernel(int32_t *__restrict__ v, int64_t n) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) v[i] = (int32_t)i;
+}
+
+struct MaxOp {
+    __host__ __device__ __forceinline__ int32_t operator()(int32_t a, int32_t b) const { return a > b ? a : b; }
+};
+
 // entry t of a rank table: first index of its sequence whose value is >= (bucket << shift)
 __global__ void build_rank_table_kernel(const int32_t *__restrict__ values, const int32_t *__restrict__ seq_off,
                                         const int64_t *__restrict__ rank_off, int n_seq, int shift,

@@ -76,6 +76,11 @@ class Engine:
         self.n_query = 0
         self.n_blocks = 0
 
+    def ranges_info(self) -> dict:
+        a, b, c = C.c_int32(), C.c_int32(), C.c_int32()
+        self._check(self._lib.nrb200_ranges_info(self._h, C.byref(a), C.byref(b), C.byref(c)))
+        return {"sorted": bool(a.value), "stranded": bool(b.value), "max_width": c.value}
+
     def set_query(self, seqid, start, end, strand=None):
         a, b, c, d = _i32(seqid), _i32(start), _i32(end), _i8(strand)
         self._check(self._lib.nrb200_set_query(self._h, a.size, ptr(a, C.c_int32), ptr(b, C.c_int32), ptr(c, C.c_int32), ptr(d, C.c_int8)))
