@@ -83,7 +83,7 @@ struct nrb200_handle {
     // rank tables of y
     int rank_shift = 0;
     std::vector<int64_t> rank_off;
-    DevMem inspect_dev;
+    DevMem inspect_dev, seq_info_dev, draw_tab;
     DevMem rank_off_dev, max_pos_dev, rank_start, rank_pmax, rank_end, end_sorted, sort_keys_a, sort_keys_b, sort_tmp;
     uint32_t flags = 0;
 
@@ -282,6 +282,15 @@ int build_rank_tables(nrb200_handle *h) {
     int rc;
     if ((rc = upload(h, h->rank_off_dev, h->rank_off.data(), (size_t)C + 1))) return rc;
     if ((rc = upload(h, h->max_pos_dev, max_pos.data(), (size_t)C))) return rc;
+    if (entries > (int64_t)INT32_MAX) return fail(h, NRB200_ERR_UNSUPPORTED, "rank tables exceed 2^31 entries");
+    std::vector<int32_t> seq_info(4 * (size_t)C);
+    for (int c = 0; c < C; ++c) {
+        seq_info[4 * c + 0] = y.h_seq_off[c];
+        seq_info[4 * c + 1] = y.h_seq_off[c + 1];
+        seq_info[4 * c + 2] = max_pos[c];
+        seq_info[4 * c + 3] = (int32_t)h->rank_off[c];
+    }
+    if ((rc = upload(h, h->seq_info_dev, seq_info.data(), seq_info.size()))) return rc;
     NRB_CUDA(h, h->rank_start.reserve(entries * sizeof(int32_t)));
     NRB_CUDA(h, h->rank_pmax.reserve(entries * sizeof(int32_t)));
     NRB_CUDA(h, h->rank_end.reserve(entries * sizeof(int32_t)));
@@ -454,7 +463,7 @@ BootParams make_params(nrb200_handle *h, const nrb200_draws *d) {
                      y.stranded ? y.strand.as<int8_t>() : nullptr, y.src.as<int32_t>(), y.seq_off.as<int32_t>(),
                      h->end_sorted.as<int32_t>(), h->rank_start.as<int32_t>(), h->rank_pmax.as<int32_t>(),
                      h->rank_end.as<int32_t>(), h->rank_off_dev.as<int64_t>(),
-                     h->max_pos_dev.as<int32_t>(), h->rank_shift};
+                     h->max_pos_dev.as<int32_t>(), h->seq_info_dev.as<int4>(), h->rank_shift};
     const RangeSet &q = h->query, &x = h->excl;
     P.query = SliceView{q.start.as<int32_t>(), q.end.as<int32_t>(), q.stranded ? q.strand.as<int8_t>() : nullptr,
                         q.src.as<int32_t>(), h->q_tile_lo.as<int32_t>(), h->q_tile_hi.as<int32_t>()};
@@ -487,6 +496,8 @@ void launch_count_t(nrb200_handle *h, const BootParams &P, unsigned grid) {
 }
 
 constexpr int kRpt = 4;     // iterations per thread on the rank path
+constexpr int64_t kMaxBatch = 2048;  // iterations per launch (multiple of kRpt; gridDim.y and scratch stay small)
+constexpr int kChunkEvents = 16;
 constexpr int kChunks = 8;  // pipeline depth of nrb200_run_counts (compute chunk k+1 while chunk k copies out)
 
 // Returns the number of kernels launched.
@@ -557,7 +568,6 @@ int run_counts_core(nrb200_handle *h, const nrb200_draws *d, bool want_counts, i
     const int64_t R = d->n_iter, G = h->query.n;
     const bool has_query = G > 0;
     want_counts = want_counts && has_query;
-    if (R > 65535LL * kRpt) return fail(h, NRB200_ERR_UNSUPPORTED, "more than 262140 iterations per call: split the run (iter0)");
     NRB_CUDA(h, h->d_iter_nranges.reserve(std::max<int64_t>(R, 1) * 8));
     NRB_CUDA(h, h->d_iter_totals.reserve(std::max<int64_t>(R, 1) * 8));
     NRB_CUDA(h, h->d_n_hits.reserve(8));
@@ -579,21 +589,27 @@ int run_counts_core(nrb200_handle *h, const nrb200_draws *d, bool want_counts, i
     NRB_CUDA(h, cudaEventRecord(h->ev[1], h->stream));
     int launches = 0;
     const bool pipelined = host_counts && counts && R > 0;
-    if (!pipelined) {
-        launches = launch_count(h, P, has_query);
-        NRB_CUDA(h, cudaGetLastError());
-    } else {
+    // Iterations go in batches: bounded draw-table scratch on the rank path and, when the matrix
+    // is wanted on the host, chunk k copies out (copy stream) while chunk k + 1 computes.
+    int64_t chunk = kMaxBatch;
+    if (pipelined) {
         if (!h->copy_stream) NRB_CUDA(h, cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
-        int64_t chunk = (R + kChunks - 1) / kChunks;
-        chunk = std::max<int64_t>((chunk + kRpt - 1) / kRpt * kRpt, 64);
-        int k = 0;
-        for (int64_t r0 = 0; r0 < R; r0 += chunk, ++k) {
-            const int64_t n = std::min(chunk, R - r0);
-            launches += launch_count(h, slice_params(P, r0, n), has_query);
-            NRB_CUDA(h, cudaGetLastError());
-            if (!h->chunk_ev[k]) NRB_CUDA(h, cudaEventCreateWithFlags(&h->chunk_ev[k], cudaEventDisableTiming));
-            NRB_CUDA(h, cudaEventRecord(h->chunk_ev[k], h->stream));
-            NRB_CUDA(h, cudaStreamWaitEvent(h->copy_stream, h->chunk_ev[k], 0));
+        chunk = std::min<int64_t>(kMaxBatch, std::max<int64_t>(((R + kChunks - 1) / kChunks + kRpt - 1) / kRpt * kRpt, 64));
+    }
+    if (rank_path_ok(h, has_query) && has_query) {
+        NRB_CUDA(h, h->draw_tab.reserve((size_t)std::min(chunk, std::max<int64_t>(R, 1)) * h->plan.n_blocks() * sizeof(int2)));
+        P.draw_tab = h->draw_tab.as<int2>();
+    }
+    int k = 0;
+    for (int64_t r0 = 0; r0 < R; r0 += chunk, ++k) {
+        const int64_t n = std::min(chunk, R - r0);
+        launches += launch_count(h, slice_params(P, r0, n), has_query);
+        NRB_CUDA(h, cudaGetLastError());
+        if (pipelined) {
+            cudaEvent_t &ev = h->chunk_ev[k % kChunkEvents];
+            if (!ev) NRB_CUDA(h, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+            NRB_CUDA(h, cudaEventRecord(ev, h->stream));
+            NRB_CUDA(h, cudaStreamWaitEvent(h->copy_stream, ev, 0));
             NRB_CUDA(h, cudaMemcpyAsync(host_counts + r0 * G, counts + r0 * G, (size_t)n * G * sizeof(int32_t),
                                         cudaMemcpyDeviceToHost, h->copy_stream));
         }
@@ -946,9 +962,11 @@ int nrb200_run_materialize(nrb200_handle *h, const nrb200_draws *draws, int64_t 
     P.item_rows = h->item_rows.as<int32_t>();
     P.n_hits = h->d_n_hits.as<unsigned long long>();
     NRB_CUDA(h, cudaEventRecord(h->ev[1], h->stream));
-    if (R > 65535LL * kRpt) return fail(h, NRB200_ERR_UNSUPPORTED, "more than 262140 iterations per call: split the run (iter0)");
-    const int count_launches = launch_count(h, P, false);
-    NRB_CUDA(h, cudaGetLastError());
+    int count_launches = 0;
+    for (int64_t r0 = 0; r0 < R; r0 += kMaxBatch) {
+        count_launches += launch_count(h, slice_params(P, r0, std::min(kMaxBatch, R - r0)), false);
+        NRB_CUDA(h, cudaGetLastError());
+    }
     if (R > 0)
         scan_iteration_kernel<<<(unsigned)R, 256, 0, h->stream>>>(h->item_rows.as<int32_t>(), B, h->within_off.as<int32_t>());
     NRB_CUDA(h, cudaGetLastError());

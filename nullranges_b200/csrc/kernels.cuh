@@ -36,6 +36,7 @@ struct RangesView {            // canonical (seqname, start, end) order
     const int32_t *rank_end;
     const int64_t *rank_off;   // [n_seq + 1] first table entry of each sequence
     const int32_t *max_pos;    // [n_seq] largest coordinate a table covers
+    const int4 *seq_info;      // [n_seq] {seq_off[c], seq_off[c+1], max_pos[c], rank_off[c]} in one 16-byte load
     int rank_shift;
 };
 
@@ -76,7 +77,8 @@ struct BootParams {
     unsigned long long *iter_nranges, *iter_totals;  // [n_iter]
     int32_t *counts;          // [n_iter x n_query], caller's query order, or nullptr
     int32_t *item_rows;       // [n_iter x n_blocks] surviving rows per item, or nullptr
-    unsigned long long *n_hits;  // total ranges streamed (byte-model H)
+    unsigned long long *n_hits;  // total ranges sampled (byte-model H)
+    int2 *draw_tab;           // [n_iter x n_blocks] {bait seq, bait start}: rank path scratch
 };
 
 // ---- searches -------------------------------------------------------------------------
@@ -123,22 +125,29 @@ __device__ __forceinline__ void locate_block(const RangesView &y, int c, int32_t
     if (lo > hi) lo = hi;
 }
 
-// First index of sequence c (canonical order) whose value in `vals` is >= key, for a per-sequence
-// ascending array with its direct-address table: one table probe + a search inside one bucket.
-__device__ __forceinline__ int32_t first_ge_ranked(const RangesView &y, const int32_t *__restrict__ vals,
-                                                   const int32_t *__restrict__ table, int c, int64_t key) {
-    if (key <= 0) return __ldg(y.seq_off + c);
-    if (key > __ldg(y.max_pos + c)) return __ldg(y.seq_off + c + 1);
-    const int64_t u = __ldg(y.rank_off + c) + ((int32_t)key >> y.rank_shift);
-    return first_ge(vals, __ldg(table + u), __ldg(table + u + 1), (int32_t)key);
+// First index of a sequence (described by si = seq_info[c]) whose value in the per-sequence
+// ascending array `vals` is >= key: one probe of the direct-address table, then a short scan
+// (buckets hold about one value); crowded buckets finish with a binary search.
+__device__ __forceinline__ int32_t first_ge_ranked(const int32_t *__restrict__ vals, const int32_t *__restrict__ table,
+                                                   int rank_shift, const int4 si, int32_t key) {
+    if (key <= 0) return si.x;
+    if (key > si.z) return si.y;
+    const int32_t u = si.w + (key >> rank_shift);
+    int32_t a = __ldg(table + u);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        if (a >= si.y || __ldg(vals + a) >= key) return a;
+        ++a;
+    }
+    return first_ge(vals, a, __ldg(table + u + 1), key);
 }
-// #{start <= a} and #{end < b} on sequence c, both as canonical-order indices (their difference
-// is the number of ranges overlapping [b, a] when b <= a).
-__device__ __forceinline__ int32_t idx_start_le(const RangesView &y, int c, int64_t a) {
-    return first_ge_ranked(y, y.start, y.rank_start, c, a + 1);
+// #{start <= a} and #{end < b} on a sequence, both as canonical-order indices (their difference
+// is the number of ranges overlapping [b, a] when b <= a).  a, b are below 2^31 - 1.
+__device__ __forceinline__ int32_t idx_start_le(const RangesView &y, const int4 si, int32_t a) {
+    return first_ge_ranked(y.start, y.rank_start, y.rank_shift, si, a + 1);
 }
-__device__ __forceinline__ int32_t idx_end_lt(const RangesView &y, int c, int64_t b) {
-    return first_ge_ranked(y, y.end_sorted, y.rank_end, c, b);
+__device__ __forceinline__ int32_t idx_end_lt(const RangesView &y, const int4 si, int32_t b) {
+    return first_ge_ranked(y.end_sorted, y.rank_end, y.rank_shift, si, b);
 }
 
 __device__ __forceinline__ bool strands_match(int a, int b) { return a == 0 || b == 0 || a == b; }
@@ -147,7 +156,7 @@ __device__ __forceinline__ bool strands_match(int a, int b) { return a == 0 || b
 
 // Production-mode draw of block b of global iteration `iter` (same arithmetic on the host:
 // philox.cuh).  Returns the sequence and start the block is sampled from.
-__device__ __forceinline__ void draw_block(const BootParams &P, uint64_t iter, int64_t b, int &c, int32_t &s) {
+__device__ __forceinline__ void draw_block(const BootParams &P, uint64_t iter, int64_t b, int &c, int &s) {
     const SamplerView &S = P.sampler;
     const Philox128 u = philox_draw(P.seed, iter, (uint32_t)b, 0u);
     if (S.kind == NRB200_UNSEG_ACROSS) {
@@ -372,40 +381,27 @@ struct FeatView {              // query features in canonical order + the tiles 
     const int32_t *pair_tile;  // tile (= block) indices
 };
 
-struct Draw {
-    int seq;
-    int32_t start;
-};
-
-__device__ __forceinline__ Draw get_draw(const BootParams &P, int64_t r, int64_t b) {
-    Draw d;
-    if (P.rng_mode == NRB200_RNG_PHILOX) {
-        draw_block(P, (uint64_t)(P.iter0 + r), b, d.seq, d.start);
-    } else {
-        d.seq = __ldg(P.bait_seq + r * P.n_blocks + b);
-        d.start = __ldg(P.bait_start + r * P.n_blocks + b);
-    }
-    return d;
-}
-
-__device__ __forceinline__ int count_pair(const RangesView &y, int c, int32_t bs, int32_t width, int32_t ts,
+// All coordinates are below 2^30 and widths at most 2^30, so every sum below fits int32.
+__device__ __forceinline__ int count_pair(const RangesView &y, int2 draw, int32_t width, int32_t ts,
                                           int32_t seq_len, int32_t gs, int32_t ge) {
-    const int64_t sh = (int64_t)ts - bs;
-    const int64_t be = (int64_t)bs + width - 1;
-    const int64_t A = min(be, min((int64_t)ge, (int64_t)seq_len) - sh);
-    const int64_t Bv = max((int64_t)bs, (int64_t)gs - sh);
+    const int32_t bs = draw.y;
+    const int32_t sh = ts - bs;
+    const int32_t be = bs + (width - 1);
+    const int32_t A = min(be, min(ge, seq_len) - sh);
+    const int32_t Bv = max(bs, gs - sh);
     if (A < 1) return 0;
-    const int32_t ia = idx_start_le(y, c, A);
-    if (Bv <= A) return ia - idx_end_lt(y, c, Bv);
-    if (Bv > __ldg(y.max_pos + c)) return 0;
+    const int4 si = __ldg(y.seq_info + draw.x);
+    const int32_t ia = idx_start_le(y, si, A);
+    if (Bv <= A) return ia - idx_end_lt(y, si, Bv);
+    if (Bv > si.z) return 0;
     int n = 0;
-    const int32_t first = __ldg(y.seq_off + c);
-    for (int32_t k = ia - 1; k >= first && __ldg(y.pmax + k) >= Bv; --k) n += __ldg(y.end + k) >= Bv;
+    for (int32_t k = ia - 1; k >= si.x && __ldg(y.pmax + k) >= Bv; --k) n += __ldg(y.end + k) >= Bv;
     return n;
 }
 
-// Thread = (feature, RPT consecutive iterations).  No atomics on the count matrix, no memset: every
-// element is written exactly once.
+// Thread = (feature, RPT consecutive iterations); the block draws come from the table the
+// block-rows kernel wrote.  No atomics on the count matrix, no memset: every element is written
+// exactly once.
 template <int RPT>
 __global__ void __launch_bounds__(256) boot_rank_count_kernel(const BootParams P, const FeatView F) {
     __shared__ int warp_tot[8][RPT];
@@ -414,22 +410,18 @@ __global__ void __launch_bounds__(256) boot_rank_count_kernel(const BootParams P
     int cnt[RPT];
 #pragma unroll
     for (int j = 0; j < RPT; ++j) cnt[j] = 0;
-    int32_t src = 0;
     if (g < P.n_query) {
         const int32_t gs = __ldg(F.start + g), ge = __ldg(F.end + g);
-        src = __ldg(F.src + g);
+        const int32_t src = __ldg(F.src + g);
         const int32_t p1 = __ldg(F.pair_off + g + 1);
         for (int32_t p = __ldg(F.pair_off + g); p < p1; ++p) {
             const int32_t t = __ldg(F.pair_tile + p);
             const int32_t ts = __ldg(P.tile_start + t), width = __ldg(P.bait_width + t);
             const int32_t seq_len = (int32_t)__ldg(P.seqlen + __ldg(P.tile_seq + t));
+            const int2 *__restrict__ tab = P.draw_tab + r0 * P.n_blocks + t;
 #pragma unroll
-            for (int j = 0; j < RPT; ++j) {
-                if (r0 + j < P.n_iter) {
-                    const Draw d = get_draw(P, r0 + j, t);
-                    cnt[j] += count_pair(P.y, d.seq, d.start, width, ts, seq_len, gs, ge);
-                }
-            }
+            for (int j = 0; j < RPT; ++j)
+                if (r0 + j < P.n_iter) cnt[j] += count_pair(P.y, __ldg(tab + j * P.n_blocks), width, ts, seq_len, gs, ge);
         }
         if (P.counts) {
 #pragma unroll
@@ -451,9 +443,11 @@ __global__ void __launch_bounds__(256) boot_rank_count_kernel(const BootParams P
     }
 }
 
-// Rows the reference's table would hold per (iteration, block), by ranks: hits of the bait block
-// minus (where the variant filters width > 0, R/bootUnsegmented.R:189) the hits shifted wholly
-// beyond the sequence end.  Requires tile_start <= seqlength for every tile (checked on the host).
+// Per (iteration, block): draws the block (Philox) or reads the caller's draw, records it in the
+// draw table for the count kernel, and counts by ranks the rows the reference's table would hold:
+// hits of the bait block minus (where the variant filters width > 0, R/bootUnsegmented.R:189) the
+// hits shifted wholly beyond the sequence end.  Requires tile_start <= seqlength for every tile
+// (checked on the host).
 template <int RPT>
 __global__ void __launch_bounds__(256) boot_block_rows_kernel(const BootParams P) {
     __shared__ int warp_rows[8][RPT];
@@ -471,12 +465,19 @@ __global__ void __launch_bounds__(256) boot_block_rows_kernel(const BootParams P
 #pragma unroll
         for (int j = 0; j < RPT; ++j) {
             if (r0 + j < P.n_iter) {
-                const Draw d = get_draw(P, r0 + j, b);
-                const int64_t be = (int64_t)d.start + width - 1;
-                const int32_t ie = idx_start_le(P.y, d.seq, be);
-                const int hits = ie - idx_end_lt(P.y, d.seq, d.start);
+                int2 d;
+                if (P.rng_mode == NRB200_RNG_PHILOX) {
+                    draw_block(P, (uint64_t)(P.iter0 + r0 + j), b, d.x, d.y);
+                } else {
+                    d.x = __ldg(P.bait_seq + (r0 + j) * P.n_blocks + b);
+                    d.y = __ldg(P.bait_start + (r0 + j) * P.n_blocks + b);
+                }
+                if (P.draw_tab) P.draw_tab[(r0 + j) * P.n_blocks + b] = d;
+                const int4 si = __ldg(P.y.seq_info + d.x);
+                const int32_t ie = idx_start_le(P.y, si, d.y + (width - 1));
+                const int hits = ie - idx_end_lt(P.y, si, d.y);
                 int dropped = 0;
-                if (P.drop_zero) dropped = max(0, ie - idx_start_le(P.y, d.seq, (int64_t)seq_len - ((int64_t)ts - d.start)));
+                if (P.drop_zero) dropped = max(0, ie - idx_start_le(P.y, si, seq_len - (ts - d.y)));
                 rows[j] = hits - dropped;
                 hits_sum += hits;
                 if (P.item_rows) P.item_rows[(r0 + j) * P.n_blocks + b] = rows[j];
