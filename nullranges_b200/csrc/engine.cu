@@ -91,7 +91,7 @@ struct nrb200_handle {
     DevMem tile_seq, tile_start, bait_width, sampler_i64, sampler_i32;
     SamplerView sampler_view{};
     bool slices_dirty = true;
-    DevMem q_tile_lo, q_tile_hi, x_tile_lo, x_tile_hi, pair_off, pair_tile;
+    DevMem q_tile_lo, q_tile_hi, x_tile_lo, x_tile_hi, pair_off, pair_tile, f_start, f_end, f_src;
     int64_t n_pairs = 0;
     bool tiles_in_bounds = false;
 
@@ -277,7 +277,7 @@ int build_rank_tables(nrb200_handle *h) {
     while (shift < 30 && (genome >> shift) > want) ++shift;
     h->rank_shift = shift;
     h->rank_off.assign(C + 1, 0);
-    for (int c = 0; c < C; ++c) h->rank_off[c + 1] = h->rank_off[c] + ((int64_t)max_pos[c] >> shift) + 2;
+    for (int c = 0; c < C; ++c) h->rank_off[c + 1] = h->rank_off[c] + ((int64_t)max_pos[c] >> shift) + 3;  // +1: probes read entry u + 1
     const int64_t entries = h->rank_off[C];
     int rc;
     if ((rc = upload(h, h->rank_off_dev, h->rank_off.data(), (size_t)C + 1))) return rc;
@@ -394,9 +394,27 @@ int build_pairs(nrb200_handle *h) {
         }
     }
     h->n_pairs = (int64_t)tiles.size();
+    // Visit order of the count kernel: features grouped by how many tiles they reach (stable, so
+    // neighbours in a group are neighbours on the genome): the lanes of a warp then loop equally often.
+    std::vector<int32_t> order(G);
+    std::iota(order.begin(), order.end(), 0);
+    std::stable_sort(order.begin(), order.end(), [&](int32_t a, int32_t b) { return off[a + 1] - off[a] < off[b + 1] - off[b]; });
+    std::vector<int32_t> f_start(G), f_end(G), f_src(G), f_off(G + 1, 0), f_tiles;
+    f_tiles.reserve(tiles.size());
+    for (int64_t i = 0; i < G; ++i) {
+        const int32_t k = order[i];
+        f_start[i] = q.h_start[k];
+        f_end[i] = q.h_end[k];
+        f_src[i] = q.h_src[k];
+        f_tiles.insert(f_tiles.end(), tiles.begin() + off[k], tiles.begin() + off[k + 1]);
+        f_off[i + 1] = (int32_t)f_tiles.size();
+    }
     int rc;
-    if ((rc = upload(h, h->pair_off, off.data(), (size_t)G + 1))) return rc;
-    if ((rc = upload(h, h->pair_tile, tiles.data(), tiles.size()))) return rc;
+    if ((rc = upload(h, h->f_start, f_start.data(), (size_t)G))) return rc;
+    if ((rc = upload(h, h->f_end, f_end.data(), (size_t)G))) return rc;
+    if ((rc = upload(h, h->f_src, f_src.data(), (size_t)G))) return rc;
+    if ((rc = upload(h, h->pair_off, f_off.data(), (size_t)G + 1))) return rc;
+    if ((rc = upload(h, h->pair_tile, f_tiles.data(), f_tiles.size()))) return rc;
     NRB_CUDA(h, cudaStreamSynchronize(h->stream));
     return NRB200_OK;
 }
@@ -506,12 +524,11 @@ int launch_rank(nrb200_handle *h, const BootParams &P, bool has_query) {
     int launches = 0;
     const unsigned gy = (unsigned)((P.n_iter + kRpt - 1) / kRpt);
     if (P.n_blocks > 0) {
-        boot_block_rows_kernel<kRpt><<<dim3((unsigned)((P.n_blocks + 255) / 256), gy), 256, 0, h->stream>>>(P);
+        boot_block_rows_kernel<1><<<dim3((unsigned)((P.n_blocks + 255) / 256), (unsigned)P.n_iter), 256, 0, h->stream>>>(P);
         ++launches;
     }
     if (has_query) {
-        const RangeSet &q = h->query;
-        const FeatView F{q.start.as<int32_t>(), q.end.as<int32_t>(), q.src.as<int32_t>(), h->pair_off.as<int32_t>(),
+        const FeatView F{h->f_start.as<int32_t>(), h->f_end.as<int32_t>(), h->f_src.as<int32_t>(), h->pair_off.as<int32_t>(),
                          h->pair_tile.as<int32_t>()};
         boot_rank_count_kernel<kRpt><<<dim3((unsigned)((P.n_query + 255) / 256), gy), 256, 0, h->stream>>>(P, F);
         ++launches;

@@ -126,20 +126,21 @@ __device__ __forceinline__ void locate_block(const RangesView &y, int c, int32_t
 }
 
 // First index of a sequence (described by si = seq_info[c]) whose value in the per-sequence
-// ascending array `vals` is >= key: one probe of the direct-address table, then a short scan
-// (buckets hold about one value); crowded buckets finish with a binary search.
+// ascending array `vals` is >= key.  Branch-free in the common case so that several queries can be
+// in flight at once: clamp the key into the table's domain, probe the direct-address table (two
+// adjacent words), read the first three values of the bucket together, count those below the key.
+// Buckets hold about one value; a bucket with more than three finishes with a binary search.
 __device__ __forceinline__ int32_t first_ge_ranked(const int32_t *__restrict__ vals, const int32_t *__restrict__ table,
                                                    int rank_shift, const int4 si, int32_t key) {
-    if (key <= 0) return si.x;
-    if (key > si.z) return si.y;
+    key = min(max(key, 0), si.z + 1);  // key <= 0 -> si.x and key > max_pos -> si.y fall out of the table
     const int32_t u = si.w + (key >> rank_shift);
-    int32_t a = __ldg(table + u);
-#pragma unroll
-    for (int k = 0; k < 3; ++k) {
-        if (a >= si.y || __ldg(vals + a) >= key) return a;
-        ++a;
-    }
-    return first_ge(vals, a, __ldg(table + u + 1), key);
+    const int32_t a = __ldg(table + u), b = __ldg(table + u + 1);
+    const int32_t v0 = a < b ? __ldg(vals + a) : INT32_MAX;
+    const int32_t v1 = a + 1 < b ? __ldg(vals + a + 1) : INT32_MAX;
+    const int32_t v2 = a + 2 < b ? __ldg(vals + a + 2) : INT32_MAX;
+    const int32_t r = a + (v0 < key) + (v1 < key) + (v2 < key);
+    if (v2 < key) return first_ge(vals, a + 3, b, key);  // rare: crowded bucket
+    return r;
 }
 // #{start <= a} and #{end < b} on a sequence, both as canonical-order indices (their difference
 // is the number of ranges overlapping [b, a] when b <= a).  a, b are below 2^31 - 1.
@@ -389,24 +390,28 @@ __device__ __forceinline__ int count_pair(const RangesView &y, int2 draw, int32_
     const int32_t be = bs + (width - 1);
     const int32_t A = min(be, min(ge, seq_len) - sh);
     const int32_t Bv = max(bs, gs - sh);
-    if (A < 1) return 0;
     const int4 si = __ldg(y.seq_info + draw.x);
-    const int32_t ia = idx_start_le(y, si, A);
-    if (Bv <= A) return ia - idx_end_lt(y, si, Bv);
-    if (Bv > si.z) return 0;
+    const int32_t ia = idx_start_le(y, si, A);   // A < 1 gives si.x
+    const int32_t ib = idx_end_lt(y, si, Bv);
+    if (Bv <= A) return A < 1 ? 0 : ia - ib;
+    // rare: the feature lies beside the tile; members contain [A, Bv]
+    if (A < 1 || Bv > si.z) return 0;
     int n = 0;
     for (int32_t k = ia - 1; k >= si.x && __ldg(y.pmax + k) >= Bv; --k) n += __ldg(y.end + k) >= Bv;
     return n;
 }
 
 // Thread = (feature, RPT consecutive iterations); the block draws come from the table the
-// block-rows kernel wrote.  No atomics on the count matrix, no memset: every element is written
-// exactly once.
+// block-rows kernel wrote.  The RPT evaluations are independent and unrolled, so their table
+// probes overlap.  Features are visited in F's order (grouped by tile count, so a warp's lanes
+// loop the same number of times).  No atomics on the count matrix, no memset: every element is
+// written exactly once.
 template <int RPT>
 __global__ void __launch_bounds__(256) boot_rank_count_kernel(const BootParams P, const FeatView F) {
     __shared__ int warp_tot[8][RPT];
     const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t r0 = (int64_t)blockIdx.y * RPT;
+    const bool full = r0 + RPT <= P.n_iter;
     int cnt[RPT];
 #pragma unroll
     for (int j = 0; j < RPT; ++j) cnt[j] = 0;
@@ -419,9 +424,16 @@ __global__ void __launch_bounds__(256) boot_rank_count_kernel(const BootParams P
             const int32_t ts = __ldg(P.tile_start + t), width = __ldg(P.bait_width + t);
             const int32_t seq_len = (int32_t)__ldg(P.seqlen + __ldg(P.tile_seq + t));
             const int2 *__restrict__ tab = P.draw_tab + r0 * P.n_blocks + t;
+            if (full) {
+                int2 d[RPT];
 #pragma unroll
-            for (int j = 0; j < RPT; ++j)
-                if (r0 + j < P.n_iter) cnt[j] += count_pair(P.y, __ldg(tab + j * P.n_blocks), width, ts, seq_len, gs, ge);
+                for (int j = 0; j < RPT; ++j) d[j] = __ldg(tab + j * P.n_blocks);
+#pragma unroll
+                for (int j = 0; j < RPT; ++j) cnt[j] += count_pair(P.y, d[j], width, ts, seq_len, gs, ge);
+            } else {
+                for (int j = 0; j < RPT; ++j)
+                    if (r0 + j < P.n_iter) cnt[j] += count_pair(P.y, __ldg(tab + j * P.n_blocks), width, ts, seq_len, gs, ge);
+            }
         }
         if (P.counts) {
 #pragma unroll

@@ -1,0 +1,120 @@
+"""CPU: host-side logic of the product (no GPU, no compute calls) and the C-ABI surface."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+from nullranges_b200 import GRanges, RRng, _lib, samplers, set_seed
+from nullranges_b200 import bootranges as BR
+from oracle import oracle as O
+from tests import helpers as H
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    header = open(os.path.join(ROOT, "include", "nrb200.h")).read()
+    declared = set(re.findall(r"\b(nrb200_[a-z0-9_]+)\s*\(", header))
+    assert len(declared) >= 25
+    lib = ctypes.CDLL(_lib.so_path() if os.path.exists(_lib.so_path()) else _lib.load()._name)
+    for name in declared:
+        assert hasattr(lib, name), f"{name} is declared in include/nrb200.h but not exported"
+    assert declared == {n for n, _, _ in _lib.SYMBOLS}, "ctypes table and header disagree"
+    # nothing else leaks out of the library (built with -fvisibility=hidden)
+    import subprocess
+    out = subprocess.run(["nm", "-D", "--defined-only", _lib.so_path()], capture_output=True, text=True).stdout
+    exported = {l.split()[-1] for l in out.splitlines() if " T " in l}
+    assert {e for e in exported if not e.startswith("nrb200_")} <= {"_init", "_fini"}
+
+
+def test_create_fails_loudly_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    from nullranges_b200 import Engine, EngineError
+    with pytest.raises(EngineError) as e:
+        Engine(0)
+    assert e.value.code == _lib.ERR_CUDA and "no CPU path" in str(e.value)
+    y = GRanges(["chr1"] * 2, [1, 20], width=[5, 5], seqlengths={"chr1": 100})
+    with pytest.raises(EngineError):
+        BR.bootRanges(y, 10)  # the product never falls back to the CPU
+
+
+def test_host_rng_matches_oracle_rng():
+    a, b = RRng(99), O.RRng(99)
+    assert np.array_equal(a.runif(50), b.runif(50))
+    assert np.array_equal(a.sample(17), b.sample(17))
+    p = np.arange(1, 301, dtype=np.float64)
+    assert np.array_equal(a.sample(300, 500, True, p), b.sample(300, 500, True, p))   # Walker alias branch
+    assert np.array_equal(a.sample(40, 500, True, p[:40]), b.sample(40, 500, True, p[:40]))  # inversion branch
+    assert np.array_equal(a.sample(1000, 64, True), b.sample(1000, 64, True))
+    assert np.array_equal(a.runif(6, [1, 2, 3], [1, 5, 3]), b.runif(6, [1.0, 2, 3], [1.0, 5, 3]))
+
+
+@pytest.mark.parametrize("kind", range(6))
+def test_python_samplers_follow_the_reference_draw_order(kind):
+    """nullranges_b200/samplers.py (what the R wrapper does with R's own RNG) against the oracle's draws."""
+    case = H.random_case(seed=500 + kind, n=10, n_seq=4, n_query=0, n_seg=12, n_states=2)
+    plan = O.Plan(kind, case["seqlen"], case["L_b"], case["seg"] if kind in (2, 3) else None)
+    L_s = case["seqlen"].astype(np.float64)
+    seg = case["seg"]
+    for seed in (1, 2, 3):
+        try:
+            want = plan.draw_R(O.RRng(seed), 3)
+        except ValueError:
+            continue
+        rng = RRng(seed)
+        for r in range(3):
+            if kind == 0:
+                d = samplers.unseg_bootstrap_across_chrom(rng, L_s, case["L_b"])
+            elif kind == 1:
+                d = samplers.unseg_bootstrap_within_chrom(rng, L_s, case["L_b"])
+            elif kind == 2:
+                d = samplers.seg_bootstrap_prop(rng, seg["chrom"], seg["start"], seg["end"], seg["state"], case["L_b"], L_s)
+            elif kind == 3:
+                d = samplers.seg_bootstrap_noprop(rng, seg["chrom"], seg["start"], seg["end"], seg["state"], case["L_b"])
+            elif kind == 4:
+                d = samplers.unseg_permute_within_chrom(rng, L_s, case["L_b"], plan.tile_start)
+            else:
+                d = samplers.unseg_permute_across_chrom(rng, plan.tile_chrom, plan.tile_start)
+            assert np.array_equal(d[0], want[0][r]) and np.array_equal(d[1], want[1][r])
+            if kind >= 4:
+                assert np.array_equal(d[2], want[2][r])
+
+
+def test_granges_sort_semantics():
+    g = GRanges(["b", "a", "a", "a"], [5, 9, 3, 3], width=[2, 1, 4, 4], strand=["*", "-", "*", "+"], seqlevels=["a", "b"],
+                seqlengths=[50, 50], score=[1, 2, 3, 4])
+    s = g.sort()
+    # seqlevel order, then strand + < - < *, then start
+    assert s.seqnames.tolist() == ["a", "a", "a", "b"] and s.mcols["score"].tolist() == [4, 2, 3, 1]
+    assert s.is_sorted() and not g.is_sorted()
+    assert GRanges(["a"], [1], end=[3], seqlengths={"a": 9}).width.tolist() == [3]
+    with pytest.raises(ValueError):
+        GRanges(["zz"], [1], width=[1], seqlevels=["a"])
+
+
+def test_front_end_argument_checks():
+    y = GRanges(["chr1"] * 3, [1, 20, 40], width=[5, 5, 5], seqlengths={"chr1": 100})
+    with pytest.raises(ValueError, match="is.na"):
+        BR._setup(GRanges(["chr1"], [1], width=[2], seqlevels=["chr1"]), 10, None, None, "drop", True, "bootstrap", False, 0)
+    with pytest.raises(ValueError, match="should be one of"):
+        BR._setup(y, 10, None, None, "keep", True, "bootstrap", False, 0)
+    with pytest.raises(ValueError, match="should be one of"):
+        BR._setup(y, 10, None, None, "drop", True, "shuffle", False, 0)
+    with pytest.raises(ValueError, match="state"):
+        BR._seg_arrays(GRanges(["chr1"], [1], end=[100], seqlengths={"chr1": 100}), y)
+    assert BR._plan_kind(None, True, "bootstrap", False) == _lib.UNSEG_ACROSS
+    assert BR._plan_kind(None, True, "permute", True) == _lib.PERMUTE_WITHIN
+    assert BR._plan_kind(y, False, "permute", True) == _lib.SEG_NOPROP  # seg given: type / withinChrom ignored
+    assert BR._match_arg(("drop", "trim"), ("drop", "trim"), "excludeOption") == "drop"
+
+
+def test_set_seed_stream_is_shared_across_calls():
+    set_seed(5)
+    from nullranges_b200.rrng import global_rng
+    a = global_rng().runif(2)
+    b = global_rng().runif(2)
+    assert np.array_equal(np.concatenate([a, b]), O.RRng(5).runif(4))

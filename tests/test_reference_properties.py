@@ -1,0 +1,130 @@
+"""The reference's own tests (tests/testthat/test_boot.R, test_trim_exclude.R), translated.
+
+They pin structural properties only.  Each runs twice: against the oracle on the CPU, and --
+marked gpu -- against the product through its bootRanges() front end, reading like the R tests.
+"""
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+
+SEQLEN = [300, 450, 200]                                             # test_boot.R:15
+CHROM = np.repeat([0, 1, 2], [4, 5, 2])                              # :7
+START = np.array([1, 101, 121, 201, 101, 201, 216, 231, 401, 1, 101])  # :9-11
+WIDTH = np.array([20, 5, 5, 30, 20, 5, 5, 5, 30, 80, 40])            # :12-14
+L_B, R = 100, 5
+SEG = {"chrom": np.array([0, 0, 1, 1, 2]), "start": np.array([1, 151, 1, 226, 1]), "end": np.array([150, 300, 225, 450, 200]),
+       "state": np.array([1, 2, 1, 2, 1])}                           # :80-82
+
+
+def _oracle_boot(kind, seed=1, seg=None):
+    plan = O.Plan(kind, SEQLEN, L_B, seg)
+    y = O.Index(3, CHROM, START, START + WIDTH - 1)
+    d = plan.draw_R(O.RRng(seed), R)
+    return [O.iteration_rows(plan, y, d[0][r], d[1][r], d[2][r]) for r in range(R)]
+
+
+def _state_at(chrom, pos):
+    for c, s, e, st in zip(SEG["chrom"], SEG["start"], SEG["end"], SEG["state"]):
+        if c == chrom and s <= pos <= e:
+            return st
+    return 0
+
+
+def _check_permute_within(iters):      # test_boot.R:27-35
+    for chrom_new, origin in iters:
+        assert np.array_equal(np.bincount(origin, minlength=3), [4, 5, 2])
+        assert np.array_equal(np.bincount(chrom_new, minlength=3), [4, 5, 2])
+
+
+def _check_bootstrap_within(iters):    # :41-48: one chromosome of origin per output chromosome
+    for chrom_new, origin in iters:
+        assert np.array_equal(chrom_new, origin)
+
+
+def _check_permute_across(iters):      # :54-61
+    assert [c.size for c, _ in iters] == [11] * R
+
+
+def _check_bootstrap_across(iters):    # :67-74
+    assert not all(c.size == 11 for c, _ in iters)
+
+
+def test_oracle_unsegmented_properties():
+    pick = lambda rows: [(r["chrom"], CHROM[r["src"]]) for r in rows]
+    _check_permute_within(pick(_oracle_boot(O.PERMUTE_WITHIN)))
+    _check_bootstrap_within(pick(_oracle_boot(O.UNSEG_WITHIN)))
+    _check_permute_across(pick(_oracle_boot(O.PERMUTE_ACROSS)))
+    _check_bootstrap_across(pick(_oracle_boot(O.UNSEG_ACROSS)))
+
+
+def test_oracle_segmented_same_state_rate():   # :86-96
+    same = total = 0
+    for rows in _oracle_boot(O.SEG_PROP, seg=SEG):
+        for c, s, e, src in zip(rows["chrom"], rows["start"], rows["end"], rows["src"]):
+            orig = _state_at(CHROM[src], START[src])
+            # join_overlap_left(seg): one row per overlapped segment
+            for sc, ss, se, st in zip(SEG["chrom"], SEG["start"], SEG["end"], SEG["state"]):
+                if sc == c and ss <= e and se >= s:
+                    total += 1
+                    same += int(st == orig)
+    assert same / total > 0.5
+
+
+# ---- the same, through the product ------------------------------------------------------------
+
+def _gr():
+    from nullranges_b200 import GRanges
+    names = np.array(["chr1", "chr2", "chr3"])[CHROM]
+    return GRanges(names, START, width=WIDTH, seqlengths={"chr1": 300, "chr2": 450, "chr3": 200}, chrom=CHROM + 1)
+
+
+def _per_iter(br):
+    return [(br.seqid[br.iter == r], br.mcols["chrom"][br.iter == r] - 1) for r in range(1, R + 1)]
+
+
+@pytest.mark.gpu
+def test_product_unsegmented_properties():
+    from nullranges_b200 import bootRanges, set_seed
+    gr = _gr()
+    set_seed(1)
+    _check_permute_within(_per_iter(bootRanges(gr, L_B, R, type="permute", withinChrom=True)))
+    set_seed(1)
+    _check_bootstrap_within(_per_iter(bootRanges(gr, L_B, R, type="bootstrap", withinChrom=True)))
+    set_seed(1)
+    _check_permute_across(_per_iter(bootRanges(gr, L_B, R, type="permute", withinChrom=False)))
+    set_seed(1)
+    br = bootRanges(gr, L_B, R, type="bootstrap", withinChrom=False)
+    _check_bootstrap_across(_per_iter(br))
+    # SURVEY 8c worked example: rows per iteration under set.seed(1)
+    assert np.bincount(br.iter, minlength=R + 1)[1:].tolist() == [14, 12, 17, 17, 10]
+    assert "block" not in br.mcols and "iter" in br.mcols      # R/bootRanges.R:122-126
+
+
+@pytest.mark.gpu
+def test_product_segmented_same_state_rate():
+    from nullranges_b200 import GRanges, bootRanges, set_seed
+    seg = GRanges(np.array(["chr1", "chr2", "chr3"])[SEG["chrom"]], SEG["start"], end=SEG["end"],
+                  seqlengths={"chr1": 300, "chr2": 450, "chr3": 200}, state=SEG["state"])
+    gr = _gr()
+    gr.mcols["state"] = np.array([_state_at(c, s) for c, s in zip(CHROM, START)])
+    set_seed(1)
+    br = bootRanges(gr, L_B, R, seg)
+    same = total = 0
+    for c, s, e, orig in zip(br.seqid, br.start, br.end, br.mcols["state"]):
+        for sc, ss, se, st in zip(SEG["chrom"], SEG["start"], SEG["end"], SEG["state"]):
+            if sc == c and ss <= e and se >= s:
+                total += 1
+                same += int(st == orig)
+    assert same / total > 0.5
+
+
+@pytest.mark.gpu
+def test_product_roxygen_example():
+    """R/bootRanges.R:65-69 with the SURVEY 8c worked values."""
+    from nullranges_b200 import GRanges, bootRanges, set_seed
+    set_seed(1)
+    gr = GRanges(["chr1"] * 5, np.arange(5) * 10 + 1, width=[5] * 5, seqlengths={"chr1": 50})
+    br = bootRanges(gr, blockLength=10, storeBlockLength=True)
+    assert br.start.tolist() == [5, 13, 25, 36, 39, 49] and br.end.tolist() == [9, 17, 29, 40, 43, 50]
+    assert br.iter.tolist() == [1] * 6 and br.mcols["blockLength"].tolist() == [10] * 6
