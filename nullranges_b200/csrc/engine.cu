@@ -12,6 +12,7 @@
 //   results  : iter_nranges[R] iter_totals[R] (uint64), counts[R x G]
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <numeric>
 #include <string>
@@ -86,6 +87,10 @@ struct nrb200_handle {
     DevMem inspect_dev, seq_info_dev, draw_tab;
     DevMem rank_off_dev, max_pos_dev, rank_start, rank_pmax, rank_end, end_sorted, sort_keys_a, sort_keys_b, sort_tmp;
     uint32_t flags = 0;
+    // tuning knobs (environment, read at create): NRB200_RPT iterations per thread of the rank count
+    // kernel, NRB200_MINB its min CTAs/SM, NRB200_TABLE_MULT rank-table entries per range
+    int tune_rpt = 1, tune_minb = 1;
+    double tune_table_mult = 4.0;
 
     Plan plan;
     DevMem tile_seq, tile_start, bait_width, sampler_i64, sampler_i32;
@@ -263,8 +268,9 @@ int load_y_device(nrb200_handle *h, int64_t n, const int32_t *seqid, const int32
 int build_rank_tables(nrb200_handle *h) {
     const int C = h->n_seq;
     RangeSet &y = h->y;
-    // ~1 range per bucket on average (2 above 4M ranges): a rank query is one table probe plus a
-    // search that rarely leaves one cache sector.
+    // 2-4 buckets per range (about 1 above 4M ranges, to keep the tables inside the L2): a rank
+    // query is one table probe plus at most three values read together; clustered ranges seldom
+    // put more than three values into a bucket.
     int64_t genome = 0;
     std::vector<int32_t> max_pos(C);
     for (int c = 0; c < C; ++c) {
@@ -273,7 +279,7 @@ int build_rank_tables(nrb200_handle *h) {
         genome += max_pos[c];
     }
     int shift = 0;
-    const int64_t want = std::max<int64_t>(y.n > (4 << 20) ? y.n / 2 : y.n, 1024);
+    const int64_t want = std::max<int64_t>(std::min<int64_t>((int64_t)(h->tune_table_mult * y.n), std::max<int64_t>(y.n, 8 << 20)), 1024);
     while (shift < 30 && (genome >> shift) > want) ++shift;
     h->rank_shift = shift;
     h->rank_off.assign(C + 1, 0);
@@ -283,6 +289,8 @@ int build_rank_tables(nrb200_handle *h) {
     if ((rc = upload(h, h->rank_off_dev, h->rank_off.data(), (size_t)C + 1))) return rc;
     if ((rc = upload(h, h->max_pos_dev, max_pos.data(), (size_t)C))) return rc;
     if (entries > (int64_t)INT32_MAX) return fail(h, NRB200_ERR_UNSUPPORTED, "rank tables exceed 2^31 entries");
+    for (int c = 0; c < C; ++c)  // packed table entries hold a per-sequence index in 29 bits
+        if (y.h_seq_off[c + 1] - y.h_seq_off[c] >= (1 << 29)) return fail(h, NRB200_ERR_UNSUPPORTED, "more than 2^29 ranges on one sequence");
     std::vector<int32_t> seq_info(4 * (size_t)C);
     for (int c = 0; c < C; ++c) {
         seq_info[4 * c + 0] = y.h_seq_off[c];
@@ -315,11 +323,11 @@ int build_rank_tables(nrb200_handle *h) {
     const int threads = 256;
     const unsigned grid = (unsigned)((entries + threads - 1) / threads);
     build_rank_table_kernel<<<grid, threads, 0, h->stream>>>(y.start.as<int32_t>(), y.seq_off.as<int32_t>(),
-                                                             h->rank_off_dev.as<int64_t>(), C, shift, h->rank_start.as<int32_t>());
+                                                             h->rank_off_dev.as<int64_t>(), C, shift, h->rank_start.as<uint32_t>());
     build_rank_table_kernel<<<grid, threads, 0, h->stream>>>(y.pmax.as<int32_t>(), y.seq_off.as<int32_t>(),
-                                                             h->rank_off_dev.as<int64_t>(), C, shift, h->rank_pmax.as<int32_t>());
+                                                             h->rank_off_dev.as<int64_t>(), C, shift, h->rank_pmax.as<uint32_t>());
     build_rank_table_kernel<<<grid, threads, 0, h->stream>>>(h->end_sorted.as<int32_t>(), y.seq_off.as<int32_t>(),
-                                                             h->rank_off_dev.as<int64_t>(), C, shift, h->rank_end.as<int32_t>());
+                                                             h->rank_off_dev.as<int64_t>(), C, shift, h->rank_end.as<uint32_t>());
     NRB_CUDA(h, cudaGetLastError());
     NRB_CUDA(h, cudaStreamSynchronize(h->stream));
     return NRB200_OK;
@@ -479,9 +487,8 @@ BootParams make_params(nrb200_handle *h, const nrb200_draws *d) {
     const RangeSet &y = h->y;
     P.y = RangesView{y.start.as<int32_t>(), y.end.as<int32_t>(), y.pmax.as<int32_t>(),
                      y.stranded ? y.strand.as<int8_t>() : nullptr, y.src.as<int32_t>(), y.seq_off.as<int32_t>(),
-                     h->end_sorted.as<int32_t>(), h->rank_start.as<int32_t>(), h->rank_pmax.as<int32_t>(),
-                     h->rank_end.as<int32_t>(), h->rank_off_dev.as<int64_t>(),
-                     h->max_pos_dev.as<int32_t>(), h->seq_info_dev.as<int4>(), h->rank_shift};
+                     h->end_sorted.as<int32_t>(), h->rank_start.as<uint32_t>(), h->rank_pmax.as<uint32_t>(),
+                     h->rank_end.as<uint32_t>(), h->seq_info_dev.as<int4>(), h->rank_shift};
     const RangeSet &q = h->query, &x = h->excl;
     P.query = SliceView{q.start.as<int32_t>(), q.end.as<int32_t>(), q.stranded ? q.strand.as<int8_t>() : nullptr,
                         q.src.as<int32_t>(), h->q_tile_lo.as<int32_t>(), h->q_tile_hi.as<int32_t>()};
@@ -513,7 +520,6 @@ void launch_count_t(nrb200_handle *h, const BootParams &P, unsigned grid) {
     boot_count_kernel<ST, HQ, HX><<<grid, 256, 0, h->stream>>>(P);
 }
 
-constexpr int kRpt = 4;     // iterations per thread on the rank path
 constexpr int64_t kMaxBatch = 2048;  // iterations per launch (multiple of kRpt; gridDim.y and scratch stay small)
 constexpr int kChunkEvents = 16;
 constexpr int kChunks = 8;  // pipeline depth of nrb200_run_counts (compute chunk k+1 while chunk k copies out)
@@ -522,7 +528,8 @@ constexpr int kChunks = 8;  // pipeline depth of nrb200_run_counts (compute chun
 int launch_rank(nrb200_handle *h, const BootParams &P, bool has_query) {
     if (P.n_iter == 0) return 0;
     int launches = 0;
-    const unsigned gy = (unsigned)((P.n_iter + kRpt - 1) / kRpt);
+    const int rpt = h->tune_rpt;
+    const unsigned gy = (unsigned)((P.n_iter + rpt - 1) / rpt);
     if (P.n_blocks > 0) {
         boot_block_rows_kernel<1><<<dim3((unsigned)((P.n_blocks + 255) / 256), (unsigned)P.n_iter), 256, 0, h->stream>>>(P);
         ++launches;
@@ -530,7 +537,17 @@ int launch_rank(nrb200_handle *h, const BootParams &P, bool has_query) {
     if (has_query) {
         const FeatView F{h->f_start.as<int32_t>(), h->f_end.as<int32_t>(), h->f_src.as<int32_t>(), h->pair_off.as<int32_t>(),
                          h->pair_tile.as<int32_t>()};
-        boot_rank_count_kernel<kRpt><<<dim3((unsigned)((P.n_query + 255) / 256), gy), 256, 0, h->stream>>>(P, F);
+        const dim3 grid((unsigned)((P.n_query + 255) / 256), gy);
+        switch (rpt * 10 + h->tune_minb) {
+        case 11: boot_rank_count_kernel<1, 1><<<grid, 256, 0, h->stream>>>(P, F); break;
+        case 21: boot_rank_count_kernel<2, 1><<<grid, 256, 0, h->stream>>>(P, F); break;
+        case 24: boot_rank_count_kernel<2, 4><<<grid, 256, 0, h->stream>>>(P, F); break;
+        case 41: boot_rank_count_kernel<4, 1><<<grid, 256, 0, h->stream>>>(P, F); break;
+        case 43: boot_rank_count_kernel<4, 3><<<grid, 256, 0, h->stream>>>(P, F); break;
+        case 44: boot_rank_count_kernel<4, 4><<<grid, 256, 0, h->stream>>>(P, F); break;
+        case 81: boot_rank_count_kernel<8, 1><<<grid, 256, 0, h->stream>>>(P, F); break;
+        default: boot_rank_count_kernel<1, 1><<<grid, 256, 0, h->stream>>>(P, F); break;
+        }
         ++launches;
     }
     return launches;
@@ -611,7 +628,7 @@ int run_counts_core(nrb200_handle *h, const nrb200_draws *d, bool want_counts, i
     int64_t chunk = kMaxBatch;
     if (pipelined) {
         if (!h->copy_stream) NRB_CUDA(h, cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
-        chunk = std::min<int64_t>(kMaxBatch, std::max<int64_t>(((R + kChunks - 1) / kChunks + kRpt - 1) / kRpt * kRpt, 64));
+        chunk = std::min<int64_t>(kMaxBatch, std::max<int64_t>(((R + kChunks - 1) / kChunks + 7) / 8 * 8, 64));
     }
     if (rank_path_ok(h, has_query) && has_query) {
         NRB_CUDA(h, h->draw_tab.reserve((size_t)std::min(chunk, std::max<int64_t>(R, 1)) * h->plan.n_blocks() * sizeof(int2)));
@@ -680,6 +697,10 @@ int nrb200_create(const nrb200_config *cfg, nrb200_handle **out) {
     nrb200_handle *h = new nrb200_handle();
     h->device = dev;
     h->flags = cfg ? cfg->flags : 0;
+    if (const char *e = getenv("NRB200_RPT")) h->tune_rpt = atoi(e);
+    if (const char *e = getenv("NRB200_MINB")) h->tune_minb = atoi(e);
+    if (const char *e = getenv("NRB200_TABLE_MULT")) h->tune_table_mult = atof(e);
+    if (h->tune_rpt != 1 && h->tune_rpt != 2 && h->tune_rpt != 4 && h->tune_rpt != 8) h->tune_rpt = 1;
     if (cfg && cfg->stream) {
         h->stream = (cudaStream_t)cfg->stream;
     } else {

@@ -29,13 +29,10 @@ struct RangesView {            // canonical (seqname, start, end) order
     const int8_t *strand;      // nullptr when every strand is '*'
     const int32_t *src;        // index in the caller's order
     const int32_t *seq_off;    // [n_seq + 1]
-    // direct-address rank tables: first index whose value is >= (bucket << shift)
-    const int32_t *end_sorted; // ends of the sequence in ascending order (rank queries)
-    const int32_t *rank_start;
-    const int32_t *rank_pmax;
-    const int32_t *rank_end;
-    const int64_t *rank_off;   // [n_seq + 1] first table entry of each sequence
-    const int32_t *max_pos;    // [n_seq] largest coordinate a table covers
+        const int32_t *end_sorted; // ends of the sequence in ascending order (rank queries)
+    const uint32_t *rank_start;  // packed rank tables, see "direct-address rank tables" below
+    const uint32_t *rank_pmax;
+    const uint32_t *rank_end;
     const int4 *seq_info;      // [n_seq] {seq_off[c], seq_off[c+1], max_pos[c], rank_off[c]} in one 16-byte load
     int rank_shift;
 };
@@ -100,48 +97,48 @@ __device__ __forceinline__ int32_t first_ge(const int32_t *__restrict__ v, int32
     return a;
 }
 
+// ---- direct-address rank tables --------------------------------------------------------
+// One table per ascending per-sequence array (start, running-max end, sorted end).  Entry u of a
+// sequence describes bucket u = [u << shift, (u + 1) << shift):
+//     entry = (first << 3) | min(count, 7)
+// first = index, relative to the sequence's first range, of the first value >= u << shift;
+// count = values inside the bucket.  One 4-byte probe therefore yields both ends of the bucket
+// (count == 7 means "7 or more": the next entry holds the end).
+constexpr int kRankCountBits = 3;
+constexpr int32_t kRankCountCap = (1 << kRankCountBits) - 1;
+
+__device__ __forceinline__ int32_t rank_clamp_key(int32_t key, const int4 si) {
+    return min(max(key, 0), si.z + 1);  // key <= 0 -> si.x and key > max_pos -> si.y fall out of the table
+}
+
+// First index of a sequence (si = seq_info[c]) whose value in `vals` is >= key.  Branch-free in the
+// common case: one table probe, then the first three values of the bucket read together.
+__device__ __forceinline__ int32_t first_ge_ranked(const int32_t *__restrict__ vals, const uint32_t *__restrict__ table,
+                                                   int rank_shift, const int4 si, int32_t key) {
+    key = rank_clamp_key(key, si);
+    const int32_t u = si.w + (key >> rank_shift);
+    const uint32_t e = __ldg(table + u);
+    const int32_t a = si.x + (int32_t)(e >> kRankCountBits), n = (int32_t)(e & kRankCountCap);
+    const int32_t v0 = n > 0 ? __ldg(vals + a) : INT32_MAX;
+    const int32_t v1 = n > 1 ? __ldg(vals + a + 1) : INT32_MAX;
+    const int32_t v2 = n > 2 ? __ldg(vals + a + 2) : INT32_MAX;
+    if (v2 < key) {  // rare: more than three values in the bucket and the first three are below the key
+        const int32_t b = n < kRankCountCap ? a + n : si.x + (int32_t)(__ldg(table + u + 1) >> kRankCountBits);
+        return first_ge(vals, a + 3, b, key);
+    }
+    return a + (v0 < key) + (v1 < key) + (v2 < key);
+}
+
 // Hits of the bait block [s, e] on sequence c are a window [lo, hi) of the canonical order:
-// hi = #{start <= e}, lo = first index whose running-max end reaches s.  Both come from one
-// rank-table probe plus a search confined to a single bucket.
+// hi = #{start <= e}, lo = first index whose running-max end reaches s.
 __device__ __forceinline__ void locate_block(const RangesView &y, int c, int32_t s, int64_t e,
                                              int32_t &lo, int32_t &hi) {
-    const int32_t seq_end = __ldg(y.seq_off + c + 1);
-    const int32_t max_pos = __ldg(y.max_pos + c);
-    const int64_t base = __ldg(y.rank_off + c);
-    if (e >= max_pos) {
-        hi = seq_end;
-    } else {
-        const int32_t pe = e < 0 ? 0 : (int32_t)e;
-        const int64_t u = base + (pe >> y.rank_shift);
-        hi = first_gt(y.start, __ldg(y.rank_start + u), __ldg(y.rank_start + u + 1), pe);
-    }
-    if (s > max_pos) {
-        lo = seq_end;
-    } else {
-        const int32_t ps = s < 0 ? 0 : s;
-        const int64_t u = base + (ps >> y.rank_shift);
-        lo = first_ge(y.pmax, __ldg(y.rank_pmax + u), __ldg(y.rank_pmax + u + 1), ps);
-    }
+    const int4 si = __ldg(y.seq_info + c);
+    hi = first_ge_ranked(y.start, y.rank_start, y.rank_shift, si, (int32_t)min(e, (int64_t)INT32_MAX - 1) + 1);
+    lo = first_ge_ranked(y.pmax, y.rank_pmax, y.rank_shift, si, s);
     if (lo > hi) lo = hi;
 }
 
-// First index of a sequence (described by si = seq_info[c]) whose value in the per-sequence
-// ascending array `vals` is >= key.  Branch-free in the common case so that several queries can be
-// in flight at once: clamp the key into the table's domain, probe the direct-address table (two
-// adjacent words), read the first three values of the bucket together, count those below the key.
-// Buckets hold about one value; a bucket with more than three finishes with a binary search.
-__device__ __forceinline__ int32_t first_ge_ranked(const int32_t *__restrict__ vals, const int32_t *__restrict__ table,
-                                                   int rank_shift, const int4 si, int32_t key) {
-    key = min(max(key, 0), si.z + 1);  // key <= 0 -> si.x and key > max_pos -> si.y fall out of the table
-    const int32_t u = si.w + (key >> rank_shift);
-    const int32_t a = __ldg(table + u), b = __ldg(table + u + 1);
-    const int32_t v0 = a < b ? __ldg(vals + a) : INT32_MAX;
-    const int32_t v1 = a + 1 < b ? __ldg(vals + a + 1) : INT32_MAX;
-    const int32_t v2 = a + 2 < b ? __ldg(vals + a + 2) : INT32_MAX;
-    const int32_t r = a + (v0 < key) + (v1 < key) + (v2 < key);
-    if (v2 < key) return first_ge(vals, a + 3, b, key);  // rare: crowded bucket
-    return r;
-}
 // #{start <= a} and #{end < b} on a sequence, both as canonical-order indices (their difference
 // is the number of ranges overlapping [b, a] when b <= a).  a, b are below 2^31 - 1.
 __device__ __forceinline__ int32_t idx_start_le(const RangesView &y, const int4 si, int32_t a) {
@@ -382,36 +379,93 @@ struct FeatView {              // query features in canonical order + the tiles 
     const int32_t *pair_tile;  // tile (= block) indices
 };
 
-// All coordinates are below 2^30 and widths at most 2^30, so every sum below fits int32.
-__device__ __forceinline__ int count_pair(const RangesView &y, int2 draw, int32_t width, int32_t ts,
-                                          int32_t seq_len, int32_t gs, int32_t ge) {
+// One (feature, tile, iteration) evaluation, split into stages so that the RPT evaluations a thread
+// owns can be issued stage by stage: all table probes first, then all value reads, so that the
+// dependent-load chain (draw -> sequence info -> table -> values) is paid once per thread, not per
+// evaluation.  All coordinates are below 2^30 and widths at most 2^30: every sum fits int32.
+struct PairProbe {
+    int4 si;                   // seq_info of the bait sequence
+    int32_t A, Bv;             // count = #{start <= A and end >= Bv}
+    int32_t key_a, key_b;      // clamped search keys (A + 1 in starts, Bv in sorted ends)
+    int32_t a0, an, b0, bn;    // bucket start and (capped) size in start[] and end_sorted[]
+};
+
+__device__ __forceinline__ void pair_keys(PairProbe &q, int2 draw, int32_t width, int32_t ts, int32_t seq_len,
+                                          int32_t gs, int32_t ge, int rank_shift, int32_t &ua, int32_t &ub) {
     const int32_t bs = draw.y;
     const int32_t sh = ts - bs;
-    const int32_t be = bs + (width - 1);
-    const int32_t A = min(be, min(ge, seq_len) - sh);
-    const int32_t Bv = max(bs, gs - sh);
-    const int4 si = __ldg(y.seq_info + draw.x);
-    const int32_t ia = idx_start_le(y, si, A);   // A < 1 gives si.x
-    const int32_t ib = idx_end_lt(y, si, Bv);
-    if (Bv <= A) return A < 1 ? 0 : ia - ib;
+    q.A = min(bs + (width - 1), min(ge, seq_len) - sh);
+    q.Bv = max(bs, gs - sh);
+    q.key_a = rank_clamp_key(q.A + 1, q.si);
+    q.key_b = rank_clamp_key(q.Bv, q.si);
+    ua = q.si.w + (q.key_a >> rank_shift);
+    ub = q.si.w + (q.key_b >> rank_shift);
+}
+
+// rank inside one bucket: first index with vals >= key (first three values already read; rare search)
+__device__ __forceinline__ int32_t bucket_rank(const int32_t *__restrict__ vals, const uint32_t *__restrict__ table, int32_t u,
+                                               const int4 si, int32_t a, int32_t n, int32_t key, int32_t v0, int32_t v1,
+                                               int32_t v2) {
+    if (v2 < key) {
+        const int32_t b = n < kRankCountCap ? a + n : si.x + (int32_t)(__ldg(table + u + 1) >> kRankCountBits);
+        return first_ge(vals, a + 3, b, key);
+    }
+    return a + (v0 < key) + (v1 < key) + (v2 < key);
+}
+
+__device__ __forceinline__ int pair_finish(const RangesView &y, const PairProbe &q, int32_t ia, int32_t ib) {
+    if (q.Bv <= q.A) return q.A < 1 ? 0 : ia - ib;
     // rare: the feature lies beside the tile; members contain [A, Bv]
-    if (A < 1 || Bv > si.z) return 0;
+    if (q.A < 1 || q.Bv > q.si.z) return 0;
     int n = 0;
-    for (int32_t k = ia - 1; k >= si.x && __ldg(y.pmax + k) >= Bv; --k) n += __ldg(y.end + k) >= Bv;
+    for (int32_t k = ia - 1; k >= q.si.x && __ldg(y.pmax + k) >= q.Bv; --k) n += __ldg(y.end + k) >= q.Bv;
     return n;
 }
 
-// Thread = (feature, RPT consecutive iterations); the block draws come from the table the
-// block-rows kernel wrote.  The RPT evaluations are independent and unrolled, so their table
-// probes overlap.  Features are visited in F's order (grouped by tile count, so a warp's lanes
-// loop the same number of times).  No atomics on the count matrix, no memset: every element is
-// written exactly once.
 template <int RPT>
-__global__ void __launch_bounds__(256) boot_rank_count_kernel(const BootParams P, const FeatView F) {
+__device__ __forceinline__ void count_pairs(const RangesView &y, const int2 (&d)[RPT], int32_t width, int32_t ts,
+                                            int32_t seq_len, int32_t gs, int32_t ge, int (&cnt)[RPT]) {
+    PairProbe q[RPT];
+    int32_t ua[RPT], ub[RPT];
+#pragma unroll
+    for (int j = 0; j < RPT; ++j) q[j].si = __ldg(y.seq_info + d[j].x);
+#pragma unroll
+    for (int j = 0; j < RPT; ++j) pair_keys(q[j], d[j], width, ts, seq_len, gs, ge, y.rank_shift, ua[j], ub[j]);
+#pragma unroll
+    for (int j = 0; j < RPT; ++j) {
+        const uint32_t ea = __ldg(y.rank_start + ua[j]), eb = __ldg(y.rank_end + ub[j]);
+        q[j].a0 = q[j].si.x + (int32_t)(ea >> kRankCountBits);
+        q[j].an = (int32_t)(ea & kRankCountCap);
+        q[j].b0 = q[j].si.x + (int32_t)(eb >> kRankCountBits);
+        q[j].bn = (int32_t)(eb & kRankCountCap);
+    }
+    int32_t va[RPT][3], vb[RPT][3];
+#pragma unroll
+    for (int j = 0; j < RPT; ++j) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            va[j][k] = k < q[j].an ? __ldg(y.start + q[j].a0 + k) : INT32_MAX;
+            vb[j][k] = k < q[j].bn ? __ldg(y.end_sorted + q[j].b0 + k) : INT32_MAX;
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < RPT; ++j) {
+        const int32_t ia = bucket_rank(y.start, y.rank_start, ua[j], q[j].si, q[j].a0, q[j].an, q[j].key_a, va[j][0], va[j][1], va[j][2]);
+        const int32_t ib = bucket_rank(y.end_sorted, y.rank_end, ub[j], q[j].si, q[j].b0, q[j].bn, q[j].key_b, vb[j][0], vb[j][1], vb[j][2]);
+        cnt[j] += pair_finish(y, q[j], ia, ib);
+    }
+}
+
+// Thread = (feature, RPT consecutive iterations); the block draws come from the table the
+// block-rows kernel wrote.  Features are visited in F's order (grouped by tile count, so a warp's
+// lanes loop the same number of times).  No atomics on the count matrix, no memset: every element
+// is written exactly once.
+template <int RPT, int MINB>
+__global__ void __launch_bounds__(256, MINB) boot_rank_count_kernel(const BootParams P, const FeatView F) {
     __shared__ int warp_tot[8][RPT];
     const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t r0 = (int64_t)blockIdx.y * RPT;
-    const bool full = r0 + RPT <= P.n_iter;
+    const int n_live = (int)min((int64_t)RPT, P.n_iter - r0);
     int cnt[RPT];
 #pragma unroll
     for (int j = 0; j < RPT; ++j) cnt[j] = 0;
@@ -424,21 +478,15 @@ __global__ void __launch_bounds__(256) boot_rank_count_kernel(const BootParams P
             const int32_t ts = __ldg(P.tile_start + t), width = __ldg(P.bait_width + t);
             const int32_t seq_len = (int32_t)__ldg(P.seqlen + __ldg(P.tile_seq + t));
             const int2 *__restrict__ tab = P.draw_tab + r0 * P.n_blocks + t;
-            if (full) {
-                int2 d[RPT];
+            int2 d[RPT];
 #pragma unroll
-                for (int j = 0; j < RPT; ++j) d[j] = __ldg(tab + j * P.n_blocks);
-#pragma unroll
-                for (int j = 0; j < RPT; ++j) cnt[j] += count_pair(P.y, d[j], width, ts, seq_len, gs, ge);
-            } else {
-                for (int j = 0; j < RPT; ++j)
-                    if (r0 + j < P.n_iter) cnt[j] += count_pair(P.y, __ldg(tab + j * P.n_blocks), width, ts, seq_len, gs, ge);
-            }
+            for (int j = 0; j < RPT; ++j) d[j] = __ldg(tab + (j < n_live ? j : 0) * P.n_blocks);  // tail: recount row 0, discarded
+            count_pairs<RPT>(P.y, d, width, ts, seq_len, gs, ge, cnt);
         }
         if (P.counts) {
 #pragma unroll
             for (int j = 0; j < RPT; ++j)
-                if (r0 + j < P.n_iter) P.counts[(r0 + j) * P.n_query + src] = cnt[j];
+                if (j < n_live) P.counts[(r0 + j) * P.n_query + src] = cnt[j];
         }
     }
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -448,7 +496,7 @@ __global__ void __launch_bounds__(256) boot_rank_count_kernel(const BootParams P
         if (lane == 0) warp_tot[warp][j] = s;
     }
     __syncthreads();
-    if (threadIdx.x < RPT && r0 + threadIdx.x < P.n_iter) {
+    if (threadIdx.x < n_live) {
         unsigned long long s = 0;
         for (int w = 0; w < 8; ++w) s += (unsigned)warp_tot[w][threadIdx.x];
         if (s) atomicAdd(P.iter_totals + r0 + threadIdx.x, s);
@@ -488,8 +536,8 @@ __global__ void __launch_bounds__(256) boot_block_rows_kernel(const BootParams P
                 const int4 si = __ldg(P.y.seq_info + d.x);
                 const int32_t ie = idx_start_le(P.y, si, d.y + (width - 1));
                 const int hits = ie - idx_end_lt(P.y, si, d.y);
-                int dropped = 0;
-                if (P.drop_zero) dropped = max(0, ie - idx_start_le(P.y, si, seq_len - (ts - d.y)));
+                int dropped = 0;  // only a tile that overhangs its sequence end can push hits beyond it
+                if (P.drop_zero && ts + (width - 1) > seq_len) dropped = max(0, ie - idx_start_le(P.y, si, seq_len - (ts - d.y)));
                 rows[j] = hits - dropped;
                 hits_sum += hits;
                 if (P.item_rows) P.item_rows[(r0 + j) * P.n_blocks + b] = rows[j];
@@ -597,10 +645,10 @@ struct MaxOp {
     __host__ __device__ __forceinline__ int32_t operator()(int32_t a, int32_t b) const { return a > b ? a : b; }
 };
 
-// entry t of a rank table: first index of its sequence whose value is >= (bucket << shift)
+// entry t of a packed rank table (see "direct-address rank tables")
 __global__ void build_rank_table_kernel(const int32_t *__restrict__ values, const int32_t *__restrict__ seq_off,
                                         const int64_t *__restrict__ rank_off, int n_seq, int shift,
-                                        int32_t *__restrict__ table) {
+                                        uint32_t *__restrict__ table) {
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= rank_off[n_seq]) return;
     int c = 0, hi = n_seq;  // sequence that owns entry t
@@ -609,9 +657,11 @@ __global__ void build_rank_table_kernel(const int32_t *__restrict__ values, cons
         if (rank_off[m] <= t) c = m; else hi = m;
     }
     const int64_t bucket = t - rank_off[c];
-    const int64_t key = bucket << shift;
+    const int64_t key = bucket << shift, next = (bucket + 1) << shift;
     const int32_t a = seq_off[c], b = seq_off[c + 1];
-    table[t] = key > INT32_MAX ? b : first_ge(values, a, b, (int32_t)key);
+    const int32_t first = key > INT32_MAX ? b : first_ge(values, a, b, (int32_t)key);
+    const int32_t last = next > INT32_MAX ? b : first_ge(values, first, b, (int32_t)next);
+    table[t] = ((uint32_t)(first - a) << kRankCountBits) | (uint32_t)min(last - first, kRankCountCap);
 }
 
 // countOverlaps(query, y) on the original ranges: one thread per y range.
