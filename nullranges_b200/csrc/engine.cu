@@ -96,7 +96,7 @@ struct nrb200_handle {
     DevMem tile_seq, tile_start, bait_width, sampler_i64, sampler_i32;
     SamplerView sampler_view{};
     bool slices_dirty = true;
-    DevMem q_tile_lo, q_tile_hi, x_tile_lo, x_tile_hi, pair_off, pair_tile, f_start, f_end, f_src;
+    DevMem q_tile_lo, q_tile_hi, x_tile_lo, x_tile_hi, pair_off, pair_rec, f_src, tile_x_off, tile_x_rec;
     int64_t n_pairs = 0;
     bool tiles_in_bounds = false;
 
@@ -360,20 +360,79 @@ int build_slices(nrb200_handle *h, const RangeSet &rs, DevMem &lo_dev, DevMem &h
     return NRB200_OK;
 }
 
-// Feature -> tiles lists of the rank path: tile t is listed for feature k when the feature comes
-// within (wmax - 1) of the tile, i.e. when a range landing on the tile can overlap it.  Features
-// that start beyond their sequence end get no tiles (trim() leaves nothing there).
+// ---- rank path tables --------------------------------------------------------------------
+// Per feature: the signed windows to count on each tile within reach (PairRec, kernels.cuh).
+// Tile t is within reach of a window when the window comes within (wmax - 1) of the tile, i.e.
+// when a range landing on the tile can overlap it.  Windows that start beyond their sequence end
+// are dropped (trim() leaves nothing there).  With an exclude set, the merged exclude regions
+// near both the tile and the feature add their pseudo-features with sign -1 (+1 for the overlap
+// of two consecutive regions), and each tile gets the same for the row counts.
+struct Interval {
+    int64_t s, e;
+};
+
+// reduce(): merged, sorted, disjoint (adjacent regions are joined: the union is what matters)
+static std::vector<std::vector<Interval>> merged_exclude(const nrb200_handle *h) {
+    const RangeSet &x = h->excl;
+    std::vector<std::vector<Interval>> out(h->n_seq);
+    for (int c = 0; c < h->n_seq; ++c) {
+        for (int32_t k = x.h_seq_off[c]; k < x.h_seq_off[c + 1]; ++k) {  // canonical order: by start
+            const int64_t s = x.h_start[k], e = x.h_end[k];
+            if (s > h->seqlen[c]) continue;  // nothing survives trim() out there
+            if (!out[c].empty() && s <= out[c].back().e + 1) out[c].back().e = std::max(out[c].back().e, e);
+            else out[c].push_back({s, e});
+        }
+    }
+    return out;
+}
+
 int build_pairs(nrb200_handle *h) {
     const Plan &p = h->plan;
     const RangeSet &q = h->query;
     const int C = h->n_seq;
     const int64_t B = p.n_blocks(), G = q.n;
     const int64_t reach = std::max<int32_t>(h->y.wmax, 1) - 1;
-    // tiles of each sequence in ascending start order with the running max of their ends
+    const bool has_excl = h->excl.n > 0;
+    const auto X = has_excl ? merged_exclude(h) : std::vector<std::vector<Interval>>(C);
+
+    // exclude regions that intersect [lo, hi]: a contiguous run [first, last) of the merged list
+    auto x_run = [&](int c, int64_t lo, int64_t hi, size_t &first, size_t &last) {
+        const auto &v = X[c];
+        first = std::lower_bound(v.begin(), v.end(), lo, [](const Interval &a, int64_t key) { return a.e < key; }) - v.begin();
+        last = std::upper_bound(v.begin(), v.end(), hi, [](int64_t key, const Interval &a) { return key < a.s; }) - v.begin();
+        if (last < first) last = first;
+    };
+
+    // ---- per tile: exclusion windows for the row counts
+    std::vector<int32_t> x_off(B + 1, 0), x_rec;
+    if (has_excl) {
+        for (int64_t t = 0; t < B; ++t) {
+            const int c = p.tile_seq[t];
+            const int64_t ts = p.tile_start[t], te = ts + p.bait_width[t] - 1;
+            size_t f, l;
+            x_run(c, ts - reach, te + reach, f, l);
+            for (size_t k = f; k < l; ++k) {
+                x_rec.insert(x_rec.end(), {(int32_t)X[c][k].s, (int32_t)std::min<int64_t>(X[c][k].e, INT32_MAX / 2), -1, 0});
+                if (k + 1 < l && X[c][k + 1].s - X[c][k].e <= reach)
+                    x_rec.insert(x_rec.end(), {(int32_t)X[c][k + 1].s, (int32_t)X[c][k].e, +1, 0});
+            }
+            x_off[t + 1] = (int32_t)(x_rec.size() / 4);
+        }
+    }
+    int rc;
+    if ((rc = upload(h, h->tile_x_off, x_off.data(), (size_t)B + 1))) return rc;
+    if ((rc = upload(h, h->tile_x_rec, x_rec.data(), x_rec.size()))) return rc;
+    if (G == 0) {
+        NRB_CUDA(h, cudaStreamSynchronize(h->stream));
+        return NRB200_OK;
+    }
+
+    // ---- per feature: tiles of each sequence in ascending start order with the running max of their ends
     std::vector<std::vector<int32_t>> by_seq(C);
     for (int64_t t = 0; t < B; ++t) by_seq[p.tile_seq[t]].push_back((int32_t)t);
-    std::vector<int32_t> off(G + 1, 0), tiles;
-    tiles.reserve((size_t)G + G / 4);
+    std::vector<int64_t> off(G + 1, 0);
+    std::vector<PairRec> recs;
+    recs.reserve((size_t)G + G / 4);
     std::vector<int64_t> ts, te_max;
     for (int c = 0; c < C; ++c) {
         auto &v = by_seq[c];
@@ -388,51 +447,67 @@ int build_pairs(nrb200_handle *h) {
             m = std::max<int64_t>(m, ts[j] + p.bait_width[v[j]] - 1);
             te_max[j] = m;
         }
+        const int32_t L = (int32_t)h->seqlen[c];
         for (int32_t k = q.h_seq_off[c]; k < q.h_seq_off[c + 1]; ++k) {
             const int64_t gs = q.h_start[k], ge = q.h_end[k];
-            if (gs <= h->seqlen[c]) {
+            if (gs <= L) {
                 int64_t j = (int64_t)(std::upper_bound(ts.begin(), ts.end(), ge + reach) - ts.begin()) - 1;
-                const size_t first = tiles.size();
-                for (; j >= 0 && te_max[j] + reach >= gs; --j)
-                    if (ts[j] + p.bait_width[v[j]] - 1 + reach >= gs) tiles.push_back(v[j]);
-                std::reverse(tiles.begin() + first, tiles.end());
+                const size_t first_rec = recs.size();
+                for (; j >= 0 && te_max[j] + reach >= gs; --j) {
+                    const int32_t t = v[j];
+                    const int64_t t_s = ts[j], t_e = t_s + p.bait_width[t] - 1;
+                    if (t_e + reach < gs) continue;
+                    auto push = [&](int64_t ws, int64_t we, int sign) {
+                        recs.push_back(PairRec{t, (int32_t)ws, (int32_t)std::min<int64_t>(we, INT32_MAX / 2), sign, (int32_t)t_s,
+                                               p.bait_width[t], L, 0});
+                    };
+                    push(gs, ge, +1);
+                    if (has_excl) {
+                        // regions a range landing on the tile can overlap together with the feature
+                        size_t f, l;
+                        x_run(c, std::max(t_s - reach, gs - reach), std::min(t_e + reach, ge + reach), f, l);
+                        for (size_t i = f; i < l; ++i) {
+                            push(std::max(X[c][i].s, gs), std::min(X[c][i].e, ge), -1);
+                            if (i + 1 < l && X[c][i + 1].s - X[c][i].e <= reach)
+                                push(std::max(X[c][i + 1].s, gs), std::min(X[c][i].e, ge), +1);
+                        }
+                    }
+                }
+                std::reverse(recs.begin() + first_rec, recs.end());
             }
-            if (tiles.size() > (size_t)INT32_MAX) return fail(h, NRB200_ERR_UNSUPPORTED, "too many (feature, tile) pairs");
-            off[k + 1] = (int32_t)tiles.size();
+            if (recs.size() > (size_t)INT32_MAX / 2) return fail(h, NRB200_ERR_UNSUPPORTED, "too many (feature, tile) pairs");
+            off[k + 1] = (int64_t)recs.size();
         }
     }
-    h->n_pairs = (int64_t)tiles.size();
-    // Visit order of the count kernel: features grouped by how many tiles they reach (stable, so
-    // neighbours in a group are neighbours on the genome): the lanes of a warp then loop equally often.
+    h->n_pairs = (int64_t)recs.size();
+    // Visit order of the count kernel: features grouped by list length (stable, so neighbours in a
+    // group are neighbours on the genome): the lanes of a warp then loop equally often.
     std::vector<int32_t> order(G);
     std::iota(order.begin(), order.end(), 0);
     std::stable_sort(order.begin(), order.end(), [&](int32_t a, int32_t b) { return off[a + 1] - off[a] < off[b + 1] - off[b]; });
-    std::vector<int32_t> f_start(G), f_end(G), f_src(G), f_off(G + 1, 0), f_tiles;
-    f_tiles.reserve(tiles.size());
+    std::vector<int32_t> f_src(G), f_off(G + 1, 0);
+    std::vector<PairRec> f_recs;
+    f_recs.reserve(recs.size());
     for (int64_t i = 0; i < G; ++i) {
         const int32_t k = order[i];
-        f_start[i] = q.h_start[k];
-        f_end[i] = q.h_end[k];
         f_src[i] = q.h_src[k];
-        f_tiles.insert(f_tiles.end(), tiles.begin() + off[k], tiles.begin() + off[k + 1]);
-        f_off[i + 1] = (int32_t)f_tiles.size();
+        f_recs.insert(f_recs.end(), recs.begin() + off[k], recs.begin() + off[k + 1]);
+        f_off[i + 1] = (int32_t)f_recs.size();
     }
-    int rc;
-    if ((rc = upload(h, h->f_start, f_start.data(), (size_t)G))) return rc;
-    if ((rc = upload(h, h->f_end, f_end.data(), (size_t)G))) return rc;
     if ((rc = upload(h, h->f_src, f_src.data(), (size_t)G))) return rc;
     if ((rc = upload(h, h->pair_off, f_off.data(), (size_t)G + 1))) return rc;
-    if ((rc = upload(h, h->pair_tile, f_tiles.data(), f_tiles.size()))) return rc;
+    if ((rc = upload(h, h->pair_rec, f_recs.data(), f_recs.size()))) return rc;
     NRB_CUDA(h, cudaStreamSynchronize(h->stream));
     return NRB200_OK;
 }
 
-// The rank path covers the bootstrap samplers without exclusion, as long as strand cannot matter
-// (y or the query is all '*').  Everything else streams the hits (boot_count_kernel).
+// The rank path covers the bootstrap samplers (with or without excludeOption = "drop") whenever
+// strand cannot matter: y is all '*', or the query and the exclude set are.  Everything else
+// streams the hits (boot_count_kernel).
 bool rank_path_ok(const nrb200_handle *h, bool with_query) {
     if (h->flags & NRB200_FLAG_FORCE_STREAM) return false;
-    if (h->plan.permute() || h->excl.n > 0 || !h->tiles_in_bounds) return false;
-    if (with_query && h->y.stranded && h->query.stranded) return false;
+    if (h->plan.permute() || !h->tiles_in_bounds) return false;
+    if (h->y.stranded && ((with_query && h->query.stranded) || (h->excl.n > 0 && h->excl.stranded))) return false;
     return true;
 }
 
@@ -444,12 +519,18 @@ int prepare(nrb200_handle *h) {
         h->tiles_in_bounds = true;
         for (int64_t t = 0; t < h->plan.n_blocks(); ++t)
             if (h->plan.tile_start[t] > h->seqlen[h->plan.tile_seq[t]]) h->tiles_in_bounds = false;
-        if (h->excl.n && (rc = build_slices(h, h->excl, h->x_tile_lo, h->x_tile_hi))) return rc;
-        if (h->query.n) {
-            if (rank_path_ok(h, true)) rc = build_pairs(h);
-            else rc = build_slices(h, h->query, h->q_tile_lo, h->q_tile_hi);
+        // rank_path_ok(h, false) holds whenever rank_path_ok(h, true) does
+        const bool rank_q = h->query.n && rank_path_ok(h, true), rank_rows = rank_path_ok(h, false);
+        if (rank_q || rank_rows) {
+            const int64_t g_keep = h->query.n;
+            if (!rank_q) h->query.n = 0;  // tables for the row counts only
+            rc = build_pairs(h);
+            h->query.n = g_keep;
             if (rc) return rc;
         }
+        // the streaming kernels (count without the rank path, and the fill pass) test exclusion per range
+        if (h->excl.n && (rc = build_slices(h, h->excl, h->x_tile_lo, h->x_tile_hi))) return rc;
+        if (h->query.n && !rank_q && (rc = build_slices(h, h->query, h->q_tile_lo, h->q_tile_hi))) return rc;
         h->slices_dirty = false;
     }
     return NRB200_OK;
@@ -531,12 +612,12 @@ int launch_rank(nrb200_handle *h, const BootParams &P, bool has_query) {
     const int rpt = h->tune_rpt;
     const unsigned gy = (unsigned)((P.n_iter + rpt - 1) / rpt);
     if (P.n_blocks > 0) {
-        boot_block_rows_kernel<1><<<dim3((unsigned)((P.n_blocks + 255) / 256), (unsigned)P.n_iter), 256, 0, h->stream>>>(P);
+        const TileExcl X{h->excl.n > 0 ? h->tile_x_off.as<int32_t>() : nullptr, h->tile_x_rec.as<int4>()};
+        boot_block_rows_kernel<1><<<dim3((unsigned)((P.n_blocks + 255) / 256), (unsigned)P.n_iter), 256, 0, h->stream>>>(P, X);
         ++launches;
     }
     if (has_query) {
-        const FeatView F{h->f_start.as<int32_t>(), h->f_end.as<int32_t>(), h->f_src.as<int32_t>(), h->pair_off.as<int32_t>(),
-                         h->pair_tile.as<int32_t>()};
+        const FeatView F{h->f_src.as<int32_t>(), h->pair_off.as<int32_t>(), h->pair_rec.as<PairRec>()};
         const dim3 grid((unsigned)((P.n_query + 255) / 256), gy);
         switch (rpt * 10 + h->tune_minb) {
         case 11: boot_rank_count_kernel<1, 1><<<grid, 256, 0, h->stream>>>(P, F); break;

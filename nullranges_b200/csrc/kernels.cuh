@@ -373,10 +373,31 @@ __global__ void __launch_bounds__(256) boot_fill_kernel(const BootParams P, cons
 // running-max-of-end bound.  Same arithmetic as the reference's findOverlaps + shift + trim +
 // countOverlaps (R/bootUnsegmented.R:133-139, :175-191; vignettes/bootRanges.Rmd:497-503).
 
-struct FeatView {              // query features in canonical order + the tiles within reach
-    const int32_t *start, *end, *src;
+// Exclusion (excludeOption = "drop", R/bootRanges.R:108-109) stays on this path: the ranges
+// dropped because they overlap exclude region X and that also land on feature g are those that
+// overlap the pseudo-feature [max(xs, gs), min(xe, ge)] (when that is empty: those that span the gap),
+// so they are counted by the same formula and SUBTRACTED.  Exclude regions are merged first
+// (disjoint, sorted), so a range overlaps a run of consecutive regions and the union is
+// sum_k |S_k| - sum_k |S_k and S_k+1|.  A feature therefore owns a list of signed windows per tile.
+
+struct PairRec {               // one signed window to count for a feature on a tile (32 bytes)
+    int32_t tile;              // block index b (row of the draw table)
+    int32_t ws, we;            // window on the tile's sequence ([gs, ge] or an exclusion pseudo-feature)
+    int32_t sign;              // +1 / -1
+    int32_t tile_start, width, seq_len;  // copied from the block tables: saves three dependent loads
+    int32_t pad;
+};
+static_assert(sizeof(PairRec) == 32, "PairRec is read as two int4");
+
+struct FeatView {              // query features in visit order (grouped by list length)
+    const int32_t *src;        // [n_query] index in the caller's order
     const int32_t *pair_off;   // [n_query + 1]
-    const int32_t *pair_tile;  // tile (= block) indices
+    const PairRec *pair_rec;
+};
+
+struct TileExcl {              // signed exclusion windows of each tile, for the rows kernel
+    const int32_t *off;        // [n_blocks + 1], or nullptr without exclusion
+    const int4 *rec;           // {ws, we, sign, 0}
 };
 
 // One (feature, tile, iteration) evaluation, split into stages so that the RPT evaluations a thread
@@ -470,18 +491,21 @@ __global__ void __launch_bounds__(256, MINB) boot_rank_count_kernel(const BootPa
 #pragma unroll
     for (int j = 0; j < RPT; ++j) cnt[j] = 0;
     if (g < P.n_query) {
-        const int32_t gs = __ldg(F.start + g), ge = __ldg(F.end + g);
         const int32_t src = __ldg(F.src + g);
         const int32_t p1 = __ldg(F.pair_off + g + 1);
         for (int32_t p = __ldg(F.pair_off + g); p < p1; ++p) {
-            const int32_t t = __ldg(F.pair_tile + p);
-            const int32_t ts = __ldg(P.tile_start + t), width = __ldg(P.bait_width + t);
-            const int32_t seq_len = (int32_t)__ldg(P.seqlen + __ldg(P.tile_seq + t));
-            const int2 *__restrict__ tab = P.draw_tab + r0 * P.n_blocks + t;
+            const int4 ra = __ldg(reinterpret_cast<const int4 *>(F.pair_rec + p));      // tile, ws, we, sign
+            const int4 rb = __ldg(reinterpret_cast<const int4 *>(F.pair_rec + p) + 1);  // tile_start, width, seq_len
+            const int2 *__restrict__ tab = P.draw_tab + r0 * P.n_blocks + ra.x;
             int2 d[RPT];
 #pragma unroll
             for (int j = 0; j < RPT; ++j) d[j] = __ldg(tab + (j < n_live ? j : 0) * P.n_blocks);  // tail: recount row 0, discarded
-            count_pairs<RPT>(P.y, d, width, ts, seq_len, gs, ge, cnt);
+            int c[RPT];
+#pragma unroll
+            for (int j = 0; j < RPT; ++j) c[j] = 0;
+            count_pairs<RPT>(P.y, d, rb.y, rb.x, rb.z, ra.y, ra.z, c);
+#pragma unroll
+            for (int j = 0; j < RPT; ++j) cnt[j] += ra.w * c[j];
         }
         if (P.counts) {
 #pragma unroll
@@ -509,7 +533,7 @@ __global__ void __launch_bounds__(256, MINB) boot_rank_count_kernel(const BootPa
 // hits shifted wholly beyond the sequence end.  Requires tile_start <= seqlength for every tile
 // (checked on the host).
 template <int RPT>
-__global__ void __launch_bounds__(256) boot_block_rows_kernel(const BootParams P) {
+__global__ void __launch_bounds__(256) boot_block_rows_kernel(const BootParams P, const TileExcl X) {
     __shared__ int warp_rows[8][RPT];
     __shared__ unsigned long long cta_hits;
     const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -539,6 +563,16 @@ __global__ void __launch_bounds__(256) boot_block_rows_kernel(const BootParams P
                 int dropped = 0;  // only a tile that overhangs its sequence end can push hits beyond it
                 if (P.drop_zero && ts + (width - 1) > seq_len) dropped = max(0, ie - idx_start_le(P.y, si, seq_len - (ts - d.y)));
                 rows[j] = hits - dropped;
+                if (X.off) {  // minus the hits that overlap an exclude region after the move
+                    const int32_t x1 = __ldg(X.off + b + 1);
+                    for (int32_t k = __ldg(X.off + b); k < x1; ++k) {
+                        const int4 w = __ldg(X.rec + k);
+                        const int2 dd[1] = {d};
+                        int c1[1] = {0};
+                        count_pairs<1>(P.y, dd, width, ts, seq_len, w.x, w.y, c1);
+                        rows[j] += w.z * c1[0];
+                    }
+                }
                 hits_sum += hits;
                 if (P.item_rows) P.item_rows[(r0 + j) * P.n_blocks + b] = rows[j];
             }

@@ -173,3 +173,49 @@ def test_cfg2_full_size(engine):
     # bootstrap mean of the total tracks the observed total (block bootstrap preserves density)
     obs, tot = engine.count_observed()
     assert abs(big["iter_totals"].mean() / tot - 1.0) < 0.05
+
+
+@pytest.mark.parametrize("kind", BOOT_KINDS)
+def test_dense_exclusion(engine, kind):
+    """Many small, close exclude regions and ranges long enough to span several of them: the rank
+    path's union-by-consecutive-overlaps must agree with the per-range test of the reference."""
+    case = H.random_case(seed=90 + kind, n=900, n_seq=3, n_query=80, n_excl=0, wmax=400, n_seg=9, n_states=2)
+    rng = np.random.default_rng(5)
+    L = case["seqlen"]
+    sid = rng.integers(0, 3, 150).astype(np.int32)
+    st = (1 + rng.random(150) * (L[sid] - 40)).astype(np.int32)
+    en = (st + rng.integers(0, 30, 150)).astype(np.int32)
+    en[::10] = (L[sid[::10]] + 50).astype(np.int32)      # some reach past the sequence end
+    st[5::25] = (L[sid[5::25]] + 1).astype(np.int32)     # some lie wholly beyond it
+    en[5::25] = st[5::25] + 10
+    case["excl"] = (sid, st, en, None)
+    _check_counts(engine, case, kind, R=6, seed=8, philox=False)
+    if kind < 3:
+        _check_counts(engine, case, kind, R=5, seed=77, philox=True)
+    # materialised rows too (the count pass of the table uses the same row counts)
+    plan, y, q, x = H.oracle_objects(case, kind)
+    H.load_engine(engine, case, kind)
+    d = H.draw_R(plan, 3, 3)
+    rows = engine.run_materialize(Draws(n_iter=3, rng_mode=_lib.RNG_HOST, bait_seqid=d[0], bait_start=d[1]))
+    it = np.repeat(np.arange(3), np.diff(rows["iter_offsets"]))
+    assert np.array_equal(H.canon_rows(rows["seqid"], rows["start"], rows["end"], rows["src"], rows["block"], it),
+                          H.oracle_rows(plan, y, x, d, 3))
+
+
+def test_cfg3_full_size(engine):
+    """BASELINE configs[2]: segmented (3 states, L_s = 2e6), proportionLength = TRUE, exclude 'drop',
+    1M ranges vs 20k genes; 24 Philox iterations against the oracle."""
+    from nullranges_b200 import synth
+    y, x = synth.atac_peaks(1_000_000, seed=3), synth.genes(20_000, seed=2)
+    seg, ex = synth.segmentation(seed=4), synth.exclude_regions(seed=5)
+    case = _synth_case(y, x)
+    case["seg"] = {"chrom": seg.seqid, "start": seg.start, "end": seg.end, "state": seg.mcols["state"].astype(np.int32)}
+    case["excl"] = (ex.seqid, ex.start, ex.end, None)
+    plan, yi, qi, xi = H.oracle_objects(case, 2)
+    assert H.load_engine(engine, case, 2) == plan.B
+    R = 24
+    got = engine.run_counts(Draws(n_iter=R, rng_mode=_lib.RNG_PHILOX, seed=11, iter0=100))
+    ref = O.boot_counts(plan, yi, qi, R, exclude=xi, seed=11, iter0=100, nthreads=O.max_threads())
+    for k in ("iter_nranges", "iter_totals", "feature_counts"):
+        assert np.array_equal(got[k], ref[k]), k
+    assert got["iter_nranges"].mean() < 1_000_000  # exclusion removes ranges
