@@ -1,0 +1,149 @@
+# bootRanges() / bootCounts() served by libnrb200 (B200).  Same arguments as nullranges::bootRanges
+# (man/bootRanges.Rd); new arguments default to the reference's behaviour.
+#
+# rng = "R": block draws come from R's own sample()/runif() under the caller's set.seed(), consumed in
+# the order of the reference (R/bootUnsegmented.R:60,122-124; R/bootRanges.R:202-209,263-267,296), so
+# the result equals nullranges::bootRanges() run under the same seed.  rng = "philox": draws happen on
+# the GPU (counter-based, reproducible from `seed`, independent of how iterations are split).
+#
+# This file cannot be executed in the build image (no R); its logic is mirrored one to one by
+# nullranges_b200/bootranges.py + samplers.py, which the test-suite runs against the oracle.
+
+.nrb_env <- new.env()
+.handle <- function(device = 0L) {
+  key <- paste0("h", device)
+  if (is.null(.nrb_env[[key]])) .nrb_env[[key]] <- .Call("nrb200_R_create", as.integer(device))
+  .nrb_env[[key]]
+}
+.strand_code <- function(x) {
+  s <- as.character(GenomicRanges::strand(x))
+  code <- c("*" = 0L, "+" = 1L, "-" = 2L)[s]
+  if (all(code == 0L)) NULL else unname(code)
+}
+.seqid <- function(x, levels) match(as.character(GenomicRanges::seqnames(x)), levels) - 1L
+.kind <- function(seg, proportionLength, type, withinChrom) {
+  if (!is.null(seg)) return(if (proportionLength) 2L else 3L)       # type / withinChrom ignored (bootRanges.R:91-98)
+  if (type == "bootstrap") (if (withinChrom) 1L else 0L) else (if (withinChrom) 4L else 5L)
+}
+
+# One iteration of block draws on R's RNG -> list(seqid (0-based), start, dst (0-based tile or NULL)).
+.draw_blocks <- function(kind, L_s, L_b, tiles, seg) {
+  n_c <- ceiling(L_s / L_b)
+  if (kind == 0L) {                                   # across chromosomes
+    pick <- sample(length(L_s), sum(n_c), replace = TRUE, prob = L_s)
+    st <- round(runif(sum(n_c), 1, (n_c[pick] - 1) * L_b + 1))
+    return(list(seqid = pick - 1L, start = as.integer(st), dst = NULL))
+  }
+  if (kind == 1L) {                                   # within chromosome: one runif() per seqlevel
+    st <- lapply(seq_along(L_s), function(c) round(runif(n_c[c], 1, (n_c[c] - 1) * L_b + 1)))
+    return(list(seqid = rep(seq_along(L_s) - 1L, n_c), start = as.integer(unlist(st)), dst = NULL))
+  }
+  if (kind == 4L) {                                   # permute within: tile k of a chromosome -> perm[k]
+    off <- c(0, cumsum(n_c))
+    dst <- unlist(lapply(seq_along(L_s), function(c) off[c] + sample(n_c[c]) - 1L))
+    return(list(seqid = tiles[[1]], start = tiles[[2]], dst = as.integer(dst)))
+  }
+  if (kind == 5L) {                                   # permute across
+    return(list(seqid = tiles[[1]], start = tiles[[2]], dst = sample(length(tiles[[1]])) - 1L))
+  }
+  w <- seg$end - seg$start + 1
+  states <- seq_len(max(seg$state))
+  if (kind == 2L) {                                   # segmented, block length proportional to state size
+    L_bs <- round(L_b * vapply(states, function(s) sum(w[seg$state == s]), 0) / sum(L_s))
+    out <- lapply(states, function(s) {
+      i <- which(seg$state == s)
+      nb <- ceiling(w[i] / L_bs[s])
+      pick <- sample(length(i), sum(nb), replace = TRUE, prob = w[i])
+      lo <- seg$start[i][pick]
+      list(seg$seqid[i][pick], round(runif(sum(nb), lo, (nb[pick] - 1) * L_bs[s] + lo)))
+    })
+    return(list(seqid = unlist(lapply(out, `[[`, 1)), start = as.integer(unlist(lapply(out, `[[`, 2))), dst = NULL))
+  }
+  nb <- ceiling(w / L_b)                              # kind 3: fixed block length, resampled per state
+  pick <- sample(length(w), sum(nb), replace = TRUE, prob = w)
+  lo <- seg$start[pick]
+  st <- round(runif(sum(nb), lo, (nb[pick] - 1) * L_b + lo))
+  out <- lapply(states, function(s) {
+    idx <- which(seg$state[pick] == s)
+    want <- sum(nb[seg$state == s])
+    stopifnot(length(idx) > 0)
+    sel <- if (length(idx) < want) sample(length(idx), want, replace = TRUE) else seq_len(want)
+    list(seg$seqid[pick[idx]][sel], st[idx][sel])
+  })
+  list(seqid = unlist(lapply(out, `[[`, 1)), start = as.integer(unlist(lapply(out, `[[`, 2))), dst = NULL)
+}
+
+.setup <- function(y, blockLength, seg, exclude, excludeOption, proportionLength, type, withinChrom, device) {
+  chr_lens <- GenomeInfoDb::seqlengths(y)
+  stopifnot(all(!is.na(chr_lens)))
+  if (excludeOption == "trim") stop("excludeOption = 'trim' is not on the device yet")
+  lv <- GenomeInfoDb::seqlevels(y)
+  h <- .handle(device)
+  kind <- .kind(seg, proportionLength, type, withinChrom)
+  sorted <- .Call("nrb200_R_set_ranges", h, as.numeric(chr_lens), .seqid(y, lv), GenomicRanges::start(y),
+                  GenomicRanges::end(y), .strand_code(y))
+  if (kind %in% c(0L, 5L)) {
+    ok <- if (is.null(.strand_code(y))) sorted else all(y == GenomicRanges::sort(y))
+    stopifnot("all(y == GenomicRanges::sort(y)) is not TRUE" = ok)
+  }
+  if (is.null(exclude)) .Call("nrb200_R_set_exclude", h, integer(), integer(), integer(), NULL)
+  else {
+    exclude <- exclude[as.character(GenomicRanges::seqnames(exclude)) %in% lv]
+    .Call("nrb200_R_set_exclude", h, .seqid(exclude, lv), GenomicRanges::start(exclude), GenomicRanges::end(exclude),
+          .strand_code(exclude))
+  }
+  segl <- NULL
+  if (!is.null(seg)) {
+    stopifnot("state" %in% names(S4Vectors::mcols(seg)))
+    segl <- list(seqid = .seqid(seg, lv), start = GenomicRanges::start(seg), end = GenomicRanges::end(seg),
+                 state = as.integer(seg$state))
+  }
+  tiles <- .Call("nrb200_R_set_plan", h, kind, as.numeric(blockLength), segl$seqid, segl$start, segl$end, segl$state)
+  list(h = h, kind = kind, L_s = as.numeric(chr_lens), tiles = tiles, seg = segl, lv = lv)
+}
+
+.draws <- function(s, R, blockLength, rng) {
+  if (rng == "philox") return(list(NULL, NULL, NULL))
+  d <- lapply(seq_len(R), function(i) .draw_blocks(s$kind, s$L_s, blockLength, s$tiles, s$seg))
+  list(unlist(lapply(d, `[[`, "seqid")), unlist(lapply(d, `[[`, "start")),
+       if (is.null(d[[1]]$dst)) NULL else unlist(lapply(d, `[[`, "dst")))
+}
+
+bootRanges <- function(y, blockLength, R = 1, seg = NULL, exclude = NULL, excludeOption = c("drop", "trim"),
+                       proportionLength = TRUE, type = c("bootstrap", "permute"), withinChrom = FALSE,
+                       storeBlockLength = FALSE, rng = c("R", "philox"), seed = 0, iter0 = 0, device = 0L) {
+  excludeOption <- match.arg(excludeOption); type <- match.arg(type); rng <- match.arg(rng)
+  s <- .setup(y, blockLength, seg, exclude, excludeOption, proportionLength, type, withinChrom, device)
+  d <- .draws(s, R, blockLength, rng)
+  res <- .Call("nrb200_R_run_materialize", s$h, as.numeric(R), as.numeric(iter0), as.numeric(seed), d[[1]], d[[2]], d[[3]])
+  src <- res[[5]]
+  br <- GenomicRanges::GRanges(S4Vectors::Rle(factor(s$lv[res[[2]] + 1L], levels = s$lv)),
+                               IRanges::IRanges(res[[3]], res[[4]]), strand = GenomicRanges::strand(y)[src],
+                               seqinfo = GenomeInfoDb::seqinfo(y))
+  mc <- S4Vectors::mcols(y)[src, , drop = FALSE]
+  mc$block <- NULL
+  S4Vectors::mcols(br) <- mc
+  S4Vectors::mcols(br)$iter <- S4Vectors::Rle(factor(rep(seq_len(R), res[[1]]), levels = seq_len(R)))
+  if (storeBlockLength) S4Vectors::mcols(br)$blockLength <- S4Vectors::Rle(as.integer(blockLength), length(br))
+  new("BootRanges", br)
+}
+
+# countOverlaps(x, bootRanges(y, ...)) per iteration without building the R x N table.
+# Returns list(iter_totals, iter_nranges, counts = integer matrix [length(x), R]).
+bootCounts <- function(y, x, blockLength, R = 1, seg = NULL, exclude = NULL, excludeOption = c("drop", "trim"),
+                       proportionLength = TRUE, type = c("bootstrap", "permute"), withinChrom = FALSE,
+                       rng = c("philox", "R"), seed = 0, iter0 = 0, perFeature = TRUE, device = 0L) {
+  excludeOption <- match.arg(excludeOption); type <- match.arg(type); rng <- match.arg(rng)
+  s <- .setup(y, blockLength, seg, exclude, excludeOption, proportionLength, type, withinChrom, device)
+  keep <- which(as.character(GenomicRanges::seqnames(x)) %in% s$lv)
+  xk <- x[keep]
+  .Call("nrb200_R_set_query", s$h, .seqid(xk, s$lv), GenomicRanges::start(xk), GenomicRanges::end(xk), .strand_code(xk))
+  d <- .draws(s, R, blockLength, rng)
+  res <- .Call("nrb200_R_run_counts", s$h, as.numeric(R), as.numeric(iter0), as.numeric(seed), d[[1]], d[[2]], d[[3]],
+               as.numeric(length(xk)), perFeature)
+  counts <- res[[3]]
+  if (!is.null(counts) && length(keep) != length(x)) {
+    full <- matrix(0L, length(x), R); full[keep, ] <- counts; counts <- full
+  }
+  list(iter_nranges = res[[1]], iter_totals = res[[2]], counts = counts)
+}
