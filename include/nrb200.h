@@ -140,6 +140,8 @@ typedef struct nrb200_stats {
     int64_t n_hits;        /* sum over iterations of ranges sampled (H of the byte model) */
     int64_t h2d_bytes;
     int64_t d2h_bytes;
+    double rows_kernel_ms;  /* rank path: boot_block_rows_kernel (draws + rows per block) */
+    double count_kernel_ms; /* rank path: boot_rank_count_kernel; streaming path: boot_count_kernel */
 } nrb200_stats;
 
 /* ---- fused path: bootstrap -> countOverlaps, the R x N table is never built -------- */

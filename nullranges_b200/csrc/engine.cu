@@ -71,6 +71,8 @@ struct nrb200_handle {
     bool own_stream = false;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     cudaStream_t copy_stream = nullptr;
+    cudaEvent_t split_ev = nullptr;       // set while a stats run wants the rows / count kernel split
+    std::vector<cudaEvent_t> batch_ev;    // 3 per batch: start, rows done, count done
     cudaEvent_t chunk_ev[16] = {};
     std::string error;
     int sm_count = 148;
@@ -616,6 +618,7 @@ int launch_rank(nrb200_handle *h, const BootParams &P, bool has_query) {
         boot_block_rows_kernel<1><<<dim3((unsigned)((P.n_blocks + 255) / 256), (unsigned)P.n_iter), 256, 0, h->stream>>>(P, X);
         ++launches;
     }
+    if (h->split_ev) cudaEventRecord(h->split_ev, h->stream);  // stats: end of the rows kernel
     if (has_query) {
         const FeatView F{h->f_src.as<int32_t>(), h->pair_off.as<int32_t>(), h->pair_rec.as<PairRec>()};
         const dim3 grid((unsigned)((P.n_query + 255) / 256), gy);
@@ -716,9 +719,21 @@ int run_counts_core(nrb200_handle *h, const nrb200_draws *d, bool want_counts, i
         P.draw_tab = h->draw_tab.as<int2>();
     }
     int k = 0;
+    const bool split = stats && rank_path_ok(h, has_query);
     for (int64_t r0 = 0; r0 < R; r0 += chunk, ++k) {
         const int64_t n = std::min(chunk, R - r0);
+        if (split) {
+            while (h->batch_ev.size() < (size_t)3 * (k + 1)) {
+                cudaEvent_t e;
+                NRB_CUDA(h, cudaEventCreate(&e));
+                h->batch_ev.push_back(e);
+            }
+            NRB_CUDA(h, cudaEventRecord(h->batch_ev[3 * k], h->stream));
+            h->split_ev = h->batch_ev[3 * k + 1];
+        }
         launches += launch_count(h, slice_params(P, r0, n), has_query);
+        h->split_ev = nullptr;
+        if (split) NRB_CUDA(h, cudaEventRecord(h->batch_ev[3 * k + 2], h->stream));
         NRB_CUDA(h, cudaGetLastError());
         if (pipelined) {
             cudaEvent_t &ev = h->chunk_ev[k % kChunkEvents];
@@ -745,6 +760,17 @@ int run_counts_core(nrb200_handle *h, const nrb200_draws *d, bool want_counts, i
         stats->total_ms = t_ms;
         stats->n_launches = launches;
         stats->n_hits = (int64_t)hits;
+        if (split) {
+            for (int b = 0; b < k; ++b) {
+                float a_ms = 0, b_ms = 0;
+                cudaEventElapsedTime(&a_ms, h->batch_ev[3 * b], h->batch_ev[3 * b + 1]);
+                cudaEventElapsedTime(&b_ms, h->batch_ev[3 * b + 1], h->batch_ev[3 * b + 2]);
+                stats->rows_kernel_ms += a_ms;
+                stats->count_kernel_ms += b_ms;
+            }
+        } else {
+            stats->count_kernel_ms = k_ms;  // streaming path: one kernel does both
+        }
         stats->h2d_bytes = d->rng_mode == NRB200_RNG_HOST ? R * h->plan.n_blocks() * (d->dst_tile ? 12 : 8) : 0;
     }
     return NRB200_OK;
@@ -806,6 +832,7 @@ void nrb200_destroy(nrb200_handle *h) {
         if (ev) cudaEventDestroy(ev);
     for (auto &ev : h->chunk_ev)
         if (ev) cudaEventDestroy(ev);
+    for (auto &ev : h->batch_ev) cudaEventDestroy(ev);
     if (h->copy_stream) {
         cudaStreamSynchronize(h->copy_stream);
         cudaStreamDestroy(h->copy_stream);
@@ -1001,6 +1028,8 @@ int nrb200_run_moments(nrb200_handle *h, const nrb200_draws *draws, int64_t batc
         if ((rc = fetch_u64_as_i64(h, h->d_iter_totals, d.n_iter, iter_totals ? iter_totals + r0 : nullptr))) return rc;
         NRB_CUDA(h, cudaStreamSynchronize(h->stream));
         acc.kernel_ms += st.kernel_ms;
+        acc.rows_kernel_ms += st.rows_kernel_ms;
+        acc.count_kernel_ms += st.count_kernel_ms;
         acc.total_ms += st.total_ms;
         acc.n_launches += st.n_launches + 1;
         acc.n_hits += st.n_hits;

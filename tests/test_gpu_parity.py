@@ -219,3 +219,34 @@ def test_cfg3_full_size(engine):
     for k in ("iter_nranges", "iter_totals", "feature_counts"):
         assert np.array_equal(got[k], ref[k]), k
     assert got["iter_nranges"].mean() < 1_000_000  # exclusion removes ranges
+
+
+def test_philox_moments_match_r_rng(engine):
+    """Production-mode (Philox) draws vs validation-mode (R RNG) draws: same bootstrap distribution.
+    Tolerances: mean of the per-iteration total within 4 standard errors of the difference; variance
+    ratio within [0.6, 1.6]; per-feature bootstrap means correlated > 0.98; block-start histogram of the
+    Philox draws uniform over the admissible starts (chi-square / dof < 1.5)."""
+    case = H.random_case(seed=123, n=20_000, n_seq=4, max_len=400_000, n_query=300, wmax=300, L_b=20_000)
+    plan, y, q, _ = H.oracle_objects(case, 0)
+    H.load_engine(engine, case, 0)
+    R = 600
+    d = H.draw_R(plan, 42, R)
+    a = engine.run_counts(Draws(n_iter=R, rng_mode=_lib.RNG_HOST, bait_seqid=d[0], bait_start=d[1]))
+    b = engine.run_counts(Draws(n_iter=R, rng_mode=_lib.RNG_PHILOX, seed=42))
+    ta, tb = a["iter_totals"].astype(float), b["iter_totals"].astype(float)
+    se = np.sqrt(ta.var(ddof=1) / R + tb.var(ddof=1) / R)
+    assert abs(ta.mean() - tb.mean()) < 4 * se
+    assert 0.6 < ta.var(ddof=1) / tb.var(ddof=1) < 1.6
+    assert abs(a["iter_nranges"].mean() - b["iter_nranges"].mean()) < 4 * np.sqrt(
+        a["iter_nranges"].var(ddof=1) / R + b["iter_nranges"].var(ddof=1) / R)
+    fa, fb = a["feature_counts"].mean(0), b["feature_counts"].mean(0)
+    assert np.corrcoef(fa, fb)[0, 1] > 0.98
+    # distribution of the Philox block draws themselves
+    pc, ps, _ = plan.draw_philox(42, 0, 2000)
+    L = case["seqlen"].astype(float)
+    share = np.bincount(pc.ravel(), minlength=4) / pc.size
+    assert np.all(np.abs(share - L / L.sum()) < 0.008)         # sequences drawn in proportion to length (about 5 s.e.)
+    c0 = ps[pc == 0]
+    span = (np.ceil(L[0] / 20_000) - 1) * 20_000 + 1
+    hist = np.histogram(c0, bins=20, range=(1, span + 1))[0]
+    assert ((hist - hist.mean()) ** 2 / hist.mean()).sum() / 19 < 1.5
