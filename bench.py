@@ -190,6 +190,8 @@ def run_gpu(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; libnrb200 has no CPU path (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
+    if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+        os.environ["NCCL_DEBUG"] = "WARN"  # keep stdout to the one JSON line
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
@@ -207,15 +209,23 @@ def run_gpu(args):
         d = Draws(n_iter=R, rng_mode=_lib.RNG_PHILOX, seed=2024, iter0=(step * world + rank) * R)
         return eng.run_counts_resident(d, want_counts=True, want_stats=want_stats)
 
+    pending = []
+
     def gather_small():
+        """All-gather of this step's [2 x R] per-iteration vectors, asynchronous: it overlaps the next
+        step's kernels; wait_gathers() (inside the next step's timed bracket) accounts for it."""
         if world == 1:
             return
         nr_p, tot_p, _ = eng.resident_pointers()
         mine = torch.stack([torch.as_tensor(DevView(nr_p, R, "<i8"), device="cuda"),
-                            torch.as_tensor(DevView(tot_p, R, "<i8"), device="cuda")])
-        out = torch.empty((world,) + tuple(mine.shape), dtype=mine.dtype, device="cuda")
-        dist.all_gather_into_tensor(out, mine)
-        return out
+                            torch.as_tensor(DevView(tot_p, R, "<i8"), device="cuda")])  # staging copy: the engine reuses its buffers
+        out = torch.empty((world * 2, R), dtype=mine.dtype, device="cuda")
+        pending.append((dist.all_gather_into_tensor(out, mine, async_op=True), out))
+
+    def wait_gathers():
+        while pending:
+            work, out = pending.pop(0)
+            work.wait()
 
     def barrier():
         if world > 1:
@@ -225,7 +235,9 @@ def run_gpu(args):
     with torch.cuda.stream(stream):
         for w in range(args.warmup):
             step_resident(w, False)
+            wait_gathers()
             gather_small()
+        wait_gathers()
         barrier()
         clocks = ClockSampler(local)
         clocks.start()
@@ -236,7 +248,10 @@ def run_gpu(args):
             flush.fill_(s & 0xFF)  # L2 flush between timed steps (outside the per-step events)
             ev[s][0].record(stream)
             st = step_resident(args.warmup + s, True)
+            wait_gathers()          # the previous step's gather ran under this step's kernels
             gather_small()
+            if s == args.steps - 1:
+                wait_gathers()      # the last one has nothing to hide behind
             ev[s][1].record(stream)
             kernel_ms += st["kernel_ms"]
             rows_ms += st["rows_kernel_ms"]

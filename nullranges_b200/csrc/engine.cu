@@ -11,6 +11,7 @@
 //   draws    : validation mode only, bait_seq/bait_start(/dst_tile) [R x B]
 //   results  : iter_nranges[R] iter_totals[R] (uint64), counts[R x G]
 #include <algorithm>
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -26,6 +27,23 @@
 #include "plan.h"
 
 namespace nrb {
+
+// NRB200_TRACE=1: host-side stage timings on stderr (development aid)
+struct Trace {
+    static bool on() {
+        static const bool v = getenv("NRB200_TRACE") != nullptr;
+        return v;
+    }
+    const char *name;
+    std::chrono::steady_clock::time_point t0;
+    explicit Trace(const char *n) : name(n), t0(std::chrono::steady_clock::now()) {}
+    void lap(const char *what) {
+        if (!on()) return;
+        const auto t1 = std::chrono::steady_clock::now();
+        fprintf(stderr, "[nrb200] %s/%s %.3f ms\n", name, what, std::chrono::duration<double, std::milli>(t1 - t0).count());
+        t0 = t1;
+    }
+};
 
 static thread_local std::string g_create_error;
 
@@ -57,6 +75,7 @@ struct RangeSet {
     std::vector<int32_t> h_start, h_end, h_pmax, h_src, h_seq_off;  // host mirror (kept for query/exclude)
     std::vector<int8_t> h_strand;
     std::vector<int32_t> max_end;  // [n_seq] largest end on the sequence (INT32_MIN when empty)
+    bool on_device = false;        // query: device copies are made on first use (the rank path needs none)
     bool sorted_input = false;     // the caller's order was already canonical
     DevMem start, end, pmax, src, strand, seq_off, seqid;
 };
@@ -97,7 +116,7 @@ struct nrb200_handle {
     Plan plan;
     DevMem tile_seq, tile_start, bait_width, sampler_i64, sampler_i32;
     SamplerView sampler_view{};
-    bool slices_dirty = true;
+    bool slices_dirty = true, have_pmax_table = false;
     DevMem q_tile_lo, q_tile_hi, x_tile_lo, x_tile_hi, pair_off, pair_rec, f_src, tile_x_off, tile_x_rec;
     int64_t n_pairs = 0;
     bool tiles_in_bounds = false;
@@ -137,8 +156,24 @@ int upload(nrb200_handle *h, DevMem &dst, const T *src, size_t n) {
 }
 
 // Canonicalise one set of ranges on the host and mirror it to the device.
+int range_set_to_device(nrb200_handle *h, RangeSet &rs) {
+    if (rs.on_device) return NRB200_OK;
+    int rc;
+    const size_t n = (size_t)rs.n;
+    if ((rc = upload(h, rs.start, rs.h_start.data(), n))) return rc;
+    if ((rc = upload(h, rs.end, rs.h_end.data(), n))) return rc;
+    if ((rc = upload(h, rs.pmax, rs.h_pmax.data(), n))) return rc;
+    if ((rc = upload(h, rs.src, rs.h_src.data(), n))) return rc;
+    if ((rc = upload(h, rs.seq_off, rs.h_seq_off.data(), rs.h_seq_off.size()))) return rc;
+    if (rs.stranded && (rc = upload(h, rs.strand, rs.h_strand.data(), n))) return rc;
+    NRB_CUDA(h, cudaStreamSynchronize(h->stream));
+    rs.on_device = true;
+    return NRB200_OK;
+}
+
 int load_range_set(nrb200_handle *h, RangeSet &rs, const char *what, int64_t n, const int32_t *seqid,
-                   const int32_t *start, const int32_t *end, const int8_t *strand, bool keep_seqid_dev) {
+                   const int32_t *start, const int32_t *end, const int8_t *strand, bool keep_seqid_dev,
+                   bool defer_device = false) {
     if (n < 0 || n > (int64_t)INT32_MAX - 64) return fail(h, NRB200_ERR_INVALID, std::string(what) + ": length out of range");
     if (n > 0 && (!seqid || !start || !end)) return fail(h, NRB200_ERR_INVALID, std::string(what) + ": null coordinate pointer");
     const int C = h->n_seq;
@@ -199,13 +234,10 @@ int load_range_set(nrb200_handle *h, RangeSet &rs, const char *what, int64_t n, 
     rs.max_end.assign(C, INT32_MIN);
     for (int c = 0; c < C; ++c)
         if (rs.h_seq_off[c + 1] > rs.h_seq_off[c]) rs.max_end[c] = rs.h_pmax[rs.h_seq_off[c + 1] - 1];
+    rs.on_device = false;
+    if (defer_device) return NRB200_OK;
     int rc;
-    if ((rc = upload(h, rs.start, rs.h_start.data(), n))) return rc;
-    if ((rc = upload(h, rs.end, rs.h_end.data(), n))) return rc;
-    if ((rc = upload(h, rs.pmax, rs.h_pmax.data(), n))) return rc;
-    if ((rc = upload(h, rs.src, rs.h_src.data(), n))) return rc;
-    if ((rc = upload(h, rs.seq_off, rs.h_seq_off.data(), (size_t)C + 1))) return rc;
-    if (stranded && (rc = upload(h, rs.strand, rs.h_strand.data(), n))) return rc;
+    if ((rc = range_set_to_device(h, rs))) return rc;
     if (keep_seqid_dev && (rc = upload(h, rs.seqid, h_seqid.data(), n))) return rc;
     NRB_CUDA(h, cudaStreamSynchronize(h->stream));  // host vectors above may go out of scope
     return NRB200_OK;
@@ -225,6 +257,8 @@ int load_y_device(nrb200_handle *h, int64_t n, const int32_t *seqid, const int32
     if ((rc = upload(h, y.start, start, (size_t)n))) return rc;
     if ((rc = upload(h, y.end, end, (size_t)n))) return rc;
     if (strand && (rc = upload(h, y.strand, strand, (size_t)n))) return rc;
+    Trace tr("load_y_device");
+    tr.lap("enqueue_h2d");
     // scratch: InspectOut | seq_count[C] | seq_max_end[C]
     const size_t words = 4 + 2 * (size_t)C;
     NRB_CUDA(h, h->inspect_dev.reserve(words * 4));
@@ -241,6 +275,7 @@ int load_y_device(nrb200_handle *h, int64_t n, const int32_t *seqid, const int32
     std::vector<int32_t> res(words);
     NRB_CUDA(h, cudaMemcpyAsync(res.data(), base, words * 4, cudaMemcpyDeviceToHost, h->stream));
     NRB_CUDA(h, cudaStreamSynchronize(h->stream));
+    tr.lap("inspect+sync");
     if (res[0] != 0 || res[1] != 0) return 1;  // invalid (host path names the problem) or unsorted
     y.n = n;
     y.sorted_input = true;
@@ -326,8 +361,7 @@ int build_rank_tables(nrb200_handle *h) {
     const unsigned grid = (unsigned)((entries + threads - 1) / threads);
     build_rank_table_kernel<<<grid, threads, 0, h->stream>>>(y.start.as<int32_t>(), y.seq_off.as<int32_t>(),
                                                              h->rank_off_dev.as<int64_t>(), C, shift, h->rank_start.as<uint32_t>());
-    build_rank_table_kernel<<<grid, threads, 0, h->stream>>>(y.pmax.as<int32_t>(), y.seq_off.as<int32_t>(),
-                                                             h->rank_off_dev.as<int64_t>(), C, shift, h->rank_pmax.as<uint32_t>());
+    h->have_pmax_table = false;  // only the streaming kernels need it: built on first use
     build_rank_table_kernel<<<grid, threads, 0, h->stream>>>(h->end_sorted.as<int32_t>(), y.seq_off.as<int32_t>(),
                                                              h->rank_off_dev.as<int64_t>(), C, shift, h->rank_end.as<uint32_t>());
     NRB_CUDA(h, cudaGetLastError());
@@ -389,6 +423,7 @@ static std::vector<std::vector<Interval>> merged_exclude(const nrb200_handle *h)
 }
 
 int build_pairs(nrb200_handle *h) {
+    Trace tr("build_pairs");
     const Plan &p = h->plan;
     const RangeSet &q = h->query;
     const int C = h->n_seq;
@@ -422,84 +457,103 @@ int build_pairs(nrb200_handle *h) {
         }
     }
     int rc;
-    if ((rc = upload(h, h->tile_x_off, x_off.data(), (size_t)B + 1))) return rc;
-    if ((rc = upload(h, h->tile_x_rec, x_rec.data(), x_rec.size()))) return rc;
+    if (has_excl) {
+        if ((rc = upload(h, h->tile_x_off, x_off.data(), (size_t)B + 1))) return rc;
+        if ((rc = upload(h, h->tile_x_rec, x_rec.data(), x_rec.size()))) return rc;
+    }
     if (G == 0) {
         NRB_CUDA(h, cudaStreamSynchronize(h->stream));
         return NRB200_OK;
     }
 
-    // ---- per feature: tiles of each sequence in ascending start order with the running max of their ends
+    // ---- per feature.  Tiles of each sequence in ascending start order with the running max of
+    // their ends; features come in canonical (start-sorted) order, so the first tile that can still
+    // reach a feature only moves forward.  Two passes over the same enumeration: list lengths, then
+    // (after grouping features by length) the records, written straight into their final place.
     std::vector<std::vector<int32_t>> by_seq(C);
     for (int64_t t = 0; t < B; ++t) by_seq[p.tile_seq[t]].push_back((int32_t)t);
-    std::vector<int64_t> off(G + 1, 0);
-    std::vector<PairRec> recs;
-    recs.reserve((size_t)G + G / 4);
-    std::vector<int64_t> ts, te_max;
+    std::vector<std::vector<int64_t>> ts(C), te(C), te_max(C);
     for (int c = 0; c < C; ++c) {
         auto &v = by_seq[c];
-        std::sort(v.begin(), v.end(), [&](int32_t a, int32_t b) {
-            return p.tile_start[a] != p.tile_start[b] ? p.tile_start[a] < p.tile_start[b] : a < b;
-        });
-        ts.resize(v.size());
-        te_max.resize(v.size());
+        bool sorted = true;
+        for (size_t j = 1; j < v.size(); ++j) sorted &= p.tile_start[v[j - 1]] <= p.tile_start[v[j]];
+        if (!sorted)
+            std::sort(v.begin(), v.end(), [&](int32_t a, int32_t b) {
+                return p.tile_start[a] != p.tile_start[b] ? p.tile_start[a] < p.tile_start[b] : a < b;
+            });
+        ts[c].resize(v.size());
+        te[c].resize(v.size());
+        te_max[c].resize(v.size());
         int64_t m = INT64_MIN;
         for (size_t j = 0; j < v.size(); ++j) {
-            ts[j] = p.tile_start[v[j]];
-            m = std::max<int64_t>(m, ts[j] + p.bait_width[v[j]] - 1);
-            te_max[j] = m;
+            ts[c][j] = p.tile_start[v[j]];
+            te[c][j] = ts[c][j] + p.bait_width[v[j]] - 1;
+            m = std::max(m, te[c][j]);
+            te_max[c][j] = m;
         }
-        const int32_t L = (int32_t)h->seqlen[c];
-        for (int32_t k = q.h_seq_off[c]; k < q.h_seq_off[c + 1]; ++k) {
-            const int64_t gs = q.h_start[k], ge = q.h_end[k];
-            if (gs <= L) {
-                int64_t j = (int64_t)(std::upper_bound(ts.begin(), ts.end(), ge + reach) - ts.begin()) - 1;
-                const size_t first_rec = recs.size();
-                for (; j >= 0 && te_max[j] + reach >= gs; --j) {
-                    const int32_t t = v[j];
-                    const int64_t t_s = ts[j], t_e = t_s + p.bait_width[t] - 1;
-                    if (t_e + reach < gs) continue;
-                    auto push = [&](int64_t ws, int64_t we, int sign) {
-                        recs.push_back(PairRec{t, (int32_t)ws, (int32_t)std::min<int64_t>(we, INT32_MAX / 2), sign, (int32_t)t_s,
-                                               p.bait_width[t], L, 0});
-                    };
-                    push(gs, ge, +1);
-                    if (has_excl) {
-                        // regions a range landing on the tile can overlap together with the feature
+    }
+    // calls emit(tile, ws, we, sign) for every signed window of every feature, features in canonical order
+    auto enumerate = [&](auto &&begin_feature, auto &&emit) {
+        for (int c = 0; c < C; ++c) {
+            const auto &v = by_seq[c];
+            const int64_t L = h->seqlen[c], nt = (int64_t)v.size();
+            int64_t lo = 0;
+            for (int32_t k = q.h_seq_off[c]; k < q.h_seq_off[c + 1]; ++k) {
+                begin_feature(k);
+                const int64_t gs = q.h_start[k], ge = q.h_end[k];
+                if (gs > L) continue;
+                while (lo < nt && te_max[c][lo] + reach < gs) ++lo;
+                for (int64_t j = lo; j < nt && ts[c][j] <= ge + reach; ++j) {
+                    if (te[c][j] + reach < gs) continue;
+                    emit(k, v[j], gs, ge, +1);
+                    if (has_excl) {  // regions a range landing on the tile can overlap together with the feature
                         size_t f, l;
-                        x_run(c, std::max(t_s - reach, gs - reach), std::min(t_e + reach, ge + reach), f, l);
+                        x_run(c, std::max(ts[c][j] - reach, gs - reach), std::min(te[c][j] + reach, ge + reach), f, l);
                         for (size_t i = f; i < l; ++i) {
-                            push(std::max(X[c][i].s, gs), std::min(X[c][i].e, ge), -1);
+                            emit(k, v[j], std::max(X[c][i].s, gs), std::min(X[c][i].e, ge), -1);
                             if (i + 1 < l && X[c][i + 1].s - X[c][i].e <= reach)
-                                push(std::max(X[c][i + 1].s, gs), std::min(X[c][i].e, ge), +1);
+                                emit(k, v[j], std::max(X[c][i + 1].s, gs), std::min(X[c][i].e, ge), +1);
                         }
                     }
                 }
-                std::reverse(recs.begin() + first_rec, recs.end());
             }
-            if (recs.size() > (size_t)INT32_MAX / 2) return fail(h, NRB200_ERR_UNSUPPORTED, "too many (feature, tile) pairs");
-            off[k + 1] = (int64_t)recs.size();
         }
+    };
+    std::vector<int32_t> len(G, 0);
+    enumerate([](int32_t) {}, [&](int32_t k, int32_t, int64_t, int64_t, int) { ++len[k]; });
+    // Visit order of the count kernel: features grouped by list length (stable counting sort, so
+    // neighbours in a group are neighbours on the genome): the lanes of a warp then loop equally often.
+    constexpr int kBins = 64;
+    int64_t bin_start[kBins + 1] = {0};
+    auto bin = [&](int64_t k) { return std::min<int>(len[k], kBins - 1); };
+    for (int64_t k = 0; k < G; ++k) bin_start[bin(k) + 1]++;
+    for (int b = 0; b < kBins; ++b) bin_start[b + 1] += bin_start[b];
+    std::vector<int32_t> pos_of(G), f_src(G), f_off(G + 1, 0);
+    for (int64_t k = 0; k < G; ++k) pos_of[k] = (int32_t)bin_start[bin(k)]++;
+    for (int64_t k = 0; k < G; ++k) {
+        f_src[pos_of[k]] = q.h_src[k];
+        f_off[pos_of[k] + 1] = len[k];
     }
-    h->n_pairs = (int64_t)recs.size();
-    // Visit order of the count kernel: features grouped by list length (stable, so neighbours in a
-    // group are neighbours on the genome): the lanes of a warp then loop equally often.
-    std::vector<int32_t> order(G);
-    std::iota(order.begin(), order.end(), 0);
-    std::stable_sort(order.begin(), order.end(), [&](int32_t a, int32_t b) { return off[a + 1] - off[a] < off[b + 1] - off[b]; });
-    std::vector<int32_t> f_src(G), f_off(G + 1, 0);
-    std::vector<PairRec> f_recs;
-    f_recs.reserve(recs.size());
+    int64_t total = 0;
     for (int64_t i = 0; i < G; ++i) {
-        const int32_t k = order[i];
-        f_src[i] = q.h_src[k];
-        f_recs.insert(f_recs.end(), recs.begin() + off[k], recs.begin() + off[k + 1]);
-        f_off[i + 1] = (int32_t)f_recs.size();
+        total += f_off[i + 1];
+        if (total > (int64_t)INT32_MAX / 2) return fail(h, NRB200_ERR_UNSUPPORTED, "too many (feature, tile) pairs");
+        f_off[i + 1] = (int32_t)total;
     }
+    h->n_pairs = total;
+    std::vector<PairRec> f_recs((size_t)total);
+    int64_t cursor = 0;
+    enumerate([&](int32_t k) { cursor = f_off[pos_of[k]]; },
+              [&](int32_t, int32_t t, int64_t ws, int64_t we, int sign) {
+                  f_recs[cursor++] = PairRec{t, (int32_t)ws, (int32_t)std::min<int64_t>(we, INT32_MAX / 2), sign, p.tile_start[t],
+                                             p.bait_width[t], (int32_t)h->seqlen[p.tile_seq[t]], 0};
+              });
+    tr.lap("lists");
     if ((rc = upload(h, h->f_src, f_src.data(), (size_t)G))) return rc;
     if ((rc = upload(h, h->pair_off, f_off.data(), (size_t)G + 1))) return rc;
     if ((rc = upload(h, h->pair_rec, f_recs.data(), f_recs.size()))) return rc;
     NRB_CUDA(h, cudaStreamSynchronize(h->stream));
+    tr.lap("upload");
     return NRB200_OK;
 }
 
@@ -513,11 +567,24 @@ bool rank_path_ok(const nrb200_handle *h, bool with_query) {
     return true;
 }
 
+// rank table over the running max of end: locate_block() of the streaming kernels
+int ensure_pmax_table(nrb200_handle *h) {
+    if (h->have_pmax_table) return NRB200_OK;
+    const int64_t entries = h->rank_off[h->n_seq];
+    build_rank_table_kernel<<<(unsigned)((entries + 255) / 256), 256, 0, h->stream>>>(
+        h->y.pmax.as<int32_t>(), h->y.seq_off.as<int32_t>(), h->rank_off_dev.as<int64_t>(), h->n_seq, h->rank_shift,
+        h->rank_pmax.as<uint32_t>());
+    NRB_CUDA(h, cudaGetLastError());
+    h->have_pmax_table = true;
+    return NRB200_OK;
+}
+
 int prepare(nrb200_handle *h) {
     if (!h->have_y) return fail(h, NRB200_ERR_STATE, "nrb200_set_ranges() has not been called");
     if (!h->have_plan) return fail(h, NRB200_ERR_STATE, "nrb200_set_plan() has not been called");
     if (h->slices_dirty) {
         int rc;
+        Trace tr("prepare");
         h->tiles_in_bounds = true;
         for (int64_t t = 0; t < h->plan.n_blocks(); ++t)
             if (h->plan.tile_start[t] > h->seqlen[h->plan.tile_seq[t]]) h->tiles_in_bounds = false;
@@ -529,10 +596,13 @@ int prepare(nrb200_handle *h) {
             rc = build_pairs(h);
             h->query.n = g_keep;
             if (rc) return rc;
+            tr.lap("build_pairs");
         }
         // the streaming kernels (count without the rank path, and the fill pass) test exclusion per range
         if (h->excl.n && (rc = build_slices(h, h->excl, h->x_tile_lo, h->x_tile_hi))) return rc;
+        if (h->query.n && !rank_q && (rc = range_set_to_device(h, h->query))) return rc;
         if (h->query.n && !rank_q && (rc = build_slices(h, h->query, h->q_tile_lo, h->q_tile_hi))) return rc;
+        if (((h->query.n && !rank_q) || !rank_rows) && (rc = ensure_pmax_table(h))) return rc;
         h->slices_dirty = false;
     }
     return NRB200_OK;
@@ -857,10 +927,13 @@ int nrb200_set_ranges(nrb200_handle *h, int64_t n, int32_t n_seq, const int64_t 
     h->seqlen.assign(seqlengths, seqlengths + n_seq);
     int rc;
     if ((rc = upload(h, h->seqlen_dev, seqlengths, (size_t)n_seq))) return rc;
+    Trace tr("set_ranges");
     rc = load_y_device(h, n, seqid, start, end, strand);
     if (rc < 0) return rc;
+    tr.lap("load_y_device");
     if (rc == 1 && (rc = load_range_set(h, h->y, "y", n, seqid, start, end, strand, true))) return rc;
     if ((rc = build_rank_tables(h))) return rc;
+    tr.lap("build_rank_tables");
     // the large host mirror of y is not needed again
     std::vector<int32_t>().swap(h->y.h_start);
     std::vector<int32_t>().swap(h->y.h_end);
@@ -890,7 +963,7 @@ static int set_side(nrb200_handle *h, RangeSet &rs, const char *what, int64_t n,
         rs.n = 0;
         return NRB200_OK;
     }
-    return load_range_set(h, rs, what, n, seqid, start, end, strand, false);
+    return load_range_set(h, rs, what, n, seqid, start, end, strand, false, &rs == &h->query);
 }
 
 int nrb200_set_query(nrb200_handle *h, int64_t n, const int32_t *seqid, const int32_t *start, const int32_t *end,
@@ -1055,8 +1128,12 @@ int nrb200_count_observed(nrb200_handle *h, int32_t *feature_counts, int64_t *to
     if (!h) return NRB200_ERR_INVALID;
     NRB_CUDA(h, cudaSetDevice(h->device));
     if (!h->have_y) return fail(h, NRB200_ERR_STATE, "nrb200_set_ranges() has not been called");
+    if (h->query.n == 0) return fail(h, NRB200_ERR_STATE, "nrb200_set_query() has not been called");
+    {
+        int rc0 = range_set_to_device(h, h->query);
+        if (rc0) return rc0;
+    }
     const RangeSet &q = h->query;
-    if (q.n == 0) return fail(h, NRB200_ERR_STATE, "nrb200_set_query() has not been called");
     DevMem counts, tot;
     NRB_CUDA(h, counts.reserve(q.n * 4));
     NRB_CUDA(h, tot.reserve(8));
@@ -1093,6 +1170,7 @@ int nrb200_run_materialize(nrb200_handle *h, const nrb200_draws *draws, int64_t 
     NRB_CUDA(h, cudaSetDevice(h->device));
     int rc;
     if ((rc = prepare(h))) return rc;
+    if ((rc = ensure_pmax_table(h))) return rc;  // the fill kernel locates the hit windows
     NRB_CUDA(h, cudaEventRecord(h->ev[0], h->stream));
     if ((rc = stage_draws(h, draws))) return rc;
     const int64_t R = draws->n_iter, B = h->plan.n_blocks(), items = R * B;

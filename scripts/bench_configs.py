@@ -68,3 +68,23 @@ if not only or "4" in only:
     m = eng.run_moments(Draws(n_iter=R, seed=1), observed=obs)
     report(f"cfg4 10M points withinChrom vs 200k enhancers, moments, R={R}", R, B, len(x), m["stats"],
            {"observed_total": int(tot), "mean_boot_total": float(m["iter_totals"].mean()), "setup_s": round(time.time() - t0, 1)})
+
+if not only or "m" in only:
+    # materialised BootRanges table (the literal drop-in return value): 24*H + 16*B bytes per iteration
+    y = synth.atac_peaks(1_000_000, seed=3)
+    eng.set_ranges(y.seqlengths, y.seqid, y.start, y.end); eng.clear_exclude(); eng.clear_query()
+    B = eng.set_plan(_lib.UNSEG_ACROSS, 500_000)
+    import ctypes as C
+    from nullranges_b200._lib import Stats, ptr
+    for R in (20, 100):
+        best_ms, rows = None, 0
+        for _ in range(3):
+            offs = np.zeros(R + 1, np.int64); st = Stats(); d = Draws(n_iter=R, seed=1).to_c()
+            eng._check(eng._lib.nrb200_run_materialize(eng._h, C.byref(d), ptr(offs, C.c_int64), C.byref(st)))
+            rows = int(offs[-1])
+            best_ms = st.kernel_ms if best_ms is None else min(best_ms, st.kernel_ms)
+        alg = 24.0 * rows + 16.0 * B * R  # read 8*H, write 16*H (+ we also write seqid: 20*H)
+        print(json.dumps({"config": f"materialise cfg2 ranges, R={R}", "rows": rows, "kernel_ms": round(best_ms, 3),
+                          "iters_per_s": round(R / best_ms * 1e3, 1), "algorithmic_GBps": round(alg / best_ms / 1e6, 1),
+                          "frac_of_measured_hbm": round(alg / best_ms / 1e6 / PEAK, 3),
+                          "actual_bytes_GBps": round((28.0 * rows) / best_ms / 1e6, 1)}), flush=True)
