@@ -288,9 +288,7 @@ int load_y_device(nrb200_handle *h, int64_t n, const int32_t *seqid, const int32
         y.max_end[c] = res[4 + C + c];
     }
     if ((rc = upload(h, y.seq_off, y.h_seq_off.data(), (size_t)C + 1))) return rc;
-    NRB_CUDA(h, y.src.reserve(n * 4));
-    NRB_CUDA(h, y.pmax.reserve(n * 4));
-    iota_kernel<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(y.src.as<int32_t>(), n);
+    NRB_CUDA(h, y.pmax.reserve(n * 4));  // src stays unset: identity (kernels take nullptr for it)
     // running max of end within each sequence
     size_t tmp_bytes = 0;
     NRB_CUDA(h, cub::DeviceScan::InclusiveScanByKey(nullptr, tmp_bytes, y.seqid.as<int32_t>(), y.end.as<int32_t>(),
@@ -639,7 +637,7 @@ BootParams make_params(nrb200_handle *h, const nrb200_draws *d) {
     BootParams P{};
     const RangeSet &y = h->y;
     P.y = RangesView{y.start.as<int32_t>(), y.end.as<int32_t>(), y.pmax.as<int32_t>(),
-                     y.stranded ? y.strand.as<int8_t>() : nullptr, y.src.as<int32_t>(), y.seq_off.as<int32_t>(),
+                     y.stranded ? y.strand.as<int8_t>() : nullptr, y.sorted_input ? nullptr : y.src.as<int32_t>(), y.seq_off.as<int32_t>(),
                      h->end_sorted.as<int32_t>(), h->rank_start.as<uint32_t>(), h->rank_pmax.as<uint32_t>(),
                      h->rank_end.as<uint32_t>(), h->seq_info_dev.as<int4>(), h->rank_shift};
     const RangeSet &q = h->query, &x = h->excl;
@@ -1189,8 +1187,15 @@ int nrb200_run_materialize(nrb200_handle *h, const nrb200_draws *draws, int64_t 
     P.n_hits = h->d_n_hits.as<unsigned long long>();
     NRB_CUDA(h, cudaEventRecord(h->ev[1], h->stream));
     int count_launches = 0;
+    const bool rank_rows = rank_path_ok(h, false);
+    if (rank_rows && items > 0) {  // the rows kernel leaves its draws for the fill kernel
+        NRB_CUDA(h, h->draw_tab.reserve((size_t)items * sizeof(int2)));
+        P.draw_tab = h->draw_tab.as<int2>();
+    }
     for (int64_t r0 = 0; r0 < R; r0 += kMaxBatch) {
-        count_launches += launch_count(h, slice_params(P, r0, std::min(kMaxBatch, R - r0)), false);
+        BootParams Q = slice_params(P, r0, std::min(kMaxBatch, R - r0));
+        if (P.draw_tab) Q.draw_tab = P.draw_tab + r0 * B;
+        count_launches += launch_count(h, Q, false);
         NRB_CUDA(h, cudaGetLastError());
     }
     if (R > 0)
@@ -1204,16 +1209,22 @@ int nrb200_run_materialize(nrb200_handle *h, const nrb200_draws *draws, int64_t 
     if ((rc = upload(h, h->iter_off_dev, offs.data(), (size_t)R + 1))) return rc;
     for (DevMem *m : {&h->row_seq, &h->row_start, &h->row_end, &h->row_src, &h->row_block})
         NRB_CUDA(h, m->reserve(std::max<int64_t>(rows, 1) * 4));
-    RowsOut O{h->row_seq.as<int32_t>(), h->row_start.as<int32_t>(), h->row_end.as<int32_t>(), h->row_src.as<int32_t>(),
-              h->row_block.as<int32_t>(), h->iter_off_dev.as<int64_t>(), h->within_off.as<int32_t>()};
+    int fill_launches = 0;
     if (items > 0) {
-        const unsigned grid = (unsigned)std::min<int64_t>((items + 7) / 8, (int64_t)h->sm_count * 64);
         const bool st = h->y.stranded && h->excl.n && h->excl.stranded;
         const bool hx = h->excl.n > 0;
-        if (st && hx) boot_fill_kernel<true, true><<<grid, 256, 0, h->stream>>>(P, O);
-        else if (hx) boot_fill_kernel<false, true><<<grid, 256, 0, h->stream>>>(P, O);
-        else boot_fill_kernel<false, false><<<grid, 256, 0, h->stream>>>(P, O);
-        NRB_CUDA(h, cudaGetLastError());
+        const int64_t kFillBatch = 32768;  // gridDim.y
+        for (int64_t r0 = 0; r0 < R; r0 += kFillBatch, ++fill_launches) {
+            BootParams Q = slice_params(P, r0, std::min(kFillBatch, R - r0));
+            if (P.draw_tab) Q.draw_tab = P.draw_tab + r0 * B;
+            const RowsOut O{h->row_seq.as<int32_t>(), h->row_start.as<int32_t>(), h->row_end.as<int32_t>(), h->row_src.as<int32_t>(),
+                            h->row_block.as<int32_t>(), h->iter_off_dev.as<int64_t>() + r0, h->within_off.as<int32_t>() + r0 * B};
+            const dim3 grid((unsigned)std::min<int64_t>((B + 7) / 8, 65535), (unsigned)Q.n_iter);
+            if (st && hx) boot_fill_kernel<true, true><<<grid, 256, 0, h->stream>>>(Q, O);
+            else if (hx) boot_fill_kernel<false, true><<<grid, 256, 0, h->stream>>>(Q, O);
+            else boot_fill_kernel<false, false><<<grid, 256, 0, h->stream>>>(Q, O);
+            NRB_CUDA(h, cudaGetLastError());
+        }
     }
     NRB_CUDA(h, cudaEventRecord(h->ev[2], h->stream));
     NRB_CUDA(h, cudaStreamSynchronize(h->stream));
@@ -1228,7 +1239,7 @@ int nrb200_run_materialize(nrb200_handle *h, const nrb200_draws *draws, int64_t 
         std::memset(stats, 0, sizeof *stats);
         stats->kernel_ms = k_ms;
         stats->total_ms = t_ms;
-        stats->n_launches = items > 0 ? count_launches + 2 : 0;
+        stats->n_launches = items > 0 ? count_launches + 1 + fill_launches : 0;
         stats->n_hits = (int64_t)hits;
     }
     return NRB200_OK;

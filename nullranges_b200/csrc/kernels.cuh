@@ -27,7 +27,7 @@ struct RangesView {            // canonical (seqname, start, end) order
     const int32_t *end;
     const int32_t *pmax;       // running max of end within the sequence
     const int8_t *strand;      // nullptr when every strand is '*'
-    const int32_t *src;        // index in the caller's order
+    const int32_t *src;        // index in the caller's order; nullptr = identity (the input was already canonical)
     const int32_t *seq_off;    // [n_seq + 1]
         const int32_t *end_sorted; // ends of the sequence in ascending order (rank queries)
     const uint32_t *rank_start;  // packed rank tables, see "direct-address rank tables" below
@@ -191,7 +191,12 @@ struct Item {
 __device__ __forceinline__ Item load_item(const BootParams &P, int64_t r, int64_t b) {
     Item it;
     const int64_t flat = r * P.n_blocks + b;
-    if (P.rng_mode == NRB200_RNG_PHILOX) {
+    if (P.draw_tab) {  // the rows kernel of the rank path already drew this block
+        const int2 d = __ldg(P.draw_tab + flat);
+        it.bait_seq = d.x;
+        it.bait_start = d.y;
+        it.tile = (int)b;
+    } else if (P.rng_mode == NRB200_RNG_PHILOX) {
         draw_block(P, (uint64_t)(P.iter0 + r), b, it.bait_seq, it.bait_start);
         it.tile = (int)b;
     } else {
@@ -325,37 +330,50 @@ struct RowsOut {
     const int32_t *within_off;    // [n_iter x n_blocks]
 };
 
+// grid = (block groups, iterations); one warp per (iteration, block), 64 candidate ranges per
+// loop trip (two independent loads per lane), ballot-compacted writes of the five columns.
 template <bool STRANDED, bool HAS_EXCL>
 __global__ void __launch_bounds__(256) boot_fill_kernel(const BootParams P, const RowsOut O) {
     const int lane = threadIdx.x & (kWarp - 1);
-    const int64_t warps_total = (int64_t)gridDim.x * (blockDim.x / kWarp);
-    const int64_t warp0 = (int64_t)blockIdx.x * (blockDim.x / kWarp) + (threadIdx.x / kWarp);
-    const int64_t n_items = P.n_iter * P.n_blocks;
-    for (int64_t item = warp0; item < n_items; item += warps_total) {
-        const int64_t r = item / P.n_blocks, b = item - r * P.n_blocks;
+    const unsigned below = (1u << lane) - 1u;
+    const int64_t r = blockIdx.y;
+    const int64_t row0 = __ldg(O.iter_off + r);
+    for (int64_t b = (int64_t)blockIdx.x * (blockDim.x / kWarp) + (threadIdx.x / kWarp); b < P.n_blocks;
+         b += (int64_t)gridDim.x * (blockDim.x / kWarp)) {
         const Item it = load_item(P, r, b);
-        int64_t out = O.iter_off[r] + O.within_off[item];
-        for (int32_t base = it.lo; base < it.hi; base += kWarp) {
-            const int32_t i = base + lane;
-            bool keep = false;
-            int32_t s2 = 0, e2 = 0;
-            if (i < it.hi) {
-                keep = transform(P, it, __ldg(P.y.start + i), __ldg(P.y.end + i), s2, e2);
-                if (keep && HAS_EXCL) {
-                    const int strand = (STRANDED && P.y.strand) ? __ldg(P.y.strand + i) : 0;
-                    keep = !excluded<STRANDED>(P.excl, it.tile, s2, e2, strand);
-                }
+        int64_t out = row0 + __ldg(O.within_off + r * P.n_blocks + b);
+        for (int32_t base = it.lo; base < it.hi; base += 2 * kWarp) {
+            const int32_t i0 = base + lane, i1 = i0 + kWarp;
+            const bool in0 = i0 < it.hi, in1 = i1 < it.hi;
+            int32_t st0 = 0, en0 = 0, st1 = 0, en1 = 0;
+            if (in0) { st0 = __ldg(P.y.start + i0); en0 = __ldg(P.y.end + i0); }
+            if (in1) { st1 = __ldg(P.y.start + i1); en1 = __ldg(P.y.end + i1); }
+            int32_t s0 = 0, e0 = 0, s1 = 0, e1 = 0;
+            bool keep0 = in0 && transform(P, it, st0, en0, s0, e0);
+            bool keep1 = in1 && transform(P, it, st1, en1, s1, e1);
+            if (HAS_EXCL) {
+                if (keep0) keep0 = !excluded<STRANDED>(P.excl, it.tile, s0, e0, (STRANDED && P.y.strand) ? __ldg(P.y.strand + i0) : 0);
+                if (keep1) keep1 = !excluded<STRANDED>(P.excl, it.tile, s1, e1, (STRANDED && P.y.strand) ? __ldg(P.y.strand + i1) : 0);
             }
-            const unsigned m = __ballot_sync(kFull, keep);
-            if (keep) {
-                const int64_t pos = out + __popc(m & ((1u << lane) - 1u));
+            const unsigned m0 = __ballot_sync(kFull, keep0), m1 = __ballot_sync(kFull, keep1);
+            if (keep0) {
+                const int64_t pos = out + __popc(m0 & below);
                 O.seq[pos] = it.tile_seq;
-                O.start[pos] = s2;
-                O.end[pos] = e2;
-                O.src[pos] = __ldg(P.y.src + i);
+                O.start[pos] = s0;
+                O.end[pos] = e0;
+                O.src[pos] = P.y.src ? __ldg(P.y.src + i0) : i0;
                 O.block[pos] = (int32_t)b;
             }
-            out += __popc(m);
+            out += __popc(m0);
+            if (keep1) {
+                const int64_t pos = out + __popc(m1 & below);
+                O.seq[pos] = it.tile_seq;
+                O.start[pos] = s1;
+                O.end[pos] = e1;
+                O.src[pos] = P.y.src ? __ldg(P.y.src + i1) : i1;
+                O.block[pos] = (int32_t)b;
+            }
+            out += __popc(m1);
         }
     }
 }
