@@ -81,6 +81,14 @@ int nrb200_set_query(nrb200_handle *h, int64_t n, const int32_t *seqid, const in
 int nrb200_set_exclude(nrb200_handle *h, int64_t n, const int32_t *seqid, const int32_t *start,
                        const int32_t *end, const int8_t *strand);
 
+/* excludeOption of bootRanges() (R/bootRanges.R:82, 106-116).  DROP (default): bootstrapped ranges that
+ * overlap an exclude range are removed.  TRIM: they are cut down to gaps(exclude, end = seqlengths(y)) --
+ * one output row per (range, gap) overlap; needs all(strand(exclude) == "*") (:84).  Call after
+ * nrb200_set_exclude(); setting a stranded exclude afterwards fails at the next run. */
+#define NRB200_EXCLUDE_DROP 0
+#define NRB200_EXCLUDE_TRIM 1
+int nrb200_set_exclude_option(nrb200_handle *h, int32_t option);
+
 /* Which sampler of the reference runs (dispatch at R/bootRanges.R:91-104 and
  * R/bootUnsegmented.R:15-40). */
 enum {

@@ -17,6 +17,7 @@ OK, ERR_INVALID, ERR_CUDA, ERR_STATE, ERR_UNSUPPORTED, ERR_NOMEM = 0, -1, -2, -3
 UNSEG_ACROSS, UNSEG_WITHIN, SEG_PROP, SEG_NOPROP, PERMUTE_WITHIN, PERMUTE_ACROSS = range(6)
 RNG_HOST, RNG_PHILOX = 0, 1
 FLAG_FORCE_STREAM = 1
+EXCLUDE_DROP, EXCLUDE_TRIM = 0, 1
 
 
 class Config(C.Structure):
@@ -52,6 +53,7 @@ SYMBOLS = [
     ("nrb200_ranges_info", C.c_int, [vp, i32p, i32p, i32p]),
     ("nrb200_set_query", C.c_int, [vp, C.c_int64, i32p, i32p, i32p, i8p]),
     ("nrb200_set_exclude", C.c_int, [vp, C.c_int64, i32p, i32p, i32p, i8p]),
+    ("nrb200_set_exclude_option", C.c_int, [vp, C.c_int32]),
     ("nrb200_set_plan", C.c_int, [vp, C.POINTER(PlanSpec), i64p]),
     ("nrb200_get_tiles", C.c_int, [vp, i32p, i32p, i32p]),
     ("nrb200_run_counts", C.c_int, [vp, C.POINTER(Draws), i64p, i64p, i32p, C.POINTER(Stats)]),

@@ -90,7 +90,6 @@ def _setup(y: GRanges, blockLength, seg, exclude, excludeOption, proportionLengt
             raise ValueError("excludeOption='trim' needs exclude")  # strand(NULL) errors in the reference (:84)
         if np.any(exclude.strand != 0):
             raise ValueError('all(strand(exclude) == "*") is not TRUE')
-        raise NotImplementedError("excludeOption='trim' is not on the device yet (SURVEY 8f rank 2)")
     if float(blockLength) != int(blockLength):
         raise ValueError("blockLength must be integer valued")
     L_b = int(blockLength)
@@ -106,7 +105,7 @@ def _setup(y: GRanges, blockLength, seg, exclude, excludeOption, proportionLengt
             raise ValueError("all(y == GenomicRanges::sort(y)) is not TRUE")
     if exclude is not None:
         xi, xs, xe, xstr, _ = _side_arrays(exclude, y, "exclude")
-        eng.set_exclude(xi, xs, xe, xstr if np.any(xstr) else None)
+        eng.set_exclude(xi, xs, xe, xstr if np.any(xstr) else None, option=excludeOption)
     else:
         eng.clear_exclude()
     eng.set_plan(kind, L_b, segd)

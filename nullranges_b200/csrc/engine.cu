@@ -100,7 +100,8 @@ struct nrb200_handle {
     std::vector<int64_t> seqlen;
     DevMem seqlen_dev;
 
-    RangeSet y, query, excl;
+    RangeSet y, query, excl, gaps;  // gaps = gaps(exclude) inside [1, seqlength], built for excludeOption "trim"
+    int excl_option = NRB200_EXCLUDE_DROP;
     bool have_y = false, have_plan = false;
     // rank tables of y
     int rank_shift = 0;
@@ -140,6 +141,11 @@ int fail(nrb200_handle *h, int code, const std::string &msg) {
     if (h) h->error = msg; else g_create_error = msg;
     return code;
 }
+
+// The set the kernels test bootstrapped ranges against: the exclude ranges ("drop") or their gaps ("trim").
+inline bool trim_mode(const nrb200_handle *h) { return h->excl_option == NRB200_EXCLUDE_TRIM && h->excl.n > 0; }
+inline const RangeSet &active_excl(const nrb200_handle *h) { return trim_mode(h) ? h->gaps : h->excl; }
+inline int excl_kind(const nrb200_handle *h) { return h->excl.n == 0 ? kExclNone : (trim_mode(h) ? kExclTrim : kExclDrop); }
 
 #define NRB_CUDA(h, call)                                                                          \
     do {                                                                                           \
@@ -420,6 +426,33 @@ static std::vector<std::vector<Interval>> merged_exclude(const nrb200_handle *h)
     return out;
 }
 
+// gaps(exclude, end = seqlengths(y)) on strand "*" (R/bootRanges.R:112-113): complement of the merged
+// exclude regions inside [1, L] on EVERY sequence, as a range set of its own.
+int build_gaps(nrb200_handle *h) {
+    const auto X = merged_exclude(h);
+    std::vector<int32_t> sid, st, en;
+    for (int c = 0; c < h->n_seq; ++c) {
+        const int64_t L = h->seqlen[c];
+        int64_t pos = 1;
+        for (const Interval &x : X[c]) {
+            if (x.s > pos) {
+                sid.push_back(c);
+                st.push_back((int32_t)pos);
+                en.push_back((int32_t)std::min<int64_t>(x.s - 1, L));
+            }
+            pos = std::max(pos, x.e + 1);
+        }
+        if (pos <= L) {
+            sid.push_back(c);
+            st.push_back((int32_t)pos);
+            en.push_back((int32_t)L);
+        }
+    }
+    h->gaps.n = 0;
+    if (sid.empty()) return NRB200_OK;
+    return load_range_set(h, h->gaps, "gaps", (int64_t)sid.size(), sid.data(), st.data(), en.data(), nullptr, false);
+}
+
 int build_pairs(nrb200_handle *h) {
     Trace tr("build_pairs");
     const Plan &p = h->plan;
@@ -427,8 +460,13 @@ int build_pairs(nrb200_handle *h) {
     const int C = h->n_seq;
     const int64_t B = p.n_blocks(), G = q.n;
     const int64_t reach = std::max<int32_t>(h->y.wmax, 1) - 1;
-    const bool has_excl = h->excl.n > 0;
-    const auto X = has_excl ? merged_exclude(h) : std::vector<std::vector<Interval>>(C);
+    const bool has_excl = h->excl.n > 0, trim = trim_mode(h);
+    // "drop": the merged exclude regions; "trim": the gaps between them (already disjoint and sorted)
+    std::vector<std::vector<Interval>> X(C);
+    if (has_excl && !trim) X = merged_exclude(h);
+    if (trim)
+        for (int c = 0; c < C; ++c)
+            for (int32_t k = h->gaps.h_seq_off[c]; k < h->gaps.h_seq_off[c + 1]; ++k) X[c].push_back({h->gaps.h_start[k], h->gaps.h_end[k]});
 
     // exclude regions that intersect [lo, hi]: a contiguous run [first, last) of the merged list
     auto x_run = [&](int c, int64_t lo, int64_t hi, size_t &first, size_t &last) {
@@ -447,6 +485,10 @@ int build_pairs(nrb200_handle *h) {
             size_t f, l;
             x_run(c, ts - reach, te + reach, f, l);
             for (size_t k = f; k < l; ++k) {
+                if (trim) {  // rows = one per (range, gap) overlap
+                    x_rec.insert(x_rec.end(), {(int32_t)X[c][k].s, (int32_t)X[c][k].e, +1, 0});
+                    continue;
+                }
                 x_rec.insert(x_rec.end(), {(int32_t)X[c][k].s, (int32_t)std::min<int64_t>(X[c][k].e, INT32_MAX / 2), -1, 0});
                 if (k + 1 < l && X[c][k + 1].s - X[c][k].e <= reach)
                     x_rec.insert(x_rec.end(), {(int32_t)X[c][k + 1].s, (int32_t)X[c][k].e, +1, 0});
@@ -503,6 +545,12 @@ int build_pairs(nrb200_handle *h) {
                 while (lo < nt && te_max[c][lo] + reach < gs) ++lo;
                 for (int64_t j = lo; j < nt && ts[c][j] <= ge + reach; ++j) {
                     if (te[c][j] + reach < gs) continue;
+                    if (trim) {  // the pieces that can land on the feature: one window per gap it intersects
+                        size_t f, l;
+                        x_run(c, std::max(ts[c][j] - reach, gs), std::min(te[c][j] + reach, ge), f, l);
+                        for (size_t i = f; i < l; ++i) emit(k, v[j], std::max(X[c][i].s, gs), std::min(X[c][i].e, ge), +1);
+                        continue;
+                    }
                     emit(k, v[j], gs, ge, +1);
                     if (has_excl) {  // regions a range landing on the tile can overlap together with the feature
                         size_t f, l;
@@ -561,7 +609,7 @@ int build_pairs(nrb200_handle *h) {
 bool rank_path_ok(const nrb200_handle *h, bool with_query) {
     if (h->flags & NRB200_FLAG_FORCE_STREAM) return false;
     if (h->plan.permute() || !h->tiles_in_bounds) return false;
-    if (h->y.stranded && ((with_query && h->query.stranded) || (h->excl.n > 0 && h->excl.stranded))) return false;
+    if (h->y.stranded && ((with_query && h->query.stranded) || (h->excl.n > 0 && active_excl(h).stranded))) return false;
     return true;
 }
 
@@ -586,6 +634,8 @@ int prepare(nrb200_handle *h) {
         h->tiles_in_bounds = true;
         for (int64_t t = 0; t < h->plan.n_blocks(); ++t)
             if (h->plan.tile_start[t] > h->seqlen[h->plan.tile_seq[t]]) h->tiles_in_bounds = false;
+        if (trim_mode(h) && h->excl.stranded) return fail(h, NRB200_ERR_INVALID, "all(strand(exclude) == \"*\") is not TRUE");
+        if (trim_mode(h) && (rc = build_gaps(h))) return rc;
         // rank_path_ok(h, false) holds whenever rank_path_ok(h, true) does
         const bool rank_q = h->query.n && rank_path_ok(h, true), rank_rows = rank_path_ok(h, false);
         if (rank_q || rank_rows) {
@@ -597,7 +647,7 @@ int prepare(nrb200_handle *h) {
             tr.lap("build_pairs");
         }
         // the streaming kernels (count without the rank path, and the fill pass) test exclusion per range
-        if (h->excl.n && (rc = build_slices(h, h->excl, h->x_tile_lo, h->x_tile_hi))) return rc;
+        if (h->excl.n && (rc = build_slices(h, active_excl(h), h->x_tile_lo, h->x_tile_hi))) return rc;
         if (h->query.n && !rank_q && (rc = range_set_to_device(h, h->query))) return rc;
         if (h->query.n && !rank_q && (rc = build_slices(h, h->query, h->q_tile_lo, h->q_tile_hi))) return rc;
         if (((h->query.n && !rank_q) || !rank_rows) && (rc = ensure_pmax_table(h))) return rc;
@@ -640,11 +690,12 @@ BootParams make_params(nrb200_handle *h, const nrb200_draws *d) {
                      y.stranded ? y.strand.as<int8_t>() : nullptr, y.sorted_input ? nullptr : y.src.as<int32_t>(), y.seq_off.as<int32_t>(),
                      h->end_sorted.as<int32_t>(), h->rank_start.as<uint32_t>(), h->rank_pmax.as<uint32_t>(),
                      h->rank_end.as<uint32_t>(), h->seq_info_dev.as<int4>(), h->rank_shift};
-    const RangeSet &q = h->query, &x = h->excl;
-    P.query = SliceView{q.start.as<int32_t>(), q.end.as<int32_t>(), q.stranded ? q.strand.as<int8_t>() : nullptr,
+    const RangeSet &q = h->query, &x = active_excl(h);
+    P.query = SliceView{q.start.as<int32_t>(), q.end.as<int32_t>(), q.pmax.as<int32_t>(), q.stranded ? q.strand.as<int8_t>() : nullptr,
                         q.src.as<int32_t>(), h->q_tile_lo.as<int32_t>(), h->q_tile_hi.as<int32_t>()};
-    P.excl = SliceView{x.start.as<int32_t>(), x.end.as<int32_t>(), x.stranded ? x.strand.as<int8_t>() : nullptr,
+    P.excl = SliceView{x.start.as<int32_t>(), x.end.as<int32_t>(), x.pmax.as<int32_t>(), x.stranded ? x.strand.as<int8_t>() : nullptr,
                        x.src.as<int32_t>(), h->x_tile_lo.as<int32_t>(), h->x_tile_hi.as<int32_t>()};
+    P.rows_windows_only = trim_mode(h);
     P.sampler = h->sampler_view;
     P.n_blocks = h->plan.n_blocks();
     P.tile_seq = h->tile_seq.as<int32_t>();
@@ -666,9 +717,11 @@ BootParams make_params(nrb200_handle *h, const nrb200_draws *d) {
     return P;
 }
 
-template <bool ST, bool HQ, bool HX>
-void launch_count_t(nrb200_handle *h, const BootParams &P, unsigned grid) {
-    boot_count_kernel<ST, HQ, HX><<<grid, 256, 0, h->stream>>>(P);
+template <bool ST, bool HQ>
+void launch_count_t(nrb200_handle *h, const BootParams &P, unsigned grid, int excl) {
+    if (excl == kExclNone) boot_count_kernel<ST, HQ, kExclNone><<<grid, 256, 0, h->stream>>>(P);
+    else if (excl == kExclDrop) boot_count_kernel<ST, HQ, kExclDrop><<<grid, 256, 0, h->stream>>>(P);
+    else boot_count_kernel<ST, HQ, kExclTrim><<<grid, 256, 0, h->stream>>>(P);
 }
 
 constexpr int64_t kMaxBatch = 2048;  // iterations per launch (multiple of kRpt; gridDim.y and scratch stay small)
@@ -682,7 +735,7 @@ int launch_rank(nrb200_handle *h, const BootParams &P, bool has_query) {
     const int rpt = h->tune_rpt;
     const unsigned gy = (unsigned)((P.n_iter + rpt - 1) / rpt);
     if (P.n_blocks > 0) {
-        const TileExcl X{h->excl.n > 0 ? h->tile_x_off.as<int32_t>() : nullptr, h->tile_x_rec.as<int4>()};
+        const TileExcl X{h->excl.n > 0 ? h->tile_x_off.as<int32_t>() : nullptr, h->tile_x_rec.as<int4>()};  // drop: minus, trim: plus
         boot_block_rows_kernel<1><<<dim3((unsigned)((P.n_blocks + 255) / 256), (unsigned)P.n_iter), 256, 0, h->stream>>>(P, X);
         ++launches;
     }
@@ -711,19 +764,12 @@ int launch_count(nrb200_handle *h, const BootParams &P, bool has_query) {
     if (items == 0) return 0;
     const int64_t ctas = (items + 7) / 8;
     const unsigned grid = (unsigned)std::min<int64_t>(ctas, (int64_t)h->sm_count * 64);
-    const bool st = h->y.stranded && ((has_query && h->query.stranded) || (h->excl.n && h->excl.stranded));
-    const bool hx = h->excl.n > 0;
-    const int key = (st ? 4 : 0) | (has_query ? 2 : 0) | (hx ? 1 : 0);
-    switch (key) {
-    case 0: launch_count_t<false, false, false>(h, P, grid); break;
-    case 1: launch_count_t<false, false, true>(h, P, grid); break;
-    case 2: launch_count_t<false, true, false>(h, P, grid); break;
-    case 3: launch_count_t<false, true, true>(h, P, grid); break;
-    case 4: launch_count_t<true, false, false>(h, P, grid); break;
-    case 5: launch_count_t<true, false, true>(h, P, grid); break;
-    case 6: launch_count_t<true, true, false>(h, P, grid); break;
-    default: launch_count_t<true, true, true>(h, P, grid); break;
-    }
+    const bool st = h->y.stranded && ((has_query && h->query.stranded) || (h->excl.n && active_excl(h).stranded));
+    const int excl = excl_kind(h);
+    if (st && has_query) launch_count_t<true, true>(h, P, grid, excl);
+    else if (st) launch_count_t<true, false>(h, P, grid, excl);
+    else if (has_query) launch_count_t<false, true>(h, P, grid, excl);
+    else launch_count_t<false, false>(h, P, grid, excl);
     return 1;
 }
 
@@ -974,6 +1020,18 @@ int nrb200_set_exclude(nrb200_handle *h, int64_t n, const int32_t *seqid, const 
     return set_side(h, h->excl, "exclude", n, seqid, start, end, strand);
 }
 
+int nrb200_set_exclude_option(nrb200_handle *h, int32_t option) {
+    if (!h) return NRB200_ERR_INVALID;
+    if (option != NRB200_EXCLUDE_DROP && option != NRB200_EXCLUDE_TRIM)
+        return fail(h, NRB200_ERR_INVALID, "'excludeOption' should be one of 'drop', 'trim'");
+    // stopifnot(all(strand(exclude) == "*"))                       R/bootRanges.R:84
+    if (option == NRB200_EXCLUDE_TRIM && h->excl.n > 0 && h->excl.stranded)
+        return fail(h, NRB200_ERR_INVALID, "all(strand(exclude) == \"*\") is not TRUE");
+    h->excl_option = option;
+    h->slices_dirty = true;
+    return NRB200_OK;
+}
+
 int nrb200_set_plan(nrb200_handle *h, const nrb200_plan_spec *spec, int64_t *n_blocks) {
     if (!h || !spec) return NRB200_ERR_INVALID;
     NRB_CUDA(h, cudaSetDevice(h->device));
@@ -1211,8 +1269,8 @@ int nrb200_run_materialize(nrb200_handle *h, const nrb200_draws *draws, int64_t 
         NRB_CUDA(h, m->reserve(std::max<int64_t>(rows, 1) * 4));
     int fill_launches = 0;
     if (items > 0) {
-        const bool st = h->y.stranded && h->excl.n && h->excl.stranded;
-        const bool hx = h->excl.n > 0;
+        const bool st = h->y.stranded && h->excl.n && active_excl(h).stranded;
+        const int excl = excl_kind(h);
         const int64_t kFillBatch = 32768;  // gridDim.y
         for (int64_t r0 = 0; r0 < R; r0 += kFillBatch, ++fill_launches) {
             BootParams Q = slice_params(P, r0, std::min(kFillBatch, R - r0));
@@ -1220,9 +1278,10 @@ int nrb200_run_materialize(nrb200_handle *h, const nrb200_draws *draws, int64_t 
             const RowsOut O{h->row_seq.as<int32_t>(), h->row_start.as<int32_t>(), h->row_end.as<int32_t>(), h->row_src.as<int32_t>(),
                             h->row_block.as<int32_t>(), h->iter_off_dev.as<int64_t>() + r0, h->within_off.as<int32_t>() + r0 * B};
             const dim3 grid((unsigned)std::min<int64_t>((B + 7) / 8, 65535), (unsigned)Q.n_iter);
-            if (st && hx) boot_fill_kernel<true, true><<<grid, 256, 0, h->stream>>>(Q, O);
-            else if (hx) boot_fill_kernel<false, true><<<grid, 256, 0, h->stream>>>(Q, O);
-            else boot_fill_kernel<false, false><<<grid, 256, 0, h->stream>>>(Q, O);
+            if (excl == kExclTrim) boot_fill_trim_kernel<<<grid, 256, 0, h->stream>>>(Q, O);
+            else if (st) boot_fill_kernel<true, kExclDrop><<<grid, 256, 0, h->stream>>>(Q, O);
+            else if (excl == kExclDrop) boot_fill_kernel<false, kExclDrop><<<grid, 256, 0, h->stream>>>(Q, O);
+            else boot_fill_kernel<false, kExclNone><<<grid, 256, 0, h->stream>>>(Q, O);
             NRB_CUDA(h, cudaGetLastError());
         }
     }

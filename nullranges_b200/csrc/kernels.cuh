@@ -37,9 +37,10 @@ struct RangesView {            // canonical (seqname, start, end) order
     int rank_shift;
 };
 
-struct SliceView {             // query or exclude, canonical order, plus a per-tile window
+struct SliceView {             // query or exclude (or, for "trim", the gaps), canonical order, plus a per-tile window
     const int32_t *start;
     const int32_t *end;
+    const int32_t *pmax;       // running max of end inside the sequence
     const int8_t *strand;
     const int32_t *src;
     const int32_t *tile_lo;    // [n_blocks] first candidate of the tile
@@ -64,6 +65,7 @@ struct BootParams {
     const int32_t *tile_seq, *tile_start, *bait_width;
     const int64_t *seqlen;
     int permute, drop_zero;
+    int rows_windows_only;    // rank path, excludeOption = "trim": rows = sum of the tile's gap windows
     // draws
     int rng_mode;
     uint64_t seed;
@@ -245,7 +247,27 @@ __device__ __forceinline__ bool excluded(const SliceView &X, int tile, int32_t s
     return false;
 }
 
-template <bool STRANDED, bool HAS_QUERY, bool HAS_EXCL>
+// Exclusion modes of the streaming kernels (template parameter EXCL)
+constexpr int kExclNone = 0;  // no exclude set
+constexpr int kExclDrop = 1;  // excludeOption = "drop": P.excl = exclude ranges, overlapping ranges vanish
+constexpr int kExclTrim = 2;  // excludeOption = "trim": P.excl = gaps(exclude), ranges are cut to the gaps
+
+// countOverlaps contribution of one (piece of a) bootstrapped range: features of the tile's slice
+// with start <= pe, walked backwards under the running-max-of-end bound.
+template <bool STRANDED>
+__device__ __forceinline__ int count_piece(const BootParams &P, int64_t r, int32_t q_lo, int32_t q_hi, int32_t ps,
+                                           int32_t pe, int strand) {
+    int n = 0;
+    for (int32_t k = first_gt(P.query.start, q_lo, q_hi, pe) - 1; k >= q_lo && __ldg(P.query.pmax + k) >= ps; --k) {
+        if (__ldg(P.query.end + k) < ps) continue;
+        if (STRANDED && P.query.strand && !strands_match(strand, __ldg(P.query.strand + k))) continue;
+        ++n;
+        if (P.counts) atomicAdd(P.counts + r * P.n_query + __ldg(P.query.src + k), 1);
+    }
+    return n;
+}
+
+template <bool STRANDED, bool HAS_QUERY, int EXCL>
 __global__ void __launch_bounds__(256) boot_count_kernel(const BootParams P) {
     const int lane = threadIdx.x & (kWarp - 1);
     const int64_t warps_total = (int64_t)gridDim.x * (blockDim.x / kWarp);
@@ -256,10 +278,14 @@ __global__ void __launch_bounds__(256) boot_count_kernel(const BootParams P) {
         const int64_t r = item / P.n_blocks, b = item - r * P.n_blocks;
         const Item it = load_item(P, r, b);
 
-        int32_t q_lo = 0, q_hi = 0;
+        int32_t q_lo = 0, q_hi = 0, x_lo = 0, x_hi = 0;
         if (HAS_QUERY) {
             q_lo = __ldg(P.query.tile_lo + it.tile);
             q_hi = __ldg(P.query.tile_hi + it.tile);
+        }
+        if (EXCL == kExclTrim) {
+            x_lo = __ldg(P.excl.tile_lo + it.tile);
+            x_hi = __ldg(P.excl.tile_hi + it.tile);
         }
         int rows = 0, hits = 0;
         int overlaps = 0;
@@ -269,17 +295,19 @@ __global__ void __launch_bounds__(256) boot_count_kernel(const BootParams P) {
             hits += (P.permute ? (st >= it.bait_start) : (en >= it.bait_start)) ? 1 : 0;
             if (!transform(P, it, st, en, s2, e2)) continue;
             const int strand = (STRANDED && P.y.strand) ? __ldg(P.y.strand + i) : 0;
-            if (HAS_EXCL && excluded<STRANDED>(P.excl, it.tile, s2, e2, strand)) continue;
-            ++rows;
-            if (HAS_QUERY && e2 >= s2) {
-                for (int32_t k = q_lo; k < q_hi; ++k) {
-                    if (s2 <= __ldg(P.query.end + k) && e2 >= __ldg(P.query.start + k)) {
-                        if (STRANDED && P.query.strand && !strands_match(strand, __ldg(P.query.strand + k))) continue;
-                        ++overlaps;
-                        if (P.counts) atomicAdd(P.counts + r * P.n_query + __ldg(P.query.src + k), 1);
-                    }
+            if (EXCL == kExclTrim) {
+                if (e2 < s2) continue;  // a zero-width survivor overlaps no gap
+                for (int32_t k = x_lo; k < x_hi; ++k) {
+                    const int32_t gs = __ldg(P.excl.start + k), ge = __ldg(P.excl.end + k);
+                    if (s2 > ge || e2 < gs) continue;
+                    ++rows;
+                    if (HAS_QUERY) overlaps += count_piece<STRANDED>(P, r, q_lo, q_hi, max(s2, gs), min(e2, ge), strand);
                 }
+                continue;
             }
+            if (EXCL == kExclDrop && excluded<STRANDED>(P.excl, it.tile, s2, e2, strand)) continue;
+            ++rows;
+            if (HAS_QUERY && e2 >= s2) overlaps += count_piece<STRANDED>(P, r, q_lo, q_hi, s2, e2, strand);
         }
         rows = __reduce_add_sync(kFull, rows);
         hits = __reduce_add_sync(kFull, hits);
@@ -332,7 +360,7 @@ struct RowsOut {
 
 // grid = (block groups, iterations); one warp per (iteration, block), 64 candidate ranges per
 // loop trip (two independent loads per lane), ballot-compacted writes of the five columns.
-template <bool STRANDED, bool HAS_EXCL>
+template <bool STRANDED, int EXCL>
 __global__ void __launch_bounds__(256) boot_fill_kernel(const BootParams P, const RowsOut O) {
     const int lane = threadIdx.x & (kWarp - 1);
     const unsigned below = (1u << lane) - 1u;
@@ -351,7 +379,7 @@ __global__ void __launch_bounds__(256) boot_fill_kernel(const BootParams P, cons
             int32_t s0 = 0, e0 = 0, s1 = 0, e1 = 0;
             bool keep0 = in0 && transform(P, it, st0, en0, s0, e0);
             bool keep1 = in1 && transform(P, it, st1, en1, s1, e1);
-            if (HAS_EXCL) {
+            if (EXCL == kExclDrop) {
                 if (keep0) keep0 = !excluded<STRANDED>(P.excl, it.tile, s0, e0, (STRANDED && P.y.strand) ? __ldg(P.y.strand + i0) : 0);
                 if (keep1) keep1 = !excluded<STRANDED>(P.excl, it.tile, s1, e1, (STRANDED && P.y.strand) ? __ldg(P.y.strand + i1) : 0);
             }
@@ -374,6 +402,50 @@ __global__ void __launch_bounds__(256) boot_fill_kernel(const BootParams P, cons
                 O.block[pos] = (int32_t)b;
             }
             out += __popc(m1);
+        }
+    }
+}
+
+// excludeOption = "trim": a range becomes one row per gap it overlaps (its intersection with the
+// gap), rows of a range in ascending gap order.  Lanes count their pieces, a warp scan places them.
+__global__ void __launch_bounds__(256) boot_fill_trim_kernel(const BootParams P, const RowsOut O) {
+    const int lane = threadIdx.x & (kWarp - 1);
+    const int64_t r = blockIdx.y;
+    const int64_t row0 = __ldg(O.iter_off + r);
+    for (int64_t b = (int64_t)blockIdx.x * (blockDim.x / kWarp) + (threadIdx.x / kWarp); b < P.n_blocks;
+         b += (int64_t)gridDim.x * (blockDim.x / kWarp)) {
+        const Item it = load_item(P, r, b);
+        const int32_t x_lo = __ldg(P.excl.tile_lo + it.tile), x_hi = __ldg(P.excl.tile_hi + it.tile);
+        int64_t out = row0 + __ldg(O.within_off + r * P.n_blocks + b);
+        for (int32_t base = it.lo; base < it.hi; base += kWarp) {
+            const int32_t i = base + lane;
+            int32_t s2 = 0, e2 = -1;
+            int n = 0;
+            if (i < it.hi && transform(P, it, __ldg(P.y.start + i), __ldg(P.y.end + i), s2, e2) && e2 >= s2) {
+                for (int32_t k = x_lo; k < x_hi; ++k) n += (s2 <= __ldg(P.excl.end + k) && e2 >= __ldg(P.excl.start + k));
+            }
+            int before = n;  // inclusive warp scan
+#pragma unroll
+            for (int d = 1; d < kWarp; d <<= 1) {
+                const int t = __shfl_up_sync(kFull, before, d);
+                if (lane >= d) before += t;
+            }
+            const int total = __shfl_sync(kFull, before, kWarp - 1);
+            if (n) {
+                int64_t pos = out + (before - n);
+                const int32_t src = P.y.src ? __ldg(P.y.src + i) : i;
+                for (int32_t k = x_lo; k < x_hi; ++k) {
+                    const int32_t gs = __ldg(P.excl.start + k), ge = __ldg(P.excl.end + k);
+                    if (s2 > ge || e2 < gs) continue;
+                    O.seq[pos] = it.tile_seq;
+                    O.start[pos] = max(s2, gs);
+                    O.end[pos] = min(e2, ge);
+                    O.src[pos] = src;
+                    O.block[pos] = (int32_t)b;
+                    ++pos;
+                }
+            }
+            out += total;
         }
     }
 }
@@ -580,7 +652,7 @@ __global__ void __launch_bounds__(256) boot_block_rows_kernel(const BootParams P
                 const int hits = ie - idx_end_lt(P.y, si, d.y);
                 int dropped = 0;  // only a tile that overhangs its sequence end can push hits beyond it
                 if (P.drop_zero && ts + (width - 1) > seq_len) dropped = max(0, ie - idx_start_le(P.y, si, seq_len - (ts - d.y)));
-                rows[j] = hits - dropped;
+                rows[j] = P.rows_windows_only ? 0 : hits - dropped;
                 if (X.off) {  // minus the hits that overlap an exclude region after the move
                     const int32_t x1 = __ldg(X.off + b + 1);
                     for (int32_t k = __ldg(X.off + b); k < x1; ++k) {

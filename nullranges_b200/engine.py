@@ -86,12 +86,15 @@ class Engine:
         self._check(self._lib.nrb200_set_query(self._h, a.size, ptr(a, C.c_int32), ptr(b, C.c_int32), ptr(c, C.c_int32), ptr(d, C.c_int8)))
         self.n_query = a.size
 
-    def set_exclude(self, seqid, start, end, strand=None):
+    def set_exclude(self, seqid, start, end, strand=None, option: str = "drop"):
+        """option: excludeOption of bootRanges() -- "drop" removes overlapping ranges, "trim" cuts them to the gaps."""
         a, b, c, d = _i32(seqid), _i32(start), _i32(end), _i8(strand)
         self._check(self._lib.nrb200_set_exclude(self._h, a.size, ptr(a, C.c_int32), ptr(b, C.c_int32), ptr(c, C.c_int32), ptr(d, C.c_int8)))
+        self._check(self._lib.nrb200_set_exclude_option(self._h, {"drop": _lib.EXCLUDE_DROP, "trim": _lib.EXCLUDE_TRIM}[option]))
 
     def clear_exclude(self):
         self._check(self._lib.nrb200_set_exclude(self._h, 0, None, None, None, None))
+        self._check(self._lib.nrb200_set_exclude_option(self._h, _lib.EXCLUDE_DROP))
 
     def clear_query(self):
         self._check(self._lib.nrb200_set_query(self._h, 0, None, None, None, None))

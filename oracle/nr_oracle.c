@@ -6,7 +6,7 @@
  * The product (nullranges_b200/, libnrb200.so) never links, imports or calls it.
  *
  * What it is: a plain-C, line-by-line restatement of the reference algorithm
- *   R/bootRanges.R:72-331        (front-end loop, segmented samplers, exclude "drop")
+ *   R/bootRanges.R:72-331        (front-end loop, segmented samplers, exclude "drop" / "trim")
  *   R/bootUnsegmented.R:1-191    (unsegmented samplers, shift_and_swap_chrom)
  * plus the semantics of the third-party calls those files make, none of which is
  * vendored under /root/reference (IRanges / GenomicRanges / S4Vectors, Bioconductor 3.17,
@@ -826,6 +826,9 @@ typedef struct {
     int64_t n, cap; /* cap < 0: count only */
 } orc_rows;
 
+#define ORC_EXCLUDE_DROP 0 /* excl = the exclude ranges; overlapping ranges are removed */
+#define ORC_EXCLUDE_TRIM 1 /* excl = gaps(exclude); ranges are cut down to the gaps      */
+
 static int cmp_i32(const void *a, const void *b) {
     int32_t x = *(const int32_t *)a, y = *(const int32_t *)b;
     return x < y ? -1 : (x > y);
@@ -841,7 +844,7 @@ static int cmp_i32(const void *a, const void *b) {
  * Bootstrap kinds: a y range is a hit of block b when it overlaps the bait block
  * (strand ignored: the bait is '*').  Permute kinds: y belongs to the ONE tile that
  * contains its start (findOverlaps(select="first"), :95, :155). */
-static int64_t one_iteration(const orc_plan *p, const orc_index *y, const orc_index *excl,
+static int64_t one_iteration(const orc_plan *p, const orc_index *y, const orc_index *excl, int excl_mode,
                              const orc_index *query, const int32_t *bait_chrom,
                              const int32_t *bait_start, const int32_t *dst_tile,
                              orc_rows *rows, int32_t *counts, int64_t *total_overlaps,
@@ -885,6 +888,31 @@ static int64_t one_iteration(const orc_plan *p, const orc_index *y, const orc_in
             else { if (s2 < 1) s2 = 1; if (e2 > Lc) e2 = Lc; }
             if (drop_zero && e2 < s2) continue; /* y_prime[width(y_prime) > 0]  :189 */
             int st = y->strand ? y->strand[id] : 0;
+            if (excl && excl_mode == ORC_EXCLUDE_TRIM) {
+                /* excludeOption = "trim"  (R/bootRanges.R:110-115): excl holds
+                 * gaps(exclude, end = seqlengths(y)) restricted to strand "*"; the range is replaced by
+                 * its intersections with the gaps it overlaps (join_overlap_intersect: one row per
+                 * (range, gap) hit, gaps ascending).  Gaps are disjoint and sorted, so the overlapped
+                 * ones are consecutive.  A zero-width range overlaps no gap. */
+                if (e2 < s2) continue;
+                int64_t glo = excl->off[tc], ghi = upper_start(excl, glo, excl->off[tc + 1], e2);
+                int64_t k0 = ghi;
+                while (k0 > glo && (int64_t)excl->end[excl->ord[k0 - 1]] >= s2) k0--;
+                for (int64_t k = k0; k < ghi; k++) {
+                    int32_t gid = excl->ord[k];
+                    int64_t ps = s2 > excl->start[gid] ? s2 : excl->start[gid];
+                    int64_t pe = e2 < excl->end[gid] ? e2 : excl->end[gid];
+                    if (rows && rows->cap >= 0 && rows->n < rows->cap) {
+                        int64_t r = rows->n;
+                        rows->chrom[r] = tc; rows->start[r] = (int32_t)ps; rows->end[r] = (int32_t)pe;
+                        rows->src[r] = id; rows->block[r] = (int32_t)b;
+                    }
+                    if (rows) rows->n++;
+                    nrows++;
+                    if (query) tot += count_into(query, tc, ps, pe, st, counts);
+                }
+                continue;
+            }
             if (excl && overlaps_any(excl, tc, s2, e2, st)) continue; /* bootRanges.R:109 */
             if (rows && rows->cap >= 0 && rows->n < rows->cap) {
                 int64_t r = rows->n;
@@ -902,7 +930,7 @@ static int64_t one_iteration(const orc_plan *p, const orc_index *y, const orc_in
 
 /* Rows of ONE iteration.  Call with cap = 0 to size, then again to fill.  Returns the
  * row count (or -1). */
-ORC_API int64_t orc_iteration_rows(const orc_plan *p, const orc_index *y, const orc_index *excl,
+ORC_API int64_t orc_iteration_rows(const orc_plan *p, const orc_index *y, const orc_index *excl, int excl_mode,
                                    const int32_t *bait_chrom, const int32_t *bait_start,
                                    const int32_t *dst_tile, int64_t cap, int32_t *out_chrom,
                                    int32_t *out_start, int32_t *out_end, int32_t *out_src,
@@ -910,7 +938,7 @@ ORC_API int64_t orc_iteration_rows(const orc_plan *p, const orc_index *y, const 
     orc_rows rows = {out_chrom, out_start, out_end, out_src, out_block, 0, cap};
     int32_t *scratch = NULL;
     int64_t scap = 0;
-    one_iteration(p, y, excl, NULL, bait_chrom, bait_start, dst_tile, &rows, NULL, NULL,
+    one_iteration(p, y, excl, excl_mode, NULL, bait_chrom, bait_start, dst_tile, &rows, NULL, NULL,
                   &scratch, &scap);
     free(scratch);
     return rows.n;
@@ -936,7 +964,7 @@ ORC_API int64_t orc_count_overlaps(const orc_index *query, int64_t n, const int3
  *          (the reference itself is single-threaded R; threads are a courtesy to the
  *          CPU baseline, iterations are independent). */
 typedef struct {
-    const orc_plan *p; const orc_index *y, *excl, *query;
+    const orc_plan *p; const orc_index *y, *excl, *query; int excl_mode;
     int64_t R; int rng_mode; uint64_t seed, iter0;
     const int32_t *bait_chrom, *bait_start, *dst_tile;
     int64_t *iter_nranges, *iter_totals; int32_t *feature_counts;
@@ -969,7 +997,7 @@ static void *orc_worker(void *arg) {
         int32_t *cnt = j->feature_counts ? j->feature_counts + r * G : NULL;
         if (cnt) memset(cnt, 0, sizeof(int32_t) * (size_t)G);
         int64_t tot = 0;
-        int64_t nr = one_iteration(p, j->y, j->excl, j->query, pc, ps, pd, NULL, cnt, &tot,
+        int64_t nr = one_iteration(p, j->y, j->excl, j->excl_mode, j->query, pc, ps, pd, NULL, cnt, &tot,
                                    &scratch, &scap);
         if (j->iter_nranges) j->iter_nranges[r] = nr;
         if (j->iter_totals) j->iter_totals[r] = tot;
@@ -978,13 +1006,13 @@ static void *orc_worker(void *arg) {
     return NULL;
 }
 
-ORC_API int orc_boot_counts(const orc_plan *p, const orc_index *y, const orc_index *excl,
+ORC_API int orc_boot_counts(const orc_plan *p, const orc_index *y, const orc_index *excl, int excl_mode,
                             const orc_index *query, int64_t R, int rng_mode, uint64_t seed,
                             uint64_t iter0, const int32_t *bait_chrom,
                             const int32_t *bait_start, const int32_t *dst_tile,
                             int64_t *iter_nranges, int64_t *iter_totals,
                             int32_t *feature_counts, int nthreads) {
-    orc_job j = {p, y, excl, query, R, rng_mode, seed, iter0, bait_chrom, bait_start, dst_tile,
+    orc_job j = {p, y, excl, query, excl_mode, R, rng_mode, seed, iter0, bait_chrom, bait_start, dst_tile,
                  iter_nranges, iter_totals, feature_counts, 0, 0, PTHREAD_MUTEX_INITIALIZER};
     if (nthreads < 1) nthreads = 1;
     if (nthreads > 256) nthreads = 256;

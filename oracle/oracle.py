@@ -65,10 +65,10 @@ def lib():
     L.orc_index_new.argtypes = [C.c_int64, C.c_int, i32p, i32p, i32p, i8p]
     L.orc_index_free.argtypes = [vp]
     L.orc_iteration_rows.restype = C.c_int64
-    L.orc_iteration_rows.argtypes = [vp, vp, vp, i32p, i32p, i32p, C.c_int64, i32p, i32p, i32p, i32p, i32p]
+    L.orc_iteration_rows.argtypes = [vp, vp, vp, C.c_int, i32p, i32p, i32p, C.c_int64, i32p, i32p, i32p, i32p, i32p]
     L.orc_count_overlaps.restype = C.c_int64
     L.orc_count_overlaps.argtypes = [vp, C.c_int64, i32p, i32p, i32p, i8p, i32p]
-    L.orc_boot_counts.argtypes = [vp, vp, vp, vp, C.c_int64, C.c_int, C.c_uint64, C.c_uint64,
+    L.orc_boot_counts.argtypes = [vp, vp, vp, C.c_int, vp, C.c_int64, C.c_int, C.c_uint64, C.c_uint64,
                                   i32p, i32p, i32p, i64p, i64p, i32p, C.c_int]
     L.orc_max_threads.restype = C.c_int
     _lib = L
@@ -207,11 +207,38 @@ class Index:
             self._h = None
 
 
-def iteration_rows(plan: Plan, y: Index, bait_chrom, bait_start, dst_tile, exclude: Index | None = None) -> dict:
-    """Rows of one iteration in ascending (block, y-index) order."""
+def gaps(n_chrom: int, seqlengths, chrom, start, end, strand=None) -> "Index":
+    """gaps(exclude, end = seqlengths(y)) %>% filter(strand == "*")  (R/bootRanges.R:112-113): the
+    complement, inside [1, seqlength], of the '*'-strand exclude ranges, per sequence, as an Index.
+    The reference insists on all(strand(exclude) == "*") for excludeOption = "trim" (:84)."""
+    if strand is not None and np.any(np.asarray(strand) != 0):
+        raise ValueError('all(strand(exclude) == "*") is not TRUE')
+    chrom, start, end = np.asarray(chrom), np.asarray(start, dtype=np.int64), np.asarray(end, dtype=np.int64)
+    gc, gs, ge = [], [], []
+    for c in range(n_chrom):
+        L = int(seqlengths[c])
+        m = chrom == c
+        o = np.argsort(start[m], kind="stable")
+        pos = 1  # first position not yet covered
+        for s, e in zip(start[m][o], end[m][o]):
+            if s > pos and pos <= L:
+                gc.append(c); gs.append(pos); ge.append(min(int(s) - 1, L))
+            pos = max(pos, int(e) + 1)
+        if pos <= L:
+            gc.append(c); gs.append(pos); ge.append(L)
+    return Index(n_chrom, np.array(gc, np.int32), np.array(gs, np.int32), np.array(ge, np.int32))
+
+
+EXCLUDE_DROP, EXCLUDE_TRIM = 0, 1
+
+
+def iteration_rows(plan: Plan, y: Index, bait_chrom, bait_start, dst_tile, exclude: Index | None = None,
+                   exclude_mode: int = EXCLUDE_DROP) -> dict:
+    """Rows of one iteration in ascending (block, y-index[, gap]) order.  exclude_mode EXCLUDE_TRIM:
+    ``exclude`` must be the gaps() index."""
     bc, bs, dt = _i32(bait_chrom), _i32(bait_start), _i32(dst_tile)
     ex = exclude._h if exclude is not None else None
-    args = (plan._h, y._h, ex, _p(bc, C.c_int32), _p(bs, C.c_int32), _p(dt, C.c_int32))
+    args = (plan._h, y._h, ex, exclude_mode, _p(bc, C.c_int32), _p(bs, C.c_int32), _p(dt, C.c_int32))
     n = lib().orc_iteration_rows(*args, 0, None, None, None, None, None)
     out = {k: np.empty(n, np.int32) for k in ("chrom", "start", "end", "src", "block")}
     lib().orc_iteration_rows(*args, n, *(_p(out[k], C.c_int32) for k in ("chrom", "start", "end", "src", "block")))
@@ -228,7 +255,7 @@ def count_overlaps(query: Index, chrom, start, end, strand=None):
 
 
 def boot_counts(plan: Plan, y: Index, query: Index | None, R: int, *, exclude: Index | None = None,
-                draws=None, seed: int = 0, iter0: int = 0, want_counts: bool = True, nthreads: int = 1) -> dict:
+                exclude_mode: int = EXCLUDE_DROP, draws=None, seed: int = 0, iter0: int = 0, want_counts: bool = True, nthreads: int = 1) -> dict:
     """Fused bootstrap -> countOverlaps over R iterations.
 
     ``draws=(bait_chrom, bait_start, dst_tile)`` ([R, B] each) selects validation mode;
@@ -245,7 +272,7 @@ def boot_counts(plan: Plan, y: Index, query: Index | None, R: int, *, exclude: I
     else:
         bc = bs = dt = None
         mode = 1
-    rc = lib().orc_boot_counts(plan._h, y._h, exclude._h if exclude is not None else None,
+    rc = lib().orc_boot_counts(plan._h, y._h, exclude._h if exclude is not None else None, exclude_mode,
                                query._h if query is not None else None, R, mode, seed, iter0,
                                _p(bc, C.c_int32), _p(bs, C.c_int32), _p(dt, C.c_int32),
                                _p(nr, C.c_int64), _p(tot, C.c_int64), _p(cnt, C.c_int32), nthreads)

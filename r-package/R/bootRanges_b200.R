@@ -76,7 +76,7 @@
 .setup <- function(y, blockLength, seg, exclude, excludeOption, proportionLength, type, withinChrom, device) {
   chr_lens <- GenomeInfoDb::seqlengths(y)
   stopifnot(all(!is.na(chr_lens)))
-  if (excludeOption == "trim") stop("excludeOption = 'trim' is not on the device yet")
+  if (excludeOption == "trim") stopifnot(all(GenomicRanges::strand(exclude) == "*"))   # R/bootRanges.R:83-85
   lv <- GenomeInfoDb::seqlevels(y)
   h <- .handle(device)
   kind <- .kind(seg, proportionLength, type, withinChrom)
@@ -86,11 +86,11 @@
     ok <- if (is.null(.strand_code(y))) sorted else all(y == GenomicRanges::sort(y))
     stopifnot("all(y == GenomicRanges::sort(y)) is not TRUE" = ok)
   }
-  if (is.null(exclude)) .Call("nrb200_R_set_exclude", h, integer(), integer(), integer(), NULL)
+  if (is.null(exclude)) .Call("nrb200_R_set_exclude", h, integer(), integer(), integer(), NULL, 0L)
   else {
     exclude <- exclude[as.character(GenomicRanges::seqnames(exclude)) %in% lv]
     .Call("nrb200_R_set_exclude", h, .seqid(exclude, lv), GenomicRanges::start(exclude), GenomicRanges::end(exclude),
-          .strand_code(exclude))
+          .strand_code(exclude), if (excludeOption == "trim") 1L else 0L)
   }
   segl <- NULL
   if (!is.null(seg)) {

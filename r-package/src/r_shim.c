@@ -85,9 +85,11 @@ SEXP nrb200_R_set_query(SEXP ptr, SEXP seqid, SEXP start, SEXP end, SEXP strand)
     return R_NilValue;
 }
 
-SEXP nrb200_R_set_exclude(SEXP ptr, SEXP seqid, SEXP start, SEXP end, SEXP strand) {
+/* option: 0 = excludeOption "drop", 1 = "trim" */
+SEXP nrb200_R_set_exclude(SEXP ptr, SEXP seqid, SEXP start, SEXP end, SEXP strand, SEXP option) {
     check(H(ptr), nrb200_set_exclude(H(ptr), XLENGTH(start), ints(seqid, "seqnames(exclude)"), ints(start, "start(exclude)"),
                                      ints(end, "end(exclude)"), strand_codes(strand)));
+    check(H(ptr), nrb200_set_exclude_option(H(ptr), Rf_asInteger(option)));
     return R_NilValue;
 }
 
@@ -178,7 +180,7 @@ static const R_CallMethodDef call_methods[] = {
     {"nrb200_R_create", (DL_FUNC)&nrb200_R_create, 1},
     {"nrb200_R_set_ranges", (DL_FUNC)&nrb200_R_set_ranges, 6},
     {"nrb200_R_set_query", (DL_FUNC)&nrb200_R_set_query, 5},
-    {"nrb200_R_set_exclude", (DL_FUNC)&nrb200_R_set_exclude, 5},
+    {"nrb200_R_set_exclude", (DL_FUNC)&nrb200_R_set_exclude, 6},
     {"nrb200_R_set_plan", (DL_FUNC)&nrb200_R_set_plan, 7},
     {"nrb200_R_run_counts", (DL_FUNC)&nrb200_R_run_counts, 9},
     {"nrb200_R_run_materialize", (DL_FUNC)&nrb200_R_run_materialize, 7},

@@ -47,12 +47,20 @@ def random_case(seed, n=400, n_seq=3, max_len=5000, n_query=60, n_excl=0, strand
 
 
 def oracle_objects(case, kind):
+    """(plan, y, query, exclude) for the oracle.  With case["trim"] the fourth item is the gaps() index and
+    must be passed with exclude_mode=O.EXCLUDE_TRIM (see excl_mode())."""
     C = case["seqlen"].size
     plan = O.Plan(kind, case["seqlen"], case["L_b"], case["seg"] if kind in (2, 3) else None)
     y = O.Index(C, *case["y"])
     q = O.Index(C, *case["query"]) if case["query"] is not None else None
-    x = O.Index(C, *case["excl"]) if case["excl"] is not None else None
+    x = None
+    if case["excl"] is not None:
+        x = O.gaps(C, case["seqlen"], *case["excl"]) if case.get("trim") else O.Index(C, *case["excl"])
     return plan, y, q, x
+
+
+def excl_mode(case):
+    return O.EXCLUDE_TRIM if case.get("trim") else O.EXCLUDE_DROP
 
 
 def load_engine(eng, case, kind):
@@ -62,7 +70,7 @@ def load_engine(eng, case, kind):
     else:
         eng.clear_query()
     if case["excl"] is not None:
-        eng.set_exclude(*case["excl"])
+        eng.set_exclude(*case["excl"], option="trim" if case.get("trim") else "drop")
     else:
         eng.clear_exclude()
     seg = case["seg"]
@@ -90,11 +98,11 @@ def canon_rows(seqid, start, end, src, block, it):
     return np.stack([it[o], seqid[o], start[o], end[o], src[o], block[o]], axis=1)
 
 
-def oracle_rows(plan, y, x, draws, R):
+def oracle_rows(plan, y, x, draws, R, mode=O.EXCLUDE_DROP):
     bc, bs, dt = draws
     out = []
     for r in range(R):
-        rows = O.iteration_rows(plan, y, bc[r], bs[r], dt[r], exclude=x)
+        rows = O.iteration_rows(plan, y, bc[r], bs[r], dt[r], exclude=x, exclude_mode=mode)
         out.append(canon_rows(rows["chrom"], rows["start"], rows["end"], rows["src"], rows["block"], np.full(rows["src"].size, r)))
     return np.concatenate(out) if out else np.empty((0, 6), np.int64)
 

@@ -21,11 +21,11 @@ def _check_counts(eng, case, kind, R, seed, philox):
     assert np.array_equal(ts, plan.tile_chrom) and np.array_equal(tt, plan.tile_start) and np.array_equal(bw, plan.bait_width)
     if philox:
         draws = Draws(n_iter=R, rng_mode=_lib.RNG_PHILOX, seed=seed, iter0=5)
-        ref = O.boot_counts(plan, y, q, R, exclude=x, seed=seed, iter0=5)
+        ref = O.boot_counts(plan, y, q, R, exclude=x, exclude_mode=H.excl_mode(case), seed=seed, iter0=5)
     else:
         d = H.draw_R(plan, seed, R)
         draws = Draws(n_iter=R, rng_mode=_lib.RNG_HOST, bait_seqid=d[0], bait_start=d[1], dst_tile=d[2] if kind >= 4 else None)
-        ref = O.boot_counts(plan, y, q, R, exclude=x, draws=d)
+        ref = O.boot_counts(plan, y, q, R, exclude=x, exclude_mode=H.excl_mode(case), draws=d)
     got = eng.run_counts(draws)
     assert np.array_equal(got["iter_nranges"], ref["iter_nranges"])
     assert np.array_equal(got["iter_totals"], ref["iter_totals"])
@@ -250,3 +250,43 @@ def test_philox_moments_match_r_rng(engine):
     span = (np.ceil(L[0] / 20_000) - 1) * 20_000 + 1
     hist = np.histogram(c0, bins=20, range=(1, span + 1))[0]
     assert ((hist - hist.mean()) ** 2 / hist.mean()).sum() / 19 < 1.5
+
+
+@pytest.mark.parametrize("kind", ALL_KINDS)
+@pytest.mark.parametrize("stranded", [False, True])
+def test_exclude_trim(engine, kind, stranded):
+    """excludeOption = "trim" (R/bootRanges.R:110-115): ranges are cut to gaps(exclude); one row per
+    (range, gap) overlap.  Counts, row counts and the table itself against the oracle."""
+    case = H.random_case(seed=210 + kind, n=700, n_seq=3, n_query=70, n_excl=0, stranded=stranded, wmax=300, n_seg=9, n_states=2)
+    rng = np.random.default_rng(6)
+    L = case["seqlen"]
+    sid = rng.integers(0, 3, 60).astype(np.int32)
+    st = (1 + rng.random(60) * (L[sid] - 60)).astype(np.int32)
+    en = (st + rng.integers(0, 50, 60)).astype(np.int32)
+    en[::12] = (L[sid[::12]] + 20).astype(np.int32)
+    case["excl"], case["trim"] = (sid, st, en, None), True
+    _check_counts(engine, case, kind, R=5, seed=4, philox=False)
+    if kind < 3:
+        _check_counts(engine, case, kind, R=4, seed=99, philox=True)
+    plan, y, q, x = H.oracle_objects(case, kind)
+    H.load_engine(engine, case, kind)
+    d = H.draw_R(plan, 8, 3)
+    rows = engine.run_materialize(Draws(n_iter=3, rng_mode=_lib.RNG_HOST, bait_seqid=d[0], bait_start=d[1], dst_tile=d[2] if kind >= 4 else None))
+    it = np.repeat(np.arange(3), np.diff(rows["iter_offsets"]))
+    want = H.oracle_rows(plan, y, x, d, 3, mode=O.EXCLUDE_TRIM)
+    got = np.stack([it, rows["seqid"], rows["start"], rows["end"], rows["src"], rows["block"]], axis=1)
+    # (iter, block, src, start): the pieces of one range come out in ascending gap order
+    key = lambda a: a[np.lexsort((a[:, 2], a[:, 4], a[:, 5], a[:, 0]))]
+    assert np.array_equal(key(got), key(want))
+    # no piece overlaps an exclude range (tests/testthat/test_trim_exclude.R:13)
+    for c, s, e in zip(rows["seqid"], rows["start"], rows["end"]):
+        assert not np.any((sid == c) & (st <= e) & (en >= s))
+
+
+def test_trim_needs_unstranded_exclude(engine):
+    from nullranges_b200 import EngineError
+    case = H.random_case(seed=5, n=50, n_excl=5, stranded=True)
+    engine.set_ranges(case["seqlen"], *case["y"])
+    with pytest.raises(EngineError, match="strand"):
+        engine.set_exclude(*case["excl"], option="trim")
+    engine.clear_exclude()

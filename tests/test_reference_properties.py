@@ -128,3 +128,42 @@ def test_product_roxygen_example():
     br = bootRanges(gr, blockLength=10, storeBlockLength=True)
     assert br.start.tolist() == [5, 13, 25, 36, 39, 49] and br.end.tolist() == [9, 17, 29, 40, 43, 50]
     assert br.iter.tolist() == [1] * 6 and br.mcols["blockLength"].tolist() == [10] * 6
+
+
+# ---- tests/testthat/test_trim_exclude.R ----------------------------------------------------------
+
+def _trim_fixture():
+    start = 1 + 2 * np.arange(46)                                  # :4
+    strand = np.tile([1, 2], 23).astype(np.int8)                   # rep(c("+","-"), length = 46)
+    order = np.lexsort((start + 9, start, np.array([2, 0, 1])[strand]))  # y <- sort(y): + before -
+    return start[order], start[order] + 9, strand[order]
+
+
+def test_oracle_trim_exclude():
+    st, en, sd = _trim_fixture()
+    plan = O.Plan(O.UNSEG_ACROSS, [100], 20)
+    y = O.Index(1, np.zeros(46, np.int32), st, en, sd)
+    g = O.gaps(1, [100], [0], [36], [45])
+    assert (g.start.tolist(), g.end.tolist()) == ([1, 46], [35, 100])
+    for seed in range(1, 6):
+        d = plan.draw_R(O.RRng(seed), 1)
+        rows = O.iteration_rows(plan, y, d[0][0], d[1][0], d[2][0], exclude=g, exclude_mode=O.EXCLUDE_TRIM)
+        assert rows["src"].size > 0
+        assert not np.any((rows["start"] <= 45) & (rows["end"] >= 36))   # expect_true(!any(overlapsAny(br, exclude)))
+
+
+@pytest.mark.gpu
+def test_product_trim_exclude():
+    from nullranges_b200 import GRanges, bootRanges, set_seed
+    st, en, sd = _trim_fixture()
+    y = GRanges(["chr1"] * 46, st, end=en, strand=sd, seqlengths={"chr1": 100}, block=np.ones(46))
+    exclude = GRanges(["chr1"], [36], end=[45], seqlengths={"chr1": 100})
+    assert y.is_sorted()
+    for seed in range(1, 6):
+        set_seed(seed)
+        br = bootRanges(y, blockLength=20, exclude=exclude, excludeOption="trim")
+        assert len(br) > 0 and not np.any((br.start <= 45) & (br.end >= 36))
+        assert "block" not in br.mcols                                # the input's own `block` column is dropped (:126)
+        assert set(np.unique(br.strand)) <= {1, 2}                     # strands ride along with the pieces
+    with pytest.raises(ValueError):
+        bootRanges(y, blockLength=20, excludeOption="trim")          # strand(NULL): the reference errors too
