@@ -90,6 +90,12 @@ struct nrb200_handle {
     bool own_stream = false;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     cudaStream_t copy_stream = nullptr;
+    // Pinned staging for small host->device uploads (block tables, window lists, ...): a copy from
+    // pageable memory would first wait for everything queued on the stream; through this arena the
+    // uploads queue behind the GPU work and the host carries on.  Reset whenever the stream is known
+    // to be idle; when full, uploads fall back to the direct (synchronising) copy.
+    char *arena = nullptr;
+    size_t arena_cap = 0, arena_used = 0;
     cudaEvent_t split_ev = nullptr;       // set while a stats run wants the rows / count kernel split
     std::vector<cudaEvent_t> batch_ev;    // 3 per batch: start, rows done, count done
     cudaEvent_t chunk_ev[16] = {};
@@ -154,8 +160,36 @@ inline int excl_kind(const nrb200_handle *h) { return h->excl.n == 0 ? kExclNone
             return fail((h), NRB200_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(err__)); \
     } while (0)
 
+constexpr size_t kArenaBytes = 16u << 20;
+
+// Waits for the stream; the staging arena can be reused afterwards.
+int sync_stream(nrb200_handle *h) {
+    NRB_CUDA(h, cudaStreamSynchronize(h->stream));
+    h->arena_used = 0;
+    return NRB200_OK;
+}
+
+// Host -> device copy of a library-owned (pageable) array, staged through the pinned arena when it fits.
 template <class T>
 int upload(nrb200_handle *h, DevMem &dst, const T *src, size_t n) {
+    const size_t bytes = n * sizeof(T);
+    NRB_CUDA(h, dst.reserve(bytes));
+    if (!n) return NRB200_OK;
+    if (!h->arena && cudaMallocHost((void **)&h->arena, kArenaBytes) == cudaSuccess) h->arena_cap = kArenaBytes;
+    const size_t at = (h->arena_used + 255) & ~(size_t)255;
+    if (h->arena && at + bytes <= h->arena_cap) {
+        std::memcpy(h->arena + at, src, bytes);
+        h->arena_used = at + bytes;
+        NRB_CUDA(h, cudaMemcpyAsync(dst.p, h->arena + at, bytes, cudaMemcpyHostToDevice, h->stream));
+    } else {
+        NRB_CUDA(h, cudaMemcpyAsync(dst.p, src, bytes, cudaMemcpyHostToDevice, h->stream));
+    }
+    return NRB200_OK;
+}
+
+// Host -> device copy straight from a caller-owned array (pinned or pageable): never staged.
+template <class T>
+int upload_direct(nrb200_handle *h, DevMem &dst, const T *src, size_t n) {
     NRB_CUDA(h, dst.reserve(n * sizeof(T)));
     if (n) NRB_CUDA(h, cudaMemcpyAsync(dst.p, src, n * sizeof(T), cudaMemcpyHostToDevice, h->stream));
     return NRB200_OK;
@@ -172,7 +206,6 @@ int range_set_to_device(nrb200_handle *h, RangeSet &rs) {
     if ((rc = upload(h, rs.src, rs.h_src.data(), n))) return rc;
     if ((rc = upload(h, rs.seq_off, rs.h_seq_off.data(), rs.h_seq_off.size()))) return rc;
     if (rs.stranded && (rc = upload(h, rs.strand, rs.h_strand.data(), n))) return rc;
-    NRB_CUDA(h, cudaStreamSynchronize(h->stream));
     rs.on_device = true;
     return NRB200_OK;
 }
@@ -245,8 +278,7 @@ int load_range_set(nrb200_handle *h, RangeSet &rs, const char *what, int64_t n, 
     int rc;
     if ((rc = range_set_to_device(h, rs))) return rc;
     if (keep_seqid_dev && (rc = upload(h, rs.seqid, h_seqid.data(), n))) return rc;
-    NRB_CUDA(h, cudaStreamSynchronize(h->stream));  // host vectors above may go out of scope
-    return NRB200_OK;
+    return NRB200_OK;  // uploads were staged or made with the synchronising copy: the host vectors may go
 }
 
 // y on the fast path: the caller's arrays go to the device as they are and ONE kernel does the
@@ -259,10 +291,10 @@ int load_y_device(nrb200_handle *h, int64_t n, const int32_t *seqid, const int32
     const int C = h->n_seq;
     if (n <= 0 || n > (int64_t)INT32_MAX - 64 || !seqid || !start || !end) return 1;  // host path words the errors
     int rc;
-    if ((rc = upload(h, y.seqid, seqid, (size_t)n))) return rc;
-    if ((rc = upload(h, y.start, start, (size_t)n))) return rc;
-    if ((rc = upload(h, y.end, end, (size_t)n))) return rc;
-    if (strand && (rc = upload(h, y.strand, strand, (size_t)n))) return rc;
+    if ((rc = upload_direct(h, y.seqid, seqid, (size_t)n))) return rc;
+    if ((rc = upload_direct(h, y.start, start, (size_t)n))) return rc;
+    if ((rc = upload_direct(h, y.end, end, (size_t)n))) return rc;
+    if (strand && (rc = upload_direct(h, y.strand, strand, (size_t)n))) return rc;
     Trace tr("load_y_device");
     tr.lap("enqueue_h2d");
     // scratch: InspectOut | seq_count[C] | seq_max_end[C]
@@ -280,7 +312,7 @@ int load_y_device(nrb200_handle *h, int64_t n, const int32_t *seqid, const int32
     NRB_CUDA(h, cudaGetLastError());
     std::vector<int32_t> res(words);
     NRB_CUDA(h, cudaMemcpyAsync(res.data(), base, words * 4, cudaMemcpyDeviceToHost, h->stream));
-    NRB_CUDA(h, cudaStreamSynchronize(h->stream));
+    if ((rc = sync_stream(h))) return rc;  // the caller's arrays are no longer read after this point
     tr.lap("inspect+sync");
     if (res[0] != 0 || res[1] != 0) return 1;  // invalid (host path names the problem) or unsorted
     y.n = n;
@@ -302,8 +334,7 @@ int load_y_device(nrb200_handle *h, int64_t n, const int32_t *seqid, const int32
     NRB_CUDA(h, h->sort_tmp.reserve(tmp_bytes));
     NRB_CUDA(h, cub::DeviceScan::InclusiveScanByKey(h->sort_tmp.p, tmp_bytes, y.seqid.as<int32_t>(), y.end.as<int32_t>(),
                                                     y.pmax.as<int32_t>(), MaxOp(), n, cub::Equality(), h->stream));
-    NRB_CUDA(h, cudaStreamSynchronize(h->stream));  // seq_off upload reads y.h_seq_off
-    return NRB200_OK;
+    return NRB200_OK;  // the index build that follows stays queued: the host moves on to the plan and the lists
 }
 
 int build_rank_tables(nrb200_handle *h) {
@@ -369,7 +400,6 @@ int build_rank_tables(nrb200_handle *h) {
     build_rank_table_kernel<<<grid, threads, 0, h->stream>>>(h->end_sorted.as<int32_t>(), y.seq_off.as<int32_t>(),
                                                              h->rank_off_dev.as<int64_t>(), C, shift, h->rank_end.as<uint32_t>());
     NRB_CUDA(h, cudaGetLastError());
-    NRB_CUDA(h, cudaStreamSynchronize(h->stream));
     return NRB200_OK;
 }
 
@@ -396,7 +426,6 @@ int build_slices(nrb200_handle *h, const RangeSet &rs, DevMem &lo_dev, DevMem &h
     int rc;
     if ((rc = upload(h, lo_dev, lo.data(), (size_t)B))) return rc;
     if ((rc = upload(h, hi_dev, hi.data(), (size_t)B))) return rc;
-    NRB_CUDA(h, cudaStreamSynchronize(h->stream));
     return NRB200_OK;
 }
 
@@ -501,10 +530,7 @@ int build_pairs(nrb200_handle *h) {
         if ((rc = upload(h, h->tile_x_off, x_off.data(), (size_t)B + 1))) return rc;
         if ((rc = upload(h, h->tile_x_rec, x_rec.data(), x_rec.size()))) return rc;
     }
-    if (G == 0) {
-        NRB_CUDA(h, cudaStreamSynchronize(h->stream));
-        return NRB200_OK;
-    }
+    if (G == 0) return NRB200_OK;
 
     // ---- per feature.  Tiles of each sequence in ascending start order with the running max of
     // their ends; features come in canonical (start-sorted) order, so the first tile that can still
@@ -598,7 +624,6 @@ int build_pairs(nrb200_handle *h) {
     if ((rc = upload(h, h->f_src, f_src.data(), (size_t)G))) return rc;
     if ((rc = upload(h, h->pair_off, f_off.data(), (size_t)G + 1))) return rc;
     if ((rc = upload(h, h->pair_rec, f_recs.data(), f_recs.size()))) return rc;
-    NRB_CUDA(h, cudaStreamSynchronize(h->stream));
     tr.lap("upload");
     return NRB200_OK;
 }
@@ -868,7 +893,7 @@ int run_counts_core(nrb200_handle *h, const nrb200_draws *d, bool want_counts, i
         cudaEventElapsedTime(&t_ms, h->ev[0], h->ev[2]);
         unsigned long long hits = 0;
         NRB_CUDA(h, cudaMemcpyAsync(&hits, h->d_n_hits.p, 8, cudaMemcpyDeviceToHost, h->stream));
-        NRB_CUDA(h, cudaStreamSynchronize(h->stream));
+        if (int rc_sync = sync_stream(h)) return rc_sync;
         std::memset(stats, 0, sizeof *stats);
         stats->kernel_ms = k_ms;
         stats->total_ms = t_ms;
@@ -951,6 +976,7 @@ void nrb200_destroy(nrb200_handle *h) {
         cudaStreamSynchronize(h->copy_stream);
         cudaStreamDestroy(h->copy_stream);
     }
+    if (h->arena) cudaFreeHost(h->arena);
     if (h->own_stream) cudaStreamDestroy(h->stream);
     delete h;
 }
@@ -1058,7 +1084,6 @@ int nrb200_set_plan(nrb200_handle *h, const nrb200_plan_spec *spec, int64_t *n_b
     const size_t o_sq = put32(pl.sg_seq), o_ss = put32(pl.sg_start), o_st = put32(pl.sg_tiles);
     if ((rc = upload(h, h->sampler_i64, i64.data(), i64.size()))) return rc;
     if ((rc = upload(h, h->sampler_i32, i32.data(), i32.size()))) return rc;
-    NRB_CUDA(h, cudaStreamSynchronize(h->stream));
     const int64_t *b64 = h->sampler_i64.as<int64_t>();
     const int32_t *b32 = h->sampler_i32.as<int32_t>();
     h->sampler_view = SamplerView{pl.kind, pl.n_seq, pl.n_states, pl.block_length, pl.genome_length,
@@ -1104,7 +1129,7 @@ int nrb200_run_counts(nrb200_handle *h, const nrb200_draws *draws, int64_t *iter
     const int64_t R = draws->n_iter, G = h->query.n;
     if ((rc = fetch_u64_as_i64(h, h->d_iter_nranges, R, iter_nranges))) return rc;
     if ((rc = fetch_u64_as_i64(h, h->d_iter_totals, R, iter_totals))) return rc;
-    NRB_CUDA(h, cudaStreamSynchronize(h->stream));
+    if (int rc_sync = sync_stream(h)) return rc_sync;
     if (h->copy_stream) NRB_CUDA(h, cudaStreamSynchronize(h->copy_stream));
     if (stats) stats->d2h_bytes = (iter_nranges ? R * 8 : 0) + (iter_totals ? R * 8 : 0) + (feature_counts ? R * G * 4 : 0);
     return NRB200_OK;
@@ -1155,7 +1180,7 @@ int nrb200_run_moments(nrb200_handle *h, const nrb200_draws *draws, int64_t batc
         NRB_CUDA(h, cudaGetLastError());
         if ((rc = fetch_u64_as_i64(h, h->d_iter_nranges, d.n_iter, iter_nranges ? iter_nranges + r0 : nullptr))) return rc;
         if ((rc = fetch_u64_as_i64(h, h->d_iter_totals, d.n_iter, iter_totals ? iter_totals + r0 : nullptr))) return rc;
-        NRB_CUDA(h, cudaStreamSynchronize(h->stream));
+        if (int rc_sync = sync_stream(h)) return rc_sync;
         acc.kernel_ms += st.kernel_ms;
         acc.rows_kernel_ms += st.rows_kernel_ms;
         acc.count_kernel_ms += st.count_kernel_ms;
@@ -1176,7 +1201,7 @@ int nrb200_moments_fetch(nrb200_handle *h, int64_t *feat_sum, int64_t *feat_sums
     if (feat_sum) NRB_CUDA(h, cudaMemcpyAsync(feat_sum, h->m_sum.p, bytes, cudaMemcpyDeviceToHost, h->stream));
     if (feat_sumsq) NRB_CUDA(h, cudaMemcpyAsync(feat_sumsq, h->m_sumsq.p, bytes, cudaMemcpyDeviceToHost, h->stream));
     if (feat_n_ge_observed) NRB_CUDA(h, cudaMemcpyAsync(feat_n_ge_observed, h->m_nge.p, bytes, cudaMemcpyDeviceToHost, h->stream));
-    NRB_CUDA(h, cudaStreamSynchronize(h->stream));
+    if (int rc_sync = sync_stream(h)) return rc_sync;
     return NRB200_OK;
 }
 
@@ -1216,7 +1241,7 @@ int nrb200_count_observed(nrb200_handle *h, int32_t *feature_counts, int64_t *to
     unsigned long long t = 0;
     if (feature_counts) NRB_CUDA(h, cudaMemcpyAsync(feature_counts, counts.p, q.n * 4, cudaMemcpyDeviceToHost, h->stream));
     NRB_CUDA(h, cudaMemcpyAsync(&t, tot.p, 8, cudaMemcpyDeviceToHost, h->stream));
-    NRB_CUDA(h, cudaStreamSynchronize(h->stream));
+    if (int rc_sync = sync_stream(h)) return rc_sync;
     if (total) *total = (int64_t)t;
     return NRB200_OK;
 }
@@ -1261,7 +1286,7 @@ int nrb200_run_materialize(nrb200_handle *h, const nrb200_draws *draws, int64_t 
     NRB_CUDA(h, cudaGetLastError());
     std::vector<int64_t> per_iter(R), offs(R + 1, 0);
     if ((rc = fetch_u64_as_i64(h, h->d_iter_nranges, R, per_iter.data()))) return rc;
-    NRB_CUDA(h, cudaStreamSynchronize(h->stream));
+    if (int rc_sync = sync_stream(h)) return rc_sync;
     for (int64_t r = 0; r < R; ++r) offs[r + 1] = offs[r] + per_iter[r];
     const int64_t rows = offs[R];
     if ((rc = upload(h, h->iter_off_dev, offs.data(), (size_t)R + 1))) return rc;
@@ -1286,7 +1311,7 @@ int nrb200_run_materialize(nrb200_handle *h, const nrb200_draws *draws, int64_t 
         }
     }
     NRB_CUDA(h, cudaEventRecord(h->ev[2], h->stream));
-    NRB_CUDA(h, cudaStreamSynchronize(h->stream));
+    if (int rc_sync = sync_stream(h)) return rc_sync;
     h->n_rows = rows;
     if (iter_offsets) std::memcpy(iter_offsets, offs.data(), (size_t)(R + 1) * 8);
     if (stats) {
@@ -1314,7 +1339,7 @@ int nrb200_fetch_rows(nrb200_handle *h, int64_t row0, int64_t n, int32_t *seqid,
     for (auto &c : cols)
         if (c.dst && n)
             NRB_CUDA(h, cudaMemcpyAsync(c.dst, c.src->as<int32_t>() + row0, n * 4, cudaMemcpyDeviceToHost, h->stream));
-    NRB_CUDA(h, cudaStreamSynchronize(h->stream));
+    if (int rc_sync = sync_stream(h)) return rc_sync;
     return NRB200_OK;
 }
 
