@@ -332,7 +332,7 @@ def run_gpu(args):
         stream_achieved = stream_alg / (stream_ms * 1e-3) / 1e9
         traffic = None
         try:
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get("boot_count_kernel_dram_bytes_per_launch")
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get("rank_launch_group_dram_bytes_per_launch")
         except Exception:
             pass
         # CPU baseline: bounded sample on this box's cores
