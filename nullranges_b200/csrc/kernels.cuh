@@ -356,6 +356,8 @@ struct RowsOut {
     int32_t *seq, *start, *end, *src, *block;
     const int64_t *iter_off;      // [n_iter + 1]
     const int32_t *within_off;    // [n_iter x n_blocks]
+    const int32_t *item_rows;     // [n_iter x n_blocks] rows the count pass promised for the item
+    int *overflow;                // set when a fill pass finds more rows than promised (never written past the promise)
 };
 
 // grid = (block groups, iterations); one warp per (iteration, block), 64 candidate ranges per
@@ -370,6 +372,7 @@ __global__ void __launch_bounds__(256) boot_fill_kernel(const BootParams P, cons
          b += (int64_t)gridDim.x * (blockDim.x / kWarp)) {
         const Item it = load_item(P, r, b);
         int64_t out = row0 + __ldg(O.within_off + r * P.n_blocks + b);
+        const int64_t out_end = out + __ldg(O.item_rows + r * P.n_blocks + b);
         for (int32_t base = it.lo; base < it.hi; base += 2 * kWarp) {
             const int32_t i0 = base + lane, i1 = i0 + kWarp;
             const bool in0 = i0 < it.hi, in1 = i1 < it.hi;
@@ -384,6 +387,10 @@ __global__ void __launch_bounds__(256) boot_fill_kernel(const BootParams P, cons
                 if (keep1) keep1 = !excluded<STRANDED>(P.excl, it.tile, s1, e1, (STRANDED && P.y.strand) ? __ldg(P.y.strand + i1) : 0);
             }
             const unsigned m0 = __ballot_sync(kFull, keep0), m1 = __ballot_sync(kFull, keep1);
+            if (out + __popc(m0) + __popc(m1) > out_end) {  // the two passes disagree: refuse to write
+                if (lane == 0) atomicExch(O.overflow, 1);
+                break;
+            }
             if (keep0) {
                 const int64_t pos = out + __popc(m0 & below);
                 O.seq[pos] = it.tile_seq;
@@ -417,6 +424,7 @@ __global__ void __launch_bounds__(256) boot_fill_trim_kernel(const BootParams P,
         const Item it = load_item(P, r, b);
         const int32_t x_lo = __ldg(P.excl.tile_lo + it.tile), x_hi = __ldg(P.excl.tile_hi + it.tile);
         int64_t out = row0 + __ldg(O.within_off + r * P.n_blocks + b);
+        const int64_t out_end = out + __ldg(O.item_rows + r * P.n_blocks + b);
         for (int32_t base = it.lo; base < it.hi; base += kWarp) {
             const int32_t i = base + lane;
             int32_t s2 = 0, e2 = -1;
@@ -431,6 +439,10 @@ __global__ void __launch_bounds__(256) boot_fill_trim_kernel(const BootParams P,
                 if (lane >= d) before += t;
             }
             const int total = __shfl_sync(kFull, before, kWarp - 1);
+            if (out + total > out_end) {
+                if (lane == 0) atomicExch(O.overflow, 1);
+                break;
+            }
             if (n) {
                 int64_t pos = out + (before - n);
                 const int32_t src = P.y.src ? __ldg(P.y.src + i) : i;
