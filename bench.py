@@ -110,7 +110,7 @@ def run_reference(args):
 # clocks
 # ---------------------------------------------------------------------------------------------
 class ClockSampler(threading.Thread):
-    """Samples SM clock and throttle reasons of one GPU every 20 ms via NVML while running."""
+    """Samples SM clock and throttle reasons of one GPU every ~2 ms via NVML while running."""
 
     def __init__(self, index: int):
         super().__init__(daemon=True)
@@ -145,7 +145,7 @@ class ClockSampler(threading.Thread):
                         self.reasons.add(name)
             except Exception:
                 pass
-            self._stop_evt.wait(0.02)
+            self._stop_evt.wait(0.002)
 
     def stop(self) -> dict:
         self._stop_evt.set()
@@ -232,6 +232,8 @@ def run_gpu(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    clocks = ClockSampler(local)  # samples from the warm-up to the end of the accounting pass (same kernels throughout)
+    clocks.start()
     with torch.cuda.stream(stream):
         for w in range(args.warmup):
             step_resident(w, False)
@@ -239,8 +241,6 @@ def run_gpu(args):
             gather_small()
         wait_gathers()
         barrier()
-        clocks = ClockSampler(local)
-        clocks.start()
         ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
         t_wall = time.perf_counter()
         for s in range(args.steps):  # no host synchronisation inside the timed region: the queue runs ahead
@@ -254,7 +254,6 @@ def run_gpu(args):
             ev[s][1].record(stream)
         barrier()
         t_wall = time.perf_counter() - t_wall
-        clk = clocks.stop()
         dev_ms = sum(a.elapsed_time(b) for a, b in ev)
         # accounting pass over the SAME steps (same global iterations, hence the same sampled ranges):
         # per-kernel CUDA-event times, launches and H of the byte model.  Not part of `value`.
@@ -267,6 +266,8 @@ def run_gpu(args):
             count_ms += st["count_kernel_ms"]
             hits += st["n_hits"]
             launches += st["n_launches"]
+        clk = clocks.stop()
+        clk["window"] = "warm-up + timed region + accounting pass (the timed region alone lasts a few ms)"
 
     # ---- the streaming kernel on the same workload (the path that really reads the 8*H bytes)
     stream_ms, stream_hits, stream_steps = 0.0, 0, 3
@@ -347,6 +348,8 @@ def run_gpu(args):
         probe = cpu_sample(O, plan, yi, qi, n_cpu, cores)
         n_cpu = int(min(R_STEP, max(n_cpu, round(12.0 / (probe / n_cpu)))))
         cpu_t = cpu_sample(O, plan, yi, qi, n_cpu, cores, iter0=100)
+        n_one = max(4, n_cpu // (4 * cores))
+        cpu_t1 = cpu_sample(O, plan, yi, qi, n_one, 1, iter0=100)
         line = {
             "metric": METRIC, "value": R * world * args.steps / (dev_ms * 1e-3), "unit": "iter/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps,
@@ -372,6 +375,7 @@ def run_gpu(args):
                                 "achieved": stream_achieved, "peak": peak, "unit": "GB/s", "frac": stream_achieved / peak,
                                 "kernel_ms_per_launch": stream_ms / stream_steps, "iters_per_s": R * stream_steps / (stream_ms * 1e-3)},
             "cpu_baseline": {"value": n_cpu / cpu_t, "unit": "iter/s", "cores": cores, "kind": "port",
+                             "single_thread_value": n_one / cpu_t1, "single_thread_sample": f"{n_one} iterations on 1 thread (R itself is single-threaded)",
                              "sample": f"{n_cpu} iterations of the same workload (same ranges/query/blockLength, Philox draws), oracle/nr_oracle.c on {cores} pthreads"},
             "clocks": clk,
         }

@@ -558,6 +558,7 @@ int build_pairs(nrb200_handle *h) {
             te_max[c][j] = m;
         }
     }
+    tr.lap("tiles_by_seq");
     // calls emit(tile, ws, we, sign) for every signed window of every feature, features in canonical order
     auto enumerate = [&](auto &&begin_feature, auto &&emit) {
         for (int c = 0; c < C; ++c) {
@@ -593,6 +594,7 @@ int build_pairs(nrb200_handle *h) {
     };
     std::vector<int32_t> len(G, 0);
     enumerate([](int32_t) {}, [&](int32_t k, int32_t, int64_t, int64_t, int) { ++len[k]; });
+    tr.lap("pass1");
     // Visit order of the count kernel: features grouped by list length (stable counting sort, so
     // neighbours in a group are neighbours on the genome): the lanes of a warp then loop equally often.
     constexpr int kBins = 64;
@@ -613,6 +615,7 @@ int build_pairs(nrb200_handle *h) {
         f_off[i + 1] = (int32_t)total;
     }
     h->n_pairs = total;
+    tr.lap("binning");
     std::vector<PairRec> f_recs((size_t)total);
     int64_t cursor = 0;
     enumerate([&](int32_t k) { cursor = f_off[pos_of[k]]; },

@@ -290,3 +290,19 @@ def test_trim_needs_unstranded_exclude(engine):
     with pytest.raises(EngineError, match="strand"):
         engine.set_exclude(*case["excl"], option="trim")
     engine.clear_exclude()
+
+
+def test_cfg2_validation_mode_R1000(engine):
+    """BASELINE target: bit-exact overlap counts in validation mode for 1M ranges x R = 1000 -- block draws
+    from R's RNG under set.seed(2024), whole [1000 x 20k] matrix, totals and row counts vs the oracle."""
+    from nullranges_b200 import synth
+    y, x = synth.atac_peaks(1_000_000, seed=3), synth.genes(20_000, seed=2)
+    case = _synth_case(y, x)
+    plan, yi, qi, _ = H.oracle_objects(case, 0)
+    H.load_engine(engine, case, 0)
+    R = 1000
+    d = plan.draw_R(O.RRng(2024), R)
+    got = engine.run_counts(Draws(n_iter=R, rng_mode=_lib.RNG_HOST, bait_seqid=d[0], bait_start=d[1]))
+    ref = O.boot_counts(plan, yi, qi, R, draws=d, nthreads=O.max_threads())
+    for k in ("iter_nranges", "iter_totals", "feature_counts"):
+        assert np.array_equal(got[k], ref[k]), k
