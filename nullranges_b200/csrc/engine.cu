@@ -631,12 +631,12 @@ int build_pairs(nrb200_handle *h) {
     return NRB200_OK;
 }
 
-// The rank path covers the bootstrap samplers (with or without excludeOption = "drop") whenever
+// The rank path covers every sampler (bootstrap and permute, with or without exclusion) whenever
 // strand cannot matter: y is all '*', or the query and the exclude set are.  Everything else
 // streams the hits (boot_count_kernel).
 bool rank_path_ok(const nrb200_handle *h, bool with_query) {
     if (h->flags & NRB200_FLAG_FORCE_STREAM) return false;
-    if (h->plan.permute() || !h->tiles_in_bounds) return false;
+    if (!h->tiles_in_bounds) return false;
     if (h->y.stranded && ((with_query && h->query.stranded) || (h->excl.n > 0 && active_excl(h).stranded))) return false;
     return true;
 }

@@ -193,7 +193,7 @@ struct Item {
 __device__ __forceinline__ Item load_item(const BootParams &P, int64_t r, int64_t b) {
     Item it;
     const int64_t flat = r * P.n_blocks + b;
-    if (P.draw_tab) {  // the rows kernel of the rank path already drew this block
+    if (P.draw_tab && !P.permute) {  // the rows kernel of the rank path already drew this block (bootstrap kinds: block b -> tile b)
         const int2 d = __ldg(P.draw_tab + flat);
         it.bait_seq = d.x;
         it.bait_start = d.y;
@@ -509,6 +509,7 @@ struct TileExcl {              // signed exclusion windows of each tile, for the
 struct PairProbe {
     int4 si;                   // seq_info of the bait sequence
     int32_t A, Bv;             // count = #{start <= A and end >= Bv}
+    int32_t bs;                // bait start (the permute variants also need start >= bs)
     int32_t key_a, key_b;      // clamped search keys (A + 1 in starts, Bv in sorted ends)
     int32_t a0, an, b0, bn;    // bucket start and (capped) size in start[] and end_sorted[]
 };
@@ -517,6 +518,7 @@ __device__ __forceinline__ void pair_keys(PairProbe &q, int2 draw, int32_t width
                                           int32_t gs, int32_t ge, int rank_shift, int32_t &ua, int32_t &ub) {
     const int32_t bs = draw.y;
     const int32_t sh = ts - bs;
+    q.bs = bs;
     q.A = min(bs + (width - 1), min(ge, seq_len) - sh);
     q.Bv = max(bs, gs - sh);
     q.key_a = rank_clamp_key(q.A + 1, q.si);
@@ -536,16 +538,27 @@ __device__ __forceinline__ int32_t bucket_rank(const int32_t *__restrict__ vals,
     return a + (v0 < key) + (v1 < key) + (v2 < key);
 }
 
-__device__ __forceinline__ int pair_finish(const RangesView &y, const PairProbe &q, int32_t ia, int32_t ib) {
-    if (q.Bv <= q.A) return q.A < 1 ? 0 : ia - ib;
-    // rare: the feature lies beside the tile; members contain [A, Bv]
-    if (q.A < 1 || q.Bv > q.si.z) return 0;
+// #{start <= a and end >= b} for a < b: such ranges contain [a, b]; walk back from #{start <= a}
+// (index ia) under the running-max-of-end bound.  Usually zero or one step.
+__device__ __forceinline__ int count_spanning(const RangesView &y, const int4 si, int32_t ia, int32_t b) {
+    if (b > si.z) return 0;
     int n = 0;
-    for (int32_t k = ia - 1; k >= q.si.x && __ldg(y.pmax + k) >= q.Bv; --k) n += __ldg(y.end + k) >= q.Bv;
+    for (int32_t k = ia - 1; k >= si.x && __ldg(y.pmax + k) >= b; --k) n += __ldg(y.end + k) >= b;
     return n;
 }
 
-template <int RPT>
+// PERMUTE: a range belongs to the ONE tile that holds its start (findOverlaps(select = "first"),
+// R/bootUnsegmented.R:95, :155), so the members are {bs <= start <= A and end >= Bv}: the bootstrap
+// count minus the ranges that start before the tile and reach Bv (they contain [bs - 1, Bv]).
+template <bool PERMUTE>
+__device__ __forceinline__ int pair_finish(const RangesView &y, const PairProbe &q, int32_t ia, int32_t ib) {
+    if (q.A < 1 || (PERMUTE && q.A < q.bs)) return 0;  // permute: no start can lie in [bs, A]
+    int n = q.Bv <= q.A ? ia - ib : count_spanning(y, q.si, ia, q.Bv);  // second form: the feature lies beside the tile
+    if (PERMUTE && n > 0) n -= count_spanning(y, q.si, first_ge_ranked(y.start, y.rank_start, y.rank_shift, q.si, q.bs), q.Bv);
+    return n;
+}
+
+template <int RPT, bool PERMUTE = false>
 __device__ __forceinline__ void count_pairs(const RangesView &y, const int2 (&d)[RPT], int32_t width, int32_t ts,
                                             int32_t seq_len, int32_t gs, int32_t ge, int (&cnt)[RPT]) {
     PairProbe q[RPT];
@@ -575,7 +588,7 @@ __device__ __forceinline__ void count_pairs(const RangesView &y, const int2 (&d)
     for (int j = 0; j < RPT; ++j) {
         const int32_t ia = bucket_rank(y.start, y.rank_start, ua[j], q[j].si, q[j].a0, q[j].an, q[j].key_a, va[j][0], va[j][1], va[j][2]);
         const int32_t ib = bucket_rank(y.end_sorted, y.rank_end, ub[j], q[j].si, q[j].b0, q[j].bn, q[j].key_b, vb[j][0], vb[j][1], vb[j][2]);
-        cnt[j] += pair_finish(y, q[j], ia, ib);
+        cnt[j] += pair_finish<PERMUTE>(y, q[j], ia, ib);
     }
 }
 
@@ -605,7 +618,8 @@ __global__ void __launch_bounds__(256, MINB) boot_rank_count_kernel(const BootPa
             int c[RPT];
 #pragma unroll
             for (int j = 0; j < RPT; ++j) c[j] = 0;
-            count_pairs<RPT>(P.y, d, rb.y, rb.x, rb.z, ra.y, ra.z, c);
+            if (P.permute) count_pairs<RPT, true>(P.y, d, rb.y, rb.x, rb.z, ra.y, ra.z, c);
+            else count_pairs<RPT, false>(P.y, d, rb.y, rb.x, rb.z, ra.y, ra.z, c);
 #pragma unroll
             for (int j = 0; j < RPT; ++j) cnt[j] += ra.w * c[j];
         }
@@ -646,32 +660,38 @@ __global__ void __launch_bounds__(256) boot_block_rows_kernel(const BootParams P
 #pragma unroll
     for (int j = 0; j < RPT; ++j) rows[j] = 0;
     if (b < P.n_blocks) {
-        const int32_t ts = __ldg(P.tile_start + b), width = __ldg(P.bait_width + b);
-        const int32_t seq_len = (int32_t)__ldg(P.seqlen + __ldg(P.tile_seq + b));
+        const int32_t width = __ldg(P.bait_width + b);
 #pragma unroll
         for (int j = 0; j < RPT; ++j) {
             if (r0 + j < P.n_iter) {
+                const int64_t flat = (r0 + j) * P.n_blocks + b;
                 int2 d;
                 if (P.rng_mode == NRB200_RNG_PHILOX) {
                     draw_block(P, (uint64_t)(P.iter0 + r0 + j), b, d.x, d.y);
                 } else {
-                    d.x = __ldg(P.bait_seq + (r0 + j) * P.n_blocks + b);
-                    d.y = __ldg(P.bait_start + (r0 + j) * P.n_blocks + b);
+                    d.x = __ldg(P.bait_seq + flat);
+                    d.y = __ldg(P.bait_start + flat);
                 }
-                if (P.draw_tab) P.draw_tab[(r0 + j) * P.n_blocks + b] = d;
+                // bootstrap kinds: block b lands on tile b; permute kinds: on the tile the caller drew
+                const int32_t t = P.dst_tile ? __ldg(P.dst_tile + flat) : (int32_t)b;
+                const int32_t ts = __ldg(P.tile_start + t);
+                const int32_t seq_len = (int32_t)__ldg(P.seqlen + __ldg(P.tile_seq + t));
+                if (P.draw_tab) P.draw_tab[(r0 + j) * P.n_blocks + t] = d;  // the count kernel looks draws up by tile
                 const int4 si = __ldg(P.y.seq_info + d.x);
                 const int32_t ie = idx_start_le(P.y, si, d.y + (width - 1));
-                const int hits = ie - idx_end_lt(P.y, si, d.y);
+                // hits: overlap of the bait block (bootstrap) / start inside the tile (permute)
+                const int hits = ie - (P.permute ? idx_start_le(P.y, si, d.y - 1) : idx_end_lt(P.y, si, d.y));
                 int dropped = 0;  // only a tile that overhangs its sequence end can push hits beyond it
                 if (P.drop_zero && ts + (width - 1) > seq_len) dropped = max(0, ie - idx_start_le(P.y, si, seq_len - (ts - d.y)));
                 rows[j] = P.rows_windows_only ? 0 : hits - dropped;
-                if (X.off) {  // minus the hits that overlap an exclude region after the move
-                    const int32_t x1 = __ldg(X.off + b + 1);
-                    for (int32_t k = __ldg(X.off + b); k < x1; ++k) {
+                if (X.off) {  // minus the hits that overlap an exclude region after the move ("trim": plus the pieces)
+                    const int32_t x1 = __ldg(X.off + t + 1);
+                    for (int32_t k = __ldg(X.off + t); k < x1; ++k) {
                         const int4 w = __ldg(X.rec + k);
                         const int2 dd[1] = {d};
                         int c1[1] = {0};
-                        count_pairs<1>(P.y, dd, width, ts, seq_len, w.x, w.y, c1);
+                        if (P.permute) count_pairs<1, true>(P.y, dd, width, ts, seq_len, w.x, w.y, c1);
+                        else count_pairs<1, false>(P.y, dd, width, ts, seq_len, w.x, w.y, c1);
                         rows[j] += w.z * c1[0];
                     }
                 }
