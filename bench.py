@@ -266,6 +266,7 @@ def run_gpu(args):
             count_ms += st["count_kernel_ms"]
             hits += st["n_hits"]
             launches += st["n_launches"]
+            n_windows = st["n_windows"]
         clk = clocks.stop()
         clk["window"] = "warm-up + timed region + accounting pass (the timed region alone lasts a few ms)"
 
@@ -371,6 +372,10 @@ def run_gpu(args):
                          "note": "bytes = SURVEY 8d model (8*H + 16*B + 4*G + 16 per iteration, H = sampled ranges). The rank path counts by "
                                  "rank differences and never reads the H ranges, so it legitimately exceeds 1.0 on this scale (SURVEY 8d); "
                                  "its own limit is L1TEX wavefronts of scattered table probes, see DESIGN.md 4a. roofline_stream is the kernel that does read them."},
+            "roofline_own": {"bound": "l1tex wavefronts (scattered 128-byte-line accesses), not HBM",
+                             "evaluations_per_launch": n_windows * R, "windows_per_iteration": n_windows,
+                             "sm_cycles_per_evaluation": (count_ms / groups) * 1e-3 * 148 * (clk.get("sm_mhz") or 1965) * 1e6 / max(n_windows * R, 1),
+                             "floor": "2 rank-table probes per evaluation = 2 line accesses at ~1 line/cycle/SM; measured ~3.4 accesses per evaluation (ncu l1tex sectors), see DESIGN.md 4a"},
             "roofline_stream": {"bound": "hbm", "kernel": "boot_count_kernel<0,1,0> (NRB200_FLAG_FORCE_STREAM, same workload)",
                                 "achieved": stream_achieved, "peak": peak, "unit": "GB/s", "frac": stream_achieved / peak,
                                 "kernel_ms_per_launch": stream_ms / stream_steps, "iters_per_s": R * stream_steps / (stream_ms * 1e-3)},

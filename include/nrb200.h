@@ -150,6 +150,7 @@ typedef struct nrb200_stats {
     int64_t d2h_bytes;
     double rows_kernel_ms;  /* rank path: boot_block_rows_kernel (draws + rows per block) */
     double count_kernel_ms; /* rank path: boot_rank_count_kernel; streaming path: boot_count_kernel */
+    int64_t n_windows;      /* rank path: signed windows evaluated per iteration (0 on the streaming path) */
 } nrb200_stats;
 
 /* ---- fused path: bootstrap -> countOverlaps, the R x N table is never built -------- */

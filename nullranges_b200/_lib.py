@@ -37,7 +37,7 @@ class Draws(C.Structure):
 class Stats(C.Structure):
     _fields_ = [("kernel_ms", C.c_double), ("total_ms", C.c_double), ("n_launches", C.c_int64),
                 ("n_hits", C.c_int64), ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64),
-                ("rows_kernel_ms", C.c_double), ("count_kernel_ms", C.c_double)]
+                ("rows_kernel_ms", C.c_double), ("count_kernel_ms", C.c_double), ("n_windows", C.c_int64)]
 
     def as_dict(self) -> dict:
         return {k: getattr(self, k) for k, _ in self._fields_}

@@ -903,6 +903,7 @@ int run_counts_core(nrb200_handle *h, const nrb200_draws *d, bool want_counts, i
         stats->n_launches = launches;
         stats->n_hits = (int64_t)hits;
         if (split) {
+            stats->n_windows = has_query ? h->n_pairs : 0;
             for (int b = 0; b < k; ++b) {
                 float a_ms = 0, b_ms = 0;
                 cudaEventElapsedTime(&a_ms, h->batch_ev[3 * b], h->batch_ev[3 * b + 1]);

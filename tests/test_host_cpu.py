@@ -118,3 +118,26 @@ def test_set_seed_stream_is_shared_across_calls():
     a = global_rng().runif(2)
     b = global_rng().runif(2)
     assert np.array_equal(np.concatenate([a, b]), O.RRng(5).runif(4))
+
+
+def test_r_shim_type_checks_against_the_header():
+    """r-package/src/r_shim.c cannot be built here (no R); it is at least compiled (-fsyntax-only) against
+    include/nrb200.h with declaration-only stand-ins of the R C API, so signature drift is caught."""
+    import subprocess
+    res = subprocess.run(["gcc", "-fsyntax-only", "-Wall", "-Wextra", "-Werror", "-Wno-cast-function-type",
+                          "-I", os.path.join(ROOT, "tests", "r_stubs"), "-I", os.path.join(ROOT, "include"),
+                          os.path.join(ROOT, "r-package", "src", "r_shim.c")], capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr
+    # every .Call used by the R wrapper is registered by the shim with the right number of arguments
+    wrapper = open(os.path.join(ROOT, "r-package", "R", "bootRanges_b200.R")).read()
+    shim = open(os.path.join(ROOT, "r-package", "src", "r_shim.c")).read()
+    registered = {m.group(1): int(m.group(2)) for m in re.finditer(r'\{"(nrb200_R_\w+)", \(DL_FUNC\)&\w+, (\d+)\}', shim)}
+    for m in re.finditer(r'\.Call\("(nrb200_R_\w+)"((?:[^()]|\([^()]*(?:\([^()]*\)[^()]*)*\))*)\)', wrapper):
+        name, args = m.group(1), m.group(2)
+        depth, n = 0, 0
+        for ch in args:
+            depth += ch in "([" 
+            depth -= ch in ")]"
+            n += (ch == "," and depth == 0)
+        assert name in registered, name
+        assert registered[name] == n, f"{name}: wrapper passes {n} arguments, shim registers {registered[name]}"
