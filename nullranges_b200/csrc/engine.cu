@@ -212,7 +212,7 @@ int range_set_to_device(nrb200_handle *h, RangeSet &rs) {
 
 int load_range_set(nrb200_handle *h, RangeSet &rs, const char *what, int64_t n, const int32_t *seqid,
                    const int32_t *start, const int32_t *end, const int8_t *strand, bool keep_seqid_dev,
-                   bool defer_device = false) {
+                   bool defer_device = false, int32_t widen = 0) {
     if (n < 0 || n > (int64_t)INT32_MAX - 64) return fail(h, NRB200_ERR_INVALID, std::string(what) + ": length out of range");
     if (n > 0 && (!seqid || !start || !end)) return fail(h, NRB200_ERR_INVALID, std::string(what) + ": null coordinate pointer");
     const int C = h->n_seq;
@@ -255,8 +255,8 @@ int load_range_set(nrb200_handle *h, RangeSet &rs, const char *what, int64_t n, 
     std::vector<int32_t> h_seqid(keep_seqid_dev ? n : 0);
     for (int64_t k = 0; k < n; ++k) {
         const int32_t i = rs.h_src[k];
-        rs.h_start[k] = start[i];
-        rs.h_end[k] = end[i];
+        rs.h_start[k] = start[i] - widen;  // widen > 0: query with maxgap (see nrb200_set_query_ex)
+        rs.h_end[k] = end[i] + widen;
         if (stranded) rs.h_strand[k] = strand[i];
         if (keep_seqid_dev) h_seqid[k] = seqid[i];
         rs.h_seq_off[seqid[i] + 1]++;
@@ -1028,7 +1028,7 @@ int nrb200_ranges_info(const nrb200_handle *h, int32_t *is_sorted, int32_t *is_s
 }
 
 static int set_side(nrb200_handle *h, RangeSet &rs, const char *what, int64_t n, const int32_t *seqid,
-                    const int32_t *start, const int32_t *end, const int8_t *strand) {
+                    const int32_t *start, const int32_t *end, const int8_t *strand, int32_t widen = 0) {
     if (!h) return NRB200_ERR_INVALID;
     NRB_CUDA(h, cudaSetDevice(h->device));
     if (!h->have_y) return fail(h, NRB200_ERR_STATE, "call nrb200_set_ranges() first (it defines the seqlevels)");
@@ -1037,12 +1037,25 @@ static int set_side(nrb200_handle *h, RangeSet &rs, const char *what, int64_t n,
         rs.n = 0;
         return NRB200_OK;
     }
-    return load_range_set(h, rs, what, n, seqid, start, end, strand, false, &rs == &h->query);
+    return load_range_set(h, rs, what, n, seqid, start, end, strand, false, &rs == &h->query, widen);
 }
 
 int nrb200_set_query(nrb200_handle *h, int64_t n, const int32_t *seqid, const int32_t *start, const int32_t *end,
                      const int8_t *strand) {
     return set_side(h, h->query, "query", n, seqid, start, end, strand);
+}
+
+// maxgap: two ranges count as overlapping when at most `maxgap` positions separate them
+// (start_q <= end_s + maxgap + 1 and end_q >= start_s - maxgap - 1).  That is plain overlap with every
+// feature widened by maxgap + 1 on both sides, which is how the query is stored; nothing downstream
+// changes.  (Bootstrapped ranges lie inside [1, seqlength], so the widening cannot create overlaps
+// that trim() would have removed.)
+int nrb200_set_query_ex(nrb200_handle *h, int64_t n, const int32_t *seqid, const int32_t *start, const int32_t *end,
+                        const int8_t *strand, int32_t maxgap) {
+    if (!h) return NRB200_ERR_INVALID;
+    if (maxgap < -1) return fail(h, NRB200_ERR_INVALID, "'maxgap' must be >= -1");
+    if (maxgap >= (1 << 29)) return fail(h, NRB200_ERR_UNSUPPORTED, "'maxgap' must be below 2^29");
+    return set_side(h, h->query, "query", n, seqid, start, end, strand, maxgap + 1);
 }
 
 int nrb200_set_exclude(nrb200_handle *h, int64_t n, const int32_t *seqid, const int32_t *start, const int32_t *end,

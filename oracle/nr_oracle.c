@@ -719,6 +719,7 @@ typedef struct orc_index {
     int32_t *pmax;        /* running max of end along ord within chrom */
     int32_t *wmax;        /* [C] largest width */
     int ord_is_identity;
+    int64_t slack;        /* as a countOverlaps() query: maxgap + 1 (0 = plain overlap, maxgap = -1) */
 } orc_index;
 
 static const orc_index *g_sort_ix;
@@ -774,6 +775,11 @@ ORC_API orc_index *orc_index_new(int64_t n, int C, const int32_t *chrom, const i
     return ix;
 }
 
+/* countOverlaps(x, boots, maxgap = m) (vignettes/bootRanges.Rmd:532-540 uses maxgap = 1e3): two ranges
+ * count as overlapping when the gap between them is <= m (adjacent ranges have gap 0; overlapping
+ * ranges -1), i.e. start_q <= end_s + m + 1 and end_q >= start_s - m - 1. */
+ORC_API void orc_index_set_maxgap(orc_index *ix, int64_t maxgap) { ix->slack = maxgap < -1 ? 0 : maxgap + 1; }
+
 /* #{k in [lo,hi) : start[ord[k]] <= x} + lo */
 static int64_t upper_start(const orc_index *ix, int64_t lo, int64_t hi, int64_t x) {
     while (lo < hi) {
@@ -808,11 +814,12 @@ static int64_t count_into(const orc_index *q, int c, int64_t s, int64_t e, int s
                           int32_t *counts) {
     if (!q || e < s) return 0;
     int64_t n = 0;
-    int64_t lo = q->off[c], hi = upper_start(q, q->off[c], q->off[c + 1], e);
+    const int64_t m1 = q->slack;
+    int64_t lo = q->off[c], hi = upper_start(q, q->off[c], q->off[c + 1], e + m1);
     for (int64_t k = hi - 1; k >= lo; k--) {
-        if ((int64_t)q->pmax[k] < s) break;
+        if ((int64_t)q->pmax[k] < s - m1) break;
         int32_t id = q->ord[k];
-        if ((int64_t)q->end[id] >= s &&
+        if ((int64_t)q->end[id] >= s - m1 &&
             strand_compatible(strand, q->strand ? q->strand[id] : 0)) {
             n++;
             if (counts) counts[id]++;

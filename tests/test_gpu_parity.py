@@ -306,3 +306,16 @@ def test_cfg2_validation_mode_R1000(engine):
     ref = O.boot_counts(plan, yi, qi, R, draws=d, nthreads=O.max_threads())
     for k in ("iter_nranges", "iter_totals", "feature_counts"):
         assert np.array_equal(got[k], ref[k]), k
+
+
+@pytest.mark.parametrize("kind", [0, 1, 2, 4, 5])
+@pytest.mark.parametrize("maxgap", [0, 75])
+def test_maxgap(engine, kind, maxgap):
+    """countOverlaps(x, boots, maxgap = m): features within m positions of a bootstrapped range count."""
+    case = H.random_case(seed=400 + kind, n=700, n_seq=3, n_query=90, n_excl=12 if kind == 2 else 0, stranded=kind == 1, n_seg=9,
+                         n_states=2, wmax=60)
+    case["maxgap"] = maxgap
+    got, ref = _check_counts(engine, case, kind, R=5, seed=6, philox=False)
+    case["maxgap"] = -1
+    _, plain = _check_counts(engine, case, kind, R=5, seed=6, philox=False)
+    assert ref["iter_totals"].sum() > plain["iter_totals"].sum()   # the gap really adds overlaps

@@ -117,3 +117,17 @@ def test_fused_counts_equal_two_step_workflow():
             assert np.array_equal(cnt, fused["feature_counts"][r]) and tot == fused["iter_totals"][r]
             assert np.array_equal(H.brute_counts(case, (rows["chrom"], rows["start"], rows["end"], strand)), cnt)
             assert rows["src"].size == fused["iter_nranges"][r]
+
+
+def test_maxgap_matches_gap_definition():
+    """Oracle countOverlaps(maxgap = m) vs the definition: gap(a, b) = positions between them (adjacent: 0,
+    overlapping: -1); overlap iff gap <= m."""
+    rng = np.random.default_rng(3)
+    qs = rng.integers(1, 900, 40); qe = qs + rng.integers(0, 30, 40)
+    rs = rng.integers(1, 900, 200); re_ = rs + rng.integers(0, 30, 200)
+    for m in (-1, 0, 1, 25):
+        q = O.Index(1, np.zeros(40, np.int32), qs, qe, maxgap=m)
+        cnt, tot = O.count_overlaps(q, np.zeros(200, np.int32), rs, re_)
+        gap = np.maximum(qs[:, None] - re_[None, :], rs[None, :] - qe[:, None]) - 1
+        want = (np.maximum(gap, -1) <= m).sum(axis=1)
+        assert np.array_equal(cnt, want) and tot == want.sum()
