@@ -169,7 +169,9 @@ def bootCounts(y: GRanges, x: GRanges, blockLength, R: int = 1, seg: GRanges | N
         raise ValueError("out= needs every seqlevel of x to be a seqlevel of y")
     res = eng.run_counts(draws, want_counts=perFeature, out=out)
     fc = res["feature_counts"]
-    if fc is not None and qkeep.size != len(x):  # features on sequences y lacks count 0
+    if fc is None and perFeature:  # no feature lies on a sequence of y
+        fc = np.zeros((int(R), len(x)), np.int32)
+    elif fc is not None and qkeep.size != len(x):  # features on sequences y lacks count 0
         full = np.zeros((int(R), len(x)), np.int32)
         full[:, qkeep] = fc
         fc = full

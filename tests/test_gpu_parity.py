@@ -319,3 +319,42 @@ def test_maxgap(engine, kind, maxgap):
     case["maxgap"] = -1
     _, plain = _check_counts(engine, case, kind, R=5, seed=6, philox=False)
     assert ref["iter_totals"].sum() > plain["iter_totals"].sum()   # the gap really adds overlaps
+
+
+def test_error_behaviour(engine):
+    """The reference's stopifnot()s and the ABI's state checks come back as error codes with the reference's wording."""
+    from nullranges_b200 import EngineError, GRanges, bootRanges, bootCounts
+    L = np.array([1000, 800], np.int64)
+    sid, st, en = np.array([0, 0, 1], np.int32), np.array([5, 50, 7], np.int32), np.array([9, 60, 20], np.int32)
+    with pytest.raises(EngineError, match="is.na"):          # stopifnot(all(!is.na(chr_lens)))  R/bootRanges.R:81
+        engine.set_ranges(np.array([1000, -1]), sid, st, en)
+    engine.set_ranges(L, sid, st, en)
+    with pytest.raises(EngineError, match="chrom_lens >= L_b"):   # R/bootUnsegmented.R:8
+        engine.set_plan(_lib.UNSEG_ACROSS, 900)
+    with pytest.raises(EngineError, match="blockLength"):
+        engine.set_plan(_lib.UNSEG_ACROSS, 0)
+    with pytest.raises(EngineError, match="state"):
+        engine.set_plan(_lib.SEG_PROP, 100, {"seqid": [0], "start": [1], "end": [1000], "state": [0]})
+    with pytest.raises(EngineError, match="seqlevels"):
+        engine.set_query(np.array([2], np.int32), np.array([1], np.int32), np.array([5], np.int32))
+    with pytest.raises(EngineError, match="maxgap"):
+        engine.set_query(np.array([0], np.int32), np.array([1], np.int32), np.array([5], np.int32), maxgap=-2)
+    engine.set_plan(_lib.UNSEG_ACROSS, 100)
+    with pytest.raises(EngineError, match="out of range"):     # host draws are validated before they reach the device
+        engine.run_counts(Draws(n_iter=1, rng_mode=_lib.RNG_HOST, bait_seqid=np.full((1, 18), 5, np.int32), bait_start=np.ones((1, 18), np.int32)))
+    engine.set_plan(_lib.PERMUTE_ACROSS, 100)
+    with pytest.raises(EngineError, match="host"):             # no device draws for the permutation variants
+        engine.run_counts(Draws(n_iter=1, rng_mode=_lib.RNG_PHILOX, seed=1))
+    with pytest.raises(EngineError, match="dst_tile"):
+        engine.run_counts(Draws(n_iter=1, rng_mode=_lib.RNG_HOST, bait_seqid=np.zeros((1, 18), np.int32), bait_start=np.ones((1, 18), np.int32)))
+    # front end: the reference's own checks
+    y = GRanges(["b", "a"], [5, 3], width=[2, 2], seqlengths={"a": 50, "b": 50}, seqlevels=["a", "b"])
+    with pytest.raises(ValueError, match="sort"):              # all(y == GenomicRanges::sort(y))  R/bootUnsegmented.R:31
+        bootRanges(y, 10)
+    assert len(bootRanges(y, 10, withinChrom=True, seed=1)) >= 0   # within-chromosome accepts any order (:15-28)
+    with pytest.raises(ValueError, match="should be one of"):
+        bootRanges(y.sort(), 10, type="jackknife")
+    with pytest.raises(ValueError, match="integer"):
+        bootRanges(y.sort(), 10.5)
+    empty = bootCounts(y.sort(), GRanges(["zz"], [1], width=[5], seqlevels=["zz"], seqlengths=[9]), 10, R=3, seed=1)
+    assert empty.feature_counts.shape == (3, 1) and empty.feature_counts.sum() == 0   # features on unknown sequences count 0
