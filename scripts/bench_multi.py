@@ -1,0 +1,110 @@
+"""BASELINE configs 4 and 5 on N GPUs of one box (torchrun, one process per GPU, NCCL).
+
+  cfg 4: 10M points, withinChrom=TRUE, 200k enhancers, R = 10^4 iterations sharded over the ranks;
+         per-feature moments (sum, sum^2, #>=observed) all-reduced, per-iteration totals all-gathered.
+  cfg 5: blockLength in {1e5, 2e5, 5e5, 1e6} x R = 1000 on 1M ranges: the four block lengths are spread
+         over the ranks (rank k takes L_b[k % 4] and 1/ceil(N/4) of its iterations); variance of the
+         per-iteration totals per block length (the vignette's variance-vs-L_b diagnostic).
+
+usage: python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 scripts/bench_multi.py --config 4
+"""
+import argparse, json, os, sys, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import torch
+import torch.distributed as dist
+from nullranges_b200 import Draws, Engine, _lib, synth
+from nullranges_b200.sharding import gather_iteration_vectors, shard_iterations
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--config", type=int, default=4)
+ap.add_argument("--iters", type=int, default=0)
+args = ap.parse_args()
+world, rank, local = int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0))
+torch.cuda.set_device(local)
+if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+    os.environ["NCCL_DEBUG"] = "WARN"
+if world > 1:
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+dev = torch.device("cuda", local)
+eng = Engine(local)
+
+
+def barrier():
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+
+
+if args.config == 4:
+    R = args.iters or 10_000
+    y, x = synth.points(10_000_000, seed=6), synth.enhancers(200_000, seed=7)
+    eng.set_ranges(y.seqlengths, y.seqid, y.start, y.end)
+    eng.set_query(x.seqid, x.start, x.end)
+    B = eng.set_plan(_lib.UNSEG_WITHIN, 500_000)
+    obs, obs_total = eng.count_observed()
+    iter0, n = shard_iterations(R, world, rank)
+    eng.run_moments(Draws(n_iter=min(n, 64), seed=7, iter0=iter0), observed=obs)  # warm-up
+    barrier()
+    t0 = time.perf_counter()
+    m = eng.run_moments(Draws(n_iter=n, seed=7, iter0=iter0), observed=obs)
+    mom = torch.from_numpy(np.stack([m["sum"], m["sumsq"], m["n_ge_observed"]])).to(dev)
+    if world > 1:
+        dist.all_reduce(mom)                                   # 3 x G x 8 bytes over NVLink
+        tot = gather_iteration_vectors({"iter_totals": m["iter_totals"], "iter_nranges": m["iter_nranges"]}, R, device=dev)
+    else:
+        tot = {"iter_totals": m["iter_totals"], "iter_nranges": m["iter_nranges"]}
+    barrier()
+    dt = time.perf_counter() - t0
+    t = torch.tensor([dt, m["stats"]["kernel_ms"]], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    mom = mom.cpu().numpy()
+    if rank == 0:
+        mean = mom[0] / R
+        var = mom[1] / R - mean ** 2
+        z = (obs - mean) / np.sqrt(np.maximum(var, 1e-12))
+        print(json.dumps({"config": "cfg4 10M points withinChrom vs 200k enhancers, per-feature moments", "n_gpus": world, "iters": R,
+                          "wall_s": float(t[0]), "iters_per_s": R / float(t[0]), "max_rank_kernel_ms": float(t[1]),
+                          "observed_total": int(obs_total), "bootstrap_mean_total": float(tot["iter_totals"].mean()),
+                          "bootstrap_sd_total": float(tot["iter_totals"].std(ddof=1)),
+                          "moments_checksum": [int(mom[0].sum()), int(mom[1].sum()), int(mom[2].sum())],
+                          "max_abs_feature_z": float(np.abs(z).max()), "blocks": int(B)}))
+else:
+    R = args.iters or 1000
+    y, x = synth.atac_peaks(1_000_000, seed=3), synth.genes(20_000, seed=2)
+    eng.set_ranges(y.seqlengths, y.seqid, y.start, y.end)
+    eng.set_query(x.seqid, x.start, x.end)
+    LBS = [100_000, 200_000, 500_000, 1_000_000]
+    per = max(1, world // 4)                                   # ranks sharing one block length
+    mine = [LBS[rank % 4]] if world >= 4 else LBS[rank::world]
+    res = {}
+    barrier()
+    t0 = time.perf_counter()
+    for Lb in mine:
+        eng.set_plan(_lib.UNSEG_ACROSS, Lb)
+        sub = (rank // 4) if world >= 4 else 0
+        iter0, n = shard_iterations(R, per, sub)
+        r = eng.run_counts(Draws(n_iter=n, seed=5, iter0=iter0), want_counts=False)
+        res[Lb] = (iter0, r["iter_totals"])
+    barrier()
+    dt = time.perf_counter() - t0
+    # gather every (L_b, slice) on rank 0
+    payload = [None] * world
+    if world > 1:
+        dist.all_gather_object(payload, res)
+    else:
+        payload = [res]
+    if rank == 0:
+        out = {}
+        for Lb in LBS:
+            parts = sorted((p[Lb] for p in payload if Lb in p), key=lambda a: a[0])
+            tot = np.concatenate([a[1] for a in parts])
+            assert tot.size == R
+            out[str(Lb)] = {"mean_total": float(tot.mean()), "var_total": float(tot.var(ddof=1))}
+        print(json.dumps({"config": "cfg5 blockLength sweep x R=1000 on 1M ranges", "n_gpus": world, "wall_s": dt,
+                          "iters_per_s": 4 * R / dt, "by_block_length": out}))
+if world > 1:
+    dist.barrier()
+    dist.destroy_process_group()
+eng.close()
