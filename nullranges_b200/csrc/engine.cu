@@ -113,6 +113,9 @@ struct nrb200_handle {
     int rank_shift = 0;
     std::vector<int64_t> rank_off;
     DevMem inspect_dev, seq_info_dev, draw_tab;
+    // stranded y only: class-major copy for the rank path (kernels.cuh, RangesView)
+    int n_cls = 1;
+    DevMem r_start, r_end, r_pmax, r_order, r_idx, r_keys_a, r_keys_b, r_voff_dev, rseq_info_dev, rrank_off_dev, rrank_start;
     DevMem rank_off_dev, max_pos_dev, rank_start, rank_pmax, rank_end, end_sorted, sort_keys_a, sort_keys_b, sort_tmp;
     uint32_t flags = 0;
     // tuning knobs (environment, read at create): NRB200_RPT iterations per thread of the rank count
@@ -357,12 +360,13 @@ int build_rank_tables(nrb200_handle *h) {
     h->rank_off.assign(C + 1, 0);
     for (int c = 0; c < C; ++c) h->rank_off[c + 1] = h->rank_off[c] + ((int64_t)max_pos[c] >> shift) + 3;  // +1: probes read entry u + 1
     const int64_t entries = h->rank_off[C];
+    h->n_cls = y.stranded ? 3 : 1;
+    if (entries * h->n_cls > (int64_t)INT32_MAX) return fail(h, NRB200_ERR_UNSUPPORTED, "rank tables exceed 2^31 entries");
+    for (int c = 0; c < C; ++c)  // packed table entries hold a per-sequence index in 29 bits
+        if (y.h_seq_off[c + 1] - y.h_seq_off[c] >= (1 << 29)) return fail(h, NRB200_ERR_UNSUPPORTED, "more than 2^29 ranges on one sequence");
     int rc;
     if ((rc = upload(h, h->rank_off_dev, h->rank_off.data(), (size_t)C + 1))) return rc;
     if ((rc = upload(h, h->max_pos_dev, max_pos.data(), (size_t)C))) return rc;
-    if (entries > (int64_t)INT32_MAX) return fail(h, NRB200_ERR_UNSUPPORTED, "rank tables exceed 2^31 entries");
-    for (int c = 0; c < C; ++c)  // packed table entries hold a per-sequence index in 29 bits
-        if (y.h_seq_off[c + 1] - y.h_seq_off[c] >= (1 << 29)) return fail(h, NRB200_ERR_UNSUPPORTED, "more than 2^29 ranges on one sequence");
     std::vector<int32_t> seq_info(4 * (size_t)C);
     for (int c = 0; c < C; ++c) {
         seq_info[4 * c + 0] = y.h_seq_off[c];
@@ -373,32 +377,85 @@ int build_rank_tables(nrb200_handle *h) {
     if ((rc = upload(h, h->seq_info_dev, seq_info.data(), seq_info.size()))) return rc;
     NRB_CUDA(h, h->rank_start.reserve(entries * sizeof(int32_t)));
     NRB_CUDA(h, h->rank_pmax.reserve(entries * sizeof(int32_t)));
-    NRB_CUDA(h, h->rank_end.reserve(entries * sizeof(int32_t)));
-    // ends in ascending order within each sequence: radix sort of (seqid << 32 | end)
     NRB_CUDA(h, h->end_sorted.reserve(std::max<int64_t>(y.n, 1) * sizeof(int32_t)));
-    if (y.n > 0) {
-        int seq_bits = 1;
-        while ((1 << seq_bits) < C) ++seq_bits;
-        NRB_CUDA(h, h->sort_keys_a.reserve(y.n * 8));
-        NRB_CUDA(h, h->sort_keys_b.reserve(y.n * 8));
-        const unsigned g = (unsigned)((y.n + 255) / 256);
-        pack_end_keys_kernel<<<g, 256, 0, h->stream>>>(y.seqid.as<int32_t>(), y.end.as<int32_t>(), y.n,
-                                                       h->sort_keys_a.as<unsigned long long>());
+    const int threads = 256;
+    const unsigned n_grid = (unsigned)((std::max<int64_t>(y.n, 1) + threads - 1) / threads);
+    const unsigned t_grid = (unsigned)((entries + threads - 1) / threads);
+    // canonical start table: locate_block() of the streaming kernels, and the rank path of an unstranded y
+    build_rank_table_kernel<<<t_grid, threads, 0, h->stream>>>(y.start.as<int32_t>(), y.seq_off.as<int32_t>(),
+                                                               h->rank_off_dev.as<int64_t>(), C, shift, h->rank_start.as<uint32_t>());
+    h->have_pmax_table = false;  // only the streaming kernels need it: built on first use
+    NRB_CUDA(h, h->sort_keys_a.reserve(std::max<int64_t>(y.n, 1) * 8));
+    NRB_CUDA(h, h->sort_keys_b.reserve(std::max<int64_t>(y.n, 1) * 8));
+    auto sort_u64 = [&](int bits) -> int {  // sort_keys_a -> sort_keys_b
         size_t tmp_bytes = 0;
         NRB_CUDA(h, cub::DeviceRadixSort::SortKeys(nullptr, tmp_bytes, h->sort_keys_a.as<unsigned long long>(),
-                                                   h->sort_keys_b.as<unsigned long long>(), y.n, 0, 32 + seq_bits, h->stream));
+                                                   h->sort_keys_b.as<unsigned long long>(), y.n, 0, bits, h->stream));
         NRB_CUDA(h, h->sort_tmp.reserve(tmp_bytes));
         NRB_CUDA(h, cub::DeviceRadixSort::SortKeys(h->sort_tmp.p, tmp_bytes, h->sort_keys_a.as<unsigned long long>(),
-                                                   h->sort_keys_b.as<unsigned long long>(), y.n, 0, 32 + seq_bits, h->stream));
-        unpack_end_keys_kernel<<<g, 256, 0, h->stream>>>(h->sort_keys_b.as<unsigned long long>(), y.n, h->end_sorted.as<int32_t>());
+                                                   h->sort_keys_b.as<unsigned long long>(), y.n, 0, bits, h->stream));
+        return NRB200_OK;
+    };
+    if (!y.stranded) {
+        // ends in ascending order within each sequence: radix sort of (seqid << 32 | end)
+        NRB_CUDA(h, h->rank_end.reserve(entries * sizeof(int32_t)));
+        if (y.n > 0) {
+            int seq_bits = 1;
+            while ((1 << seq_bits) < C) ++seq_bits;
+            pack_end_keys_kernel<<<n_grid, threads, 0, h->stream>>>(y.seqid.as<int32_t>(), y.end.as<int32_t>(), y.n,
+                                                                    h->sort_keys_a.as<unsigned long long>());
+            if ((rc = sort_u64(32 + seq_bits))) return rc;
+            unpack_end_keys_kernel<<<n_grid, threads, 0, h->stream>>>(h->sort_keys_b.as<unsigned long long>(), y.n, h->end_sorted.as<int32_t>());
+        }
+        build_rank_table_kernel<<<t_grid, threads, 0, h->stream>>>(h->end_sorted.as<int32_t>(), y.seq_off.as<int32_t>(),
+                                                                   h->rank_off_dev.as<int64_t>(), C, shift, h->rank_end.as<uint32_t>());
+        NRB_CUDA(h, cudaGetLastError());
+        return NRB200_OK;
     }
-    const int threads = 256;
-    const unsigned grid = (unsigned)((entries + threads - 1) / threads);
-    build_rank_table_kernel<<<grid, threads, 0, h->stream>>>(y.start.as<int32_t>(), y.seq_off.as<int32_t>(),
-                                                             h->rank_off_dev.as<int64_t>(), C, shift, h->rank_start.as<uint32_t>());
-    h->have_pmax_table = false;  // only the streaming kernels need it: built on first use
-    build_rank_table_kernel<<<grid, threads, 0, h->stream>>>(h->end_sorted.as<int32_t>(), y.seq_off.as<int32_t>(),
-                                                             h->rank_off_dev.as<int64_t>(), C, shift, h->rank_end.as<uint32_t>());
+    // ---- stranded y: a second copy grouped by strand class inside each sequence (virtual sequences)
+    const int V = 3 * C;
+    std::vector<int64_t> roff(V + 1, 0);
+    for (int v = 0; v < V; ++v) roff[v + 1] = roff[v] + ((int64_t)max_pos[v / 3] >> shift) + 3;
+    const int64_t r_entries = roff[V];
+    if ((rc = upload(h, h->rrank_off_dev, roff.data(), (size_t)V + 1))) return rc;
+    for (DevMem *m : {&h->r_start, &h->r_end, &h->r_pmax, &h->r_order, &h->r_idx, &h->r_keys_a, &h->r_keys_b})
+        NRB_CUDA(h, m->reserve(std::max<int64_t>(y.n, 1) * 4));
+    NRB_CUDA(h, h->r_voff_dev.reserve(((size_t)V + 1) * 4));
+    NRB_CUDA(h, h->rseq_info_dev.reserve((size_t)V * sizeof(int4)));
+    NRB_CUDA(h, h->rrank_start.reserve(r_entries * sizeof(int32_t)));
+    NRB_CUDA(h, h->rank_end.reserve(r_entries * sizeof(int32_t)));
+    int v_bits = 1;
+    while ((1 << v_bits) < V) ++v_bits;
+    if (y.n > 0) {
+        vseq_keys_kernel<<<n_grid, threads, 0, h->stream>>>(y.seqid.as<int32_t>(), y.strand.as<int8_t>(), y.n,
+                                                            h->r_keys_a.as<unsigned>(), h->r_idx.as<int32_t>());
+        size_t tmp_bytes = 0;  // stable: inside a virtual sequence the canonical (start, end) order survives
+        NRB_CUDA(h, cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, h->r_keys_a.as<unsigned>(), h->r_keys_b.as<unsigned>(),
+                                                    h->r_idx.as<int32_t>(), h->r_order.as<int32_t>(), y.n, 0, v_bits, h->stream));
+        NRB_CUDA(h, h->sort_tmp.reserve(tmp_bytes));
+        NRB_CUDA(h, cub::DeviceRadixSort::SortPairs(h->sort_tmp.p, tmp_bytes, h->r_keys_a.as<unsigned>(), h->r_keys_b.as<unsigned>(),
+                                                    h->r_idx.as<int32_t>(), h->r_order.as<int32_t>(), y.n, 0, v_bits, h->stream));
+        gather_by_order_kernel<<<n_grid, threads, 0, h->stream>>>(h->r_order.as<int32_t>(), y.start.as<int32_t>(), y.end.as<int32_t>(), y.n,
+                                                                  h->r_start.as<int32_t>(), h->r_end.as<int32_t>());
+        tmp_bytes = 0;
+        NRB_CUDA(h, cub::DeviceScan::InclusiveScanByKey(nullptr, tmp_bytes, h->r_keys_b.as<unsigned>(), h->r_end.as<int32_t>(),
+                                                        h->r_pmax.as<int32_t>(), MaxOp(), y.n, cub::Equality(), h->stream));
+        NRB_CUDA(h, h->sort_tmp.reserve(tmp_bytes));
+        NRB_CUDA(h, cub::DeviceScan::InclusiveScanByKey(h->sort_tmp.p, tmp_bytes, h->r_keys_b.as<unsigned>(), h->r_end.as<int32_t>(),
+                                                        h->r_pmax.as<int32_t>(), MaxOp(), y.n, cub::Equality(), h->stream));
+        pack_vend_keys_kernel<<<n_grid, threads, 0, h->stream>>>(h->r_keys_b.as<unsigned>(), h->r_end.as<int32_t>(), y.n,
+                                                                 h->sort_keys_a.as<unsigned long long>());
+        if ((rc = sort_u64(32 + v_bits))) return rc;
+        unpack_end_keys_kernel<<<n_grid, threads, 0, h->stream>>>(h->sort_keys_b.as<unsigned long long>(), y.n, h->end_sorted.as<int32_t>());
+    }
+    vseq_info_kernel<<<(unsigned)((V + 1 + threads - 1) / threads), threads, 0, h->stream>>>(
+        h->r_keys_b.as<unsigned>(), y.n, V, h->max_pos_dev.as<int32_t>(), h->rrank_off_dev.as<int64_t>(), h->r_voff_dev.as<int32_t>(),
+        h->rseq_info_dev.as<int4>());
+    const unsigned rt_grid = (unsigned)((r_entries + threads - 1) / threads);
+    build_rank_table_kernel<<<rt_grid, threads, 0, h->stream>>>(h->r_start.as<int32_t>(), h->r_voff_dev.as<int32_t>(),
+                                                                h->rrank_off_dev.as<int64_t>(), V, shift, h->rrank_start.as<uint32_t>());
+    build_rank_table_kernel<<<rt_grid, threads, 0, h->stream>>>(h->end_sorted.as<int32_t>(), h->r_voff_dev.as<int32_t>(),
+                                                                h->rrank_off_dev.as<int64_t>(), V, shift, h->rank_end.as<uint32_t>());
     NRB_CUDA(h, cudaGetLastError());
     return NRB200_OK;
 }
@@ -440,12 +497,16 @@ struct Interval {
     int64_t s, e;
 };
 
-// reduce(): merged, sorted, disjoint (adjacent regions are joined: the union is what matters)
-static std::vector<std::vector<Interval>> merged_exclude(const nrb200_handle *h) {
+inline bool strands_compatible(int a, int b) { return a == 0 || b == 0 || a == b; }
+
+// reduce(): merged, sorted, disjoint (adjacent regions are joined: the union is what matters) -- of the
+// exclude ranges a y range of strand class `cls` can overlap ('*' y: all of them).
+static std::vector<std::vector<Interval>> merged_exclude(const nrb200_handle *h, int cls = 0) {
     const RangeSet &x = h->excl;
     std::vector<std::vector<Interval>> out(h->n_seq);
     for (int c = 0; c < h->n_seq; ++c) {
         for (int32_t k = x.h_seq_off[c]; k < x.h_seq_off[c + 1]; ++k) {  // canonical order: by start
+            if (x.stranded && !strands_compatible(cls, x.h_strand[k])) continue;
             const int64_t s = x.h_start[k], e = x.h_end[k];
             if (s > h->seqlen[c]) continue;  // nothing survives trim() out there
             if (!out[c].empty() && s <= out[c].back().e + 1) out[c].back().e = std::max(out[c].back().e, e);
@@ -490,44 +551,50 @@ int build_pairs(nrb200_handle *h) {
     const int64_t B = p.n_blocks(), G = q.n;
     const int64_t reach = std::max<int32_t>(h->y.wmax, 1) - 1;
     const bool has_excl = h->excl.n > 0, trim = trim_mode(h);
-    // "drop": the merged exclude regions; "trim": the gaps between them (already disjoint and sorted)
-    std::vector<std::vector<Interval>> X(C);
-    if (has_excl && !trim) X = merged_exclude(h);
-    if (trim)
-        for (int c = 0; c < C; ++c)
-            for (int32_t k = h->gaps.h_seq_off[c]; k < h->gaps.h_seq_off[c + 1]; ++k) X[c].push_back({h->gaps.h_start[k], h->gaps.h_end[k]});
+    const int n_cls = h->n_cls;
+    // Per strand class of y -- "drop": the merged exclude regions that class can overlap; "trim": the gaps
+    // (already disjoint and sorted, strand-free).
+    std::vector<std::vector<std::vector<Interval>>> XC(n_cls, std::vector<std::vector<Interval>>(C));
+    for (int cls = 0; cls < n_cls; ++cls) {
+        if (has_excl && !trim) XC[cls] = merged_exclude(h, cls);
+        if (trim)
+            for (int c = 0; c < C; ++c)
+                for (int32_t k = h->gaps.h_seq_off[c]; k < h->gaps.h_seq_off[c + 1]; ++k)
+                    XC[cls][c].push_back({h->gaps.h_start[k], h->gaps.h_end[k]});
+    }
 
     // exclude regions that intersect [lo, hi]: a contiguous run [first, last) of the merged list
-    auto x_run = [&](int c, int64_t lo, int64_t hi, size_t &first, size_t &last) {
-        const auto &v = X[c];
+    auto x_run = [&](const std::vector<Interval> &v, int64_t lo, int64_t hi, size_t &first, size_t &last) {
         first = std::lower_bound(v.begin(), v.end(), lo, [](const Interval &a, int64_t key) { return a.e < key; }) - v.begin();
         last = std::upper_bound(v.begin(), v.end(), hi, [](int64_t key, const Interval &a) { return key < a.s; }) - v.begin();
         if (last < first) last = first;
     };
 
-    // ---- per tile: exclusion windows for the row counts
-    std::vector<int32_t> x_off(B + 1, 0), x_rec;
+    // ---- per (tile, strand class): exclusion windows for the row counts
+    std::vector<int32_t> x_off((size_t)B * n_cls + 1, 0), x_rec;
     if (has_excl) {
         for (int64_t t = 0; t < B; ++t) {
             const int c = p.tile_seq[t];
             const int64_t ts = p.tile_start[t], te = ts + p.bait_width[t] - 1;
-            size_t f, l;
-            x_run(c, ts - reach, te + reach, f, l);
-            for (size_t k = f; k < l; ++k) {
-                if (trim) {  // rows = one per (range, gap) overlap
-                    x_rec.insert(x_rec.end(), {(int32_t)X[c][k].s, (int32_t)X[c][k].e, +1, 0});
-                    continue;
+            for (int cls = 0; cls < n_cls; ++cls) {
+                const auto &X = XC[cls][c];
+                size_t f, l;
+                x_run(X, ts - reach, te + reach, f, l);
+                for (size_t k = f; k < l; ++k) {
+                    if (trim) {  // rows = one per (range, gap) overlap
+                        x_rec.insert(x_rec.end(), {(int32_t)X[k].s, (int32_t)X[k].e, +1, 0});
+                        continue;
+                    }
+                    x_rec.insert(x_rec.end(), {(int32_t)X[k].s, (int32_t)std::min<int64_t>(X[k].e, INT32_MAX / 2), -1, 0});
+                    if (k + 1 < l && X[k + 1].s - X[k].e <= reach) x_rec.insert(x_rec.end(), {(int32_t)X[k + 1].s, (int32_t)X[k].e, +1, 0});
                 }
-                x_rec.insert(x_rec.end(), {(int32_t)X[c][k].s, (int32_t)std::min<int64_t>(X[c][k].e, INT32_MAX / 2), -1, 0});
-                if (k + 1 < l && X[c][k + 1].s - X[c][k].e <= reach)
-                    x_rec.insert(x_rec.end(), {(int32_t)X[c][k + 1].s, (int32_t)X[c][k].e, +1, 0});
+                x_off[t * n_cls + cls + 1] = (int32_t)(x_rec.size() / 4);
             }
-            x_off[t + 1] = (int32_t)(x_rec.size() / 4);
         }
     }
     int rc;
     if (has_excl) {
-        if ((rc = upload(h, h->tile_x_off, x_off.data(), (size_t)B + 1))) return rc;
+        if ((rc = upload(h, h->tile_x_off, x_off.data(), x_off.size()))) return rc;
         if ((rc = upload(h, h->tile_x_rec, x_rec.data(), x_rec.size()))) return rc;
     }
     if (G == 0) return NRB200_OK;
@@ -570,22 +637,26 @@ int build_pairs(nrb200_handle *h) {
                 const int64_t gs = q.h_start[k], ge = q.h_end[k];
                 if (gs > L) continue;
                 while (lo < nt && te_max[c][lo] + reach < gs) ++lo;
+                const int g_strand = q.stranded ? q.h_strand[k] : 0;
                 for (int64_t j = lo; j < nt && ts[c][j] <= ge + reach; ++j) {
                     if (te[c][j] + reach < gs) continue;
-                    if (trim) {  // the pieces that can land on the feature: one window per gap it intersects
-                        size_t f, l;
-                        x_run(c, std::max(ts[c][j] - reach, gs), std::min(te[c][j] + reach, ge), f, l);
-                        for (size_t i = f; i < l; ++i) emit(k, v[j], std::max(X[c][i].s, gs), std::min(X[c][i].e, ge), +1);
-                        continue;
-                    }
-                    emit(k, v[j], gs, ge, +1);
-                    if (has_excl) {  // regions a range landing on the tile can overlap together with the feature
-                        size_t f, l;
-                        x_run(c, std::max(ts[c][j] - reach, gs - reach), std::min(te[c][j] + reach, ge + reach), f, l);
-                        for (size_t i = f; i < l; ++i) {
-                            emit(k, v[j], std::max(X[c][i].s, gs), std::min(X[c][i].e, ge), -1);
-                            if (i + 1 < l && X[c][i + 1].s - X[c][i].e <= reach)
-                                emit(k, v[j], std::max(X[c][i + 1].s, gs), std::min(X[c][i].e, ge), +1);
+                    for (int cls = 0; cls < n_cls; ++cls) {  // strand classes of y this feature counts
+                        if (!strands_compatible(cls, g_strand)) continue;
+                        const auto &X = XC[cls][c];
+                        if (trim) {  // the pieces that can land on the feature: one window per gap it intersects
+                            size_t f, l;
+                            x_run(X, std::max(ts[c][j] - reach, gs), std::min(te[c][j] + reach, ge), f, l);
+                            for (size_t i = f; i < l; ++i) emit(k, v[j], std::max(X[i].s, gs), std::min(X[i].e, ge), +1, cls);
+                            continue;
+                        }
+                        emit(k, v[j], gs, ge, +1, cls);
+                        if (has_excl) {  // regions a range landing on the tile can overlap together with the feature
+                            size_t f, l;
+                            x_run(X, std::max(ts[c][j] - reach, gs - reach), std::min(te[c][j] + reach, ge + reach), f, l);
+                            for (size_t i = f; i < l; ++i) {
+                                emit(k, v[j], std::max(X[i].s, gs), std::min(X[i].e, ge), -1, cls);
+                                if (i + 1 < l && X[i + 1].s - X[i].e <= reach) emit(k, v[j], std::max(X[i + 1].s, gs), std::min(X[i].e, ge), +1, cls);
+                            }
                         }
                     }
                 }
@@ -593,7 +664,7 @@ int build_pairs(nrb200_handle *h) {
         }
     };
     std::vector<int32_t> len(G, 0);
-    enumerate([](int32_t) {}, [&](int32_t k, int32_t, int64_t, int64_t, int) { ++len[k]; });
+    enumerate([](int32_t) {}, [&](int32_t k, int32_t, int64_t, int64_t, int, int) { ++len[k]; });
     tr.lap("pass1");
     // Visit order of the count kernel: features grouped by list length (stable counting sort, so
     // neighbours in a group are neighbours on the genome): the lanes of a warp then loop equally often.
@@ -619,9 +690,9 @@ int build_pairs(nrb200_handle *h) {
     std::vector<PairRec> f_recs((size_t)total);
     int64_t cursor = 0;
     enumerate([&](int32_t k) { cursor = f_off[pos_of[k]]; },
-              [&](int32_t, int32_t t, int64_t ws, int64_t we, int sign) {
+              [&](int32_t, int32_t t, int64_t ws, int64_t we, int sign, int cls) {
                   f_recs[cursor++] = PairRec{t, (int32_t)ws, (int32_t)std::min<int64_t>(we, INT32_MAX / 2), sign, p.tile_start[t],
-                                             p.bait_width[t], (int32_t)h->seqlen[p.tile_seq[t]], 0};
+                                             p.bait_width[t], (int32_t)h->seqlen[p.tile_seq[t]], cls};
               });
     tr.lap("lists");
     if ((rc = upload(h, h->f_src, f_src.data(), (size_t)G))) return rc;
@@ -631,14 +702,12 @@ int build_pairs(nrb200_handle *h) {
     return NRB200_OK;
 }
 
-// The rank path covers every sampler (bootstrap and permute, with or without exclusion) whenever
-// strand cannot matter: y is all '*', or the query and the exclude set are.  Everything else
-// streams the hits (boot_count_kernel).
+// The rank path covers every sampler (bootstrap and permute, with or without exclusion, any strands);
+// only a segmentation reaching beyond its sequence falls back to streaming the hits (boot_count_kernel).
 bool rank_path_ok(const nrb200_handle *h, bool with_query) {
+    (void)with_query;
     if (h->flags & NRB200_FLAG_FORCE_STREAM) return false;
-    if (!h->tiles_in_bounds) return false;
-    if (h->y.stranded && ((with_query && h->query.stranded) || (h->excl.n > 0 && active_excl(h).stranded))) return false;
-    return true;
+    return h->tiles_in_bounds;
 }
 
 // rank table over the running max of end: locate_block() of the streaming kernels
@@ -714,10 +783,34 @@ int stage_draws(nrb200_handle *h, const nrb200_draws *d) {
 BootParams make_params(nrb200_handle *h, const nrb200_draws *d) {
     BootParams P{};
     const RangeSet &y = h->y;
-    P.y = RangesView{y.start.as<int32_t>(), y.end.as<int32_t>(), y.pmax.as<int32_t>(),
-                     y.stranded ? y.strand.as<int8_t>() : nullptr, y.sorted_input ? nullptr : y.src.as<int32_t>(), y.seq_off.as<int32_t>(),
-                     h->end_sorted.as<int32_t>(), h->rank_start.as<uint32_t>(), h->rank_pmax.as<uint32_t>(),
-                     h->rank_end.as<uint32_t>(), h->seq_info_dev.as<int4>(), h->rank_shift};
+    RangesView Y{};
+    Y.start = y.start.as<int32_t>();
+    Y.end = y.end.as<int32_t>();
+    Y.pmax = y.pmax.as<int32_t>();
+    Y.strand = y.stranded ? y.strand.as<int8_t>() : nullptr;
+    Y.src = y.sorted_input ? nullptr : y.src.as<int32_t>();
+    Y.seq_off = y.seq_off.as<int32_t>();
+    Y.seq_info = h->seq_info_dev.as<int4>();
+    Y.rank_start = h->rank_start.as<uint32_t>();
+    Y.rank_pmax = h->rank_pmax.as<uint32_t>();
+    Y.rank_shift = h->rank_shift;
+    Y.n_cls = h->n_cls;
+    Y.end_sorted = h->end_sorted.as<int32_t>();
+    Y.rank_end = h->rank_end.as<uint32_t>();
+    if (h->n_cls == 1) {  // unstranded: the rank path reads the canonical arrays
+        Y.rstart = Y.start;
+        Y.rend = Y.end;
+        Y.rpmax = Y.pmax;
+        Y.rseq_info = Y.seq_info;
+        Y.rrank_start = Y.rank_start;
+    } else {
+        Y.rstart = h->r_start.as<int32_t>();
+        Y.rend = h->r_end.as<int32_t>();
+        Y.rpmax = h->r_pmax.as<int32_t>();
+        Y.rseq_info = h->rseq_info_dev.as<int4>();
+        Y.rrank_start = h->rrank_start.as<uint32_t>();
+    }
+    P.y = Y;
     const RangeSet &q = h->query, &x = active_excl(h);
     P.query = SliceView{q.start.as<int32_t>(), q.end.as<int32_t>(), q.pmax.as<int32_t>(), q.stranded ? q.strand.as<int8_t>() : nullptr,
                         q.src.as<int32_t>(), h->q_tile_lo.as<int32_t>(), h->q_tile_hi.as<int32_t>()};

@@ -29,12 +29,18 @@ struct RangesView {            // canonical (seqname, start, end) order
     const int8_t *strand;      // nullptr when every strand is '*'
     const int32_t *src;        // index in the caller's order; nullptr = identity (the input was already canonical)
     const int32_t *seq_off;    // [n_seq + 1]
-        const int32_t *end_sorted; // ends of the sequence in ascending order (rank queries)
-    const uint32_t *rank_start;  // packed rank tables, see "direct-address rank tables" below
+    const int4 *seq_info;      // [n_seq] {seq_off[c], seq_off[c+1], max_pos[c], first table entry} in one 16-byte load
+    const uint32_t *rank_start;  // packed rank tables over start / pmax, see "direct-address rank tables" below
     const uint32_t *rank_pmax;
-    const uint32_t *rank_end;
-    const int4 *seq_info;      // [n_seq] {seq_off[c], seq_off[c+1], max_pos[c], rank_off[c]} in one 16-byte load
     int rank_shift;
+    // Rank path.  When strand can matter the ranges are ALSO kept grouped by strand class inside each
+    // sequence ("virtual sequence" v = seq * n_cls + class, class 0 '*', 1 '+', 2 '-'), so that a count
+    // can be taken per class; with an unstranded y (n_cls = 1) these alias the canonical arrays.
+    int n_cls;
+    const int32_t *rstart, *rend, *rpmax;   // (seq, class, start, end) order
+    const int32_t *end_sorted;               // ends ascending inside each virtual sequence
+    const int4 *rseq_info;                   // [n_seq * n_cls]
+    const uint32_t *rrank_start, *rank_end;  // tables over rstart / end_sorted
 };
 
 struct SliceView {             // query or exclude (or, for "trim", the gaps), canonical order, plus a per-tile window
@@ -144,7 +150,7 @@ __device__ __forceinline__ void locate_block(const RangesView &y, int c, int32_t
 // #{start <= a} and #{end < b} on a sequence, both as canonical-order indices (their difference
 // is the number of ranges overlapping [b, a] when b <= a).  a, b are below 2^31 - 1.
 __device__ __forceinline__ int32_t idx_start_le(const RangesView &y, const int4 si, int32_t a) {
-    return first_ge_ranked(y.start, y.rank_start, y.rank_shift, si, a + 1);
+    return first_ge_ranked(y.rstart, y.rrank_start, y.rank_shift, si, a + 1);
 }
 __device__ __forceinline__ int32_t idx_end_lt(const RangesView &y, const int4 si, int32_t b) {
     return first_ge_ranked(y.end_sorted, y.rank_end, y.rank_shift, si, b);
@@ -487,7 +493,7 @@ struct PairRec {               // one signed window to count for a feature on a 
     int32_t ws, we;            // window on the tile's sequence ([gs, ge] or an exclusion pseudo-feature)
     int32_t sign;              // +1 / -1
     int32_t tile_start, width, seq_len;  // copied from the block tables: saves three dependent loads
-    int32_t pad;
+    int32_t cls;               // strand class of y the window counts (0 when y is unstranded)
 };
 static_assert(sizeof(PairRec) == 32, "PairRec is read as two int4");
 
@@ -497,8 +503,8 @@ struct FeatView {              // query features in visit order (grouped by list
     const PairRec *pair_rec;
 };
 
-struct TileExcl {              // signed exclusion windows of each tile, for the rows kernel
-    const int32_t *off;        // [n_blocks + 1], or nullptr without exclusion
+struct TileExcl {              // signed exclusion windows of each (tile, strand class), for the rows kernel
+    const int32_t *off;        // [n_blocks * n_cls + 1], or nullptr without exclusion
     const int4 *rec;           // {ws, we, sign, 0}
 };
 
@@ -543,7 +549,7 @@ __device__ __forceinline__ int32_t bucket_rank(const int32_t *__restrict__ vals,
 __device__ __forceinline__ int count_spanning(const RangesView &y, const int4 si, int32_t ia, int32_t b) {
     if (b > si.z) return 0;
     int n = 0;
-    for (int32_t k = ia - 1; k >= si.x && __ldg(y.pmax + k) >= b; --k) n += __ldg(y.end + k) >= b;
+    for (int32_t k = ia - 1; k >= si.x && __ldg(y.rpmax + k) >= b; --k) n += __ldg(y.rend + k) >= b;
     return n;
 }
 
@@ -554,22 +560,22 @@ template <bool PERMUTE>
 __device__ __forceinline__ int pair_finish(const RangesView &y, const PairProbe &q, int32_t ia, int32_t ib) {
     if (q.A < 1 || (PERMUTE && q.A < q.bs)) return 0;  // permute: no start can lie in [bs, A]
     int n = q.Bv <= q.A ? ia - ib : count_spanning(y, q.si, ia, q.Bv);  // second form: the feature lies beside the tile
-    if (PERMUTE && n > 0) n -= count_spanning(y, q.si, first_ge_ranked(y.start, y.rank_start, y.rank_shift, q.si, q.bs), q.Bv);
+    if (PERMUTE && n > 0) n -= count_spanning(y, q.si, first_ge_ranked(y.rstart, y.rrank_start, y.rank_shift, q.si, q.bs), q.Bv);
     return n;
 }
 
 template <int RPT, bool PERMUTE = false>
-__device__ __forceinline__ void count_pairs(const RangesView &y, const int2 (&d)[RPT], int32_t width, int32_t ts,
+__device__ __forceinline__ void count_pairs(const RangesView &y, const int2 (&d)[RPT], int cls, int32_t width, int32_t ts,
                                             int32_t seq_len, int32_t gs, int32_t ge, int (&cnt)[RPT]) {
     PairProbe q[RPT];
     int32_t ua[RPT], ub[RPT];
 #pragma unroll
-    for (int j = 0; j < RPT; ++j) q[j].si = __ldg(y.seq_info + d[j].x);
+    for (int j = 0; j < RPT; ++j) q[j].si = __ldg(y.rseq_info + d[j].x * y.n_cls + cls);
 #pragma unroll
     for (int j = 0; j < RPT; ++j) pair_keys(q[j], d[j], width, ts, seq_len, gs, ge, y.rank_shift, ua[j], ub[j]);
 #pragma unroll
     for (int j = 0; j < RPT; ++j) {
-        const uint32_t ea = __ldg(y.rank_start + ua[j]), eb = __ldg(y.rank_end + ub[j]);
+        const uint32_t ea = __ldg(y.rrank_start + ua[j]), eb = __ldg(y.rank_end + ub[j]);
         q[j].a0 = q[j].si.x + (int32_t)(ea >> kRankCountBits);
         q[j].an = (int32_t)(ea & kRankCountCap);
         q[j].b0 = q[j].si.x + (int32_t)(eb >> kRankCountBits);
@@ -580,13 +586,13 @@ __device__ __forceinline__ void count_pairs(const RangesView &y, const int2 (&d)
     for (int j = 0; j < RPT; ++j) {
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
-            va[j][k] = k < q[j].an ? __ldg(y.start + q[j].a0 + k) : INT32_MAX;
+            va[j][k] = k < q[j].an ? __ldg(y.rstart + q[j].a0 + k) : INT32_MAX;
             vb[j][k] = k < q[j].bn ? __ldg(y.end_sorted + q[j].b0 + k) : INT32_MAX;
         }
     }
 #pragma unroll
     for (int j = 0; j < RPT; ++j) {
-        const int32_t ia = bucket_rank(y.start, y.rank_start, ua[j], q[j].si, q[j].a0, q[j].an, q[j].key_a, va[j][0], va[j][1], va[j][2]);
+        const int32_t ia = bucket_rank(y.rstart, y.rrank_start, ua[j], q[j].si, q[j].a0, q[j].an, q[j].key_a, va[j][0], va[j][1], va[j][2]);
         const int32_t ib = bucket_rank(y.end_sorted, y.rank_end, ub[j], q[j].si, q[j].b0, q[j].bn, q[j].key_b, vb[j][0], vb[j][1], vb[j][2]);
         cnt[j] += pair_finish<PERMUTE>(y, q[j], ia, ib);
     }
@@ -618,8 +624,8 @@ __global__ void __launch_bounds__(256, MINB) boot_rank_count_kernel(const BootPa
             int c[RPT];
 #pragma unroll
             for (int j = 0; j < RPT; ++j) c[j] = 0;
-            if (P.permute) count_pairs<RPT, true>(P.y, d, rb.y, rb.x, rb.z, ra.y, ra.z, c);
-            else count_pairs<RPT, false>(P.y, d, rb.y, rb.x, rb.z, ra.y, ra.z, c);
+            if (P.permute) count_pairs<RPT, true>(P.y, d, rb.w, rb.y, rb.x, rb.z, ra.y, ra.z, c);
+            else count_pairs<RPT, false>(P.y, d, rb.w, rb.y, rb.x, rb.z, ra.y, ra.z, c);
 #pragma unroll
             for (int j = 0; j < RPT; ++j) cnt[j] += ra.w * c[j];
         }
@@ -677,22 +683,26 @@ __global__ void __launch_bounds__(256) boot_block_rows_kernel(const BootParams P
                 const int32_t ts = __ldg(P.tile_start + t);
                 const int32_t seq_len = (int32_t)__ldg(P.seqlen + __ldg(P.tile_seq + t));
                 if (P.draw_tab) P.draw_tab[(r0 + j) * P.n_blocks + t] = d;  // the count kernel looks draws up by tile
-                const int4 si = __ldg(P.y.seq_info + d.x);
-                const int32_t ie = idx_start_le(P.y, si, d.y + (width - 1));
-                // hits: overlap of the bait block (bootstrap) / start inside the tile (permute)
-                const int hits = ie - (P.permute ? idx_start_le(P.y, si, d.y - 1) : idx_end_lt(P.y, si, d.y));
-                int dropped = 0;  // only a tile that overhangs its sequence end can push hits beyond it
-                if (P.drop_zero && ts + (width - 1) > seq_len) dropped = max(0, ie - idx_start_le(P.y, si, seq_len - (ts - d.y)));
-                rows[j] = P.rows_windows_only ? 0 : hits - dropped;
-                if (X.off) {  // minus the hits that overlap an exclude region after the move ("trim": plus the pieces)
-                    const int32_t x1 = __ldg(X.off + t + 1);
-                    for (int32_t k = __ldg(X.off + t); k < x1; ++k) {
-                        const int4 w = __ldg(X.rec + k);
-                        const int2 dd[1] = {d};
-                        int c1[1] = {0};
-                        if (P.permute) count_pairs<1, true>(P.y, dd, width, ts, seq_len, w.x, w.y, c1);
-                        else count_pairs<1, false>(P.y, dd, width, ts, seq_len, w.x, w.y, c1);
-                        rows[j] += w.z * c1[0];
+                int hits = 0;
+                for (int cls = 0; cls < P.y.n_cls; ++cls) {  // one pass per strand class of y (one when y is unstranded)
+                    const int4 si = __ldg(P.y.rseq_info + d.x * P.y.n_cls + cls);
+                    const int32_t ie = idx_start_le(P.y, si, d.y + (width - 1));
+                    // hits: overlap of the bait block (bootstrap) / start inside the tile (permute)
+                    const int h1 = ie - (P.permute ? idx_start_le(P.y, si, d.y - 1) : idx_end_lt(P.y, si, d.y));
+                    int dropped = 0;  // only a tile that overhangs its sequence end can push hits beyond it
+                    if (P.drop_zero && ts + (width - 1) > seq_len) dropped = max(0, ie - idx_start_le(P.y, si, seq_len - (ts - d.y)));
+                    hits += h1;
+                    if (!P.rows_windows_only) rows[j] += h1 - dropped;
+                    if (X.off) {  // minus the hits that overlap an exclude region after the move ("trim": plus the pieces)
+                        const int32_t x1 = __ldg(X.off + t * P.y.n_cls + cls + 1);
+                        for (int32_t k = __ldg(X.off + t * P.y.n_cls + cls); k < x1; ++k) {
+                            const int4 w = __ldg(X.rec + k);
+                            const int2 dd[1] = {d};
+                            int c1[1] = {0};
+                            if (P.permute) count_pairs<1, true>(P.y, dd, cls, width, ts, seq_len, w.x, w.y, c1);
+                            else count_pairs<1, false>(P.y, dd, cls, width, ts, seq_len, w.x, w.y, c1);
+                            rows[j] += w.z * c1[0];
+                        }
                     }
                 }
                 hits_sum += hits;
@@ -800,6 +810,50 @@ __global__ void iota_kernel(int32_t *__restrict__ v, int64_t n) {
 struct MaxOp {
     __host__ __device__ __forceinline__ int32_t operator()(int32_t a, int32_t b) const { return a > b ? a : b; }
 };
+
+// ---- strand-class grouping of y for the rank path -----------------------------------------
+// virtual sequence of a range: seq * 3 + strand code
+__global__ void vseq_keys_kernel(const int32_t *__restrict__ seqid, const int8_t *__restrict__ strand, int64_t n,
+                                 unsigned *__restrict__ keys, int32_t *__restrict__ idx) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        keys[i] = (unsigned)seqid[i] * 3u + (unsigned)strand[i];
+        idx[i] = (int32_t)i;
+    }
+}
+// class-major copies of start / end (order = stable sort of the canonical order on the virtual sequence)
+__global__ void gather_by_order_kernel(const int32_t *__restrict__ order, const int32_t *__restrict__ start,
+                                       const int32_t *__restrict__ end, int64_t n, int32_t *__restrict__ rstart,
+                                       int32_t *__restrict__ rend) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        const int32_t o = order[i];
+        rstart[i] = start[o];
+        rend[i] = end[o];
+    }
+}
+// voff[v] = first position of virtual sequence v in the sorted keys; seq_info of every virtual sequence
+__global__ void vseq_info_kernel(const unsigned *__restrict__ sorted_keys, int64_t n, int n_vseq, const int32_t *__restrict__ max_pos,
+                                 const int64_t *__restrict__ rank_off, int32_t *__restrict__ voff, int4 *__restrict__ info) {
+    const int v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v > n_vseq) return;
+    auto lower = [&](unsigned key) {
+        int64_t a = 0, b = n;
+        while (a < b) {
+            const int64_t m = (a + b) >> 1;
+            if (sorted_keys[m] < key) a = m + 1; else b = m;
+        }
+        return (int32_t)a;
+    };
+    const int32_t lo = lower((unsigned)v);
+    voff[v] = lo;
+    if (v < n_vseq) info[v] = make_int4(lo, lower((unsigned)v + 1u), max_pos[v / 3], (int32_t)rank_off[v]);
+}
+__global__ void pack_vend_keys_kernel(const unsigned *__restrict__ vkeys, const int32_t *__restrict__ end, int64_t n,
+                                      unsigned long long *__restrict__ keys) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) keys[i] = ((unsigned long long)vkeys[i] << 32) | (unsigned)end[i];
+}
 
 // entry t of a packed rank table (see "direct-address rank tables")
 __global__ void build_rank_table_kernel(const int32_t *__restrict__ values, const int32_t *__restrict__ seq_off,

@@ -51,6 +51,7 @@ class Engine:
         if rc:
             raise EngineError(rc, self._lib.nrb200_last_error(None).decode())
         self.device = device
+        self.force_stream = bool(force_stream)
         self.n_blocks = 0
         self.n_query = 0
         self.n_seq = 0

@@ -358,3 +358,17 @@ def test_error_behaviour(engine):
         bootRanges(y.sort(), 10.5)
     empty = bootCounts(y.sort(), GRanges(["zz"], [1], width=[5], seqlevels=["zz"], seqlengths=[9]), 10, R=3, seed=1)
     assert empty.feature_counts.shape == (3, 1) and empty.feature_counts.sum() == 0   # features on unknown sequences count 0
+
+
+@pytest.mark.parametrize("kind", ALL_KINDS)
+def test_dispatch_rank_vs_stream(engine, kind):
+    """Every sampler -- stranded, excluded, permuted -- runs on the rank path by default (stats.n_windows > 0);
+    an engine created with force_stream reports none."""
+    case = H.random_case(seed=600 + kind, n=300, n_seq=3, n_query=40, n_excl=10, stranded=True, n_seg=9, n_states=2)
+    plan, y, q, x = H.oracle_objects(case, kind)
+    H.load_engine(engine, case, kind)
+    d = H.draw_R(plan, 2, 2)
+    st = engine.run_counts_resident(Draws(n_iter=2, rng_mode=_lib.RNG_HOST, bait_seqid=d[0], bait_start=d[1],
+                                          dst_tile=d[2] if kind >= 4 else None), True, True)
+    assert (st["n_windows"] == 0) == engine.force_stream
+    assert st["n_launches"] == (1 if engine.force_stream else 2)
