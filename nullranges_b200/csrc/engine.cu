@@ -134,13 +134,12 @@ struct nrb200_handle {
     // run scratch / results
     DevMem d_bait_seq, d_bait_start, d_dst_tile;
     DevMem d_iter_nranges, d_iter_totals, d_counts, d_n_hits;
-    int64_t res_iter = 0;
     bool res_has_counts = false;
     // moments
     DevMem m_sum, m_sumsq, m_nge, m_observed;
     bool moments_ready = false;
     // rows
-    DevMem item_rows, within_off, iter_off_dev, row_seq, row_start, row_end, row_src, row_block;
+    DevMem item_rec, item_rows, within_off, iter_off_dev, row_seq, row_start, row_end, row_src, row_block;
     int64_t n_rows = 0;
 };
 
@@ -906,6 +905,7 @@ BootParams slice_params(const BootParams &P, int64_t r0, int64_t n) {
     if (P.iter_totals) Q.iter_totals = P.iter_totals + r0;
     if (P.counts) Q.counts = P.counts + r0 * P.n_query;
     if (P.item_rows) Q.item_rows = P.item_rows + r0 * P.n_blocks;
+    if (P.item_rec) Q.item_rec = P.item_rec + r0 * P.n_blocks;
     return Q;
 }
 
@@ -980,7 +980,6 @@ int run_counts_core(nrb200_handle *h, const nrb200_draws *d, bool want_counts, i
         }
     }
     NRB_CUDA(h, cudaEventRecord(h->ev[2], h->stream));
-    h->res_iter = R;
     h->res_has_counts = want_counts;
     if (stats) {
         NRB_CUDA(h, cudaEventSynchronize(h->ev[2]));
@@ -1381,13 +1380,12 @@ int nrb200_run_materialize(nrb200_handle *h, const nrb200_draws *draws, int64_t 
     NRB_CUDA(h, cudaEventRecord(h->ev[1], h->stream));
     int count_launches = 0;
     const bool rank_rows = rank_path_ok(h, false);
-    if (rank_rows && items > 0) {  // the rows kernel leaves its draws for the fill kernel
-        NRB_CUDA(h, h->draw_tab.reserve((size_t)items * sizeof(int2)));
-        P.draw_tab = h->draw_tab.as<int2>();
+    if (rank_rows && items > 0) {  // the rows kernel leaves each block's draw and hit window for the fill kernel
+        NRB_CUDA(h, h->item_rec.reserve((size_t)items * sizeof(int4)));
+        P.item_rec = h->item_rec.as<int4>();
     }
     for (int64_t r0 = 0; r0 < R; r0 += kMaxBatch) {
         BootParams Q = slice_params(P, r0, std::min(kMaxBatch, R - r0));
-        if (P.draw_tab) Q.draw_tab = P.draw_tab + r0 * B;
         count_launches += launch_count(h, Q, false);
         NRB_CUDA(h, cudaGetLastError());
     }
@@ -1409,7 +1407,6 @@ int nrb200_run_materialize(nrb200_handle *h, const nrb200_draws *draws, int64_t 
         const int64_t kFillBatch = 32768;  // gridDim.y
         for (int64_t r0 = 0; r0 < R; r0 += kFillBatch, ++fill_launches) {
             BootParams Q = slice_params(P, r0, std::min(kFillBatch, R - r0));
-            if (P.draw_tab) Q.draw_tab = P.draw_tab + r0 * B;
             const RowsOut O{h->row_seq.as<int32_t>(), h->row_start.as<int32_t>(), h->row_end.as<int32_t>(), h->row_src.as<int32_t>(),
                             h->row_block.as<int32_t>(), h->iter_off_dev.as<int64_t>() + r0, h->within_off.as<int32_t>() + r0 * B,
                             h->item_rows.as<int32_t>() + r0 * B, reinterpret_cast<int *>(h->d_n_hits.as<char>() + 8)};

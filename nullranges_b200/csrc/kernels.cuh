@@ -84,6 +84,7 @@ struct BootParams {
     int32_t *item_rows;       // [n_iter x n_blocks] surviving rows per item, or nullptr
     unsigned long long *n_hits;  // total ranges sampled (byte-model H)
     int2 *draw_tab;           // [n_iter x n_blocks] {bait seq, bait start}: rank path scratch
+    int4 *item_rec;           // [n_iter x n_blocks] {lo, hi, bait seq, bait start}: written by the rows kernel for the fill pass
 };
 
 // ---- searches -------------------------------------------------------------------------
@@ -199,6 +200,19 @@ struct Item {
 __device__ __forceinline__ Item load_item(const BootParams &P, int64_t r, int64_t b) {
     Item it;
     const int64_t flat = r * P.n_blocks + b;
+    if (P.item_rec) {  // the rows kernel already drew the block and located its hit window
+        const int4 rec = __ldg(P.item_rec + flat);
+        it.lo = rec.x;
+        it.hi = rec.y;
+        it.bait_seq = rec.z;
+        it.bait_start = rec.w;
+        it.tile = P.dst_tile ? __ldg(P.dst_tile + flat) : (int)b;
+        it.bait_end = (int64_t)it.bait_start + __ldg(P.bait_width + b) - 1;
+        it.tile_seq = __ldg(P.tile_seq + it.tile);
+        it.shift = __ldg(P.tile_start + it.tile) - it.bait_start;
+        it.seq_len = (int32_t)__ldg(P.seqlen + it.tile_seq);
+        return it;
+    }
     if (P.draw_tab && !P.permute) {  // the rows kernel of the rank path already drew this block (bootstrap kinds: block b -> tile b)
         const int2 d = __ldg(P.draw_tab + flat);
         it.bait_seq = d.x;
@@ -683,6 +697,11 @@ __global__ void __launch_bounds__(256) boot_block_rows_kernel(const BootParams P
                 const int32_t ts = __ldg(P.tile_start + t);
                 const int32_t seq_len = (int32_t)__ldg(P.seqlen + __ldg(P.tile_seq + t));
                 if (P.draw_tab) P.draw_tab[(r0 + j) * P.n_blocks + t] = d;  // the count kernel looks draws up by tile
+                if (P.item_rec) {  // materialising: the fill pass streams canonical window [lo, hi) of this block
+                    int32_t lo, hi;
+                    locate_block(P.y, d.x, d.y, (int64_t)d.y + width - 1, lo, hi);
+                    P.item_rec[flat] = make_int4(lo, hi, d.x, d.y);
+                }
                 int hits = 0;
                 for (int cls = 0; cls < P.y.n_cls; ++cls) {  // one pass per strand class of y (one when y is unstranded)
                     const int4 si = __ldg(P.y.rseq_info + d.x * P.y.n_cls + cls);
@@ -800,11 +819,6 @@ __global__ void __launch_bounds__(256) inspect_ranges_kernel(const int32_t *__re
         if (stranded) atomicOr(&out->stranded, 1);
         atomicMax(&out->wmax, wmax);
     }
-}
-
-__global__ void iota_kernel(int32_t *__restrict__ v, int64_t n) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) v[i] = (int32_t)i;
 }
 
 struct MaxOp {
