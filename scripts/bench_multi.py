@@ -45,6 +45,9 @@ if args.config == 4:
     obs, obs_total = eng.count_observed()
     iter0, n = shard_iterations(R, world, rank)
     eng.run_moments(Draws(n_iter=min(n, 64), seed=7, iter0=iter0), observed=obs)  # warm-up
+    if world > 1:  # first collectives set up the communicator: keep that out of the timing
+        dist.all_reduce(torch.zeros(8, device=dev))
+        gather_iteration_vectors({"iter_totals": np.zeros(n, np.int64)}, R, device=dev)
     barrier()
     t0 = time.perf_counter()
     m = eng.run_moments(Draws(n_iter=n, seed=7, iter0=iter0), observed=obs)
@@ -79,6 +82,8 @@ else:
     per = max(1, world // 4)                                   # ranks sharing one block length
     mine = [LBS[rank % 4]] if world >= 4 else LBS[rank::world]
     res = {}
+    if world > 1:
+        dist.all_reduce(torch.zeros(8, device=dev))
     barrier()
     t0 = time.perf_counter()
     for Lb in mine:
