@@ -372,3 +372,66 @@ def test_dispatch_rank_vs_stream(engine, kind):
                                           dst_tile=d[2] if kind >= 4 else None), True, True)
     assert (st["n_windows"] == 0) == engine.force_stream
     assert st["n_launches"] == (1 if engine.force_stream else 2)
+
+
+@pytest.mark.parametrize("seed", range(240))
+def test_fuzz_parity(engine, seed):
+    """Random configurations across every option at once (sampler, strands of y / query / exclude set
+    independently, exclusion mode, maxgap, unsorted input, points, ranges wider than a block, features past
+    the sequence end): fused counts, row counts and the materialised table vs the oracle."""
+    rng = np.random.default_rng(10_000 + seed)
+    kind = int(rng.integers(0, 6))
+    n_seq = int(rng.integers(1, 6))
+    L_b = int(rng.choice([50, 200, 500, 1500]))
+    case = H.random_case(seed=20_000 + seed, n=int(rng.integers(0, 900)), n_seq=n_seq, max_len=int(rng.choice([3000, 6000, 20000])),
+                         n_query=int(rng.integers(1, 120)), n_excl=0, stranded=False, wmax=int(rng.choice([1, 30, 300, 2500])),
+                         L_b=L_b, n_seg=3 * n_seq, n_states=int(rng.integers(1, 4)), sort=bool(rng.integers(0, 2)) or kind in (0, 5),
+                         points=bool(rng.integers(0, 5) == 0))
+    L = case["seqlen"]
+
+    def restrand(t, p):
+        return t if rng.random() > p else (t[0], t[1], t[2], rng.integers(0, 3, t[0].size).astype(np.int8))
+
+    case["y"] = restrand(case["y"], 0.4)
+    q = restrand(case["query"], 0.4)
+    qs, qe = q[1].copy(), q[2].copy()
+    far = rng.random(qs.size) < 0.1                                 # some features straddle / lie past the sequence end
+    qe[far] = (L[q[0][far]] + rng.integers(0, 200, int(far.sum()))).astype(np.int32)
+    qs[far] = np.minimum(qs[far], qe[far])
+    case["query"] = (q[0], qs, qe, q[3])
+    mode = rng.choice(["none", "drop", "trim"], p=[0.3, 0.4, 0.3])
+    if mode != "none":
+        m = int(rng.integers(1, 80))
+        sid = rng.integers(0, n_seq, m).astype(np.int32)
+        st = (1 + rng.random(m) * (L[sid] - 1)).astype(np.int32)
+        en = (st + rng.integers(0, int(rng.choice([5, 60, 900])), m)).astype(np.int32)
+        x = (sid, st, en, None)
+        case["excl"] = x if mode == "trim" else restrand(x, 0.4)
+        case["trim"] = mode == "trim"
+    case["maxgap"] = int(rng.choice([-1, -1, 0, 40]))
+    try:
+        plan, y, qi, xi = H.oracle_objects(case, kind)
+    except ValueError as e:                                      # e.g. a state's scaled block length rounds to 0
+        with pytest.raises(Exception):
+            H.load_engine(engine, case, kind)
+        return
+    B = H.load_engine(engine, case, kind)
+    assert B == plan.B
+    R = 3
+    d = H.draw_R(plan, 1 + seed, R)
+    draws = Draws(n_iter=R, rng_mode=_lib.RNG_HOST, bait_seqid=d[0], bait_start=d[1], dst_tile=d[2] if kind >= 4 else None)
+    ref = O.boot_counts(plan, y, qi, R, exclude=xi, exclude_mode=H.excl_mode(case), draws=d)
+    got = engine.run_counts(draws)
+    for k in ("iter_nranges", "iter_totals", "feature_counts"):
+        assert np.array_equal(got[k], ref[k]), (k, kind, mode)
+    if kind < 3:
+        ref = O.boot_counts(plan, y, qi, R, exclude=xi, exclude_mode=H.excl_mode(case), seed=seed, iter0=11)
+        got = engine.run_counts(Draws(n_iter=R, rng_mode=_lib.RNG_PHILOX, seed=seed, iter0=11))
+        for k in ("iter_nranges", "iter_totals", "feature_counts"):
+            assert np.array_equal(got[k], ref[k]), (k, kind, mode, "philox")
+    rows = engine.run_materialize(draws)
+    it = np.repeat(np.arange(R), np.diff(rows["iter_offsets"]))
+    got_rows = np.stack([it, rows["seqid"], rows["start"], rows["end"], rows["src"], rows["block"]], axis=1)
+    want = H.oracle_rows(plan, y, xi, d, R, mode=H.excl_mode(case))
+    key = lambda a: a[np.lexsort((a[:, 2], a[:, 4], a[:, 5], a[:, 0]))] if a.size else a
+    assert np.array_equal(key(got_rows), key(want)), (kind, mode)
