@@ -189,6 +189,21 @@ int upload(nrb200_handle *h, DevMem &dst, const T *src, size_t n) {
     return NRB200_OK;
 }
 
+// Room inside the pinned arena to BUILD an array in place (then upload_staged): nullptr when it does not fit.
+void *arena_alloc(nrb200_handle *h, size_t bytes) {
+    if (!h->arena && cudaMallocHost((void **)&h->arena, kArenaBytes) == cudaSuccess) h->arena_cap = kArenaBytes;
+    const size_t at = (h->arena_used + 255) & ~(size_t)255;
+    if (!h->arena || at + bytes > h->arena_cap) return nullptr;
+    h->arena_used = at + bytes;
+    return h->arena + at;
+}
+template <class T>
+int upload_staged(nrb200_handle *h, DevMem &dst, const T *arena_src, size_t n) {
+    NRB_CUDA(h, dst.reserve(n * sizeof(T)));
+    if (n) NRB_CUDA(h, cudaMemcpyAsync(dst.p, arena_src, n * sizeof(T), cudaMemcpyHostToDevice, h->stream));
+    return NRB200_OK;
+}
+
 // Host -> device copy straight from a caller-owned array (pinned or pageable): never staged.
 template <class T>
 int upload_direct(nrb200_handle *h, DevMem &dst, const T *src, size_t n) {
@@ -686,7 +701,14 @@ int build_pairs(nrb200_handle *h) {
     }
     h->n_pairs = total;
     tr.lap("binning");
-    std::vector<PairRec> f_recs((size_t)total);
+    // records are written straight into pinned staging memory when they fit there
+    std::vector<PairRec> f_recs_vec;
+    PairRec *f_recs = static_cast<PairRec *>(arena_alloc(h, (size_t)std::max<int64_t>(total, 1) * sizeof(PairRec)));
+    const bool staged = f_recs != nullptr;
+    if (!staged) {
+        f_recs_vec.resize((size_t)total);
+        f_recs = f_recs_vec.data();
+    }
     int64_t cursor = 0;
     enumerate([&](int32_t k) { cursor = f_off[pos_of[k]]; },
               [&](int32_t, int32_t t, int64_t ws, int64_t we, int sign, int cls) {
@@ -696,7 +718,7 @@ int build_pairs(nrb200_handle *h) {
     tr.lap("lists");
     if ((rc = upload(h, h->f_src, f_src.data(), (size_t)G))) return rc;
     if ((rc = upload(h, h->pair_off, f_off.data(), (size_t)G + 1))) return rc;
-    if ((rc = upload(h, h->pair_rec, f_recs.data(), f_recs.size()))) return rc;
+    if ((rc = staged ? upload_staged(h, h->pair_rec, f_recs, (size_t)total) : upload(h, h->pair_rec, f_recs, (size_t)total))) return rc;
     tr.lap("upload");
     return NRB200_OK;
 }
