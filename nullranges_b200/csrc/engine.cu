@@ -132,7 +132,7 @@ struct nrb200_handle {
     bool tiles_in_bounds = false;
 
     // run scratch / results
-    DevMem d_bait_seq, d_bait_start, d_dst_tile;
+    DevMem d_bait_seq, d_bait_start, d_dst_tile, perm_vals_a, perm_vals_b;
     DevMem d_iter_nranges, d_iter_totals, d_counts, d_n_hits;
     bool res_has_counts = false;
     // moments
@@ -779,10 +779,39 @@ int stage_draws(nrb200_handle *h, const nrb200_draws *d) {
     const Plan &p = h->plan;
     const int64_t B = p.n_blocks();
     if (d->rng_mode == NRB200_RNG_PHILOX) {
-        if (p.kind != NRB200_UNSEG_ACROSS && p.kind != NRB200_UNSEG_WITHIN && p.kind != NRB200_SEG_PROP)
+        if (p.kind == NRB200_SEG_NOPROP)
             return fail(h, NRB200_ERR_UNSUPPORTED,
-                        "device Philox draws cover the unsegmented and proportionLength=TRUE bootstraps; "
-                        "draw this sampler on the host (NRB200_RNG_HOST)");
+                        "device Philox draws cover every sampler except proportionLength=FALSE; "
+                        "draw that one on the host (NRB200_RNG_HOST)");
+        if (!p.permute()) return NRB200_OK;
+        // permute variants: one random permutation of the tiles per iteration, made on the device
+        if (h->n_seq > 4096) return fail(h, NRB200_ERR_UNSUPPORTED, "device permutations support at most 4096 sequences");
+        const int64_t R = d->n_iter;
+        NRB_CUDA(h, h->d_dst_tile.reserve((size_t)std::max<int64_t>(R * B, 1) * 4));
+        const int64_t kPermBatch = 4096;  // 12 bits of the sort key
+        const int64_t cap = std::min(R, kPermBatch) * B;
+        NRB_CUDA(h, h->sort_keys_a.reserve((size_t)std::max<int64_t>(cap, 1) * 8));
+        NRB_CUDA(h, h->sort_keys_b.reserve((size_t)std::max<int64_t>(cap, 1) * 8));
+        NRB_CUDA(h, h->perm_vals_a.reserve((size_t)std::max<int64_t>(cap, 1) * 4));
+        NRB_CUDA(h, h->perm_vals_b.reserve((size_t)std::max<int64_t>(cap, 1) * 4));
+        for (int64_t r0 = 0; r0 < R; r0 += kPermBatch) {
+            const int64_t n = std::min(kPermBatch, R - r0), items = n * B;
+            if (items == 0) continue;
+            const unsigned grid = (unsigned)((items + 255) / 256);
+            permute_keys_kernel<<<grid, 256, 0, h->stream>>>(d->seed, d->iter0 + r0, n, B, h->tile_seq.as<int32_t>(),
+                                                              p.kind == NRB200_PERMUTE_WITHIN, h->sort_keys_a.as<unsigned long long>(),
+                                                              h->perm_vals_a.as<int32_t>());
+            size_t tmp_bytes = 0;
+            NRB_CUDA(h, cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, h->sort_keys_a.as<unsigned long long>(),
+                                                        h->sort_keys_b.as<unsigned long long>(), h->perm_vals_a.as<int32_t>(),
+                                                        h->perm_vals_b.as<int32_t>(), items, 0, 64, h->stream));
+            NRB_CUDA(h, h->sort_tmp.reserve(tmp_bytes));
+            NRB_CUDA(h, cub::DeviceRadixSort::SortPairs(h->sort_tmp.p, tmp_bytes, h->sort_keys_a.as<unsigned long long>(),
+                                                        h->sort_keys_b.as<unsigned long long>(), h->perm_vals_a.as<int32_t>(),
+                                                        h->perm_vals_b.as<int32_t>(), items, 0, 64, h->stream));
+            permute_scatter_kernel<<<grid, 256, 0, h->stream>>>(h->perm_vals_b.as<int32_t>(), n, B, h->d_dst_tile.as<int32_t>() + r0 * B);
+            NRB_CUDA(h, cudaGetLastError());
+        }
         return NRB200_OK;
     }
     if (d->rng_mode != NRB200_RNG_HOST) return fail(h, NRB200_ERR_INVALID, "draws: unknown rng_mode");
@@ -853,6 +882,8 @@ BootParams make_params(nrb200_handle *h, const nrb200_draws *d) {
         P.bait_seq = h->d_bait_seq.as<int32_t>();
         P.bait_start = h->d_bait_start.as<int32_t>();
         P.dst_tile = d->dst_tile ? h->d_dst_tile.as<int32_t>() : nullptr;
+    } else if (h->plan.permute()) {
+        P.dst_tile = h->d_dst_tile.as<int32_t>();  // made by stage_draws() on the device
     }
     P.n_iter = d->n_iter;
     P.n_query = q.n;

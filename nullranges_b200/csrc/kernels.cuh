@@ -173,6 +173,9 @@ __device__ __forceinline__ void draw_block(const BootParams &P, uint64_t iter, i
     } else if (S.kind == NRB200_UNSEG_WITHIN) {
         c = __ldg(P.tile_seq + b);
         s = (int32_t)rounded_uniform(u.hi, 1, (S.tiles_per_seq[c] - 1) * S.block_length);
+    } else if (S.kind == NRB200_PERMUTE_WITHIN || S.kind == NRB200_PERMUTE_ACROSS) {
+        c = __ldg(P.tile_seq + b);    // the blocks ARE the tiles; the draw is where they go (dst_tile, permute_keys_kernel)
+        s = __ldg(P.tile_start + b);
     } else {  // NRB200_SEG_PROP
         int st = 1;
         while (st < S.n_states && b >= S.state_block_off[st + 1]) ++st;
@@ -220,7 +223,7 @@ __device__ __forceinline__ Item load_item(const BootParams &P, int64_t r, int64_
         it.tile = (int)b;
     } else if (P.rng_mode == NRB200_RNG_PHILOX) {
         draw_block(P, (uint64_t)(P.iter0 + r), b, it.bait_seq, it.bait_start);
-        it.tile = (int)b;
+        it.tile = P.dst_tile ? __ldg(P.dst_tile + flat) : (int)b;
     } else {
         it.bait_seq = __ldg(P.bait_seq + flat);
         it.bait_start = __ldg(P.bait_start + flat);
@@ -824,6 +827,29 @@ __global__ void __launch_bounds__(256) inspect_ranges_kernel(const int32_t *__re
 struct MaxOp {
     __host__ __device__ __forceinline__ int32_t operator()(int32_t a, int32_t b) const { return a > b ? a : b; }
 };
+
+// ---- device-side permutations (production mode of the permute variants) -------------------
+// Image of sample(n) (R/bootUnsegmented.R:97, :156): tile b of local iteration r gets the sort key
+// (r << 52) | (sequence << 40 -- within-chromosome variant only) | 40 Philox bits (stream 1); a stable
+// radix sort groups each iteration (and sequence) and orders its tiles at random; block b moves to the
+// tile whose index equals its position inside the iteration.
+__global__ void permute_keys_kernel(uint64_t seed, int64_t iter0, int64_t n_iter, int64_t n_blocks, const int32_t *__restrict__ tile_seq,
+                                    int within, unsigned long long *__restrict__ keys, int32_t *__restrict__ vals) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_iter * n_blocks) return;
+    const int64_t r = i / n_blocks, b = i - r * n_blocks;
+    const Philox128 u = philox_draw(seed, (uint64_t)(iter0 + r), (uint32_t)b, 1u);
+    const unsigned long long chrom = within ? (unsigned long long)tile_seq[b] : 0ull;
+    keys[i] = ((unsigned long long)r << 52) | (chrom << 40) | (u.lo >> 24);
+    vals[i] = (int32_t)b;
+}
+__global__ void permute_scatter_kernel(const int32_t *__restrict__ sorted_vals, int64_t n_iter, int64_t n_blocks,
+                                       int32_t *__restrict__ dst_tile) {
+    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n_iter * n_blocks) return;
+    const int64_t r = p / n_blocks, q = p - r * n_blocks;
+    dst_tile[r * n_blocks + sorted_vals[p]] = (int32_t)q;
+}
 
 // ---- strand-class grouping of y for the rank path -----------------------------------------
 // virtual sequence of a range: seq * 3 + strand code

@@ -700,6 +700,38 @@ ORC_API int orc_plan_draw_philox(const orc_plan *p, uint64_t seed, uint64_t iter
             }
         }
         return 0;
+    case ORC_PERMUTE_WITHIN:
+    case ORC_PERMUTE_ACROSS: {
+        /* Production-mode image of sample(n) (R/bootUnsegmented.R:97, :156): every tile gets a 40-bit
+         * Philox key (stream 1); tiles are ranked by (sequence -- within-chromosome variant only --, key),
+         * ties by tile index; block b moves to the tile of its rank.  A uniformly random permutation
+         * up to key ties (probability ~ B^2 / 2^41 per iteration). */
+        typedef struct { uint64_t key; int32_t b; } pk;
+        pk *v = (pk *)malloc(sizeof(pk) * (size_t)(B ? B : 1));
+        for (int64_t b = 0; b < B; b++) {
+            philox_draw(seed, iter, (uint32_t)b, 1, &u0, &u1);
+            uint64_t chrom = p->kind == ORC_PERMUTE_WITHIN ? (uint64_t)p->tile_chrom[b] : 0;
+            v[b].key = (chrom << 40) | (u0 >> 24);
+            v[b].b = (int32_t)b;
+            bait_chrom[b] = p->tile_chrom[b];
+            bait_start[b] = p->tile_start[b];
+        }
+        /* stable insertion-free sort: merge sort by key, ties keep ascending b */
+        pk *tmp = (pk *)malloc(sizeof(pk) * (size_t)(B ? B : 1));
+        for (int64_t w = 1; w < B; w *= 2) {
+            for (int64_t lo = 0; lo < B; lo += 2 * w) {
+                int64_t mid = lo + w < B ? lo + w : B, hi = lo + 2 * w < B ? lo + 2 * w : B;
+                int64_t i = lo, j = mid, k = lo;
+                while (i < mid && j < hi) tmp[k++] = (v[j].key < v[i].key) ? v[j++] : v[i++];
+                while (i < mid) tmp[k++] = v[i++];
+                while (j < hi) tmp[k++] = v[j++];
+            }
+            pk *t = v; v = tmp; tmp = t;
+        }
+        for (int64_t q = 0; q < B; q++) dst_tile[v[q].b] = (int32_t)q;
+        free(v); free(tmp);
+        return 0;
+    }
     default:
         return orc_fail("philox draws: implemented for unsegmented (across/within) and "
                         "segmented proportionLength=TRUE bootstrap");

@@ -44,7 +44,7 @@ def test_counts_validation_mode(engine, kind, stranded, n_excl):
     _check_counts(engine, case, kind, R=6, seed=3, philox=False)
 
 
-@pytest.mark.parametrize("kind", [0, 1, 2])
+@pytest.mark.parametrize("kind", [0, 1, 2, 4, 5])
 @pytest.mark.parametrize("n_excl", [0, 25])
 def test_counts_philox_mode(engine, kind, n_excl):
     case = H.random_case(seed=20 + kind, n=700, n_seq=5, n_query=90, n_excl=n_excl, n_seg=15)
@@ -342,9 +342,10 @@ def test_error_behaviour(engine):
     engine.set_plan(_lib.UNSEG_ACROSS, 100)
     with pytest.raises(EngineError, match="out of range"):     # host draws are validated before they reach the device
         engine.run_counts(Draws(n_iter=1, rng_mode=_lib.RNG_HOST, bait_seqid=np.full((1, 18), 5, np.int32), bait_start=np.ones((1, 18), np.int32)))
-    engine.set_plan(_lib.PERMUTE_ACROSS, 100)
-    with pytest.raises(EngineError, match="host"):             # no device draws for the permutation variants
+    engine.set_plan(_lib.SEG_NOPROP, 100, {"seqid": [0, 1], "start": [1, 1], "end": [1000, 800], "state": [1, 2]})
+    with pytest.raises(EngineError, match="host"):             # no device draws for proportionLength = FALSE
         engine.run_counts(Draws(n_iter=1, rng_mode=_lib.RNG_PHILOX, seed=1))
+    engine.set_plan(_lib.PERMUTE_ACROSS, 100)
     with pytest.raises(EngineError, match="dst_tile"):
         engine.run_counts(Draws(n_iter=1, rng_mode=_lib.RNG_HOST, bait_seqid=np.zeros((1, 18), np.int32), bait_start=np.ones((1, 18), np.int32)))
     # front end: the reference's own checks
@@ -424,7 +425,7 @@ def test_fuzz_parity(engine, seed):
     got = engine.run_counts(draws)
     for k in ("iter_nranges", "iter_totals", "feature_counts"):
         assert np.array_equal(got[k], ref[k]), (k, kind, mode)
-    if kind < 3:
+    if kind != 3:
         ref = O.boot_counts(plan, y, qi, R, exclude=xi, exclude_mode=H.excl_mode(case), seed=seed, iter0=11)
         got = engine.run_counts(Draws(n_iter=R, rng_mode=_lib.RNG_PHILOX, seed=seed, iter0=11))
         for k in ("iter_nranges", "iter_totals", "feature_counts"):
