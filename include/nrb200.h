@@ -195,6 +195,10 @@ int nrb200_moments_fetch(nrb200_handle *h, int64_t *feat_sum, int64_t *feat_sums
 /* countOverlaps(x, y) on the ORIGINAL ranges (the observed statistic,
  * vignettes/bootRanges.Rmd:482-483). */
 int nrb200_count_observed(nrb200_handle *h, int32_t *feature_counts, int64_t *total);
+/* The same with countOverlaps(x, y, minoverlap = minoverlap): only intersections at least that wide count.
+ * With x = the tiles of the genome this is the counting step of segmentDensity()
+ * (R/segmentDensity.R:77: countOverlaps(query_accept, x, minoverlap = 8)).  Not combinable with maxgap. */
+int nrb200_count_observed_ex(nrb200_handle *h, int32_t minoverlap, int32_t *feature_counts, int64_t *total);
 
 /* ---- materialising path: the literal BootRanges table ------------------------------ */
 

@@ -10,6 +10,7 @@ from .bootranges import BootCounts, bootCounts, bootRanges
 from .engine import Draws, Engine, EngineError, get_engine
 from .granges import BootRanges, GRanges
 from .rrng import RRng, set_seed
+from .segment import countOverlaps, segmentTileCounts, tileGenome
 
 __all__ = ["GRanges", "BootRanges", "bootRanges", "bootCounts", "BootCounts", "set_seed", "RRng",
-           "Engine", "EngineError", "Draws", "get_engine"]
+           "Engine", "EngineError", "Draws", "get_engine", "countOverlaps", "segmentTileCounts", "tileGenome"]

@@ -64,6 +64,7 @@ SYMBOLS = [
     ("nrb200_run_moments", C.c_int, [vp, C.POINTER(Draws), C.c_int64, i32p, i64p, i64p, C.POINTER(Stats)]),
     ("nrb200_moments_fetch", C.c_int, [vp, i64p, i64p, i64p]),
     ("nrb200_count_observed", C.c_int, [vp, i32p, i64p]),
+    ("nrb200_count_observed_ex", C.c_int, [vp, C.c_int32, i32p, i64p]),
     ("nrb200_run_materialize", C.c_int, [vp, C.POINTER(Draws), i64p, C.POINTER(Stats)]),
     ("nrb200_fetch_rows", C.c_int, [vp, C.c_int64, C.c_int64, i32p, i32p, i32p, i32p, i32p]),
     ("nrb200_rrng_create", vp, [C.c_uint32]),

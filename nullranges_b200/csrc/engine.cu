@@ -106,6 +106,7 @@ struct nrb200_handle {
     std::vector<int64_t> seqlen;
     DevMem seqlen_dev;
 
+    int32_t query_widen = 0;  // maxgap + 1 of the stored query
     RangeSet y, query, excl, gaps;  // gaps = gaps(exclude) inside [1, seqlength], built for excludeOption "trim"
     int excl_option = NRB200_EXCLUDE_DROP;
     bool have_y = false, have_plan = false;
@@ -1187,7 +1188,7 @@ static int set_side(nrb200_handle *h, RangeSet &rs, const char *what, int64_t n,
 
 int nrb200_set_query(nrb200_handle *h, int64_t n, const int32_t *seqid, const int32_t *start, const int32_t *end,
                      const int8_t *strand) {
-    return set_side(h, h->query, "query", n, seqid, start, end, strand);
+    return nrb200_set_query_ex(h, n, seqid, start, end, strand, -1);
 }
 
 // maxgap: two ranges count as overlapping when at most `maxgap` positions separate them
@@ -1200,7 +1201,9 @@ int nrb200_set_query_ex(nrb200_handle *h, int64_t n, const int32_t *seqid, const
     if (!h) return NRB200_ERR_INVALID;
     if (maxgap < -1) return fail(h, NRB200_ERR_INVALID, "'maxgap' must be >= -1");
     if (maxgap >= (1 << 29)) return fail(h, NRB200_ERR_UNSUPPORTED, "'maxgap' must be below 2^29");
-    return set_side(h, h->query, "query", n, seqid, start, end, strand, maxgap + 1);
+    const int rc = set_side(h, h->query, "query", n, seqid, start, end, strand, maxgap + 1);
+    if (rc == NRB200_OK) h->query_widen = maxgap + 1;
+    return rc;
 }
 
 int nrb200_set_exclude(nrb200_handle *h, int64_t n, const int32_t *seqid, const int32_t *start, const int32_t *end,
@@ -1368,8 +1371,14 @@ int nrb200_moments_fetch(nrb200_handle *h, int64_t *feat_sum, int64_t *feat_sums
 }
 
 int nrb200_count_observed(nrb200_handle *h, int32_t *feature_counts, int64_t *total) {
+    return nrb200_count_observed_ex(h, 0, feature_counts, total);
+}
+
+int nrb200_count_observed_ex(nrb200_handle *h, int32_t minoverlap, int32_t *feature_counts, int64_t *total) {
     if (!h) return NRB200_ERR_INVALID;
     NRB_CUDA(h, cudaSetDevice(h->device));
+    if (minoverlap < 0) return fail(h, NRB200_ERR_INVALID, "'minoverlap' must be >= 0");
+    if (minoverlap > 0 && h->query_widen > 0) return fail(h, NRB200_ERR_INVALID, "'maxgap' and 'minoverlap' cannot both be set");
     if (!h->have_y) return fail(h, NRB200_ERR_STATE, "nrb200_set_ranges() has not been called");
     if (h->query.n == 0) return fail(h, NRB200_ERR_STATE, "nrb200_set_query() has not been called");
     {
@@ -1393,11 +1402,11 @@ int nrb200_count_observed(nrb200_handle *h, int32_t *feature_counts, int64_t *to
         if (y.stranded && q.stranded)
             count_observed_kernel<true><<<grid, threads, 0, h->stream>>>(yv, y.n, y.seqid.as<int32_t>(), q.start.as<int32_t>(),
                 q.end.as<int32_t>(), q.pmax.as<int32_t>(), q.strand.as<int8_t>(), q.src.as<int32_t>(), q.seq_off.as<int32_t>(),
-                counts.as<int32_t>(), tot.as<unsigned long long>());
+                minoverlap, counts.as<int32_t>(), tot.as<unsigned long long>());
         else
             count_observed_kernel<false><<<grid, threads, 0, h->stream>>>(yv, y.n, y.seqid.as<int32_t>(), q.start.as<int32_t>(),
                 q.end.as<int32_t>(), q.pmax.as<int32_t>(), nullptr, q.src.as<int32_t>(), q.seq_off.as<int32_t>(),
-                counts.as<int32_t>(), tot.as<unsigned long long>());
+                minoverlap, counts.as<int32_t>(), tot.as<unsigned long long>());
         NRB_CUDA(h, cudaGetLastError());
     }
     unsigned long long t = 0;

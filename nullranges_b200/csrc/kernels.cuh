@@ -920,7 +920,7 @@ __global__ void count_observed_kernel(const RangesView y, int64_t n, const int32
                                       const int32_t *__restrict__ q_start, const int32_t *__restrict__ q_end,
                                       const int32_t *__restrict__ q_pmax, const int8_t *__restrict__ q_strand,
                                       const int32_t *__restrict__ q_src, const int32_t *__restrict__ q_seq_off,
-                                      int32_t *__restrict__ counts, unsigned long long *__restrict__ total) {
+                                      int32_t minoverlap, int32_t *__restrict__ counts, unsigned long long *__restrict__ total) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     int found = 0;
     if (i < n) {
@@ -929,10 +929,10 @@ __global__ void count_observed_kernel(const RangesView y, int64_t n, const int32
         const int strand = (STRANDED && y.strand) ? y.strand[i] : 0;
         const int32_t a = q_seq_off[c];
         for (int32_t k = first_gt(q_start, a, q_seq_off[c + 1], e) - 1; k >= a && q_pmax[k] >= s; --k) {
-            if (q_end[k] >= s && (!STRANDED || !q_strand || strands_match(strand, q_strand[k]))) {
-                ++found;
-                atomicAdd(counts + q_src[k], 1);
-            }
+            if (q_end[k] < s || (STRANDED && q_strand && !strands_match(strand, q_strand[k]))) continue;
+            if (minoverlap > 0 && min(e, q_end[k]) - max(s, q_start[k]) + 1 < minoverlap) continue;  // width of the intersection
+            ++found;
+            atomicAdd(counts + q_src[k], 1);
         }
     }
     found = __reduce_add_sync(kFull, found);

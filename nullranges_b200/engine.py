@@ -169,10 +169,11 @@ class Engine:
         self._check(self._lib.nrb200_moments_fetch(self._h, ptr(s, C.c_int64), ptr(q, C.c_int64), ptr(ge, C.c_int64)))
         return {"iter_nranges": nr, "iter_totals": tot, "sum": s, "sumsq": q, "n_ge_observed": ge, "stats": st.as_dict()}
 
-    def count_observed(self):
+    def count_observed(self, minoverlap: int = 0):
+        """countOverlaps(query, y[, minoverlap]) on the ranges as given (no bootstrap)."""
         cnt = np.zeros(self.n_query, np.int32)
         tot = C.c_int64()
-        self._check(self._lib.nrb200_count_observed(self._h, ptr(cnt, C.c_int32), C.byref(tot)))
+        self._check(self._lib.nrb200_count_observed_ex(self._h, int(minoverlap), ptr(cnt, C.c_int32), C.byref(tot)))
         return cnt, tot.value
 
     # ---- materialising

@@ -752,6 +752,7 @@ typedef struct orc_index {
     int32_t *wmax;        /* [C] largest width */
     int ord_is_identity;
     int64_t slack;        /* as a countOverlaps() query: maxgap + 1 (0 = plain overlap, maxgap = -1) */
+    int64_t minoverlap;   /* as a countOverlaps() query: smallest intersection width that counts (0 = any) */
 } orc_index;
 
 static const orc_index *g_sort_ix;
@@ -811,6 +812,9 @@ ORC_API orc_index *orc_index_new(int64_t n, int C, const int32_t *chrom, const i
  * count as overlapping when the gap between them is <= m (adjacent ranges have gap 0; overlapping
  * ranges -1), i.e. start_q <= end_s + m + 1 and end_q >= start_s - m - 1. */
 ORC_API void orc_index_set_maxgap(orc_index *ix, int64_t maxgap) { ix->slack = maxgap < -1 ? 0 : maxgap + 1; }
+/* countOverlaps(x, y, minoverlap = k): the intersection must be at least k wide
+ * (R/segmentDensity.R:77 counts ranges per genome tile with minoverlap = 8). */
+ORC_API void orc_index_set_minoverlap(orc_index *ix, int64_t k) { ix->minoverlap = k < 0 ? 0 : k; }
 
 /* #{k in [lo,hi) : start[ord[k]] <= x} + lo */
 static int64_t upper_start(const orc_index *ix, int64_t lo, int64_t hi, int64_t x) {
@@ -853,6 +857,10 @@ static int64_t count_into(const orc_index *q, int c, int64_t s, int64_t e, int s
         int32_t id = q->ord[k];
         if ((int64_t)q->end[id] >= s - m1 &&
             strand_compatible(strand, q->strand ? q->strand[id] : 0)) {
+            if (q->minoverlap > 0) {
+                int64_t lo2 = s > q->start[id] ? s : q->start[id], hi2 = e < q->end[id] ? e : q->end[id];
+                if (hi2 - lo2 + 1 < q->minoverlap) continue;
+            }
             n++;
             if (counts) counts[id]++;
         }

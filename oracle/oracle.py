@@ -65,6 +65,7 @@ def lib():
     L.orc_index_new.argtypes = [C.c_int64, C.c_int, i32p, i32p, i32p, i8p]
     L.orc_index_free.argtypes = [vp]
     L.orc_index_set_maxgap.argtypes = [vp, C.c_int64]
+    L.orc_index_set_minoverlap.argtypes = [vp, C.c_int64]
     L.orc_iteration_rows.restype = C.c_int64
     L.orc_iteration_rows.argtypes = [vp, vp, vp, C.c_int, i32p, i32p, i32p, C.c_int64, i32p, i32p, i32p, i32p, i32p]
     L.orc_count_overlaps.restype = C.c_int64
@@ -193,8 +194,8 @@ class Plan:
 class Index:
     """A set of ranges (y, exclude or query) with its per-chromosome overlap index."""
 
-    def __init__(self, n_chrom: int, chrom, start, end, strand=None, maxgap: int = -1):
-        """maxgap: only meaningful for a query index -- countOverlaps(x, boots, maxgap = maxgap)."""
+    def __init__(self, n_chrom: int, chrom, start, end, strand=None, maxgap: int = -1, minoverlap: int = 0):
+        """maxgap / minoverlap: only meaningful for a query index -- countOverlaps(x, boots, maxgap=, minoverlap=)."""
         self.chrom, self.start, self.end = _i32(chrom), _i32(start), _i32(end)
         self.strand = None if strand is None else np.ascontiguousarray(strand, dtype=np.int8)
         self.n = self.chrom.size
@@ -204,6 +205,8 @@ class Index:
             raise ValueError(_err())
         if maxgap != -1:
             lib().orc_index_set_maxgap(self._h, int(maxgap))
+        if minoverlap:
+            lib().orc_index_set_minoverlap(self._h, int(minoverlap))
 
     def __del__(self):
         if getattr(self, "_h", None):

@@ -436,3 +436,34 @@ def test_fuzz_parity(engine, seed):
     want = H.oracle_rows(plan, y, xi, d, R, mode=H.excl_mode(case))
     key = lambda a: a[np.lexsort((a[:, 2], a[:, 4], a[:, 5], a[:, 0]))] if a.size else a
     assert np.array_equal(key(got_rows), key(want)), (kind, mode)
+
+
+def test_count_overlaps_and_segment_tile_counts(engine):
+    """countOverlaps(query, subject, maxgap / minoverlap) on plain ranges and the tile counts of
+    segmentDensity() (R/segmentDensity.R:53-78, roxygen example data) against the oracle."""
+    from nullranges_b200 import GRanges, countOverlaps, segmentTileCounts
+    rng = np.random.default_rng(1)
+    n = 10_000                                                     # R/segmentDensity.R:40-47
+    st = np.rint(np.concatenate([rng.uniform(1, 991, n // 4), rng.uniform(1001, 3991, n // 4),
+                                 rng.uniform(4001, 4991, n // 4), rng.uniform(7001, 9991, n // 4)])).astype(np.int64)
+    gr = GRanges(["chr1"] * n, np.sort(st), width=np.full(n, 10), seqlengths={"chr1": 10_000})
+    exclude = GRanges(["chr1"], [5001], end=[6000], seqlengths={"chr1": 10_000})
+    tiles, raw, std = segmentTileCounts(gr, L_s=100, exclude=exclude)
+    assert len(tiles) == 90 and not np.any((tiles.start <= 6000) & (tiles.end >= 5001))
+    qi = O.Index(1, tiles.seqid, tiles.start, tiles.end, minoverlap=8)
+    want, _ = O.count_overlaps(qi, gr.seqid, gr.start, gr.end)
+    assert np.array_equal(raw, want) and np.allclose(std, want / tiles.width * 100)
+    plain = countOverlaps(tiles, gr)
+    assert np.all(plain >= raw) and plain.sum() > raw.sum()          # minoverlap = 8 drops the shallow overlaps
+    # random stranded ranges, each option
+    case = H.random_case(seed=77, n=2000, n_seq=3, n_query=150, stranded=True, wmax=80)
+    names = np.array(["a", "b", "c"])
+    sl = {k: int(v) for k, v in zip(names, case["seqlen"])}
+    y = GRanges(names[case["y"][0]], case["y"][1], end=case["y"][2], strand=case["y"][3], seqlengths=sl)
+    q = GRanges(names[case["query"][0]], case["query"][1], end=case["query"][2], strand=case["query"][3], seqlengths=sl)
+    for kw in ({}, {"maxgap": 25}, {"minoverlap": 12}):
+        qi = O.Index(3, q.seqid, q.start, q.end, q.strand, **kw)
+        want, _ = O.count_overlaps(qi, y.seqid, y.start, y.end, y.strand)
+        assert np.array_equal(countOverlaps(q, y, **kw), want), kw
+    with pytest.raises(ValueError):
+        countOverlaps(q, y, maxgap=3, minoverlap=2)

@@ -131,3 +131,14 @@ def test_maxgap_matches_gap_definition():
         gap = np.maximum(qs[:, None] - re_[None, :], rs[None, :] - qe[:, None]) - 1
         want = (np.maximum(gap, -1) <= m).sum(axis=1)
         assert np.array_equal(cnt, want) and tot == want.sum()
+
+
+def test_minoverlap_matches_definition():
+    rng = np.random.default_rng(4)
+    qs = rng.integers(1, 900, 40); qe = qs + rng.integers(0, 60, 40)
+    rs = rng.integers(1, 900, 300); re_ = rs + rng.integers(0, 30, 300)
+    for k in (1, 8, 20):
+        q = O.Index(1, np.zeros(40, np.int32), qs, qe, minoverlap=k)
+        cnt, _ = O.count_overlaps(q, np.zeros(300, np.int32), rs, re_)
+        width = np.minimum(qe[:, None], re_[None, :]) - np.maximum(qs[:, None], rs[None, :]) + 1
+        assert np.array_equal(cnt, (width >= k).sum(axis=1))
