@@ -136,7 +136,8 @@ int nrb200_get_tiles(const nrb200_handle *h, int32_t *tile_seqid, int32_t *tile_
 #define NRB200_RNG_PHILOX 1 /* production mode: Philox4x32-10 on the device, counter =
                                (global iteration, block), key = seed.  Bootstrap samplers: the block's
                                source; permute variants: a random permutation of the tiles per iteration
-                               (40-bit keys, device radix sort).  Not for NRB200_SEG_NOPROP. */
+                               (40-bit keys, device radix sort); proportionLength = FALSE: global draws,
+                               per-state compaction and resampling, all on the device. */
 
 typedef struct nrb200_draws {
     int64_t n_iter;            /* R */

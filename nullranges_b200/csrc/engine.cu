@@ -133,7 +133,7 @@ struct nrb200_handle {
     bool tiles_in_bounds = false;
 
     // run scratch / results
-    DevMem d_bait_seq, d_bait_start, d_dst_tile, perm_vals_a, perm_vals_b;
+    DevMem d_bait_seq, d_bait_start, d_dst_tile, perm_vals_a, perm_vals_b, np_seg, np_start, np_state, np_list, np_cnt;
     DevMem d_iter_nranges, d_iter_totals, d_counts, d_n_hits;
     bool res_has_counts = false;
     // moments
@@ -780,10 +780,34 @@ int stage_draws(nrb200_handle *h, const nrb200_draws *d) {
     const Plan &p = h->plan;
     const int64_t B = p.n_blocks();
     if (d->rng_mode == NRB200_RNG_PHILOX) {
-        if (p.kind == NRB200_SEG_NOPROP)
-            return fail(h, NRB200_ERR_UNSUPPORTED,
-                        "device Philox draws cover every sampler except proportionLength=FALSE; "
-                        "draw that one on the host (NRB200_RNG_HOST)");
+        if (p.kind == NRB200_SEG_NOPROP) {
+            // proportionLength = FALSE: the draws are made on the device into the tables host mode would upload
+            const int64_t R = d->n_iter, items = R * B;
+            const int S = p.n_states;
+            if (S > 127) return fail(h, NRB200_ERR_UNSUPPORTED, "device draws for proportionLength=FALSE support at most 127 states");
+            for (DevMem *m : {&h->d_bait_seq, &h->d_bait_start, &h->np_seg, &h->np_start, &h->np_list})
+                NRB_CUDA(h, m->reserve((size_t)std::max<int64_t>(items, 1) * 4));
+            NRB_CUDA(h, h->np_state.reserve((size_t)std::max<int64_t>(items, 1)));
+            NRB_CUDA(h, h->np_cnt.reserve((size_t)std::max<int64_t>(R, 1) * (S + 1) * 4 + 4));
+            if (items == 0) return NRB200_OK;
+            int *err = h->np_cnt.as<int>() + R * (S + 1);
+            NRB_CUDA(h, cudaMemsetAsync(err, 0, 4, h->stream));
+            const unsigned grid = (unsigned)((items + 255) / 256);
+            noprop_draw_kernel<<<grid, 256, 0, h->stream>>>(h->sampler_view, d->seed, d->iter0, R, B, h->np_seg.as<int32_t>(),
+                                                             h->np_start.as<int32_t>(), h->np_state.as<int8_t>());
+            noprop_lists_kernel<<<(unsigned)R, 256, 0, h->stream>>>(S, B, h->np_state.as<int8_t>(), h->np_list.as<int32_t>(),
+                                                                    h->np_cnt.as<int32_t>());
+            noprop_assign_kernel<<<grid, 256, 0, h->stream>>>(h->sampler_view, d->seed, d->iter0, R, B, h->np_seg.as<int32_t>(),
+                                                               h->np_start.as<int32_t>(), h->np_list.as<int32_t>(), h->np_cnt.as<int32_t>(),
+                                                               h->d_bait_seq.as<int32_t>(), h->d_bait_start.as<int32_t>(), err);
+            NRB_CUDA(h, cudaGetLastError());
+            int flag = 0;
+            NRB_CUDA(h, cudaMemcpyAsync(&flag, err, 4, cudaMemcpyDeviceToHost, h->stream));
+            if (int rc_sync = sync_stream(h)) return rc_sync;
+            // the reference stops here too: length(rearranged_blocks_start) == length(random_blocks_start) fails (R/bootRanges.R:303)
+            if (flag) return fail(h, NRB200_ERR_INVALID, "seg_bootstrap_noprop: a state drew no segments in some iteration");
+            return NRB200_OK;
+        }
         if (!p.permute()) return NRB200_OK;
         // permute variants: one random permutation of the tiles per iteration, made on the device
         if (h->n_seq > 4096) return fail(h, NRB200_ERR_UNSUPPORTED, "device permutations support at most 4096 sequences");
@@ -876,13 +900,15 @@ BootParams make_params(nrb200_handle *h, const nrb200_draws *d) {
     P.seqlen = h->seqlen_dev.as<int64_t>();
     P.permute = h->plan.permute();
     P.drop_zero = h->plan.drop_zero_width();
-    P.rng_mode = d->rng_mode;
+    // proportionLength = FALSE in production mode: stage_draws() filled the host-mode tables on the device
+    const bool noprop_dev = d->rng_mode == NRB200_RNG_PHILOX && h->plan.kind == NRB200_SEG_NOPROP;
+    P.rng_mode = noprop_dev ? NRB200_RNG_HOST : d->rng_mode;
     P.seed = d->seed;
     P.iter0 = d->iter0;
-    if (d->rng_mode == NRB200_RNG_HOST) {
+    if (d->rng_mode == NRB200_RNG_HOST || noprop_dev) {
         P.bait_seq = h->d_bait_seq.as<int32_t>();
         P.bait_start = h->d_bait_start.as<int32_t>();
-        P.dst_tile = d->dst_tile ? h->d_dst_tile.as<int32_t>() : nullptr;
+        P.dst_tile = (!noprop_dev && d->dst_tile) ? h->d_dst_tile.as<int32_t>() : nullptr;
     } else if (h->plan.permute()) {
         P.dst_tile = h->d_dst_tile.as<int32_t>();  // made by stage_draws() on the device
     }

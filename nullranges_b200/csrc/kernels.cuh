@@ -851,6 +851,94 @@ __global__ void permute_scatter_kernel(const int32_t *__restrict__ sorted_vals, 
     dst_tile[r * n_blocks + sorted_vals[p]] = (int32_t)q;
 }
 
+// ---- device-side draws for proportionLength = FALSE (production mode) ----------------------
+// Image of seg_bootstrap_noprop (R/bootRanges.R:256-331), three steps per batch of iterations:
+// (1) B global draws: segment in proportion to width (states in order, segments in seg order inside a
+// state), start round(U(start_j, start_j + (tiles_j - 1) L_b)); (2) per iteration, the draws of each state
+// in draw order (stable compaction, one CTA per iteration); (3) tile k of state s takes the k-th draw of
+// its state when there are enough, else draw number floor(U * rand_n) (the image of
+// sample(rand_n, rearr_n, replace = TRUE)); a state without draws raises the error flag.
+__global__ void noprop_draw_kernel(const SamplerView S, uint64_t seed, int64_t iter0, int64_t n_iter, int64_t n_blocks,
+                                   int32_t *__restrict__ dseg, int32_t *__restrict__ dstart, int8_t *__restrict__ dstate) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_iter * n_blocks) return;
+    const int64_t r = t / n_blocks, i = t - r * n_blocks;
+    const Philox128 u = philox_draw(seed, (uint64_t)(iter0 + r), (uint32_t)i, 0u);
+    int64_t total = 0;
+    for (int st = 1; st <= S.n_states; ++st) total += S.state_len[st];
+    int64_t pos = (int64_t)mul_hi_u64(u.lo, (uint64_t)total);
+    int st = 1;
+    while (st < S.n_states && pos >= S.state_len[st]) pos -= S.state_len[st++];
+    const int64_t first = S.state_seg_off[st];
+    const int n = (int)(S.state_seg_off[st + 1] - first);
+    const int64_t j = first + pick_by_length(S.sg_cum + first, n, pos);
+    dseg[t] = (int32_t)j;
+    dstart[t] = (int32_t)rounded_uniform(u.hi, S.sg_start[j], (int64_t)(S.sg_tiles[j] - 1) * S.block_length);
+    dstate[t] = (int8_t)st;
+}
+
+// one CTA per iteration: list[r][.] = draw indices grouped by state (ascending inside a state), cnt[r][s]
+__global__ void __launch_bounds__(256) noprop_lists_kernel(int n_states, int64_t n_blocks, const int8_t *__restrict__ dstate,
+                                                           int32_t *__restrict__ list, int32_t *__restrict__ cnt) {
+    __shared__ int warp_sums[8];
+    __shared__ int carry;
+    const int64_t r = blockIdx.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (int st = 1; st <= n_states; ++st) {
+        const int begin = carry;
+        __syncthreads();
+        for (int64_t base = 0; base < n_blocks; base += blockDim.x) {
+            const int64_t i = base + threadIdx.x;
+            const int v = (i < n_blocks && dstate[r * n_blocks + i] == st) ? 1 : 0;
+            int x = v;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const int t = __shfl_up_sync(kFull, x, d);
+                if (lane >= d) x += t;
+            }
+            if (lane == 31) warp_sums[warp] = x;
+            __syncthreads();
+            int before = carry;
+            for (int w = 0; w < warp; ++w) before += warp_sums[w];
+            if (v) list[r * n_blocks + before + x - 1] = (int32_t)i;
+            __syncthreads();
+            if (threadIdx.x == blockDim.x - 1) carry = before + x;
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) cnt[r * (n_states + 1) + st] = carry - begin;
+        __syncthreads();
+    }
+}
+
+__global__ void noprop_assign_kernel(const SamplerView S, uint64_t seed, int64_t iter0, int64_t n_iter, int64_t n_blocks,
+                                     const int32_t *__restrict__ dseg, const int32_t *__restrict__ dstart,
+                                     const int32_t *__restrict__ list, const int32_t *__restrict__ cnt,
+                                     int32_t *__restrict__ bait_seq, int32_t *__restrict__ bait_start, int *__restrict__ err) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_iter * n_blocks) return;
+    const int64_t r = t / n_blocks, b = t - r * n_blocks;
+    int st = 1;
+    while (st < S.n_states && b >= S.state_block_off[st + 1]) ++st;
+    const int64_t k = b - S.state_block_off[st], rearr_n = S.state_block_off[st + 1] - S.state_block_off[st];
+    const int32_t *c = cnt + r * (S.n_states + 1);
+    int64_t off = 0;
+    for (int s2 = 1; s2 < st; ++s2) off += c[s2];
+    const int64_t rand_n = c[st];
+    if (rand_n == 0) {
+        atomicExch(err, 1);
+        bait_seq[t] = 0;
+        bait_start[t] = 1;
+        return;
+    }
+    int64_t m = k;
+    if (rand_n < rearr_n) m = (int64_t)mul_hi_u64(philox_draw(seed, (uint64_t)(iter0 + r), (uint32_t)b, 2u).lo, (uint64_t)rand_n);
+    const int32_t i = list[r * n_blocks + off + m];
+    bait_seq[t] = S.sg_seq[dseg[r * n_blocks + i]];
+    bait_start[t] = dstart[r * n_blocks + i];
+}
+
 // ---- strand-class grouping of y for the rank path -----------------------------------------
 // virtual sequence of a range: seq * 3 + strand code
 __global__ void vseq_keys_kernel(const int32_t *__restrict__ seqid, const int8_t *__restrict__ strand, int64_t n,

@@ -700,6 +700,54 @@ ORC_API int orc_plan_draw_philox(const orc_plan *p, uint64_t seed, uint64_t iter
             }
         }
         return 0;
+    case ORC_SEG_NOPROP: {
+        /* Production-mode image of seg_bootstrap_noprop (R/bootRanges.R:256-331).  Draw i of the B global
+         * draws (counter i, stream 0) picks a segment in proportion to its width -- segments taken state by
+         * state, in seg order inside a state -- and a start round(U(start_j, start_j + (nblk_j - 1) L_b)).
+         * State s then owns the draws that fell on its segments, in draw order; its k-th tile takes the k-th
+         * of them when there are enough (:297-301), else draw number floor(U * rand_n) with U from counter
+         * (tile, stream 2) -- the image of sample(rand_n, rearr_n, replace = TRUE) (:295-296).  A state
+         * without any draw is an error, as in the reference (:303). */
+        int64_t L_tot = 0;
+        for (int j = 0; j < p->nseg; j++) L_tot += (int64_t)p->seg_end[j] - p->seg_start[j] + 1;
+        int32_t *d_seg = (int32_t *)malloc(sizeof(int32_t) * (size_t)(B ? B : 1));
+        int32_t *d_start = (int32_t *)malloc(sizeof(int32_t) * (size_t)(B ? B : 1));
+        for (int64_t i = 0; i < B; i++) {
+            philox_draw(seed, iter, (uint32_t)i, 0, &u0, &u1);
+            int64_t pos = (int64_t)mulhi64(u0, (uint64_t)L_tot), cum = 0;
+            int64_t t = 0;
+            for (;; t++) { /* walk state_segs: state-major, seg order inside a state */
+                int j = p->state_segs[t];
+                int64_t w = (int64_t)p->seg_end[j] - p->seg_start[j] + 1;
+                if (t == p->nseg - 1 || pos < cum + w) break;
+                cum += w;
+            }
+            int j = p->state_segs[t];
+            d_seg[i] = j;
+            d_start[i] = (int32_t)philox_round_unif(u1, p->seg_start[j], (p->seg_nblk[j] - 1) * p->L_b);
+        }
+        int32_t *list = (int32_t *)malloc(sizeof(int32_t) * (size_t)(B ? B : 1));
+        int rc = 0;
+        for (int s = 1; s <= p->S && !rc; s++) {
+            int64_t rand_n = 0;
+            for (int64_t i = 0; i < B; i++)
+                if (p->seg_state[d_seg[i]] == s) list[rand_n++] = (int32_t)i;
+            int64_t rearr_n = p->state_off[s + 1] - p->state_off[s];
+            if (rand_n == 0 && rearr_n > 0) { rc = orc_fail("seg_bootstrap_noprop: a state drew no segments (reference fails: length(random) != length(rearranged))"); break; }
+            for (int64_t k = 0; k < rearr_n; k++) {
+                int64_t b = p->state_off[s] + k, m = k;
+                if (rand_n < rearr_n) {
+                    philox_draw(seed, iter, (uint32_t)b, 2, &u0, &u1);
+                    m = (int64_t)mulhi64(u0, (uint64_t)rand_n);
+                }
+                int32_t i = list[m];
+                bait_chrom[b] = p->seg_chrom[d_seg[i]];
+                bait_start[b] = d_start[i];
+            }
+        }
+        free(d_seg); free(d_start); free(list);
+        return rc;
+    }
     case ORC_PERMUTE_WITHIN:
     case ORC_PERMUTE_ACROSS: {
         /* Production-mode image of sample(n) (R/bootUnsegmented.R:97, :156): every tile gets a 40-bit
@@ -1016,6 +1064,7 @@ typedef struct {
     const int32_t *bait_chrom, *bait_start, *dst_tile;
     int64_t *iter_nranges, *iter_totals; int32_t *feature_counts;
     int64_t next; int err; pthread_mutex_t mu;
+    char errmsg[256];
 } orc_job;
 
 static void *orc_worker(void *arg) {
@@ -1036,7 +1085,13 @@ static void *orc_worker(void *arg) {
         if (r >= j->R) break;
         const int32_t *pc, *ps, *pd;
         if (j->rng_mode == 1) {
-            if (orc_plan_draw_philox(p, j->seed, j->iter0 + (uint64_t)r, bc, bs, dt)) { j->err = 1; continue; }
+            if (orc_plan_draw_philox(p, j->seed, j->iter0 + (uint64_t)r, bc, bs, dt)) {
+                pthread_mutex_lock(&j->mu);  /* the message lives in this thread's buffer: hand it to the caller */
+                if (!j->err) snprintf(j->errmsg, sizeof j->errmsg, "%.250s", orc_errbuf);
+                j->err = 1;
+                pthread_mutex_unlock(&j->mu);
+                continue;
+            }
             pc = bc; ps = bs; pd = dt;
         } else {
             pc = j->bait_chrom + r * B; ps = j->bait_start + r * B; pd = j->dst_tile + r * B;
@@ -1060,7 +1115,7 @@ ORC_API int orc_boot_counts(const orc_plan *p, const orc_index *y, const orc_ind
                             int64_t *iter_nranges, int64_t *iter_totals,
                             int32_t *feature_counts, int nthreads) {
     orc_job j = {p, y, excl, query, excl_mode, R, rng_mode, seed, iter0, bait_chrom, bait_start, dst_tile,
-                 iter_nranges, iter_totals, feature_counts, 0, 0, PTHREAD_MUTEX_INITIALIZER};
+                 iter_nranges, iter_totals, feature_counts, 0, 0, PTHREAD_MUTEX_INITIALIZER, {0}};
     if (nthreads < 1) nthreads = 1;
     if (nthreads > 256) nthreads = 256;
     if (nthreads == 1) {
@@ -1070,7 +1125,7 @@ ORC_API int orc_boot_counts(const orc_plan *p, const orc_index *y, const orc_ind
         for (int t = 0; t < nthreads; t++) pthread_create(&th[t], NULL, orc_worker, &j);
         for (int t = 0; t < nthreads; t++) pthread_join(th[t], NULL);
     }
-    if (j.err) return orc_fail("philox draws unsupported for this plan kind");
+    if (j.err) return orc_fail(j.errmsg);
     return 0;
 }
 
