@@ -71,7 +71,7 @@ struct DevMem {
 struct RangeSet {
     int64_t n = 0;
     bool stranded = false;
-    int32_t wmax = 0;
+    int32_t wmax = 0, wmin = 0;
     std::vector<int32_t> h_start, h_end, h_pmax, h_src, h_seq_off;  // host mirror (kept for query/exclude)
     std::vector<int8_t> h_strand;
     std::vector<int32_t> max_end;  // [n_seq] largest end on the sequence (INT32_MIN when empty)
@@ -116,6 +116,8 @@ struct nrb200_handle {
     DevMem inspect_dev, seq_info_dev, draw_tab;
     // stranded y only: class-major copy for the rank path (kernels.cuh, RangesView)
     int n_cls = 1;
+    int32_t end_shift = 0;
+    bool ends_alias_starts = false;
     DevMem r_start, r_end, r_pmax, r_order, r_idx, r_keys_a, r_keys_b, r_voff_dev, rseq_info_dev, rrank_off_dev, rrank_start;
     DevMem rank_off_dev, max_pos_dev, rank_start, rank_pmax, rank_end, end_sorted, sort_keys_a, sort_keys_b, sort_tmp;
     uint32_t flags = 0;
@@ -123,6 +125,8 @@ struct nrb200_handle {
     // kernel, NRB200_MINB its min CTAs/SM, NRB200_TABLE_MULT rank-table entries per range
     int tune_rpt = 1, tune_minb = 1;
     double tune_table_mult = 4.0;
+    int64_t tune_max_batch = 2048;     // NRB200_MAX_BATCH: iterations per launch group
+    int64_t tune_table_cap = 8 << 20;  // NRB200_TABLE_CAP: the multiplier applies up to this many entries
 
     Plan plan;
     DevMem tile_seq, tile_start, bait_width, sampler_i64, sampler_i32;
@@ -235,7 +239,7 @@ int load_range_set(nrb200_handle *h, RangeSet &rs, const char *what, int64_t n, 
     if (n > 0 && (!seqid || !start || !end)) return fail(h, NRB200_ERR_INVALID, std::string(what) + ": null coordinate pointer");
     const int C = h->n_seq;
     bool sorted = true, stranded = false;
-    int32_t wmax = 0;
+    int32_t wmax = 0, wmin = INT32_MAX;
     for (int64_t i = 0; i < n; ++i) {
         if (seqid[i] < 0 || seqid[i] >= C) return fail(h, NRB200_ERR_INVALID, std::string(what) + ": seqname not in seqlevels(y)");
         if (start[i] < 1) return fail(h, NRB200_ERR_UNSUPPORTED, std::string(what) + ": ranges must start at position >= 1");
@@ -246,6 +250,7 @@ int load_range_set(nrb200_handle *h, RangeSet &rs, const char *what, int64_t n, 
             stranded |= strand[i] != 0;
         }
         wmax = std::max(wmax, end[i] - start[i] + 1);
+        wmin = std::min(wmin, end[i] - start[i] + 1);
         if (i > 0) {
             const int64_t j = i - 1;
             if (seqid[i] < seqid[j] || (seqid[i] == seqid[j] && (start[i] < start[j] || (start[i] == start[j] && end[i] < end[j]))))
@@ -255,6 +260,7 @@ int load_range_set(nrb200_handle *h, RangeSet &rs, const char *what, int64_t n, 
     rs.n = n;
     rs.stranded = stranded;
     rs.wmax = wmax;
+    rs.wmin = n ? wmin : 0;
     rs.h_src.resize(n);
     std::iota(rs.h_src.begin(), rs.h_src.end(), 0);
     if (!sorted)
@@ -315,18 +321,20 @@ int load_y_device(nrb200_handle *h, int64_t n, const int32_t *seqid, const int32
     if (strand && (rc = upload_direct(h, y.strand, strand, (size_t)n))) return rc;
     Trace tr("load_y_device");
     tr.lap("enqueue_h2d");
-    // scratch: InspectOut | seq_count[C] | seq_max_end[C]
-    const size_t words = 4 + 2 * (size_t)C;
+    // scratch: InspectOut (5 words, padded to 8) | seq_count[C] | seq_max_end[C]
+    const size_t kHead = 8;
+    const size_t words = kHead + 2 * (size_t)C;
     NRB_CUDA(h, h->inspect_dev.reserve(words * 4));
     std::vector<int32_t> init(words, 0);
-    for (int c = 0; c < C; ++c) init[4 + C + c] = INT32_MIN;
+    init[4] = INT32_MAX;  // wmin
+    for (int c = 0; c < C; ++c) init[kHead + C + c] = INT32_MIN;
     NRB_CUDA(h, cudaMemcpyAsync(h->inspect_dev.p, init.data(), words * 4, cudaMemcpyHostToDevice, h->stream));
     int32_t *base = h->inspect_dev.as<int32_t>();
     const unsigned grid = (unsigned)std::min<int64_t>((n + 255) / 256, (int64_t)h->sm_count * 8);
     inspect_ranges_kernel<<<grid, 256, 0, h->stream>>>(y.seqid.as<int32_t>(), y.start.as<int32_t>(), y.end.as<int32_t>(),
                                                        strand ? y.strand.as<int8_t>() : nullptr, n, C,
-                                                       reinterpret_cast<InspectOut *>(base), reinterpret_cast<unsigned *>(base + 4),
-                                                       base + 4 + C);
+                                                       reinterpret_cast<InspectOut *>(base), reinterpret_cast<unsigned *>(base + kHead),
+                                                       base + kHead + C);
     NRB_CUDA(h, cudaGetLastError());
     std::vector<int32_t> res(words);
     NRB_CUDA(h, cudaMemcpyAsync(res.data(), base, words * 4, cudaMemcpyDeviceToHost, h->stream));
@@ -337,11 +345,12 @@ int load_y_device(nrb200_handle *h, int64_t n, const int32_t *seqid, const int32
     y.sorted_input = true;
     y.stranded = res[2] != 0;
     y.wmax = res[3];
+    y.wmin = res[4];
     y.h_seq_off.assign(C + 1, 0);
     y.max_end.assign(C, INT32_MIN);
     for (int c = 0; c < C; ++c) {
-        y.h_seq_off[c + 1] = y.h_seq_off[c] + res[4 + c];
-        y.max_end[c] = res[4 + C + c];
+        y.h_seq_off[c + 1] = y.h_seq_off[c] + res[kHead + c];
+        y.max_end[c] = res[kHead + C + c];
     }
     if ((rc = upload(h, y.seq_off, y.h_seq_off.data(), (size_t)C + 1))) return rc;
     NRB_CUDA(h, y.pmax.reserve(n * 4));  // src stays unset: identity (kernels take nullptr for it)
@@ -369,7 +378,7 @@ int build_rank_tables(nrb200_handle *h) {
         genome += max_pos[c];
     }
     int shift = 0;
-    const int64_t want = std::max<int64_t>(std::min<int64_t>((int64_t)(h->tune_table_mult * y.n), std::max<int64_t>(y.n, 8 << 20)), 1024);
+    const int64_t want = std::max<int64_t>(std::min<int64_t>((int64_t)(h->tune_table_mult * y.n), std::max<int64_t>(y.n, h->tune_table_cap)), 1024);
     while (shift < 30 && (genome >> shift) > want) ++shift;
     h->rank_shift = shift;
     h->rank_off.assign(C + 1, 0);
@@ -411,7 +420,12 @@ int build_rank_tables(nrb200_handle *h) {
                                                    h->sort_keys_b.as<unsigned long long>(), y.n, 0, bits, h->stream));
         return NRB200_OK;
     };
+    // Equally wide ranges (points, fixed-width windows): the end order is the start order, so the start
+    // array and its table answer #{end < b} as #{start < b - (w - 1)}: no sorted-ends copy, half the index.
+    h->end_shift = (y.n > 0 && y.wmin == y.wmax) ? y.wmax - 1 : 0;
+    h->ends_alias_starts = y.n > 0 && y.wmin == y.wmax;
     if (!y.stranded) {
+        if (h->ends_alias_starts) return NRB200_OK;
         // ends in ascending order within each sequence: radix sort of (seqid << 32 | end)
         NRB_CUDA(h, h->rank_end.reserve(entries * sizeof(int32_t)));
         if (y.n > 0) {
@@ -458,10 +472,12 @@ int build_rank_tables(nrb200_handle *h) {
         NRB_CUDA(h, h->sort_tmp.reserve(tmp_bytes));
         NRB_CUDA(h, cub::DeviceScan::InclusiveScanByKey(h->sort_tmp.p, tmp_bytes, h->r_keys_b.as<unsigned>(), h->r_end.as<int32_t>(),
                                                         h->r_pmax.as<int32_t>(), MaxOp(), y.n, cub::Equality(), h->stream));
-        pack_vend_keys_kernel<<<n_grid, threads, 0, h->stream>>>(h->r_keys_b.as<unsigned>(), h->r_end.as<int32_t>(), y.n,
-                                                                 h->sort_keys_a.as<unsigned long long>());
-        if ((rc = sort_u64(32 + v_bits))) return rc;
-        unpack_end_keys_kernel<<<n_grid, threads, 0, h->stream>>>(h->sort_keys_b.as<unsigned long long>(), y.n, h->end_sorted.as<int32_t>());
+        if (!h->ends_alias_starts) {
+            pack_vend_keys_kernel<<<n_grid, threads, 0, h->stream>>>(h->r_keys_b.as<unsigned>(), h->r_end.as<int32_t>(), y.n,
+                                                                     h->sort_keys_a.as<unsigned long long>());
+            if ((rc = sort_u64(32 + v_bits))) return rc;
+            unpack_end_keys_kernel<<<n_grid, threads, 0, h->stream>>>(h->sort_keys_b.as<unsigned long long>(), y.n, h->end_sorted.as<int32_t>());
+        }
     }
     vseq_info_kernel<<<(unsigned)((V + 1 + threads - 1) / threads), threads, 0, h->stream>>>(
         h->r_keys_b.as<unsigned>(), y.n, V, h->max_pos_dev.as<int32_t>(), h->rrank_off_dev.as<int64_t>(), h->r_voff_dev.as<int32_t>(),
@@ -469,8 +485,9 @@ int build_rank_tables(nrb200_handle *h) {
     const unsigned rt_grid = (unsigned)((r_entries + threads - 1) / threads);
     build_rank_table_kernel<<<rt_grid, threads, 0, h->stream>>>(h->r_start.as<int32_t>(), h->r_voff_dev.as<int32_t>(),
                                                                 h->rrank_off_dev.as<int64_t>(), V, shift, h->rrank_start.as<uint32_t>());
-    build_rank_table_kernel<<<rt_grid, threads, 0, h->stream>>>(h->end_sorted.as<int32_t>(), h->r_voff_dev.as<int32_t>(),
-                                                                h->rrank_off_dev.as<int64_t>(), V, shift, h->rank_end.as<uint32_t>());
+    if (!h->ends_alias_starts)
+        build_rank_table_kernel<<<rt_grid, threads, 0, h->stream>>>(h->end_sorted.as<int32_t>(), h->r_voff_dev.as<int32_t>(),
+                                                                    h->rrank_off_dev.as<int64_t>(), V, shift, h->rank_end.as<uint32_t>());
     NRB_CUDA(h, cudaGetLastError());
     return NRB200_OK;
 }
@@ -885,6 +902,11 @@ BootParams make_params(nrb200_handle *h, const nrb200_draws *d) {
         Y.rseq_info = h->rseq_info_dev.as<int4>();
         Y.rrank_start = h->rrank_start.as<uint32_t>();
     }
+    Y.end_shift = h->end_shift;
+    if (h->ends_alias_starts) {
+        Y.end_sorted = Y.rstart;
+        Y.rank_end = Y.rrank_start;
+    }
     P.y = Y;
     const RangeSet &q = h->query, &x = active_excl(h);
     P.query = SliceView{q.start.as<int32_t>(), q.end.as<int32_t>(), q.pmax.as<int32_t>(), q.stranded ? q.strand.as<int8_t>() : nullptr,
@@ -924,7 +946,7 @@ void launch_count_t(nrb200_handle *h, const BootParams &P, unsigned grid, int ex
     else boot_count_kernel<ST, HQ, kExclTrim><<<grid, 256, 0, h->stream>>>(P);
 }
 
-constexpr int64_t kMaxBatch = 2048;  // iterations per launch (multiple of kRpt; gridDim.y and scratch stay small)
+constexpr int64_t kMaxBatch = 2048;  // iterations per launch at most (gridDim.y and scratch stay small); NRB200_MAX_BATCH lowers it
 constexpr int kChunkEvents = 16;
 constexpr int kChunks = 8;  // pipeline depth of nrb200_run_counts (compute chunk k+1 while chunk k copies out)
 
@@ -1024,10 +1046,10 @@ int run_counts_core(nrb200_handle *h, const nrb200_draws *d, bool want_counts, i
     const bool pipelined = host_counts && counts && R > 0;
     // Iterations go in batches: bounded draw-table scratch on the rank path and, when the matrix
     // is wanted on the host, chunk k copies out (copy stream) while chunk k + 1 computes.
-    int64_t chunk = kMaxBatch;
+    int64_t chunk = h->tune_max_batch;
     if (pipelined) {
         if (!h->copy_stream) NRB_CUDA(h, cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
-        chunk = std::min<int64_t>(kMaxBatch, std::max<int64_t>(((R + kChunks - 1) / kChunks + 7) / 8 * 8, 64));
+        chunk = std::min<int64_t>(h->tune_max_batch, std::max<int64_t>(((R + kChunks - 1) / kChunks + 7) / 8 * 8, 64));
     }
     if (rank_path_ok(h, has_query) && has_query) {
         NRB_CUDA(h, h->draw_tab.reserve((size_t)std::min(chunk, std::max<int64_t>(R, 1)) * h->plan.n_blocks() * sizeof(int2)));
@@ -1122,6 +1144,8 @@ int nrb200_create(const nrb200_config *cfg, nrb200_handle **out) {
     if (const char *e = getenv("NRB200_RPT")) h->tune_rpt = atoi(e);
     if (const char *e = getenv("NRB200_MINB")) h->tune_minb = atoi(e);
     if (const char *e = getenv("NRB200_TABLE_MULT")) h->tune_table_mult = atof(e);
+    if (const char *e = getenv("NRB200_TABLE_CAP")) h->tune_table_cap = atoll(e);
+    if (const char *e = getenv("NRB200_MAX_BATCH")) h->tune_max_batch = std::min<int64_t>(std::max<int64_t>(atoll(e), 8), 2048);
     if (h->tune_rpt != 1 && h->tune_rpt != 2 && h->tune_rpt != 4 && h->tune_rpt != 8) h->tune_rpt = 1;
     if (cfg && cfg->stream) {
         h->stream = (cudaStream_t)cfg->stream;

@@ -39,6 +39,8 @@ struct RangesView {            // canonical (seqname, start, end) order
     int n_cls;
     const int32_t *rstart, *rend, *rpmax;   // (seq, class, start, end) order
     const int32_t *end_sorted;               // ends ascending inside each virtual sequence
+    int32_t end_shift;                       // all ranges equally wide (w): end order = start order, end_sorted aliases
+                                             // rstart and #{end < b} = #{start < b - (w - 1)}; end_shift = w - 1, else 0
     const int4 *rseq_info;                   // [n_seq * n_cls]
     const uint32_t *rrank_start, *rank_end;  // tables over rstart / end_sorted
 };
@@ -154,7 +156,7 @@ __device__ __forceinline__ int32_t idx_start_le(const RangesView &y, const int4 
     return first_ge_ranked(y.rstart, y.rrank_start, y.rank_shift, si, a + 1);
 }
 __device__ __forceinline__ int32_t idx_end_lt(const RangesView &y, const int4 si, int32_t b) {
-    return first_ge_ranked(y.end_sorted, y.rank_end, y.rank_shift, si, b);
+    return first_ge_ranked(y.end_sorted, y.rank_end, y.rank_shift, si, b - y.end_shift);
 }
 
 __device__ __forceinline__ bool strands_match(int a, int b) { return a == 0 || b == 0 || a == b; }
@@ -538,14 +540,14 @@ struct PairProbe {
 };
 
 __device__ __forceinline__ void pair_keys(PairProbe &q, int2 draw, int32_t width, int32_t ts, int32_t seq_len,
-                                          int32_t gs, int32_t ge, int rank_shift, int32_t &ua, int32_t &ub) {
+                                          int32_t gs, int32_t ge, int rank_shift, int32_t end_shift, int32_t &ua, int32_t &ub) {
     const int32_t bs = draw.y;
     const int32_t sh = ts - bs;
     q.bs = bs;
     q.A = min(bs + (width - 1), min(ge, seq_len) - sh);
     q.Bv = max(bs, gs - sh);
     q.key_a = rank_clamp_key(q.A + 1, q.si);
-    q.key_b = rank_clamp_key(q.Bv, q.si);
+    q.key_b = rank_clamp_key(q.Bv - end_shift, q.si);
     ua = q.si.w + (q.key_a >> rank_shift);
     ub = q.si.w + (q.key_b >> rank_shift);
 }
@@ -589,7 +591,7 @@ __device__ __forceinline__ void count_pairs(const RangesView &y, const int2 (&d)
 #pragma unroll
     for (int j = 0; j < RPT; ++j) q[j].si = __ldg(y.rseq_info + d[j].x * y.n_cls + cls);
 #pragma unroll
-    for (int j = 0; j < RPT; ++j) pair_keys(q[j], d[j], width, ts, seq_len, gs, ge, y.rank_shift, ua[j], ub[j]);
+    for (int j = 0; j < RPT; ++j) pair_keys(q[j], d[j], width, ts, seq_len, gs, ge, y.rank_shift, y.end_shift, ua[j], ub[j]);
 #pragma unroll
     for (int j = 0; j < RPT; ++j) {
         const uint32_t ea = __ldg(y.rrank_start + ua[j]), eb = __ldg(y.rank_end + ub[j]);
@@ -770,6 +772,7 @@ struct InspectOut {
     int32_t unsorted;  // some neighbour pair is out of (seqid, start, end) order
     int32_t stranded;  // some strand is '+' or '-'
     int32_t wmax;      // widest range
+    int32_t wmin;      // narrowest range (initialise to INT32_MAX)
 };
 
 __global__ void __launch_bounds__(256) inspect_ranges_kernel(const int32_t *__restrict__ seqid, const int32_t *__restrict__ start,
@@ -777,7 +780,7 @@ __global__ void __launch_bounds__(256) inspect_ranges_kernel(const int32_t *__re
                                                              int64_t n, int n_seq, InspectOut *__restrict__ out,
                                                              unsigned *__restrict__ seq_count, int32_t *__restrict__ seq_max_end) {
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    int err = 0, unsorted = 0, stranded = 0, wmax = 0;
+    int err = 0, unsorted = 0, stranded = 0, wmax = 0, wmin = INT32_MAX;
     for (int64_t base = (int64_t)blockIdx.x * blockDim.x; base < n; base += stride) {  // warp-uniform trip count
         const int64_t i = base + threadIdx.x;
         const bool live = i < n;
@@ -797,6 +800,7 @@ __global__ void __launch_bounds__(256) inspect_ranges_kernel(const int32_t *__re
                 stranded |= t != 0;
             }
             wmax = max(wmax, e - s + 1);
+            wmin = min(wmin, e - s + 1);
             if (i > 0) {
                 const int32_t pc = seqid[i - 1], ps = start[i - 1], pe = end[i - 1];
                 if (c < pc || (c == pc && (s < ps || (s == ps && e < pe)))) unsorted = 1;
@@ -816,7 +820,9 @@ __global__ void __launch_bounds__(256) inspect_ranges_kernel(const int32_t *__re
     unsorted = __reduce_or_sync(kFull, unsorted);
     stranded = __reduce_or_sync(kFull, stranded);
     wmax = __reduce_max_sync(kFull, wmax);
+    wmin = __reduce_min_sync(kFull, wmin);
     if ((threadIdx.x & 31) == 0) {
+        atomicMin(&out->wmin, wmin);
         if (err) atomicOr(&out->err, err);
         if (unsorted) atomicOr(&out->unsorted, 1);
         if (stranded) atomicOr(&out->stranded, 1);
