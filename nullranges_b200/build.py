@@ -15,8 +15,8 @@ HEADERS = ["kernels.cuh", "philox.cuh", "plan.h", os.path.join("..", "..", "incl
 NVCC_FLAGS = [
     "-O3", "-std=c++17", "-lineinfo",
     "-gencode", "arch=compute_100a,code=sm_100a",
-    "-Xcompiler", "-fPIC,-fvisibility=hidden,-Wall",
-    "-shared", "-cudart", "static",
+    "-Xcompiler", "-fPIC,-fvisibility=hidden,-Wall,-fopenmp",
+    "-shared", "-cudart", "static", "-lgomp",
 ]
 
 

@@ -659,8 +659,9 @@ int build_pairs(nrb200_handle *h) {
     }
     tr.lap("tiles_by_seq");
     // calls emit(tile, ws, we, sign) for every signed window of every feature, features in canonical order
-    auto enumerate = [&](auto &&begin_feature, auto &&emit) {
-        for (int c = 0; c < C; ++c) {
+    // (one sequence at a time: the sequences are independent, so the two passes run them in parallel)
+    auto enumerate_seq = [&](int c, auto &&begin_feature, auto &&emit) {
+        {
             const auto &v = by_seq[c];
             const int64_t L = h->seqlen[c], nt = (int64_t)v.size();
             int64_t lo = 0;
@@ -696,7 +697,8 @@ int build_pairs(nrb200_handle *h) {
         }
     };
     std::vector<int32_t> len(G, 0);
-    enumerate([](int32_t) {}, [&](int32_t k, int32_t, int64_t, int64_t, int, int) { ++len[k]; });
+#pragma omp parallel for schedule(dynamic, 1) if (G >= 4096)
+    for (int c = 0; c < C; ++c) enumerate_seq(c, [](int32_t) {}, [&](int32_t k, int32_t, int64_t, int64_t, int, int) { ++len[k]; });
     tr.lap("pass1");
     // Visit order of the count kernel: features grouped by list length (stable counting sort, so
     // neighbours in a group are neighbours on the genome): the lanes of a warp then loop equally often.
@@ -727,12 +729,15 @@ int build_pairs(nrb200_handle *h) {
         f_recs_vec.resize((size_t)total);
         f_recs = f_recs_vec.data();
     }
-    int64_t cursor = 0;
-    enumerate([&](int32_t k) { cursor = f_off[pos_of[k]]; },
-              [&](int32_t, int32_t t, int64_t ws, int64_t we, int sign, int cls) {
-                  f_recs[cursor++] = PairRec{t, (int32_t)ws, (int32_t)std::min<int64_t>(we, INT32_MAX / 2), sign, p.tile_start[t],
-                                             p.bait_width[t], (int32_t)h->seqlen[p.tile_seq[t]], cls};
-              });
+#pragma omp parallel for schedule(dynamic, 1) if (G >= 4096)
+    for (int c = 0; c < C; ++c) {
+        int64_t cursor = 0;
+        enumerate_seq(c, [&](int32_t k) { cursor = f_off[pos_of[k]]; },
+                      [&](int32_t, int32_t t, int64_t ws, int64_t we, int sign, int cls) {
+                          f_recs[cursor++] = PairRec{t, (int32_t)ws, (int32_t)std::min<int64_t>(we, INT32_MAX / 2), sign, p.tile_start[t],
+                                                     p.bait_width[t], (int32_t)h->seqlen[p.tile_seq[t]], cls};
+                      });
+    }
     tr.lap("lists");
     if ((rc = upload(h, h->f_src, f_src.data(), (size_t)G))) return rc;
     if ((rc = upload(h, h->pair_off, f_off.data(), (size_t)G + 1))) return rc;
