@@ -76,11 +76,12 @@ int nrb200_ranges_info(const nrb200_handle *h, int32_t *is_sorted, int32_t *is_s
 int nrb200_set_query(nrb200_handle *h, int64_t n, const int32_t *seqid, const int32_t *start,
                      const int32_t *end, const int8_t *strand);
 
-/* The same with countOverlaps(x, boots, maxgap = maxgap) / join_overlap_inner(x, boots, maxgap = ...)
- * (vignettes/bootRanges.Rmd:532-540): ranges separated by at most `maxgap` positions count as
- * overlapping (adjacent ranges: gap 0).  maxgap = -1 is nrb200_set_query(). */
+/* The same with countOverlaps(x, boots, maxgap = , minoverlap = ) / join_overlap_inner(x, boots, maxgap = ...)
+ * (vignettes/bootRanges.Rmd:532-540): maxgap -- ranges separated by at most that many positions count as
+ * overlapping (adjacent ranges: gap 0); minoverlap -- the intersection must be at least that wide.  The two
+ * cannot be combined (as in GenomicRanges).  maxgap = -1, minoverlap = 0 is nrb200_set_query(). */
 int nrb200_set_query_ex(nrb200_handle *h, int64_t n, const int32_t *seqid, const int32_t *start,
-                        const int32_t *end, const int8_t *strand, int32_t maxgap);
+                        const int32_t *end, const int8_t *strand, int32_t maxgap, int32_t minoverlap);
 
 /* exclude of bootRanges(..., exclude, excludeOption = "drop") (R/bootRanges.R:106-109).
  * n = 0 clears. */

@@ -52,7 +52,7 @@ SYMBOLS = [
     ("nrb200_set_ranges", C.c_int, [vp, C.c_int64, C.c_int32, i64p, i32p, i32p, i32p, i8p]),
     ("nrb200_ranges_info", C.c_int, [vp, i32p, i32p, i32p]),
     ("nrb200_set_query", C.c_int, [vp, C.c_int64, i32p, i32p, i32p, i8p]),
-    ("nrb200_set_query_ex", C.c_int, [vp, C.c_int64, i32p, i32p, i32p, i8p, C.c_int32]),
+    ("nrb200_set_query_ex", C.c_int, [vp, C.c_int64, i32p, i32p, i32p, i8p, C.c_int32, C.c_int32]),
     ("nrb200_set_exclude", C.c_int, [vp, C.c_int64, i32p, i32p, i32p, i8p]),
     ("nrb200_set_exclude_option", C.c_int, [vp, C.c_int32]),
     ("nrb200_set_plan", C.c_int, [vp, C.POINTER(PlanSpec), i64p]),

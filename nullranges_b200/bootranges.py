@@ -159,11 +159,12 @@ class BootCounts:
 def bootCounts(y: GRanges, x: GRanges, blockLength, R: int = 1, seg: GRanges | None = None,
                exclude: GRanges | None = None, excludeOption=("drop", "trim"), proportionLength: bool = True,
                type=("bootstrap", "permute"), withinChrom: bool = False, *, rng="philox", seed=None, iter0: int = 0,
-               perFeature: bool = True, device: int = 0, out: dict | None = None, maxgap: int = -1) -> BootCounts:
-    """countOverlaps(x, bootRanges(y, ...), maxgap = maxgap) per iteration, fused on the GPU."""
+               perFeature: bool = True, device: int = 0, out: dict | None = None, maxgap: int = -1,
+               minoverlap: int = 0) -> BootCounts:
+    """countOverlaps(x, bootRanges(y, ...), maxgap = , minoverlap = ) per iteration, fused on the GPU."""
     eng, kind, L_b, segd = _setup(y, blockLength, seg, exclude, excludeOption, proportionLength, type, withinChrom, device)
     qi, qs, qe, qstr, qkeep = _side_arrays(x, y, "x")
-    eng.set_query(qi, qs, qe, qstr if np.any(qstr) else None, maxgap=maxgap)
+    eng.set_query(qi, qs, qe, qstr if np.any(qstr) else None, maxgap=maxgap, minoverlap=minoverlap)
     draws = _make_draws(eng, kind, int(R), y, L_b, segd, rng, seed, iter0)
     if out is not None and qkeep.size != len(x):
         raise ValueError("out= needs every seqlevel of x to be a seqlevel of y")

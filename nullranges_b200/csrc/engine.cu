@@ -115,7 +115,8 @@ struct nrb200_handle {
     std::vector<int64_t> rank_off;
     DevMem inspect_dev, seq_info_dev, draw_tab;
     // stranded y only: class-major copy for the rank path (kernels.cuh, RangesView)
-    int n_cls = 1;
+    int n_cls = 1, n_width = 1;
+    int32_t query_minoverlap = 0, index_minoverlap = 0;  // the index groups y by "narrower than minoverlap": rebuilt when it changes
     int32_t end_shift = 0;
     bool ends_alias_starts = false;
     DevMem r_start, r_end, r_pmax, r_order, r_idx, r_keys_a, r_keys_b, r_voff_dev, rseq_info_dev, rrank_off_dev, rrank_start;
@@ -384,7 +385,10 @@ int build_rank_tables(nrb200_handle *h) {
     h->rank_off.assign(C + 1, 0);
     for (int c = 0; c < C; ++c) h->rank_off[c + 1] = h->rank_off[c] + ((int64_t)max_pos[c] >> shift) + 3;  // +1: probes read entry u + 1
     const int64_t entries = h->rank_off[C];
-    h->n_cls = y.stranded ? 3 : 1;
+    // classes of y the rank path counts separately: strand class x (narrower than the query's minoverlap?)
+    h->n_width = h->query_minoverlap > 0 ? 2 : 1;
+    h->n_cls = (y.stranded ? 3 : 1) * h->n_width;
+    h->index_minoverlap = h->query_minoverlap;
     if (entries * h->n_cls > (int64_t)INT32_MAX) return fail(h, NRB200_ERR_UNSUPPORTED, "rank tables exceed 2^31 entries");
     for (int c = 0; c < C; ++c)  // packed table entries hold a per-sequence index in 29 bits
         if (y.h_seq_off[c + 1] - y.h_seq_off[c] >= (1 << 29)) return fail(h, NRB200_ERR_UNSUPPORTED, "more than 2^29 ranges on one sequence");
@@ -424,7 +428,7 @@ int build_rank_tables(nrb200_handle *h) {
     // array and its table answer #{end < b} as #{start < b - (w - 1)}: no sorted-ends copy, half the index.
     h->end_shift = (y.n > 0 && y.wmin == y.wmax) ? y.wmax - 1 : 0;
     h->ends_alias_starts = y.n > 0 && y.wmin == y.wmax;
-    if (!y.stranded) {
+    if (h->n_cls == 1) {
         if (h->ends_alias_starts) return NRB200_OK;
         // ends in ascending order within each sequence: radix sort of (seqid << 32 | end)
         NRB_CUDA(h, h->rank_end.reserve(entries * sizeof(int32_t)));
@@ -441,10 +445,10 @@ int build_rank_tables(nrb200_handle *h) {
         NRB_CUDA(h, cudaGetLastError());
         return NRB200_OK;
     }
-    // ---- stranded y: a second copy grouped by strand class inside each sequence (virtual sequences)
-    const int V = 3 * C;
+    // ---- several classes: a second copy grouped by class inside each sequence (virtual sequences)
+    const int V = h->n_cls * C;
     std::vector<int64_t> roff(V + 1, 0);
-    for (int v = 0; v < V; ++v) roff[v + 1] = roff[v] + ((int64_t)max_pos[v / 3] >> shift) + 3;
+    for (int v = 0; v < V; ++v) roff[v + 1] = roff[v] + ((int64_t)max_pos[v / h->n_cls] >> shift) + 3;
     const int64_t r_entries = roff[V];
     if ((rc = upload(h, h->rrank_off_dev, roff.data(), (size_t)V + 1))) return rc;
     for (DevMem *m : {&h->r_start, &h->r_end, &h->r_pmax, &h->r_order, &h->r_idx, &h->r_keys_a, &h->r_keys_b})
@@ -456,8 +460,9 @@ int build_rank_tables(nrb200_handle *h) {
     int v_bits = 1;
     while ((1 << v_bits) < V) ++v_bits;
     if (y.n > 0) {
-        vseq_keys_kernel<<<n_grid, threads, 0, h->stream>>>(y.seqid.as<int32_t>(), y.strand.as<int8_t>(), y.n,
-                                                            h->r_keys_a.as<unsigned>(), h->r_idx.as<int32_t>());
+        vseq_keys_kernel<<<n_grid, threads, 0, h->stream>>>(y.seqid.as<int32_t>(), y.stranded ? y.strand.as<int8_t>() : nullptr,
+                                                            y.start.as<int32_t>(), y.end.as<int32_t>(), y.n, h->n_cls, h->n_width,
+                                                            h->query_minoverlap, h->r_keys_a.as<unsigned>(), h->r_idx.as<int32_t>());
         size_t tmp_bytes = 0;  // stable: inside a virtual sequence the canonical (start, end) order survives
         NRB_CUDA(h, cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, h->r_keys_a.as<unsigned>(), h->r_keys_b.as<unsigned>(),
                                                     h->r_idx.as<int32_t>(), h->r_order.as<int32_t>(), y.n, 0, v_bits, h->stream));
@@ -480,7 +485,7 @@ int build_rank_tables(nrb200_handle *h) {
         }
     }
     vseq_info_kernel<<<(unsigned)((V + 1 + threads - 1) / threads), threads, 0, h->stream>>>(
-        h->r_keys_b.as<unsigned>(), y.n, V, h->max_pos_dev.as<int32_t>(), h->rrank_off_dev.as<int64_t>(), h->r_voff_dev.as<int32_t>(),
+        h->r_keys_b.as<unsigned>(), y.n, V, h->n_cls, h->max_pos_dev.as<int32_t>(), h->rrank_off_dev.as<int64_t>(), h->r_voff_dev.as<int32_t>(),
         h->rseq_info_dev.as<int4>());
     const unsigned rt_grid = (unsigned)((r_entries + threads - 1) / threads);
     build_rank_table_kernel<<<rt_grid, threads, 0, h->stream>>>(h->r_start.as<int32_t>(), h->r_voff_dev.as<int32_t>(),
@@ -587,8 +592,10 @@ int build_pairs(nrb200_handle *h) {
     // Per strand class of y -- "drop": the merged exclude regions that class can overlap; "trim": the gaps
     // (already disjoint and sorted, strand-free).
     std::vector<std::vector<std::vector<Interval>>> XC(n_cls, std::vector<std::vector<Interval>>(C));
+    const int n_width = h->n_width;
+    const int64_t kk = h->query_minoverlap;  // 0: any overlap counts
     for (int cls = 0; cls < n_cls; ++cls) {
-        if (has_excl && !trim) XC[cls] = merged_exclude(h, cls);
+        if (has_excl && !trim) XC[cls] = (cls % n_width) ? XC[cls - 1] : merged_exclude(h, cls / n_width);
         if (trim)
             for (int c = 0; c < C; ++c)
                 for (int32_t k = h->gaps.h_seq_off[c]; k < h->gaps.h_seq_off[c + 1]; ++k)
@@ -608,7 +615,7 @@ int build_pairs(nrb200_handle *h) {
         for (int64_t t = 0; t < B; ++t) {
             const int c = p.tile_seq[t];
             const int64_t ts = p.tile_start[t], te = ts + p.bait_width[t] - 1;
-            for (int cls = 0; cls < n_cls; ++cls) {
+            for (int cls = 0; cls < n_cls; ++cls) {  // rows count every class, narrow ranges included
                 const auto &X = XC[cls][c];
                 size_t f, l;
                 x_run(X, ts - reach, te + reach, f, l);
@@ -671,24 +678,39 @@ int build_pairs(nrb200_handle *h) {
                 if (gs > L) continue;
                 while (lo < nt && te_max[c][lo] + reach < gs) ++lo;
                 const int g_strand = q.stranded ? q.h_strand[k] : 0;
+                // minoverlap = kk: start' <= we - kk + 1, end' >= ws + kk - 1, and the trimmed range itself at
+                // least kk wide (start' <= L - kk + 1, end' >= kk; the ranges narrower than kk sit in classes of
+                // their own that no window names).  All of it folds into the window's end points.
+                auto window = [&](int64_t ws, int64_t we, int64_t &lo_w, int64_t &hi_w) {
+                    if (kk <= 0) { lo_w = ws; hi_w = we; return true; }
+                    if (we - ws + 1 < kk) return false;
+                    lo_w = std::max(ws + kk - 1, kk);
+                    hi_w = std::min(we - kk + 1, L - kk + 1);
+                    return true;
+                };
+                int64_t g_lo, g_hi;
+                if (!window(gs, ge, g_lo, g_hi)) continue;
                 for (int64_t j = lo; j < nt && ts[c][j] <= ge + reach; ++j) {
                     if (te[c][j] + reach < gs) continue;
-                    for (int cls = 0; cls < n_cls; ++cls) {  // strand classes of y this feature counts
-                        if (!strands_compatible(cls, g_strand)) continue;
+                    for (int cls = 0; cls < n_cls; ++cls) {  // classes of y this feature counts
+                        if ((cls % n_width) != 0 || !strands_compatible(cls / n_width, g_strand)) continue;
                         const auto &X = XC[cls][c];
                         if (trim) {  // the pieces that can land on the feature: one window per gap it intersects
                             size_t f, l;
                             x_run(X, std::max(ts[c][j] - reach, gs), std::min(te[c][j] + reach, ge), f, l);
-                            for (size_t i = f; i < l; ++i) emit(k, v[j], std::max(X[i].s, gs), std::min(X[i].e, ge), +1, cls);
+                            for (size_t i = f; i < l; ++i) {
+                                int64_t p_lo, p_hi;
+                                if (window(std::max(X[i].s, gs), std::min(X[i].e, ge), p_lo, p_hi)) emit(k, v[j], p_lo, p_hi, +1, cls);
+                            }
                             continue;
                         }
-                        emit(k, v[j], gs, ge, +1, cls);
+                        emit(k, v[j], g_lo, g_hi, +1, cls);
                         if (has_excl) {  // regions a range landing on the tile can overlap together with the feature
                             size_t f, l;
                             x_run(X, std::max(ts[c][j] - reach, gs - reach), std::min(te[c][j] + reach, ge + reach), f, l);
                             for (size_t i = f; i < l; ++i) {
-                                emit(k, v[j], std::max(X[i].s, gs), std::min(X[i].e, ge), -1, cls);
-                                if (i + 1 < l && X[i + 1].s - X[i].e <= reach) emit(k, v[j], std::max(X[i + 1].s, gs), std::min(X[i].e, ge), +1, cls);
+                                emit(k, v[j], std::max(X[i].s, g_lo), std::min(X[i].e, g_hi), -1, cls);
+                                if (i + 1 < l && X[i + 1].s - X[i].e <= reach) emit(k, v[j], std::max(X[i + 1].s, g_lo), std::min(X[i].e, g_hi), +1, cls);
                             }
                         }
                     }
@@ -775,6 +797,7 @@ int prepare(nrb200_handle *h) {
         h->tiles_in_bounds = true;
         for (int64_t t = 0; t < h->plan.n_blocks(); ++t)
             if (h->plan.tile_start[t] > h->seqlen[h->plan.tile_seq[t]]) h->tiles_in_bounds = false;
+        if (h->index_minoverlap != h->query_minoverlap && (rc = build_rank_tables(h))) return rc;  // the width classes changed
         if (trim_mode(h) && h->excl.stranded) return fail(h, NRB200_ERR_INVALID, "all(strand(exclude) == \"*\") is not TRUE");
         if (trim_mode(h) && (rc = build_gaps(h))) return rc;
         // rank_path_ok(h, false) holds whenever rank_path_ok(h, true) does
@@ -919,6 +942,7 @@ BootParams make_params(nrb200_handle *h, const nrb200_draws *d) {
     P.excl = SliceView{x.start.as<int32_t>(), x.end.as<int32_t>(), x.pmax.as<int32_t>(), x.stranded ? x.strand.as<int8_t>() : nullptr,
                        x.src.as<int32_t>(), h->x_tile_lo.as<int32_t>(), h->x_tile_hi.as<int32_t>()};
     P.rows_windows_only = trim_mode(h);
+    P.minoverlap = h->query_minoverlap;
     P.sampler = h->sampler_view;
     P.n_blocks = h->plan.n_blocks();
     P.tile_seq = h->tile_seq.as<int32_t>();
@@ -1198,6 +1222,7 @@ int nrb200_set_ranges(nrb200_handle *h, int64_t n, int32_t n_seq, const int64_t 
     }
     h->have_y = h->have_plan = false;
     h->query.n = h->excl.n = 0;  // seqlevels may have changed
+    h->query_minoverlap = 0;
     h->n_seq = n_seq;
     h->seqlen.assign(seqlengths, seqlengths + n_seq);
     int rc;
@@ -1243,7 +1268,7 @@ static int set_side(nrb200_handle *h, RangeSet &rs, const char *what, int64_t n,
 
 int nrb200_set_query(nrb200_handle *h, int64_t n, const int32_t *seqid, const int32_t *start, const int32_t *end,
                      const int8_t *strand) {
-    return nrb200_set_query_ex(h, n, seqid, start, end, strand, -1);
+    return nrb200_set_query_ex(h, n, seqid, start, end, strand, -1, 0);
 }
 
 // maxgap: two ranges count as overlapping when at most `maxgap` positions separate them
@@ -1251,13 +1276,20 @@ int nrb200_set_query(nrb200_handle *h, int64_t n, const int32_t *seqid, const in
 // feature widened by maxgap + 1 on both sides, which is how the query is stored; nothing downstream
 // changes.  (Bootstrapped ranges lie inside [1, seqlength], so the widening cannot create overlaps
 // that trim() would have removed.)
+// minoverlap: the intersection must be at least that wide.  On the rank path this is a condition on the window's
+// end points plus "the range itself is at least that wide": y is indexed in width classes (build_rank_tables).
 int nrb200_set_query_ex(nrb200_handle *h, int64_t n, const int32_t *seqid, const int32_t *start, const int32_t *end,
-                        const int8_t *strand, int32_t maxgap) {
+                        const int8_t *strand, int32_t maxgap, int32_t minoverlap) {
     if (!h) return NRB200_ERR_INVALID;
     if (maxgap < -1) return fail(h, NRB200_ERR_INVALID, "'maxgap' must be >= -1");
     if (maxgap >= (1 << 29)) return fail(h, NRB200_ERR_UNSUPPORTED, "'maxgap' must be below 2^29");
+    if (minoverlap < 0) return fail(h, NRB200_ERR_INVALID, "'minoverlap' must be >= 0");
+    if (minoverlap > 0 && maxgap != -1) return fail(h, NRB200_ERR_INVALID, "'maxgap' and 'minoverlap' cannot both be set");
     const int rc = set_side(h, h->query, "query", n, seqid, start, end, strand, maxgap + 1);
-    if (rc == NRB200_OK) h->query_widen = maxgap + 1;
+    if (rc == NRB200_OK) {
+        h->query_widen = maxgap + 1;
+        h->query_minoverlap = n > 0 ? minoverlap : 0;
+    }
     return rc;
 }
 

@@ -34,8 +34,9 @@ struct RangesView {            // canonical (seqname, start, end) order
     const uint32_t *rank_pmax;
     int rank_shift;
     // Rank path.  When strand can matter the ranges are ALSO kept grouped by strand class inside each
-    // sequence ("virtual sequence" v = seq * n_cls + class, class 0 '*', 1 '+', 2 '-'), so that a count
-    // can be taken per class; with an unstranded y (n_cls = 1) these alias the canonical arrays.
+    // sequence ("virtual sequence" v = seq * n_cls + class), so that a count can be taken per class; class =
+    // strand class ('*', '+', '-' when y is stranded) x width class (ranges narrower than the query's
+    // minoverlap can never count).  With one class (n_cls = 1) these alias the canonical arrays.
     int n_cls;
     const int32_t *rstart, *rend, *rpmax;   // (seq, class, start, end) order
     const int32_t *end_sorted;               // ends ascending inside each virtual sequence
@@ -74,6 +75,7 @@ struct BootParams {
     const int64_t *seqlen;
     int permute, drop_zero;
     int rows_windows_only;    // rank path, excludeOption = "trim": rows = sum of the tile's gap windows
+    int32_t minoverlap;       // countOverlaps(minoverlap =): smallest intersection width that counts (0 = any)
     // draws
     int rng_mode;
     uint64_t seed;
@@ -284,8 +286,10 @@ __device__ __forceinline__ int count_piece(const BootParams &P, int64_t r, int32
                                            int32_t pe, int strand) {
     int n = 0;
     for (int32_t k = first_gt(P.query.start, q_lo, q_hi, pe) - 1; k >= q_lo && __ldg(P.query.pmax + k) >= ps; --k) {
-        if (__ldg(P.query.end + k) < ps) continue;
+        const int32_t qe = __ldg(P.query.end + k);
+        if (qe < ps) continue;
         if (STRANDED && P.query.strand && !strands_match(strand, __ldg(P.query.strand + k))) continue;
+        if (P.minoverlap > 0 && min(pe, qe) - max(ps, __ldg(P.query.start + k)) + 1 < P.minoverlap) continue;
         ++n;
         if (P.counts) atomicAdd(P.counts + r * P.n_query + __ldg(P.query.src + k), 1);
     }
@@ -946,12 +950,15 @@ __global__ void noprop_assign_kernel(const SamplerView S, uint64_t seed, int64_t
 }
 
 // ---- strand-class grouping of y for the rank path -----------------------------------------
-// virtual sequence of a range: seq * 3 + strand code
-__global__ void vseq_keys_kernel(const int32_t *__restrict__ seqid, const int8_t *__restrict__ strand, int64_t n,
-                                 unsigned *__restrict__ keys, int32_t *__restrict__ idx) {
+// virtual sequence of a range: seq * n_cls + class, class = strand class * n_width + (narrower than minoverlap)
+__global__ void vseq_keys_kernel(const int32_t *__restrict__ seqid, const int8_t *__restrict__ strand,
+                                 const int32_t *__restrict__ start, const int32_t *__restrict__ end, int64_t n, int n_cls,
+                                 int n_width, int32_t minoverlap, unsigned *__restrict__ keys, int32_t *__restrict__ idx) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) {
-        keys[i] = (unsigned)seqid[i] * 3u + (unsigned)strand[i];
+        const unsigned sc = strand ? (unsigned)strand[i] : 0u;
+        const unsigned narrow = (n_width > 1 && end[i] - start[i] + 1 < minoverlap) ? 1u : 0u;
+        keys[i] = (unsigned)seqid[i] * (unsigned)n_cls + sc * (unsigned)n_width + narrow;
         idx[i] = (int32_t)i;
     }
 }
@@ -967,7 +974,7 @@ __global__ void gather_by_order_kernel(const int32_t *__restrict__ order, const 
     }
 }
 // voff[v] = first position of virtual sequence v in the sorted keys; seq_info of every virtual sequence
-__global__ void vseq_info_kernel(const unsigned *__restrict__ sorted_keys, int64_t n, int n_vseq, const int32_t *__restrict__ max_pos,
+__global__ void vseq_info_kernel(const unsigned *__restrict__ sorted_keys, int64_t n, int n_vseq, int n_cls, const int32_t *__restrict__ max_pos,
                                  const int64_t *__restrict__ rank_off, int32_t *__restrict__ voff, int4 *__restrict__ info) {
     const int v = blockIdx.x * blockDim.x + threadIdx.x;
     if (v > n_vseq) return;
@@ -981,7 +988,7 @@ __global__ void vseq_info_kernel(const unsigned *__restrict__ sorted_keys, int64
     };
     const int32_t lo = lower((unsigned)v);
     voff[v] = lo;
-    if (v < n_vseq) info[v] = make_int4(lo, lower((unsigned)v + 1u), max_pos[v / 3], (int32_t)rank_off[v]);
+    if (v < n_vseq) info[v] = make_int4(lo, lower((unsigned)v + 1u), max_pos[v / n_cls], (int32_t)rank_off[v]);
 }
 __global__ void pack_vend_keys_kernel(const unsigned *__restrict__ vkeys, const int32_t *__restrict__ end, int64_t n,
                                       unsigned long long *__restrict__ keys) {

@@ -82,11 +82,11 @@ class Engine:
         self._check(self._lib.nrb200_ranges_info(self._h, C.byref(a), C.byref(b), C.byref(c)))
         return {"sorted": bool(a.value), "stranded": bool(b.value), "max_width": c.value}
 
-    def set_query(self, seqid, start, end, strand=None, maxgap: int = -1):
-        """maxgap as in countOverlaps(x, boots, maxgap=): ranges at most maxgap positions apart count as overlapping."""
+    def set_query(self, seqid, start, end, strand=None, maxgap: int = -1, minoverlap: int = 0):
+        """maxgap / minoverlap as in countOverlaps(x, boots, maxgap=, minoverlap=)."""
         a, b, c, d = _i32(seqid), _i32(start), _i32(end), _i8(strand)
         self._check(self._lib.nrb200_set_query_ex(self._h, a.size, ptr(a, C.c_int32), ptr(b, C.c_int32), ptr(c, C.c_int32),
-                                                  ptr(d, C.c_int8), int(maxgap)))
+                                                  ptr(d, C.c_int8), int(maxgap), int(minoverlap)))
         self.n_query = a.size
 
     def set_exclude(self, seqid, start, end, strand=None, option: str = "drop"):

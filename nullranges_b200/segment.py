@@ -25,7 +25,7 @@ def countOverlaps(query: GRanges, subject: GRanges, maxgap: int = -1, minoverlap
     if keep.size:
         strand = query.strand[keep]
         eng.set_query(ids[keep], query.start[keep], query.end[keep], strand if np.any(strand) else None, maxgap=maxgap)
-        out[keep] = eng.count_observed(minoverlap=minoverlap)[0]
+        out[keep] = eng.count_observed(minoverlap=minoverlap)[0]  # minoverlap is applied by the counting kernel itself
     return out
 
 

@@ -132,13 +132,13 @@ bootRanges <- function(y, blockLength, R = 1, seg = NULL, exclude = NULL, exclud
 # Returns list(iter_totals, iter_nranges, counts = integer matrix [length(x), R]).
 bootCounts <- function(y, x, blockLength, R = 1, seg = NULL, exclude = NULL, excludeOption = c("drop", "trim"),
                        proportionLength = TRUE, type = c("bootstrap", "permute"), withinChrom = FALSE,
-                       rng = c("philox", "R"), seed = 0, iter0 = 0, perFeature = TRUE, maxgap = -1L, device = 0L) {
+                       rng = c("philox", "R"), seed = 0, iter0 = 0, perFeature = TRUE, maxgap = -1L, minoverlap = 0L, device = 0L) {
   excludeOption <- match.arg(excludeOption); type <- match.arg(type); rng <- match.arg(rng)
   s <- .setup(y, blockLength, seg, exclude, excludeOption, proportionLength, type, withinChrom, device)
   keep <- which(as.character(GenomicRanges::seqnames(x)) %in% s$lv)
   xk <- x[keep]
   .Call("nrb200_R_set_query", s$h, .seqid(xk, s$lv), GenomicRanges::start(xk), GenomicRanges::end(xk), .strand_code(xk),
-        as.integer(maxgap))
+        as.integer(maxgap), as.integer(minoverlap))
   d <- .draws(s, R, blockLength, rng)
   res <- .Call("nrb200_R_run_counts", s$h, as.numeric(R), as.numeric(iter0), as.numeric(seed), d[[1]], d[[2]], d[[3]],
                as.numeric(length(xk)), perFeature)

@@ -79,9 +79,9 @@ SEXP nrb200_R_set_ranges(SEXP ptr, SEXP seqlengths, SEXP seqid, SEXP start, SEXP
     return Rf_ScalarLogical(sorted);
 }
 
-SEXP nrb200_R_set_query(SEXP ptr, SEXP seqid, SEXP start, SEXP end, SEXP strand, SEXP maxgap) {
+SEXP nrb200_R_set_query(SEXP ptr, SEXP seqid, SEXP start, SEXP end, SEXP strand, SEXP maxgap, SEXP minoverlap) {
     check(H(ptr), nrb200_set_query_ex(H(ptr), XLENGTH(start), ints(seqid, "seqnames(x)"), ints(start, "start(x)"),
-                                      ints(end, "end(x)"), strand_codes(strand), Rf_asInteger(maxgap)));
+                                      ints(end, "end(x)"), strand_codes(strand), Rf_asInteger(maxgap), Rf_asInteger(minoverlap)));
     return R_NilValue;
 }
 
@@ -179,7 +179,7 @@ SEXP nrb200_R_run_materialize(SEXP ptr, SEXP n_iter, SEXP iter0, SEXP seed, SEXP
 static const R_CallMethodDef call_methods[] = {
     {"nrb200_R_create", (DL_FUNC)&nrb200_R_create, 1},
     {"nrb200_R_set_ranges", (DL_FUNC)&nrb200_R_set_ranges, 6},
-    {"nrb200_R_set_query", (DL_FUNC)&nrb200_R_set_query, 6},
+    {"nrb200_R_set_query", (DL_FUNC)&nrb200_R_set_query, 7},
     {"nrb200_R_set_exclude", (DL_FUNC)&nrb200_R_set_exclude, 6},
     {"nrb200_R_set_plan", (DL_FUNC)&nrb200_R_set_plan, 7},
     {"nrb200_R_run_counts", (DL_FUNC)&nrb200_R_run_counts, 9},

@@ -52,7 +52,7 @@ def oracle_objects(case, kind):
     C = case["seqlen"].size
     plan = O.Plan(kind, case["seqlen"], case["L_b"], case["seg"] if kind in (2, 3) else None)
     y = O.Index(C, *case["y"])
-    q = O.Index(C, *case["query"], maxgap=case.get("maxgap", -1)) if case["query"] is not None else None
+    q = O.Index(C, *case["query"], maxgap=case.get("maxgap", -1), minoverlap=case.get("minoverlap", 0)) if case["query"] is not None else None
     x = None
     if case["excl"] is not None:
         x = O.gaps(C, case["seqlen"], *case["excl"]) if case.get("trim") else O.Index(C, *case["excl"])
@@ -66,7 +66,7 @@ def excl_mode(case):
 def load_engine(eng, case, kind):
     eng.set_ranges(case["seqlen"], *case["y"])
     if case["query"] is not None:
-        eng.set_query(*case["query"], maxgap=case.get("maxgap", -1))
+        eng.set_query(*case["query"], maxgap=case.get("maxgap", -1), minoverlap=case.get("minoverlap", 0))
     else:
         eng.clear_query()
     if case["excl"] is not None:

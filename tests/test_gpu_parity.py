@@ -414,6 +414,8 @@ def test_fuzz_parity(engine, seed):
         case["excl"] = x if mode == "trim" else restrand(x, 0.4)
         case["trim"] = mode == "trim"
     case["maxgap"] = int(rng.choice([-1, -1, 0, 40]))
+    if case["maxgap"] == -1 and rng.random() < 0.4:
+        case["minoverlap"] = int(rng.choice([1, 5, 25, 200]))
     try:
         plan, y, qi, xi = H.oracle_objects(case, kind)
     except ValueError as e:                                      # e.g. a state's scaled block length rounds to 0
@@ -478,3 +480,25 @@ def test_count_overlaps_and_segment_tile_counts(engine):
         assert np.array_equal(countOverlaps(q, y, **kw), want), kw
     with pytest.raises(ValueError):
         countOverlaps(q, y, maxgap=3, minoverlap=2)
+
+
+@pytest.mark.parametrize("kind", [0, 1, 2, 4])
+@pytest.mark.parametrize("minoverlap", [1, 20, 90])
+def test_minoverlap(engine, kind, minoverlap):
+    """countOverlaps(x, boots, minoverlap = k): the intersection of the trimmed range and the feature must be k wide."""
+    case = H.random_case(seed=700 + kind, n=800, n_seq=3, n_query=90, n_excl=12 if kind == 2 else 0, stranded=kind == 1, n_seg=9,
+                         n_states=2, wmax=120)
+    if kind == 0:
+        case["excl"], case["trim"] = (np.array([0, 1], np.int32), np.array([300, 900], np.int32), np.array([420, 1500], np.int32), None), True
+    case["minoverlap"] = minoverlap
+    got, ref = _check_counts(engine, case, kind, R=5, seed=6, philox=False)
+    case["minoverlap"] = 0
+    _, plain = _check_counts(engine, case, kind, R=5, seed=6, philox=False)
+    assert np.array_equal(ref["iter_nranges"], plain["iter_nranges"])          # rows do not depend on the query
+    if minoverlap > 1:
+        assert ref["iter_totals"].sum() < plain["iter_totals"].sum()
+    else:
+        assert np.array_equal(ref["feature_counts"], plain["feature_counts"])   # minoverlap = 1 is plain overlap
+    from nullranges_b200 import EngineError
+    with pytest.raises(EngineError, match="cannot both"):
+        engine.set_query(*case["query"], maxgap=5, minoverlap=3)

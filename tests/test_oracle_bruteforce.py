@@ -28,6 +28,7 @@ def brute_iteration(case, kind, plan, bc, bs, dt):
     q = case["query"]
     qsd = np.zeros(q[0].size, np.int8) if q[3] is None else q[3]
     m1 = case.get("maxgap", -1) + 1
+    mo = case.get("minoverlap", 0)
     counts = np.zeros(q[0].size, np.int64)
     rows = []
     for b in range(plan.B):
@@ -67,7 +68,8 @@ def brute_iteration(case, kind, plan, bc, bs, dt):
             for ps, pe in pieces:
                 rows.append((tc, ps, pe, i, b))
                 if pe >= ps:
-                    counts += (q[0] == tc) & (q[1] - m1 <= pe) & (q[2] + m1 >= ps) & _compat(ysd[i], qsd)
+                    ov = np.minimum(pe, q[2]) - np.maximum(ps, q[1]) + 1
+                    counts += (q[0] == tc) & (q[1] - m1 <= pe) & (q[2] + m1 >= ps) & _compat(ysd[i], qsd) & ((mo == 0) | (ov >= mo))
     return np.array(rows, np.int64).reshape(-1, 5), counts
 
 
@@ -90,6 +92,8 @@ def test_oracle_equals_bruteforce(seed):
         sd = rng.integers(0, 3, m).astype(np.int8) if (mode == "drop" and rng.random() < 0.5) else None
         case["excl"], case["trim"] = (sid, st, en, sd), mode == "trim"
     case["maxgap"] = int(rng.choice([-1, 0, 15]))
+    if case["maxgap"] == -1 and rng.random() < 0.5:
+        case["minoverlap"] = int(rng.choice([1, 4, 30]))
     try:
         plan, y, q, x = H.oracle_objects(case, kind)
     except ValueError:
