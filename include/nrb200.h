@@ -194,6 +194,16 @@ int nrb200_run_moments(nrb200_handle *h, const nrb200_draws *draws, int64_t batc
 int nrb200_moments_fetch(nrb200_handle *h, int64_t *feat_sum, int64_t *feat_sumsq,
                          int64_t *feat_n_ge_observed);
 
+/* ---- weighted statistic: sum of a numeric column of y over the ranges that land on each feature -----
+ * (vignettes/bootRanges.Rmd:532-540: join_overlap_inner(...) %>% group_by(x_id, iter) %>% summarize(sum(signal))).
+ * weights: [n of nrb200_set_ranges], in the caller's order; NULL clears.  Call after nrb200_set_ranges().
+ * nrb200_run_weighted: iter_sums [n_iter] = sum over features, feature_sums [n_iter x n_query] (may be NULL).
+ * Floating point (double): sums are formed from running sums along two orders of y, so they agree with a
+ * plain summation to rounding (relative 1e-9 in the tests), not bit for bit. */
+int nrb200_set_weights(nrb200_handle *h, const double *weights);
+int nrb200_run_weighted(nrb200_handle *h, const nrb200_draws *draws, double *iter_sums, double *feature_sums,
+                        nrb200_stats *stats);
+
 /* countOverlaps(x, y) on the ORIGINAL ranges (the observed statistic,
  * vignettes/bootRanges.Rmd:482-483). */
 int nrb200_count_observed(nrb200_handle *h, int32_t *feature_counts, int64_t *total);

@@ -154,14 +154,18 @@ class BootCounts:
     iter_nranges: np.ndarray           # [R] length of the iteration's bootstrap sample
     feature_counts: np.ndarray | None  # [R, length(x)] countOverlaps(x, boots[iter == r])
     stats: dict
+    iter_sums: np.ndarray | None = None     # with weights=: [R] sum over features of feature_sums
+    feature_sums: np.ndarray | None = None  # with weights=: [R, length(x)] sum of the column over the overlapping ranges
 
 
 def bootCounts(y: GRanges, x: GRanges, blockLength, R: int = 1, seg: GRanges | None = None,
                exclude: GRanges | None = None, excludeOption=("drop", "trim"), proportionLength: bool = True,
                type=("bootstrap", "permute"), withinChrom: bool = False, *, rng="philox", seed=None, iter0: int = 0,
                perFeature: bool = True, device: int = 0, out: dict | None = None, maxgap: int = -1,
-               minoverlap: int = 0) -> BootCounts:
-    """countOverlaps(x, bootRanges(y, ...), maxgap = , minoverlap = ) per iteration, fused on the GPU."""
+               minoverlap: int = 0, weights: str | None = None) -> BootCounts:
+    """countOverlaps(x, bootRanges(y, ...), maxgap = , minoverlap = ) per iteration, fused on the GPU.
+    weights: name of a numeric metadata column of y; adds its sum over the overlapping bootstrapped ranges per
+    (iteration, feature) -- summarize(sum(signal)) of vignettes/bootRanges.Rmd:532-540."""
     eng, kind, L_b, segd = _setup(y, blockLength, seg, exclude, excludeOption, proportionLength, type, withinChrom, device)
     qi, qs, qe, qstr, qkeep = _side_arrays(x, y, "x")
     eng.set_query(qi, qs, qe, qstr if np.any(qstr) else None, maxgap=maxgap, minoverlap=minoverlap)
@@ -176,4 +180,16 @@ def bootCounts(y: GRanges, x: GRanges, blockLength, R: int = 1, seg: GRanges | N
         full = np.zeros((int(R), len(x)), np.int32)
         full[:, qkeep] = fc
         fc = full
-    return BootCounts(res["iter_totals"], res["iter_nranges"], fc, res["stats"])
+    bc = BootCounts(res["iter_totals"], res["iter_nranges"], fc, res["stats"])
+    if weights is not None:
+        if weights not in y.mcols:
+            raise ValueError(f"{weights!r} is not a metadata column of y")
+        eng.set_weights(y.mcols[weights])
+        ws = eng.run_weighted(draws, want_matrix=perFeature)
+        fs = ws["feature_sums"]
+        if fs is not None and qkeep.size != len(x):
+            full = np.zeros((int(R), len(x)), np.float64)
+            full[:, qkeep] = fs
+            fs = full
+        bc.iter_sums, bc.feature_sums = ws["iter_sums"], fs
+    return bc

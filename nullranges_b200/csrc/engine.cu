@@ -119,6 +119,9 @@ struct nrb200_handle {
     int32_t query_minoverlap = 0, index_minoverlap = 0;  // the index groups y by "narrower than minoverlap": rebuilt when it changes
     int32_t end_shift = 0;
     bool ends_alias_starts = false;
+    // weights of y (nrb200_set_weights): canonical order, class-major order, running sums along start / end order
+    bool have_weights = false, weights_dirty = true;
+    DevMem w_in, w_c, w_r, w_e, w_ps, w_pe, w_keys_e, w_perm_a, w_perm_b, ws_sums, ws_iter;
     DevMem r_start, r_end, r_pmax, r_order, r_idx, r_keys_a, r_keys_b, r_voff_dev, rseq_info_dev, rrank_off_dev, rrank_start;
     DevMem rank_off_dev, max_pos_dev, rank_start, rank_pmax, rank_end, end_sorted, sort_keys_a, sort_keys_b, sort_tmp;
     uint32_t flags = 0;
@@ -389,6 +392,7 @@ int build_rank_tables(nrb200_handle *h) {
     h->n_width = h->query_minoverlap > 0 ? 2 : 1;
     h->n_cls = (y.stranded ? 3 : 1) * h->n_width;
     h->index_minoverlap = h->query_minoverlap;
+    h->weights_dirty = true;  // the class-major order of the weights follows the index
     if (entries * h->n_cls > (int64_t)INT32_MAX) return fail(h, NRB200_ERR_UNSUPPORTED, "rank tables exceed 2^31 entries");
     for (int c = 0; c < C; ++c)  // packed table entries hold a per-sequence index in 29 bits
         if (y.h_seq_off[c + 1] - y.h_seq_off[c] >= (1 << 29)) return fail(h, NRB200_ERR_UNSUPPORTED, "more than 2^29 ranges on one sequence");
@@ -1150,6 +1154,58 @@ int fetch_u64_as_i64(nrb200_handle *h, const DevMem &src, int64_t n, int64_t *ds
 
 }  // namespace
 
+// Weights in the rank path's orders and their running sums (see WeightView, kernels.cuh).
+int build_weight_index(nrb200_handle *h) {
+    if (!h->weights_dirty) return NRB200_OK;
+    RangeSet &y = h->y;
+    const int64_t n = y.n;
+    if (n == 0) {
+        h->weights_dirty = false;
+        return NRB200_OK;
+    }
+    const unsigned grid = (unsigned)((n + 255) / 256);
+    const bool classes = h->n_cls > 1;
+    for (DevMem *m : {&h->w_r, &h->w_e, &h->w_ps, &h->w_pe}) NRB_CUDA(h, m->reserve((size_t)n * 8));
+    const double *w_r = h->w_c.as<double>();
+    if (classes) {
+        gather_f64_kernel<<<grid, 256, 0, h->stream>>>(h->w_c.as<double>(), h->r_order.as<int32_t>(), n, h->w_r.as<double>());
+        w_r = h->w_r.as<double>();
+    }
+    auto scan_by_key = [&](const unsigned *keys, const double *in, double *out) -> int {
+        size_t tmp = 0;
+        NRB_CUDA(h, cub::DeviceScan::InclusiveScanByKey(nullptr, tmp, keys, in, out, AddF64(), n, cub::Equality(), h->stream));
+        NRB_CUDA(h, h->sort_tmp.reserve(tmp));
+        NRB_CUDA(h, cub::DeviceScan::InclusiveScanByKey(h->sort_tmp.p, tmp, keys, in, out, AddF64(), n, cub::Equality(), h->stream));
+        return NRB200_OK;
+    };
+    // virtual-sequence key of every position of the (class-major) start order
+    const unsigned *vkeys = classes ? h->r_keys_b.as<unsigned>() : reinterpret_cast<const unsigned *>(y.seqid.as<int32_t>());
+    int rc;
+    if ((rc = scan_by_key(vkeys, w_r, h->w_ps.as<double>()))) return rc;
+    if (!h->ends_alias_starts) {
+        NRB_CUDA(h, h->sort_keys_a.reserve((size_t)n * 8));
+        NRB_CUDA(h, h->sort_keys_b.reserve((size_t)n * 8));
+        NRB_CUDA(h, h->w_perm_a.reserve((size_t)n * 4));
+        NRB_CUDA(h, h->w_perm_b.reserve((size_t)n * 4));
+        NRB_CUDA(h, h->w_keys_e.reserve((size_t)n * 4));
+        const int32_t *rend = classes ? h->r_end.as<int32_t>() : y.end.as<int32_t>();
+        pack_vend_pairs_kernel<<<grid, 256, 0, h->stream>>>(classes ? h->r_keys_b.as<unsigned>() : nullptr, y.seqid.as<int32_t>(), rend, n,
+                                                            h->sort_keys_a.as<unsigned long long>(), h->w_perm_a.as<int32_t>());
+        size_t tmp = 0;
+        NRB_CUDA(h, cub::DeviceRadixSort::SortPairs(nullptr, tmp, h->sort_keys_a.as<unsigned long long>(), h->sort_keys_b.as<unsigned long long>(),
+                                                    h->w_perm_a.as<int32_t>(), h->w_perm_b.as<int32_t>(), n, 0, 64, h->stream));
+        NRB_CUDA(h, h->sort_tmp.reserve(tmp));
+        NRB_CUDA(h, cub::DeviceRadixSort::SortPairs(h->sort_tmp.p, tmp, h->sort_keys_a.as<unsigned long long>(), h->sort_keys_b.as<unsigned long long>(),
+                                                    h->w_perm_a.as<int32_t>(), h->w_perm_b.as<int32_t>(), n, 0, 64, h->stream));
+        gather_f64_kernel<<<grid, 256, 0, h->stream>>>(w_r, h->w_perm_b.as<int32_t>(), n, h->w_e.as<double>());
+        high32_kernel<<<grid, 256, 0, h->stream>>>(h->sort_keys_b.as<unsigned long long>(), n, h->w_keys_e.as<unsigned>());
+        if ((rc = scan_by_key(h->w_keys_e.as<unsigned>(), h->w_e.as<double>(), h->w_pe.as<double>()))) return rc;
+    }
+    NRB_CUDA(h, cudaGetLastError());
+    h->weights_dirty = false;
+    return NRB200_OK;
+}
+
 extern "C" {
 
 const char *nrb200_version(void) { return "nrb200 0.1.0 (sm_100a)"; }
@@ -1454,6 +1510,89 @@ int nrb200_moments_fetch(nrb200_handle *h, int64_t *feat_sum, int64_t *feat_sums
     if (feat_sumsq) NRB_CUDA(h, cudaMemcpyAsync(feat_sumsq, h->m_sumsq.p, bytes, cudaMemcpyDeviceToHost, h->stream));
     if (feat_n_ge_observed) NRB_CUDA(h, cudaMemcpyAsync(feat_n_ge_observed, h->m_nge.p, bytes, cudaMemcpyDeviceToHost, h->stream));
     if (int rc_sync = sync_stream(h)) return rc_sync;
+    return NRB200_OK;
+}
+
+int nrb200_set_weights(nrb200_handle *h, const double *weights) {
+    if (!h) return NRB200_ERR_INVALID;
+    NRB_CUDA(h, cudaSetDevice(h->device));
+    if (!h->have_y) return fail(h, NRB200_ERR_STATE, "call nrb200_set_ranges() first");
+    if (!weights) {
+        h->have_weights = false;
+        return NRB200_OK;
+    }
+    const int64_t n = h->y.n;
+    int rc;
+    if ((rc = upload_direct(h, h->w_in, weights, (size_t)n))) return rc;
+    NRB_CUDA(h, h->w_c.reserve((size_t)std::max<int64_t>(n, 1) * 8));
+    if (n > 0) {
+        // caller's order -> canonical order (identity when the input was already canonical; else y.src, on the device)
+        gather_f64_kernel<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(h->w_in.as<double>(), h->y.sorted_input ? nullptr : h->y.src.as<int32_t>(),
+                                                                              n, h->w_c.as<double>());
+        NRB_CUDA(h, cudaGetLastError());
+    }
+    if ((rc = sync_stream(h))) return rc;  // the caller's array is no longer read
+    h->have_weights = true;
+    h->weights_dirty = true;
+    return NRB200_OK;
+}
+
+int nrb200_run_weighted(nrb200_handle *h, const nrb200_draws *draws, double *iter_sums, double *feature_sums, nrb200_stats *stats) {
+    if (!h || !draws) return NRB200_ERR_INVALID;
+    NRB_CUDA(h, cudaSetDevice(h->device));
+    int rc;
+    if ((rc = prepare(h))) return rc;
+    if (!h->have_weights) return fail(h, NRB200_ERR_STATE, "nrb200_set_weights() has not been called");
+    if (h->query.n == 0) return fail(h, NRB200_ERR_STATE, "nrb200_set_query() has not been called");
+    if (!rank_path_ok(h, true))
+        return fail(h, NRB200_ERR_UNSUPPORTED, "weighted sums run on the rank path only (segmentation within seqlengths, no NRB200_FLAG_FORCE_STREAM)");
+    if ((rc = build_weight_index(h))) return rc;
+    NRB_CUDA(h, cudaEventRecord(h->ev[0], h->stream));
+    if ((rc = stage_draws(h, draws))) return rc;
+    const int64_t R = draws->n_iter, G = h->query.n, B = h->plan.n_blocks();
+    const int64_t batch = std::max<int64_t>(1, std::min<int64_t>(h->tune_max_batch, ((int64_t)1 << 27) / std::max<int64_t>(G, 1)));
+    NRB_CUDA(h, h->d_iter_nranges.reserve(std::max<int64_t>(R, 1) * 8));
+    NRB_CUDA(h, h->d_n_hits.reserve(16));
+    NRB_CUDA(h, h->ws_iter.reserve(std::max<int64_t>(R, 1) * 8));
+    NRB_CUDA(h, h->ws_sums.reserve((size_t)std::min(batch, std::max<int64_t>(R, 1)) * G * 8));
+    NRB_CUDA(h, h->draw_tab.reserve((size_t)std::min(batch, std::max<int64_t>(R, 1)) * B * sizeof(int2)));
+    NRB_CUDA(h, cudaMemsetAsync(h->d_iter_nranges.p, 0, R * 8, h->stream));
+    NRB_CUDA(h, cudaMemsetAsync(h->d_n_hits.p, 0, 16, h->stream));
+    NRB_CUDA(h, cudaMemsetAsync(h->ws_iter.p, 0, R * 8, h->stream));
+    BootParams P = make_params(h, draws);
+    P.iter_nranges = h->d_iter_nranges.as<unsigned long long>();
+    P.n_hits = h->d_n_hits.as<unsigned long long>();
+    P.draw_tab = h->draw_tab.as<int2>();
+    const FeatView F{h->f_src.as<int32_t>(), h->pair_off.as<int32_t>(), h->pair_rec.as<PairRec>()};
+    const WeightView W{h->n_cls > 1 ? h->w_r.as<double>() : h->w_c.as<double>(), h->w_ps.as<double>(),
+                       h->ends_alias_starts ? h->w_ps.as<double>() : h->w_pe.as<double>()};
+    NRB_CUDA(h, cudaEventRecord(h->ev[1], h->stream));
+    int launches = 0;
+    for (int64_t r0 = 0; r0 < R; r0 += batch) {
+        const int64_t n = std::min(batch, R - r0);
+        const BootParams Q = slice_params(P, r0, n);
+        launches += launch_rank(h, Q, false);  // rows kernel: draws the blocks, fills the draw table
+        boot_rank_wsum_kernel<<<dim3((unsigned)((G + 255) / 256), (unsigned)n), 256, 0, h->stream>>>(Q, F, W, h->ws_sums.as<double>(),
+                                                                                                     h->ws_iter.as<double>() + r0);
+        ++launches;
+        NRB_CUDA(h, cudaGetLastError());
+        if (feature_sums)
+            NRB_CUDA(h, cudaMemcpyAsync(feature_sums + r0 * G, h->ws_sums.p, (size_t)n * G * 8, cudaMemcpyDeviceToHost, h->stream));
+    }
+    NRB_CUDA(h, cudaEventRecord(h->ev[2], h->stream));
+    if (iter_sums && R > 0) NRB_CUDA(h, cudaMemcpyAsync(iter_sums, h->ws_iter.p, R * 8, cudaMemcpyDeviceToHost, h->stream));
+    if ((rc = sync_stream(h))) return rc;
+    if (stats) {
+        float k_ms = 0, t_ms = 0;
+        cudaEventElapsedTime(&k_ms, h->ev[1], h->ev[2]);
+        cudaEventElapsedTime(&t_ms, h->ev[0], h->ev[2]);
+        std::memset(stats, 0, sizeof *stats);
+        stats->kernel_ms = k_ms;
+        stats->total_ms = t_ms;
+        stats->n_launches = launches;
+        stats->n_windows = h->n_pairs;
+        stats->d2h_bytes = (feature_sums ? R * G * 8 : 0) + (iter_sums ? R * 8 : 0);
+    }
     return NRB200_OK;
 }
 

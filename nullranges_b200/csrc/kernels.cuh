@@ -672,6 +672,103 @@ __global__ void __launch_bounds__(256, MINB) boot_rank_count_kernel(const BootPa
     }
 }
 
+// ---- weighted sums on the rank path -----------------------------------------------------------
+// sum of a numeric column of y over the ranges that land on a feature (vignettes/bootRanges.Rmd:532-540:
+// summarize(sum(signal)) per (feature, iter)).  Same windows and ranks as the counts; instead of
+// #{start <= A} - #{end < Bv} it takes the difference of two running sums of the weight, one along the
+// start order and one along the sorted-end order (both restart at every virtual sequence).
+struct WeightView {
+    const double *w;           // weights in the rank path's (class-major) start order
+    const double *ps;          // inclusive running sum of w inside each virtual sequence
+    const double *pe;          // the same along the sorted-end order
+};
+
+__device__ __forceinline__ double run_sum(const double *__restrict__ p, int32_t first, int32_t idx) {
+    return idx > first ? __ldg(p + idx - 1) : 0.0;  // sum of the first (idx - first) elements of the sequence
+}
+__device__ __forceinline__ double sum_spanning(const RangesView &y, const WeightView &W, const int4 si, int32_t ia, int32_t b) {
+    if (b > si.z) return 0.0;
+    double s = 0.0;
+    for (int32_t k = ia - 1; k >= si.x && __ldg(y.rpmax + k) >= b; --k)
+        if (__ldg(y.rend + k) >= b) s += __ldg(W.w + k);
+    return s;
+}
+
+template <bool PERMUTE>
+__device__ __forceinline__ double weighted_pair(const RangesView &y, const WeightView &W, int2 draw, int cls, int32_t width,
+                                                int32_t ts, int32_t seq_len, int32_t ws, int32_t we) {
+    PairProbe q;
+    int32_t ua, ub;
+    q.si = __ldg(y.rseq_info + draw.x * y.n_cls + cls);
+    pair_keys(q, draw, width, ts, seq_len, ws, we, y.rank_shift, y.end_shift, ua, ub);
+    if (q.A < 1 || (PERMUTE && q.A < q.bs)) return 0.0;
+    const int32_t ia = first_ge_ranked(y.rstart, y.rrank_start, y.rank_shift, q.si, q.A + 1);
+    double s;
+    if (q.Bv <= q.A) {
+        const int32_t ib = first_ge_ranked(y.end_sorted, y.rank_end, y.rank_shift, q.si, q.Bv - y.end_shift);
+        s = run_sum(W.ps, q.si.x, ia) - run_sum(W.pe, q.si.x, ib);
+    } else {
+        s = sum_spanning(y, W, q.si, ia, q.Bv);
+    }
+    if (PERMUTE) s -= sum_spanning(y, W, q.si, first_ge_ranked(y.rstart, y.rrank_start, y.rank_shift, q.si, q.bs), q.Bv);
+    return s;
+}
+
+// Thread = (feature, iteration), like boot_rank_count_kernel<1>; sums[r, g] written once, iter_sums by atomics.
+__global__ void __launch_bounds__(256) boot_rank_wsum_kernel(const BootParams P, const FeatView F, const WeightView W,
+                                                             double *__restrict__ sums, double *__restrict__ iter_sums) {
+    __shared__ double warp_tot[8];
+    const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t r = blockIdx.y;
+    double acc = 0.0;
+    if (g < P.n_query) {
+        const int32_t src = __ldg(F.src + g);
+        const int32_t p1 = __ldg(F.pair_off + g + 1);
+        for (int32_t p = __ldg(F.pair_off + g); p < p1; ++p) {
+            const int4 ra = __ldg(reinterpret_cast<const int4 *>(F.pair_rec + p));
+            const int4 rb = __ldg(reinterpret_cast<const int4 *>(F.pair_rec + p) + 1);
+            const int2 d = __ldg(P.draw_tab + r * P.n_blocks + ra.x);
+            const double v = P.permute ? weighted_pair<true>(P.y, W, d, rb.w, rb.y, rb.x, rb.z, ra.y, ra.z)
+                                       : weighted_pair<false>(P.y, W, d, rb.w, rb.y, rb.x, rb.z, ra.y, ra.z);
+            acc += ra.w * v;
+        }
+        if (sums) sums[r * P.n_query + src] = acc;
+    }
+    double t = acc;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(kFull, t, o);
+    if ((threadIdx.x & 31) == 0) warp_tot[threadIdx.x >> 5] = t;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double s = 0.0;
+        for (int w = 0; w < 8; ++w) s += warp_tot[w];
+        if (s != 0.0) atomicAdd(iter_sums + r, s);
+    }
+}
+
+// gathers for the weight arrays: out[i] = in[order[i]] (order == nullptr: identity)
+__global__ void gather_f64_kernel(const double *__restrict__ in, const int32_t *__restrict__ order, int64_t n, double *__restrict__ out) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = in[order ? order[i] : i];
+}
+// sort keys (virtual sequence << 32 | end) with the position as payload: the sorted-end order of the weights
+__global__ void pack_vend_pairs_kernel(const unsigned *__restrict__ vkeys, const int32_t *__restrict__ seqid, const int32_t *__restrict__ end,
+                                       int64_t n, unsigned long long *__restrict__ keys, int32_t *__restrict__ idx) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        const unsigned v = vkeys ? vkeys[i] : (unsigned)seqid[i];
+        keys[i] = ((unsigned long long)v << 32) | (unsigned)end[i];
+        idx[i] = (int32_t)i;
+    }
+}
+__global__ void high32_kernel(const unsigned long long *__restrict__ keys, int64_t n, unsigned *__restrict__ out) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = (unsigned)(keys[i] >> 32);
+}
+struct AddF64 {
+    __host__ __device__ __forceinline__ double operator()(double a, double b) const { return a + b; }
+};
+
 // Per (iteration, block): draws the block (Philox) or reads the caller's draw, records it in the
 // draw table for the count kernel, and counts by ranks the rows the reference's table would hold:
 // hits of the bait block minus (where the variant filters width > 0, R/bootUnsegmented.R:189) the

@@ -169,6 +169,21 @@ class Engine:
         self._check(self._lib.nrb200_moments_fetch(self._h, ptr(s, C.c_int64), ptr(q, C.c_int64), ptr(ge, C.c_int64)))
         return {"iter_nranges": nr, "iter_totals": tot, "sum": s, "sumsq": q, "n_ge_observed": ge, "stats": st.as_dict()}
 
+    def set_weights(self, weights):
+        """One numeric value per range of y (the caller's order) for run_weighted(); None clears."""
+        w = None if weights is None else np.ascontiguousarray(weights, dtype=np.float64)
+        self._check(self._lib.nrb200_set_weights(self._h, ptr(w, C.c_double)))
+
+    def run_weighted(self, draws: Draws, want_matrix: bool = True) -> dict:
+        """Sum of the weights of the bootstrapped ranges overlapping each feature, per iteration."""
+        R, G = int(draws.n_iter), self.n_query
+        it = np.zeros(R, np.float64)
+        fs = np.zeros((R, G), np.float64) if want_matrix else None
+        st = _lib.Stats()
+        d = draws.to_c()
+        self._check(self._lib.nrb200_run_weighted(self._h, C.byref(d), ptr(it, C.c_double), ptr(fs, C.c_double), C.byref(st)))
+        return {"iter_sums": it, "feature_sums": fs, "stats": st.as_dict()}
+
     def count_observed(self, minoverlap: int = 0):
         """countOverlaps(query, y[, minoverlap]) on the ranges as given (no bootstrap)."""
         cnt = np.zeros(self.n_query, np.int32)

@@ -290,3 +290,29 @@ def boot_counts(plan: Plan, y: Index, query: Index | None, R: int, *, exclude: I
 
 def max_threads() -> int:
     return lib().orc_max_threads()
+
+
+def boot_weighted(plan: Plan, y: Index, query: Index, weights, R: int, *, exclude: Index | None = None,
+                  exclude_mode: int = EXCLUDE_DROP, draws=None, seed: int = 0, iter0: int = 0, maxgap: int = -1,
+                  minoverlap: int = 0) -> dict:
+    """Sum of ``weights`` (one per range of y) over the bootstrapped ranges overlapping each feature, per
+    iteration: the vignette's summarize(sum(signal)) per (x_id, iter) (vignettes/bootRanges.Rmd:532-540).
+    Plain Python / numpy over the oracle's rows: small cases only."""
+    w = np.asarray(weights, dtype=np.float64)
+    if draws is None:
+        draws = plan.draw_philox(seed, iter0, R)
+    ystr = y.strand if y.strand is not None else np.zeros(y.n, np.int8)
+    qstr = query.strand if query.strand is not None else np.zeros(query.n, np.int8)
+    m1 = maxgap + 1
+    sums = np.zeros((R, query.n), np.float64)
+    for r in range(R):
+        rows = iteration_rows(plan, y, draws[0][r], draws[1][r], draws[2][r], exclude=exclude, exclude_mode=exclude_mode)
+        for c, s, e, src in zip(rows["chrom"], rows["start"], rows["end"], rows["src"]):
+            if e < s:
+                continue
+            ov = np.minimum(e, query.end) - np.maximum(s, query.start) + 1
+            hit = (query.chrom == c) & (query.start - m1 <= e) & (query.end + m1 >= s) & ((ystr[src] == 0) | (qstr == 0) | (ystr[src] == qstr))
+            if minoverlap > 0:
+                hit &= ov >= minoverlap
+            sums[r, hit] += w[src]
+    return {"feature_sums": sums, "iter_sums": sums.sum(axis=1)}

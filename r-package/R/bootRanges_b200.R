@@ -132,7 +132,7 @@ bootRanges <- function(y, blockLength, R = 1, seg = NULL, exclude = NULL, exclud
 # Returns list(iter_totals, iter_nranges, counts = integer matrix [length(x), R]).
 bootCounts <- function(y, x, blockLength, R = 1, seg = NULL, exclude = NULL, excludeOption = c("drop", "trim"),
                        proportionLength = TRUE, type = c("bootstrap", "permute"), withinChrom = FALSE,
-                       rng = c("philox", "R"), seed = 0, iter0 = 0, perFeature = TRUE, maxgap = -1L, minoverlap = 0L, device = 0L) {
+                       rng = c("philox", "R"), seed = 0, iter0 = 0, perFeature = TRUE, maxgap = -1L, minoverlap = 0L, weights = NULL, device = 0L) {
   excludeOption <- match.arg(excludeOption); type <- match.arg(type); rng <- match.arg(rng)
   s <- .setup(y, blockLength, seg, exclude, excludeOption, proportionLength, type, withinChrom, device)
   keep <- which(as.character(GenomicRanges::seqnames(x)) %in% s$lv)
@@ -146,5 +146,16 @@ bootCounts <- function(y, x, blockLength, R = 1, seg = NULL, exclude = NULL, exc
   if (!is.null(counts) && length(keep) != length(x)) {
     full <- matrix(0L, length(x), R); full[keep, ] <- counts; counts <- full
   }
-  list(iter_nranges = res[[1]], iter_totals = res[[2]], counts = counts)
+  out <- list(iter_nranges = res[[1]], iter_totals = res[[2]], counts = counts)
+  if (!is.null(weights)) {   # sum of a numeric column of y over the overlapping ranges (vignette: summarize(sum(signal)))
+    w <- as.numeric(S4Vectors::mcols(y)[[weights]])
+    ws <- .Call("nrb200_R_run_weighted", s$h, w, as.numeric(R), as.numeric(iter0), as.numeric(seed), d[[1]], d[[2]], d[[3]],
+                as.numeric(length(xk)), perFeature)
+    sums <- ws[[2]]
+    if (!is.null(sums) && length(keep) != length(x)) {
+      full <- matrix(0, length(x), R); full[keep, ] <- sums; sums <- full
+    }
+    out$iter_sums <- ws[[1]]; out$sums <- sums
+  }
+  out
 }

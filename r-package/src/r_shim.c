@@ -154,6 +154,29 @@ SEXP nrb200_R_run_counts(SEXP ptr, SEXP n_iter, SEXP iter0, SEXP seed, SEXP bait
     return out;
 }
 
+/* weighted statistic: list(iter_sums = double[R], sums = double matrix [G x R] or NULL).  weights: double vector
+ * along y (NA rejected). */
+SEXP nrb200_R_run_weighted(SEXP ptr, SEXP weights, SEXP n_iter, SEXP iter0, SEXP seed, SEXP bait_seqid, SEXP bait_start,
+                           SEXP dst_tile, SEXP n_query, SEXP want_matrix) {
+    for (R_xlen_t i = 0, n = XLENGTH(weights); i < n; i++)
+        if (ISNA(REAL(weights)[i])) Rf_error("weights contain NA");
+    check(H(ptr), nrb200_set_weights(H(ptr), REAL(weights)));
+    nrb200_draws d;
+    fill_draws(&d, n_iter, iter0, seed, bait_seqid, bait_start, dst_tile);
+    const R_xlen_t R = (R_xlen_t)d.n_iter, G = (R_xlen_t)Rf_asReal(n_query);
+    SEXP out = PROTECT(Rf_allocVector(VECSXP, 2));
+    SEXP it = Rf_allocVector(REALSXP, R);
+    SET_VECTOR_ELT(out, 0, it);
+    SEXP mat = R_NilValue;
+    if (Rf_asLogical(want_matrix) && G > 0) {
+        mat = Rf_allocMatrix(REALSXP, (int)G, (int)R);
+        SET_VECTOR_ELT(out, 1, mat);
+    }
+    check(H(ptr), nrb200_run_weighted(H(ptr), &d, REAL(it), mat == R_NilValue ? NULL : REAL(mat), NULL));
+    UNPROTECT(1);
+    return out;
+}
+
 /* materialising path: list(lens = double[R], seqid, start, end, src_idx (1-based), block (1-based)) */
 SEXP nrb200_R_run_materialize(SEXP ptr, SEXP n_iter, SEXP iter0, SEXP seed, SEXP bait_seqid, SEXP bait_start, SEXP dst_tile) {
     nrb200_draws d;
@@ -183,6 +206,7 @@ static const R_CallMethodDef call_methods[] = {
     {"nrb200_R_set_exclude", (DL_FUNC)&nrb200_R_set_exclude, 6},
     {"nrb200_R_set_plan", (DL_FUNC)&nrb200_R_set_plan, 7},
     {"nrb200_R_run_counts", (DL_FUNC)&nrb200_R_run_counts, 9},
+    {"nrb200_R_run_weighted", (DL_FUNC)&nrb200_R_run_weighted, 10},
     {"nrb200_R_run_materialize", (DL_FUNC)&nrb200_R_run_materialize, 7},
     {NULL, NULL, 0}};
 

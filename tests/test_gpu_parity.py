@@ -502,3 +502,43 @@ def test_minoverlap(engine, kind, minoverlap):
     from nullranges_b200 import EngineError
     with pytest.raises(EngineError, match="cannot both"):
         engine.set_query(*case["query"], maxgap=5, minoverlap=3)
+
+
+@pytest.mark.parametrize("kind", ALL_KINDS)
+@pytest.mark.parametrize("variant", ["plain", "stranded", "drop", "trim", "maxgap", "minoverlap", "points", "unsorted"])
+def test_weighted_sums(engine, kind, variant):
+    """sum of a numeric column of y over the bootstrapped ranges that overlap each feature (rank path; double
+    arithmetic: relative tolerance 1e-9 against a plain summation over the oracle's rows)."""
+    from nullranges_b200 import EngineError
+    sort = variant != "unsorted" or kind in (0, 5)
+    case = H.random_case(seed=800 + kind, n=500, n_seq=3, n_query=60, stranded=variant == "stranded", n_excl=15 if variant == "drop" else 0,
+                         n_seg=9, n_states=2, wmax=90, points=variant == "points", sort=sort)
+    if variant == "trim":
+        case["excl"], case["trim"] = (np.array([0, 1, 2], np.int32), np.array([300, 900, 50], np.int32), np.array([420, 1500, 80], np.int32), None), True
+    if variant == "maxgap":
+        case["maxgap"] = 30
+    if variant == "minoverlap":
+        case["minoverlap"] = 15
+    plan, y, q, x = H.oracle_objects(case, kind)
+    H.load_engine(engine, case, kind)
+    w = np.random.default_rng(kind).normal(5.0, 2.0, case["y"][0].size)
+    R = 3
+    d = H.draw_R(plan, 4, R)
+    draws = Draws(n_iter=R, rng_mode=_lib.RNG_HOST, bait_seqid=d[0], bait_start=d[1], dst_tile=d[2] if kind >= 4 else None)
+    if engine.force_stream:
+        engine.set_weights(w)
+        with pytest.raises(EngineError, match="rank path"):
+            engine.run_weighted(draws)
+        return
+    engine.set_weights(w)
+    got = engine.run_weighted(draws)
+    ref = O.boot_weighted(plan, y, q, w, R, exclude=x, exclude_mode=H.excl_mode(case), draws=d, maxgap=case.get("maxgap", -1),
+                          minoverlap=case.get("minoverlap", 0))
+    scale = np.abs(w).sum()
+    assert np.allclose(got["feature_sums"], ref["feature_sums"], rtol=1e-9, atol=1e-9 * scale)
+    assert np.allclose(got["iter_sums"], ref["iter_sums"], rtol=1e-9, atol=1e-9 * scale)
+    # unit weights reproduce the counts exactly
+    engine.set_weights(np.ones_like(w))
+    ones = engine.run_weighted(draws)
+    cnt = engine.run_counts(draws)
+    assert np.array_equal(ones["feature_sums"], cnt["feature_counts"].astype(np.float64))
