@@ -1,0 +1,540 @@
+// libnrb200: the extern "C" entry points of include/nrb200.h.  (textually included by engine.cu)
+extern "C" {
+
+const char *nrb200_version(void) { return "nrb200 0.1.0 (sm_100a)"; }
+
+const char *nrb200_last_error(const nrb200_handle *h) { return h ? h->error.c_str() : g_create_error.c_str(); }
+
+int nrb200_create(const nrb200_config *cfg, nrb200_handle **out) {
+    if (!out) return fail(nullptr, NRB200_ERR_INVALID, "nrb200_create: out is NULL");
+    *out = nullptr;
+    const int dev = cfg ? cfg->device : 0;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+        return fail(nullptr, NRB200_ERR_CUDA, std::string("no CUDA device: ") + cudaGetErrorString(e) +
+                                                 " (libnrb200 has no CPU path)");
+    if (dev < 0 || dev >= count) return fail(nullptr, NRB200_ERR_INVALID, "nrb200_create: device ordinal out of range");
+    NRB_CUDA(nullptr, cudaSetDevice(dev));
+    nrb200_handle *h = new nrb200_handle();
+    h->device = dev;
+    h->flags = cfg ? cfg->flags : 0;
+    if (const char *e = getenv("NRB200_RPT")) h->tune_rpt = atoi(e);
+    if (const char *e = getenv("NRB200_MINB")) h->tune_minb = atoi(e);
+    if (const char *e = getenv("NRB200_TABLE_MULT")) h->tune_table_mult = atof(e);
+    if (const char *e = getenv("NRB200_TABLE_CAP")) h->tune_table_cap = atoll(e);
+    if (const char *e = getenv("NRB200_MAX_BATCH")) h->tune_max_batch = std::min<int64_t>(std::max<int64_t>(atoll(e), 8), 2048);
+    if (h->tune_rpt != 1 && h->tune_rpt != 2 && h->tune_rpt != 4 && h->tune_rpt != 8) h->tune_rpt = 1;
+    if (cfg && cfg->stream) {
+        h->stream = (cudaStream_t)cfg->stream;
+    } else {
+        e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
+        if (e != cudaSuccess) {
+            delete h;
+            return fail(nullptr, NRB200_ERR_CUDA, std::string("cudaStreamCreate: ") + cudaGetErrorString(e));
+        }
+        h->own_stream = true;
+    }
+    for (auto &ev : h->ev) cudaEventCreate(&ev);
+    cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, dev);
+    *out = h;
+    return NRB200_OK;
+}
+
+void nrb200_destroy(nrb200_handle *h) {
+    if (!h) return;
+    cudaSetDevice(h->device);
+    cudaStreamSynchronize(h->stream);
+    for (auto &ev : h->ev)
+        if (ev) cudaEventDestroy(ev);
+    for (auto &ev : h->chunk_ev)
+        if (ev) cudaEventDestroy(ev);
+    for (auto &ev : h->batch_ev) cudaEventDestroy(ev);
+    if (h->copy_stream) {
+        cudaStreamSynchronize(h->copy_stream);
+        cudaStreamDestroy(h->copy_stream);
+    }
+    if (h->arena) cudaFreeHost(h->arena);
+    if (h->own_stream) cudaStreamDestroy(h->stream);
+    delete h;
+}
+
+int nrb200_set_ranges(nrb200_handle *h, int64_t n, int32_t n_seq, const int64_t *seqlengths, const int32_t *seqid,
+                      const int32_t *start, const int32_t *end, const int8_t *strand) {
+    if (!h) return NRB200_ERR_INVALID;
+    NRB_CUDA(h, cudaSetDevice(h->device));
+    if (n_seq <= 0 || !seqlengths) return fail(h, NRB200_ERR_INVALID, "seqlengths(y) must be known");
+    for (int c = 0; c < n_seq; ++c) {
+        // stopifnot(all(!is.na(chr_lens)))                          R/bootRanges.R:81
+        if (seqlengths[c] <= 0) return fail(h, NRB200_ERR_INVALID, "all(!is.na(seqlengths(y))) is not TRUE");
+        if (seqlengths[c] >= (1 << 30)) return fail(h, NRB200_ERR_UNSUPPORTED, "seqlengths must be below 2^30");
+    }
+    h->have_y = h->have_plan = false;
+    h->query.n = h->excl.n = 0;  // seqlevels may have changed
+    h->query_minoverlap = 0;
+    h->n_seq = n_seq;
+    h->seqlen.assign(seqlengths, seqlengths + n_seq);
+    int rc;
+    if ((rc = upload(h, h->seqlen_dev, seqlengths, (size_t)n_seq))) return rc;
+    Trace tr("set_ranges");
+    rc = load_y_device(h, n, seqid, start, end, strand);
+    if (rc < 0) return rc;
+    tr.lap("load_y_device");
+    if (rc == 1 && (rc = load_range_set(h, h->y, "y", n, seqid, start, end, strand, true))) return rc;
+    if ((rc = build_rank_tables(h))) return rc;
+    tr.lap("build_rank_tables");
+    // the large host mirror of y is not needed again
+    std::vector<int32_t>().swap(h->y.h_start);
+    std::vector<int32_t>().swap(h->y.h_end);
+    std::vector<int32_t>().swap(h->y.h_pmax);
+    std::vector<int32_t>().swap(h->y.h_src);
+    std::vector<int8_t>().swap(h->y.h_strand);
+    h->have_y = true;
+    h->slices_dirty = true;
+    return NRB200_OK;
+}
+
+int nrb200_ranges_info(const nrb200_handle *h, int32_t *is_sorted, int32_t *is_stranded, int32_t *max_width) {
+    if (!h || !h->have_y) return NRB200_ERR_STATE;
+    if (is_sorted) *is_sorted = h->y.sorted_input;
+    if (is_stranded) *is_stranded = h->y.stranded;
+    if (max_width) *max_width = h->y.wmax;
+    return NRB200_OK;
+}
+
+static int set_side(nrb200_handle *h, RangeSet &rs, const char *what, int64_t n, const int32_t *seqid,
+                    const int32_t *start, const int32_t *end, const int8_t *strand, int32_t widen = 0) {
+    if (!h) return NRB200_ERR_INVALID;
+    NRB_CUDA(h, cudaSetDevice(h->device));
+    if (!h->have_y) return fail(h, NRB200_ERR_STATE, "call nrb200_set_ranges() first (it defines the seqlevels)");
+    h->slices_dirty = true;
+    if (n == 0) {
+        rs.n = 0;
+        return NRB200_OK;
+    }
+    return load_range_set(h, rs, what, n, seqid, start, end, strand, false, &rs == &h->query, widen);
+}
+
+int nrb200_set_query(nrb200_handle *h, int64_t n, const int32_t *seqid, const int32_t *start, const int32_t *end,
+                     const int8_t *strand) {
+    return nrb200_set_query_ex(h, n, seqid, start, end, strand, -1, 0);
+}
+
+// maxgap: two ranges count as overlapping when at most `maxgap` positions separate them
+// (start_q <= end_s + maxgap + 1 and end_q >= start_s - maxgap - 1).  That is plain overlap with every
+// feature widened by maxgap + 1 on both sides, which is how the query is stored; nothing downstream
+// changes.  (Bootstrapped ranges lie inside [1, seqlength], so the widening cannot create overlaps
+// that trim() would have removed.)
+// minoverlap: the intersection must be at least that wide.  On the rank path this is a condition on the window's
+// end points plus "the range itself is at least that wide": y is indexed in width classes (build_rank_tables).
+int nrb200_set_query_ex(nrb200_handle *h, int64_t n, const int32_t *seqid, const int32_t *start, const int32_t *end,
+                        const int8_t *strand, int32_t maxgap, int32_t minoverlap) {
+    if (!h) return NRB200_ERR_INVALID;
+    if (maxgap < -1) return fail(h, NRB200_ERR_INVALID, "'maxgap' must be >= -1");
+    if (maxgap >= (1 << 29)) return fail(h, NRB200_ERR_UNSUPPORTED, "'maxgap' must be below 2^29");
+    if (minoverlap < 0) return fail(h, NRB200_ERR_INVALID, "'minoverlap' must be >= 0");
+    if (minoverlap > 0 && maxgap != -1) return fail(h, NRB200_ERR_INVALID, "'maxgap' and 'minoverlap' cannot both be set");
+    const int rc = set_side(h, h->query, "query", n, seqid, start, end, strand, maxgap + 1);
+    if (rc == NRB200_OK) {
+        h->query_widen = maxgap + 1;
+        h->query_minoverlap = n > 0 ? minoverlap : 0;
+    }
+    return rc;
+}
+
+int nrb200_set_exclude(nrb200_handle *h, int64_t n, const int32_t *seqid, const int32_t *start, const int32_t *end,
+                       const int8_t *strand) {
+    return set_side(h, h->excl, "exclude", n, seqid, start, end, strand);
+}
+
+int nrb200_set_exclude_option(nrb200_handle *h, int32_t option) {
+    if (!h) return NRB200_ERR_INVALID;
+    if (option != NRB200_EXCLUDE_DROP && option != NRB200_EXCLUDE_TRIM)
+        return fail(h, NRB200_ERR_INVALID, "'excludeOption' should be one of 'drop', 'trim'");
+    // stopifnot(all(strand(exclude) == "*"))                       R/bootRanges.R:84
+    if (option == NRB200_EXCLUDE_TRIM && h->excl.n > 0 && h->excl.stranded)
+        return fail(h, NRB200_ERR_INVALID, "all(strand(exclude) == \"*\") is not TRUE");
+    h->excl_option = option;
+    h->slices_dirty = true;
+    return NRB200_OK;
+}
+
+int nrb200_set_plan(nrb200_handle *h, const nrb200_plan_spec *spec, int64_t *n_blocks) {
+    if (!h || !spec) return NRB200_ERR_INVALID;
+    NRB_CUDA(h, cudaSetDevice(h->device));
+    if (!h->have_y) return fail(h, NRB200_ERR_STATE, "call nrb200_set_ranges() first (the plan needs seqlengths)");
+    Plan p;
+    const std::string msg = build_plan(*spec, h->seqlen, p);
+    if (!msg.empty()) return fail(h, NRB200_ERR_INVALID, msg);
+    if (p.n_blocks() > (int64_t)INT32_MAX / 2) return fail(h, NRB200_ERR_UNSUPPORTED, "too many blocks per iteration");
+    h->plan = std::move(p);
+    const Plan &pl = h->plan;
+    const size_t B = (size_t)pl.n_blocks();
+    int rc;
+    if ((rc = upload(h, h->tile_seq, pl.tile_seq.data(), B))) return rc;
+    if ((rc = upload(h, h->tile_start, pl.tile_start.data(), B))) return rc;
+    if ((rc = upload(h, h->bait_width, pl.bait_width.data(), B))) return rc;
+    // sampler tables packed into one int64 and one int32 buffer
+    std::vector<int64_t> i64;
+    std::vector<int32_t> i32;
+    auto put64 = [&](const std::vector<int64_t> &v) { size_t o = i64.size(); i64.insert(i64.end(), v.begin(), v.end()); return o; };
+    auto put32 = [&](const std::vector<int32_t> &v) { size_t o = i32.size(); i32.insert(i32.end(), v.begin(), v.end()); return o; };
+    const size_t o_cum = put64(pl.seq_cum), o_tps = put64(pl.tiles_per_seq), o_sbo = put64(pl.state_block_off),
+                 o_sso = put64(pl.state_seg_off), o_sl = put64(pl.state_len), o_sbl = put64(pl.state_block_len),
+                 o_sgc = put64(pl.sg_cum);
+    const size_t o_sq = put32(pl.sg_seq), o_ss = put32(pl.sg_start), o_st = put32(pl.sg_tiles);
+    if ((rc = upload(h, h->sampler_i64, i64.data(), i64.size()))) return rc;
+    if ((rc = upload(h, h->sampler_i32, i32.data(), i32.size()))) return rc;
+    const int64_t *b64 = h->sampler_i64.as<int64_t>();
+    const int32_t *b32 = h->sampler_i32.as<int32_t>();
+    h->sampler_view = SamplerView{pl.kind, pl.n_seq, pl.n_states, pl.block_length, pl.genome_length,
+                                  b64 + o_cum, b64 + o_tps, b64 + o_sbo, b64 + o_sso, b64 + o_sl, b64 + o_sbl,
+                                  b64 + o_sgc, b32 + o_sq, b32 + o_ss, b32 + o_st};
+    h->have_plan = true;
+    h->slices_dirty = true;
+    if (n_blocks) *n_blocks = pl.n_blocks();
+    return NRB200_OK;
+}
+
+int nrb200_get_tiles(const nrb200_handle *h, int32_t *tile_seqid, int32_t *tile_start, int32_t *bait_width) {
+    if (!h || !h->have_plan) return NRB200_ERR_STATE;
+    const size_t bytes = (size_t)h->plan.n_blocks() * sizeof(int32_t);
+    if (tile_seqid) std::memcpy(tile_seqid, h->plan.tile_seq.data(), bytes);
+    if (tile_start) std::memcpy(tile_start, h->plan.tile_start.data(), bytes);
+    if (bait_width) std::memcpy(bait_width, h->plan.bait_width.data(), bytes);
+    return NRB200_OK;
+}
+
+int nrb200_run_counts_resident(nrb200_handle *h, const nrb200_draws *draws, int32_t want_feature_counts,
+                               nrb200_stats *stats) {
+    if (!h) return NRB200_ERR_INVALID;
+    NRB_CUDA(h, cudaSetDevice(h->device));
+    return run_counts_core(h, draws, want_feature_counts != 0, nullptr, stats);
+}
+
+int nrb200_resident_pointers(const nrb200_handle *h, void **iter_nranges_dev, void **iter_totals_dev,
+                             void **feature_counts_dev) {
+    if (!h) return NRB200_ERR_INVALID;
+    if (iter_nranges_dev) *iter_nranges_dev = h->d_iter_nranges.p;
+    if (iter_totals_dev) *iter_totals_dev = h->d_iter_totals.p;
+    if (feature_counts_dev) *feature_counts_dev = h->res_has_counts ? h->d_counts.p : nullptr;
+    return NRB200_OK;
+}
+
+int nrb200_run_counts(nrb200_handle *h, const nrb200_draws *draws, int64_t *iter_nranges, int64_t *iter_totals,
+                      int32_t *feature_counts, nrb200_stats *stats) {
+    if (!h) return NRB200_ERR_INVALID;
+    NRB_CUDA(h, cudaSetDevice(h->device));
+    int rc = run_counts_core(h, draws, feature_counts != nullptr, feature_counts, stats);
+    if (rc) return rc;
+    const int64_t R = draws->n_iter, G = h->query.n;
+    if ((rc = fetch_u64_as_i64(h, h->d_iter_nranges, R, iter_nranges))) return rc;
+    if ((rc = fetch_u64_as_i64(h, h->d_iter_totals, R, iter_totals))) return rc;
+    if (int rc_sync = sync_stream(h)) return rc_sync;
+    if (h->copy_stream) NRB_CUDA(h, cudaStreamSynchronize(h->copy_stream));
+    if (stats) stats->d2h_bytes = (iter_nranges ? R * 8 : 0) + (iter_totals ? R * 8 : 0) + (feature_counts ? R * G * 4 : 0);
+    return NRB200_OK;
+}
+
+int nrb200_moments_reset(nrb200_handle *h) {
+    if (!h) return NRB200_ERR_INVALID;
+    NRB_CUDA(h, cudaSetDevice(h->device));
+    const int64_t G = h->query.n;
+    if (G == 0) return fail(h, NRB200_ERR_STATE, "moments need a query (nrb200_set_query)");
+    NRB_CUDA(h, h->m_sum.reserve(G * 8));
+    NRB_CUDA(h, h->m_sumsq.reserve(G * 8));
+    NRB_CUDA(h, h->m_nge.reserve(G * 8));
+    NRB_CUDA(h, cudaMemsetAsync(h->m_sum.p, 0, G * 8, h->stream));
+    NRB_CUDA(h, cudaMemsetAsync(h->m_sumsq.p, 0, G * 8, h->stream));
+    NRB_CUDA(h, cudaMemsetAsync(h->m_nge.p, 0, G * 8, h->stream));
+    h->moments_ready = true;
+    return NRB200_OK;
+}
+
+int nrb200_run_moments(nrb200_handle *h, const nrb200_draws *draws, int64_t batch_iter, const int32_t *observed,
+                       int64_t *iter_nranges, int64_t *iter_totals, nrb200_stats *stats) {
+    if (!h || !draws) return NRB200_ERR_INVALID;
+    NRB_CUDA(h, cudaSetDevice(h->device));
+    const int64_t G = h->query.n;
+    if (G == 0) return fail(h, NRB200_ERR_STATE, "moments need a query (nrb200_set_query)");
+    int rc;
+    if (!h->moments_ready && (rc = nrb200_moments_reset(h))) return rc;
+    if (observed && (rc = upload(h, h->m_observed, observed, (size_t)G))) return rc;
+    if (batch_iter <= 0) batch_iter = std::max<int64_t>(1, std::min<int64_t>(draws->n_iter, ((int64_t)1 << 28) / std::max<int64_t>(G, 1)));
+    const int64_t B = h->plan.n_blocks();
+    nrb200_stats acc{};
+    for (int64_t r0 = 0; r0 < draws->n_iter; r0 += batch_iter) {
+        nrb200_draws d = *draws;
+        d.n_iter = std::min(batch_iter, draws->n_iter - r0);
+        d.iter0 = draws->iter0 + r0;
+        if (draws->rng_mode == NRB200_RNG_HOST) {
+            d.bait_seqid = draws->bait_seqid + r0 * B;
+            d.bait_start = draws->bait_start + r0 * B;
+            d.dst_tile = draws->dst_tile ? draws->dst_tile + r0 * B : nullptr;
+        }
+        nrb200_stats st{};
+        if ((rc = run_counts_core(h, &d, true, nullptr, &st))) return rc;
+        const int threads = 256;
+        accumulate_moments_kernel<<<(unsigned)((G + threads - 1) / threads), threads, 0, h->stream>>>(
+            h->d_counts.as<int32_t>(), d.n_iter, G, observed ? h->m_observed.as<int32_t>() : nullptr,
+            h->m_sum.as<long long>(), h->m_sumsq.as<long long>(), h->m_nge.as<long long>());
+        NRB_CUDA(h, cudaGetLastError());
+        if ((rc = fetch_u64_as_i64(h, h->d_iter_nranges, d.n_iter, iter_nranges ? iter_nranges + r0 : nullptr))) return rc;
+        if ((rc = fetch_u64_as_i64(h, h->d_iter_totals, d.n_iter, iter_totals ? iter_totals + r0 : nullptr))) return rc;
+        if (int rc_sync = sync_stream(h)) return rc_sync;
+        acc.kernel_ms += st.kernel_ms;
+        acc.rows_kernel_ms += st.rows_kernel_ms;
+        acc.count_kernel_ms += st.count_kernel_ms;
+        acc.total_ms += st.total_ms;
+        acc.n_launches += st.n_launches + 1;
+        acc.n_hits += st.n_hits;
+        acc.h2d_bytes += st.h2d_bytes;
+    }
+    if (stats) *stats = acc;
+    return NRB200_OK;
+}
+
+int nrb200_moments_fetch(nrb200_handle *h, int64_t *feat_sum, int64_t *feat_sumsq, int64_t *feat_n_ge_observed) {
+    if (!h) return NRB200_ERR_INVALID;
+    if (!h->moments_ready) return fail(h, NRB200_ERR_STATE, "no moments accumulated");
+    NRB_CUDA(h, cudaSetDevice(h->device));
+    const size_t bytes = (size_t)h->query.n * 8;
+    if (feat_sum) NRB_CUDA(h, cudaMemcpyAsync(feat_sum, h->m_sum.p, bytes, cudaMemcpyDeviceToHost, h->stream));
+    if (feat_sumsq) NRB_CUDA(h, cudaMemcpyAsync(feat_sumsq, h->m_sumsq.p, bytes, cudaMemcpyDeviceToHost, h->stream));
+    if (feat_n_ge_observed) NRB_CUDA(h, cudaMemcpyAsync(feat_n_ge_observed, h->m_nge.p, bytes, cudaMemcpyDeviceToHost, h->stream));
+    if (int rc_sync = sync_stream(h)) return rc_sync;
+    return NRB200_OK;
+}
+
+int nrb200_set_weights(nrb200_handle *h, const double *weights) {
+    if (!h) return NRB200_ERR_INVALID;
+    NRB_CUDA(h, cudaSetDevice(h->device));
+    if (!h->have_y) return fail(h, NRB200_ERR_STATE, "call nrb200_set_ranges() first");
+    if (!weights) {
+        h->have_weights = false;
+        return NRB200_OK;
+    }
+    const int64_t n = h->y.n;
+    int rc;
+    if ((rc = upload_direct(h, h->w_in, weights, (size_t)n))) return rc;
+    NRB_CUDA(h, h->w_c.reserve((size_t)std::max<int64_t>(n, 1) * 8));
+    if (n > 0) {
+        // caller's order -> canonical order (identity when the input was already canonical; else y.src, on the device)
+        gather_f64_kernel<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(h->w_in.as<double>(), h->y.sorted_input ? nullptr : h->y.src.as<int32_t>(),
+                                                                              n, h->w_c.as<double>());
+        NRB_CUDA(h, cudaGetLastError());
+    }
+    if ((rc = sync_stream(h))) return rc;  // the caller's array is no longer read
+    h->have_weights = true;
+    h->weights_dirty = true;
+    return NRB200_OK;
+}
+
+int nrb200_run_weighted(nrb200_handle *h, const nrb200_draws *draws, double *iter_sums, double *feature_sums, nrb200_stats *stats) {
+    if (!h || !draws) return NRB200_ERR_INVALID;
+    NRB_CUDA(h, cudaSetDevice(h->device));
+    int rc;
+    if ((rc = prepare(h))) return rc;
+    if (!h->have_weights) return fail(h, NRB200_ERR_STATE, "nrb200_set_weights() has not been called");
+    if (h->query.n == 0) return fail(h, NRB200_ERR_STATE, "nrb200_set_query() has not been called");
+    if (!rank_path_ok(h, true))
+        return fail(h, NRB200_ERR_UNSUPPORTED, "weighted sums run on the rank path only (segmentation within seqlengths, no NRB200_FLAG_FORCE_STREAM)");
+    if ((rc = build_weight_index(h))) return rc;
+    NRB_CUDA(h, cudaEventRecord(h->ev[0], h->stream));
+    if ((rc = stage_draws(h, draws))) return rc;
+    const int64_t R = draws->n_iter, G = h->query.n, B = h->plan.n_blocks();
+    const int64_t batch = std::max<int64_t>(1, std::min<int64_t>(h->tune_max_batch, ((int64_t)1 << 27) / std::max<int64_t>(G, 1)));
+    NRB_CUDA(h, h->d_iter_nranges.reserve(std::max<int64_t>(R, 1) * 8));
+    NRB_CUDA(h, h->d_n_hits.reserve(16));
+    NRB_CUDA(h, h->ws_iter.reserve(std::max<int64_t>(R, 1) * 8));
+    NRB_CUDA(h, h->ws_sums.reserve((size_t)std::min(batch, std::max<int64_t>(R, 1)) * G * 8));
+    NRB_CUDA(h, h->draw_tab.reserve((size_t)std::min(batch, std::max<int64_t>(R, 1)) * B * sizeof(int2)));
+    NRB_CUDA(h, cudaMemsetAsync(h->d_iter_nranges.p, 0, R * 8, h->stream));
+    NRB_CUDA(h, cudaMemsetAsync(h->d_n_hits.p, 0, 16, h->stream));
+    NRB_CUDA(h, cudaMemsetAsync(h->ws_iter.p, 0, R * 8, h->stream));
+    BootParams P = make_params(h, draws);
+    P.iter_nranges = h->d_iter_nranges.as<unsigned long long>();
+    P.n_hits = h->d_n_hits.as<unsigned long long>();
+    P.draw_tab = h->draw_tab.as<int2>();
+    const FeatView F{h->f_src.as<int32_t>(), h->pair_off.as<int32_t>(), h->pair_rec.as<PairRec>()};
+    const WeightView W{h->n_cls > 1 ? h->w_r.as<double>() : h->w_c.as<double>(), h->w_ps.as<double>(),
+                       h->ends_alias_starts ? h->w_ps.as<double>() : h->w_pe.as<double>()};
+    NRB_CUDA(h, cudaEventRecord(h->ev[1], h->stream));
+    int launches = 0;
+    for (int64_t r0 = 0; r0 < R; r0 += batch) {
+        const int64_t n = std::min(batch, R - r0);
+        const BootParams Q = slice_params(P, r0, n);
+        launches += launch_rank(h, Q, false);  // rows kernel: draws the blocks, fills the draw table
+        boot_rank_wsum_kernel<<<dim3((unsigned)((G + 255) / 256), (unsigned)n), 256, 0, h->stream>>>(Q, F, W, h->ws_sums.as<double>(),
+                                                                                                     h->ws_iter.as<double>() + r0);
+        ++launches;
+        NRB_CUDA(h, cudaGetLastError());
+        if (feature_sums)
+            NRB_CUDA(h, cudaMemcpyAsync(feature_sums + r0 * G, h->ws_sums.p, (size_t)n * G * 8, cudaMemcpyDeviceToHost, h->stream));
+    }
+    NRB_CUDA(h, cudaEventRecord(h->ev[2], h->stream));
+    if (iter_sums && R > 0) NRB_CUDA(h, cudaMemcpyAsync(iter_sums, h->ws_iter.p, R * 8, cudaMemcpyDeviceToHost, h->stream));
+    if ((rc = sync_stream(h))) return rc;
+    if (stats) {
+        float k_ms = 0, t_ms = 0;
+        cudaEventElapsedTime(&k_ms, h->ev[1], h->ev[2]);
+        cudaEventElapsedTime(&t_ms, h->ev[0], h->ev[2]);
+        std::memset(stats, 0, sizeof *stats);
+        stats->kernel_ms = k_ms;
+        stats->total_ms = t_ms;
+        stats->n_launches = launches;
+        stats->n_windows = h->n_pairs;
+        stats->d2h_bytes = (feature_sums ? R * G * 8 : 0) + (iter_sums ? R * 8 : 0);
+    }
+    return NRB200_OK;
+}
+
+int nrb200_count_observed(nrb200_handle *h, int32_t *feature_counts, int64_t *total) {
+    return nrb200_count_observed_ex(h, 0, feature_counts, total);
+}
+
+int nrb200_count_observed_ex(nrb200_handle *h, int32_t minoverlap, int32_t *feature_counts, int64_t *total) {
+    if (!h) return NRB200_ERR_INVALID;
+    NRB_CUDA(h, cudaSetDevice(h->device));
+    if (minoverlap < 0) return fail(h, NRB200_ERR_INVALID, "'minoverlap' must be >= 0");
+    if (minoverlap > 0 && h->query_widen > 0) return fail(h, NRB200_ERR_INVALID, "'maxgap' and 'minoverlap' cannot both be set");
+    if (!h->have_y) return fail(h, NRB200_ERR_STATE, "nrb200_set_ranges() has not been called");
+    if (h->query.n == 0) return fail(h, NRB200_ERR_STATE, "nrb200_set_query() has not been called");
+    {
+        int rc0 = range_set_to_device(h, h->query);
+        if (rc0) return rc0;
+    }
+    const RangeSet &q = h->query;
+    DevMem counts, tot;
+    NRB_CUDA(h, counts.reserve(q.n * 4));
+    NRB_CUDA(h, tot.reserve(8));
+    NRB_CUDA(h, cudaMemsetAsync(counts.p, 0, q.n * 4, h->stream));
+    NRB_CUDA(h, cudaMemsetAsync(tot.p, 0, 8, h->stream));
+    const RangeSet &y = h->y;
+    RangesView yv{};
+    yv.start = y.start.as<int32_t>();
+    yv.end = y.end.as<int32_t>();
+    yv.strand = y.stranded ? y.strand.as<int8_t>() : nullptr;
+    const int threads = 256;
+    const unsigned grid = (unsigned)((y.n + threads - 1) / threads);
+    if (y.n > 0) {
+        if (y.stranded && q.stranded)
+            count_observed_kernel<true><<<grid, threads, 0, h->stream>>>(yv, y.n, y.seqid.as<int32_t>(), q.start.as<int32_t>(),
+                q.end.as<int32_t>(), q.pmax.as<int32_t>(), q.strand.as<int8_t>(), q.src.as<int32_t>(), q.seq_off.as<int32_t>(),
+                minoverlap, counts.as<int32_t>(), tot.as<unsigned long long>());
+        else
+            count_observed_kernel<false><<<grid, threads, 0, h->stream>>>(yv, y.n, y.seqid.as<int32_t>(), q.start.as<int32_t>(),
+                q.end.as<int32_t>(), q.pmax.as<int32_t>(), nullptr, q.src.as<int32_t>(), q.seq_off.as<int32_t>(),
+                minoverlap, counts.as<int32_t>(), tot.as<unsigned long long>());
+        NRB_CUDA(h, cudaGetLastError());
+    }
+    unsigned long long t = 0;
+    if (feature_counts) NRB_CUDA(h, cudaMemcpyAsync(feature_counts, counts.p, q.n * 4, cudaMemcpyDeviceToHost, h->stream));
+    NRB_CUDA(h, cudaMemcpyAsync(&t, tot.p, 8, cudaMemcpyDeviceToHost, h->stream));
+    if (int rc_sync = sync_stream(h)) return rc_sync;
+    if (total) *total = (int64_t)t;
+    return NRB200_OK;
+}
+
+int nrb200_run_materialize(nrb200_handle *h, const nrb200_draws *draws, int64_t *iter_offsets, nrb200_stats *stats) {
+    if (!h || !draws) return NRB200_ERR_INVALID;
+    NRB_CUDA(h, cudaSetDevice(h->device));
+    int rc;
+    if ((rc = prepare(h))) return rc;
+    if ((rc = ensure_pmax_table(h))) return rc;  // the fill kernel locates the hit windows
+    NRB_CUDA(h, cudaEventRecord(h->ev[0], h->stream));
+    if ((rc = stage_draws(h, draws))) return rc;
+    const int64_t R = draws->n_iter, B = h->plan.n_blocks(), items = R * B;
+    NRB_CUDA(h, h->d_iter_nranges.reserve(std::max<int64_t>(R, 1) * 8));
+    NRB_CUDA(h, h->d_n_hits.reserve(16));  // [0] hits, [1] fill-overflow flag
+    NRB_CUDA(h, h->item_rows.reserve(std::max<int64_t>(items, 1) * 4));
+    NRB_CUDA(h, h->within_off.reserve(std::max<int64_t>(items, 1) * 4));
+    NRB_CUDA(h, h->iter_off_dev.reserve((R + 1) * 8));
+    NRB_CUDA(h, cudaMemsetAsync(h->d_iter_nranges.p, 0, R * 8, h->stream));
+    NRB_CUDA(h, cudaMemsetAsync(h->d_n_hits.p, 0, 16, h->stream));
+    BootParams P = make_params(h, draws);
+    P.n_query = 0;
+    P.iter_nranges = h->d_iter_nranges.as<unsigned long long>();
+    P.iter_totals = nullptr;
+    P.item_rows = h->item_rows.as<int32_t>();
+    P.n_hits = h->d_n_hits.as<unsigned long long>();
+    NRB_CUDA(h, cudaEventRecord(h->ev[1], h->stream));
+    int count_launches = 0;
+    const bool rank_rows = rank_path_ok(h, false);
+    if (rank_rows && items > 0) {  // the rows kernel leaves each block's draw and hit window for the fill kernel
+        NRB_CUDA(h, h->item_rec.reserve((size_t)items * sizeof(int4)));
+        P.item_rec = h->item_rec.as<int4>();
+    }
+    for (int64_t r0 = 0; r0 < R; r0 += kMaxBatch) {
+        BootParams Q = slice_params(P, r0, std::min(kMaxBatch, R - r0));
+        count_launches += launch_count(h, Q, false);
+        NRB_CUDA(h, cudaGetLastError());
+    }
+    if (R > 0)
+        scan_iteration_kernel<<<(unsigned)R, 256, 0, h->stream>>>(h->item_rows.as<int32_t>(), B, h->within_off.as<int32_t>());
+    NRB_CUDA(h, cudaGetLastError());
+    std::vector<int64_t> per_iter(R), offs(R + 1, 0);
+    if ((rc = fetch_u64_as_i64(h, h->d_iter_nranges, R, per_iter.data()))) return rc;
+    if (int rc_sync = sync_stream(h)) return rc_sync;
+    for (int64_t r = 0; r < R; ++r) offs[r + 1] = offs[r] + per_iter[r];
+    const int64_t rows = offs[R];
+    if ((rc = upload(h, h->iter_off_dev, offs.data(), (size_t)R + 1))) return rc;
+    for (DevMem *m : {&h->row_seq, &h->row_start, &h->row_end, &h->row_src, &h->row_block})
+        NRB_CUDA(h, m->reserve(std::max<int64_t>(rows, 1) * 4));
+    int fill_launches = 0;
+    if (items > 0) {
+        const bool st = h->y.stranded && h->excl.n && active_excl(h).stranded;
+        const int excl = excl_kind(h);
+        const int64_t kFillBatch = 32768;  // gridDim.y
+        for (int64_t r0 = 0; r0 < R; r0 += kFillBatch, ++fill_launches) {
+            BootParams Q = slice_params(P, r0, std::min(kFillBatch, R - r0));
+            const RowsOut O{h->row_seq.as<int32_t>(), h->row_start.as<int32_t>(), h->row_end.as<int32_t>(), h->row_src.as<int32_t>(),
+                            h->row_block.as<int32_t>(), h->iter_off_dev.as<int64_t>() + r0, h->within_off.as<int32_t>() + r0 * B,
+                            h->item_rows.as<int32_t>() + r0 * B, reinterpret_cast<int *>(h->d_n_hits.as<char>() + 8)};
+            const dim3 grid((unsigned)std::min<int64_t>((B + 7) / 8, 65535), (unsigned)Q.n_iter);
+            if (excl == kExclTrim) boot_fill_trim_kernel<<<grid, 256, 0, h->stream>>>(Q, O);
+            else if (st) boot_fill_kernel<true, kExclDrop><<<grid, 256, 0, h->stream>>>(Q, O);
+            else if (excl == kExclDrop) boot_fill_kernel<false, kExclDrop><<<grid, 256, 0, h->stream>>>(Q, O);
+            else boot_fill_kernel<false, kExclNone><<<grid, 256, 0, h->stream>>>(Q, O);
+            NRB_CUDA(h, cudaGetLastError());
+        }
+    }
+    NRB_CUDA(h, cudaEventRecord(h->ev[2], h->stream));
+    unsigned long long hits_and_flag[2] = {0, 0};
+    NRB_CUDA(h, cudaMemcpyAsync(hits_and_flag, h->d_n_hits.p, 16, cudaMemcpyDeviceToHost, h->stream));
+    if (int rc_sync = sync_stream(h)) return rc_sync;
+    if (hits_and_flag[1] != 0) {
+        h->n_rows = 0;
+        return fail(h, NRB200_ERR_STATE, "internal error: the count and fill passes of the table disagree (no row was written out of place)");
+    }
+    h->n_rows = rows;
+    if (iter_offsets) std::memcpy(iter_offsets, offs.data(), (size_t)(R + 1) * 8);
+    if (stats) {
+        float k_ms = 0, t_ms = 0;
+        cudaEventElapsedTime(&k_ms, h->ev[1], h->ev[2]);
+        cudaEventElapsedTime(&t_ms, h->ev[0], h->ev[2]);
+        const unsigned long long hits = hits_and_flag[0];
+        std::memset(stats, 0, sizeof *stats);
+        stats->kernel_ms = k_ms;
+        stats->total_ms = t_ms;
+        stats->n_launches = items > 0 ? count_launches + 1 + fill_launches : 0;
+        stats->n_hits = (int64_t)hits;
+    }
+    return NRB200_OK;
+}
+
+int nrb200_fetch_rows(nrb200_handle *h, int64_t row0, int64_t n, int32_t *seqid, int32_t *start, int32_t *end,
+                      int32_t *src_idx, int32_t *block) {
+    if (!h) return NRB200_ERR_INVALID;
+    NRB_CUDA(h, cudaSetDevice(h->device));
+    if (row0 < 0 || n < 0 || row0 + n > h->n_rows) return fail(h, NRB200_ERR_INVALID, "fetch_rows: range outside the materialised table");
+    struct { int32_t *dst; DevMem *src; } cols[] = {{seqid, &h->row_seq}, {start, &h->row_start}, {end, &h->row_end},
+                                                     {src_idx, &h->row_src}, {block, &h->row_block}};
+    for (auto &c : cols)
+        if (c.dst && n)
+            NRB_CUDA(h, cudaMemcpyAsync(c.dst, c.src->as<int32_t>() + row0, n * 4, cudaMemcpyDeviceToHost, h->stream));
+    if (int rc_sync = sync_stream(h)) return rc_sync;
+    return NRB200_OK;
+}
+
+}  // extern "C"

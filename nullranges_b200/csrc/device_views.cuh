@@ -1,0 +1,188 @@
+// Device-side views of the engine's buffers, the searches and direct-address rank tables, Philox block draws.
+// (part of kernels.cuh)
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#include "../../include/nrb200.h"
+#include "philox.cuh"
+
+namespace nrb {
+
+
+constexpr int kWarp = 32;
+constexpr unsigned kFull = 0xffffffffu;
+
+// ---- device views ---------------------------------------------------------------------
+
+struct RangesView {            // canonical (seqname, start, end) order
+    const int32_t *start;
+    const int32_t *end;
+    const int32_t *pmax;       // running max of end within the sequence
+    const int8_t *strand;      // nullptr when every strand is '*'
+    const int32_t *src;        // index in the caller's order; nullptr = identity (the input was already canonical)
+    const int32_t *seq_off;    // [n_seq + 1]
+    const int4 *seq_info;      // [n_seq] {seq_off[c], seq_off[c+1], max_pos[c], first table entry} in one 16-byte load
+    const uint32_t *rank_start;  // packed rank tables over start / pmax, see "direct-address rank tables" below
+    const uint32_t *rank_pmax;
+    int rank_shift;
+    // Rank path.  When strand can matter the ranges are ALSO kept grouped by strand class inside each
+    // sequence ("virtual sequence" v = seq * n_cls + class), so that a count can be taken per class; class =
+    // strand class ('*', '+', '-' when y is stranded) x width class (ranges narrower than the query's
+    // minoverlap can never count).  With one class (n_cls = 1) these alias the canonical arrays.
+    int n_cls;
+    const int32_t *rstart, *rend, *rpmax;   // (seq, class, start, end) order
+    const int32_t *end_sorted;               // ends ascending inside each virtual sequence
+    int32_t end_shift;                       // all ranges equally wide (w): end order = start order, end_sorted aliases
+                                             // rstart and #{end < b} = #{start < b - (w - 1)}; end_shift = w - 1, else 0
+    const int4 *rseq_info;                   // [n_seq * n_cls]
+    const uint32_t *rrank_start, *rank_end;  // tables over rstart / end_sorted
+};
+
+struct SliceView {             // query or exclude (or, for "trim", the gaps), canonical order, plus a per-tile window
+    const int32_t *start;
+    const int32_t *end;
+    const int32_t *pmax;       // running max of end inside the sequence
+    const int8_t *strand;
+    const int32_t *src;
+    const int32_t *tile_lo;    // [n_blocks] first candidate of the tile
+    const int32_t *tile_hi;    // [n_blocks] one past the last
+};
+
+struct SamplerView {
+    int kind, n_seq, n_states;
+    int64_t block_length, genome_length;
+    const int64_t *seq_cum, *tiles_per_seq;
+    const int64_t *state_block_off, *state_seg_off, *state_len, *state_block_len;
+    const int64_t *sg_cum;
+    const int32_t *sg_seq, *sg_start, *sg_tiles;
+};
+
+struct BootParams {
+    RangesView y;
+    SliceView query, excl;
+    SamplerView sampler;
+    // iteration-invariant block tables
+    int64_t n_blocks;
+    const int32_t *tile_seq, *tile_start, *bait_width;
+    const int64_t *seqlen;
+    int permute, drop_zero;
+    int rows_windows_only;    // rank path, excludeOption = "trim": rows = sum of the tile's gap windows
+    int32_t minoverlap;       // countOverlaps(minoverlap =): smallest intersection width that counts (0 = any)
+    // draws
+    int rng_mode;
+    uint64_t seed;
+    int64_t iter0;            // global index of local iteration 0 (Philox counter)
+    const int32_t *bait_seq, *bait_start, *dst_tile;  // [n_iter x n_blocks] (host draws)
+    // outputs
+    int64_t n_iter, n_query;
+    unsigned long long *iter_nranges, *iter_totals;  // [n_iter]
+    int32_t *counts;          // [n_iter x n_query], caller's query order, or nullptr
+    int32_t *item_rows;       // [n_iter x n_blocks] surviving rows per item, or nullptr
+    unsigned long long *n_hits;  // total ranges sampled (byte-model H)
+    int2 *draw_tab;           // [n_iter x n_blocks] {bait seq, bait start}: rank path scratch
+    int4 *item_rec;           // [n_iter x n_blocks] {lo, hi, bait seq, bait start}: written by the rows kernel for the fill pass
+};
+
+// ---- searches -------------------------------------------------------------------------
+
+// first index in [a, b) with v[idx] > key
+__device__ __forceinline__ int32_t first_gt(const int32_t *__restrict__ v, int32_t a, int32_t b, int32_t key) {
+    while (a < b) {
+        const int32_t m = (a + b) >> 1;
+        if (__ldg(v + m) <= key) a = m + 1; else b = m;
+    }
+    return a;
+}
+// first index in [a, b) with v[idx] >= key
+__device__ __forceinline__ int32_t first_ge(const int32_t *__restrict__ v, int32_t a, int32_t b, int32_t key) {
+    while (a < b) {
+        const int32_t m = (a + b) >> 1;
+        if (__ldg(v + m) < key) a = m + 1; else b = m;
+    }
+    return a;
+}
+
+// ---- direct-address rank tables --------------------------------------------------------
+// One table per ascending per-sequence array (start, running-max end, sorted end).  Entry u of a
+// sequence describes bucket u = [u << shift, (u + 1) << shift):
+//     entry = (first << 3) | min(count, 7)
+// first = index, relative to the sequence's first range, of the first value >= u << shift;
+// count = values inside the bucket.  One 4-byte probe therefore yields both ends of the bucket
+// (count == 7 means "7 or more": the next entry holds the end).
+constexpr int kRankCountBits = 3;
+constexpr int32_t kRankCountCap = (1 << kRankCountBits) - 1;
+
+__device__ __forceinline__ int32_t rank_clamp_key(int32_t key, const int4 si) {
+    return min(max(key, 0), si.z + 1);  // key <= 0 -> si.x and key > max_pos -> si.y fall out of the table
+}
+
+// First index of a sequence (si = seq_info[c]) whose value in `vals` is >= key.  Branch-free in the
+// common case: one table probe, then the first three values of the bucket read together.
+__device__ __forceinline__ int32_t first_ge_ranked(const int32_t *__restrict__ vals, const uint32_t *__restrict__ table,
+                                                   int rank_shift, const int4 si, int32_t key) {
+    key = rank_clamp_key(key, si);
+    const int32_t u = si.w + (key >> rank_shift);
+    const uint32_t e = __ldg(table + u);
+    const int32_t a = si.x + (int32_t)(e >> kRankCountBits), n = (int32_t)(e & kRankCountCap);
+    const int32_t v0 = n > 0 ? __ldg(vals + a) : INT32_MAX;
+    const int32_t v1 = n > 1 ? __ldg(vals + a + 1) : INT32_MAX;
+    const int32_t v2 = n > 2 ? __ldg(vals + a + 2) : INT32_MAX;
+    if (v2 < key) {  // rare: more than three values in the bucket and the first three are below the key
+        const int32_t b = n < kRankCountCap ? a + n : si.x + (int32_t)(__ldg(table + u + 1) >> kRankCountBits);
+        return first_ge(vals, a + 3, b, key);
+    }
+    return a + (v0 < key) + (v1 < key) + (v2 < key);
+}
+
+// Hits of the bait block [s, e] on sequence c are a window [lo, hi) of the canonical order:
+// hi = #{start <= e}, lo = first index whose running-max end reaches s.
+__device__ __forceinline__ void locate_block(const RangesView &y, int c, int32_t s, int64_t e,
+                                             int32_t &lo, int32_t &hi) {
+    const int4 si = __ldg(y.seq_info + c);
+    hi = first_ge_ranked(y.start, y.rank_start, y.rank_shift, si, (int32_t)min(e, (int64_t)INT32_MAX - 1) + 1);
+    lo = first_ge_ranked(y.pmax, y.rank_pmax, y.rank_shift, si, s);
+    if (lo > hi) lo = hi;
+}
+
+// #{start <= a} and #{end < b} on a sequence, both as canonical-order indices (their difference
+// is the number of ranges overlapping [b, a] when b <= a).  a, b are below 2^31 - 1.
+__device__ __forceinline__ int32_t idx_start_le(const RangesView &y, const int4 si, int32_t a) {
+    return first_ge_ranked(y.rstart, y.rrank_start, y.rank_shift, si, a + 1);
+}
+__device__ __forceinline__ int32_t idx_end_lt(const RangesView &y, const int4 si, int32_t b) {
+    return first_ge_ranked(y.end_sorted, y.rank_end, y.rank_shift, si, b - y.end_shift);
+}
+
+__device__ __forceinline__ bool strands_match(int a, int b) { return a == 0 || b == 0 || a == b; }
+
+// ---- block draws ----------------------------------------------------------------------
+
+// Production-mode draw of block b of global iteration `iter` (same arithmetic on the host:
+// philox.cuh).  Returns the sequence and start the block is sampled from.
+__device__ __forceinline__ void draw_block(const BootParams &P, uint64_t iter, int64_t b, int &c, int &s) {
+    const SamplerView &S = P.sampler;
+    const Philox128 u = philox_draw(P.seed, iter, (uint32_t)b, 0u);
+    if (S.kind == NRB200_UNSEG_ACROSS) {
+        const int64_t pos = (int64_t)mul_hi_u64(u.lo, (uint64_t)S.genome_length);
+        c = pick_by_length(S.seq_cum, S.n_seq, pos);
+        s = (int32_t)rounded_uniform(u.hi, 1, (S.tiles_per_seq[c] - 1) * S.block_length);
+    } else if (S.kind == NRB200_UNSEG_WITHIN) {
+        c = __ldg(P.tile_seq + b);
+        s = (int32_t)rounded_uniform(u.hi, 1, (S.tiles_per_seq[c] - 1) * S.block_length);
+    } else if (S.kind == NRB200_PERMUTE_WITHIN || S.kind == NRB200_PERMUTE_ACROSS) {
+        c = __ldg(P.tile_seq + b);    // the blocks ARE the tiles; the draw is where they go (dst_tile, permute_keys_kernel)
+        s = __ldg(P.tile_start + b);
+    } else {  // NRB200_SEG_PROP
+        int st = 1;
+        while (st < S.n_states && b >= S.state_block_off[st + 1]) ++st;
+        const int64_t first = S.state_seg_off[st];
+        const int n = (int)(S.state_seg_off[st + 1] - first);
+        const int64_t pos = (int64_t)mul_hi_u64(u.lo, (uint64_t)S.state_len[st]);
+        const int64_t j = first + pick_by_length(S.sg_cum + first, n, pos);
+        c = S.sg_seq[j];
+        s = (int32_t)rounded_uniform(u.hi, S.sg_start[j], (int64_t)(S.sg_tiles[j] - 1) * S.state_block_len[st]);
+    }
+}
+
+}  // namespace nrb

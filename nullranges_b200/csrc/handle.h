@@ -1,0 +1,215 @@
+// libnrb200: the handle (device buffers, host mirrors, tuning knobs) and small helpers shared by the
+// parts of the engine.  (textually included by engine.cu)
+#pragma once
+#include <algorithm>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <numeric>
+#include <string>
+#include <vector>
+
+#include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
+
+#include "../../include/nrb200.h"
+#include "kernels.cuh"
+#include "plan.h"
+
+namespace nrb {
+
+// NRB200_TRACE=1: host-side stage timings on stderr (development aid)
+struct Trace {
+    static bool on() {
+        static const bool v = getenv("NRB200_TRACE") != nullptr;
+        return v;
+    }
+    const char *name;
+    std::chrono::steady_clock::time_point t0;
+    explicit Trace(const char *n) : name(n), t0(std::chrono::steady_clock::now()) {}
+    void lap(const char *what) {
+        if (!on()) return;
+        const auto t1 = std::chrono::steady_clock::now();
+        fprintf(stderr, "[nrb200] %s/%s %.3f ms\n", name, what, std::chrono::duration<double, std::milli>(t1 - t0).count());
+        t0 = t1;
+    }
+};
+
+static thread_local std::string g_create_error;
+
+// Growth-only device buffer.
+struct DevMem {
+    void *p = nullptr;
+    size_t cap = 0;
+    ~DevMem() { release(); }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+    cudaError_t reserve(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        release();
+        cudaError_t e = cudaMalloc(&p, bytes ? bytes : 1);
+        if (e == cudaSuccess) cap = bytes;
+        return e;
+    }
+    template <class T> T *as() const { return static_cast<T *>(p); }
+};
+
+// One set of ranges in canonical order, host mirror + device copy.
+struct RangeSet {
+    int64_t n = 0;
+    bool stranded = false;
+    int32_t wmax = 0, wmin = 0;
+    std::vector<int32_t> h_start, h_end, h_pmax, h_src, h_seq_off;  // host mirror (kept for query/exclude)
+    std::vector<int8_t> h_strand;
+    std::vector<int32_t> max_end;  // [n_seq] largest end on the sequence (INT32_MIN when empty)
+    bool on_device = false;        // query: device copies are made on first use (the rank path needs none)
+    bool sorted_input = false;     // the caller's order was already canonical
+    DevMem start, end, pmax, src, strand, seq_off, seqid;
+};
+
+}  // namespace nrb
+
+using namespace nrb;
+
+struct nrb200_handle {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    cudaStream_t copy_stream = nullptr;
+    // Pinned staging for small host->device uploads (block tables, window lists, ...): a copy from
+    // pageable memory would first wait for everything queued on the stream; through this arena the
+    // uploads queue behind the GPU work and the host carries on.  Reset whenever the stream is known
+    // to be idle; when full, uploads fall back to the direct (synchronising) copy.
+    char *arena = nullptr;
+    size_t arena_cap = 0, arena_used = 0;
+    cudaEvent_t split_ev = nullptr;       // set while a stats run wants the rows / count kernel split
+    std::vector<cudaEvent_t> batch_ev;    // 3 per batch: start, rows done, count done
+    cudaEvent_t chunk_ev[16] = {};
+    std::string error;
+    int sm_count = 148;
+
+    int n_seq = 0;
+    std::vector<int64_t> seqlen;
+    DevMem seqlen_dev;
+
+    int32_t query_widen = 0;  // maxgap + 1 of the stored query
+    RangeSet y, query, excl, gaps;  // gaps = gaps(exclude) inside [1, seqlength], built for excludeOption "trim"
+    int excl_option = NRB200_EXCLUDE_DROP;
+    bool have_y = false, have_plan = false;
+    // rank tables of y
+    int rank_shift = 0;
+    std::vector<int64_t> rank_off;
+    DevMem inspect_dev, seq_info_dev, draw_tab;
+    // stranded y only: class-major copy for the rank path (kernels.cuh, RangesView)
+    int n_cls = 1, n_width = 1;
+    int32_t query_minoverlap = 0, index_minoverlap = 0;  // the index groups y by "narrower than minoverlap": rebuilt when it changes
+    int32_t end_shift = 0;
+    bool ends_alias_starts = false;
+    // weights of y (nrb200_set_weights): canonical order, class-major order, running sums along start / end order
+    bool have_weights = false, weights_dirty = true;
+    DevMem w_in, w_c, w_r, w_e, w_ps, w_pe, w_keys_e, w_perm_a, w_perm_b, ws_sums, ws_iter;
+    DevMem r_start, r_end, r_pmax, r_order, r_idx, r_keys_a, r_keys_b, r_voff_dev, rseq_info_dev, rrank_off_dev, rrank_start;
+    DevMem rank_off_dev, max_pos_dev, rank_start, rank_pmax, rank_end, end_sorted, sort_keys_a, sort_keys_b, sort_tmp;
+    uint32_t flags = 0;
+    // tuning knobs (environment, read at create): NRB200_RPT iterations per thread of the rank count
+    // kernel, NRB200_MINB its min CTAs/SM, NRB200_TABLE_MULT rank-table entries per range
+    int tune_rpt = 1, tune_minb = 1;
+    double tune_table_mult = 4.0;
+    int64_t tune_max_batch = 2048;     // NRB200_MAX_BATCH: iterations per launch group
+    int64_t tune_table_cap = 8 << 20;  // NRB200_TABLE_CAP: the multiplier applies up to this many entries
+
+    Plan plan;
+    DevMem tile_seq, tile_start, bait_width, sampler_i64, sampler_i32;
+    SamplerView sampler_view{};
+    bool slices_dirty = true, have_pmax_table = false;
+    DevMem q_tile_lo, q_tile_hi, x_tile_lo, x_tile_hi, pair_off, pair_rec, f_src, tile_x_off, tile_x_rec;
+    int64_t n_pairs = 0;
+    bool tiles_in_bounds = false;
+
+    // run scratch / results
+    DevMem d_bait_seq, d_bait_start, d_dst_tile, perm_vals_a, perm_vals_b, np_seg, np_start, np_state, np_list, np_cnt;
+    DevMem d_iter_nranges, d_iter_totals, d_counts, d_n_hits;
+    bool res_has_counts = false;
+    // moments
+    DevMem m_sum, m_sumsq, m_nge, m_observed;
+    bool moments_ready = false;
+    // rows
+    DevMem item_rec, item_rows, within_off, iter_off_dev, row_seq, row_start, row_end, row_src, row_block;
+    int64_t n_rows = 0;
+};
+
+namespace {
+
+int fail(nrb200_handle *h, int code, const std::string &msg) {
+    if (h) h->error = msg; else g_create_error = msg;
+    return code;
+}
+
+// The set the kernels test bootstrapped ranges against: the exclude ranges ("drop") or their gaps ("trim").
+inline bool trim_mode(const nrb200_handle *h) { return h->excl_option == NRB200_EXCLUDE_TRIM && h->excl.n > 0; }
+inline const RangeSet &active_excl(const nrb200_handle *h) { return trim_mode(h) ? h->gaps : h->excl; }
+inline int excl_kind(const nrb200_handle *h) { return h->excl.n == 0 ? kExclNone : (trim_mode(h) ? kExclTrim : kExclDrop); }
+
+#define NRB_CUDA(h, call)                                                                          \
+    do {                                                                                           \
+        cudaError_t err__ = (call);                                                                \
+        if (err__ != cudaSuccess)                                                                  \
+            return fail((h), NRB200_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(err__)); \
+    } while (0)
+
+constexpr size_t kArenaBytes = 16u << 20;
+
+// Waits for the stream; the staging arena can be reused afterwards.
+int sync_stream(nrb200_handle *h) {
+    NRB_CUDA(h, cudaStreamSynchronize(h->stream));
+    h->arena_used = 0;
+    return NRB200_OK;
+}
+
+// Host -> device copy of a library-owned (pageable) array, staged through the pinned arena when it fits.
+template <class T>
+int upload(nrb200_handle *h, DevMem &dst, const T *src, size_t n) {
+    const size_t bytes = n * sizeof(T);
+    NRB_CUDA(h, dst.reserve(bytes));
+    if (!n) return NRB200_OK;
+    if (!h->arena && cudaMallocHost((void **)&h->arena, kArenaBytes) == cudaSuccess) h->arena_cap = kArenaBytes;
+    const size_t at = (h->arena_used + 255) & ~(size_t)255;
+    if (h->arena && at + bytes <= h->arena_cap) {
+        std::memcpy(h->arena + at, src, bytes);
+        h->arena_used = at + bytes;
+        NRB_CUDA(h, cudaMemcpyAsync(dst.p, h->arena + at, bytes, cudaMemcpyHostToDevice, h->stream));
+    } else {
+        NRB_CUDA(h, cudaMemcpyAsync(dst.p, src, bytes, cudaMemcpyHostToDevice, h->stream));
+    }
+    return NRB200_OK;
+}
+
+// Room inside the pinned arena to BUILD an array in place (then upload_staged): nullptr when it does not fit.
+void *arena_alloc(nrb200_handle *h, size_t bytes) {
+    if (!h->arena && cudaMallocHost((void **)&h->arena, kArenaBytes) == cudaSuccess) h->arena_cap = kArenaBytes;
+    const size_t at = (h->arena_used + 255) & ~(size_t)255;
+    if (!h->arena || at + bytes > h->arena_cap) return nullptr;
+    h->arena_used = at + bytes;
+    return h->arena + at;
+}
+template <class T>
+int upload_staged(nrb200_handle *h, DevMem &dst, const T *arena_src, size_t n) {
+    NRB_CUDA(h, dst.reserve(n * sizeof(T)));
+    if (n) NRB_CUDA(h, cudaMemcpyAsync(dst.p, arena_src, n * sizeof(T), cudaMemcpyHostToDevice, h->stream));
+    return NRB200_OK;
+}
+
+// Host -> device copy straight from a caller-owned array (pinned or pageable): never staged.
+template <class T>
+int upload_direct(nrb200_handle *h, DevMem &dst, const T *src, size_t n) {
+    NRB_CUDA(h, dst.reserve(n * sizeof(T)));
+    if (n) NRB_CUDA(h, cudaMemcpyAsync(dst.p, src, n * sizeof(T), cudaMemcpyHostToDevice, h->stream));
+    return NRB200_OK;
+}
+
+}  // namespace

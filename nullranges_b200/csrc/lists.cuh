@@ -1,0 +1,276 @@
+// libnrb200: host-built tables of a run -- per-tile slices (streaming path), gaps(exclude), and the
+// signed window lists of the rank path.  (textually included by engine.cu)
+namespace {
+
+// Per-tile candidate window of a query/exclude set: everything that can overlap a range
+// landing on the tile.  A shifted range overlaps [tile_start, tile_start + width - 1] before
+// trimming, so it lies within (wmax - 1) of it on either side.
+int build_slices(nrb200_handle *h, const RangeSet &rs, DevMem &lo_dev, DevMem &hi_dev) {
+    const Plan &p = h->plan;
+    const int64_t B = p.n_blocks();
+    std::vector<int32_t> lo(B), hi(B);
+    const int64_t reach = std::max<int32_t>(h->y.wmax, 1) - 1;
+    for (int64_t t = 0; t < B; ++t) {
+        const int c = p.tile_seq[t];
+        const int64_t r_lo = (int64_t)p.tile_start[t] - reach;
+        const int64_t r_hi = (int64_t)p.tile_start[t] + p.bait_width[t] - 1 + reach;
+        const int32_t *sb = rs.h_start.data() + rs.h_seq_off[c], *se = rs.h_start.data() + rs.h_seq_off[c + 1];
+        const int32_t *pb = rs.h_pmax.data() + rs.h_seq_off[c], *pe = rs.h_pmax.data() + rs.h_seq_off[c + 1];
+        int32_t a = (int32_t)(std::lower_bound(pb, pe, r_lo, [](int32_t v, int64_t key) { return (int64_t)v < key; }) - rs.h_pmax.data());
+        int32_t b = (int32_t)(std::upper_bound(sb, se, r_hi, [](int64_t key, int32_t v) { return key < (int64_t)v; }) - rs.h_start.data());
+        if (a > b) a = b;
+        lo[t] = a;
+        hi[t] = b;
+    }
+    int rc;
+    if ((rc = upload(h, lo_dev, lo.data(), (size_t)B))) return rc;
+    if ((rc = upload(h, hi_dev, hi.data(), (size_t)B))) return rc;
+    return NRB200_OK;
+}
+
+// ---- rank path tables --------------------------------------------------------------------
+// Per feature: the signed windows to count on each tile within reach (PairRec, kernels.cuh).
+// Tile t is within reach of a window when the window comes within (wmax - 1) of the tile, i.e.
+// when a range landing on the tile can overlap it.  Windows that start beyond their sequence end
+// are dropped (trim() leaves nothing there).  With an exclude set, the merged exclude regions
+// near both the tile and the feature add their pseudo-features with sign -1 (+1 for the overlap
+// of two consecutive regions), and each tile gets the same for the row counts.
+struct Interval {
+    int64_t s, e;
+};
+
+inline bool strands_compatible(int a, int b) { return a == 0 || b == 0 || a == b; }
+
+// reduce(): merged, sorted, disjoint (adjacent regions are joined: the union is what matters) -- of the
+// exclude ranges a y range of strand class `cls` can overlap ('*' y: all of them).
+static std::vector<std::vector<Interval>> merged_exclude(const nrb200_handle *h, int cls = 0) {
+    const RangeSet &x = h->excl;
+    std::vector<std::vector<Interval>> out(h->n_seq);
+    for (int c = 0; c < h->n_seq; ++c) {
+        for (int32_t k = x.h_seq_off[c]; k < x.h_seq_off[c + 1]; ++k) {  // canonical order: by start
+            if (x.stranded && !strands_compatible(cls, x.h_strand[k])) continue;
+            const int64_t s = x.h_start[k], e = x.h_end[k];
+            if (s > h->seqlen[c]) continue;  // nothing survives trim() out there
+            if (!out[c].empty() && s <= out[c].back().e + 1) out[c].back().e = std::max(out[c].back().e, e);
+            else out[c].push_back({s, e});
+        }
+    }
+    return out;
+}
+
+// gaps(exclude, end = seqlengths(y)) on strand "*" (R/bootRanges.R:112-113): complement of the merged
+// exclude regions inside [1, L] on EVERY sequence, as a range set of its own.
+int build_gaps(nrb200_handle *h) {
+    const auto X = merged_exclude(h);
+    std::vector<int32_t> sid, st, en;
+    for (int c = 0; c < h->n_seq; ++c) {
+        const int64_t L = h->seqlen[c];
+        int64_t pos = 1;
+        for (const Interval &x : X[c]) {
+            if (x.s > pos) {
+                sid.push_back(c);
+                st.push_back((int32_t)pos);
+                en.push_back((int32_t)std::min<int64_t>(x.s - 1, L));
+            }
+            pos = std::max(pos, x.e + 1);
+        }
+        if (pos <= L) {
+            sid.push_back(c);
+            st.push_back((int32_t)pos);
+            en.push_back((int32_t)L);
+        }
+    }
+    h->gaps.n = 0;
+    if (sid.empty()) return NRB200_OK;
+    return load_range_set(h, h->gaps, "gaps", (int64_t)sid.size(), sid.data(), st.data(), en.data(), nullptr, false);
+}
+
+int build_pairs(nrb200_handle *h) {
+    Trace tr("build_pairs");
+    const Plan &p = h->plan;
+    const RangeSet &q = h->query;
+    const int C = h->n_seq;
+    const int64_t B = p.n_blocks(), G = q.n;
+    const int64_t reach = std::max<int32_t>(h->y.wmax, 1) - 1;
+    const bool has_excl = h->excl.n > 0, trim = trim_mode(h);
+    const int n_cls = h->n_cls;
+    // Per strand class of y -- "drop": the merged exclude regions that class can overlap; "trim": the gaps
+    // (already disjoint and sorted, strand-free).
+    std::vector<std::vector<std::vector<Interval>>> XC(n_cls, std::vector<std::vector<Interval>>(C));
+    const int n_width = h->n_width;
+    const int64_t kk = h->query_minoverlap;  // 0: any overlap counts
+    for (int cls = 0; cls < n_cls; ++cls) {
+        if (has_excl && !trim) XC[cls] = (cls % n_width) ? XC[cls - 1] : merged_exclude(h, cls / n_width);
+        if (trim)
+            for (int c = 0; c < C; ++c)
+                for (int32_t k = h->gaps.h_seq_off[c]; k < h->gaps.h_seq_off[c + 1]; ++k)
+                    XC[cls][c].push_back({h->gaps.h_start[k], h->gaps.h_end[k]});
+    }
+
+    // exclude regions that intersect [lo, hi]: a contiguous run [first, last) of the merged list
+    auto x_run = [&](const std::vector<Interval> &v, int64_t lo, int64_t hi, size_t &first, size_t &last) {
+        first = std::lower_bound(v.begin(), v.end(), lo, [](const Interval &a, int64_t key) { return a.e < key; }) - v.begin();
+        last = std::upper_bound(v.begin(), v.end(), hi, [](int64_t key, const Interval &a) { return key < a.s; }) - v.begin();
+        if (last < first) last = first;
+    };
+
+    // ---- per (tile, strand class): exclusion windows for the row counts
+    std::vector<int32_t> x_off((size_t)B * n_cls + 1, 0), x_rec;
+    if (has_excl) {
+        for (int64_t t = 0; t < B; ++t) {
+            const int c = p.tile_seq[t];
+            const int64_t ts = p.tile_start[t], te = ts + p.bait_width[t] - 1;
+            for (int cls = 0; cls < n_cls; ++cls) {  // rows count every class, narrow ranges included
+                const auto &X = XC[cls][c];
+                size_t f, l;
+                x_run(X, ts - reach, te + reach, f, l);
+                for (size_t k = f; k < l; ++k) {
+                    if (trim) {  // rows = one per (range, gap) overlap
+                        x_rec.insert(x_rec.end(), {(int32_t)X[k].s, (int32_t)X[k].e, +1, 0});
+                        continue;
+                    }
+                    x_rec.insert(x_rec.end(), {(int32_t)X[k].s, (int32_t)std::min<int64_t>(X[k].e, INT32_MAX / 2), -1, 0});
+                    if (k + 1 < l && X[k + 1].s - X[k].e <= reach) x_rec.insert(x_rec.end(), {(int32_t)X[k + 1].s, (int32_t)X[k].e, +1, 0});
+                }
+                x_off[t * n_cls + cls + 1] = (int32_t)(x_rec.size() / 4);
+            }
+        }
+    }
+    int rc;
+    if (has_excl) {
+        if ((rc = upload(h, h->tile_x_off, x_off.data(), x_off.size()))) return rc;
+        if ((rc = upload(h, h->tile_x_rec, x_rec.data(), x_rec.size()))) return rc;
+    }
+    if (G == 0) return NRB200_OK;
+
+    // ---- per feature.  Tiles of each sequence in ascending start order with the running max of
+    // their ends; features come in canonical (start-sorted) order, so the first tile that can still
+    // reach a feature only moves forward.  Two passes over the same enumeration: list lengths, then
+    // (after grouping features by length) the records, written straight into their final place.
+    std::vector<std::vector<int32_t>> by_seq(C);
+    for (int64_t t = 0; t < B; ++t) by_seq[p.tile_seq[t]].push_back((int32_t)t);
+    std::vector<std::vector<int64_t>> ts(C), te(C), te_max(C);
+    for (int c = 0; c < C; ++c) {
+        auto &v = by_seq[c];
+        bool sorted = true;
+        for (size_t j = 1; j < v.size(); ++j) sorted &= p.tile_start[v[j - 1]] <= p.tile_start[v[j]];
+        if (!sorted)
+            std::sort(v.begin(), v.end(), [&](int32_t a, int32_t b) {
+                return p.tile_start[a] != p.tile_start[b] ? p.tile_start[a] < p.tile_start[b] : a < b;
+            });
+        ts[c].resize(v.size());
+        te[c].resize(v.size());
+        te_max[c].resize(v.size());
+        int64_t m = INT64_MIN;
+        for (size_t j = 0; j < v.size(); ++j) {
+            ts[c][j] = p.tile_start[v[j]];
+            te[c][j] = ts[c][j] + p.bait_width[v[j]] - 1;
+            m = std::max(m, te[c][j]);
+            te_max[c][j] = m;
+        }
+    }
+    tr.lap("tiles_by_seq");
+    // calls emit(tile, ws, we, sign) for every signed window of every feature, features in canonical order
+    // (one sequence at a time: the sequences are independent, so the two passes run them in parallel)
+    auto enumerate_seq = [&](int c, auto &&begin_feature, auto &&emit) {
+        {
+            const auto &v = by_seq[c];
+            const int64_t L = h->seqlen[c], nt = (int64_t)v.size();
+            int64_t lo = 0;
+            for (int32_t k = q.h_seq_off[c]; k < q.h_seq_off[c + 1]; ++k) {
+                begin_feature(k);
+                const int64_t gs = q.h_start[k], ge = q.h_end[k];
+                if (gs > L) continue;
+                while (lo < nt && te_max[c][lo] + reach < gs) ++lo;
+                const int g_strand = q.stranded ? q.h_strand[k] : 0;
+                // minoverlap = kk: start' <= we - kk + 1, end' >= ws + kk - 1, and the trimmed range itself at
+                // least kk wide (start' <= L - kk + 1, end' >= kk; the ranges narrower than kk sit in classes of
+                // their own that no window names).  All of it folds into the window's end points.
+                auto window = [&](int64_t ws, int64_t we, int64_t &lo_w, int64_t &hi_w) {
+                    if (kk <= 0) { lo_w = ws; hi_w = we; return true; }
+                    if (we - ws + 1 < kk) return false;
+                    lo_w = std::max(ws + kk - 1, kk);
+                    hi_w = std::min(we - kk + 1, L - kk + 1);
+                    return true;
+                };
+                int64_t g_lo, g_hi;
+                if (!window(gs, ge, g_lo, g_hi)) continue;
+                for (int64_t j = lo; j < nt && ts[c][j] <= ge + reach; ++j) {
+                    if (te[c][j] + reach < gs) continue;
+                    for (int cls = 0; cls < n_cls; ++cls) {  // classes of y this feature counts
+                        if ((cls % n_width) != 0 || !strands_compatible(cls / n_width, g_strand)) continue;
+                        const auto &X = XC[cls][c];
+                        if (trim) {  // the pieces that can land on the feature: one window per gap it intersects
+                            size_t f, l;
+                            x_run(X, std::max(ts[c][j] - reach, gs), std::min(te[c][j] + reach, ge), f, l);
+                            for (size_t i = f; i < l; ++i) {
+                                int64_t p_lo, p_hi;
+                                if (window(std::max(X[i].s, gs), std::min(X[i].e, ge), p_lo, p_hi)) emit(k, v[j], p_lo, p_hi, +1, cls);
+                            }
+                            continue;
+                        }
+                        emit(k, v[j], g_lo, g_hi, +1, cls);
+                        if (has_excl) {  // regions a range landing on the tile can overlap together with the feature
+                            size_t f, l;
+                            x_run(X, std::max(ts[c][j] - reach, gs - reach), std::min(te[c][j] + reach, ge + reach), f, l);
+                            for (size_t i = f; i < l; ++i) {
+                                emit(k, v[j], std::max(X[i].s, g_lo), std::min(X[i].e, g_hi), -1, cls);
+                                if (i + 1 < l && X[i + 1].s - X[i].e <= reach) emit(k, v[j], std::max(X[i + 1].s, g_lo), std::min(X[i].e, g_hi), +1, cls);
+                            }
+                        }
+                    }
+                }
+            }
+        }
+    };
+    std::vector<int32_t> len(G, 0);
+#pragma omp parallel for schedule(dynamic, 1) if (G >= 4096)
+    for (int c = 0; c < C; ++c) enumerate_seq(c, [](int32_t) {}, [&](int32_t k, int32_t, int64_t, int64_t, int, int) { ++len[k]; });
+    tr.lap("pass1");
+    // Visit order of the count kernel: features grouped by list length (stable counting sort, so
+    // neighbours in a group are neighbours on the genome): the lanes of a warp then loop equally often.
+    constexpr int kBins = 64;
+    int64_t bin_start[kBins + 1] = {0};
+    auto bin = [&](int64_t k) { return std::min<int>(len[k], kBins - 1); };
+    for (int64_t k = 0; k < G; ++k) bin_start[bin(k) + 1]++;
+    for (int b = 0; b < kBins; ++b) bin_start[b + 1] += bin_start[b];
+    std::vector<int32_t> pos_of(G), f_src(G), f_off(G + 1, 0);
+    for (int64_t k = 0; k < G; ++k) pos_of[k] = (int32_t)bin_start[bin(k)]++;
+    for (int64_t k = 0; k < G; ++k) {
+        f_src[pos_of[k]] = q.h_src[k];
+        f_off[pos_of[k] + 1] = len[k];
+    }
+    int64_t total = 0;
+    for (int64_t i = 0; i < G; ++i) {
+        total += f_off[i + 1];
+        if (total > (int64_t)INT32_MAX / 2) return fail(h, NRB200_ERR_UNSUPPORTED, "too many (feature, tile) pairs");
+        f_off[i + 1] = (int32_t)total;
+    }
+    h->n_pairs = total;
+    tr.lap("binning");
+    // records are written straight into pinned staging memory when they fit there
+    std::vector<PairRec> f_recs_vec;
+    PairRec *f_recs = static_cast<PairRec *>(arena_alloc(h, (size_t)std::max<int64_t>(total, 1) * sizeof(PairRec)));
+    const bool staged = f_recs != nullptr;
+    if (!staged) {
+        f_recs_vec.resize((size_t)total);
+        f_recs = f_recs_vec.data();
+    }
+#pragma omp parallel for schedule(dynamic, 1) if (G >= 4096)
+    for (int c = 0; c < C; ++c) {
+        int64_t cursor = 0;
+        enumerate_seq(c, [&](int32_t k) { cursor = f_off[pos_of[k]]; },
+                      [&](int32_t, int32_t t, int64_t ws, int64_t we, int sign, int cls) {
+                          f_recs[cursor++] = PairRec{t, (int32_t)ws, (int32_t)std::min<int64_t>(we, INT32_MAX / 2), sign, p.tile_start[t],
+                                                     p.bait_width[t], (int32_t)h->seqlen[p.tile_seq[t]], cls};
+                      });
+    }
+    tr.lap("lists");
+    if ((rc = upload(h, h->f_src, f_src.data(), (size_t)G))) return rc;
+    if ((rc = upload(h, h->pair_off, f_off.data(), (size_t)G + 1))) return rc;
+    if ((rc = staged ? upload_staged(h, h->pair_rec, f_recs, (size_t)total) : upload(h, h->pair_rec, f_recs, (size_t)total))) return rc;
+    tr.lap("upload");
+    return NRB200_OK;
+}
+
+}  // namespace

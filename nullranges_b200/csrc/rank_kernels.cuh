@@ -1,0 +1,382 @@
+// Rank path: counting (and weighted sums) by rank differences, and the per-block rows kernel.
+// (part of kernels.cuh)
+#pragma once
+#include "device_views.cuh"
+#include "stream_kernels.cuh"
+
+namespace nrb {
+
+// ---- rank path: counting without streaming the ranges ------------------------------------
+//
+// For a bootstrap block sampled at [bs, be] on sequence c and moved by sh = tile_start - bs, the
+// ranges that land on feature [gs, ge] of the tile's sequence (length L) are exactly
+//     { i on c : start_i <= A  and  end_i >= Bv },   A = min(be, ge - sh, L - sh),  Bv = max(bs, gs - sh)
+// (hit of the bait block, overlap after shift(), and start + sh <= L so trim() leaves a positive
+// width; trim() never changes whether a positive-width range overlaps a feature inside [1, L]).
+// When Bv <= A that set has  #{start <= A} - #{end < Bv}  members: two rank queries.  When A < Bv
+// (the feature lies beside the tile, reached only by ranges hanging over the block edge) the
+// members all contain [A, Bv]; they are enumerated backwards from #{start <= A} under the
+// running-max-of-end bound.  Same arithmetic as the reference's findOverlaps + shift + trim +
+// countOverlaps (R/bootUnsegmented.R:133-139, :175-191; vignettes/bootRanges.Rmd:497-503).
+
+// Exclusion (excludeOption = "drop", R/bootRanges.R:108-109) stays on this path: the ranges
+// dropped because they overlap exclude region X and that also land on feature g are those that
+// overlap the pseudo-feature [max(xs, gs), min(xe, ge)] (when that is empty: those that span the gap),
+// so they are counted by the same formula and SUBTRACTED.  Exclude regions are merged first
+// (disjoint, sorted), so a range overlaps a run of consecutive regions and the union is
+// sum_k |S_k| - sum_k |S_k and S_k+1|.  A feature therefore owns a list of signed windows per tile.
+
+struct PairRec {               // one signed window to count for a feature on a tile (32 bytes)
+    int32_t tile;              // block index b (row of the draw table)
+    int32_t ws, we;            // window on the tile's sequence ([gs, ge] or an exclusion pseudo-feature)
+    int32_t sign;              // +1 / -1
+    int32_t tile_start, width, seq_len;  // copied from the block tables: saves three dependent loads
+    int32_t cls;               // strand class of y the window counts (0 when y is unstranded)
+};
+static_assert(sizeof(PairRec) == 32, "PairRec is read as two int4");
+
+struct FeatView {              // query features in visit order (grouped by list length)
+    const int32_t *src;        // [n_query] index in the caller's order
+    const int32_t *pair_off;   // [n_query + 1]
+    const PairRec *pair_rec;
+};
+
+struct TileExcl {              // signed exclusion windows of each (tile, strand class), for the rows kernel
+    const int32_t *off;        // [n_blocks * n_cls + 1], or nullptr without exclusion
+    const int4 *rec;           // {ws, we, sign, 0}
+};
+
+// One (feature, tile, iteration) evaluation, split into stages so that the RPT evaluations a thread
+// owns can be issued stage by stage: all table probes first, then all value reads, so that the
+// dependent-load chain (draw -> sequence info -> table -> values) is paid once per thread, not per
+// evaluation.  All coordinates are below 2^30 and widths at most 2^30: every sum fits int32.
+struct PairProbe {
+    int4 si;                   // seq_info of the bait sequence
+    int32_t A, Bv;             // count = #{start <= A and end >= Bv}
+    int32_t bs;                // bait start (the permute variants also need start >= bs)
+    int32_t key_a, key_b;      // clamped search keys (A + 1 in starts, Bv in sorted ends)
+    int32_t a0, an, b0, bn;    // bucket start and (capped) size in start[] and end_sorted[]
+};
+
+__device__ __forceinline__ void pair_keys(PairProbe &q, int2 draw, int32_t width, int32_t ts, int32_t seq_len,
+                                          int32_t gs, int32_t ge, int rank_shift, int32_t end_shift, int32_t &ua, int32_t &ub) {
+    const int32_t bs = draw.y;
+    const int32_t sh = ts - bs;
+    q.bs = bs;
+    q.A = min(bs + (width - 1), min(ge, seq_len) - sh);
+    q.Bv = max(bs, gs - sh);
+    q.key_a = rank_clamp_key(q.A + 1, q.si);
+    q.key_b = rank_clamp_key(q.Bv - end_shift, q.si);
+    ua = q.si.w + (q.key_a >> rank_shift);
+    ub = q.si.w + (q.key_b >> rank_shift);
+}
+
+// rank inside one bucket: first index with vals >= key (first three values already read; rare search)
+__device__ __forceinline__ int32_t bucket_rank(const int32_t *__restrict__ vals, const uint32_t *__restrict__ table, int32_t u,
+                                               const int4 si, int32_t a, int32_t n, int32_t key, int32_t v0, int32_t v1,
+                                               int32_t v2) {
+    if (v2 < key) {
+        const int32_t b = n < kRankCountCap ? a + n : si.x + (int32_t)(__ldg(table + u + 1) >> kRankCountBits);
+        return first_ge(vals, a + 3, b, key);
+    }
+    return a + (v0 < key) + (v1 < key) + (v2 < key);
+}
+
+// #{start <= a and end >= b} for a < b: such ranges contain [a, b]; walk back from #{start <= a}
+// (index ia) under the running-max-of-end bound.  Usually zero or one step.
+__device__ __forceinline__ int count_spanning(const RangesView &y, const int4 si, int32_t ia, int32_t b) {
+    if (b > si.z) return 0;
+    int n = 0;
+    for (int32_t k = ia - 1; k >= si.x && __ldg(y.rpmax + k) >= b; --k) n += __ldg(y.rend + k) >= b;
+    return n;
+}
+
+// PERMUTE: a range belongs to the ONE tile that holds its start (findOverlaps(select = "first"),
+// R/bootUnsegmented.R:95, :155), so the members are {bs <= start <= A and end >= Bv}: the bootstrap
+// count minus the ranges that start before the tile and reach Bv (they contain [bs - 1, Bv]).
+template <bool PERMUTE>
+__device__ __forceinline__ int pair_finish(const RangesView &y, const PairProbe &q, int32_t ia, int32_t ib) {
+    if (q.A < 1 || (PERMUTE && q.A < q.bs)) return 0;  // permute: no start can lie in [bs, A]
+    int n = q.Bv <= q.A ? ia - ib : count_spanning(y, q.si, ia, q.Bv);  // second form: the feature lies beside the tile
+    if (PERMUTE && n > 0) n -= count_spanning(y, q.si, first_ge_ranked(y.rstart, y.rrank_start, y.rank_shift, q.si, q.bs), q.Bv);
+    return n;
+}
+
+template <int RPT, bool PERMUTE = false>
+__device__ __forceinline__ void count_pairs(const RangesView &y, const int2 (&d)[RPT], int cls, int32_t width, int32_t ts,
+                                            int32_t seq_len, int32_t gs, int32_t ge, int (&cnt)[RPT]) {
+    PairProbe q[RPT];
+    int32_t ua[RPT], ub[RPT];
+#pragma unroll
+    for (int j = 0; j < RPT; ++j) q[j].si = __ldg(y.rseq_info + d[j].x * y.n_cls + cls);
+#pragma unroll
+    for (int j = 0; j < RPT; ++j) pair_keys(q[j], d[j], width, ts, seq_len, gs, ge, y.rank_shift, y.end_shift, ua[j], ub[j]);
+#pragma unroll
+    for (int j = 0; j < RPT; ++j) {
+        const uint32_t ea = __ldg(y.rrank_start + ua[j]), eb = __ldg(y.rank_end + ub[j]);
+        q[j].a0 = q[j].si.x + (int32_t)(ea >> kRankCountBits);
+        q[j].an = (int32_t)(ea & kRankCountCap);
+        q[j].b0 = q[j].si.x + (int32_t)(eb >> kRankCountBits);
+        q[j].bn = (int32_t)(eb & kRankCountCap);
+    }
+    int32_t va[RPT][3], vb[RPT][3];
+#pragma unroll
+    for (int j = 0; j < RPT; ++j) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            va[j][k] = k < q[j].an ? __ldg(y.rstart + q[j].a0 + k) : INT32_MAX;
+            vb[j][k] = k < q[j].bn ? __ldg(y.end_sorted + q[j].b0 + k) : INT32_MAX;
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < RPT; ++j) {
+        const int32_t ia = bucket_rank(y.rstart, y.rrank_start, ua[j], q[j].si, q[j].a0, q[j].an, q[j].key_a, va[j][0], va[j][1], va[j][2]);
+        const int32_t ib = bucket_rank(y.end_sorted, y.rank_end, ub[j], q[j].si, q[j].b0, q[j].bn, q[j].key_b, vb[j][0], vb[j][1], vb[j][2]);
+        cnt[j] += pair_finish<PERMUTE>(y, q[j], ia, ib);
+    }
+}
+
+// Thread = (feature, RPT consecutive iterations); the block draws come from the table the
+// block-rows kernel wrote.  Features are visited in F's order (grouped by tile count, so a warp's
+// lanes loop the same number of times).  No atomics on the count matrix, no memset: every element
+// is written exactly once.
+template <int RPT, int MINB>
+__global__ void __launch_bounds__(256, MINB) boot_rank_count_kernel(const BootParams P, const FeatView F) {
+    __shared__ int warp_tot[8][RPT];
+    const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t r0 = (int64_t)blockIdx.y * RPT;
+    const int n_live = (int)min((int64_t)RPT, P.n_iter - r0);
+    int cnt[RPT];
+#pragma unroll
+    for (int j = 0; j < RPT; ++j) cnt[j] = 0;
+    if (g < P.n_query) {
+        const int32_t src = __ldg(F.src + g);
+        const int32_t p1 = __ldg(F.pair_off + g + 1);
+        for (int32_t p = __ldg(F.pair_off + g); p < p1; ++p) {
+            const int4 ra = __ldg(reinterpret_cast<const int4 *>(F.pair_rec + p));      // tile, ws, we, sign
+            const int4 rb = __ldg(reinterpret_cast<const int4 *>(F.pair_rec + p) + 1);  // tile_start, width, seq_len
+            const int2 *__restrict__ tab = P.draw_tab + r0 * P.n_blocks + ra.x;
+            int2 d[RPT];
+#pragma unroll
+            for (int j = 0; j < RPT; ++j) d[j] = __ldg(tab + (j < n_live ? j : 0) * P.n_blocks);  // tail: recount row 0, discarded
+            int c[RPT];
+#pragma unroll
+            for (int j = 0; j < RPT; ++j) c[j] = 0;
+            if (P.permute) count_pairs<RPT, true>(P.y, d, rb.w, rb.y, rb.x, rb.z, ra.y, ra.z, c);
+            else count_pairs<RPT, false>(P.y, d, rb.w, rb.y, rb.x, rb.z, ra.y, ra.z, c);
+#pragma unroll
+            for (int j = 0; j < RPT; ++j) cnt[j] += ra.w * c[j];
+        }
+        if (P.counts) {
+#pragma unroll
+            for (int j = 0; j < RPT; ++j)
+                if (j < n_live) P.counts[(r0 + j) * P.n_query + src] = cnt[j];
+        }
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int j = 0; j < RPT; ++j) {
+        const int s = __reduce_add_sync(kFull, cnt[j]);
+        if (lane == 0) warp_tot[warp][j] = s;
+    }
+    __syncthreads();
+    if (threadIdx.x < n_live) {
+        unsigned long long s = 0;
+        for (int w = 0; w < 8; ++w) s += (unsigned)warp_tot[w][threadIdx.x];
+        if (s) atomicAdd(P.iter_totals + r0 + threadIdx.x, s);
+    }
+}
+
+// ---- weighted sums on the rank path -----------------------------------------------------------
+// sum of a numeric column of y over the ranges that land on a feature (vignettes/bootRanges.Rmd:532-540:
+// summarize(sum(signal)) per (feature, iter)).  Same windows and ranks as the counts; instead of
+// #{start <= A} - #{end < Bv} it takes the difference of two running sums of the weight, one along the
+// start order and one along the sorted-end order (both restart at every virtual sequence).
+struct WeightView {
+    const double *w;           // weights in the rank path's (class-major) start order
+    const double *ps;          // inclusive running sum of w inside each virtual sequence
+    const double *pe;          // the same along the sorted-end order
+};
+
+__device__ __forceinline__ double run_sum(const double *__restrict__ p, int32_t first, int32_t idx) {
+    return idx > first ? __ldg(p + idx - 1) : 0.0;  // sum of the first (idx - first) elements of the sequence
+}
+__device__ __forceinline__ double sum_spanning(const RangesView &y, const WeightView &W, const int4 si, int32_t ia, int32_t b) {
+    if (b > si.z) return 0.0;
+    double s = 0.0;
+    for (int32_t k = ia - 1; k >= si.x && __ldg(y.rpmax + k) >= b; --k)
+        if (__ldg(y.rend + k) >= b) s += __ldg(W.w + k);
+    return s;
+}
+
+template <bool PERMUTE>
+__device__ __forceinline__ double weighted_pair(const RangesView &y, const WeightView &W, int2 draw, int cls, int32_t width,
+                                                int32_t ts, int32_t seq_len, int32_t ws, int32_t we) {
+    PairProbe q;
+    int32_t ua, ub;
+    q.si = __ldg(y.rseq_info + draw.x * y.n_cls + cls);
+    pair_keys(q, draw, width, ts, seq_len, ws, we, y.rank_shift, y.end_shift, ua, ub);
+    if (q.A < 1 || (PERMUTE && q.A < q.bs)) return 0.0;
+    const int32_t ia = first_ge_ranked(y.rstart, y.rrank_start, y.rank_shift, q.si, q.A + 1);
+    double s;
+    if (q.Bv <= q.A) {
+        const int32_t ib = first_ge_ranked(y.end_sorted, y.rank_end, y.rank_shift, q.si, q.Bv - y.end_shift);
+        s = run_sum(W.ps, q.si.x, ia) - run_sum(W.pe, q.si.x, ib);
+    } else {
+        s = sum_spanning(y, W, q.si, ia, q.Bv);
+    }
+    if (PERMUTE) s -= sum_spanning(y, W, q.si, first_ge_ranked(y.rstart, y.rrank_start, y.rank_shift, q.si, q.bs), q.Bv);
+    return s;
+}
+
+// Thread = (feature, iteration), like boot_rank_count_kernel<1>; sums[r, g] written once, iter_sums by atomics.
+__global__ void __launch_bounds__(256) boot_rank_wsum_kernel(const BootParams P, const FeatView F, const WeightView W,
+                                                             double *__restrict__ sums, double *__restrict__ iter_sums) {
+    __shared__ double warp_tot[8];
+    const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t r = blockIdx.y;
+    double acc = 0.0;
+    if (g < P.n_query) {
+        const int32_t src = __ldg(F.src + g);
+        const int32_t p1 = __ldg(F.pair_off + g + 1);
+        for (int32_t p = __ldg(F.pair_off + g); p < p1; ++p) {
+            const int4 ra = __ldg(reinterpret_cast<const int4 *>(F.pair_rec + p));
+            const int4 rb = __ldg(reinterpret_cast<const int4 *>(F.pair_rec + p) + 1);
+            const int2 d = __ldg(P.draw_tab + r * P.n_blocks + ra.x);
+            const double v = P.permute ? weighted_pair<true>(P.y, W, d, rb.w, rb.y, rb.x, rb.z, ra.y, ra.z)
+                                       : weighted_pair<false>(P.y, W, d, rb.w, rb.y, rb.x, rb.z, ra.y, ra.z);
+            acc += ra.w * v;
+        }
+        if (sums) sums[r * P.n_query + src] = acc;
+    }
+    double t = acc;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(kFull, t, o);
+    if ((threadIdx.x & 31) == 0) warp_tot[threadIdx.x >> 5] = t;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double s = 0.0;
+        for (int w = 0; w < 8; ++w) s += warp_tot[w];
+        if (s != 0.0) atomicAdd(iter_sums + r, s);
+    }
+}
+
+// gathers for the weight arrays: out[i] = in[order[i]] (order == nullptr: identity)
+__global__ void gather_f64_kernel(const double *__restrict__ in, const int32_t *__restrict__ order, int64_t n, double *__restrict__ out) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = in[order ? order[i] : i];
+}
+// sort keys (virtual sequence << 32 | end) with the position as payload: the sorted-end order of the weights
+__global__ void pack_vend_pairs_kernel(const unsigned *__restrict__ vkeys, const int32_t *__restrict__ seqid, const int32_t *__restrict__ end,
+                                       int64_t n, unsigned long long *__restrict__ keys, int32_t *__restrict__ idx) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        const unsigned v = vkeys ? vkeys[i] : (unsigned)seqid[i];
+        keys[i] = ((unsigned long long)v << 32) | (unsigned)end[i];
+        idx[i] = (int32_t)i;
+    }
+}
+__global__ void high32_kernel(const unsigned long long *__restrict__ keys, int64_t n, unsigned *__restrict__ out) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = (unsigned)(keys[i] >> 32);
+}
+struct AddF64 {
+    __host__ __device__ __forceinline__ double operator()(double a, double b) const { return a + b; }
+};
+
+// Per (iteration, block): draws the block (Philox) or reads the caller's draw, records it in the
+// draw table for the count kernel, and counts by ranks the rows the reference's table would hold:
+// hits of the bait block minus (where the variant filters width > 0, R/bootUnsegmented.R:189) the
+// hits shifted wholly beyond the sequence end.  Requires tile_start <= seqlength for every tile
+// (checked on the host).
+template <int RPT>
+__global__ void __launch_bounds__(256) boot_block_rows_kernel(const BootParams P, const TileExcl X) {
+    __shared__ int warp_rows[8][RPT];
+    __shared__ unsigned long long cta_hits;
+    const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t r0 = (int64_t)blockIdx.y * RPT;
+    if (threadIdx.x == 0) cta_hits = 0;
+    int rows[RPT];
+    int hits_sum = 0;
+#pragma unroll
+    for (int j = 0; j < RPT; ++j) rows[j] = 0;
+    if (b < P.n_blocks) {
+        const int32_t width = __ldg(P.bait_width + b);
+#pragma unroll
+        for (int j = 0; j < RPT; ++j) {
+            if (r0 + j < P.n_iter) {
+                const int64_t flat = (r0 + j) * P.n_blocks + b;
+                int2 d;
+                if (P.rng_mode == NRB200_RNG_PHILOX) {
+                    draw_block(P, (uint64_t)(P.iter0 + r0 + j), b, d.x, d.y);
+                } else {
+                    d.x = __ldg(P.bait_seq + flat);
+                    d.y = __ldg(P.bait_start + flat);
+                }
+                // bootstrap kinds: block b lands on tile b; permute kinds: on the tile the caller drew
+                const int32_t t = P.dst_tile ? __ldg(P.dst_tile + flat) : (int32_t)b;
+                const int32_t ts = __ldg(P.tile_start + t);
+                const int32_t seq_len = (int32_t)__ldg(P.seqlen + __ldg(P.tile_seq + t));
+                if (P.draw_tab) P.draw_tab[(r0 + j) * P.n_blocks + t] = d;  // the count kernel looks draws up by tile
+                if (P.item_rec) {  // materialising: the fill pass streams canonical window [lo, hi) of this block
+                    int32_t lo, hi;
+                    locate_block(P.y, d.x, d.y, (int64_t)d.y + width - 1, lo, hi);
+                    P.item_rec[flat] = make_int4(lo, hi, d.x, d.y);
+                }
+                int hits = 0;
+                for (int cls = 0; cls < P.y.n_cls; ++cls) {  // one pass per strand class of y (one when y is unstranded)
+                    const int4 si = __ldg(P.y.rseq_info + d.x * P.y.n_cls + cls);
+                    const int32_t ie = idx_start_le(P.y, si, d.y + (width - 1));
+                    // hits: overlap of the bait block (bootstrap) / start inside the tile (permute)
+                    const int h1 = ie - (P.permute ? idx_start_le(P.y, si, d.y - 1) : idx_end_lt(P.y, si, d.y));
+                    int dropped = 0;  // only a tile that overhangs its sequence end can push hits beyond it
+                    if (P.drop_zero && ts + (width - 1) > seq_len) dropped = max(0, ie - idx_start_le(P.y, si, seq_len - (ts - d.y)));
+                    hits += h1;
+                    if (!P.rows_windows_only) rows[j] += h1 - dropped;
+                    if (X.off) {  // minus the hits that overlap an exclude region after the move ("trim": plus the pieces)
+                        const int32_t x1 = __ldg(X.off + t * P.y.n_cls + cls + 1);
+                        for (int32_t k = __ldg(X.off + t * P.y.n_cls + cls); k < x1; ++k) {
+                            const int4 w = __ldg(X.rec + k);
+                            const int2 dd[1] = {d};
+                            int c1[1] = {0};
+                            if (P.permute) count_pairs<1, true>(P.y, dd, cls, width, ts, seq_len, w.x, w.y, c1);
+                            else count_pairs<1, false>(P.y, dd, cls, width, ts, seq_len, w.x, w.y, c1);
+                            rows[j] += w.z * c1[0];
+                        }
+                    }
+                }
+                hits_sum += hits;
+                if (P.item_rows) P.item_rows[(r0 + j) * P.n_blocks + b] = rows[j];
+            }
+        }
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int j = 0; j < RPT; ++j) {
+        const int s = __reduce_add_sync(kFull, rows[j]);
+        if (lane == 0) warp_rows[warp][j] = s;
+    }
+    hits_sum = __reduce_add_sync(kFull, hits_sum);
+    __syncthreads();
+    if (lane == 0 && hits_sum) atomicAdd(&cta_hits, (unsigned long long)hits_sum);
+    if (threadIdx.x < RPT && r0 + threadIdx.x < P.n_iter) {
+        unsigned long long s = 0;
+        for (int w = 0; w < 8; ++w) s += (unsigned)warp_rows[w][threadIdx.x];
+        if (s) atomicAdd(P.iter_nranges + r0 + threadIdx.x, s);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0 && P.n_hits && cta_hits) atomicAdd(P.n_hits, cta_hits);
+}
+
+// (seqid << 32 | end) sort keys and their unpacking: the sorted-ends array of the rank path
+__global__ void pack_end_keys_kernel(const int32_t *__restrict__ seqid, const int32_t *__restrict__ end, int64_t n,
+                                     unsigned long long *__restrict__ keys) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) keys[i] = ((unsigned long long)(unsigned)seqid[i] << 32) | (unsigned)end[i];
+}
+__global__ void unpack_end_keys_kernel(const unsigned long long *__restrict__ keys, int64_t n, int32_t *__restrict__ end_sorted) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) end_sorted[i] = (int32_t)(unsigned)keys[i];
+}
+
+}  // namespace nrb

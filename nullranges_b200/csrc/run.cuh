@@ -1,0 +1,373 @@
+// libnrb200: dispatch, block draws, kernel launches and the core of the counting entry points.
+// (textually included by engine.cu)
+namespace {
+
+// The rank path covers every sampler (bootstrap and permute, with or without exclusion, any strands);
+// only a segmentation reaching beyond its sequence falls back to streaming the hits (boot_count_kernel).
+bool rank_path_ok(const nrb200_handle *h, bool with_query) {
+    (void)with_query;
+    if (h->flags & NRB200_FLAG_FORCE_STREAM) return false;
+    return h->tiles_in_bounds;
+}
+
+int prepare(nrb200_handle *h) {
+    if (!h->have_y) return fail(h, NRB200_ERR_STATE, "nrb200_set_ranges() has not been called");
+    if (!h->have_plan) return fail(h, NRB200_ERR_STATE, "nrb200_set_plan() has not been called");
+    if (h->slices_dirty) {
+        int rc;
+        Trace tr("prepare");
+        h->tiles_in_bounds = true;
+        for (int64_t t = 0; t < h->plan.n_blocks(); ++t)
+            if (h->plan.tile_start[t] > h->seqlen[h->plan.tile_seq[t]]) h->tiles_in_bounds = false;
+        if (h->index_minoverlap != h->query_minoverlap && (rc = build_rank_tables(h))) return rc;  // the width classes changed
+        if (trim_mode(h) && h->excl.stranded) return fail(h, NRB200_ERR_INVALID, "all(strand(exclude) == \"*\") is not TRUE");
+        if (trim_mode(h) && (rc = build_gaps(h))) return rc;
+        // rank_path_ok(h, false) holds whenever rank_path_ok(h, true) does
+        const bool rank_q = h->query.n && rank_path_ok(h, true), rank_rows = rank_path_ok(h, false);
+        if (rank_q || rank_rows) {
+            const int64_t g_keep = h->query.n;
+            if (!rank_q) h->query.n = 0;  // tables for the row counts only
+            rc = build_pairs(h);
+            h->query.n = g_keep;
+            if (rc) return rc;
+            tr.lap("build_pairs");
+        }
+        // the streaming kernels (count without the rank path, and the fill pass) test exclusion per range
+        if (h->excl.n && (rc = build_slices(h, active_excl(h), h->x_tile_lo, h->x_tile_hi))) return rc;
+        if (h->query.n && !rank_q && (rc = range_set_to_device(h, h->query))) return rc;
+        if (h->query.n && !rank_q && (rc = build_slices(h, h->query, h->q_tile_lo, h->q_tile_hi))) return rc;
+        if (((h->query.n && !rank_q) || !rank_rows) && (rc = ensure_pmax_table(h))) return rc;
+        h->slices_dirty = false;
+    }
+    return NRB200_OK;
+}
+
+int stage_draws(nrb200_handle *h, const nrb200_draws *d) {
+    if (!d || d->n_iter < 0) return fail(h, NRB200_ERR_INVALID, "draws: n_iter must be >= 0");
+    const Plan &p = h->plan;
+    const int64_t B = p.n_blocks();
+    if (d->rng_mode == NRB200_RNG_PHILOX) {
+        if (p.kind == NRB200_SEG_NOPROP) {
+            // proportionLength = FALSE: the draws are made on the device into the tables host mode would upload
+            const int64_t R = d->n_iter, items = R * B;
+            const int S = p.n_states;
+            if (S > 127) return fail(h, NRB200_ERR_UNSUPPORTED, "device draws for proportionLength=FALSE support at most 127 states");
+            for (DevMem *m : {&h->d_bait_seq, &h->d_bait_start, &h->np_seg, &h->np_start, &h->np_list})
+                NRB_CUDA(h, m->reserve((size_t)std::max<int64_t>(items, 1) * 4));
+            NRB_CUDA(h, h->np_state.reserve((size_t)std::max<int64_t>(items, 1)));
+            NRB_CUDA(h, h->np_cnt.reserve((size_t)std::max<int64_t>(R, 1) * (S + 1) * 4 + 4));
+            if (items == 0) return NRB200_OK;
+            int *err = h->np_cnt.as<int>() + R * (S + 1);
+            NRB_CUDA(h, cudaMemsetAsync(err, 0, 4, h->stream));
+            const unsigned grid = (unsigned)((items + 255) / 256);
+            noprop_draw_kernel<<<grid, 256, 0, h->stream>>>(h->sampler_view, d->seed, d->iter0, R, B, h->np_seg.as<int32_t>(),
+                                                             h->np_start.as<int32_t>(), h->np_state.as<int8_t>());
+            noprop_lists_kernel<<<(unsigned)R, 256, 0, h->stream>>>(S, B, h->np_state.as<int8_t>(), h->np_list.as<int32_t>(),
+                                                                    h->np_cnt.as<int32_t>());
+            noprop_assign_kernel<<<grid, 256, 0, h->stream>>>(h->sampler_view, d->seed, d->iter0, R, B, h->np_seg.as<int32_t>(),
+                                                               h->np_start.as<int32_t>(), h->np_list.as<int32_t>(), h->np_cnt.as<int32_t>(),
+                                                               h->d_bait_seq.as<int32_t>(), h->d_bait_start.as<int32_t>(), err);
+            NRB_CUDA(h, cudaGetLastError());
+            int flag = 0;
+            NRB_CUDA(h, cudaMemcpyAsync(&flag, err, 4, cudaMemcpyDeviceToHost, h->stream));
+            if (int rc_sync = sync_stream(h)) return rc_sync;
+            // the reference stops here too: length(rearranged_blocks_start) == length(random_blocks_start) fails (R/bootRanges.R:303)
+            if (flag) return fail(h, NRB200_ERR_INVALID, "seg_bootstrap_noprop: a state drew no segments in some iteration");
+            return NRB200_OK;
+        }
+        if (!p.permute()) return NRB200_OK;
+        // permute variants: one random permutation of the tiles per iteration, made on the device
+        if (h->n_seq > 4096) return fail(h, NRB200_ERR_UNSUPPORTED, "device permutations support at most 4096 sequences");
+        const int64_t R = d->n_iter;
+        NRB_CUDA(h, h->d_dst_tile.reserve((size_t)std::max<int64_t>(R * B, 1) * 4));
+        const int64_t kPermBatch = 4096;  // 12 bits of the sort key
+        const int64_t cap = std::min(R, kPermBatch) * B;
+        NRB_CUDA(h, h->sort_keys_a.reserve((size_t)std::max<int64_t>(cap, 1) * 8));
+        NRB_CUDA(h, h->sort_keys_b.reserve((size_t)std::max<int64_t>(cap, 1) * 8));
+        NRB_CUDA(h, h->perm_vals_a.reserve((size_t)std::max<int64_t>(cap, 1) * 4));
+        NRB_CUDA(h, h->perm_vals_b.reserve((size_t)std::max<int64_t>(cap, 1) * 4));
+        for (int64_t r0 = 0; r0 < R; r0 += kPermBatch) {
+            const int64_t n = std::min(kPermBatch, R - r0), items = n * B;
+            if (items == 0) continue;
+            const unsigned grid = (unsigned)((items + 255) / 256);
+            permute_keys_kernel<<<grid, 256, 0, h->stream>>>(d->seed, d->iter0 + r0, n, B, h->tile_seq.as<int32_t>(),
+                                                              p.kind == NRB200_PERMUTE_WITHIN, h->sort_keys_a.as<unsigned long long>(),
+                                                              h->perm_vals_a.as<int32_t>());
+            size_t tmp_bytes = 0;
+            NRB_CUDA(h, cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, h->sort_keys_a.as<unsigned long long>(),
+                                                        h->sort_keys_b.as<unsigned long long>(), h->perm_vals_a.as<int32_t>(),
+                                                        h->perm_vals_b.as<int32_t>(), items, 0, 64, h->stream));
+            NRB_CUDA(h, h->sort_tmp.reserve(tmp_bytes));
+            NRB_CUDA(h, cub::DeviceRadixSort::SortPairs(h->sort_tmp.p, tmp_bytes, h->sort_keys_a.as<unsigned long long>(),
+                                                        h->sort_keys_b.as<unsigned long long>(), h->perm_vals_a.as<int32_t>(),
+                                                        h->perm_vals_b.as<int32_t>(), items, 0, 64, h->stream));
+            permute_scatter_kernel<<<grid, 256, 0, h->stream>>>(h->perm_vals_b.as<int32_t>(), n, B, h->d_dst_tile.as<int32_t>() + r0 * B);
+            NRB_CUDA(h, cudaGetLastError());
+        }
+        return NRB200_OK;
+    }
+    if (d->rng_mode != NRB200_RNG_HOST) return fail(h, NRB200_ERR_INVALID, "draws: unknown rng_mode");
+    const int64_t n = d->n_iter * B;
+    if (n > 0 && (!d->bait_seqid || !d->bait_start)) return fail(h, NRB200_ERR_INVALID, "draws: bait_seqid/bait_start are required in host mode");
+    if (p.permute() && n > 0 && !d->dst_tile) return fail(h, NRB200_ERR_INVALID, "draws: permute kinds need dst_tile");
+    for (int64_t i = 0; i < n; ++i) {
+        if (d->bait_seqid[i] < 0 || d->bait_seqid[i] >= h->n_seq) return fail(h, NRB200_ERR_INVALID, "draws: bait_seqid out of range");
+        if (d->bait_start[i] < 1 || d->bait_start[i] >= (1 << 30)) return fail(h, NRB200_ERR_INVALID, "draws: bait_start out of range");
+        if (d->dst_tile && (d->dst_tile[i] < 0 || d->dst_tile[i] >= B)) return fail(h, NRB200_ERR_INVALID, "draws: dst_tile out of range");
+    }
+    int rc;
+    if ((rc = upload(h, h->d_bait_seq, d->bait_seqid, (size_t)n))) return rc;
+    if ((rc = upload(h, h->d_bait_start, d->bait_start, (size_t)n))) return rc;
+    if (d->dst_tile && (rc = upload(h, h->d_dst_tile, d->dst_tile, (size_t)n))) return rc;
+    return NRB200_OK;
+}
+
+BootParams make_params(nrb200_handle *h, const nrb200_draws *d) {
+    BootParams P{};
+    const RangeSet &y = h->y;
+    RangesView Y{};
+    Y.start = y.start.as<int32_t>();
+    Y.end = y.end.as<int32_t>();
+    Y.pmax = y.pmax.as<int32_t>();
+    Y.strand = y.stranded ? y.strand.as<int8_t>() : nullptr;
+    Y.src = y.sorted_input ? nullptr : y.src.as<int32_t>();
+    Y.seq_off = y.seq_off.as<int32_t>();
+    Y.seq_info = h->seq_info_dev.as<int4>();
+    Y.rank_start = h->rank_start.as<uint32_t>();
+    Y.rank_pmax = h->rank_pmax.as<uint32_t>();
+    Y.rank_shift = h->rank_shift;
+    Y.n_cls = h->n_cls;
+    Y.end_sorted = h->end_sorted.as<int32_t>();
+    Y.rank_end = h->rank_end.as<uint32_t>();
+    if (h->n_cls == 1) {  // unstranded: the rank path reads the canonical arrays
+        Y.rstart = Y.start;
+        Y.rend = Y.end;
+        Y.rpmax = Y.pmax;
+        Y.rseq_info = Y.seq_info;
+        Y.rrank_start = Y.rank_start;
+    } else {
+        Y.rstart = h->r_start.as<int32_t>();
+        Y.rend = h->r_end.as<int32_t>();
+        Y.rpmax = h->r_pmax.as<int32_t>();
+        Y.rseq_info = h->rseq_info_dev.as<int4>();
+        Y.rrank_start = h->rrank_start.as<uint32_t>();
+    }
+    Y.end_shift = h->end_shift;
+    if (h->ends_alias_starts) {
+        Y.end_sorted = Y.rstart;
+        Y.rank_end = Y.rrank_start;
+    }
+    P.y = Y;
+    const RangeSet &q = h->query, &x = active_excl(h);
+    P.query = SliceView{q.start.as<int32_t>(), q.end.as<int32_t>(), q.pmax.as<int32_t>(), q.stranded ? q.strand.as<int8_t>() : nullptr,
+                        q.src.as<int32_t>(), h->q_tile_lo.as<int32_t>(), h->q_tile_hi.as<int32_t>()};
+    P.excl = SliceView{x.start.as<int32_t>(), x.end.as<int32_t>(), x.pmax.as<int32_t>(), x.stranded ? x.strand.as<int8_t>() : nullptr,
+                       x.src.as<int32_t>(), h->x_tile_lo.as<int32_t>(), h->x_tile_hi.as<int32_t>()};
+    P.rows_windows_only = trim_mode(h);
+    P.minoverlap = h->query_minoverlap;
+    P.sampler = h->sampler_view;
+    P.n_blocks = h->plan.n_blocks();
+    P.tile_seq = h->tile_seq.as<int32_t>();
+    P.tile_start = h->tile_start.as<int32_t>();
+    P.bait_width = h->bait_width.as<int32_t>();
+    P.seqlen = h->seqlen_dev.as<int64_t>();
+    P.permute = h->plan.permute();
+    P.drop_zero = h->plan.drop_zero_width();
+    // proportionLength = FALSE in production mode: stage_draws() filled the host-mode tables on the device
+    const bool noprop_dev = d->rng_mode == NRB200_RNG_PHILOX && h->plan.kind == NRB200_SEG_NOPROP;
+    P.rng_mode = noprop_dev ? NRB200_RNG_HOST : d->rng_mode;
+    P.seed = d->seed;
+    P.iter0 = d->iter0;
+    if (d->rng_mode == NRB200_RNG_HOST || noprop_dev) {
+        P.bait_seq = h->d_bait_seq.as<int32_t>();
+        P.bait_start = h->d_bait_start.as<int32_t>();
+        P.dst_tile = (!noprop_dev && d->dst_tile) ? h->d_dst_tile.as<int32_t>() : nullptr;
+    } else if (h->plan.permute()) {
+        P.dst_tile = h->d_dst_tile.as<int32_t>();  // made by stage_draws() on the device
+    }
+    P.n_iter = d->n_iter;
+    P.n_query = q.n;
+    return P;
+}
+
+template <bool ST, bool HQ>
+void launch_count_t(nrb200_handle *h, const BootParams &P, unsigned grid, int excl) {
+    if (excl == kExclNone) boot_count_kernel<ST, HQ, kExclNone><<<grid, 256, 0, h->stream>>>(P);
+    else if (excl == kExclDrop) boot_count_kernel<ST, HQ, kExclDrop><<<grid, 256, 0, h->stream>>>(P);
+    else boot_count_kernel<ST, HQ, kExclTrim><<<grid, 256, 0, h->stream>>>(P);
+}
+
+constexpr int64_t kMaxBatch = 2048;  // iterations per launch at most (gridDim.y and scratch stay small); NRB200_MAX_BATCH lowers it
+constexpr int kChunkEvents = 16;
+constexpr int kChunks = 8;  // pipeline depth of nrb200_run_counts (compute chunk k+1 while chunk k copies out)
+
+// Returns the number of kernels launched.
+int launch_rank(nrb200_handle *h, const BootParams &P, bool has_query) {
+    if (P.n_iter == 0) return 0;
+    int launches = 0;
+    const int rpt = h->tune_rpt;
+    const unsigned gy = (unsigned)((P.n_iter + rpt - 1) / rpt);
+    if (P.n_blocks > 0) {
+        const TileExcl X{h->excl.n > 0 ? h->tile_x_off.as<int32_t>() : nullptr, h->tile_x_rec.as<int4>()};  // drop: minus, trim: plus
+        boot_block_rows_kernel<1><<<dim3((unsigned)((P.n_blocks + 255) / 256), (unsigned)P.n_iter), 256, 0, h->stream>>>(P, X);
+        ++launches;
+    }
+    if (h->split_ev) cudaEventRecord(h->split_ev, h->stream);  // stats: end of the rows kernel
+    if (has_query) {
+        const FeatView F{h->f_src.as<int32_t>(), h->pair_off.as<int32_t>(), h->pair_rec.as<PairRec>()};
+        const dim3 grid((unsigned)((P.n_query + 255) / 256), gy);
+        switch (rpt * 10 + h->tune_minb) {
+        case 11: boot_rank_count_kernel<1, 1><<<grid, 256, 0, h->stream>>>(P, F); break;
+        case 21: boot_rank_count_kernel<2, 1><<<grid, 256, 0, h->stream>>>(P, F); break;
+        case 24: boot_rank_count_kernel<2, 4><<<grid, 256, 0, h->stream>>>(P, F); break;
+        case 41: boot_rank_count_kernel<4, 1><<<grid, 256, 0, h->stream>>>(P, F); break;
+        case 43: boot_rank_count_kernel<4, 3><<<grid, 256, 0, h->stream>>>(P, F); break;
+        case 44: boot_rank_count_kernel<4, 4><<<grid, 256, 0, h->stream>>>(P, F); break;
+        case 81: boot_rank_count_kernel<8, 1><<<grid, 256, 0, h->stream>>>(P, F); break;
+        default: boot_rank_count_kernel<1, 1><<<grid, 256, 0, h->stream>>>(P, F); break;
+        }
+        ++launches;
+    }
+    return launches;
+}
+
+int launch_count(nrb200_handle *h, const BootParams &P, bool has_query) {
+    if (rank_path_ok(h, has_query)) return launch_rank(h, P, has_query);
+    const int64_t items = P.n_iter * P.n_blocks;
+    if (items == 0) return 0;
+    const int64_t ctas = (items + 7) / 8;
+    const unsigned grid = (unsigned)std::min<int64_t>(ctas, (int64_t)h->sm_count * 64);
+    const bool st = h->y.stranded && ((has_query && h->query.stranded) || (h->excl.n && active_excl(h).stranded));
+    const int excl = excl_kind(h);
+    if (st && has_query) launch_count_t<true, true>(h, P, grid, excl);
+    else if (st) launch_count_t<true, false>(h, P, grid, excl);
+    else if (has_query) launch_count_t<false, true>(h, P, grid, excl);
+    else launch_count_t<false, false>(h, P, grid, excl);
+    return 1;
+}
+
+// P restricted to local iterations [r0, r0 + n).
+BootParams slice_params(const BootParams &P, int64_t r0, int64_t n) {
+    BootParams Q = P;
+    Q.n_iter = n;
+    Q.iter0 = P.iter0 + r0;
+    if (P.bait_seq) Q.bait_seq = P.bait_seq + r0 * P.n_blocks;
+    if (P.bait_start) Q.bait_start = P.bait_start + r0 * P.n_blocks;
+    if (P.dst_tile) Q.dst_tile = P.dst_tile + r0 * P.n_blocks;
+    if (P.iter_nranges) Q.iter_nranges = P.iter_nranges + r0;
+    if (P.iter_totals) Q.iter_totals = P.iter_totals + r0;
+    if (P.counts) Q.counts = P.counts + r0 * P.n_query;
+    if (P.item_rows) Q.item_rows = P.item_rows + r0 * P.n_blocks;
+    if (P.item_rec) Q.item_rec = P.item_rec + r0 * P.n_blocks;
+    return Q;
+}
+
+// Core of every counting entry point: results stay on the device.  With host_counts set, the
+// iterations run in chunks and each chunk of the [R x G] matrix starts its way to the host
+// (copy stream) while the next chunk computes.
+int run_counts_core(nrb200_handle *h, const nrb200_draws *d, bool want_counts, int32_t *host_counts,
+                    nrb200_stats *stats) {
+    int rc;
+    if ((rc = prepare(h))) return rc;
+    NRB_CUDA(h, cudaEventRecord(h->ev[0], h->stream));
+    if ((rc = stage_draws(h, d))) return rc;
+    const int64_t R = d->n_iter, G = h->query.n;
+    const bool has_query = G > 0;
+    want_counts = want_counts && has_query;
+    NRB_CUDA(h, h->d_iter_nranges.reserve(std::max<int64_t>(R, 1) * 8));
+    NRB_CUDA(h, h->d_iter_totals.reserve(std::max<int64_t>(R, 1) * 8));
+    NRB_CUDA(h, h->d_n_hits.reserve(8));
+    NRB_CUDA(h, cudaMemsetAsync(h->d_iter_nranges.p, 0, R * 8, h->stream));
+    NRB_CUDA(h, cudaMemsetAsync(h->d_iter_totals.p, 0, R * 8, h->stream));
+    NRB_CUDA(h, cudaMemsetAsync(h->d_n_hits.p, 0, 8, h->stream));
+    int32_t *counts = nullptr;
+    if (want_counts) {
+        NRB_CUDA(h, h->d_counts.reserve((size_t)R * G * sizeof(int32_t)));
+        counts = h->d_counts.as<int32_t>();
+        // the rank path writes every element; the streaming path accumulates with atomics
+        if (!rank_path_ok(h, true)) NRB_CUDA(h, cudaMemsetAsync(counts, 0, (size_t)R * G * sizeof(int32_t), h->stream));
+    }
+    BootParams P = make_params(h, d);
+    P.iter_nranges = h->d_iter_nranges.as<unsigned long long>();
+    P.iter_totals = h->d_iter_totals.as<unsigned long long>();
+    P.counts = counts;
+    P.n_hits = h->d_n_hits.as<unsigned long long>();
+    NRB_CUDA(h, cudaEventRecord(h->ev[1], h->stream));
+    int launches = 0;
+    const bool pipelined = host_counts && counts && R > 0;
+    // Iterations go in batches: bounded draw-table scratch on the rank path and, when the matrix
+    // is wanted on the host, chunk k copies out (copy stream) while chunk k + 1 computes.
+    int64_t chunk = h->tune_max_batch;
+    if (pipelined) {
+        if (!h->copy_stream) NRB_CUDA(h, cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+        chunk = std::min<int64_t>(h->tune_max_batch, std::max<int64_t>(((R + kChunks - 1) / kChunks + 7) / 8 * 8, 64));
+    }
+    if (rank_path_ok(h, has_query) && has_query) {
+        NRB_CUDA(h, h->draw_tab.reserve((size_t)std::min(chunk, std::max<int64_t>(R, 1)) * h->plan.n_blocks() * sizeof(int2)));
+        P.draw_tab = h->draw_tab.as<int2>();
+    }
+    int k = 0;
+    const bool split = stats && rank_path_ok(h, has_query);
+    for (int64_t r0 = 0; r0 < R; r0 += chunk, ++k) {
+        const int64_t n = std::min(chunk, R - r0);
+        if (split) {
+            while (h->batch_ev.size() < (size_t)3 * (k + 1)) {
+                cudaEvent_t e;
+                NRB_CUDA(h, cudaEventCreate(&e));
+                h->batch_ev.push_back(e);
+            }
+            NRB_CUDA(h, cudaEventRecord(h->batch_ev[3 * k], h->stream));
+            h->split_ev = h->batch_ev[3 * k + 1];
+        }
+        launches += launch_count(h, slice_params(P, r0, n), has_query);
+        h->split_ev = nullptr;
+        if (split) NRB_CUDA(h, cudaEventRecord(h->batch_ev[3 * k + 2], h->stream));
+        NRB_CUDA(h, cudaGetLastError());
+        if (pipelined) {
+            cudaEvent_t &ev = h->chunk_ev[k % kChunkEvents];
+            if (!ev) NRB_CUDA(h, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+            NRB_CUDA(h, cudaEventRecord(ev, h->stream));
+            NRB_CUDA(h, cudaStreamWaitEvent(h->copy_stream, ev, 0));
+            NRB_CUDA(h, cudaMemcpyAsync(host_counts + r0 * G, counts + r0 * G, (size_t)n * G * sizeof(int32_t),
+                                        cudaMemcpyDeviceToHost, h->copy_stream));
+        }
+    }
+    NRB_CUDA(h, cudaEventRecord(h->ev[2], h->stream));
+    h->res_has_counts = want_counts;
+    if (stats) {
+        NRB_CUDA(h, cudaEventSynchronize(h->ev[2]));
+        float k_ms = 0, t_ms = 0;
+        cudaEventElapsedTime(&k_ms, h->ev[1], h->ev[2]);
+        cudaEventElapsedTime(&t_ms, h->ev[0], h->ev[2]);
+        unsigned long long hits = 0;
+        NRB_CUDA(h, cudaMemcpyAsync(&hits, h->d_n_hits.p, 8, cudaMemcpyDeviceToHost, h->stream));
+        if (int rc_sync = sync_stream(h)) return rc_sync;
+        std::memset(stats, 0, sizeof *stats);
+        stats->kernel_ms = k_ms;
+        stats->total_ms = t_ms;
+        stats->n_launches = launches;
+        stats->n_hits = (int64_t)hits;
+        if (split) {
+            stats->n_windows = has_query ? h->n_pairs : 0;
+            for (int b = 0; b < k; ++b) {
+                float a_ms = 0, b_ms = 0;
+                cudaEventElapsedTime(&a_ms, h->batch_ev[3 * b], h->batch_ev[3 * b + 1]);
+                cudaEventElapsedTime(&b_ms, h->batch_ev[3 * b + 1], h->batch_ev[3 * b + 2]);
+                stats->rows_kernel_ms += a_ms;
+                stats->count_kernel_ms += b_ms;
+            }
+        } else {
+            stats->count_kernel_ms = k_ms;  // streaming path: one kernel does both
+        }
+        stats->h2d_bytes = d->rng_mode == NRB200_RNG_HOST ? R * h->plan.n_blocks() * (d->dst_tile ? 12 : 8) : 0;
+    }
+    return NRB200_OK;
+}
+
+int fetch_u64_as_i64(nrb200_handle *h, const DevMem &src, int64_t n, int64_t *dst) {
+    if (!dst || n == 0) return NRB200_OK;
+    NRB_CUDA(h, cudaMemcpyAsync(dst, src.p, n * 8, cudaMemcpyDeviceToHost, h->stream));
+    return NRB200_OK;
+}
+
+}  // namespace

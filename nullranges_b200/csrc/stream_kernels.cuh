@@ -1,0 +1,307 @@
+// Streaming path: the fused count kernel (one warp per iteration x block) and the materialising scan / fill kernels.
+// (part of kernels.cuh)
+#pragma once
+#include "device_views.cuh"
+
+namespace nrb {
+
+// ---- the fused kernel -----------------------------------------------------------------
+
+struct Item {
+    int bait_seq, tile;        // sampled-from sequence; destination tile index
+    int32_t bait_start;
+    int64_t bait_end;
+    int tile_seq;
+    int32_t shift;             // tile_start - bait_start       (block_shift, :179)
+    int32_t seq_len;           // seqlengths[tile_seq]
+    int32_t lo, hi;            // hit window in canonical y
+};
+
+__device__ __forceinline__ Item load_item(const BootParams &P, int64_t r, int64_t b) {
+    Item it;
+    const int64_t flat = r * P.n_blocks + b;
+    if (P.item_rec) {  // the rows kernel already drew the block and located its hit window
+        const int4 rec = __ldg(P.item_rec + flat);
+        it.lo = rec.x;
+        it.hi = rec.y;
+        it.bait_seq = rec.z;
+        it.bait_start = rec.w;
+        it.tile = P.dst_tile ? __ldg(P.dst_tile + flat) : (int)b;
+        it.bait_end = (int64_t)it.bait_start + __ldg(P.bait_width + b) - 1;
+        it.tile_seq = __ldg(P.tile_seq + it.tile);
+        it.shift = __ldg(P.tile_start + it.tile) - it.bait_start;
+        it.seq_len = (int32_t)__ldg(P.seqlen + it.tile_seq);
+        return it;
+    }
+    if (P.draw_tab && !P.permute) {  // the rows kernel of the rank path already drew this block (bootstrap kinds: block b -> tile b)
+        const int2 d = __ldg(P.draw_tab + flat);
+        it.bait_seq = d.x;
+        it.bait_start = d.y;
+        it.tile = (int)b;
+    } else if (P.rng_mode == NRB200_RNG_PHILOX) {
+        draw_block(P, (uint64_t)(P.iter0 + r), b, it.bait_seq, it.bait_start);
+        it.tile = P.dst_tile ? __ldg(P.dst_tile + flat) : (int)b;
+    } else {
+        it.bait_seq = __ldg(P.bait_seq + flat);
+        it.bait_start = __ldg(P.bait_start + flat);
+        it.tile = P.dst_tile ? __ldg(P.dst_tile + flat) : (int)b;
+    }
+    it.bait_end = (int64_t)it.bait_start + __ldg(P.bait_width + b) - 1;
+    it.tile_seq = __ldg(P.tile_seq + it.tile);
+    it.shift = __ldg(P.tile_start + it.tile) - it.bait_start;
+    it.seq_len = (int32_t)__ldg(P.seqlen + it.tile_seq);
+    locate_block(P.y, it.bait_seq, it.bait_start, it.bait_end, it.lo, it.hi);
+    return it;
+}
+
+// shift() + trim() + the width filter for one candidate.  Returns false when the range is
+// not a hit or is dropped.  (s2, e2) is the trimmed range; e2 < s2 marks a zero-width
+// survivor of the within-chromosome variants.
+__device__ __forceinline__ bool transform(const BootParams &P, const Item &it, int32_t st, int32_t en,
+                                          int32_t &s2, int32_t &e2) {
+    // bootstrap: any overlap with the bait block; permute: the tile that holds the start
+    const bool hit = P.permute ? (st >= it.bait_start) : (en >= it.bait_start);
+    if (!hit) return false;
+    s2 = st + it.shift;
+    e2 = en + it.shift;
+    if (s2 > it.seq_len) {       // wholly beyond the sequence end -> [L + 1, L]
+        if (P.drop_zero) return false;
+        s2 = it.seq_len + 1;
+        e2 = it.seq_len;
+    } else {
+        s2 = max(s2, 1);
+        e2 = min(e2, it.seq_len);
+    }
+    return true;
+}
+
+template <bool STRANDED>
+__device__ __forceinline__ bool excluded(const SliceView &X, int tile, int32_t s2, int32_t e2, int strand) {
+    if (e2 < s2) return false;
+    const int32_t a = __ldg(X.tile_lo + tile), b = __ldg(X.tile_hi + tile);
+    for (int32_t k = a; k < b; ++k) {
+        if (s2 <= __ldg(X.end + k) && e2 >= __ldg(X.start + k)) {
+            if (!STRANDED || !X.strand || strands_match(strand, __ldg(X.strand + k))) return true;
+        }
+    }
+    return false;
+}
+
+// Exclusion modes of the streaming kernels (template parameter EXCL)
+constexpr int kExclNone = 0;  // no exclude set
+constexpr int kExclDrop = 1;  // excludeOption = "drop": P.excl = exclude ranges, overlapping ranges vanish
+constexpr int kExclTrim = 2;  // excludeOption = "trim": P.excl = gaps(exclude), ranges are cut to the gaps
+
+// countOverlaps contribution of one (piece of a) bootstrapped range: features of the tile's slice
+// with start <= pe, walked backwards under the running-max-of-end bound.
+template <bool STRANDED>
+__device__ __forceinline__ int count_piece(const BootParams &P, int64_t r, int32_t q_lo, int32_t q_hi, int32_t ps,
+                                           int32_t pe, int strand) {
+    int n = 0;
+    for (int32_t k = first_gt(P.query.start, q_lo, q_hi, pe) - 1; k >= q_lo && __ldg(P.query.pmax + k) >= ps; --k) {
+        const int32_t qe = __ldg(P.query.end + k);
+        if (qe < ps) continue;
+        if (STRANDED && P.query.strand && !strands_match(strand, __ldg(P.query.strand + k))) continue;
+        if (P.minoverlap > 0 && min(pe, qe) - max(ps, __ldg(P.query.start + k)) + 1 < P.minoverlap) continue;
+        ++n;
+        if (P.counts) atomicAdd(P.counts + r * P.n_query + __ldg(P.query.src + k), 1);
+    }
+    return n;
+}
+
+template <bool STRANDED, bool HAS_QUERY, int EXCL>
+__global__ void __launch_bounds__(256) boot_count_kernel(const BootParams P) {
+    const int lane = threadIdx.x & (kWarp - 1);
+    const int64_t warps_total = (int64_t)gridDim.x * (blockDim.x / kWarp);
+    const int64_t warp0 = (int64_t)blockIdx.x * (blockDim.x / kWarp) + (threadIdx.x / kWarp);
+    const int64_t n_items = P.n_iter * P.n_blocks;
+
+    for (int64_t item = warp0; item < n_items; item += warps_total) {
+        const int64_t r = item / P.n_blocks, b = item - r * P.n_blocks;
+        const Item it = load_item(P, r, b);
+
+        int32_t q_lo = 0, q_hi = 0, x_lo = 0, x_hi = 0;
+        if (HAS_QUERY) {
+            q_lo = __ldg(P.query.tile_lo + it.tile);
+            q_hi = __ldg(P.query.tile_hi + it.tile);
+        }
+        if (EXCL == kExclTrim) {
+            x_lo = __ldg(P.excl.tile_lo + it.tile);
+            x_hi = __ldg(P.excl.tile_hi + it.tile);
+        }
+        int rows = 0, hits = 0;
+        int overlaps = 0;
+        for (int32_t i = it.lo + lane; i < it.hi; i += kWarp) {
+            const int32_t st = __ldg(P.y.start + i), en = __ldg(P.y.end + i);
+            int32_t s2, e2;
+            hits += (P.permute ? (st >= it.bait_start) : (en >= it.bait_start)) ? 1 : 0;
+            if (!transform(P, it, st, en, s2, e2)) continue;
+            const int strand = (STRANDED && P.y.strand) ? __ldg(P.y.strand + i) : 0;
+            if (EXCL == kExclTrim) {
+                if (e2 < s2) continue;  // a zero-width survivor overlaps no gap
+                for (int32_t k = x_lo; k < x_hi; ++k) {
+                    const int32_t gs = __ldg(P.excl.start + k), ge = __ldg(P.excl.end + k);
+                    if (s2 > ge || e2 < gs) continue;
+                    ++rows;
+                    if (HAS_QUERY) overlaps += count_piece<STRANDED>(P, r, q_lo, q_hi, max(s2, gs), min(e2, ge), strand);
+                }
+                continue;
+            }
+            if (EXCL == kExclDrop && excluded<STRANDED>(P.excl, it.tile, s2, e2, strand)) continue;
+            ++rows;
+            if (HAS_QUERY && e2 >= s2) overlaps += count_piece<STRANDED>(P, r, q_lo, q_hi, s2, e2, strand);
+        }
+        rows = __reduce_add_sync(kFull, rows);
+        hits = __reduce_add_sync(kFull, hits);
+        if (HAS_QUERY) overlaps = __reduce_add_sync(kFull, overlaps);
+        if (lane == 0) {
+            if (rows) atomicAdd(P.iter_nranges + r, (unsigned long long)rows);
+            if (HAS_QUERY && overlaps) atomicAdd(P.iter_totals + r, (unsigned long long)overlaps);
+            if (P.item_rows) P.item_rows[item] = rows;
+            if (P.n_hits && hits) atomicAdd(P.n_hits, (unsigned long long)hits);
+        }
+    }
+}
+
+// ---- materialising path ---------------------------------------------------------------
+
+// One CTA per iteration: exclusive scan of the rows-per-block of that iteration.
+__global__ void __launch_bounds__(256) scan_iteration_kernel(const int32_t *__restrict__ item_rows, int64_t n_blocks,
+                                                             int32_t *__restrict__ within_off) {
+    __shared__ int warp_sums[8];
+    __shared__ int carry;
+    const int64_t r = blockIdx.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (int64_t base = 0; base < n_blocks; base += blockDim.x) {
+        const int64_t b = base + threadIdx.x;
+        const int v = b < n_blocks ? item_rows[r * n_blocks + b] : 0;
+        int x = v;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int t = __shfl_up_sync(kFull, x, d);
+            if (lane >= d) x += t;
+        }
+        if (lane == 31) warp_sums[warp] = x;
+        __syncthreads();
+        int before = carry;
+        for (int w = 0; w < warp; ++w) before += warp_sums[w];
+        if (b < n_blocks) within_off[r * n_blocks + b] = before + x - v;
+        __syncthreads();
+        if (threadIdx.x == blockDim.x - 1) carry = before + x;
+        __syncthreads();
+    }
+}
+
+struct RowsOut {
+    int32_t *seq, *start, *end, *src, *block;
+    const int64_t *iter_off;      // [n_iter + 1]
+    const int32_t *within_off;    // [n_iter x n_blocks]
+    const int32_t *item_rows;     // [n_iter x n_blocks] rows the count pass promised for the item
+    int *overflow;                // set when a fill pass finds more rows than promised (never written past the promise)
+};
+
+// grid = (block groups, iterations); one warp per (iteration, block), 64 candidate ranges per
+// loop trip (two independent loads per lane), ballot-compacted writes of the five columns.
+template <bool STRANDED, int EXCL>
+__global__ void __launch_bounds__(256) boot_fill_kernel(const BootParams P, const RowsOut O) {
+    const int lane = threadIdx.x & (kWarp - 1);
+    const unsigned below = (1u << lane) - 1u;
+    const int64_t r = blockIdx.y;
+    const int64_t row0 = __ldg(O.iter_off + r);
+    for (int64_t b = (int64_t)blockIdx.x * (blockDim.x / kWarp) + (threadIdx.x / kWarp); b < P.n_blocks;
+         b += (int64_t)gridDim.x * (blockDim.x / kWarp)) {
+        const Item it = load_item(P, r, b);
+        int64_t out = row0 + __ldg(O.within_off + r * P.n_blocks + b);
+        const int64_t out_end = out + __ldg(O.item_rows + r * P.n_blocks + b);
+        for (int32_t base = it.lo; base < it.hi; base += 2 * kWarp) {
+            const int32_t i0 = base + lane, i1 = i0 + kWarp;
+            const bool in0 = i0 < it.hi, in1 = i1 < it.hi;
+            int32_t st0 = 0, en0 = 0, st1 = 0, en1 = 0;
+            if (in0) { st0 = __ldg(P.y.start + i0); en0 = __ldg(P.y.end + i0); }
+            if (in1) { st1 = __ldg(P.y.start + i1); en1 = __ldg(P.y.end + i1); }
+            int32_t s0 = 0, e0 = 0, s1 = 0, e1 = 0;
+            bool keep0 = in0 && transform(P, it, st0, en0, s0, e0);
+            bool keep1 = in1 && transform(P, it, st1, en1, s1, e1);
+            if (EXCL == kExclDrop) {
+                if (keep0) keep0 = !excluded<STRANDED>(P.excl, it.tile, s0, e0, (STRANDED && P.y.strand) ? __ldg(P.y.strand + i0) : 0);
+                if (keep1) keep1 = !excluded<STRANDED>(P.excl, it.tile, s1, e1, (STRANDED && P.y.strand) ? __ldg(P.y.strand + i1) : 0);
+            }
+            const unsigned m0 = __ballot_sync(kFull, keep0), m1 = __ballot_sync(kFull, keep1);
+            if (out + __popc(m0) + __popc(m1) > out_end) {  // the two passes disagree: refuse to write
+                if (lane == 0) atomicExch(O.overflow, 1);
+                break;
+            }
+            if (keep0) {
+                const int64_t pos = out + __popc(m0 & below);
+                O.seq[pos] = it.tile_seq;
+                O.start[pos] = s0;
+                O.end[pos] = e0;
+                O.src[pos] = P.y.src ? __ldg(P.y.src + i0) : i0;
+                O.block[pos] = (int32_t)b;
+            }
+            out += __popc(m0);
+            if (keep1) {
+                const int64_t pos = out + __popc(m1 & below);
+                O.seq[pos] = it.tile_seq;
+                O.start[pos] = s1;
+                O.end[pos] = e1;
+                O.src[pos] = P.y.src ? __ldg(P.y.src + i1) : i1;
+                O.block[pos] = (int32_t)b;
+            }
+            out += __popc(m1);
+        }
+    }
+}
+
+// excludeOption = "trim": a range becomes one row per gap it overlaps (its intersection with the
+// gap), rows of a range in ascending gap order.  Lanes count their pieces, a warp scan places them.
+__global__ void __launch_bounds__(256) boot_fill_trim_kernel(const BootParams P, const RowsOut O) {
+    const int lane = threadIdx.x & (kWarp - 1);
+    const int64_t r = blockIdx.y;
+    const int64_t row0 = __ldg(O.iter_off + r);
+    for (int64_t b = (int64_t)blockIdx.x * (blockDim.x / kWarp) + (threadIdx.x / kWarp); b < P.n_blocks;
+         b += (int64_t)gridDim.x * (blockDim.x / kWarp)) {
+        const Item it = load_item(P, r, b);
+        const int32_t x_lo = __ldg(P.excl.tile_lo + it.tile), x_hi = __ldg(P.excl.tile_hi + it.tile);
+        int64_t out = row0 + __ldg(O.within_off + r * P.n_blocks + b);
+        const int64_t out_end = out + __ldg(O.item_rows + r * P.n_blocks + b);
+        for (int32_t base = it.lo; base < it.hi; base += kWarp) {
+            const int32_t i = base + lane;
+            int32_t s2 = 0, e2 = -1;
+            int n = 0;
+            if (i < it.hi && transform(P, it, __ldg(P.y.start + i), __ldg(P.y.end + i), s2, e2) && e2 >= s2) {
+                for (int32_t k = x_lo; k < x_hi; ++k) n += (s2 <= __ldg(P.excl.end + k) && e2 >= __ldg(P.excl.start + k));
+            }
+            int before = n;  // inclusive warp scan
+#pragma unroll
+            for (int d = 1; d < kWarp; d <<= 1) {
+                const int t = __shfl_up_sync(kFull, before, d);
+                if (lane >= d) before += t;
+            }
+            const int total = __shfl_sync(kFull, before, kWarp - 1);
+            if (out + total > out_end) {
+                if (lane == 0) atomicExch(O.overflow, 1);
+                break;
+            }
+            if (n) {
+                int64_t pos = out + (before - n);
+                const int32_t src = P.y.src ? __ldg(P.y.src + i) : i;
+                for (int32_t k = x_lo; k < x_hi; ++k) {
+                    const int32_t gs = __ldg(P.excl.start + k), ge = __ldg(P.excl.end + k);
+                    if (s2 > ge || e2 < gs) continue;
+                    O.seq[pos] = it.tile_seq;
+                    O.start[pos] = max(s2, gs);
+                    O.end[pos] = min(e2, ge);
+                    O.src[pos] = src;
+                    O.block[pos] = (int32_t)b;
+                    ++pos;
+                }
+            }
+            out += total;
+        }
+    }
+}
+
+}  // namespace nrb
