@@ -542,3 +542,30 @@ def test_weighted_sums(engine, kind, variant):
     ones = engine.run_weighted(draws)
     cnt = engine.run_counts(draws)
     assert np.array_equal(ones["feature_sums"], cnt["feature_counts"].astype(np.float64))
+
+
+def test_many_iterations_cross_batches(engine):
+    """R larger than one launch batch (2048) and than the D2H pipeline chunking: every entry point that loops
+    over batches gives the same answer as the oracle / as one-shot runs."""
+    case = H.random_case(seed=901, n=400, n_seq=3, n_query=37, n_excl=8, wmax=80)
+    plan, y, q, x = H.oracle_objects(case, 0)
+    H.load_engine(engine, case, 0)
+    R = 5000
+    ref = O.boot_counts(plan, y, q, R, exclude=x, seed=3, iter0=17, nthreads=O.max_threads())
+    got = engine.run_counts(Draws(n_iter=R, rng_mode=_lib.RNG_PHILOX, seed=3, iter0=17))
+    for k in ("iter_nranges", "iter_totals", "feature_counts"):
+        assert np.array_equal(got[k], ref[k]), k
+    tot_only = engine.run_counts(Draws(n_iter=R, rng_mode=_lib.RNG_PHILOX, seed=3, iter0=17), want_counts=False)
+    assert np.array_equal(tot_only["iter_totals"], ref["iter_totals"]) and tot_only["feature_counts"] is None
+    obs, _ = engine.count_observed()
+    m = engine.run_moments(Draws(n_iter=R, seed=3, iter0=17), observed=obs, batch_iter=1700)
+    fc = ref["feature_counts"].astype(np.int64)
+    assert np.array_equal(m["sum"], fc.sum(0)) and np.array_equal(m["sumsq"], (fc * fc).sum(0))
+    assert np.array_equal(m["n_ge_observed"], (fc >= obs[None, :]).sum(0))
+    rows = engine.run_materialize(Draws(n_iter=2500, rng_mode=_lib.RNG_PHILOX, seed=3, iter0=17))
+    assert np.array_equal(np.diff(rows["iter_offsets"]), ref["iter_nranges"][:2500])
+    if not engine.force_stream:
+        engine.set_weights(np.ones(case["y"][0].size))
+        ws = engine.run_weighted(Draws(n_iter=R, rng_mode=_lib.RNG_PHILOX, seed=3, iter0=17))
+        assert np.array_equal(ws["feature_sums"], ref["feature_counts"].astype(np.float64))
+        assert np.array_equal(ws["iter_sums"], ref["iter_totals"].astype(np.float64))
