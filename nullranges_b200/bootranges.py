@@ -129,8 +129,18 @@ def bootRanges(y: GRanges, blockLength, R: int = 1, seg: GRanges | None = None, 
     eng, kind, L_b, segd = _setup(y, blockLength, seg, exclude, excludeOption, proportionLength, type, withinChrom, device)
     draws = _make_draws(eng, kind, int(R), y, L_b, segd, rng, seed, iter0)
     rows = eng.run_materialize(draws)
-    src = rows["src"]
     lens = np.diff(rows["iter_offsets"])
+    if not eng.ranges_info()["sorted"]:
+        # The engine emits (iteration, block, canonical y order).  The reference's row order follows the order y was
+        # GIVEN in: findOverlaps() lists a block's hits by subject index (R/bootUnsegmented.R:67, 133; R/bootRanges.R:166),
+        # and the permute variants shift y in place, chromosome by chromosome (:28, :105, :164).  Only an unsorted y
+        # (allowed within chromosomes and with seg) can tell the difference.
+        it = np.repeat(np.arange(int(R)), lens)
+        second = y.seqid[rows["src"]] if kind in (_lib.PERMUTE_WITHIN, _lib.PERMUTE_ACROSS) else rows["block"]
+        o = np.lexsort((rows["start"], rows["src"], second, it))   # start: the pieces of a trimmed range stay ascending
+        for k in ("seqid", "start", "end", "src", "block"):
+            rows[k] = rows[k][o]
+    src = rows["src"]
     br = object.__new__(BootRanges)
     br.seqlevels, br.seqlengths = y.seqlevels, y.seqlengths
     br.seqid, br.start, br.end = rows["seqid"], rows["start"], rows["end"]

@@ -99,7 +99,7 @@
                  state = as.integer(seg$state))
   }
   tiles <- .Call("nrb200_R_set_plan", h, kind, as.numeric(blockLength), segl$seqid, segl$start, segl$end, segl$state)
-  list(h = h, kind = kind, L_s = as.numeric(chr_lens), tiles = tiles, seg = segl, lv = lv)
+  list(h = h, kind = kind, L_s = as.numeric(chr_lens), tiles = tiles, seg = segl, lv = lv, sorted = sorted)
 }
 
 .draws <- function(s, R, blockLength, rng) {
@@ -116,6 +116,12 @@ bootRanges <- function(y, blockLength, R = 1, seg = NULL, exclude = NULL, exclud
   s <- .setup(y, blockLength, seg, exclude, excludeOption, proportionLength, type, withinChrom, device)
   d <- .draws(s, R, blockLength, rng)
   res <- .Call("nrb200_R_run_materialize", s$h, as.numeric(R), as.numeric(iter0), as.numeric(seed), d[[1]], d[[2]], d[[3]])
+  if (!s$sorted) {   # row order of the reference follows the order y was given in (see bootranges.py)
+    it <- rep(seq_len(R), res[[1]])
+    second <- if (s$kind %in% c(4L, 5L)) .seqid(y, s$lv)[res[[5]]] else res[[6]]
+    o <- order(it, second, res[[5]], res[[3]])
+    for (k in 2:6) res[[k]] <- res[[k]][o]
+  }
   src <- res[[5]]
   br <- GenomicRanges::GRanges(S4Vectors::Rle(factor(s$lv[res[[2]] + 1L], levels = s$lv)),
                                IRanges::IRanges(res[[3]], res[[4]]), strand = GenomicRanges::strand(y)[src],

@@ -167,3 +167,43 @@ def test_product_trim_exclude():
         assert set(np.unique(br.strand)) <= {1, 2}                     # strands ride along with the pieces
     with pytest.raises(ValueError):
         bootRanges(y, blockLength=20, excludeOption="trim")          # strand(NULL): the reference errors too
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kind_args", [dict(type="bootstrap", withinChrom=True), dict(type="permute", withinChrom=True), dict(seg=True)])
+def test_product_row_order_follows_given_y(kind_args):
+    """An unsorted y (allowed within chromosomes and with seg): rows come out in the reference's order -- a block's
+    hits by index into y as given; the permute variants chromosome by chromosome in y's own order."""
+    from nullranges_b200 import GRanges, bootRanges, set_seed
+    rng = np.random.default_rng(3)
+    n = 60
+    seqid = rng.integers(0, 3, n)
+    start = (1 + rng.random(n) * (np.array(SEQLEN)[seqid] - 30)).astype(np.int64)
+    gr = GRanges(np.array(["chr1", "chr2", "chr3"])[seqid], start, width=rng.integers(1, 25, n),
+                 seqlengths={"chr1": 300, "chr2": 450, "chr3": 200}, idx=np.arange(n))
+    assert not gr.is_sorted()
+    kw = dict(kind_args)
+    if kw.pop("seg", False):
+        kw["seg"] = GRanges(np.array(["chr1", "chr2", "chr3"])[SEG["chrom"]], SEG["start"], end=SEG["end"],
+                            seqlengths={"chr1": 300, "chr2": 450, "chr3": 200}, state=SEG["state"])
+    set_seed(2)
+    br = bootRanges(gr, L_B, 3, storeBlockStart=True, **kw)
+    idx, it = br.mcols["idx"], br.iter
+    for r in (1, 2, 3):
+        m = it == r
+        if kw.get("type") == "permute":
+            key = np.stack([gr.seqid[idx[m]], idx[m]], axis=1)      # chromosome of origin, then y's own order
+            assert np.array_equal(key, key[np.lexsort((key[:, 1], key[:, 0]))])
+    if kw.get("type") != "permute":
+        # compare with the oracle's (block, y-index) order directly
+        from nullranges_b200 import Draws, _lib, get_engine
+        eng = get_engine(0)
+        kind = _lib.SEG_PROP if "seg" in kw else _lib.UNSEG_WITHIN
+        seg = SEG if "seg" in kw else None
+        plan = O.Plan(kind, SEQLEN, L_B, seg)
+        y = O.Index(3, gr.seqid, gr.start, gr.end)
+        d = plan.draw_R(O.RRng(2), 3)
+        want = np.concatenate([np.stack([O.iteration_rows(plan, y, d[0][r], d[1][r], d[2][r])[k] for k in ("chrom", "start", "end", "src")], axis=1)
+                               for r in range(3)])
+        got = np.stack([br.seqid, br.start, br.end, idx], axis=1)
+        assert np.array_equal(got, want)
