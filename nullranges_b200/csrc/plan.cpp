@@ -24,11 +24,17 @@ std::string build_plan(const nrb200_plan_spec &spec, const std::vector<int64_t> 
         p.tiles_per_seq[c] = ceil_div(seqlengths[c], spec.block_length);
     }
     p.genome_length = p.seq_cum[p.n_seq];
+    // the block tables are materialised: refuse absurd block counts before allocating them
+    constexpr int64_t kMaxBlocks = (int64_t)1 << 28;
+    auto too_many = [&](int64_t n) { return n > kMaxBlocks; };
 
     if (!p.segmented()) {
         // stopifnot(all(chrom_lens >= L_b))                       R/bootUnsegmented.R:8
         for (int64_t len : seqlengths)
             if (len < spec.block_length) return "all(chrom_lens >= L_b) is not TRUE";
+        int64_t total_tiles = 0;
+        for (int64_t t : p.tiles_per_seq) total_tiles += t;
+        if (too_many(total_tiles)) return "too many blocks per iteration (blockLength too small for this genome)";
         // Tile k of sequence c starts at 1 + k * L_b, sequences in seqlevel order.
         for (int c = 0; c < p.n_seq; ++c)
             for (int64_t k = 0; k < p.tiles_per_seq[c]; ++k) {
@@ -76,6 +82,7 @@ std::string build_plan(const nrb200_plan_spec &spec, const std::vector<int64_t> 
             if (Lbs <= 0) return "a state's scaled block length round(L_b * L_s / L_g) is 0";
         }
         p.state_block_len[s] = Lbs;
+        if (too_many(p.n_blocks() + ceil_div(total, Lbs))) return "too many blocks per iteration (blockLength too small for this genome)";
         int64_t before = 0;
         for (int64_t j : members) {
             const int64_t width = (int64_t)spec.seg_end[j] - spec.seg_start[j] + 1;
