@@ -56,6 +56,13 @@ struct DevMem {
         return e;
     }
     template <class T> T *as() const { return static_cast<T *>(p); }
+    void swap(DevMem &o) {
+        std::swap(p, o.p);
+        std::swap(cap, o.cap);
+    }
+    DevMem() = default;
+    DevMem(const DevMem &) = delete;  // owns its allocation
+    DevMem &operator=(const DevMem &) = delete;
 };
 
 // One set of ranges in canonical order, host mirror + device copy.
@@ -105,6 +112,7 @@ struct nrb200_handle {
     int rank_shift = 0;
     std::vector<int64_t> rank_off;
     DevMem inspect_dev, seq_info_dev, draw_tab;
+    DevMem raw_seqid, raw_start, raw_end, raw_strand;  // caller-order copies of an unsorted y while it is being sorted
     // stranded y only: class-major copy for the rank path (kernels.cuh, RangesView)
     int n_cls = 1, n_width = 1;
     int32_t query_minoverlap = 0, index_minoverlap = 0;  // the index groups y by "narrower than minoverlap": rebuilt when it changes

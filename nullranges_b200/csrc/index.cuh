@@ -93,7 +93,8 @@ int load_range_set(nrb200_handle *h, RangeSet &rs, const char *what, int64_t n, 
 // y on the fast path: the caller's arrays go to the device as they are and ONE kernel does the
 // argument checks and finds out whether they are already in canonical order (the usual case:
 // the reference insists on sort(y) for the across-chromosome samplers, R/bootUnsegmented.R:31).
-// Unsorted input falls back to the host canonicalisation above.  Returns 1 for "fall back".
+// Unsorted input is sorted on the device (two stable radix sorts); only INVALID input falls back to the host
+// path above, which words the error.  Returns 1 for "fall back".
 int load_y_device(nrb200_handle *h, int64_t n, const int32_t *seqid, const int32_t *start, const int32_t *end,
                   const int8_t *strand) {
     RangeSet &y = h->y;
@@ -125,10 +126,49 @@ int load_y_device(nrb200_handle *h, int64_t n, const int32_t *seqid, const int32
     NRB_CUDA(h, cudaMemcpyAsync(res.data(), base, words * 4, cudaMemcpyDeviceToHost, h->stream));
     if ((rc = sync_stream(h))) return rc;  // the caller's arrays are no longer read after this point
     tr.lap("inspect+sync");
-    if (res[0] != 0 || res[1] != 0) return 1;  // invalid (host path names the problem) or unsorted
+    if (res[0] != 0) return 1;  // invalid: the host path names the problem
     y.n = n;
-    y.sorted_input = true;
+    y.sorted_input = res[1] == 0;
     y.stranded = res[2] != 0;
+    if (!y.sorted_input) {
+        // Canonical order on the device: stable LSD sort, first on end, then on (seqid << 32 | start); the
+        // sorted payload is src, the canonical -> caller's-order map; the columns are gathered through it.
+        const unsigned grid = (unsigned)((n + 255) / 256);
+        NRB_CUDA(h, h->sort_keys_a.reserve((size_t)n * 8));
+        NRB_CUDA(h, h->sort_keys_b.reserve((size_t)n * 8));
+        for (DevMem *m : {&h->r_idx, &h->r_order, &h->r_keys_a, &h->r_keys_b, &y.src}) NRB_CUDA(h, m->reserve((size_t)n * 4));
+        canon_keys_end_kernel<<<grid, 256, 0, h->stream>>>(y.end.as<int32_t>(), n, h->r_keys_a.as<unsigned>(), h->r_idx.as<int32_t>());
+        size_t tmp = 0;
+        NRB_CUDA(h, cub::DeviceRadixSort::SortPairs(nullptr, tmp, h->r_keys_a.as<unsigned>(), h->r_keys_b.as<unsigned>(),
+                                                    h->r_idx.as<int32_t>(), h->r_order.as<int32_t>(), n, 0, 31, h->stream));
+        NRB_CUDA(h, h->sort_tmp.reserve(tmp));
+        NRB_CUDA(h, cub::DeviceRadixSort::SortPairs(h->sort_tmp.p, tmp, h->r_keys_a.as<unsigned>(), h->r_keys_b.as<unsigned>(),
+                                                    h->r_idx.as<int32_t>(), h->r_order.as<int32_t>(), n, 0, 31, h->stream));
+        canon_keys_seq_start_kernel<<<grid, 256, 0, h->stream>>>(h->r_order.as<int32_t>(), y.seqid.as<int32_t>(), y.start.as<int32_t>(), n,
+                                                                 h->sort_keys_a.as<unsigned long long>());
+        int seq_bits = 1;
+        while ((1 << seq_bits) < C) ++seq_bits;
+        tmp = 0;
+        NRB_CUDA(h, cub::DeviceRadixSort::SortPairs(nullptr, tmp, h->sort_keys_a.as<unsigned long long>(), h->sort_keys_b.as<unsigned long long>(),
+                                                    h->r_order.as<int32_t>(), y.src.as<int32_t>(), n, 0, 32 + seq_bits, h->stream));
+        NRB_CUDA(h, h->sort_tmp.reserve(tmp));
+        NRB_CUDA(h, cub::DeviceRadixSort::SortPairs(h->sort_tmp.p, tmp, h->sort_keys_a.as<unsigned long long>(), h->sort_keys_b.as<unsigned long long>(),
+                                                    h->r_order.as<int32_t>(), y.src.as<int32_t>(), n, 0, 32 + seq_bits, h->stream));
+        // gather the columns: the caller-order copies move aside, the canonical ones take their place
+        y.seqid.swap(h->raw_seqid);
+        y.start.swap(h->raw_start);
+        y.end.swap(h->raw_end);
+        for (DevMem *m : {&y.seqid, &y.start, &y.end}) NRB_CUDA(h, m->reserve((size_t)n * 4));
+        gather_ranges_kernel<<<grid, 256, 0, h->stream>>>(y.src.as<int32_t>(), h->raw_seqid.as<int32_t>(), h->raw_start.as<int32_t>(),
+                                                          h->raw_end.as<int32_t>(), n, y.seqid.as<int32_t>(), y.start.as<int32_t>(),
+                                                          y.end.as<int32_t>());
+        if (strand) {
+            y.strand.swap(h->raw_strand);
+            NRB_CUDA(h, y.strand.reserve((size_t)n));
+            gather_i8_kernel<<<grid, 256, 0, h->stream>>>(y.src.as<int32_t>(), h->raw_strand.as<int8_t>(), n, y.strand.as<int8_t>());
+        }
+        NRB_CUDA(h, cudaGetLastError());
+    }
     y.wmax = res[3];
     y.wmin = res[4];
     y.h_seq_off.assign(C + 1, 0);

@@ -234,6 +234,39 @@ __global__ void pack_vend_keys_kernel(const unsigned *__restrict__ vkeys, const 
     if (i < n) keys[i] = ((unsigned long long)vkeys[i] << 32) | (unsigned)end[i];
 }
 
+// ---- canonical order of an unsorted y, on the device ------------------------------------------
+// (seqid, start, end) order = stable sort on end, then stable sort on (seqid << 32 | start)
+__global__ void canon_keys_end_kernel(const int32_t *__restrict__ end, int64_t n, unsigned *__restrict__ keys, int32_t *__restrict__ idx) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        keys[i] = (unsigned)end[i];
+        idx[i] = (int32_t)i;
+    }
+}
+__global__ void canon_keys_seq_start_kernel(const int32_t *__restrict__ order, const int32_t *__restrict__ seqid,
+                                            const int32_t *__restrict__ start, int64_t n, unsigned long long *__restrict__ keys) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        const int32_t o = order[i];
+        keys[i] = ((unsigned long long)(unsigned)seqid[o] << 32) | (unsigned)start[o];
+    }
+}
+__global__ void gather_ranges_kernel(const int32_t *__restrict__ src, const int32_t *__restrict__ seqid, const int32_t *__restrict__ start,
+                                     const int32_t *__restrict__ end, int64_t n, int32_t *__restrict__ c_seqid,
+                                     int32_t *__restrict__ c_start, int32_t *__restrict__ c_end) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        const int32_t o = src[i];
+        c_seqid[i] = seqid[o];
+        c_start[i] = start[o];
+        c_end[i] = end[o];
+    }
+}
+__global__ void gather_i8_kernel(const int32_t *__restrict__ src, const int8_t *__restrict__ in, int64_t n, int8_t *__restrict__ out) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = in[src[i]];
+}
+
 // entry t of a packed rank table (see "direct-address rank tables")
 __global__ void build_rank_table_kernel(const int32_t *__restrict__ values, const int32_t *__restrict__ seq_off,
                                         const int64_t *__restrict__ rank_off, int n_seq, int shift,
