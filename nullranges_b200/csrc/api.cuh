@@ -49,6 +49,10 @@ void nrb200_destroy(nrb200_handle *h) {
         if (ev) cudaEventDestroy(ev);
     for (auto &ev : h->chunk_ev)
         if (ev) cudaEventDestroy(ev);
+    for (auto &ev : h->copied_ev)
+        if (ev) cudaEventDestroy(ev);
+    if (h->stage_buf) cudaFreeHost(h->stage_buf);
+    if (h->stage_in) cudaFreeHost(h->stage_in);
     for (auto &ev : h->batch_ev) cudaEventDestroy(ev);
     if (h->copy_stream) {
         cudaStreamSynchronize(h->copy_stream);

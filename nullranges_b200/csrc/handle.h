@@ -97,6 +97,11 @@ struct nrb200_handle {
     cudaEvent_t split_ev = nullptr;       // set while a stats run wants the rows / count kernel split
     std::vector<cudaEvent_t> batch_ev;    // 3 per batch: start, rows done, count done
     cudaEvent_t chunk_ev[16] = {};
+    cudaEvent_t copied_ev[16] = {};   // pageable destinations: chunk k has reached the pinned staging buffer
+    void *stage_buf = nullptr;        // that buffer (pinned, grown on demand)
+    size_t stage_cap = 0;
+    void *stage_in = nullptr;         // pinned staging for large pageable INPUT columns (4 regions)
+    size_t stage_in_cap = 0;
     std::string error;
     int sm_count = 148;
 
@@ -212,11 +217,42 @@ int upload_staged(nrb200_handle *h, DevMem &dst, const T *arena_src, size_t n) {
     return NRB200_OK;
 }
 
-// Host -> device copy straight from a caller-owned array (pinned or pageable): never staged.
+// Host -> device copy of a (large) caller-owned array.  Pinned memory goes straight to the DMA engine.  Pageable
+// memory (R's vectors, plain numpy arrays) would be staged by the driver at a few GB/s: it is copied into a pinned
+// buffer of the handle with a parallel memcpy first.  `slot` (0..3) picks the region of that buffer, so that the
+// columns of one call do not overwrite each other before the stream is synchronised.
 template <class T>
-int upload_direct(nrb200_handle *h, DevMem &dst, const T *src, size_t n) {
-    NRB_CUDA(h, dst.reserve(n * sizeof(T)));
-    if (n) NRB_CUDA(h, cudaMemcpyAsync(dst.p, src, n * sizeof(T), cudaMemcpyHostToDevice, h->stream));
+int upload_direct(nrb200_handle *h, DevMem &dst, const T *src, size_t n, int slot = 0) {
+    const size_t bytes = n * sizeof(T);
+    NRB_CUDA(h, dst.reserve(bytes));
+    if (!n) return NRB200_OK;
+    const void *from = src;
+    if (bytes >= ((size_t)256 << 10) && bytes <= ((size_t)256 << 20)) {
+        cudaPointerAttributes attr{};
+        const bool pageable = cudaPointerGetAttributes(&attr, src) != cudaSuccess || attr.type == cudaMemoryTypeUnregistered;
+        cudaGetLastError();
+        if (pageable) {
+            // regions are sized for 8-byte elements whatever T is: the columns of one call (same n) never overlap
+            const size_t region = (n * 8 + 4095) & ~(size_t)4095, need = 4 * region;
+            if (h->stage_in_cap < need) {
+                if (h->stage_in) cudaFreeHost(h->stage_in);
+                h->stage_in = nullptr;
+                h->stage_in_cap = 0;
+                if (cudaMallocHost((void **)&h->stage_in, need) == cudaSuccess) h->stage_in_cap = need;
+                else cudaGetLastError();
+            }
+            if (h->stage_in_cap >= need) {
+                char *to = static_cast<char *>(h->stage_in) + (size_t)slot * region;
+                const size_t piece = (size_t)1 << 20;
+                const int64_t pieces = (int64_t)((bytes + piece - 1) / piece);
+#pragma omp parallel for schedule(static)
+                for (int64_t i = 0; i < pieces; ++i)
+                    std::memcpy(to + i * piece, reinterpret_cast<const char *>(src) + i * piece, std::min(piece, bytes - (size_t)i * piece));
+                from = to;
+            }
+        }
+    }
+    NRB_CUDA(h, cudaMemcpyAsync(dst.p, from, bytes, cudaMemcpyHostToDevice, h->stream));
     return NRB200_OK;
 }
 

@@ -101,10 +101,10 @@ int load_y_device(nrb200_handle *h, int64_t n, const int32_t *seqid, const int32
     const int C = h->n_seq;
     if (n <= 0 || n > (int64_t)INT32_MAX - 64 || !seqid || !start || !end) return 1;  // host path words the errors
     int rc;
-    if ((rc = upload_direct(h, y.seqid, seqid, (size_t)n))) return rc;
-    if ((rc = upload_direct(h, y.start, start, (size_t)n))) return rc;
-    if ((rc = upload_direct(h, y.end, end, (size_t)n))) return rc;
-    if (strand && (rc = upload_direct(h, y.strand, strand, (size_t)n))) return rc;
+    if ((rc = upload_direct(h, y.seqid, seqid, (size_t)n, 0))) return rc;
+    if ((rc = upload_direct(h, y.start, start, (size_t)n, 1))) return rc;
+    if ((rc = upload_direct(h, y.end, end, (size_t)n, 2))) return rc;
+    if (strand && (rc = upload_direct(h, y.strand, strand, (size_t)n, 3))) return rc;
     Trace tr("load_y_device");
     tr.lap("enqueue_h2d");
     // scratch: InspectOut (5 words, padded to 8) | seq_count[C] | seq_max_end[C]

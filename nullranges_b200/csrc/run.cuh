@@ -199,6 +199,7 @@ void launch_count_t(nrb200_handle *h, const BootParams &P, unsigned grid, int ex
 
 constexpr int64_t kMaxBatch = 2048;  // iterations per launch at most (gridDim.y and scratch stay small); NRB200_MAX_BATCH lowers it
 constexpr int kChunkEvents = 16;
+constexpr size_t kMaxStagingBytes = (size_t)2 << 30;  // pinned staging for pageable result buffers, at most
 constexpr int kChunks = 8;  // pipeline depth of nrb200_run_counts (compute chunk k+1 while chunk k copies out)
 
 // Returns the number of kernels launched.
@@ -306,6 +307,27 @@ int run_counts_core(nrb200_handle *h, const nrb200_draws *d, bool want_counts, i
         NRB_CUDA(h, h->draw_tab.reserve((size_t)std::min(chunk, std::max<int64_t>(R, 1)) * h->plan.n_blocks() * sizeof(int2)));
         P.draw_tab = h->draw_tab.as<int2>();
     }
+    // A pageable destination (R's own vectors are): cudaMemcpyAsync would stage it synchronously at a few GB/s.
+    // Copy chunk by chunk into a pinned staging buffer of the handle instead and move each chunk on with a
+    // parallel memcpy as soon as its copy event fires, while later chunks still compute / travel.
+    int32_t *staging = nullptr;
+    std::vector<std::pair<int64_t, int64_t>> staged;  // (first iteration, count) of every chunk, in order
+    if (pipelined) {
+        cudaPointerAttributes attr{};
+        const bool pageable = cudaPointerGetAttributes(&attr, host_counts) != cudaSuccess || attr.type == cudaMemoryTypeUnregistered;
+        cudaGetLastError();  // an unregistered pointer may leave a sticky-free error behind on older drivers
+        const size_t bytes = (size_t)R * G * sizeof(int32_t);
+        if (pageable && bytes <= kMaxStagingBytes) {
+            if (h->stage_cap < bytes) {
+                if (h->stage_buf) cudaFreeHost(h->stage_buf);
+                h->stage_buf = nullptr;
+                h->stage_cap = 0;
+                if (cudaMallocHost((void **)&h->stage_buf, bytes) == cudaSuccess) h->stage_cap = bytes;
+                else cudaGetLastError();
+            }
+            if (h->stage_cap >= bytes) staging = static_cast<int32_t *>(h->stage_buf);
+        }
+    }
     int k = 0;
     const bool split = stats && rank_path_ok(h, has_query);
     for (int64_t r0 = 0; r0 < R; r0 += chunk, ++k) {
@@ -328,11 +350,28 @@ int run_counts_core(nrb200_handle *h, const nrb200_draws *d, bool want_counts, i
             if (!ev) NRB_CUDA(h, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
             NRB_CUDA(h, cudaEventRecord(ev, h->stream));
             NRB_CUDA(h, cudaStreamWaitEvent(h->copy_stream, ev, 0));
-            NRB_CUDA(h, cudaMemcpyAsync(host_counts + r0 * G, counts + r0 * G, (size_t)n * G * sizeof(int32_t),
+            NRB_CUDA(h, cudaMemcpyAsync((staging ? staging : host_counts) + r0 * G, counts + r0 * G, (size_t)n * G * sizeof(int32_t),
                                         cudaMemcpyDeviceToHost, h->copy_stream));
+            if (staging) {
+                cudaEvent_t &done = h->copied_ev[k % kChunkEvents];
+                if (!done) NRB_CUDA(h, cudaEventCreateWithFlags(&done, cudaEventDisableTiming));
+                NRB_CUDA(h, cudaEventRecord(done, h->copy_stream));
+                staged.emplace_back(r0, n);
+            }
         }
     }
     NRB_CUDA(h, cudaEventRecord(h->ev[2], h->stream));
+    for (size_t c = 0; c < staged.size(); ++c) {  // chunk c has landed in pinned memory: hand it to the caller
+        NRB_CUDA(h, cudaEventSynchronize(h->copied_ev[c % kChunkEvents]));
+        const int64_t r0 = staged[c].first, n = staged[c].second;
+        const size_t bytes = (size_t)n * G * sizeof(int32_t);
+        const char *src = reinterpret_cast<const char *>(staging + r0 * G);
+        char *dst = reinterpret_cast<char *>(host_counts + r0 * G);
+        const size_t piece = (size_t)1 << 20;
+        const int64_t pieces = (int64_t)((bytes + piece - 1) / piece);
+#pragma omp parallel for schedule(static)
+        for (int64_t i = 0; i < pieces; ++i) std::memcpy(dst + i * piece, src + i * piece, std::min(piece, bytes - (size_t)i * piece));
+    }
     h->res_has_counts = want_counts;
     if (stats) {
         NRB_CUDA(h, cudaEventSynchronize(h->ev[2]));
