@@ -170,7 +170,7 @@ __global__ void __launch_bounds__(256, MINB) boot_rank_count_kernel(const BootPa
         if (P.counts) {
 #pragma unroll
             for (int j = 0; j < RPT; ++j)
-                if (j < n_live) P.counts[(r0 + j) * P.n_query + src] = cnt[j];
+                if (j < n_live) __stcs(P.counts + (r0 + j) * P.n_query + src, cnt[j]);  // streaming store: written once, read back by the copy engine
         }
     }
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
