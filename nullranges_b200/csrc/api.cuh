@@ -341,7 +341,7 @@ int nrb200_run_weighted(nrb200_handle *h, const nrb200_draws *draws, double *ite
     if ((rc = prepare(h))) return rc;
     if (!h->have_weights) return fail(h, NRB200_ERR_STATE, "nrb200_set_weights() has not been called");
     if (h->query.n == 0) return fail(h, NRB200_ERR_STATE, "nrb200_set_query() has not been called");
-    if (!rank_path_ok(h, true))
+    if (!rank_path_ok(h))
         return fail(h, NRB200_ERR_UNSUPPORTED, "weighted sums run on the rank path only (segmentation within seqlengths, no NRB200_FLAG_FORCE_STREAM)");
     if ((rc = build_weight_index(h))) return rc;
     NRB_CUDA(h, cudaEventRecord(h->ev[0], h->stream));
@@ -464,7 +464,7 @@ int nrb200_run_materialize(nrb200_handle *h, const nrb200_draws *draws, int64_t 
     P.n_hits = h->d_n_hits.as<unsigned long long>();
     NRB_CUDA(h, cudaEventRecord(h->ev[1], h->stream));
     int count_launches = 0;
-    const bool rank_rows = rank_path_ok(h, false);
+    const bool rank_rows = rank_path_ok(h);
     if (rank_rows && items > 0) {  // the rows kernel leaves each block's draw and hit window for the fill kernel
         NRB_CUDA(h, h->item_rec.reserve((size_t)items * sizeof(int4)));
         P.item_rec = h->item_rec.as<int4>();

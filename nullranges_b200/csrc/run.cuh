@@ -4,8 +4,7 @@ namespace {
 
 // The rank path covers every sampler (bootstrap and permute, with or without exclusion, any strands);
 // only a segmentation reaching beyond its sequence falls back to streaming the hits (boot_count_kernel).
-bool rank_path_ok(const nrb200_handle *h, bool with_query) {
-    (void)with_query;
+bool rank_path_ok(const nrb200_handle *h) {
     if (h->flags & NRB200_FLAG_FORCE_STREAM) return false;
     return h->tiles_in_bounds;
 }
@@ -22,21 +21,18 @@ int prepare(nrb200_handle *h) {
         if (h->index_minoverlap != h->query_minoverlap && (rc = build_rank_tables(h))) return rc;  // the width classes changed
         if (trim_mode(h) && h->excl.stranded) return fail(h, NRB200_ERR_INVALID, "all(strand(exclude) == \"*\") is not TRUE");
         if (trim_mode(h) && (rc = build_gaps(h))) return rc;
-        // rank_path_ok(h, false) holds whenever rank_path_ok(h, true) does
-        const bool rank_q = h->query.n && rank_path_ok(h, true), rank_rows = rank_path_ok(h, false);
-        if (rank_q || rank_rows) {
-            const int64_t g_keep = h->query.n;
-            if (!rank_q) h->query.n = 0;  // tables for the row counts only
-            rc = build_pairs(h);
-            h->query.n = g_keep;
-            if (rc) return rc;
+        const bool rank = rank_path_ok(h);
+        if (rank) {
+            if ((rc = build_pairs(h))) return rc;  // window lists of the features and of the tiles
             tr.lap("build_pairs");
         }
         // the streaming kernels (count without the rank path, and the fill pass) test exclusion per range
         if (h->excl.n && (rc = build_slices(h, active_excl(h), h->x_tile_lo, h->x_tile_hi))) return rc;
-        if (h->query.n && !rank_q && (rc = range_set_to_device(h, h->query))) return rc;
-        if (h->query.n && !rank_q && (rc = build_slices(h, h->query, h->q_tile_lo, h->q_tile_hi))) return rc;
-        if (((h->query.n && !rank_q) || !rank_rows) && (rc = ensure_pmax_table(h))) return rc;
+        if (!rank) {
+            if (h->query.n && (rc = range_set_to_device(h, h->query))) return rc;
+            if (h->query.n && (rc = build_slices(h, h->query, h->q_tile_lo, h->q_tile_hi))) return rc;
+            if ((rc = ensure_pmax_table(h))) return rc;
+        }
         h->slices_dirty = false;
     }
     return NRB200_OK;
@@ -114,6 +110,17 @@ int stage_draws(nrb200_handle *h, const nrb200_draws *d) {
         if (d->bait_seqid[i] < 0 || d->bait_seqid[i] >= h->n_seq) return fail(h, NRB200_ERR_INVALID, "draws: bait_seqid out of range");
         if (d->bait_start[i] < 1 || d->bait_start[i] >= (1 << 30)) return fail(h, NRB200_ERR_INVALID, "draws: bait_start out of range");
         if (d->dst_tile && (d->dst_tile[i] < 0 || d->dst_tile[i] >= B)) return fail(h, NRB200_ERR_INVALID, "draws: dst_tile out of range");
+    }
+    if (p.permute() && n > 0) {  // sample(n) (R/bootUnsegmented.R:97, :156): every tile is the destination of exactly one block
+        std::vector<uint8_t> seen((size_t)B);
+        for (int64_t r = 0; r < d->n_iter; ++r) {
+            std::fill(seen.begin(), seen.end(), 0);
+            for (int64_t b = 0; b < B; ++b) {
+                uint8_t &s = seen[d->dst_tile[r * B + b]];
+                if (s) return fail(h, NRB200_ERR_INVALID, "draws: dst_tile must be a permutation of the tiles in every iteration");
+                s = 1;
+            }
+        }
     }
     int rc;
     if ((rc = upload(h, h->d_bait_seq, d->bait_seqid, (size_t)n))) return rc;
@@ -233,7 +240,7 @@ int launch_rank(nrb200_handle *h, const BootParams &P, bool has_query) {
 }
 
 int launch_count(nrb200_handle *h, const BootParams &P, bool has_query) {
-    if (rank_path_ok(h, has_query)) return launch_rank(h, P, has_query);
+    if (rank_path_ok(h)) return launch_rank(h, P, has_query);
     const int64_t items = P.n_iter * P.n_blocks;
     if (items == 0) return 0;
     const int64_t ctas = (items + 7) / 8;
@@ -286,7 +293,7 @@ int run_counts_core(nrb200_handle *h, const nrb200_draws *d, bool want_counts, i
         NRB_CUDA(h, h->d_counts.reserve((size_t)R * G * sizeof(int32_t)));
         counts = h->d_counts.as<int32_t>();
         // the rank path writes every element; the streaming path accumulates with atomics
-        if (!rank_path_ok(h, true)) NRB_CUDA(h, cudaMemsetAsync(counts, 0, (size_t)R * G * sizeof(int32_t), h->stream));
+        if (!rank_path_ok(h)) NRB_CUDA(h, cudaMemsetAsync(counts, 0, (size_t)R * G * sizeof(int32_t), h->stream));
     }
     BootParams P = make_params(h, d);
     P.iter_nranges = h->d_iter_nranges.as<unsigned long long>();
@@ -303,7 +310,7 @@ int run_counts_core(nrb200_handle *h, const nrb200_draws *d, bool want_counts, i
         if (!h->copy_stream) NRB_CUDA(h, cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
         chunk = std::min<int64_t>(h->tune_max_batch, std::max<int64_t>(((R + kChunks - 1) / kChunks + 7) / 8 * 8, 64));
     }
-    if (rank_path_ok(h, has_query) && has_query) {
+    if (rank_path_ok(h) && has_query) {
         NRB_CUDA(h, h->draw_tab.reserve((size_t)std::min(chunk, std::max<int64_t>(R, 1)) * h->plan.n_blocks() * sizeof(int2)));
         P.draw_tab = h->draw_tab.as<int2>();
     }
@@ -329,7 +336,7 @@ int run_counts_core(nrb200_handle *h, const nrb200_draws *d, bool want_counts, i
         }
     }
     int k = 0;
-    const bool split = stats && rank_path_ok(h, has_query);
+    const bool split = stats && rank_path_ok(h);
     for (int64_t r0 = 0; r0 < R; r0 += chunk, ++k) {
         const int64_t n = std::min(chunk, R - r0);
         if (split) {

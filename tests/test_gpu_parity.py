@@ -569,3 +569,15 @@ def test_many_iterations_cross_batches(engine):
         ws = engine.run_weighted(Draws(n_iter=R, rng_mode=_lib.RNG_PHILOX, seed=3, iter0=17))
         assert np.array_equal(ws["feature_sums"], ref["feature_counts"].astype(np.float64))
         assert np.array_equal(ws["iter_sums"], ref["iter_totals"].astype(np.float64))
+
+
+def test_host_permutation_is_validated(engine):
+    from nullranges_b200 import EngineError
+    case = H.random_case(seed=5, n=100, n_seq=2, n_query=10)
+    plan, *_ = H.oracle_objects(case, 5)
+    H.load_engine(engine, case, 5)
+    d = H.draw_R(plan, 1, 2)
+    bad = d[2].copy()
+    bad[1, 0] = bad[1, 1]          # two blocks sent to the same tile
+    with pytest.raises(EngineError, match="permutation"):
+        engine.run_counts(Draws(n_iter=2, rng_mode=_lib.RNG_HOST, bait_seqid=d[0], bait_start=d[1], dst_tile=bad))
