@@ -144,7 +144,7 @@ def bootRanges(y: GRanges, blockLength, R: int = 1, seg: GRanges | None = None, 
     br = object.__new__(BootRanges)
     br.seqlevels, br.seqlengths = y.seqlevels, y.seqlengths
     br.seqid, br.start, br.end = rows["seqid"], rows["start"], rows["end"]
-    br.strand = y.strand[src]
+    br.strand = y.strand[src] if np.any(y.strand) else np.zeros(src.size, np.int8)
     br.mcols = {k: v[src] for k, v in y.mcols.items() if k != "block"}
     # mcols(br)$iter <- Rle(factor(rep(seq_len(R), lens), levels = seq_len(R)))   R/bootRanges.R:122
     br.mcols["iter"] = np.repeat(np.arange(1, int(R) + 1, dtype=np.int32), lens)

@@ -534,10 +534,10 @@ int nrb200_fetch_rows(nrb200_handle *h, int64_t row0, int64_t n, int32_t *seqid,
     if (row0 < 0 || n < 0 || row0 + n > h->n_rows) return fail(h, NRB200_ERR_INVALID, "fetch_rows: range outside the materialised table");
     struct { int32_t *dst; DevMem *src; } cols[] = {{seqid, &h->row_seq}, {start, &h->row_start}, {end, &h->row_end},
                                                      {src_idx, &h->row_src}, {block, &h->row_block}};
+    if (int rc_sync = sync_stream(h)) return rc_sync;
     for (auto &c : cols)
         if (c.dst && n)
-            NRB_CUDA(h, cudaMemcpyAsync(c.dst, c.src->as<int32_t>() + row0, n * 4, cudaMemcpyDeviceToHost, h->stream));
-    if (int rc_sync = sync_stream(h)) return rc_sync;
+            if (int rc = download(h, c.dst, c.src->as<int32_t>() + row0, (size_t)n * 4)) return rc;
     return NRB200_OK;
 }
 

@@ -217,6 +217,56 @@ int upload_staged(nrb200_handle *h, DevMem &dst, const T *arena_src, size_t n) {
     return NRB200_OK;
 }
 
+// Device -> host copy into a caller-owned buffer, complete on return.  Pinned destinations take one DMA; large
+// pageable ones (R's vectors, plain numpy arrays) go through a double-buffered pinned staging area: chunk i
+// travels while chunk i - 1 is moved on with a parallel memcpy.
+inline int download(nrb200_handle *h, void *dst, const void *src_dev, size_t bytes) {
+    if (!bytes) return NRB200_OK;
+    cudaPointerAttributes attr{};
+    const bool pageable = cudaPointerGetAttributes(&attr, dst) != cudaSuccess || attr.type == cudaMemoryTypeUnregistered;
+    cudaGetLastError();
+    constexpr size_t kChunk = (size_t)32 << 20;
+    if (pageable && bytes >= ((size_t)1 << 20)) {
+        if (h->stage_cap < 2 * kChunk) {
+            if (h->stage_buf) cudaFreeHost(h->stage_buf);
+            h->stage_buf = nullptr;
+            h->stage_cap = 0;
+            if (cudaMallocHost((void **)&h->stage_buf, 2 * kChunk) == cudaSuccess) h->stage_cap = 2 * kChunk;
+            else cudaGetLastError();
+        }
+    }
+    if (!pageable || bytes < ((size_t)1 << 20) || h->stage_cap < 2 * kChunk) {
+        NRB_CUDA(h, cudaMemcpyAsync(dst, src_dev, bytes, cudaMemcpyDeviceToHost, h->stream));
+        NRB_CUDA(h, cudaStreamSynchronize(h->stream));
+        return NRB200_OK;
+    }
+    for (int k = 0; k < 2; ++k)
+        if (!h->copied_ev[k]) NRB_CUDA(h, cudaEventCreateWithFlags(&h->copied_ev[k], cudaEventDisableTiming));
+    auto move_out = [&](size_t chunk) {
+        const size_t off = chunk * kChunk, len = std::min(kChunk, bytes - off);
+        const char *from = static_cast<const char *>(h->stage_buf) + (chunk & 1) * kChunk;
+        char *to = static_cast<char *>(dst) + off;
+        const size_t piece = (size_t)1 << 20;
+        const int64_t pieces = (int64_t)((len + piece - 1) / piece);
+#pragma omp parallel for schedule(static)
+        for (int64_t i = 0; i < pieces; ++i) std::memcpy(to + i * piece, from + i * piece, std::min(piece, len - (size_t)i * piece));
+    };
+    const size_t chunks = (bytes + kChunk - 1) / kChunk;
+    for (size_t c = 0; c < chunks; ++c) {
+        const size_t off = c * kChunk, len = std::min(kChunk, bytes - off);
+        NRB_CUDA(h, cudaMemcpyAsync(static_cast<char *>(h->stage_buf) + (c & 1) * kChunk, static_cast<const char *>(src_dev) + off, len,
+                                    cudaMemcpyDeviceToHost, h->stream));
+        NRB_CUDA(h, cudaEventRecord(h->copied_ev[c & 1], h->stream));
+        if (c > 0) {  // chunk c - 1 has its own slot: move it out while chunk c is on the wire
+            NRB_CUDA(h, cudaEventSynchronize(h->copied_ev[(c - 1) & 1]));
+            move_out(c - 1);
+        }
+    }
+    NRB_CUDA(h, cudaEventSynchronize(h->copied_ev[(chunks - 1) & 1]));
+    move_out(chunks - 1);
+    return NRB200_OK;
+}
+
 // Host -> device copy of a (large) caller-owned array.  Pinned memory goes straight to the DMA engine.  Pageable
 // memory (R's vectors, plain numpy arrays) would be staged by the driver at a few GB/s: it is copied into a pinned
 // buffer of the handle with a parallel memcpy first.  `slot` (0..3) picks the region of that buffer, so that the
