@@ -581,3 +581,13 @@ def test_host_permutation_is_validated(engine):
     bad[1, 0] = bad[1, 1]          # two blocks sent to the same tile
     with pytest.raises(EngineError, match="permutation"):
         engine.run_counts(Draws(n_iter=2, rng_mode=_lib.RNG_HOST, bait_seqid=d[0], bait_start=d[1], dst_tile=bad))
+
+
+@pytest.mark.parametrize("kind", [0, 1, 2, 5])
+def test_many_sequences(engine, kind):
+    """Hundreds of seqlevels (assemblies with contigs): per-sequence tables, draws in proportion to length,
+    device permutations with a wide sequence field."""
+    case = H.random_case(seed=950 + kind, n=3000, n_seq=300, max_len=4000, n_query=400, n_excl=40, stranded=kind == 1, L_b=700,
+                         n_seg=600, n_states=3, wmax=150)
+    _check_counts(engine, case, kind, R=3, seed=5, philox=False)
+    _check_counts(engine, case, kind, R=3, seed=5, philox=True)
