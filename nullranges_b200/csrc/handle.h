@@ -39,11 +39,31 @@ struct Trace {
 static thread_local std::string g_create_error;
 
 // Growth-only device buffer.
+// NRB200_GUARD=1 (development aid; compute-sanitizer is not available on the test pool): every buffer gets a
+// 256-byte tail filled with a pattern, checked whenever the buffer is released; an out-of-bounds WRITE behind
+// any device buffer aborts with a message.
+inline bool guard_on() {
+    static const bool v = getenv("NRB200_GUARD") != nullptr;
+    return v;
+}
+constexpr size_t kGuardBytes = 256;
+
 struct DevMem {
     void *p = nullptr;
     size_t cap = 0;
     ~DevMem() { release(); }
+    void check_guard() const {
+        if (!p || !guard_on()) return;
+        unsigned char tail[kGuardBytes];
+        if (cudaMemcpy(tail, static_cast<char *>(p) + cap, kGuardBytes, cudaMemcpyDeviceToHost) != cudaSuccess) return;
+        for (size_t i = 0; i < kGuardBytes; ++i)
+            if (tail[i] != 0xA5) {
+                fprintf(stderr, "[nrb200] GUARD: write past the end of a device buffer of %zu bytes (offset +%zu)\n", cap, i);
+                abort();
+            }
+    }
     void release() {
+        check_guard();
         if (p) cudaFree(p);
         p = nullptr;
         cap = 0;
@@ -51,8 +71,12 @@ struct DevMem {
     cudaError_t reserve(size_t bytes) {
         if (bytes <= cap) return cudaSuccess;
         release();
-        cudaError_t e = cudaMalloc(&p, bytes ? bytes : 1);
-        if (e == cudaSuccess) cap = bytes;
+        const size_t want = bytes ? bytes : 1;
+        cudaError_t e = cudaMalloc(&p, want + (guard_on() ? kGuardBytes : 0));
+        if (e == cudaSuccess) {
+            cap = want;
+            if (guard_on()) cudaMemset(static_cast<char *>(p) + cap, 0xA5, kGuardBytes);
+        }
         return e;
     }
     template <class T> T *as() const { return static_cast<T *>(p); }
