@@ -17,8 +17,10 @@
  * installed in the build image, and the reference's own tests (tests/testthat/test_boot.R,
  * test_trim_exclude.R) pin structural properties only, never a coordinate or a count.
  * What IS pinned: the R RNG stream (set.seed/runif/sample known answers from real R,
- * tests/test_oracle_rng.py), Philox4x32-10 (Random123 known answers), and the structural
- * properties of the reference tests (tests/test_oracle_reference_properties.py).
+ * tests/test_oracle_golden.py + tests/golden/), Philox4x32-10 (Random123 known answers), the worked
+ * examples of SURVEY 8c, the structural properties of the reference tests
+ * (tests/test_reference_properties.py), and an independent numpy brute force of the whole iteration
+ * (tests/test_oracle_bruteforce.py).
  *
  * Conventions: coordinates are R integers (int32), 1-based closed intervals.  chrom ids
  * are 0-based seqlevel indices.  strand codes: 0 '*', 1 '+', 2 '-'.
