@@ -190,8 +190,11 @@ def run_gpu(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; libnrb200 has no CPU path (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
-    if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
-        os.environ["NCCL_DEBUG"] = "WARN"  # keep stdout to the one JSON line
+    # Keep stdout to the one JSON line: libraries (NCCL with NCCL_DEBUG=VERSION set on the box, for one) write
+    # there on their own.  File descriptor 1 points at stderr until the line is ready.
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
@@ -384,7 +387,10 @@ def run_gpu(args):
                              "sample": f"{n_cpu} iterations of the same workload (same ranges/query/blockLength, Philox draws), oracle/nr_oracle.c on {cores} pthreads"},
             "clocks": clk,
         }
-        print(json.dumps(line))
+        sys.stdout.flush()
+        os.dup2(saved_stdout, 1)
+        print(json.dumps(line), flush=True)
+        os.dup2(2, 1)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
