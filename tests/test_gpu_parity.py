@@ -591,3 +591,27 @@ def test_many_sequences(engine, kind):
                          n_seg=600, n_states=3, wmax=150)
     _check_counts(engine, case, kind, R=3, seed=5, philox=False)
     _check_counts(engine, case, kind, R=3, seed=5, philox=True)
+
+
+def test_cfg4_full_size(engine):
+    """BASELINE configs[3] at full size: 10M width-1 points, withinChrom = TRUE, 200k enhancers, blockLength 5e5;
+    8 Philox iterations against the oracle (counts and per-feature moments), plus a shard taken elsewhere in the
+    iteration range (what a second GPU would compute)."""
+    if engine.force_stream:
+        pytest.skip("the streaming path at this size is covered by cfg 2 / cfg 3")
+    from nullranges_b200 import synth
+    y, x = synth.points(10_000_000, seed=6), synth.enhancers(200_000, seed=7)
+    case = _synth_case(y, x)
+    plan, yi, qi, _ = H.oracle_objects(case, 1)
+    assert H.load_engine(engine, case, 1) == plan.B
+    R = 8
+    ref = O.boot_counts(plan, yi, qi, R, seed=7, iter0=5000, nthreads=O.max_threads())
+    got = engine.run_counts(Draws(n_iter=R, rng_mode=_lib.RNG_PHILOX, seed=7, iter0=5000))
+    for k in ("iter_nranges", "iter_totals", "feature_counts"):
+        assert np.array_equal(got[k], ref[k]), k
+    obs, tot = engine.count_observed()
+    m = engine.run_moments(Draws(n_iter=R, seed=7, iter0=5000), observed=obs, batch_iter=3)
+    fc = ref["feature_counts"].astype(np.int64)
+    assert np.array_equal(m["sum"], fc.sum(0)) and np.array_equal(m["sumsq"], (fc * fc).sum(0))
+    assert np.array_equal(m["n_ge_observed"], (fc >= obs[None, :]).sum(0))
+    assert abs(got["iter_totals"].mean() / tot - 1.0) < 0.01
