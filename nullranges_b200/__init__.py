@@ -10,7 +10,7 @@ from .bootranges import BootCounts, bootCounts, bootRanges
 from .engine import Draws, Engine, EngineError, get_engine
 from .granges import BootRanges, GRanges
 from .rrng import RRng, set_seed
-from .segment import countOverlaps, segmentTileCounts, tileGenome
+from .segment import countOverlaps, oneRegionSegment, segmentTileCounts, tileGenome
 
 __all__ = ["GRanges", "BootRanges", "bootRanges", "bootCounts", "BootCounts", "set_seed", "RRng",
-           "Engine", "EngineError", "Draws", "get_engine", "countOverlaps", "segmentTileCounts", "tileGenome"]
+           "Engine", "EngineError", "Draws", "get_engine", "countOverlaps", "segmentTileCounts", "tileGenome", "oneRegionSegment"]

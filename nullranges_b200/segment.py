@@ -74,3 +74,15 @@ def segmentTileCounts(x: GRanges, L_s: int = 1_000_000, exclude: GRanges | None 
                         seqlengths={s: int(L) for s, L in zip(tiles.seqlevels, tiles.seqlengths)}, seqlevels=tiles.seqlevels)
     counts_nostand = countOverlaps(tiles, x, minoverlap=minoverlap, device=device)
     return tiles, counts_nostand, counts_nostand / tiles.width * L_s
+
+
+def oneRegionSegment(x: GRanges, seqlength: int) -> GRanges:
+    """nullranges::oneRegionSegment(x, seqlength) (R/bootHelper.R:24-40): a three-range segmentation around one
+    region -- state 1 before it, state 2 the region, state 1 after it -- for bootstrapping inside the region with
+    bootRanges(..., seg = , proportionLength = FALSE) (vignettes/bootRanges.Rmd:733-749)."""
+    if len(x) != 1:
+        raise ValueError("length(x) == 1 is not TRUE")
+    name = x.seqnames[0]
+    s, e = int(x.start[0]), int(x.end[0])
+    return GRanges([name] * 3, [1, s, e + 1], end=[s - 1, e, int(seqlength)], seqlengths={name: int(seqlength)},
+                   state=np.array([1, 2, 1]))

@@ -207,3 +207,123 @@ def test_product_row_order_follows_given_y(kind_args):
                                for r in range(3)])
         got = np.stack([br.seqid, br.start, br.end, idx], axis=1)
         assert np.array_equal(got, want)
+
+
+# ---- vignette fixtures: toy segmentation + uniform toy ranges, one-region case ----------
+
+TOY_SEG = {"chrom": np.array([0, 0, 0, 0, 1, 1, 1]), "start": np.array([1, 101, 201, 401, 1, 201, 301]),
+           "end": np.array([100, 200, 400, 500, 200, 300, 400]), "state": np.array([1, 2, 1, 3, 3, 2, 1])}   # Rmd:796-804
+TOY_LEN = [500, 400]
+
+
+def _toy_ranges():
+    """vignettes/bootRanges.Rmd:816-831 under set.seed(1), with R's own stream."""
+    g = O.RRng(1)
+    chrom = np.sort(g.sample(2, 200, replace=True) - 1)
+    start = np.rint(g.runif(200, 1, 500 - 10 + 1)).astype(np.int64)
+    end = start + 9
+    keep = ~((chrom == 1) & (end > 400))
+    chrom, start, end = chrom[keep], start[keep], end[keep]
+    o = np.lexsort((end, start, chrom))
+    chrom, start, end = chrom[o], start[o], end[o]
+    state = np.zeros(chrom.size, np.int64)     # findOverlaps(gr, seg, type = "within", select = "first")
+    for c, s, e, st in zip(TOY_SEG["chrom"], TOY_SEG["start"], TOY_SEG["end"], TOY_SEG["state"]):
+        inside = (chrom == c) & (start >= s) & (end <= e) & (state == 0)
+        state[inside] = st
+    m = state > 0
+    return chrom[m], start[m], end[m], state[m]
+
+
+def _same_state_rate(rows, src_state):
+    same = total = 0
+    for c, s, e, src in zip(rows["chrom"], rows["start"], rows["end"], rows["src"]):
+        for sc, ss, se, st in zip(TOY_SEG["chrom"], TOY_SEG["start"], TOY_SEG["end"], TOY_SEG["state"]):
+            if sc == c and ss <= e and se >= s:
+                total += 1
+                same += int(st == src_state[src])
+    return same / max(total, 1)
+
+
+@pytest.mark.parametrize("kind,L_b", [(O.SEG_NOPROP, 25), (O.SEG_PROP, 50)])      # Rmd:841-858
+def test_oracle_toy_segmentation(kind, L_b):
+    chrom, start, end, state = _toy_ranges()
+    assert 150 < chrom.size <= 200
+    plan = O.Plan(kind, TOY_LEN, L_b, TOY_SEG)
+    if kind == O.SEG_PROP:   # L_b_per_state = round(50 * c(400, 200, 300) / 900)
+        assert [plan.state_block_length(s) for s in (1, 2, 3)] == [22, 11, 17]
+    y = O.Index(2, chrom, start, end)
+    d = plan.draw_R(O.RRng(1), 1)
+    rows = O.iteration_rows(plan, y, d[0][0], d[1][0], d[2][0])
+    assert rows["src"].size > 100
+    assert np.all(rows["start"] >= 1) and np.all(rows["end"] <= np.array(TOY_LEN)[rows["chrom"]])
+    assert _same_state_rate(rows, state) > 0.6      # "some ranges from adjacent states are allowed to be placed within different states"
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("prop,L_b", [(False, 25), (True, 50)])
+def test_product_toy_segmentation(prop, L_b):
+    from nullranges_b200 import GRanges, bootRanges, set_seed
+    chrom, start, end, state = _toy_ranges()
+    names = np.array(["chr1", "chr2"])
+    sl = {"chr1": 500, "chr2": 400}
+    gr = GRanges(names[chrom], start, end=end, seqlengths=sl, state=state)
+    seg = GRanges(names[TOY_SEG["chrom"]], TOY_SEG["start"], end=TOY_SEG["end"], seqlengths=sl, state=TOY_SEG["state"])
+    set_seed(1)
+    br = bootRanges(gr, blockLength=L_b, seg=seg, proportionLength=prop)
+    plan = O.Plan(O.SEG_PROP if prop else O.SEG_NOPROP, TOY_LEN, L_b, TOY_SEG)
+    d = plan.draw_R(O.RRng(1), 1)
+    rows = O.iteration_rows(plan, O.Index(2, chrom, start, end), d[0][0], d[1][0], d[2][0])
+    assert np.array_equal(br.seqid, rows["chrom"]) and np.array_equal(br.start, rows["start"]) and np.array_equal(br.end, rows["end"])
+    assert np.array_equal(br.mcols["state"], state[rows["src"]])
+
+
+def _one_region_case():
+    """vignettes/bootRanges.Rmd:733-749 with synthetic peaks in place of the DHS data (not in the tree)."""
+    rng = np.random.default_rng(9)
+    start = np.sort(10_000_001 + rng.integers(0, 1_000_000 - 400, 800))
+    return start, start + rng.integers(150, 400, 800)
+
+
+def test_oracle_one_region_segment():
+    start, end = _one_region_case()
+    L = 248_956_422
+    seg = {"chrom": np.zeros(3, np.int64), "start": np.array([1, 10_000_001, 11_000_001]), "end": np.array([10_000_000, 11_000_000, L]),
+           "state": np.array([1, 2, 1])}
+    plan = O.Plan(O.SEG_NOPROP, [L], 100_000, seg)
+    assert plan.B == 100 + 10 + 2380
+    y = O.Index(1, np.zeros(800, np.int64), start, end)
+    for seed in range(1, 30):
+        try:
+            d = plan.draw_R(O.RRng(seed), 1)
+        except ValueError:
+            continue     # the region drew no block: the reference stops as well (R/bootRanges.R:303)
+        rows = O.iteration_rows(plan, y, d[0][0], d[1][0], d[2][0])
+        inside = (rows["end"] >= 10_000_001 - 100_000) & (rows["start"] <= 11_000_000 + 100_000)
+        assert rows["src"].size > 0 and inside.mean() > 0.8   # the data are bootstrapped "just in this region"
+        break
+    else:
+        pytest.fail("no seed produced a draw in the region")
+
+
+@pytest.mark.gpu
+def test_product_one_region_segment():
+    from nullranges_b200 import GRanges, bootCounts, bootRanges, oneRegionSegment, set_seed
+    start, end = _one_region_case()
+    L = 248_956_422
+    y = GRanges(["chr1"] * 800, start, end=end, seqlengths={"chr1": L})
+    region = GRanges(["chr1"], [10_000_001], width=[1_000_000], seqlengths={"chr1": L})
+    x = GRanges(["chr1"] * 10, 10_000_001 + np.arange(10) * 100_000, width=[10_000] * 10, seqlengths={"chr1": L})
+    seg = oneRegionSegment(region, seqlength=L)
+    assert seg.start.tolist() == [1, 10_000_001, 11_000_001] and seg.mcols["state"].tolist() == [1, 2, 1]
+    bc = bootCounts(y, x, 100_000, R=200, seg=seg, proportionLength=False, rng="philox", seed=3)
+    assert bc.feature_counts.shape == (200, 10)
+    obs = np.array([np.sum((y.start <= e) & (y.end >= s)) for s, e in zip(x.start, x.end)])
+    assert abs(bc.feature_counts.mean() / obs.mean() - 1.0) < 0.25     # the bootstrap keeps the region's density
+    for seed in range(1, 30):
+        set_seed(seed)
+        try:
+            boot = bootRanges(y, blockLength=100_000, R=1, seg=seg, proportionLength=False)
+        except ValueError:
+            continue
+        assert ((boot.end >= 9_900_001) & (boot.start <= 11_100_000)).mean() > 0.8
+        break
