@@ -76,6 +76,8 @@ int nrb200_set_ranges(nrb200_handle *h, int64_t n, int32_t n_seq, const int64_t 
     h->have_y = h->have_plan = false;
     h->query.n = h->excl.n = 0;  // seqlevels may have changed
     h->query_minoverlap = 0;
+    h->query_widen = 0;
+    h->have_weights = false;      // weights belong to the ranges they were set for
     h->n_seq = n_seq;
     h->seqlen.assign(seqlengths, seqlengths + n_seq);
     int rc;

@@ -615,3 +615,21 @@ def test_cfg4_full_size(engine):
     assert np.array_equal(m["sum"], fc.sum(0)) and np.array_equal(m["sumsq"], (fc * fc).sum(0))
     assert np.array_equal(m["n_ge_observed"], (fc >= obs[None, :]).sum(0))
     assert abs(got["iter_totals"].mean() / tot - 1.0) < 0.01
+
+
+def test_state_resets_with_new_ranges(engine):
+    """nrb200_set_ranges() starts a new problem: query, exclude set, query options and weights of the previous one are gone."""
+    from nullranges_b200 import EngineError
+    case = H.random_case(seed=11, n=200, n_query=20, n_excl=5)
+    H.load_engine(engine, case, 0)
+    engine.set_weights(np.ones(200))
+    engine.set_ranges(case["seqlen"], *H.random_case(seed=12, n=50)["y"])
+    engine.set_plan(_lib.UNSEG_ACROSS, case["L_b"])
+    with pytest.raises(EngineError, match="set_query"):
+        engine.count_observed()
+    engine.set_query(*case["query"])
+    if not engine.force_stream:
+        with pytest.raises(EngineError, match="set_weights"):
+            engine.run_weighted(Draws(n_iter=1, seed=1))
+    got = engine.run_counts(Draws(n_iter=2, seed=1))
+    assert got["iter_nranges"].sum() > 0
