@@ -66,6 +66,18 @@ int nrb200_set_ranges(nrb200_handle *h, int64_t n, int32_t n_seq, const int64_t 
                       const int32_t *seqid, const int32_t *start, const int32_t *end,
                       const int8_t *strand);
 
+/* The same in two halves, for callers with host-side work to do in between.  _begin checks seqlengths, then only
+ * QUEUES the upload of y, its inspection on the device and the copy of the verdict; _end waits for them, reports
+ * what nrb200_set_ranges() would have reported and queues the index build.  Between the two, only
+ * nrb200_set_query*(), nrb200_set_exclude*() and nrb200_set_plan() may be called (they need seqlengths, not y), and
+ * the arrays given to _begin must stay valid and unchanged until _end returns.  The front end uses this to prepare
+ * the query and the plan while y is on the wire (R/bootRanges.R:80-88 has no such ordering constraint: its checks
+ * are independent of each other). */
+int nrb200_set_ranges_begin(nrb200_handle *h, int64_t n, int32_t n_seq, const int64_t *seqlengths,
+                            const int32_t *seqid, const int32_t *start, const int32_t *end,
+                            const int8_t *strand);
+int nrb200_set_ranges_end(nrb200_handle *h);
+
 /* What set_ranges found: is_sorted = the caller's order was already (seqname, start, end) -- for
  * an unstranded y that is the all(y == sort(y)) check of R/bootUnsegmented.R:31, so the wrapper
  * need not sort again; is_stranded = some strand is '+' or '-'; max_width = widest range. */

@@ -50,6 +50,8 @@ SYMBOLS = [
     ("nrb200_last_error", C.c_char_p, [vp]),
     ("nrb200_version", C.c_char_p, []),
     ("nrb200_set_ranges", C.c_int, [vp, C.c_int64, C.c_int32, i64p, i32p, i32p, i32p, i8p]),
+    ("nrb200_set_ranges_begin", C.c_int, [vp, C.c_int64, C.c_int32, i64p, i32p, i32p, i32p, i8p]),
+    ("nrb200_set_ranges_end", C.c_int, [vp]),
     ("nrb200_ranges_info", C.c_int, [vp, i32p, i32p, i32p]),
     ("nrb200_set_query", C.c_int, [vp, C.c_int64, i32p, i32p, i32p, i8p]),
     ("nrb200_set_query_ex", C.c_int, [vp, C.c_int64, i32p, i32p, i32p, i8p, C.c_int32, C.c_int32]),

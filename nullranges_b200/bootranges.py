@@ -49,10 +49,17 @@ def _seg_arrays(seg: GRanges, y: GRanges):
 
 
 def _side_arrays(x: GRanges, y: GRanges, what: str):
+    """(seqid in y's seqlevels, start, end, strand or None when all '*', positions kept) of the ranges of x that lie
+    on sequences y has."""
+    strand = x.strand if np.any(x.strand) else None
+    if x.seqlevels == y.seqlevels:
+        return x.seqid, x.start, x.end, strand, None
     lut = {s: i for i, s in enumerate(y.seqlevels)}
     ids = np.array([lut.get(s, -1) for s in x.seqlevels], dtype=np.int32)[x.seqid]
     keep = ids >= 0  # ranges on sequences y does not have can never be hit
-    return ids[keep], x.start[keep], x.end[keep], x.strand[keep], np.flatnonzero(keep)
+    if keep.all():
+        return ids, x.start, x.end, strand, None
+    return ids[keep], x.start[keep], x.end[keep], None if strand is None else strand[keep], np.flatnonzero(keep)
 
 
 def _draw_host(kind, rng: RRng, R: int, y: GRanges, L_b: int, seg, eng: Engine):
@@ -79,7 +86,10 @@ def _draw_host(kind, rng: RRng, R: int, y: GRanges, L_b: int, seg, eng: Engine):
     return bait_seq, bait_start, dst
 
 
-def _setup(y: GRanges, blockLength, seg, exclude, excludeOption, proportionLength, type_, withinChrom, device):
+def _setup(y: GRanges, blockLength, seg, exclude, excludeOption, proportionLength, type_, withinChrom, device, query=None):
+    """Argument checks of R/bootRanges.R:80-88 and R/bootUnsegmented.R:8,31, inputs to the engine.  y goes first and
+    asynchronously (nrb200_set_ranges_begin): exclude, plan and query are prepared while it is on the wire.
+    query: (x, maxgap, minoverlap) of bootCounts(); returns (engine, kind, L_b, seg arrays, positions of x kept)."""
     chr_lens = y.seqlengths
     if np.any(chr_lens < 0):
         raise ValueError("all(!is.na(chr_lens)) is not TRUE")  # R/bootRanges.R:81
@@ -97,19 +107,27 @@ def _setup(y: GRanges, blockLength, seg, exclude, excludeOption, proportionLengt
     segd = _seg_arrays(seg, y) if seg is not None else None
     eng = get_engine(device)
     stranded = bool(np.any(y.strand))
-    eng.set_ranges(chr_lens, y.seqid, y.start, y.end, y.strand if stranded else None)
+    eng.set_ranges(chr_lens, y.seqid, y.start, y.end, y.strand if stranded else None, defer=True)
+    qkeep = None
+    try:
+        if exclude is not None:
+            xi, xs, xe, xstr, _ = _side_arrays(exclude, y, "exclude")
+            eng.set_exclude(xi, xs, xe, xstr, option=excludeOption)
+        else:
+            eng.clear_exclude()
+        eng.set_plan(kind, L_b, segd)
+        if query is not None:
+            x, maxgap, minoverlap = query
+            qi, qs, qe, qstr, qkeep = _side_arrays(x, y, "x")
+            eng.set_query(qi, qs, qe, qstr, maxgap=maxgap, minoverlap=minoverlap)
+    finally:
+        eng.finish_ranges()  # y's own problems are reported first, as nrb200_set_ranges() would
     if kind in (_lib.UNSEG_ACROSS, _lib.PERMUTE_ACROSS):
         # stopifnot(all(y == GenomicRanges::sort(y)))  R/bootUnsegmented.R:31.  For an unstranded y the
         # engine's canonical-order test (made on the GPU while loading) is that check.
         if not (eng.ranges_info()["sorted"] if not stranded else y.is_sorted()):
             raise ValueError("all(y == GenomicRanges::sort(y)) is not TRUE")
-    if exclude is not None:
-        xi, xs, xe, xstr, _ = _side_arrays(exclude, y, "exclude")
-        eng.set_exclude(xi, xs, xe, xstr if np.any(xstr) else None, option=excludeOption)
-    else:
-        eng.clear_exclude()
-    eng.set_plan(kind, L_b, segd)
-    return eng, kind, L_b, segd
+    return eng, kind, L_b, segd, qkeep
 
 
 def _make_draws(eng, kind, R, y, L_b, segd, rng, seed, iter0):
@@ -126,7 +144,7 @@ def bootRanges(y: GRanges, blockLength, R: int = 1, seg: GRanges | None = None, 
                withinChrom: bool = False, storeBlockLength: bool = False, *, rng="R", seed=None, iter0: int = 0,
                storeBlockStart: bool = False, device: int = 0) -> BootRanges:
     """Block bootstrap of genomic ranges; returns all iterations concatenated with an ``iter`` column."""
-    eng, kind, L_b, segd = _setup(y, blockLength, seg, exclude, excludeOption, proportionLength, type, withinChrom, device)
+    eng, kind, L_b, segd, _ = _setup(y, blockLength, seg, exclude, excludeOption, proportionLength, type, withinChrom, device)
     draws = _make_draws(eng, kind, int(R), y, L_b, segd, rng, seed, iter0)
     rows = eng.run_materialize(draws)
     lens = np.diff(rows["iter_offsets"])
@@ -176,17 +194,16 @@ def bootCounts(y: GRanges, x: GRanges, blockLength, R: int = 1, seg: GRanges | N
     """countOverlaps(x, bootRanges(y, ...), maxgap = , minoverlap = ) per iteration, fused on the GPU.
     weights: name of a numeric metadata column of y; adds its sum over the overlapping bootstrapped ranges per
     (iteration, feature) -- summarize(sum(signal)) of vignettes/bootRanges.Rmd:532-540."""
-    eng, kind, L_b, segd = _setup(y, blockLength, seg, exclude, excludeOption, proportionLength, type, withinChrom, device)
-    qi, qs, qe, qstr, qkeep = _side_arrays(x, y, "x")
-    eng.set_query(qi, qs, qe, qstr if np.any(qstr) else None, maxgap=maxgap, minoverlap=minoverlap)
+    eng, kind, L_b, segd, qkeep = _setup(y, blockLength, seg, exclude, excludeOption, proportionLength, type, withinChrom, device,
+                                         query=(x, maxgap, minoverlap))
     draws = _make_draws(eng, kind, int(R), y, L_b, segd, rng, seed, iter0)
-    if out is not None and qkeep.size != len(x):
+    if out is not None and qkeep is not None:
         raise ValueError("out= needs every seqlevel of x to be a seqlevel of y")
     res = eng.run_counts(draws, want_counts=perFeature, out=out)
     fc = res["feature_counts"]
     if fc is None and perFeature:  # no feature lies on a sequence of y
         fc = np.zeros((int(R), len(x)), np.int32)
-    elif fc is not None and qkeep.size != len(x):  # features on sequences y lacks count 0
+    elif fc is not None and qkeep is not None:  # features on sequences y lacks count 0
         full = np.zeros((int(R), len(x)), np.int32)
         full[:, qkeep] = fc
         fc = full
@@ -197,7 +214,7 @@ def bootCounts(y: GRanges, x: GRanges, blockLength, R: int = 1, seg: GRanges | N
         eng.set_weights(y.mcols[weights])
         ws = eng.run_weighted(draws, want_matrix=perFeature)
         fs = ws["feature_sums"]
-        if fs is not None and qkeep.size != len(x):
+        if fs is not None and qkeep is not None:
             full = np.zeros((int(R), len(x)), np.float64)
             full[:, qkeep] = fs
             fs = full

@@ -53,6 +53,7 @@ void nrb200_destroy(nrb200_handle *h) {
         if (ev) cudaEventDestroy(ev);
     if (h->stage_buf) cudaFreeHost(h->stage_buf);
     if (h->stage_in) cudaFreeHost(h->stage_in);
+    if (h->inspect_host) cudaFreeHost(h->inspect_host);
     for (auto &ev : h->batch_ev) cudaEventDestroy(ev);
     if (h->copy_stream) {
         cudaStreamSynchronize(h->copy_stream);
@@ -63,10 +64,11 @@ void nrb200_destroy(nrb200_handle *h) {
     delete h;
 }
 
-int nrb200_set_ranges(nrb200_handle *h, int64_t n, int32_t n_seq, const int64_t *seqlengths, const int32_t *seqid,
-                      const int32_t *start, const int32_t *end, const int8_t *strand) {
+int nrb200_set_ranges_begin(nrb200_handle *h, int64_t n, int32_t n_seq, const int64_t *seqlengths, const int32_t *seqid,
+                            const int32_t *start, const int32_t *end, const int8_t *strand) {
     if (!h) return NRB200_ERR_INVALID;
     NRB_CUDA(h, cudaSetDevice(h->device));
+    h->y_pending = false;
     if (n_seq <= 0 || !seqlengths) return fail(h, NRB200_ERR_INVALID, "seqlengths(y) must be known");
     for (int c = 0; c < n_seq; ++c) {
         // stopifnot(all(!is.na(chr_lens)))                          R/bootRanges.R:81
@@ -82,11 +84,23 @@ int nrb200_set_ranges(nrb200_handle *h, int64_t n, int32_t n_seq, const int64_t 
     h->seqlen.assign(seqlengths, seqlengths + n_seq);
     int rc;
     if ((rc = upload(h, h->seqlen_dev, seqlengths, (size_t)n_seq))) return rc;
-    Trace tr("set_ranges");
-    rc = load_y_device(h, n, seqid, start, end, strand);
+    if ((rc = load_y_begin(h, n, seqid, start, end, strand))) return rc;
+    h->y_pending = true;
+    return NRB200_OK;
+}
+
+int nrb200_set_ranges_end(nrb200_handle *h) {
+    if (!h) return NRB200_ERR_INVALID;
+    NRB_CUDA(h, cudaSetDevice(h->device));
+    if (!h->y_pending) return fail(h, NRB200_ERR_STATE, "nrb200_set_ranges_begin() has not been called");
+    h->y_pending = false;
+    Trace tr("set_ranges_end");
+    int rc = load_y_end(h);
     if (rc < 0) return rc;
-    tr.lap("load_y_device");
-    if (rc == 1 && (rc = load_range_set(h, h->y, "y", n, seqid, start, end, strand, true))) return rc;
+    tr.lap("load_y_end");
+    if (rc == 1 && (rc = load_range_set(h, h->y, "y", h->pend.n, h->pend.seqid, h->pend.start, h->pend.end, h->pend.strand, true)))
+        return rc;
+    h->pend = {};
     if ((rc = build_rank_tables(h))) return rc;
     tr.lap("build_rank_tables");
     // the large host mirror of y is not needed again
@@ -98,6 +112,12 @@ int nrb200_set_ranges(nrb200_handle *h, int64_t n, int32_t n_seq, const int64_t 
     h->have_y = true;
     h->slices_dirty = true;
     return NRB200_OK;
+}
+
+int nrb200_set_ranges(nrb200_handle *h, int64_t n, int32_t n_seq, const int64_t *seqlengths, const int32_t *seqid,
+                      const int32_t *start, const int32_t *end, const int8_t *strand) {
+    if (int rc = nrb200_set_ranges_begin(h, n, n_seq, seqlengths, seqid, start, end, strand)) return rc;
+    return nrb200_set_ranges_end(h);
 }
 
 int nrb200_ranges_info(const nrb200_handle *h, int32_t *is_sorted, int32_t *is_stranded, int32_t *max_width) {
@@ -112,7 +132,7 @@ static int set_side(nrb200_handle *h, RangeSet &rs, const char *what, int64_t n,
                     const int32_t *start, const int32_t *end, const int8_t *strand, int32_t widen = 0) {
     if (!h) return NRB200_ERR_INVALID;
     NRB_CUDA(h, cudaSetDevice(h->device));
-    if (!h->have_y) return fail(h, NRB200_ERR_STATE, "call nrb200_set_ranges() first (it defines the seqlevels)");
+    if (!h->have_y && !h->y_pending) return fail(h, NRB200_ERR_STATE, "call nrb200_set_ranges() first (it defines the seqlevels)");
     h->slices_dirty = true;
     if (n == 0) {
         rs.n = 0;
@@ -168,7 +188,7 @@ int nrb200_set_exclude_option(nrb200_handle *h, int32_t option) {
 int nrb200_set_plan(nrb200_handle *h, const nrb200_plan_spec *spec, int64_t *n_blocks) {
     if (!h || !spec) return NRB200_ERR_INVALID;
     NRB_CUDA(h, cudaSetDevice(h->device));
-    if (!h->have_y) return fail(h, NRB200_ERR_STATE, "call nrb200_set_ranges() first (the plan needs seqlengths)");
+    if (!h->have_y && !h->y_pending) return fail(h, NRB200_ERR_STATE, "call nrb200_set_ranges() first (the plan needs seqlengths)");
     Plan p;
     const std::string msg = build_plan(*spec, h->seqlen, p);
     if (!msg.empty()) return fail(h, NRB200_ERR_INVALID, msg);
@@ -196,6 +216,34 @@ int nrb200_set_plan(nrb200_handle *h, const nrb200_plan_spec *spec, int64_t *n_b
     h->sampler_view = SamplerView{pl.kind, pl.n_seq, pl.n_states, pl.block_length, pl.genome_length,
                                   b64 + o_cum, b64 + o_tps, b64 + o_sbo, b64 + o_sso, b64 + o_sl, b64 + o_sbl,
                                   b64 + o_sgc, b32 + o_sq, b32 + o_ss, b32 + o_st};
+    {   // tiles of each sequence by start, for the window lists (build_pairs)
+        auto &T = h->tiles_by_seq;
+        const int C = h->n_seq;
+        T.id.assign(C, {});
+        T.ts.assign(C, {});
+        T.te.assign(C, {});
+        T.te_max.assign(C, {});
+        for (int64_t t = 0; t < pl.n_blocks(); ++t) T.id[pl.tile_seq[t]].push_back((int32_t)t);
+        for (int c = 0; c < C; ++c) {
+            auto &v = T.id[c];
+            bool sorted = true;
+            for (size_t j = 1; j < v.size(); ++j) sorted &= pl.tile_start[v[j - 1]] <= pl.tile_start[v[j]];
+            if (!sorted)
+                std::sort(v.begin(), v.end(), [&](int32_t a, int32_t b) {
+                    return pl.tile_start[a] != pl.tile_start[b] ? pl.tile_start[a] < pl.tile_start[b] : a < b;
+                });
+            T.ts[c].resize(v.size());
+            T.te[c].resize(v.size());
+            T.te_max[c].resize(v.size());
+            int64_t m = INT64_MIN;
+            for (size_t j = 0; j < v.size(); ++j) {
+                T.ts[c][j] = pl.tile_start[v[j]];
+                T.te[c][j] = T.ts[c][j] + pl.bait_width[v[j]] - 1;
+                m = std::max(m, T.te[c][j]);
+                T.te_max[c][j] = m;
+            }
+        }
+    }
     h->have_plan = true;
     h->slices_dirty = true;
     if (n_blocks) *n_blocks = pl.n_blocks();

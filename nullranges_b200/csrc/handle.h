@@ -141,6 +141,16 @@ struct nrb200_handle {
     int rank_shift = 0;
     std::vector<int64_t> rank_off;
     DevMem inspect_dev, seq_info_dev, draw_tab;
+    // nrb200_set_ranges_begin() .. _end(): the upload and the inspection are queued, their verdict not yet read
+    bool y_pending = false;
+    struct {
+        int64_t n = 0;
+        const int32_t *seqid = nullptr, *start = nullptr, *end = nullptr;
+        const int8_t *strand = nullptr;
+        bool on_device = false;  // false: degenerate input, the host path takes it at _end()
+    } pend;
+    int32_t *inspect_host = nullptr;  // pinned landing place of the inspection verdict
+    size_t inspect_host_words = 0;
     DevMem raw_seqid, raw_start, raw_end, raw_strand;  // caller-order copies of an unsorted y while it is being sorted
     // stranded y only: class-major copy for the rank path (kernels.cuh, RangesView)
     int n_cls = 1, n_width = 1;
@@ -166,6 +176,12 @@ struct nrb200_handle {
     bool slices_dirty = true, have_pmax_table = false;
     DevMem q_tile_lo, q_tile_hi, x_tile_lo, x_tile_hi, pair_off, pair_rec, f_src, tile_x_off, tile_x_rec;
     int64_t n_pairs = 0;
+    // tiles of each sequence in ascending start order, with the running max of their ends (made by nrb200_set_plan
+    // for build_pairs)
+    struct TilesBySeq {
+        std::vector<std::vector<int32_t>> id;
+        std::vector<std::vector<int64_t>> ts, te, te_max;
+    } tiles_by_seq;
     bool tiles_in_bounds = false;
 
     // run scratch / results

@@ -94,27 +94,41 @@ int load_range_set(nrb200_handle *h, RangeSet &rs, const char *what, int64_t n, 
 // argument checks and finds out whether they are already in canonical order (the usual case:
 // the reference insists on sort(y) for the across-chromosome samplers, R/bootUnsegmented.R:31).
 // Unsorted input is sorted on the device (two stable radix sorts); only INVALID input falls back to the host
-// path above, which words the error.  Returns 1 for "fall back".
-int load_y_device(nrb200_handle *h, int64_t n, const int32_t *seqid, const int32_t *start, const int32_t *end,
-                  const int8_t *strand) {
+// path above, which words the error.  Two halves (nrb200_set_ranges_begin / _end): the first only queues the
+// copies, the inspection and the copy of its verdict into pinned memory, so the caller's host-side work on the
+// query, the exclude set and the plan runs while y is on the wire.
+int load_y_begin(nrb200_handle *h, int64_t n, const int32_t *seqid, const int32_t *start, const int32_t *end,
+                 const int8_t *strand) {
     RangeSet &y = h->y;
     const int C = h->n_seq;
-    if (n <= 0 || n > (int64_t)INT32_MAX - 64 || !seqid || !start || !end) return 1;  // host path words the errors
+    h->pend.n = n;
+    h->pend.seqid = seqid;
+    h->pend.start = start;
+    h->pend.end = end;
+    h->pend.strand = strand;
+    h->pend.on_device = false;
+    if (n <= 0 || n > (int64_t)INT32_MAX - 64 || !seqid || !start || !end) return NRB200_OK;  // host path words the errors
     int rc;
     if ((rc = upload_direct(h, y.seqid, seqid, (size_t)n, 0))) return rc;
     if ((rc = upload_direct(h, y.start, start, (size_t)n, 1))) return rc;
     if ((rc = upload_direct(h, y.end, end, (size_t)n, 2))) return rc;
     if (strand && (rc = upload_direct(h, y.strand, strand, (size_t)n, 3))) return rc;
-    Trace tr("load_y_device");
-    tr.lap("enqueue_h2d");
     // scratch: InspectOut (5 words, padded to 8) | seq_count[C] | seq_max_end[C]
     const size_t kHead = 8;
     const size_t words = kHead + 2 * (size_t)C;
     NRB_CUDA(h, h->inspect_dev.reserve(words * 4));
-    std::vector<int32_t> init(words, 0);
+    if (h->inspect_host_words < words) {
+        if (h->inspect_host) cudaFreeHost(h->inspect_host);
+        h->inspect_host = nullptr;
+        h->inspect_host_words = 0;
+        NRB_CUDA(h, cudaMallocHost((void **)&h->inspect_host, 2 * words * 4));  // verdict | initial values
+        h->inspect_host_words = words;
+    }
+    int32_t *init = h->inspect_host + words;
+    std::fill(init, init + words, 0);
     init[4] = INT32_MAX;  // wmin
     for (int c = 0; c < C; ++c) init[kHead + C + c] = INT32_MIN;
-    NRB_CUDA(h, cudaMemcpyAsync(h->inspect_dev.p, init.data(), words * 4, cudaMemcpyHostToDevice, h->stream));
+    NRB_CUDA(h, cudaMemcpyAsync(h->inspect_dev.p, init, words * 4, cudaMemcpyHostToDevice, h->stream));
     int32_t *base = h->inspect_dev.as<int32_t>();
     const unsigned grid = (unsigned)std::min<int64_t>((n + 255) / 256, (int64_t)h->sm_count * 8);
     inspect_ranges_kernel<<<grid, 256, 0, h->stream>>>(y.seqid.as<int32_t>(), y.start.as<int32_t>(), y.end.as<int32_t>(),
@@ -122,10 +136,24 @@ int load_y_device(nrb200_handle *h, int64_t n, const int32_t *seqid, const int32
                                                        reinterpret_cast<InspectOut *>(base), reinterpret_cast<unsigned *>(base + kHead),
                                                        base + kHead + C);
     NRB_CUDA(h, cudaGetLastError());
-    std::vector<int32_t> res(words);
-    NRB_CUDA(h, cudaMemcpyAsync(res.data(), base, words * 4, cudaMemcpyDeviceToHost, h->stream));
+    NRB_CUDA(h, cudaMemcpyAsync(h->inspect_host, base, words * 4, cudaMemcpyDeviceToHost, h->stream));
+    h->pend.on_device = true;
+    return NRB200_OK;
+}
+
+// Second half: waits for the verdict.  Returns 1 for "fall back to the host path".
+int load_y_end(nrb200_handle *h) {
+    if (!h->pend.on_device) return 1;
+    RangeSet &y = h->y;
+    const int C = h->n_seq;
+    const int64_t n = h->pend.n;
+    const int8_t *strand = h->pend.strand;
+    const size_t kHead = 8;
+    int rc;
+    Trace tr("load_y_end");
     if ((rc = sync_stream(h))) return rc;  // the caller's arrays are no longer read after this point
-    tr.lap("inspect+sync");
+    tr.lap("sync");
+    const int32_t *res = h->inspect_host;
     if (res[0] != 0) return 1;  // invalid: the host path names the problem
     y.n = n;
     y.sorted_input = res[1] == 0;

@@ -144,32 +144,11 @@ int build_pairs(nrb200_handle *h) {
     if (G == 0) return NRB200_OK;
 
     // ---- per feature.  Tiles of each sequence in ascending start order with the running max of
-    // their ends; features come in canonical (start-sorted) order, so the first tile that can still
-    // reach a feature only moves forward.  Two passes over the same enumeration: list lengths, then
-    // (after grouping features by length) the records, written straight into their final place.
-    std::vector<std::vector<int32_t>> by_seq(C);
-    for (int64_t t = 0; t < B; ++t) by_seq[p.tile_seq[t]].push_back((int32_t)t);
-    std::vector<std::vector<int64_t>> ts(C), te(C), te_max(C);
-    for (int c = 0; c < C; ++c) {
-        auto &v = by_seq[c];
-        bool sorted = true;
-        for (size_t j = 1; j < v.size(); ++j) sorted &= p.tile_start[v[j - 1]] <= p.tile_start[v[j]];
-        if (!sorted)
-            std::sort(v.begin(), v.end(), [&](int32_t a, int32_t b) {
-                return p.tile_start[a] != p.tile_start[b] ? p.tile_start[a] < p.tile_start[b] : a < b;
-            });
-        ts[c].resize(v.size());
-        te[c].resize(v.size());
-        te_max[c].resize(v.size());
-        int64_t m = INT64_MIN;
-        for (size_t j = 0; j < v.size(); ++j) {
-            ts[c][j] = p.tile_start[v[j]];
-            te[c][j] = ts[c][j] + p.bait_width[v[j]] - 1;
-            m = std::max(m, te[c][j]);
-            te_max[c][j] = m;
-        }
-    }
-    tr.lap("tiles_by_seq");
+    // their ends (tiles_by_seq, made with the plan); features come in canonical (start-sorted) order, so the
+    // first tile that can still reach a feature only moves forward.  Two passes over the same enumeration: list
+    // lengths, then the records, written straight into their final place.
+    const auto &by_seq = h->tiles_by_seq.id;
+    const auto &ts = h->tiles_by_seq.ts, &te = h->tiles_by_seq.te, &te_max = h->tiles_by_seq.te_max;
     // calls emit(tile, ws, we, sign) for every signed window of every feature, features in canonical order
     // (one sequence at a time: the sequences are independent, so the two passes run them in parallel)
     auto enumerate_seq = [&](int c, auto &&begin_feature, auto &&emit) {
@@ -223,31 +202,45 @@ int build_pairs(nrb200_handle *h) {
             }
         }
     };
-    std::vector<int32_t> len(G, 0);
-#pragma omp parallel for schedule(dynamic, 1) if (G >= 4096)
-    for (int c = 0; c < C; ++c) enumerate_seq(c, [](int32_t) {}, [&](int32_t k, int32_t, int64_t, int64_t, int, int) { ++len[k]; });
-    tr.lap("pass1");
-    // Visit order of the count kernel: features grouped by list length (stable counting sort, so
-    // neighbours in a group are neighbours on the genome): the lanes of a warp then loop equally often.
+    // Visit order of the count kernel: features grouped by list length (bins 0..62 hold exactly that length, the
+    // last bin everything longer), inside a bin in canonical order, so neighbours in a group are neighbours on the
+    // genome and the lanes of a warp loop equally often.  Sequences are enumerated in parallel: pass 1 also counts
+    // each sequence's features per bin, which fixes where every (bin, sequence) group starts -- both among the
+    // features and among the records (length x position inside a bin; a running sum in the last one).
     constexpr int kBins = 64;
-    int64_t bin_start[kBins + 1] = {0};
+    std::vector<int32_t> len(G, 0);
+    std::vector<int64_t> hist((size_t)C * kBins, 0), long_sum(C, 0);
     auto bin = [&](int64_t k) { return std::min<int>(len[k], kBins - 1); };
-    for (int64_t k = 0; k < G; ++k) bin_start[bin(k) + 1]++;
-    for (int b = 0; b < kBins; ++b) bin_start[b + 1] += bin_start[b];
-    std::vector<int32_t> pos_of(G), f_src(G), f_off(G + 1, 0);
-    for (int64_t k = 0; k < G; ++k) pos_of[k] = (int32_t)bin_start[bin(k)]++;
-    for (int64_t k = 0; k < G; ++k) {
-        f_src[pos_of[k]] = q.h_src[k];
-        f_off[pos_of[k] + 1] = len[k];
+#pragma omp parallel for schedule(dynamic, 1) if (G >= 4096)
+    for (int c = 0; c < C; ++c) {
+        enumerate_seq(c, [](int32_t) {}, [&](int32_t k, int32_t, int64_t, int64_t, int, int) { ++len[k]; });
+        for (int32_t k = q.h_seq_off[c]; k < q.h_seq_off[c + 1]; ++k) {
+            hist[(size_t)c * kBins + bin(k)]++;
+            if (len[k] >= kBins - 1) long_sum[c] += len[k];
+        }
     }
-    int64_t total = 0;
-    for (int64_t i = 0; i < G; ++i) {
-        total += f_off[i + 1];
-        if (total > (int64_t)INT32_MAX / 2) return fail(h, NRB200_ERR_UNSUPPORTED, "too many (feature, tile) pairs");
-        f_off[i + 1] = (int32_t)total;
+    tr.lap("pass1");
+    std::vector<int64_t> pos_start((size_t)C * kBins);  // first position of the (sequence, bin) group
+    int64_t bin_first[kBins], rec_first[kBins];
+    std::vector<int64_t> long_rec(C);  // first record of the sequence's features in the last bin
+    int64_t pos = 0, total = 0;
+    for (int b = 0; b < kBins; ++b) {
+        bin_first[b] = pos;
+        rec_first[b] = total;
+        for (int c = 0; c < C; ++c) {
+            pos_start[(size_t)c * kBins + b] = pos;
+            pos += hist[(size_t)c * kBins + b];
+            if (b == kBins - 1) {
+                long_rec[c] = total;
+                total += long_sum[c];
+            }
+        }
+        if (b < kBins - 1) total += (pos - bin_first[b]) * b;
     }
+    if (total > (int64_t)INT32_MAX / 2) return fail(h, NRB200_ERR_UNSUPPORTED, "too many (feature, tile) pairs");
     h->n_pairs = total;
-    tr.lap("binning");
+    std::vector<int32_t> f_src(G), f_off(G + 1);
+    f_off[G] = (int32_t)total;
     // records are written straight into pinned staging memory when they fit there
     std::vector<PairRec> f_recs_vec;
     PairRec *f_recs = static_cast<PairRec *>(arena_alloc(h, (size_t)std::max<int64_t>(total, 1) * sizeof(PairRec)));
@@ -258,8 +251,21 @@ int build_pairs(nrb200_handle *h) {
     }
 #pragma omp parallel for schedule(dynamic, 1) if (G >= 4096)
     for (int c = 0; c < C; ++c) {
-        int64_t cursor = 0;
-        enumerate_seq(c, [&](int32_t k) { cursor = f_off[pos_of[k]]; },
+        int64_t cursor = 0, long_cursor = long_rec[c];
+        int64_t *next_pos = &pos_start[(size_t)c * kBins];
+        enumerate_seq(c,
+                      [&](int32_t k) {
+                          const int b = bin(k);
+                          const int64_t at = next_pos[b]++;
+                          if (b < kBins - 1) {
+                              cursor = rec_first[b] + (at - bin_first[b]) * b;
+                          } else {
+                              cursor = long_cursor;
+                              long_cursor += len[k];
+                          }
+                          f_src[at] = q.h_src[k];
+                          f_off[at] = (int32_t)cursor;
+                      },
                       [&](int32_t, int32_t t, int64_t ws, int64_t we, int sign, int cls) {
                           f_recs[cursor++] = PairRec{t, (int32_t)ws, (int32_t)std::min<int64_t>(we, INT32_MAX / 2), sign, p.tile_start[t],
                                                      p.bait_width[t], (int32_t)h->seqlen[p.tile_seq[t]], cls};

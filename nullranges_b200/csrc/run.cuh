@@ -10,7 +10,7 @@ bool rank_path_ok(const nrb200_handle *h) {
 }
 
 int prepare(nrb200_handle *h) {
-    if (!h->have_y) return fail(h, NRB200_ERR_STATE, "nrb200_set_ranges() has not been called");
+    if (!h->have_y) return fail(h, NRB200_ERR_STATE, h->y_pending ? "nrb200_set_ranges_end() has not been called" : "nrb200_set_ranges() has not been called");
     if (!h->have_plan) return fail(h, NRB200_ERR_STATE, "nrb200_set_plan() has not been called");
     if (h->slices_dirty) {
         int rc;

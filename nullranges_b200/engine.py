@@ -68,14 +68,26 @@ class Engine:
             raise EngineError(rc, self._lib.nrb200_last_error(self._h).decode())
 
     # ---- inputs
-    def set_ranges(self, seqlengths, seqid, start, end, strand=None):
+    def set_ranges(self, seqlengths, seqid, start, end, strand=None, defer: bool = False):
+        """defer=True: nrb200_set_ranges_begin() only -- the upload and the checks are queued; set_query / set_exclude /
+        set_plan may follow, then finish_ranges() (which reports what set_ranges would have reported)."""
         sl = np.ascontiguousarray(seqlengths, dtype=np.int64)
         a, b, c, d = _i32(seqid), _i32(start), _i32(end), _i8(strand)
-        self._check(self._lib.nrb200_set_ranges(self._h, a.size, sl.size, ptr(sl, C.c_int64), ptr(a, C.c_int32),
-                                                ptr(b, C.c_int32), ptr(c, C.c_int32), ptr(d, C.c_int8)))
+        self._pending = None
+        fn = self._lib.nrb200_set_ranges_begin if defer else self._lib.nrb200_set_ranges
+        self._check(fn(self._h, a.size, sl.size, ptr(sl, C.c_int64), ptr(a, C.c_int32), ptr(b, C.c_int32), ptr(c, C.c_int32),
+                       ptr(d, C.c_int8)))
+        if defer:
+            self._pending = (sl, a, b, c, d)  # the arrays stay alive (and must stay unchanged) until finish_ranges()
         self.n_seq = sl.size
         self.n_query = 0
         self.n_blocks = 0
+
+    def finish_ranges(self):
+        try:
+            self._check(self._lib.nrb200_set_ranges_end(self._h))
+        finally:
+            self._pending = None
 
     def ranges_info(self) -> dict:
         a, b, c = C.c_int32(), C.c_int32(), C.c_int32()

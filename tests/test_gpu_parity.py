@@ -633,3 +633,32 @@ def test_state_resets_with_new_ranges(engine):
             engine.run_weighted(Draws(n_iter=1, seed=1))
     got = engine.run_counts(Draws(n_iter=2, seed=1))
     assert got["iter_nranges"].sum() > 0
+
+
+def test_set_ranges_in_two_halves(engine):
+    """nrb200_set_ranges_begin / _end: query, exclude and plan may be set in between; results equal the one-call form;
+    y's errors surface at _end; running before _end is a state error."""
+    from nullranges_b200 import EngineError
+    case = H.random_case(seed=21, n=3000, n_query=200, n_excl=20)
+    H.load_engine(engine, case, 0)
+    want = engine.run_counts(Draws(n_iter=5, seed=3))
+    sid, st, en, sd = case["y"]
+    engine.set_ranges(case["seqlen"], sid, st, en, sd, defer=True)
+    engine.set_exclude(*case["excl"])
+    engine.set_plan(_lib.UNSEG_ACROSS, case["L_b"])
+    engine.set_query(*case["query"])
+    with pytest.raises(EngineError, match="set_ranges_end"):
+        engine.run_counts(Draws(n_iter=1, seed=3))
+    engine.finish_ranges()
+    got = engine.run_counts(Draws(n_iter=5, seed=3))
+    for k in ("iter_totals", "iter_nranges", "feature_counts"):
+        np.testing.assert_array_equal(got[k], want[k])
+    with pytest.raises(EngineError, match="set_ranges_begin"):
+        engine.finish_ranges()
+    bad = st.copy()
+    bad[7] = 0
+    engine.set_ranges(case["seqlen"], sid, bad, en, sd, defer=True)
+    with pytest.raises(EngineError, match="start at position >= 1"):
+        engine.finish_ranges()
+    with pytest.raises(EngineError):
+        engine.set_plan(_lib.UNSEG_ACROSS, case["L_b"])  # no ranges: a failed _end leaves the handle without y
