@@ -23,6 +23,7 @@ int nrb200_create(const nrb200_config *cfg, nrb200_handle **out) {
     if (const char *e = getenv("NRB200_MINB")) h->tune_minb = atoi(e);
     if (const char *e = getenv("NRB200_TABLE_MULT")) h->tune_table_mult = atof(e);
     if (const char *e = getenv("NRB200_TABLE_CAP")) h->tune_table_cap = atoll(e);
+    if (const char *e = getenv("NRB200_CHUNKS")) h->tune_chunks = std::min(std::max(atoi(e), 1), 64);
     if (const char *e = getenv("NRB200_MAX_BATCH")) h->tune_max_batch = std::min<int64_t>(std::max<int64_t>(atoll(e), 8), 2048);
     if (h->tune_rpt != 1 && h->tune_rpt != 2 && h->tune_rpt != 4 && h->tune_rpt != 8) h->tune_rpt = 1;
     if (cfg && cfg->stream) {
@@ -95,13 +96,16 @@ int nrb200_set_ranges_end(nrb200_handle *h) {
     if (!h->y_pending) return fail(h, NRB200_ERR_STATE, "nrb200_set_ranges_begin() has not been called");
     h->y_pending = false;
     Trace tr("set_ranges_end");
+    h->slices_dirty = true;
     int rc = load_y_end(h);
     if (rc < 0) return rc;
     tr.lap("load_y_end");
     if (rc == 1 && (rc = load_range_set(h, h->y, "y", h->pend.n, h->pend.seqid, h->pend.start, h->pend.end, h->pend.strand, true)))
         return rc;
     h->pend = {};
+    h->timeline.mark("verdict read", h->stream);
     if ((rc = build_rank_tables(h))) return rc;
+    h->timeline.mark("index built", h->stream);
     tr.lap("build_rank_tables");
     // the large host mirror of y is not needed again
     std::vector<int32_t>().swap(h->y.h_start);
@@ -286,6 +290,8 @@ int nrb200_run_counts(nrb200_handle *h, const nrb200_draws *draws, int64_t *iter
     if ((rc = fetch_u64_as_i64(h, h->d_iter_totals, R, iter_totals))) return rc;
     if (int rc_sync = sync_stream(h)) return rc_sync;
     if (h->copy_stream) NRB_CUDA(h, cudaStreamSynchronize(h->copy_stream));
+    h->timeline.mark("run_counts returns", h->stream);
+    h->timeline.dump();
     if (stats) stats->d2h_bytes = (iter_nranges ? R * 8 : 0) + (iter_totals ? R * 8 : 0) + (feature_counts ? R * G * 4 : 0);
     return NRB200_OK;
 }

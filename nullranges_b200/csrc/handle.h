@@ -36,6 +36,47 @@ struct Trace {
     }
 };
 
+// NRB200_TRACE_DEV=1: device-side timeline (development aid).  mark() records a timing event on a stream together
+// with the host clock; dump() prints, for every mark, when the host queued it and when the device reached it, both
+// relative to the first mark.
+struct DevTimeline {
+    static bool on() {
+        static const bool v = getenv("NRB200_TRACE_DEV") != nullptr;
+        return v;
+    }
+    struct Mark {
+        const char *what;
+        cudaEvent_t ev;
+        std::chrono::steady_clock::time_point host;
+    };
+    std::vector<Mark> marks;
+    std::vector<cudaEvent_t> pool;
+    void mark(const char *what, cudaStream_t s) {
+        if (!on()) return;
+        cudaEvent_t e = nullptr;
+        if (!pool.empty()) {
+            e = pool.back();
+            pool.pop_back();
+        } else if (cudaEventCreate(&e) != cudaSuccess) {
+            return;
+        }
+        cudaEventRecord(e, s);
+        marks.push_back({what, e, std::chrono::steady_clock::now()});
+    }
+    void dump() {
+        if (!on() || marks.empty()) return;
+        for (auto &m : marks) cudaEventSynchronize(m.ev);
+        for (auto &m : marks) {
+            float ms = 0;
+            cudaEventElapsedTime(&ms, marks[0].ev, m.ev);
+            fprintf(stderr, "[nrb200-dev] %-28s queued %7.3f ms   reached %7.3f ms\n", m.what,
+                    std::chrono::duration<double, std::milli>(m.host - marks[0].host).count(), ms);
+            pool.push_back(m.ev);
+        }
+        marks.clear();
+    }
+};
+
 static thread_local std::string g_create_error;
 
 // Growth-only device buffer.
@@ -120,8 +161,8 @@ struct nrb200_handle {
     size_t arena_cap = 0, arena_used = 0;
     cudaEvent_t split_ev = nullptr;       // set while a stats run wants the rows / count kernel split
     std::vector<cudaEvent_t> batch_ev;    // 3 per batch: start, rows done, count done
-    cudaEvent_t chunk_ev[16] = {};
-    cudaEvent_t copied_ev[16] = {};   // pageable destinations: chunk k has reached the pinned staging buffer
+    cudaEvent_t chunk_ev[64] = {};
+    cudaEvent_t copied_ev[64] = {};   // pageable destinations: chunk k has reached the pinned staging buffer
     void *stage_buf = nullptr;        // that buffer (pinned, grown on demand)
     size_t stage_cap = 0;
     void *stage_in = nullptr;         // pinned staging for large pageable INPUT columns (4 regions)
@@ -141,6 +182,7 @@ struct nrb200_handle {
     int rank_shift = 0;
     std::vector<int64_t> rank_off;
     DevMem inspect_dev, seq_info_dev, draw_tab;
+    DevTimeline timeline;
     // nrb200_set_ranges_begin() .. _end(): the upload and the inspection are queued, their verdict not yet read
     bool y_pending = false;
     struct {
@@ -149,7 +191,7 @@ struct nrb200_handle {
         const int8_t *strand = nullptr;
         bool on_device = false;  // false: degenerate input, the host path takes it at _end()
     } pend;
-    int32_t *inspect_host = nullptr;  // pinned landing place of the inspection verdict
+    int32_t *inspect_host = nullptr;  // pinned landing place of the inspection verdict (+ the initial values)
     size_t inspect_host_words = 0;
     DevMem raw_seqid, raw_start, raw_end, raw_strand;  // caller-order copies of an unsorted y while it is being sorted
     // stranded y only: class-major copy for the rank path (kernels.cuh, RangesView)
@@ -167,6 +209,7 @@ struct nrb200_handle {
     // kernel, NRB200_MINB its min CTAs/SM, NRB200_TABLE_MULT rank-table entries per range
     int tune_rpt = 1, tune_minb = 1;
     double tune_table_mult = 4.0;
+    int tune_chunks = 8;               // NRB200_CHUNKS: pipeline depth of nrb200_run_counts
     int64_t tune_max_batch = 2048;     // NRB200_MAX_BATCH: iterations per launch group
     int64_t tune_table_cap = 8 << 20;  // NRB200_TABLE_CAP: the multiplier applies up to this many entries
 

@@ -109,10 +109,6 @@ int load_y_begin(nrb200_handle *h, int64_t n, const int32_t *seqid, const int32_
     h->pend.on_device = false;
     if (n <= 0 || n > (int64_t)INT32_MAX - 64 || !seqid || !start || !end) return NRB200_OK;  // host path words the errors
     int rc;
-    if ((rc = upload_direct(h, y.seqid, seqid, (size_t)n, 0))) return rc;
-    if ((rc = upload_direct(h, y.start, start, (size_t)n, 1))) return rc;
-    if ((rc = upload_direct(h, y.end, end, (size_t)n, 2))) return rc;
-    if (strand && (rc = upload_direct(h, y.strand, strand, (size_t)n, 3))) return rc;
     // scratch: InspectOut (5 words, padded to 8) | seq_count[C] | seq_max_end[C]
     const size_t kHead = 8;
     const size_t words = kHead + 2 * (size_t)C;
@@ -124,6 +120,7 @@ int load_y_begin(nrb200_handle *h, int64_t n, const int32_t *seqid, const int32_
         NRB_CUDA(h, cudaMallocHost((void **)&h->inspect_host, 2 * words * 4));  // verdict | initial values
         h->inspect_host_words = words;
     }
+    h->timeline.mark("begin", h->stream);
     int32_t *init = h->inspect_host + words;
     std::fill(init, init + words, 0);
     init[4] = INT32_MAX;  // wmin
@@ -131,12 +128,17 @@ int load_y_begin(nrb200_handle *h, int64_t n, const int32_t *seqid, const int32_
     NRB_CUDA(h, cudaMemcpyAsync(h->inspect_dev.p, init, words * 4, cudaMemcpyHostToDevice, h->stream));
     int32_t *base = h->inspect_dev.as<int32_t>();
     const unsigned grid = (unsigned)std::min<int64_t>((n + 255) / 256, (int64_t)h->sm_count * 8);
+    if ((rc = upload_direct(h, y.start, start, (size_t)n, 1))) return rc;
+    if ((rc = upload_direct(h, y.end, end, (size_t)n, 2))) return rc;
+    if ((rc = upload_direct(h, y.seqid, seqid, (size_t)n, 0))) return rc;
+    if (strand && (rc = upload_direct(h, y.strand, strand, (size_t)n, 3))) return rc;
     inspect_ranges_kernel<<<grid, 256, 0, h->stream>>>(y.seqid.as<int32_t>(), y.start.as<int32_t>(), y.end.as<int32_t>(),
                                                        strand ? y.strand.as<int8_t>() : nullptr, n, C,
                                                        reinterpret_cast<InspectOut *>(base), reinterpret_cast<unsigned *>(base + kHead),
                                                        base + kHead + C);
     NRB_CUDA(h, cudaGetLastError());
     NRB_CUDA(h, cudaMemcpyAsync(h->inspect_host, base, words * 4, cudaMemcpyDeviceToHost, h->stream));
+    h->timeline.mark("verdict copied", h->stream);
     h->pend.on_device = true;
     return NRB200_OK;
 }
@@ -261,7 +263,7 @@ int build_rank_tables(nrb200_handle *h) {
     NRB_CUDA(h, h->end_sorted.reserve(std::max<int64_t>(y.n, 1) * sizeof(int32_t)));
     const int threads = 256;
     const unsigned n_grid = (unsigned)((std::max<int64_t>(y.n, 1) + threads - 1) / threads);
-    const unsigned t_grid = (unsigned)((entries + threads - 1) / threads);
+    const unsigned t_grid = rank_table_grid(entries);
     // canonical start table: locate_block() of the streaming kernels, and the rank path of an unstranded y
     build_rank_table_kernel<<<t_grid, threads, 0, h->stream>>>(y.start.as<int32_t>(), y.seq_off.as<int32_t>(),
                                                                h->rank_off_dev.as<int64_t>(), C, shift, h->rank_start.as<uint32_t>());
@@ -340,7 +342,7 @@ int build_rank_tables(nrb200_handle *h) {
     vseq_info_kernel<<<(unsigned)((V + 1 + threads - 1) / threads), threads, 0, h->stream>>>(
         h->r_keys_b.as<unsigned>(), y.n, V, h->n_cls, h->max_pos_dev.as<int32_t>(), h->rrank_off_dev.as<int64_t>(), h->r_voff_dev.as<int32_t>(),
         h->rseq_info_dev.as<int4>());
-    const unsigned rt_grid = (unsigned)((r_entries + threads - 1) / threads);
+    const unsigned rt_grid = rank_table_grid(r_entries);
     build_rank_table_kernel<<<rt_grid, threads, 0, h->stream>>>(h->r_start.as<int32_t>(), h->r_voff_dev.as<int32_t>(),
                                                                 h->rrank_off_dev.as<int64_t>(), V, shift, h->rrank_start.as<uint32_t>());
     if (!h->ends_alias_starts)
@@ -355,7 +357,7 @@ int build_rank_tables(nrb200_handle *h) {
 int ensure_pmax_table(nrb200_handle *h) {
     if (h->have_pmax_table) return NRB200_OK;
     const int64_t entries = h->rank_off[h->n_seq];
-    build_rank_table_kernel<<<(unsigned)((entries + 255) / 256), 256, 0, h->stream>>>(
+    build_rank_table_kernel<<<rank_table_grid(entries), 256, 0, h->stream>>>(
         h->y.pmax.as<int32_t>(), h->y.seq_off.as<int32_t>(), h->rank_off_dev.as<int64_t>(), h->n_seq, h->rank_shift,
         h->rank_pmax.as<uint32_t>());
     NRB_CUDA(h, cudaGetLastError());

@@ -17,15 +17,32 @@ struct InspectOut {
     int32_t wmin;      // narrowest range (initialise to INT32_MAX)
 };
 
+constexpr int kInspectSeqs = 1024;  // per-sequence tallies are kept in shared memory up to this many sequences
+
+// Every CTA takes one contiguous piece of y (a sorted y then touches one or two sequences per CTA) and tallies the
+// per-sequence counts / largest ends in shared memory; global atomics only when the CTA is done.
 __global__ void __launch_bounds__(256) inspect_ranges_kernel(const int32_t *__restrict__ seqid, const int32_t *__restrict__ start,
                                                              const int32_t *__restrict__ end, const int8_t *__restrict__ strand,
                                                              int64_t n, int n_seq, InspectOut *__restrict__ out,
                                                              unsigned *__restrict__ seq_count, int32_t *__restrict__ seq_max_end) {
-    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    __shared__ unsigned s_count[kInspectSeqs];
+    __shared__ int32_t s_max[kInspectSeqs];
+    const bool local = n_seq <= kInspectSeqs;
+    if (local) {
+        for (int c = threadIdx.x; c < n_seq; c += blockDim.x) {
+            s_count[c] = 0;
+            s_max[c] = INT32_MIN;
+        }
+        __syncthreads();
+    }
+    unsigned *cnt = local ? s_count : seq_count;
+    int32_t *mx = local ? s_max : seq_max_end;
+    const int64_t piece = (n + gridDim.x - 1) / gridDim.x;
+    const int64_t lo = (int64_t)blockIdx.x * piece, hi = min(n, lo + piece);
     int err = 0, unsorted = 0, stranded = 0, wmax = 0, wmin = INT32_MAX;
-    for (int64_t base = (int64_t)blockIdx.x * blockDim.x; base < n; base += stride) {  // warp-uniform trip count
+    for (int64_t base = lo; base < hi; base += blockDim.x) {  // CTA-uniform trip count
         const int64_t i = base + threadIdx.x;
-        const bool live = i < n;
+        const bool live = i < hi;
         int c = -1;
         int32_t e = 0;
         if (live) {
@@ -53,8 +70,8 @@ __global__ void __launch_bounds__(256) inspect_ranges_kernel(const int32_t *__re
             const unsigned peers = __match_any_sync(active, c);
             const int32_t m = __reduce_max_sync(peers, e);
             if ((threadIdx.x & 31) == __ffs(peers) - 1) {
-                atomicAdd(seq_count + c, (unsigned)__popc(peers));
-                atomicMax(seq_max_end + c, m);
+                atomicAdd(cnt + c, (unsigned)__popc(peers));
+                atomicMax(mx + c, m);
             }
         }
     }
@@ -69,6 +86,14 @@ __global__ void __launch_bounds__(256) inspect_ranges_kernel(const int32_t *__re
         if (unsorted) atomicOr(&out->unsorted, 1);
         if (stranded) atomicOr(&out->stranded, 1);
         atomicMax(&out->wmax, wmax);
+    }
+    if (local) {
+        __syncthreads();
+        for (int c = threadIdx.x; c < n_seq; c += blockDim.x)
+            if (s_count[c]) {
+                atomicAdd(seq_count + c, s_count[c]);
+                atomicMax(seq_max_end + c, s_max[c]);
+            }
     }
 }
 
@@ -267,24 +292,60 @@ __global__ void gather_i8_kernel(const int32_t *__restrict__ src, const int8_t *
     if (i < n) out[i] = in[src[i]];
 }
 
-// entry t of a packed rank table (see "direct-address rank tables")
-__global__ void build_rank_table_kernel(const int32_t *__restrict__ values, const int32_t *__restrict__ seq_off,
-                                        const int64_t *__restrict__ rank_off, int n_seq, int shift,
-                                        uint32_t *__restrict__ table) {
-    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= rank_off[n_seq]) return;
-    int c = 0, hi = n_seq;  // sequence that owns entry t
-    while (hi - c > 1) {
-        const int m = (c + hi) >> 1;
-        if (rank_off[m] <= t) c = m; else hi = m;
+// Packed rank table (see "direct-address rank tables").  A thread fills kTableRun consecutive entries: one binary
+// search for the first, then it walks the values forward bucket by bucket (an entry's end is the next entry's
+// start); the CTA's entries go out through shared memory so that the stores are contiguous.
+constexpr int kTableRun = 8;
+__global__ void __launch_bounds__(256) build_rank_table_kernel(const int32_t *__restrict__ values, const int32_t *__restrict__ seq_off,
+                                                               const int64_t *__restrict__ rank_off, int n_seq, int shift,
+                                                               uint32_t *__restrict__ table) {
+    __shared__ uint32_t buf[256 * kTableRun + 256 / 4];  // skewed: one pad word per four threads' runs
+    const int64_t total = rank_off[n_seq];
+    const int64_t cta_first = (int64_t)blockIdx.x * (256 * kTableRun);
+    const int64_t t0 = cta_first + (int64_t)threadIdx.x * kTableRun;
+    if (t0 < total) {
+        int c = 0, hi = n_seq;  // sequence that owns entry t0
+        while (hi - c > 1) {
+            const int m = (c + hi) >> 1;
+            if (rank_off[m] <= t0) c = m; else hi = m;
+        }
+        int64_t seq_last = rank_off[c + 1];
+        int32_t a = seq_off[c], b = seq_off[c + 1];
+        int64_t bucket = t0 - rank_off[c];
+        int32_t p = (bucket << shift) > INT32_MAX ? b : first_ge(values, a, b, (int32_t)(bucket << shift));
+        const int out0 = threadIdx.x * kTableRun + threadIdx.x / 4;
+        for (int j = 0; j < kTableRun && t0 + j < total; ++j, ++bucket) {
+            if (t0 + j >= seq_last) {  // the run crosses into the next sequence (every sequence has entries)
+                ++c;
+                seq_last = rank_off[c + 1];
+                a = seq_off[c];
+                b = seq_off[c + 1];
+                bucket = 0;
+                p = a;
+            }
+            const int64_t next = (bucket + 1) << shift;
+            int32_t q = p;
+            if (next > INT32_MAX) {
+                q = b;
+            } else {
+                int steps = 0;
+                while (q < b && __ldg(values + q) < (int32_t)next) {
+                    ++q;
+                    if (++steps == 16) {  // a crowded bucket: finish with a binary search
+                        q = first_ge(values, q, b, (int32_t)next);
+                        break;
+                    }
+                }
+            }
+            buf[out0 + j] = ((uint32_t)(p - a) << kRankCountBits) | (uint32_t)min(q - p, kRankCountCap);
+            p = q;
+        }
     }
-    const int64_t bucket = t - rank_off[c];
-    const int64_t key = bucket << shift, next = (bucket + 1) << shift;
-    const int32_t a = seq_off[c], b = seq_off[c + 1];
-    const int32_t first = key > INT32_MAX ? b : first_ge(values, a, b, (int32_t)key);
-    const int32_t last = next > INT32_MAX ? b : first_ge(values, first, b, (int32_t)next);
-    table[t] = ((uint32_t)(first - a) << kRankCountBits) | (uint32_t)min(last - first, kRankCountCap);
+    __syncthreads();
+    for (int i = threadIdx.x; i < 256 * kTableRun; i += 256)
+        if (cta_first + i < total) table[cta_first + i] = buf[i + (i / kTableRun) / 4];
 }
+inline unsigned rank_table_grid(int64_t entries) { return (unsigned)((entries + 256 * kTableRun - 1) / (256 * kTableRun)); }
 
 // countOverlaps(query, y) on the original ranges: one thread per y range.
 template <bool STRANDED>

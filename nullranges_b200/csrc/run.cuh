@@ -9,32 +9,40 @@ bool rank_path_ok(const nrb200_handle *h) {
     return h->tiles_in_bounds;
 }
 
+// Everything a run needs that hangs on the plan, the query, the exclude set and -- of y -- only its widest range and
+// its classes: the window lists of the rank path, the per-tile slices of the streaming kernels.
+int prepare_lists(nrb200_handle *h) {
+    int rc;
+    Trace tr("prepare");
+    h->tiles_in_bounds = true;
+    for (int64_t t = 0; t < h->plan.n_blocks(); ++t)
+        if (h->plan.tile_start[t] > h->seqlen[h->plan.tile_seq[t]]) h->tiles_in_bounds = false;
+    if (trim_mode(h) && h->excl.stranded) return fail(h, NRB200_ERR_INVALID, "all(strand(exclude) == \"*\") is not TRUE");
+    if (trim_mode(h) && (rc = build_gaps(h))) return rc;
+    const bool rank = rank_path_ok(h);
+    if (rank) {
+        if ((rc = build_pairs(h))) return rc;  // window lists of the features and of the tiles
+        tr.lap("build_pairs");
+    }
+    // the streaming kernels (count without the rank path, and the fill pass) test exclusion per range
+    if (h->excl.n && (rc = build_slices(h, active_excl(h), h->x_tile_lo, h->x_tile_hi))) return rc;
+    if (!rank) {
+        if (h->query.n && (rc = range_set_to_device(h, h->query))) return rc;
+        if (h->query.n && (rc = build_slices(h, h->query, h->q_tile_lo, h->q_tile_hi))) return rc;
+    }
+    return NRB200_OK;
+}
+
 int prepare(nrb200_handle *h) {
     if (!h->have_y) return fail(h, NRB200_ERR_STATE, h->y_pending ? "nrb200_set_ranges_end() has not been called" : "nrb200_set_ranges() has not been called");
     if (!h->have_plan) return fail(h, NRB200_ERR_STATE, "nrb200_set_plan() has not been called");
     if (h->slices_dirty) {
         int rc;
-        Trace tr("prepare");
-        h->tiles_in_bounds = true;
-        for (int64_t t = 0; t < h->plan.n_blocks(); ++t)
-            if (h->plan.tile_start[t] > h->seqlen[h->plan.tile_seq[t]]) h->tiles_in_bounds = false;
         if (h->index_minoverlap != h->query_minoverlap && (rc = build_rank_tables(h))) return rc;  // the width classes changed
-        if (trim_mode(h) && h->excl.stranded) return fail(h, NRB200_ERR_INVALID, "all(strand(exclude) == \"*\") is not TRUE");
-        if (trim_mode(h) && (rc = build_gaps(h))) return rc;
-        const bool rank = rank_path_ok(h);
-        if (rank) {
-            if ((rc = build_pairs(h))) return rc;  // window lists of the features and of the tiles
-            tr.lap("build_pairs");
-        }
-        // the streaming kernels (count without the rank path, and the fill pass) test exclusion per range
-        if (h->excl.n && (rc = build_slices(h, active_excl(h), h->x_tile_lo, h->x_tile_hi))) return rc;
-        if (!rank) {
-            if (h->query.n && (rc = range_set_to_device(h, h->query))) return rc;
-            if (h->query.n && (rc = build_slices(h, h->query, h->q_tile_lo, h->q_tile_hi))) return rc;
-            if ((rc = ensure_pmax_table(h))) return rc;
-        }
+        if ((rc = prepare_lists(h))) return rc;
         h->slices_dirty = false;
     }
+    if (!rank_path_ok(h)) return ensure_pmax_table(h);
     return NRB200_OK;
 }
 
@@ -205,9 +213,8 @@ void launch_count_t(nrb200_handle *h, const BootParams &P, unsigned grid, int ex
 }
 
 constexpr int64_t kMaxBatch = 2048;  // iterations per launch at most (gridDim.y and scratch stay small); NRB200_MAX_BATCH lowers it
-constexpr int kChunkEvents = 16;
+constexpr int kChunkEvents = 64;
 constexpr size_t kMaxStagingBytes = (size_t)2 << 30;  // pinned staging for pageable result buffers, at most
-constexpr int kChunks = 8;  // pipeline depth of nrb200_run_counts (compute chunk k+1 while chunk k copies out)
 
 // Returns the number of kernels launched.
 int launch_rank(nrb200_handle *h, const BootParams &P, bool has_query) {
@@ -277,6 +284,7 @@ int run_counts_core(nrb200_handle *h, const nrb200_draws *d, bool want_counts, i
                     nrb200_stats *stats) {
     int rc;
     if ((rc = prepare(h))) return rc;
+    h->timeline.mark("lists ready", h->stream);
     NRB_CUDA(h, cudaEventRecord(h->ev[0], h->stream));
     if ((rc = stage_draws(h, d))) return rc;
     const int64_t R = d->n_iter, G = h->query.n;
@@ -308,7 +316,7 @@ int run_counts_core(nrb200_handle *h, const nrb200_draws *d, bool want_counts, i
     int64_t chunk = h->tune_max_batch;
     if (pipelined) {
         if (!h->copy_stream) NRB_CUDA(h, cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
-        chunk = std::min<int64_t>(h->tune_max_batch, std::max<int64_t>(((R + kChunks - 1) / kChunks + 7) / 8 * 8, 64));
+        chunk = std::min<int64_t>(h->tune_max_batch, std::max<int64_t>(((R + h->tune_chunks - 1) / h->tune_chunks + 7) / 8 * 8, 64));
     }
     if (rank_path_ok(h) && has_query) {
         NRB_CUDA(h, h->draw_tab.reserve((size_t)std::min(chunk, std::max<int64_t>(R, 1)) * h->plan.n_blocks() * sizeof(int2)));
@@ -352,6 +360,7 @@ int run_counts_core(nrb200_handle *h, const nrb200_draws *d, bool want_counts, i
         h->split_ev = nullptr;
         if (split) NRB_CUDA(h, cudaEventRecord(h->batch_ev[3 * k + 2], h->stream));
         NRB_CUDA(h, cudaGetLastError());
+        h->timeline.mark("chunk computed", h->stream);
         if (pipelined) {
             cudaEvent_t &ev = h->chunk_ev[k % kChunkEvents];
             if (!ev) NRB_CUDA(h, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
@@ -359,6 +368,7 @@ int run_counts_core(nrb200_handle *h, const nrb200_draws *d, bool want_counts, i
             NRB_CUDA(h, cudaStreamWaitEvent(h->copy_stream, ev, 0));
             NRB_CUDA(h, cudaMemcpyAsync((staging ? staging : host_counts) + r0 * G, counts + r0 * G, (size_t)n * G * sizeof(int32_t),
                                         cudaMemcpyDeviceToHost, h->copy_stream));
+            h->timeline.mark("chunk copied out", h->copy_stream);
             if (staging) {
                 cudaEvent_t &done = h->copied_ev[k % kChunkEvents];
                 if (!done) NRB_CUDA(h, cudaEventCreateWithFlags(&done, cudaEventDisableTiming));
