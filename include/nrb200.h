@@ -254,6 +254,10 @@ int nrb200_rrng_runif(nrb200_rrng *g, int64_t n, const double *min, int64_t n_mi
 int nrb200_rrng_sample(nrb200_rrng *g, int32_t n, int64_t size, int32_t replace,
                        const double *prob, int32_t *out);
 double nrb200_r_round(double x); /* round(x): half to even */
+/* rep(first:(first + n_runs - 1), diff(offsets)) as int32: the dense image of the `iter` column
+ * (Rle(factor(rep(seq_len(R), lens))), R/bootRanges.R:122) for hosts without run-length vectors; R builds the Rle
+ * from iter_offsets directly and never needs it.  out: [offsets[n_runs] - offsets[0]]. */
+void nrb200_expand_runs(const int64_t *offsets, int64_t n_runs, int32_t first, int32_t *out);
 
 #if defined(__GNUC__)
 #pragma GCC visibility pop

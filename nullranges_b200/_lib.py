@@ -77,6 +77,7 @@ SYMBOLS = [
     ("nrb200_rrng_runif", C.c_int, [vp, C.c_int64, dp, C.c_int64, dp, C.c_int64, dp]),
     ("nrb200_rrng_sample", C.c_int, [vp, C.c_int32, C.c_int64, C.c_int32, dp, i32p]),
     ("nrb200_r_round", C.c_double, [C.c_double]),
+    ("nrb200_expand_runs", None, [i64p, C.c_int64, C.c_int32, i32p]),
 ]
 
 _lib = None

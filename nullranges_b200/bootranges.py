@@ -165,7 +165,7 @@ def bootRanges(y: GRanges, blockLength, R: int = 1, seg: GRanges | None = None, 
     br.strand = y.strand[src] if np.any(y.strand) else np.zeros(src.size, np.int8)
     br.mcols = {k: v[src] for k, v in y.mcols.items() if k != "block"}
     # mcols(br)$iter <- Rle(factor(rep(seq_len(R), lens), levels = seq_len(R)))   R/bootRanges.R:122
-    br.mcols["iter"] = np.repeat(np.arange(1, int(R) + 1, dtype=np.int32), lens)
+    br.mcols["iter"] = eng.expand_runs(rows["iter_offsets"], first=1)
     if storeBlockLength:
         br.mcols["blockLength"] = np.full(src.size, L_b, dtype=np.int32)  # :123-125
     if storeBlockStart:

@@ -597,4 +597,22 @@ int nrb200_fetch_rows(nrb200_handle *h, int64_t row0, int64_t n, int32_t *seqid,
     return NRB200_OK;
 }
 
+void nrb200_expand_runs(const int64_t *offsets, int64_t n_runs, int32_t first, int32_t *out) {
+    if (!offsets || !out || n_runs <= 0) return;
+    const int64_t base = offsets[0], total = offsets[n_runs] - base;
+    const int64_t piece = (int64_t)1 << 18;  // elements per task
+    const int64_t pieces = (total + piece - 1) / piece;
+#pragma omp parallel for schedule(static) if (total >= ((int64_t)1 << 20))
+    for (int64_t p = 0; p < pieces; ++p) {
+        const int64_t lo = base + p * piece, hi = std::min(lo + piece, base + total);
+        int64_t r = std::upper_bound(offsets, offsets + n_runs + 1, lo) - offsets - 1;  // run that holds element lo
+        for (int64_t i = lo; i < hi;) {
+            while (offsets[r + 1] <= i) ++r;
+            const int64_t stop = std::min(hi, offsets[r + 1]);
+            std::fill(out + (i - base), out + (stop - base), (int32_t)(first + r));
+            i = stop;
+        }
+    }
+}
+
 }  // extern "C"

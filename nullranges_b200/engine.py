@@ -218,6 +218,14 @@ class Engine:
         return cols
 
 
+    def expand_runs(self, offsets, first: int = 1) -> np.ndarray:
+        """rep(first:(first + R - 1), diff(offsets)) as int32 (the dense `iter` column), filled by all host cores."""
+        offs = np.ascontiguousarray(offsets, dtype=np.int64)
+        out = np.empty(int(offs[-1] - offs[0]), np.int32)
+        self._lib.nrb200_expand_runs(ptr(offs, C.c_int64), offs.size - 1, int(first), ptr(out, C.c_int32))
+        return out
+
+
 _engines: dict[int, Engine] = {}
 
 

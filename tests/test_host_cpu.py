@@ -141,3 +141,17 @@ def test_r_shim_type_checks_against_the_header():
             n += (ch == "," and depth == 0)
         assert name in registered, name
         assert registered[name] == n, f"{name}: wrapper passes {n} arguments, shim registers {registered[name]}"
+
+
+def test_expand_runs_matches_numpy_repeat():
+    """nrb200_expand_runs(): the dense iter column, rep(seq_len(R), lens) of R/bootRanges.R:122 (host utility, no GPU)."""
+    import ctypes as C
+    from nullranges_b200 import _lib
+    lib = _lib.load()
+    rng = np.random.default_rng(0)
+    for n_runs, scale in ((1, 5), (7, 3), (1000, 3000), (50, 100000), (3, 0)):
+        lens = rng.integers(0, scale + 1, n_runs)
+        offs = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64) + 17
+        out = np.empty(int(offs[-1] - offs[0]), np.int32)
+        lib.nrb200_expand_runs(_lib.ptr(offs, C.c_int64), n_runs, 1, _lib.ptr(out, C.c_int32))
+        np.testing.assert_array_equal(out, np.repeat(np.arange(1, n_runs + 1, dtype=np.int32), lens))
