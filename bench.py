@@ -33,6 +33,16 @@ import sys
 import threading
 import time
 
+# torchrun pins OMP_NUM_THREADS to 1 for every rank unless the caller set it.  The engine's host side (window lists,
+# staging copies) is OpenMP: give each rank its share of the cores instead.  Must happen before numpy / torch load.
+_lws = int(os.environ.get("LOCAL_WORLD_SIZE", "1") or 1)
+if _lws > 1 and os.environ.get("OMP_NUM_THREADS") == "1":
+    try:
+        _cores = len(os.sched_getaffinity(0))
+    except AttributeError:
+        _cores = os.cpu_count() or 1
+    os.environ["OMP_NUM_THREADS"] = str(max(1, _cores // _lws))
+
 import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
@@ -361,6 +371,7 @@ def run_gpu(args):
             "config": {"workload": WORKLOAD, "iters_per_step_per_gpu": R, "n_blocks": int(B), "rng": "philox4x32-10 on device",
                        "l2": "flushed between timed steps (256 MiB fill, outside the step events); inside a step the 12 MB range table is re-read by design",
                        "sharding": "iterations, rank-major; [2 x R] int64 per-iteration vectors all-gathered over NCCL each step" if world > 1 else "single GPU",
+                       "host_threads_per_rank": int(os.environ.get("OMP_NUM_THREADS", "0") or 0) or host_cores(),
                        "wall_s_timed_region": t_wall},
             "e2e": {"value": R * world * e2e_steps / e2e_s, "unit": "iter/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "steps": e2e_steps, "api": "nullranges_b200.bootCounts(y, x, blockLength, R) from host arrays (upload + index build + run + D2H every step)"},
