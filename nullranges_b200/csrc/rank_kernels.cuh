@@ -289,8 +289,8 @@ struct AddF64 {
 // hits of the bait block minus (where the variant filters width > 0, R/bootUnsegmented.R:189) the
 // hits shifted wholly beyond the sequence end.  Requires tile_start <= seqlength for every tile
 // (checked on the host).
-template <int RPT>
-__global__ void __launch_bounds__(256) boot_block_rows_kernel(const BootParams P, const TileExcl X) {
+template <int RPT, int MINB>
+__global__ void __launch_bounds__(256, MINB) boot_block_rows_kernel(const BootParams P, const TileExcl X) {
     __shared__ int warp_rows[8][RPT];
     __shared__ unsigned long long cta_hits;
     const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;

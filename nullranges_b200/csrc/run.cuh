@@ -224,7 +224,11 @@ int launch_rank(nrb200_handle *h, const BootParams &P, bool has_query) {
     const unsigned gy = (unsigned)((P.n_iter + rpt - 1) / rpt);
     if (P.n_blocks > 0) {
         const TileExcl X{h->excl.n > 0 ? h->tile_x_off.as<int32_t>() : nullptr, h->tile_x_rec.as<int4>()};  // drop: minus, trim: plus
-        boot_block_rows_kernel<1><<<dim3((unsigned)((P.n_blocks + 255) / 256), (unsigned)P.n_iter), 256, 0, h->stream>>>(P, X);
+        const dim3 rows_grid((unsigned)((P.n_blocks + 255) / 256), (unsigned)P.n_iter);
+        if (h->tune_minb_rows >= 8) boot_block_rows_kernel<1, 8><<<rows_grid, 256, 0, h->stream>>>(P, X);
+        else if (h->tune_minb_rows == 6) boot_block_rows_kernel<1, 6><<<rows_grid, 256, 0, h->stream>>>(P, X);
+        else if (h->tune_minb_rows == 5) boot_block_rows_kernel<1, 5><<<rows_grid, 256, 0, h->stream>>>(P, X);
+        else boot_block_rows_kernel<1, 1><<<rows_grid, 256, 0, h->stream>>>(P, X);
         ++launches;
     }
     if (h->split_ev) cudaEventRecord(h->split_ev, h->stream);  // stats: end of the rows kernel
@@ -233,6 +237,8 @@ int launch_rank(nrb200_handle *h, const BootParams &P, bool has_query) {
         const dim3 grid((unsigned)((P.n_query + 255) / 256), gy);
         switch (rpt * 10 + h->tune_minb) {
         case 11: boot_rank_count_kernel<1, 1><<<grid, 256, 0, h->stream>>>(P, F); break;
+        case 17: boot_rank_count_kernel<1, 7><<<grid, 256, 0, h->stream>>>(P, F); break;
+        case 18: boot_rank_count_kernel<1, 8><<<grid, 256, 0, h->stream>>>(P, F); break;
         case 21: boot_rank_count_kernel<2, 1><<<grid, 256, 0, h->stream>>>(P, F); break;
         case 24: boot_rank_count_kernel<2, 4><<<grid, 256, 0, h->stream>>>(P, F); break;
         case 41: boot_rank_count_kernel<4, 1><<<grid, 256, 0, h->stream>>>(P, F); break;

@@ -14,8 +14,9 @@ if len(sys.argv) > 1 and sys.argv[1] == "child":
     ab = min(e.run_counts_resident(d, True, True)["kernel_ms"] for _ in range(8))
     print(json.dumps({"A_ms": round(a, 4), "AB_ms": round(ab, 4), "B_ms": round(ab - a, 4)}))
     sys.exit(0)
-for rpt, minb, mult in [(4, 1, 4), (4, 3, 4), (4, 4, 4), (2, 1, 4), (2, 4, 4), (1, 1, 4), (8, 1, 4),
+combos = [tuple(int(v) for v in a.split(",")) for a in sys.argv[1:]] or None  # e.g. 1,1,4 1,8,4
+for rpt, minb, mult in combos or [(4, 1, 4), (4, 3, 4), (4, 4, 4), (2, 1, 4), (2, 4, 4), (1, 1, 4), (8, 1, 4),
                         (2, 1, 1), (2, 1, 2), (2, 1, 8), (4, 3, 1), (4, 3, 2), (1, 1, 1), (1, 1, 2)]:
-    env = dict(os.environ, NRB200_RPT=str(rpt), NRB200_MINB=str(minb), NRB200_TABLE_MULT=str(mult))
+    env = dict(os.environ, NRB200_RPT=str(rpt), NRB200_MINB=str(minb), NRB200_TABLE_MULT=str(mult))  # NRB200_MINB_ROWS passes through
     out = subprocess.run([sys.executable, __file__, "child"], env=env, capture_output=True, text=True)
     print(f"rpt={rpt} minb={minb} table_mult={mult}: {out.stdout.strip() or out.stderr[-300:]}", flush=True)
