@@ -220,7 +220,9 @@ constexpr size_t kMaxStagingBytes = (size_t)2 << 30;  // pinned staging for page
 int launch_rank(nrb200_handle *h, const BootParams &P, bool has_query) {
     if (P.n_iter == 0) return 0;
     int launches = 0;
-    const int rpt = h->tune_rpt;
+    int rpt = h->tune_rpt;
+    const int variant = rpt * 10 + h->tune_minb;  // tuning variants kept from the sweep; anything else runs <1, 8>
+    if (variant != 11 && variant != 17 && variant != 21 && variant != 24 && variant != 41 && variant != 43 && variant != 44 && variant != 81) rpt = 1;
     const unsigned gy = (unsigned)((P.n_iter + rpt - 1) / rpt);
     if (P.n_blocks > 0) {
         const TileExcl X{h->excl.n > 0 ? h->tile_x_off.as<int32_t>() : nullptr, h->tile_x_rec.as<int4>()};  // drop: minus, trim: plus
@@ -235,17 +237,16 @@ int launch_rank(nrb200_handle *h, const BootParams &P, bool has_query) {
     if (has_query) {
         const FeatView F{h->f_src.as<int32_t>(), h->pair_off.as<int32_t>(), h->pair_rec.as<PairRec>()};
         const dim3 grid((unsigned)((P.n_query + 255) / 256), gy);
-        switch (rpt * 10 + h->tune_minb) {
+        switch (variant) {
         case 11: boot_rank_count_kernel<1, 1><<<grid, 256, 0, h->stream>>>(P, F); break;
         case 17: boot_rank_count_kernel<1, 7><<<grid, 256, 0, h->stream>>>(P, F); break;
-        case 18: boot_rank_count_kernel<1, 8><<<grid, 256, 0, h->stream>>>(P, F); break;
         case 21: boot_rank_count_kernel<2, 1><<<grid, 256, 0, h->stream>>>(P, F); break;
         case 24: boot_rank_count_kernel<2, 4><<<grid, 256, 0, h->stream>>>(P, F); break;
         case 41: boot_rank_count_kernel<4, 1><<<grid, 256, 0, h->stream>>>(P, F); break;
         case 43: boot_rank_count_kernel<4, 3><<<grid, 256, 0, h->stream>>>(P, F); break;
         case 44: boot_rank_count_kernel<4, 4><<<grid, 256, 0, h->stream>>>(P, F); break;
         case 81: boot_rank_count_kernel<8, 1><<<grid, 256, 0, h->stream>>>(P, F); break;
-        default: boot_rank_count_kernel<1, 1><<<grid, 256, 0, h->stream>>>(P, F); break;
+        default: boot_rank_count_kernel<1, 8><<<grid, 256, 0, h->stream>>>(P, F); break;
         }
         ++launches;
     }
