@@ -406,12 +406,11 @@ int nrb200_run_weighted(nrb200_handle *h, const nrb200_draws *draws, double *ite
     const int64_t R = draws->n_iter, G = h->query.n, B = h->plan.n_blocks();
     const int64_t batch = std::max<int64_t>(1, std::min<int64_t>(h->tune_max_batch, ((int64_t)1 << 27) / std::max<int64_t>(G, 1)));
     NRB_CUDA(h, h->d_iter_nranges.reserve(std::max<int64_t>(R, 1) * 8));
-    NRB_CUDA(h, h->d_n_hits.reserve(16));
     NRB_CUDA(h, h->ws_iter.reserve(std::max<int64_t>(R, 1) * 8));
     NRB_CUDA(h, h->ws_sums.reserve((size_t)std::min(batch, std::max<int64_t>(R, 1)) * G * 8));
     NRB_CUDA(h, h->draw_tab.reserve((size_t)std::min(batch, std::max<int64_t>(R, 1)) * B * sizeof(int2)));
     NRB_CUDA(h, cudaMemsetAsync(h->d_iter_nranges.p, 0, R * 8, h->stream));
-    NRB_CUDA(h, cudaMemsetAsync(h->d_n_hits.p, 0, 16, h->stream));
+    if ((rc = hits_reset(h))) return rc;
     NRB_CUDA(h, cudaMemsetAsync(h->ws_iter.p, 0, R * 8, h->stream));
     BootParams P = make_params(h, draws);
     P.iter_nranges = h->d_iter_nranges.as<unsigned long long>();
@@ -507,12 +506,11 @@ int nrb200_run_materialize(nrb200_handle *h, const nrb200_draws *draws, int64_t 
     if ((rc = stage_draws(h, draws))) return rc;
     const int64_t R = draws->n_iter, B = h->plan.n_blocks(), items = R * B;
     NRB_CUDA(h, h->d_iter_nranges.reserve(std::max<int64_t>(R, 1) * 8));
-    NRB_CUDA(h, h->d_n_hits.reserve(16));  // [0] hits, [1] fill-overflow flag
     NRB_CUDA(h, h->item_rows.reserve(std::max<int64_t>(items, 1) * 4));
     NRB_CUDA(h, h->within_off.reserve(std::max<int64_t>(items, 1) * 4));
     NRB_CUDA(h, h->iter_off_dev.reserve((R + 1) * 8));
     NRB_CUDA(h, cudaMemsetAsync(h->d_iter_nranges.p, 0, R * 8, h->stream));
-    NRB_CUDA(h, cudaMemsetAsync(h->d_n_hits.p, 0, 16, h->stream));
+    if ((rc = hits_reset(h))) return rc;  // partial hit sums, then the fill-overflow flag
     BootParams P = make_params(h, draws);
     P.n_query = 0;
     P.iter_nranges = h->d_iter_nranges.as<unsigned long long>();
@@ -551,7 +549,7 @@ int nrb200_run_materialize(nrb200_handle *h, const nrb200_draws *draws, int64_t 
             BootParams Q = slice_params(P, r0, std::min(kFillBatch, R - r0));
             const RowsOut O{h->row_seq.as<int32_t>(), h->row_start.as<int32_t>(), h->row_end.as<int32_t>(), h->row_src.as<int32_t>(),
                             h->row_block.as<int32_t>(), h->iter_off_dev.as<int64_t>() + r0, h->within_off.as<int32_t>() + r0 * B,
-                            h->item_rows.as<int32_t>() + r0 * B, reinterpret_cast<int *>(h->d_n_hits.as<char>() + 8)};
+                            h->item_rows.as<int32_t>() + r0 * B, reinterpret_cast<int *>(h->d_n_hits.as<unsigned long long>() + kHitSlots)};
             const dim3 grid((unsigned)std::min<int64_t>((B + 7) / 8, 65535), (unsigned)Q.n_iter);
             if (excl == kExclTrim) boot_fill_trim_kernel<<<grid, 256, 0, h->stream>>>(Q, O);
             else if (st) boot_fill_kernel<true, kExclDrop><<<grid, 256, 0, h->stream>>>(Q, O);
@@ -561,10 +559,10 @@ int nrb200_run_materialize(nrb200_handle *h, const nrb200_draws *draws, int64_t 
         }
     }
     NRB_CUDA(h, cudaEventRecord(h->ev[2], h->stream));
-    unsigned long long hits_and_flag[2] = {0, 0};
-    NRB_CUDA(h, cudaMemcpyAsync(hits_and_flag, h->d_n_hits.p, 16, cudaMemcpyDeviceToHost, h->stream));
+    unsigned long long hit_words[kHitSlots + 1] = {};
+    if ((rc = hits_fetch(h, hit_words))) return rc;
     if (int rc_sync = sync_stream(h)) return rc_sync;
-    if (hits_and_flag[1] != 0) {
+    if (hit_words[kHitSlots] != 0) {
         h->n_rows = 0;
         return fail(h, NRB200_ERR_STATE, "internal error: the count and fill passes of the table disagree (no row was written out of place)");
     }
@@ -574,7 +572,7 @@ int nrb200_run_materialize(nrb200_handle *h, const nrb200_draws *draws, int64_t 
         float k_ms = 0, t_ms = 0;
         cudaEventElapsedTime(&k_ms, h->ev[1], h->ev[2]);
         cudaEventElapsedTime(&t_ms, h->ev[0], h->ev[2]);
-        const unsigned long long hits = hits_and_flag[0];
+        const unsigned long long hits = hits_total(hit_words);
         std::memset(stats, 0, sizeof *stats);
         stats->kernel_ms = k_ms;
         stats->total_ms = t_ms;

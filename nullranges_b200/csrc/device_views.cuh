@@ -79,7 +79,7 @@ struct BootParams {
     unsigned long long *iter_nranges, *iter_totals;  // [n_iter]
     int32_t *counts;          // [n_iter x n_query], caller's query order, or nullptr
     int32_t *item_rows;       // [n_iter x n_blocks] surviving rows per item, or nullptr
-    unsigned long long *n_hits;  // total ranges sampled (byte-model H)
+    unsigned long long *n_hits;  // [kHitSlots] partial sums of the ranges sampled (byte-model H), slot = iteration % kHitSlots
     int2 *draw_tab;           // [n_iter x n_blocks] {bait seq, bait start}: rank path scratch
     int4 *item_rec;           // [n_iter x n_blocks] {lo, hi, bait seq, bait start}: written by the rows kernel for the fill pass
 };
@@ -110,6 +110,7 @@ __device__ __forceinline__ int32_t first_ge(const int32_t *__restrict__ v, int32
 // first = index, relative to the sequence's first range, of the first value >= u << shift;
 // count = values inside the bucket.  One 4-byte probe therefore yields both ends of the bucket
 // (count == 7 means "7 or more": the next entry holds the end).
+constexpr int kHitSlots = 64;  // the H statistic is tallied in this many places so that no single address takes every atomic
 constexpr int kRankCountBits = 3;
 constexpr int32_t kRankCountCap = (1 << kRankCountBits) - 1;
 

@@ -389,4 +389,22 @@ int upload_direct(nrb200_handle *h, DevMem &dst, const T *src, size_t n, int slo
     return NRB200_OK;
 }
 
+// The H statistic: kHitSlots partial sums followed by one flag word (the table's fill-overflow flag).
+constexpr size_t kHitBytes = ((size_t)64 + 1) * 8;
+inline int hits_reset(nrb200_handle *h) {
+    NRB_CUDA(h, h->d_n_hits.reserve(kHitBytes));
+    NRB_CUDA(h, cudaMemsetAsync(h->d_n_hits.p, 0, kHitBytes, h->stream));
+    return NRB200_OK;
+}
+// queues the copy; after the next synchronisation hits_total() sums what landed in `buf` ([65] words)
+inline int hits_fetch(nrb200_handle *h, unsigned long long *buf) {
+    NRB_CUDA(h, cudaMemcpyAsync(buf, h->d_n_hits.p, kHitBytes, cudaMemcpyDeviceToHost, h->stream));
+    return NRB200_OK;
+}
+inline unsigned long long hits_total(const unsigned long long *buf) {
+    unsigned long long s = 0;
+    for (int i = 0; i < 64; ++i) s += buf[i];
+    return s;
+}
+
 }  // namespace

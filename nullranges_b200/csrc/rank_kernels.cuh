@@ -291,11 +291,8 @@ struct AddF64 {
 // (checked on the host).
 template <int RPT, int MINB>
 __global__ void __launch_bounds__(256, MINB) boot_block_rows_kernel(const BootParams P, const TileExcl X) {
-    __shared__ int warp_rows[8][RPT];
-    __shared__ unsigned long long cta_hits;
     const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t r0 = (int64_t)blockIdx.y * RPT;
-    if (threadIdx.x == 0) cta_hits = 0;
     int rows[RPT];
     int hits_sum = 0;
 #pragma unroll
@@ -350,22 +347,16 @@ __global__ void __launch_bounds__(256, MINB) boot_block_rows_kernel(const BootPa
             }
         }
     }
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    // every warp adds its share straight to the per-iteration tallies (spread over the iterations' addresses): no
+    // shared-memory stage, no barrier, a warp retires as soon as its 32 blocks are done
+    const int lane = threadIdx.x & 31;
 #pragma unroll
     for (int j = 0; j < RPT; ++j) {
         const int s = __reduce_add_sync(kFull, rows[j]);
-        if (lane == 0) warp_rows[warp][j] = s;
+        if (lane == 0 && s && r0 + j < P.n_iter) atomicAdd(P.iter_nranges + r0 + j, (unsigned long long)(unsigned)s);
     }
     hits_sum = __reduce_add_sync(kFull, hits_sum);
-    __syncthreads();
-    if (lane == 0 && hits_sum) atomicAdd(&cta_hits, (unsigned long long)hits_sum);
-    if (threadIdx.x < RPT && r0 + threadIdx.x < P.n_iter) {
-        unsigned long long s = 0;
-        for (int w = 0; w < 8; ++w) s += (unsigned)warp_rows[w][threadIdx.x];
-        if (s) atomicAdd(P.iter_nranges + r0 + threadIdx.x, s);
-    }
-    __syncthreads();
-    if (threadIdx.x == 0 && P.n_hits && cta_hits) atomicAdd(P.n_hits, cta_hits);
+    if (lane == 0 && P.n_hits && hits_sum) atomicAdd(P.n_hits + (r0 & (kHitSlots - 1)), (unsigned long long)hits_sum);
 }
 
 // (seqid << 32 | end) sort keys and their unpacking: the sorted-ends array of the rank path

@@ -299,10 +299,9 @@ int run_counts_core(nrb200_handle *h, const nrb200_draws *d, bool want_counts, i
     want_counts = want_counts && has_query;
     NRB_CUDA(h, h->d_iter_nranges.reserve(std::max<int64_t>(R, 1) * 8));
     NRB_CUDA(h, h->d_iter_totals.reserve(std::max<int64_t>(R, 1) * 8));
-    NRB_CUDA(h, h->d_n_hits.reserve(8));
     NRB_CUDA(h, cudaMemsetAsync(h->d_iter_nranges.p, 0, R * 8, h->stream));
     NRB_CUDA(h, cudaMemsetAsync(h->d_iter_totals.p, 0, R * 8, h->stream));
-    NRB_CUDA(h, cudaMemsetAsync(h->d_n_hits.p, 0, 8, h->stream));
+    if ((rc = hits_reset(h))) return rc;
     int32_t *counts = nullptr;
     if (want_counts) {
         NRB_CUDA(h, h->d_counts.reserve((size_t)R * G * sizeof(int32_t)));
@@ -402,9 +401,10 @@ int run_counts_core(nrb200_handle *h, const nrb200_draws *d, bool want_counts, i
         float k_ms = 0, t_ms = 0;
         cudaEventElapsedTime(&k_ms, h->ev[1], h->ev[2]);
         cudaEventElapsedTime(&t_ms, h->ev[0], h->ev[2]);
-        unsigned long long hits = 0;
-        NRB_CUDA(h, cudaMemcpyAsync(&hits, h->d_n_hits.p, 8, cudaMemcpyDeviceToHost, h->stream));
+        unsigned long long hit_words[kHitSlots + 1];
+        if ((rc = hits_fetch(h, hit_words))) return rc;
         if (int rc_sync = sync_stream(h)) return rc_sync;
+        const unsigned long long hits = hits_total(hit_words);
         std::memset(stats, 0, sizeof *stats);
         stats->kernel_ms = k_ms;
         stats->total_ms = t_ms;

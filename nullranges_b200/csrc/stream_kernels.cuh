@@ -158,7 +158,7 @@ __global__ void __launch_bounds__(256) boot_count_kernel(const BootParams P) {
             if (rows) atomicAdd(P.iter_nranges + r, (unsigned long long)rows);
             if (HAS_QUERY && overlaps) atomicAdd(P.iter_totals + r, (unsigned long long)overlaps);
             if (P.item_rows) P.item_rows[item] = rows;
-            if (P.n_hits && hits) atomicAdd(P.n_hits, (unsigned long long)hits);
+            if (P.n_hits && hits) atomicAdd(P.n_hits + (r & (kHitSlots - 1)), (unsigned long long)hits);
         }
     }
 }
