@@ -416,7 +416,7 @@ int nrb200_run_weighted(nrb200_handle *h, const nrb200_draws *draws, double *ite
     P.iter_nranges = h->d_iter_nranges.as<unsigned long long>();
     P.n_hits = h->d_n_hits.as<unsigned long long>();
     P.draw_tab = h->draw_tab.as<int2>();
-    const FeatView F{h->f_src.as<int32_t>(), h->pair_off.as<int32_t>(), h->pair_rec.as<PairRec>()};
+    const FeatView F{h->f_src.as<int32_t>(), h->pair_off.as<int32_t>(), h->pair_rec.as<int4>(), h->pair_rec.as<int4>() + h->n_pairs};
     const WeightView W{h->n_cls > 1 ? h->w_r.as<double>() : h->w_c.as<double>(), h->w_ps.as<double>(),
                        h->ends_alias_starts ? h->w_ps.as<double>() : h->w_pe.as<double>()};
     NRB_CUDA(h, cudaEventRecord(h->ev[1], h->stream));

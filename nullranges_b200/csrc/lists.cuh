@@ -29,7 +29,7 @@ int build_slices(nrb200_handle *h, const RangeSet &rs, DevMem &lo_dev, DevMem &h
 }
 
 // ---- rank path tables --------------------------------------------------------------------
-// Per feature: the signed windows to count on each tile within reach (PairRec, kernels.cuh).
+// Per feature: the signed windows to count on each tile within reach (two int4 per window, rank_kernels.cuh).
 // Tile t is within reach of a window when the window comes within (wmax - 1) of the tile, i.e.
 // when a range landing on the tile can overlap it.  Windows that start beyond their sequence end
 // are dropped (trim() leaves nothing there).  With an exclude set, the merged exclude regions
@@ -242,11 +242,14 @@ int build_pairs(nrb200_handle *h) {
     std::vector<int32_t> f_src(G), f_off(G + 1);
     f_off[G] = (int32_t)total;
     // records are written straight into pinned staging memory when they fit there
-    std::vector<PairRec> f_recs_vec;
-    PairRec *f_recs = static_cast<PairRec *>(arena_alloc(h, (size_t)std::max<int64_t>(total, 1) * sizeof(PairRec)));
+    struct Rec4 {
+        int32_t x, y, z, w;
+    };
+    std::vector<Rec4> f_recs_vec;  // the "a" halves of all records, then the "b" halves (rank_kernels.cuh)
+    Rec4 *f_recs = static_cast<Rec4 *>(arena_alloc(h, (size_t)std::max<int64_t>(2 * total, 1) * sizeof(Rec4)));
     const bool staged = f_recs != nullptr;
     if (!staged) {
-        f_recs_vec.resize((size_t)total);
+        f_recs_vec.resize((size_t)(2 * total));
         f_recs = f_recs_vec.data();
     }
 #pragma omp parallel for schedule(dynamic, 1) if (G >= 4096)
@@ -267,14 +270,15 @@ int build_pairs(nrb200_handle *h) {
                           f_off[at] = (int32_t)cursor;
                       },
                       [&](int32_t, int32_t t, int64_t ws, int64_t we, int sign, int cls) {
-                          f_recs[cursor++] = PairRec{t, (int32_t)ws, (int32_t)std::min<int64_t>(we, INT32_MAX / 2), sign, p.tile_start[t],
-                                                     p.bait_width[t], (int32_t)h->seqlen[p.tile_seq[t]], cls};
+                          f_recs[cursor] = Rec4{t, (int32_t)ws, (int32_t)std::min<int64_t>(we, INT32_MAX / 2), sign};
+                          f_recs[total + cursor] = Rec4{p.tile_start[t], p.bait_width[t], (int32_t)h->seqlen[p.tile_seq[t]], cls};
+                          ++cursor;
                       });
     }
     tr.lap("lists");
     if ((rc = upload(h, h->f_src, f_src.data(), (size_t)G))) return rc;
     if ((rc = upload(h, h->pair_off, f_off.data(), (size_t)G + 1))) return rc;
-    if ((rc = staged ? upload_staged(h, h->pair_rec, f_recs, (size_t)total) : upload(h, h->pair_rec, f_recs, (size_t)total))) return rc;
+    if ((rc = staged ? upload_staged(h, h->pair_rec, f_recs, (size_t)(2 * total)) : upload(h, h->pair_rec, f_recs, (size_t)(2 * total)))) return rc;
     tr.lap("upload");
     return NRB200_OK;
 }

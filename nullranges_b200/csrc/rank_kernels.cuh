@@ -26,19 +26,17 @@ namespace nrb {
 // (disjoint, sorted), so a range overlaps a run of consecutive regions and the union is
 // sum_k |S_k| - sum_k |S_k and S_k+1|.  A feature therefore owns a list of signed windows per tile.
 
-struct PairRec {               // one signed window to count for a feature on a tile (32 bytes)
-    int32_t tile;              // block index b (row of the draw table)
-    int32_t ws, we;            // window on the tile's sequence ([gs, ge] or an exclusion pseudo-feature)
-    int32_t sign;              // +1 / -1
-    int32_t tile_start, width, seq_len;  // copied from the block tables: saves three dependent loads
-    int32_t cls;               // strand class of y the window counts (0 when y is unstranded)
-};
-static_assert(sizeof(PairRec) == 32, "PairRec is read as two int4");
+// One signed window to count for a feature on a tile: 32 bytes kept as two int4 in two parallel arrays, so that a
+// warp's 32 consecutive records are 4 full lines per load instead of 8 half-used ones.
+//   a = {tile (block index b, row of the draw table), ws, we (window on the tile's sequence: [gs, ge] or an exclusion
+//        pseudo-feature), sign (+1 / -1)}
+//   b = {tile_start, width, seq_len (copied from the block tables: saves three dependent loads), cls (strand class of
+//        y the window counts; 0 when y is unstranded)}
 
 struct FeatView {              // query features in visit order (grouped by list length)
     const int32_t *src;        // [n_query] index in the caller's order
     const int32_t *pair_off;   // [n_query + 1]
-    const PairRec *pair_rec;
+    const int4 *rec_a, *rec_b;  // [n_pairs] each
 };
 
 struct TileExcl {              // signed exclusion windows of each (tile, strand class), for the rows kernel
@@ -153,8 +151,8 @@ __global__ void __launch_bounds__(256, MINB) boot_rank_count_kernel(const BootPa
         const int32_t src = __ldg(F.src + g);
         const int32_t p1 = __ldg(F.pair_off + g + 1);
         for (int32_t p = __ldg(F.pair_off + g); p < p1; ++p) {
-            const int4 ra = __ldg(reinterpret_cast<const int4 *>(F.pair_rec + p));      // tile, ws, we, sign
-            const int4 rb = __ldg(reinterpret_cast<const int4 *>(F.pair_rec + p) + 1);  // tile_start, width, seq_len
+            const int4 ra = __ldg(F.rec_a + p);  // tile, ws, we, sign
+            const int4 rb = __ldg(F.rec_b + p);  // tile_start, width, seq_len, cls
             const int2 *__restrict__ tab = P.draw_tab + r0 * P.n_blocks + ra.x;
             int2 d[RPT];
 #pragma unroll
@@ -240,8 +238,8 @@ __global__ void __launch_bounds__(256) boot_rank_wsum_kernel(const BootParams P,
         const int32_t src = __ldg(F.src + g);
         const int32_t p1 = __ldg(F.pair_off + g + 1);
         for (int32_t p = __ldg(F.pair_off + g); p < p1; ++p) {
-            const int4 ra = __ldg(reinterpret_cast<const int4 *>(F.pair_rec + p));
-            const int4 rb = __ldg(reinterpret_cast<const int4 *>(F.pair_rec + p) + 1);
+            const int4 ra = __ldg(F.rec_a + p);
+            const int4 rb = __ldg(F.rec_b + p);
             const int2 d = __ldg(P.draw_tab + r * P.n_blocks + ra.x);
             const double v = P.permute ? weighted_pair<true>(P.y, W, d, rb.w, rb.y, rb.x, rb.z, ra.y, ra.z)
                                        : weighted_pair<false>(P.y, W, d, rb.w, rb.y, rb.x, rb.z, ra.y, ra.z);

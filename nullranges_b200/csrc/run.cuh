@@ -235,7 +235,7 @@ int launch_rank(nrb200_handle *h, const BootParams &P, bool has_query) {
     }
     if (h->split_ev) cudaEventRecord(h->split_ev, h->stream);  // stats: end of the rows kernel
     if (has_query) {
-        const FeatView F{h->f_src.as<int32_t>(), h->pair_off.as<int32_t>(), h->pair_rec.as<PairRec>()};
+        const FeatView F{h->f_src.as<int32_t>(), h->pair_off.as<int32_t>(), h->pair_rec.as<int4>(), h->pair_rec.as<int4>() + h->n_pairs};
         const dim3 grid((unsigned)((P.n_query + 255) / 256), gy);
         switch (variant) {
         case 11: boot_rank_count_kernel<1, 1><<<grid, 256, 0, h->stream>>>(P, F); break;
