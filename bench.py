@@ -175,13 +175,6 @@ class ClockSampler(threading.Thread):
 # ---------------------------------------------------------------------------------------------
 # GPU arm
 # ---------------------------------------------------------------------------------------------
-class DevView:
-    """Zero-copy torch view of a device buffer owned by libnrb200."""
-
-    def __init__(self, ptr, n, typestr):
-        self.__cuda_array_interface__ = {"shape": (n,), "typestr": typestr, "data": (ptr, False), "version": 2}
-
-
 def pinned(shape, dtype):
     import torch
     t = torch.empty(shape, dtype=dtype, pin_memory=True)
@@ -193,6 +186,7 @@ def run_gpu(args):
     import torch.distributed as dist
 
     from nullranges_b200 import Draws, Engine, _lib, bootCounts
+    from nullranges_b200.sharding import resident_tensors
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -229,9 +223,8 @@ def run_gpu(args):
         step's kernels; wait_gathers() (inside the next step's timed bracket) accounts for it."""
         if world == 1:
             return
-        nr_p, tot_p, _ = eng.resident_pointers()
-        mine = torch.stack([torch.as_tensor(DevView(nr_p, R, "<i8"), device="cuda"),
-                            torch.as_tensor(DevView(tot_p, R, "<i8"), device="cuda")])  # staging copy: the engine reuses its buffers
+        views = resident_tensors(eng, R, 0)
+        mine = torch.stack([views["iter_nranges"], views["iter_totals"]])  # staging copy: the engine reuses its buffers
         out = torch.empty((world * 2, R), dtype=mine.dtype, device="cuda")
         pending.append((dist.all_gather_into_tensor(out, mine, async_op=True), out))
 

@@ -1,5 +1,7 @@
-"""BASELINE configs 4 and 5 on N GPUs of one box (torchrun, one process per GPU, NCCL).
+"""BASELINE configs 2 (sharded, matrix gathered), 4 and 5 on N GPUs of one box (torchrun, one process per GPU, NCCL).
 
+  cfg 2: R = 1000 iterations sharded over the ranks; every rank ends up with the whole [R x 20k] count matrix on its
+         GPU: one all-gather of the [R/N x G] tiles, device to device, straight out of the engine's buffers.
   cfg 4: 10M points, withinChrom=TRUE, 200k enhancers, R = 10^4 iterations sharded over the ranks;
          per-feature moments (sum, sum^2, #>=observed) all-reduced, per-iteration totals all-gathered.
   cfg 5: blockLength in {1e5, 2e5, 5e5, 1e6} x R = 1000 on 1M ranges: the four block lengths are spread
@@ -14,7 +16,7 @@ import numpy as np
 import torch
 import torch.distributed as dist
 from nullranges_b200 import Draws, Engine, _lib, synth
-from nullranges_b200.sharding import gather_iteration_vectors, shard_iterations
+from nullranges_b200.sharding import allreduce_moments, gather_count_matrix, gather_iteration_vectors, resident_tensors, shard_iterations
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--config", type=int, default=4)
@@ -27,7 +29,9 @@ if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
 if world > 1:
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 dev = torch.device("cuda", local)
-eng = Engine(local)
+stream = torch.cuda.Stream(device=dev)   # one stream for the engine's kernels AND the collectives that read its buffers
+torch.cuda.set_stream(stream)
+eng = Engine(local, stream=stream.cuda_stream)
 
 
 def barrier():
@@ -36,7 +40,45 @@ def barrier():
     torch.cuda.synchronize()
 
 
-if args.config == 4:
+if args.config == 2:
+    R = args.iters or 1000
+    y, x = synth.atac_peaks(1_000_000, seed=3), synth.genes(20_000, seed=2)
+    eng.set_ranges(y.seqlengths, y.seqid, y.start, y.end)
+    eng.set_query(x.seqid, x.start, x.end)
+    B = eng.set_plan(_lib.UNSEG_ACROSS, 500_000)
+    G = len(x)
+    iter0, n = shard_iterations(R, world, rank)
+
+    def step(seed):
+        eng.run_counts_resident(Draws(n_iter=n, seed=seed, iter0=iter0), True, False)
+        tile = resident_tensors(eng, n, G)["feature_counts"]
+        return gather_count_matrix(tile, R) if world > 1 else tile
+
+    for s_ in range(3):
+        step(100 + s_)
+    barrier()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    steps = 10
+    ev[0].record()
+    for s_ in range(steps):
+        full = step(s_)
+    ev[1].record()
+    barrier()
+    ms = ev[0].elapsed_time(ev[1]) / steps
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    # every rank holds the same matrix; its checksum does not depend on the number of GPUs
+    chk = torch.tensor([int(full.sum()), int((full.to(torch.int64) * torch.arange(1, G + 1, device=dev)).sum() % (1 << 61))], device=dev)
+    same = chk.clone()
+    if world > 1:
+        dist.all_reduce(same, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        print(json.dumps({"config": "cfg2 R=1000 sharded, [R x 20k] matrix all-gathered on every GPU", "n_gpus": world, "iters": R,
+                          "ms_per_1000_iterations": float(t[0]), "iters_per_s": R / float(t[0]) * 1e3,
+                          "matrix_bytes": int(full.numel() * 4), "checksum": [int(v) for v in chk.tolist()],
+                          "ranks_agree": bool((same == chk).all())}))
+elif args.config == 4:
     R = args.iters or 10_000
     y, x = synth.points(10_000_000, seed=6), synth.enhancers(200_000, seed=7)
     eng.set_ranges(y.seqlengths, y.seqid, y.start, y.end)
@@ -53,7 +95,7 @@ if args.config == 4:
     m = eng.run_moments(Draws(n_iter=n, seed=7, iter0=iter0), observed=obs)
     mom = torch.from_numpy(np.stack([m["sum"], m["sumsq"], m["n_ge_observed"]])).to(dev)
     if world > 1:
-        dist.all_reduce(mom)                                   # 3 x G x 8 bytes over NVLink
+        allreduce_moments(mom)                                 # 3 x G x 8 bytes over NVLink
         tot = gather_iteration_vectors({"iter_totals": m["iter_totals"], "iter_nranges": m["iter_nranges"]}, R, device=dev)
     else:
         tot = {"iter_totals": m["iter_totals"], "iter_nranges": m["iter_nranges"]}

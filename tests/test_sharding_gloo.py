@@ -32,8 +32,14 @@ def _worker(rank, world, port, R, q):
     dist.init_process_group("gloo", rank=rank, world_size=world)
     case = H.random_case(seed=77, n=400, n_seq=3, n_query=30)
     plan, y, qi, _ = H.oracle_objects(case, 0)
-    out = boot_counts_sharded(lambda i0, n: O.boot_counts(plan, y, qi, n, seed=99, iter0=i0), R)
-    q.put((rank, out["iter_totals"], out["iter_nranges"], out["local_iter0"], out["local_feature_counts"]))
+    out = boot_counts_sharded(lambda i0, n: O.boot_counts(plan, y, qi, n, seed=99, iter0=i0), R, gather_matrix=True)
+    import torch
+    from nullranges_b200.sharding import allreduce_moments
+    fc = torch.as_tensor(out["local_feature_counts"]).to(torch.int64)
+    m1, m2 = fc.sum(0), (fc * fc).sum(0)
+    allreduce_moments(m1, m2)
+    q.put((rank, out["iter_totals"], out["iter_nranges"], out["local_iter0"], out["local_feature_counts"], out["feature_counts"],
+           m1.numpy(), m2.numpy()))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -58,6 +64,9 @@ def test_sharded_equals_unsharded_gloo(R):
     case = H.random_case(seed=77, n=400, n_seq=3, n_query=30)
     plan, y, qi, _ = H.oracle_objects(case, 0)
     ref = O.boot_counts(plan, y, qi, R, seed=99, iter0=0)
-    for rank, tot, nr, i0, fc in got:
+    full = ref["feature_counts"].astype(np.int64)
+    for rank, tot, nr, i0, fc, matrix, m1, m2 in got:
         assert np.array_equal(tot, ref["iter_totals"]) and np.array_equal(nr, ref["iter_nranges"])
         assert np.array_equal(fc, ref["feature_counts"][i0 : i0 + fc.shape[0]])
+        assert np.array_equal(matrix, ref["feature_counts"])          # all-gathered tiles, global iteration order
+        assert np.array_equal(m1, full.sum(0)) and np.array_equal(m2, (full * full).sum(0))  # all-reduced moments
