@@ -662,3 +662,23 @@ def test_set_ranges_in_two_halves(engine):
         engine.finish_ranges()
     with pytest.raises(EngineError):
         engine.set_plan(_lib.UNSEG_ACROSS, case["L_b"])  # no ranges: a failed _end leaves the handle without y
+
+
+def test_resident_tensors_view_the_engine_buffers():
+    """sharding.resident_tensors(): zero-copy torch views of the device-resident results equal what run_counts copies out."""
+    import torch
+    from nullranges_b200 import Engine
+    from nullranges_b200.sharding import resident_tensors
+    case = H.random_case(seed=31, n=2000, n_query=150)
+    stream = torch.cuda.Stream()
+    with torch.cuda.stream(stream):
+        eng = Engine(0, stream=stream.cuda_stream)
+        H.load_engine(eng, case, 0)
+        d = Draws(n_iter=7, seed=5)
+        want = eng.run_counts(d)
+        eng.run_counts_resident(d, True, False)
+        views = resident_tensors(eng, 7)
+        got = {k: v.cpu().numpy() for k, v in views.items()}
+        eng.close()
+    for k in ("iter_totals", "iter_nranges", "feature_counts"):
+        np.testing.assert_array_equal(got[k], want[k])
