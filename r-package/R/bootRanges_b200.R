@@ -129,7 +129,8 @@ bootRanges <- function(y, blockLength, R = 1, seg = NULL, exclude = NULL, exclud
   mc <- S4Vectors::mcols(y)[src, , drop = FALSE]
   mc$block <- NULL
   S4Vectors::mcols(br) <- mc
-  S4Vectors::mcols(br)$iter <- S4Vectors::Rle(factor(rep(seq_len(R), res[[1]]), levels = seq_len(R)))
+  # Rle(factor(rep(seq_len(R), lens))) of R/bootRanges.R:122, built from (values, run lengths): no per-row work
+  S4Vectors::mcols(br)$iter <- S4Vectors::Rle(factor(seq_len(R), levels = seq_len(R)), res[[1]])
   if (storeBlockLength) S4Vectors::mcols(br)$blockLength <- S4Vectors::Rle(as.integer(blockLength), length(br))
   new("BootRanges", br)
 }
