@@ -26,6 +26,8 @@ R_KNOWN = {
         {"seed": 1, "n": 5, "value": [0.2655087, 0.3721239, 0.5728534, 0.9082078, 0.2016819]},
         {"seed": 42, "n": 3, "value": [0.9148060, 0.9370754, 0.2861395]},
         {"seed": 123, "n": 3, "value": [0.2875775, 0.7883051, 0.4089769]},
+        {"seed": 2, "n": 3, "value": [0.1848823, 0.7023740, 0.5733263]},
+        {"seed": 10, "n": 3, "value": [0.5074782, 0.3067685, 0.4269077]},
     ],
     "sample": [
         {"seed": 1, "n": 10, "size": 10, "value": [9, 4, 7, 1, 2, 5, 3, 10, 6, 8]},
@@ -33,6 +35,7 @@ R_KNOWN = {
         {"seed": 123, "n": 5, "size": 5, "value": [3, 2, 5, 4, 1]},
         {"seed": 123, "n": 10, "size": 10, "value": [3, 10, 2, 8, 6, 9, 1, 7, 5, 4]},
         {"seed": 1, "n": 100, "size": 5, "value": [68, 39, 1, 34, 87]},
+        {"seed": 1, "n": 5, "size": 5, "replace": True, "value": [1, 4, 1, 2, 5]},   # sample(1:5, 5, replace = TRUE)
     ],
     "philox4x32_10": [
         {"ctr": [0, 0, 0, 0], "key": [0, 0], "value": [0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8]},

@@ -20,7 +20,7 @@ def test_r_runif_known_answers(case):
 
 @pytest.mark.parametrize("case", KNOWN["sample"])
 def test_r_sample_known_answers(case):
-    assert O.RRng(case["seed"]).sample(case["n"], case["size"]).tolist() == case["value"]
+    assert O.RRng(case["seed"]).sample(case["n"], case["size"], bool(case.get("replace", False))).tolist() == case["value"]
 
 
 @pytest.mark.parametrize("case", KNOWN["philox4x32_10"])
