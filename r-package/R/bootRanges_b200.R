@@ -123,7 +123,10 @@ bootRanges <- function(y, blockLength, R = 1, seg = NULL, exclude = NULL, exclud
     for (k in 2:6) res[[k]] <- res[[k]][o]
   }
   src <- res[[5]]
-  br <- GenomicRanges::GRanges(S4Vectors::Rle(factor(s$lv[res[[2]] + 1L], levels = s$lv)),
+  sn <- res[[2]] + 1L                       # integer codes straight into a factor: no per-row strings
+  attr(sn, "levels") <- s$lv
+  class(sn) <- "factor"
+  br <- GenomicRanges::GRanges(S4Vectors::Rle(sn),
                                IRanges::IRanges(res[[3]], res[[4]]), strand = GenomicRanges::strand(y)[src],
                                seqinfo = GenomeInfoDb::seqinfo(y))
   mc <- S4Vectors::mcols(y)[src, , drop = FALSE]
