@@ -338,6 +338,7 @@ int run_counts_core(nrb200_handle *h, const nrb200_draws *d, bool want_counts, i
         const bool pageable = cudaPointerGetAttributes(&attr, host_counts) != cudaSuccess || attr.type == cudaMemoryTypeUnregistered;
         cudaGetLastError();  // an unregistered pointer may leave a sticky-free error behind on older drivers
         const size_t bytes = (size_t)R * G * sizeof(int32_t);
+        if (pageable) advise_huge_pages(host_counts, bytes);
         if (pageable && bytes <= kMaxStagingBytes) {
             if (h->stage_cap < bytes) {
                 if (h->stage_buf) cudaFreeHost(h->stage_buf);
