@@ -215,6 +215,13 @@ int nrb200_moments_fetch(nrb200_handle *h, int64_t *feat_sum, int64_t *feat_sums
 int nrb200_set_weights(nrb200_handle *h, const double *weights);
 int nrb200_run_weighted(nrb200_handle *h, const nrb200_draws *draws, double *iter_sums, double *feature_sums,
                         nrb200_stats *stats);
+/* The same without the [n_iter x n_query] matrix: per-feature moments of the weighted sums over the iterations of
+ * this call -- sum_r s[r,g], sum_r s[r,g]^2 (double) and #{r : s[r,g] >= observed[g]} (observed may be NULL) --
+ * enough for the z-scores / empirical p-values of vignettes/bootRanges.Rmd:540-560 at any number of iterations.
+ * Every output pointer may be NULL.  Accumulate over calls on the host if wanted. */
+int nrb200_run_weighted_moments(nrb200_handle *h, const nrb200_draws *draws, const double *observed,
+                                double *iter_sums, double *feat_sum, double *feat_sumsq,
+                                int64_t *feat_n_ge_observed, nrb200_stats *stats);
 
 /* countOverlaps(x, y) on the ORIGINAL ranges (the observed statistic,
  * vignettes/bootRanges.Rmd:482-483). */

@@ -6,11 +6,11 @@ excludeOption, proportionLength, type, withinChrom, storeBlockLength)`` returnin
 The compute path is libnrb200.so (hand-written sm_100a CUDA behind include/nrb200.h);
 there is no CPU fallback.
 """
-from .bootranges import BootCounts, bootCounts, bootRanges
+from .bootranges import BootCounts, BootMoments, bootCounts, bootMoments, bootRanges
 from .engine import Draws, Engine, EngineError, get_engine
 from .granges import BootRanges, GRanges
 from .rrng import RRng, set_seed
 from .segment import countOverlaps, oneRegionSegment, segmentTileCounts, tileGenome
 
-__all__ = ["GRanges", "BootRanges", "bootRanges", "bootCounts", "BootCounts", "set_seed", "RRng",
+__all__ = ["GRanges", "BootRanges", "bootRanges", "bootCounts", "BootCounts", "bootMoments", "BootMoments", "set_seed", "RRng",
            "Engine", "EngineError", "Draws", "get_engine", "countOverlaps", "segmentTileCounts", "tileGenome", "oneRegionSegment"]

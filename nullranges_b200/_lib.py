@@ -67,6 +67,7 @@ SYMBOLS = [
     ("nrb200_moments_fetch", C.c_int, [vp, i64p, i64p, i64p]),
     ("nrb200_set_weights", C.c_int, [vp, dp]),
     ("nrb200_run_weighted", C.c_int, [vp, C.POINTER(Draws), dp, dp, C.POINTER(Stats)]),
+    ("nrb200_run_weighted_moments", C.c_int, [vp, C.POINTER(Draws), dp, dp, dp, dp, i64p, C.POINTER(Stats)]),
     ("nrb200_count_observed", C.c_int, [vp, i32p, i64p]),
     ("nrb200_count_observed_ex", C.c_int, [vp, C.c_int32, i32p, i64p]),
     ("nrb200_run_materialize", C.c_int, [vp, C.POINTER(Draws), i64p, C.POINTER(Stats)]),

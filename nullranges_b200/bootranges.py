@@ -220,3 +220,54 @@ def bootCounts(y: GRanges, x: GRanges, blockLength, R: int = 1, seg: GRanges | N
             fs = full
         bc.iter_sums, bc.feature_sums = ws["iter_sums"], fs
     return bc
+
+
+@dataclass
+class BootMoments:
+    """Per-feature summary of the bootstrap distribution of a statistic, without the [R, G] matrix."""
+    n_iter: int
+    mean: np.ndarray                  # [length(x)]
+    sd: np.ndarray                    # sample standard deviation over the iterations
+    observed: np.ndarray | None       # the statistic on y itself (counts: countOverlaps(x, y); weights: as given)
+    z: np.ndarray | None              # (observed - mean) / sd
+    p_ge: np.ndarray | None           # empirical P(bootstrap >= observed) = (#{>=} + 1) / (R + 1)
+    sum: np.ndarray
+    sumsq: np.ndarray
+    stats: dict
+
+
+def bootMoments(y: GRanges, x: GRanges, blockLength, R: int = 1, seg: GRanges | None = None,
+                exclude: GRanges | None = None, excludeOption=("drop", "trim"), proportionLength: bool = True,
+                type=("bootstrap", "permute"), withinChrom: bool = False, *, rng="philox", seed=None, iter0: int = 0,
+                device: int = 0, maxgap: int = -1, minoverlap: int = 0, weights: str | None = None,
+                observed=None) -> BootMoments:
+    """Mean / sd / z-score / empirical p-value per feature of countOverlaps(x, boots) -- or, with ``weights``, of the
+    sum of that metadata column over the overlapping bootstrapped ranges -- over R iterations, accumulated on the GPU
+    (the summary the vignette computes from the per-iteration table, vignettes/bootRanges.Rmd:497-560; no R x G
+    matrix, so R = 10^4 with 10^5 features is fine).  observed: the statistic on the original ranges; for counts it
+    defaults to countOverlaps(x, y), for weights it has to be given to get z and p."""
+    eng, kind, L_b, segd, qkeep = _setup(y, blockLength, seg, exclude, excludeOption, proportionLength, type, withinChrom, device,
+                                         query=(x, maxgap, minoverlap))
+    if qkeep is not None:
+        raise ValueError("bootMoments needs every seqlevel of x to be a seqlevel of y")
+    draws = _make_draws(eng, kind, int(R), y, L_b, segd, rng, seed, iter0)
+    if weights is None:
+        obs = eng.count_observed(minoverlap=minoverlap)[0] if observed is None else np.asarray(observed, dtype=np.int32)
+        m = eng.run_moments(draws, observed=obs)
+    else:
+        if weights not in y.mcols:
+            raise ValueError(f"{weights!r} is not a metadata column of y")
+        eng.set_weights(y.mcols[weights])
+        obs = None if observed is None else np.asarray(observed, dtype=np.float64)
+        m = eng.run_weighted_moments(draws, observed=obs)
+    n = int(R)
+    s, q = m["sum"].astype(np.float64), m["sumsq"].astype(np.float64)
+    mean = s / max(n, 1)
+    var = np.maximum(q - n * mean * mean, 0.0) / max(n - 1, 1)
+    sd = np.sqrt(var)
+    z = p = None
+    if obs is not None:
+        with np.errstate(divide="ignore", invalid="ignore"):
+            z = (obs - mean) / sd
+        p = (m["n_ge_observed"] + 1.0) / (n + 1.0)
+    return BootMoments(n, mean, sd, obs, z, p, m["sum"], m["sumsq"], m["stats"])

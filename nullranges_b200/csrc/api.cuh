@@ -391,7 +391,14 @@ int nrb200_set_weights(nrb200_handle *h, const double *weights) {
     return NRB200_OK;
 }
 
-int nrb200_run_weighted(nrb200_handle *h, const nrb200_draws *draws, double *iter_sums, double *feature_sums, nrb200_stats *stats) {
+struct WeightedMoments {      // per-feature moments of the weighted sums over the iterations of one call (all optional)
+    const double *observed;
+    double *sum, *sumsq;
+    int64_t *n_ge;
+};
+
+static int run_weighted_core(nrb200_handle *h, const nrb200_draws *draws, double *iter_sums, double *feature_sums,
+                             const WeightedMoments *mom, nrb200_stats *stats) {
     if (!h || !draws) return NRB200_ERR_INVALID;
     NRB_CUDA(h, cudaSetDevice(h->device));
     int rc;
@@ -412,6 +419,13 @@ int nrb200_run_weighted(nrb200_handle *h, const nrb200_draws *draws, double *ite
     NRB_CUDA(h, cudaMemsetAsync(h->d_iter_nranges.p, 0, R * 8, h->stream));
     if ((rc = hits_reset(h))) return rc;
     NRB_CUDA(h, cudaMemsetAsync(h->ws_iter.p, 0, R * 8, h->stream));
+    if (mom) {
+        for (DevMem *m : {&h->wm_sum, &h->wm_sumsq, &h->wm_nge}) {
+            NRB_CUDA(h, m->reserve((size_t)G * 8));
+            NRB_CUDA(h, cudaMemsetAsync(m->p, 0, (size_t)G * 8, h->stream));
+        }
+        if (mom->observed && (rc = upload(h, h->wm_observed, mom->observed, (size_t)G))) return rc;
+    }
     BootParams P = make_params(h, draws);
     P.iter_nranges = h->d_iter_nranges.as<unsigned long long>();
     P.n_hits = h->d_n_hits.as<unsigned long long>();
@@ -429,11 +443,23 @@ int nrb200_run_weighted(nrb200_handle *h, const nrb200_draws *draws, double *ite
                                                                                                      h->ws_iter.as<double>() + r0);
         ++launches;
         NRB_CUDA(h, cudaGetLastError());
+        if (mom) {
+            accumulate_moments_f64_kernel<<<(unsigned)((G + 255) / 256), 256, 0, h->stream>>>(
+                h->ws_sums.as<double>(), n, G, mom->observed ? h->wm_observed.as<double>() : nullptr, h->wm_sum.as<double>(),
+                h->wm_sumsq.as<double>(), h->wm_nge.as<long long>());
+            ++launches;
+            NRB_CUDA(h, cudaGetLastError());
+        }
         if (feature_sums)
             NRB_CUDA(h, cudaMemcpyAsync(feature_sums + r0 * G, h->ws_sums.p, (size_t)n * G * 8, cudaMemcpyDeviceToHost, h->stream));
     }
     NRB_CUDA(h, cudaEventRecord(h->ev[2], h->stream));
     if (iter_sums && R > 0) NRB_CUDA(h, cudaMemcpyAsync(iter_sums, h->ws_iter.p, R * 8, cudaMemcpyDeviceToHost, h->stream));
+    if (mom) {
+        if (mom->sum) NRB_CUDA(h, cudaMemcpyAsync(mom->sum, h->wm_sum.p, (size_t)G * 8, cudaMemcpyDeviceToHost, h->stream));
+        if (mom->sumsq) NRB_CUDA(h, cudaMemcpyAsync(mom->sumsq, h->wm_sumsq.p, (size_t)G * 8, cudaMemcpyDeviceToHost, h->stream));
+        if (mom->n_ge) NRB_CUDA(h, cudaMemcpyAsync(mom->n_ge, h->wm_nge.p, (size_t)G * 8, cudaMemcpyDeviceToHost, h->stream));
+    }
     if ((rc = sync_stream(h))) return rc;
     if (stats) {
         float k_ms = 0, t_ms = 0;
@@ -447,6 +473,16 @@ int nrb200_run_weighted(nrb200_handle *h, const nrb200_draws *draws, double *ite
         stats->d2h_bytes = (feature_sums ? R * G * 8 : 0) + (iter_sums ? R * 8 : 0);
     }
     return NRB200_OK;
+}
+
+int nrb200_run_weighted(nrb200_handle *h, const nrb200_draws *draws, double *iter_sums, double *feature_sums, nrb200_stats *stats) {
+    return run_weighted_core(h, draws, iter_sums, feature_sums, nullptr, stats);
+}
+
+int nrb200_run_weighted_moments(nrb200_handle *h, const nrb200_draws *draws, const double *observed, double *iter_sums,
+                                double *feat_sum, double *feat_sumsq, int64_t *feat_n_ge_observed, nrb200_stats *stats) {
+    const WeightedMoments mom{observed, feat_sum, feat_sumsq, feat_n_ge_observed};
+    return run_weighted_core(h, draws, iter_sums, nullptr, &mom, stats);
 }
 
 int nrb200_count_observed(nrb200_handle *h, int32_t *feature_counts, int64_t *total) {

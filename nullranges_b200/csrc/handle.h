@@ -234,6 +234,7 @@ struct nrb200_handle {
     bool res_has_counts = false;
     // moments
     DevMem m_sum, m_sumsq, m_nge, m_observed;
+    DevMem wm_sum, wm_sumsq, wm_nge, wm_observed;  // moments of the weighted sums (double; n_ge int64)
     bool moments_ready = false;
     // rows
     DevMem item_rec, item_rows, within_off, iter_off_dev, row_seq, row_start, row_end, row_src, row_block;

@@ -391,4 +391,25 @@ __global__ void accumulate_moments_kernel(const int32_t *__restrict__ counts, in
     n_ge[g] += ge;
 }
 
+// The same for the weighted sums (double): sequential over the batch's iterations, so the result does not depend on
+// the launch shape.
+__global__ void accumulate_moments_f64_kernel(const double *__restrict__ sums, int64_t n_iter, int64_t n_query,
+                                              const double *__restrict__ observed, double *__restrict__ sum,
+                                              double *__restrict__ sumsq, long long *__restrict__ n_ge) {
+    const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= n_query) return;
+    double s = 0.0, q = 0.0;
+    long long ge = 0;
+    const double obs = observed ? observed[g] : 0.0;
+    for (int64_t r = 0; r < n_iter; ++r) {
+        const double v = sums[r * n_query + g];
+        s += v;
+        q += v * v;
+        ge += (observed && v >= obs) ? 1 : 0;
+    }
+    sum[g] += s;
+    sumsq[g] += q;
+    n_ge[g] += ge;
+}
+
 }  // namespace nrb

@@ -196,6 +196,19 @@ class Engine:
         self._check(self._lib.nrb200_run_weighted(self._h, C.byref(d), ptr(it, C.c_double), ptr(fs, C.c_double), C.byref(st)))
         return {"iter_sums": it, "feature_sums": fs, "stats": st.as_dict()}
 
+    def run_weighted_moments(self, draws: Draws, observed=None) -> dict:
+        """Per-feature moments of the weighted sums over the iterations (no [R, G] matrix): sum, sum of squares and,
+        with observed, #{iterations with sum >= observed}."""
+        R, G = int(draws.n_iter), self.n_query
+        it = np.zeros(R, np.float64)
+        s, q, ge = np.zeros(G, np.float64), np.zeros(G, np.float64), np.zeros(G, np.int64)
+        obs = None if observed is None else np.ascontiguousarray(observed, dtype=np.float64)
+        st = _lib.Stats()
+        d = draws.to_c()
+        self._check(self._lib.nrb200_run_weighted_moments(self._h, C.byref(d), ptr(obs, C.c_double), ptr(it, C.c_double), ptr(s, C.c_double),
+                                                          ptr(q, C.c_double), ptr(ge, C.c_int64), C.byref(st)))
+        return {"iter_sums": it, "sum": s, "sumsq": q, "n_ge_observed": ge, "stats": st.as_dict()}
+
     def count_observed(self, minoverlap: int = 0):
         """countOverlaps(query, y[, minoverlap]) on the ranges as given (no bootstrap)."""
         cnt = np.zeros(self.n_query, np.int32)

@@ -177,6 +177,34 @@ SEXP nrb200_R_run_weighted(SEXP ptr, SEXP weights, SEXP n_iter, SEXP iter0, SEXP
     return out;
 }
 
+/* per-feature moments of the weighted sums, no [G x R] matrix: list(iter_sums = double[R], sum = double[G],
+ * sumsq = double[G], n_ge = double[G] (counts of iterations; exact in a double)).  observed: double[G] or NULL. */
+SEXP nrb200_R_run_weighted_moments(SEXP ptr, SEXP weights, SEXP observed, SEXP n_iter, SEXP iter0, SEXP seed, SEXP bait_seqid,
+                                   SEXP bait_start, SEXP dst_tile, SEXP n_query) {
+    for (R_xlen_t i = 0, n = XLENGTH(weights); i < n; i++)
+        if (ISNA(REAL(weights)[i])) Rf_error("weights contain NA");
+    check(H(ptr), nrb200_set_weights(H(ptr), REAL(weights)));
+    nrb200_draws d;
+    fill_draws(&d, n_iter, iter0, seed, bait_seqid, bait_start, dst_tile);
+    const R_xlen_t R = (R_xlen_t)d.n_iter, G = (R_xlen_t)Rf_asReal(n_query);
+    if (observed != R_NilValue && XLENGTH(observed) != G) Rf_error("observed must have one value per feature");
+    SEXP out = PROTECT(Rf_allocVector(VECSXP, 4));
+    SEXP it = Rf_allocVector(REALSXP, R);
+    SET_VECTOR_ELT(out, 0, it);
+    SEXP sum = Rf_allocVector(REALSXP, G);
+    SET_VECTOR_ELT(out, 1, sum);
+    SEXP sumsq = Rf_allocVector(REALSXP, G);
+    SET_VECTOR_ELT(out, 2, sumsq);
+    SEXP nge = Rf_allocVector(REALSXP, G);
+    SET_VECTOR_ELT(out, 3, nge);
+    int64_t *ge = (int64_t *)R_alloc(G ? G : 1, sizeof(int64_t));
+    check(H(ptr), nrb200_run_weighted_moments(H(ptr), &d, observed == R_NilValue ? NULL : REAL(observed), REAL(it), REAL(sum),
+                                              REAL(sumsq), ge, NULL));
+    for (R_xlen_t g = 0; g < G; g++) REAL(nge)[g] = (double)ge[g];
+    UNPROTECT(1);
+    return out;
+}
+
 /* materialising path: list(lens = double[R], seqid, start, end, src_idx (1-based), block (1-based)) */
 SEXP nrb200_R_run_materialize(SEXP ptr, SEXP n_iter, SEXP iter0, SEXP seed, SEXP bait_seqid, SEXP bait_start, SEXP dst_tile) {
     nrb200_draws d;
@@ -207,6 +235,7 @@ static const R_CallMethodDef call_methods[] = {
     {"nrb200_R_set_plan", (DL_FUNC)&nrb200_R_set_plan, 7},
     {"nrb200_R_run_counts", (DL_FUNC)&nrb200_R_run_counts, 9},
     {"nrb200_R_run_weighted", (DL_FUNC)&nrb200_R_run_weighted, 10},
+    {"nrb200_R_run_weighted_moments", (DL_FUNC)&nrb200_R_run_weighted_moments, 10},
     {"nrb200_R_run_materialize", (DL_FUNC)&nrb200_R_run_materialize, 7},
     {NULL, NULL, 0}};
 

@@ -682,3 +682,61 @@ def test_resident_tensors_view_the_engine_buffers():
         eng.close()
     for k in ("iter_totals", "iter_nranges", "feature_counts"):
         np.testing.assert_array_equal(got[k], want[k])
+
+
+def test_weighted_moments_equal_the_matrix_moments():
+    """nrb200_run_weighted_moments(): per-feature sum / sum of squares / #{>= observed} of the weighted sums equal the
+    moments of the [R, G] matrix nrb200_run_weighted() returns, across launch batches (R > NRB200_MAX_BATCH), and unit
+    weights reproduce the integer moments of the counts."""
+    from nullranges_b200 import Engine
+    case = H.random_case(seed=41, n=3000, n_seq=3, n_query=90, wmax=120)
+    eng = Engine(0)
+    H.load_engine(eng, case, 0)
+    w = np.random.default_rng(3).gamma(2.0, 3.0, case["y"][0].size)
+    eng.set_weights(w)
+    R = 2500  # two launch batches
+    d = Draws(n_iter=R, seed=17)
+    full = eng.run_weighted(d)
+    fs = full["feature_sums"]
+    obs = np.quantile(fs, 0.9, axis=0)
+    got = eng.run_weighted_moments(d, observed=obs)
+    assert np.allclose(got["sum"], fs.sum(0), rtol=1e-9)
+    assert np.allclose(got["sumsq"], (fs * fs).sum(0), rtol=1e-9)
+    assert np.array_equal(got["n_ge_observed"], (fs >= obs).sum(0))
+    assert np.allclose(got["iter_sums"], full["iter_sums"], rtol=1e-12)
+    eng.set_weights(np.ones_like(w))
+    ones = eng.run_weighted_moments(d)
+    mom = eng.run_moments(d)
+    assert np.array_equal(ones["sum"], mom["sum"].astype(np.float64)) and np.array_equal(ones["sumsq"], mom["sumsq"].astype(np.float64))
+    assert not ones["n_ge_observed"].any()
+    eng.close()
+
+
+def test_boot_moments_front_end():
+    """bootMoments(): mean / sd / z / empirical p per feature equal what the [R, G] matrix of bootCounts() gives."""
+    from nullranges_b200 import GRanges, bootCounts, bootMoments, countOverlaps
+    rng = np.random.default_rng(5)
+    lv, L = ["chr1", "chr2"], {"chr1": 60000, "chr2": 40000}
+    n = 4000
+    sq = np.sort(rng.integers(0, 2, n))
+    st = rng.integers(1, 39000, n)
+    y = GRanges(np.array(lv, dtype=object)[sq], st, width=rng.integers(20, 200, n), seqlengths=L, score=rng.gamma(2.0, 2.0, n))
+    y = y[np.lexsort((y.end, y.start, y.seqid))]
+    g = 50
+    xs = np.sort(rng.integers(0, 2, g))
+    x = GRanges(np.array(lv, dtype=object)[xs], rng.integers(1, 38000, g), width=rng.integers(100, 1500, g), seqlengths=L)
+    R = 300
+    bc = bootCounts(y, x, 5000, R=R, seed=9, weights="score")
+    bm = bootMoments(y, x, 5000, R=R, seed=9)
+    fc = bc.feature_counts.astype(np.float64)
+    assert np.allclose(bm.mean, fc.mean(0)) and np.allclose(bm.sd, fc.std(0, ddof=1))
+    obs = countOverlaps(x, y)
+    assert np.array_equal(bm.observed, obs)
+    assert np.allclose(bm.p_ge, ((fc >= obs).sum(0) + 1) / (R + 1))
+    ok = bm.sd > 0
+    assert np.allclose(bm.z[ok], ((obs - fc.mean(0)) / fc.std(0, ddof=1))[ok])
+    fs = bc.feature_sums
+    target = np.median(fs, axis=0)
+    bw = bootMoments(y, x, 5000, R=R, seed=9, weights="score", observed=target)
+    assert np.allclose(bw.mean, fs.mean(0), rtol=1e-9) and np.allclose(bw.sd, fs.std(0, ddof=1), rtol=1e-6)
+    assert np.allclose(bw.p_ge, ((fs >= target).sum(0) + 1) / (R + 1))
