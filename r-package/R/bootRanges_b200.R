@@ -169,3 +169,29 @@ bootCounts <- function(y, x, blockLength, R = 1, seg = NULL, exclude = NULL, exc
   }
   out
 }
+
+# Per-feature mean / sd / z / empirical p of the weighted statistic over R iterations, reduced on the GPU (no G x R
+# matrix): the summary vignettes/bootRanges.Rmd:532-560 computes from the per-iteration table.  observed: the statistic
+# on y itself (numeric, one value per feature of x), or NULL for mean and sd only.
+bootWeightedMoments <- function(y, x, blockLength, weights, R = 1, observed = NULL, seg = NULL, exclude = NULL,
+                                excludeOption = c("drop", "trim"), proportionLength = TRUE, type = c("bootstrap", "permute"),
+                                withinChrom = FALSE, rng = c("philox", "R"), seed = 0, iter0 = 0, maxgap = -1L, minoverlap = 0L,
+                                device = 0L) {
+  excludeOption <- match.arg(excludeOption); type <- match.arg(type); rng <- match.arg(rng)
+  s <- .setup(y, blockLength, seg, exclude, excludeOption, proportionLength, type, withinChrom, device)
+  stopifnot("every seqlevel of x must be a seqlevel of y" = all(as.character(GenomicRanges::seqnames(x)) %in% s$lv))
+  .Call("nrb200_R_set_query", s$h, .seqid(x, s$lv), GenomicRanges::start(x), GenomicRanges::end(x), .strand_code(x),
+        as.integer(maxgap), as.integer(minoverlap))
+  d <- .draws(s, R, blockLength, rng)
+  w <- as.numeric(S4Vectors::mcols(y)[[weights]])
+  m <- .Call("nrb200_R_run_weighted_moments", s$h, w, if (is.null(observed)) NULL else as.numeric(observed), as.numeric(R),
+             as.numeric(iter0), as.numeric(seed), d[[1]], d[[2]], d[[3]], as.numeric(length(x)))
+  mean <- m[[2]] / R
+  sd <- sqrt(pmax(m[[3]] - R * mean^2, 0) / max(R - 1, 1))
+  out <- list(iter_sums = m[[1]], mean = mean, sd = sd)
+  if (!is.null(observed)) {
+    out$z <- (observed - mean) / sd
+    out$p_ge <- (m[[4]] + 1) / (R + 1)
+  }
+  out
+}
