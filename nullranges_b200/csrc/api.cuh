@@ -214,13 +214,32 @@ int nrb200_set_plan(nrb200_handle *h, const nrb200_plan_spec *spec, int64_t *n_b
                  o_sso = put64(pl.state_seg_off), o_sl = put64(pl.state_len), o_sbl = put64(pl.state_block_len),
                  o_sgc = put64(pl.sg_cum);
     const size_t o_sq = put32(pl.sg_seq), o_ss = put32(pl.sg_start), o_st = put32(pl.sg_tiles);
+    // coarse pick tables (philox.cuh, pick_by_length_tab): [0] over the sequences, [st] over the segments of state st
+    std::vector<int32_t> pick_tab((size_t)(pl.n_states + 1) * kPickBuckets, 0), pick_shift(pl.n_states + 1, 0);
+    auto make_pick = [&](int slot, const int64_t *cum, int n, int64_t total) {
+        int shift = 0;
+        while ((total >> shift) >= kPickBuckets) ++shift;
+        pick_shift[slot] = shift;
+        int i = 0;
+        for (int k = 0; k < kPickBuckets; ++k) {
+            const int64_t at = (int64_t)k << shift;
+            while (i + 1 < n && cum[i + 1] <= at) ++i;
+            pick_tab[(size_t)slot * kPickBuckets + k] = i;
+        }
+    };
+    make_pick(0, pl.seq_cum.data(), pl.n_seq, pl.genome_length);
+    for (int st = 1; st <= pl.n_states; ++st) {
+        const int64_t first = pl.state_seg_off[st];
+        make_pick(st, pl.sg_cum.data() + first, (int)(pl.state_seg_off[st + 1] - first), pl.state_len[st]);
+    }
+    const size_t o_pt = put32(pick_tab), o_ps = put32(pick_shift);
     if ((rc = upload(h, h->sampler_i64, i64.data(), i64.size()))) return rc;
     if ((rc = upload(h, h->sampler_i32, i32.data(), i32.size()))) return rc;
     const int64_t *b64 = h->sampler_i64.as<int64_t>();
     const int32_t *b32 = h->sampler_i32.as<int32_t>();
     h->sampler_view = SamplerView{pl.kind, pl.n_seq, pl.n_states, pl.block_length, pl.genome_length,
                                   b64 + o_cum, b64 + o_tps, b64 + o_sbo, b64 + o_sso, b64 + o_sl, b64 + o_sbl,
-                                  b64 + o_sgc, b32 + o_sq, b32 + o_ss, b32 + o_st};
+                                  b64 + o_sgc, b32 + o_sq, b32 + o_ss, b32 + o_st, b32 + o_pt, b32 + o_ps};
     {   // tiles of each sequence by start, for the window lists (build_pairs)
         auto &T = h->tiles_by_seq;
         const int C = h->n_seq;

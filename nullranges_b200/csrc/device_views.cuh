@@ -56,6 +56,7 @@ struct SamplerView {
     const int64_t *state_block_off, *state_seg_off, *state_len, *state_block_len;
     const int64_t *sg_cum;
     const int32_t *sg_seq, *sg_start, *sg_tiles;
+    const int32_t *pick_tab, *pick_shift;  // coarse pick tables (philox.cuh): [0] over seq_cum, [st] over state st's sg_cum
 };
 
 struct BootParams {
@@ -165,8 +166,8 @@ __device__ __forceinline__ void draw_block(const BootParams &P, uint64_t iter, i
     const SamplerView &S = P.sampler;
     const Philox128 u = philox_draw(P.seed, iter, (uint32_t)b, 0u);
     if (S.kind == NRB200_UNSEG_ACROSS) {
-        const int64_t pos = (int64_t)mul_hi_u64(u.lo, (uint64_t)S.genome_length);
-        c = pick_by_length(S.seq_cum, S.n_seq, pos);
+        const int64_t pos = (int64_t)mul_hi_u64_any(u.lo, (uint64_t)S.genome_length);
+        c = pick_by_length_tab(S.seq_cum, S.n_seq, pos, S.pick_tab, S.pick_shift[0]);
         s = (int32_t)rounded_uniform(u.hi, 1, (S.tiles_per_seq[c] - 1) * S.block_length);
     } else if (S.kind == NRB200_UNSEG_WITHIN) {
         c = __ldg(P.tile_seq + b);
@@ -179,8 +180,8 @@ __device__ __forceinline__ void draw_block(const BootParams &P, uint64_t iter, i
         while (st < S.n_states && b >= S.state_block_off[st + 1]) ++st;
         const int64_t first = S.state_seg_off[st];
         const int n = (int)(S.state_seg_off[st + 1] - first);
-        const int64_t pos = (int64_t)mul_hi_u64(u.lo, (uint64_t)S.state_len[st]);
-        const int64_t j = first + pick_by_length(S.sg_cum + first, n, pos);
+        const int64_t pos = (int64_t)mul_hi_u64_any(u.lo, (uint64_t)S.state_len[st]);
+        const int64_t j = first + pick_by_length_tab(S.sg_cum + first, n, pos, S.pick_tab + st * kPickBuckets, S.pick_shift[st]);
         c = S.sg_seq[j];
         s = (int32_t)rounded_uniform(u.hi, S.sg_start[j], (int64_t)(S.sg_tiles[j] - 1) * S.state_block_len[st]);
     }

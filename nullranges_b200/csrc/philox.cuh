@@ -57,11 +57,13 @@ NRB_HD Philox128 philox_draw(uint64_t seed, uint64_t iter, uint32_t element, uin
     return {((uint64_t)c1 << 32) | c0, ((uint64_t)c3 << 32) | c2};
 }
 
+NRB_HD uint64_t mul_hi_u64_any(uint64_t a, uint64_t b);
+
 // round(runif(1, lo, lo + span)) on integers: endpoints carry half the weight of interior
 // points, exactly like rounding a continuous uniform.
 NRB_HD int64_t rounded_uniform(uint64_t bits, int64_t lo, int64_t span) {
     if (span <= 0) return lo;
-    const uint64_t v = mul_hi_u64(bits, (uint64_t)(2 * span));
+    const uint64_t v = mul_hi_u64_any(bits, (uint64_t)(2 * span));
     return lo + (int64_t)((v + 1) >> 1);
 }
 
@@ -77,5 +79,25 @@ NRB_HD int pick_by_length(const int64_t *cum, int n, int64_t pos) {
     }
     return lo;
 }
+
+// The same answer through a coarse table: tab[k] = pick_by_length(cum, n, k << shift) for the kPickBuckets buckets that
+// cover [0, total); a draw then starts at its bucket's entry and walks forward (0 or 1 steps when the elements are wider
+// than a bucket, which chromosomes and segmentation states are), falling back to the search after a few steps.
+constexpr int kPickBuckets = 1024;
+NRB_HD int pick_by_length_tab(const int64_t *cum, int n, int64_t pos, const int32_t *tab, int shift) {
+    int i = tab[pos >> shift];
+    for (int step = 0; i + 1 < n && cum[i + 1] <= pos; ++step) {
+        ++i;
+        if (step == 4) return i + pick_by_length(cum + i, n - i, pos);
+    }
+    return i;
+}
+
+// floor(a * b / 2^64) for b < 2^32 (two 32 x 32 -> 64 multiplies instead of the full 64 x 64 high product); exact.
+NRB_HD uint64_t mul_hi_u64_small(uint64_t a, uint64_t b) {
+    const uint64_t lo = (a & 0xffffffffu) * b, hi = (a >> 32) * b;  // b < 2^32: no overflow
+    return (hi + (lo >> 32)) >> 32;
+}
+NRB_HD uint64_t mul_hi_u64_any(uint64_t a, uint64_t b) { return (b >> 32) ? mul_hi_u64(a, b) : mul_hi_u64_small(a, b); }
 
 }  // namespace nrb
