@@ -288,9 +288,13 @@ struct AddF64 {
 // hits shifted wholly beyond the sequence end.  Requires tile_start <= seqlength for every tile
 // (checked on the host).
 template <int RPT, int MINB>
-__global__ void __launch_bounds__(256, MINB) boot_block_rows_kernel(const BootParams P, const TileExcl X) {
+__global__ void __launch_bounds__(256, MINB) boot_block_rows_kernel(const BootParams P, const TileExcl X, int ipc) {
     const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int64_t r0 = (int64_t)blockIdx.y * RPT;
+    const int lane = threadIdx.x & 31;
+#pragma unroll 1
+  for (int it = 0; it < ipc; ++it) {  // a CTA keeps its 256 blocks for `ipc` iteration groups (fewer, longer-lived CTAs)
+    const int64_t r0 = ((int64_t)blockIdx.y * ipc + it) * RPT;
+    if (r0 >= P.n_iter) break;
     int rows[RPT];
     int hits_sum = 0;
 #pragma unroll
@@ -347,7 +351,6 @@ __global__ void __launch_bounds__(256, MINB) boot_block_rows_kernel(const BootPa
     }
     // every warp adds its share straight to the per-iteration tallies (spread over the iterations' addresses): no
     // shared-memory stage, no barrier, a warp retires as soon as its 32 blocks are done
-    const int lane = threadIdx.x & 31;
 #pragma unroll
     for (int j = 0; j < RPT; ++j) {
         const int s = __reduce_add_sync(kFull, rows[j]);
@@ -355,6 +358,7 @@ __global__ void __launch_bounds__(256, MINB) boot_block_rows_kernel(const BootPa
     }
     hits_sum = __reduce_add_sync(kFull, hits_sum);
     if (lane == 0 && P.n_hits && hits_sum) atomicAdd(P.n_hits + (r0 & (kHitSlots - 1)), (unsigned long long)hits_sum);
+  }
 }
 
 // (seqid << 32 | end) sort keys and their unpacking: the sorted-ends array of the rank path

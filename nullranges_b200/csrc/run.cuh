@@ -226,11 +226,14 @@ int launch_rank(nrb200_handle *h, const BootParams &P, bool has_query) {
     const unsigned gy = (unsigned)((P.n_iter + rpt - 1) / rpt);
     if (P.n_blocks > 0) {
         const TileExcl X{h->excl.n > 0 ? h->tile_x_off.as<int32_t>() : nullptr, h->tile_x_rec.as<int4>()};  // drop: minus, trim: plus
-        const dim3 rows_grid((unsigned)((P.n_blocks + 255) / 256), (unsigned)P.n_iter);
-        if (h->tune_minb_rows >= 8) boot_block_rows_kernel<1, 8><<<rows_grid, 256, 0, h->stream>>>(P, X);
-        else if (h->tune_minb_rows == 6) boot_block_rows_kernel<1, 6><<<rows_grid, 256, 0, h->stream>>>(P, X);
-        else if (h->tune_minb_rows == 5) boot_block_rows_kernel<1, 5><<<rows_grid, 256, 0, h->stream>>>(P, X);
-        else boot_block_rows_kernel<1, 1><<<rows_grid, 256, 0, h->stream>>>(P, X);
+        // iterations a CTA loops over: up to NRB200_ROWS_IPC, as long as the grid still holds a few CTAs per resident slot
+        const int64_t ctas_x = (P.n_blocks + 255) / 256;
+        const int ipc = (int)std::max<int64_t>(1, std::min<int64_t>(h->tune_rows_ipc, P.n_iter * ctas_x / ((int64_t)h->sm_count * 12)));
+        const dim3 rows_grid((unsigned)((P.n_blocks + 255) / 256), (unsigned)((P.n_iter + ipc - 1) / ipc));
+        if (h->tune_minb_rows >= 8) boot_block_rows_kernel<1, 8><<<rows_grid, 256, 0, h->stream>>>(P, X, ipc);
+        else if (h->tune_minb_rows == 6) boot_block_rows_kernel<1, 6><<<rows_grid, 256, 0, h->stream>>>(P, X, ipc);
+        else if (h->tune_minb_rows == 5) boot_block_rows_kernel<1, 5><<<rows_grid, 256, 0, h->stream>>>(P, X, ipc);
+        else boot_block_rows_kernel<1, 1><<<rows_grid, 256, 0, h->stream>>>(P, X, ipc);
         ++launches;
     }
     if (h->split_ev) cudaEventRecord(h->split_ev, h->stream);  // stats: end of the rows kernel
