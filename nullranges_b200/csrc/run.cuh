@@ -316,7 +316,7 @@ int run_counts_core(nrb200_handle *h, const nrb200_draws *d, bool want_counts, i
     P.iter_nranges = h->d_iter_nranges.as<unsigned long long>();
     P.iter_totals = h->d_iter_totals.as<unsigned long long>();
     P.counts = counts;
-    P.n_hits = h->d_n_hits.as<unsigned long long>();
+    P.n_hits = stats ? h->d_n_hits.as<unsigned long long>() : nullptr;  // the H statistic is tallied only when it is asked for
     NRB_CUDA(h, cudaEventRecord(h->ev[1], h->stream));
     int launches = 0;
     const bool pipelined = host_counts && counts && R > 0;
