@@ -287,7 +287,9 @@ struct AddF64 {
 // hits of the bait block minus (where the variant filters width > 0, R/bootUnsegmented.R:189) the
 // hits shifted wholly beyond the sequence end.  Requires tile_start <= seqlength for every tile
 // (checked on the host).
-template <int RPT, int MINB>
+// SIMPLE: one class of y, bootstrap kinds, no exclusion, no table wanted -- the common fused-counts call; the general
+// branches are compiled out.
+template <int RPT, int MINB, bool SIMPLE>
 __global__ void __launch_bounds__(256, MINB) boot_block_rows_kernel(const BootParams P, const TileExcl X, int ipc) {
     const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int lane = threadIdx.x & 31;
@@ -313,28 +315,29 @@ __global__ void __launch_bounds__(256, MINB) boot_block_rows_kernel(const BootPa
                     d.y = __ldg(P.bait_start + flat);
                 }
                 // bootstrap kinds: block b lands on tile b; permute kinds: on the tile the caller drew
-                const int32_t t = P.dst_tile ? __ldg(P.dst_tile + flat) : (int32_t)b;
+                const int32_t t = (!SIMPLE && P.dst_tile) ? __ldg(P.dst_tile + flat) : (int32_t)b;
                 const int32_t ts = __ldg(P.tile_start + t);
                 const int32_t seq_len = (int32_t)__ldg(P.seqlen + __ldg(P.tile_seq + t));
                 if (P.draw_tab) P.draw_tab[(r0 + j) * P.n_blocks + t] = d;  // the count kernel looks draws up by tile
-                if (P.item_rec) {  // materialising: the fill pass streams canonical window [lo, hi) of this block
+                if (!SIMPLE && P.item_rec) {  // materialising: the fill pass streams canonical window [lo, hi) of this block
                     int32_t lo, hi;
                     locate_block(P.y, d.x, d.y, (int64_t)d.y + width - 1, lo, hi);
                     P.item_rec[flat] = make_int4(lo, hi, d.x, d.y);
                 }
                 int hits = 0;
-                for (int cls = 0; cls < P.y.n_cls; ++cls) {  // one pass per strand class of y (one when y is unstranded)
-                    const int4 si = __ldg(P.y.rseq_info + d.x * P.y.n_cls + cls);
+                const int n_cls = SIMPLE ? 1 : P.y.n_cls;
+                for (int cls = 0; cls < n_cls; ++cls) {  // one pass per strand class of y (one when y is unstranded)
+                    const int4 si = __ldg(P.y.rseq_info + d.x * n_cls + cls);
                     const int32_t ie = idx_start_le(P.y, si, d.y + (width - 1));
                     // hits: overlap of the bait block (bootstrap) / start inside the tile (permute)
-                    const int h1 = ie - (P.permute ? idx_start_le(P.y, si, d.y - 1) : idx_end_lt(P.y, si, d.y));
+                    const int h1 = ie - ((!SIMPLE && P.permute) ? idx_start_le(P.y, si, d.y - 1) : idx_end_lt(P.y, si, d.y));
                     int dropped = 0;  // only a tile that overhangs its sequence end can push hits beyond it
                     if (P.drop_zero && ts + (width - 1) > seq_len) dropped = max(0, ie - idx_start_le(P.y, si, seq_len - (ts - d.y)));
                     hits += h1;
-                    if (!P.rows_windows_only) rows[j] += h1 - dropped;
-                    if (X.off) {  // minus the hits that overlap an exclude region after the move ("trim": plus the pieces)
-                        const int32_t x1 = __ldg(X.off + t * P.y.n_cls + cls + 1);
-                        for (int32_t k = __ldg(X.off + t * P.y.n_cls + cls); k < x1; ++k) {
+                    if (SIMPLE || !P.rows_windows_only) rows[j] += h1 - dropped;
+                    if (!SIMPLE && X.off) {  // minus the hits that overlap an exclude region after the move ("trim": plus the pieces)
+                        const int32_t x1 = __ldg(X.off + t * n_cls + cls + 1);
+                        for (int32_t k = __ldg(X.off + t * n_cls + cls); k < x1; ++k) {
                             const int4 w = __ldg(X.rec + k);
                             const int2 dd[1] = {d};
                             int c1[1] = {0};
@@ -345,7 +348,7 @@ __global__ void __launch_bounds__(256, MINB) boot_block_rows_kernel(const BootPa
                     }
                 }
                 hits_sum += hits;
-                if (P.item_rows) P.item_rows[(r0 + j) * P.n_blocks + b] = rows[j];
+                if (!SIMPLE && P.item_rows) P.item_rows[(r0 + j) * P.n_blocks + b] = rows[j];
             }
         }
     }

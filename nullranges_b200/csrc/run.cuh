@@ -230,10 +230,13 @@ int launch_rank(nrb200_handle *h, const BootParams &P, bool has_query) {
         const int64_t ctas_x = (P.n_blocks + 255) / 256;
         const int ipc = (int)std::max<int64_t>(1, std::min<int64_t>(h->tune_rows_ipc, P.n_iter * ctas_x / ((int64_t)h->sm_count * 12)));
         const dim3 rows_grid((unsigned)((P.n_blocks + 255) / 256), (unsigned)((P.n_iter + ipc - 1) / ipc));
-        if (h->tune_minb_rows >= 8) boot_block_rows_kernel<1, 8><<<rows_grid, 256, 0, h->stream>>>(P, X, ipc);
-        else if (h->tune_minb_rows == 6) boot_block_rows_kernel<1, 6><<<rows_grid, 256, 0, h->stream>>>(P, X, ipc);
-        else if (h->tune_minb_rows == 5) boot_block_rows_kernel<1, 5><<<rows_grid, 256, 0, h->stream>>>(P, X, ipc);
-        else boot_block_rows_kernel<1, 1><<<rows_grid, 256, 0, h->stream>>>(P, X, ipc);
+        const bool simple = P.y.n_cls == 1 && !X.off && !P.item_rec && !P.item_rows && !P.permute && !P.dst_tile && !P.rows_windows_only;
+        if (simple && h->tune_minb_rows == 6) boot_block_rows_kernel<1, 6, true><<<rows_grid, 256, 0, h->stream>>>(P, X, ipc);
+        else if (simple && h->tune_minb_rows == 8) boot_block_rows_kernel<1, 8, true><<<rows_grid, 256, 0, h->stream>>>(P, X, ipc);
+        else if (h->tune_minb_rows >= 8) boot_block_rows_kernel<1, 8, false><<<rows_grid, 256, 0, h->stream>>>(P, X, ipc);
+        else if (h->tune_minb_rows == 6) boot_block_rows_kernel<1, 6, false><<<rows_grid, 256, 0, h->stream>>>(P, X, ipc);
+        else if (h->tune_minb_rows == 5) boot_block_rows_kernel<1, 5, false><<<rows_grid, 256, 0, h->stream>>>(P, X, ipc);
+        else boot_block_rows_kernel<1, 1, false><<<rows_grid, 256, 0, h->stream>>>(P, X, ipc);
         ++launches;
     }
     if (h->split_ev) cudaEventRecord(h->split_ev, h->stream);  // stats: end of the rows kernel
