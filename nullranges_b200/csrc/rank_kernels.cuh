@@ -138,9 +138,10 @@ __device__ __forceinline__ void count_pairs(const RangesView &y, const int2 (&d)
 // block-rows kernel wrote.  Features are visited in F's order (grouped by tile count, so a warp's
 // lanes loop the same number of times).  No atomics on the count matrix, no memset: every element
 // is written exactly once.
+constexpr int kCountThreads = 128;  // CTA size of the count kernel: 128 beat 64 / 256 / 512 (0.258 vs 0.297 / 0.271 / 0.294 ms at cfg 2)
 template <int RPT, int MINB>
-__global__ void __launch_bounds__(256, MINB) boot_rank_count_kernel(const BootParams P, const FeatView F) {
-    __shared__ int warp_tot[8][RPT];
+__global__ void __launch_bounds__(kCountThreads, (MINB * 256) / kCountThreads > 0 ? (MINB * 256) / kCountThreads : 1) boot_rank_count_kernel(const BootParams P, const FeatView F) {
+    __shared__ int warp_tot[kCountThreads / 32][RPT];
     const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t r0 = (int64_t)blockIdx.y * RPT;
     const int n_live = (int)min((int64_t)RPT, P.n_iter - r0);
@@ -180,7 +181,7 @@ __global__ void __launch_bounds__(256, MINB) boot_rank_count_kernel(const BootPa
     __syncthreads();
     if (threadIdx.x < n_live) {
         unsigned long long s = 0;
-        for (int w = 0; w < 8; ++w) s += (unsigned)warp_tot[w][threadIdx.x];
+        for (int w = 0; w < kCountThreads / 32; ++w) s += (unsigned)warp_tot[w][threadIdx.x];
         if (s) atomicAdd(P.iter_totals + r0 + threadIdx.x, s);
     }
 }
@@ -289,8 +290,9 @@ struct AddF64 {
 // (checked on the host).
 // SIMPLE: one class of y, bootstrap kinds, no exclusion, no table wanted -- the common fused-counts call; the general
 // branches are compiled out.
+constexpr int kRowsThreads = 256;  // 128 measured the same
 template <int RPT, int MINB, bool SIMPLE>
-__global__ void __launch_bounds__(256, MINB) boot_block_rows_kernel(const BootParams P, const TileExcl X, int ipc) {
+__global__ void __launch_bounds__(kRowsThreads, (MINB * 256) / kRowsThreads) boot_block_rows_kernel(const BootParams P, const TileExcl X, int ipc) {
     const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int lane = threadIdx.x & 31;
 #pragma unroll 1

@@ -227,32 +227,32 @@ int launch_rank(nrb200_handle *h, const BootParams &P, bool has_query) {
     if (P.n_blocks > 0) {
         const TileExcl X{h->excl.n > 0 ? h->tile_x_off.as<int32_t>() : nullptr, h->tile_x_rec.as<int4>()};  // drop: minus, trim: plus
         // iterations a CTA loops over: up to NRB200_ROWS_IPC, as long as the grid still holds a few CTAs per resident slot
-        const int64_t ctas_x = (P.n_blocks + 255) / 256;
+        const int64_t ctas_x = (P.n_blocks + kRowsThreads - 1) / kRowsThreads;
         const int ipc = (int)std::max<int64_t>(1, std::min<int64_t>(h->tune_rows_ipc, P.n_iter * ctas_x / ((int64_t)h->sm_count * 12)));
-        const dim3 rows_grid((unsigned)((P.n_blocks + 255) / 256), (unsigned)((P.n_iter + ipc - 1) / ipc));
+        const dim3 rows_grid((unsigned)ctas_x, (unsigned)((P.n_iter + ipc - 1) / ipc));
         const bool simple = P.y.n_cls == 1 && !X.off && !P.item_rec && !P.item_rows && !P.permute && !P.dst_tile && !P.rows_windows_only;
-        if (simple && h->tune_minb_rows == 6) boot_block_rows_kernel<1, 6, true><<<rows_grid, 256, 0, h->stream>>>(P, X, ipc);
-        else if (simple && h->tune_minb_rows == 8) boot_block_rows_kernel<1, 8, true><<<rows_grid, 256, 0, h->stream>>>(P, X, ipc);
-        else if (h->tune_minb_rows >= 8) boot_block_rows_kernel<1, 8, false><<<rows_grid, 256, 0, h->stream>>>(P, X, ipc);
-        else if (h->tune_minb_rows == 6) boot_block_rows_kernel<1, 6, false><<<rows_grid, 256, 0, h->stream>>>(P, X, ipc);
-        else if (h->tune_minb_rows == 5) boot_block_rows_kernel<1, 5, false><<<rows_grid, 256, 0, h->stream>>>(P, X, ipc);
-        else boot_block_rows_kernel<1, 1, false><<<rows_grid, 256, 0, h->stream>>>(P, X, ipc);
+        if (simple && h->tune_minb_rows == 6) boot_block_rows_kernel<1, 6, true><<<rows_grid, kRowsThreads, 0, h->stream>>>(P, X, ipc);
+        else if (simple && h->tune_minb_rows == 8) boot_block_rows_kernel<1, 8, true><<<rows_grid, kRowsThreads, 0, h->stream>>>(P, X, ipc);
+        else if (h->tune_minb_rows >= 8) boot_block_rows_kernel<1, 8, false><<<rows_grid, kRowsThreads, 0, h->stream>>>(P, X, ipc);
+        else if (h->tune_minb_rows == 6) boot_block_rows_kernel<1, 6, false><<<rows_grid, kRowsThreads, 0, h->stream>>>(P, X, ipc);
+        else if (h->tune_minb_rows == 5) boot_block_rows_kernel<1, 5, false><<<rows_grid, kRowsThreads, 0, h->stream>>>(P, X, ipc);
+        else boot_block_rows_kernel<1, 1, false><<<rows_grid, kRowsThreads, 0, h->stream>>>(P, X, ipc);
         ++launches;
     }
     if (h->split_ev) cudaEventRecord(h->split_ev, h->stream);  // stats: end of the rows kernel
     if (has_query) {
         const FeatView F{h->f_src.as<int32_t>(), h->pair_off.as<int32_t>(), h->pair_rec.as<int4>(), h->pair_rec.as<int4>() + h->n_pairs};
-        const dim3 grid((unsigned)((P.n_query + 255) / 256), gy);
+        const dim3 grid((unsigned)((P.n_query + kCountThreads - 1) / kCountThreads), gy);
         switch (variant) {
-        case 11: boot_rank_count_kernel<1, 1><<<grid, 256, 0, h->stream>>>(P, F); break;
-        case 17: boot_rank_count_kernel<1, 7><<<grid, 256, 0, h->stream>>>(P, F); break;
-        case 21: boot_rank_count_kernel<2, 1><<<grid, 256, 0, h->stream>>>(P, F); break;
-        case 24: boot_rank_count_kernel<2, 4><<<grid, 256, 0, h->stream>>>(P, F); break;
-        case 41: boot_rank_count_kernel<4, 1><<<grid, 256, 0, h->stream>>>(P, F); break;
-        case 43: boot_rank_count_kernel<4, 3><<<grid, 256, 0, h->stream>>>(P, F); break;
-        case 44: boot_rank_count_kernel<4, 4><<<grid, 256, 0, h->stream>>>(P, F); break;
-        case 81: boot_rank_count_kernel<8, 1><<<grid, 256, 0, h->stream>>>(P, F); break;
-        default: boot_rank_count_kernel<1, 8><<<grid, 256, 0, h->stream>>>(P, F); break;
+        case 11: boot_rank_count_kernel<1, 1><<<grid, kCountThreads, 0, h->stream>>>(P, F); break;
+        case 17: boot_rank_count_kernel<1, 7><<<grid, kCountThreads, 0, h->stream>>>(P, F); break;
+        case 21: boot_rank_count_kernel<2, 1><<<grid, kCountThreads, 0, h->stream>>>(P, F); break;
+        case 24: boot_rank_count_kernel<2, 4><<<grid, kCountThreads, 0, h->stream>>>(P, F); break;
+        case 41: boot_rank_count_kernel<4, 1><<<grid, kCountThreads, 0, h->stream>>>(P, F); break;
+        case 43: boot_rank_count_kernel<4, 3><<<grid, kCountThreads, 0, h->stream>>>(P, F); break;
+        case 44: boot_rank_count_kernel<4, 4><<<grid, kCountThreads, 0, h->stream>>>(P, F); break;
+        case 81: boot_rank_count_kernel<8, 1><<<grid, kCountThreads, 0, h->stream>>>(P, F); break;
+        default: boot_rank_count_kernel<1, 8><<<grid, kCountThreads, 0, h->stream>>>(P, F); break;
         }
         ++launches;
     }
