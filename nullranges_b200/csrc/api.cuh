@@ -21,6 +21,7 @@ int nrb200_create(const nrb200_config *cfg, nrb200_handle **out) {
     h->flags = cfg ? cfg->flags : 0;
     if (const char *e = getenv("NRB200_RPT")) h->tune_rpt = atoi(e);
     if (const char *e = getenv("NRB200_MINB")) h->tune_minb = atoi(e);
+    if (const char *e = getenv("NRB200_END_RANK")) h->tune_end_rank = atoi(e) != 0;
     if (const char *e = getenv("NRB200_ROWS_IPC")) h->tune_rows_ipc = std::min(std::max(atoi(e), 1), 64);
     if (const char *e = getenv("NRB200_MINB_ROWS")) h->tune_minb_rows = atoi(e);
     if (const char *e = getenv("NRB200_TABLE_MULT")) h->tune_table_mult = atof(e);

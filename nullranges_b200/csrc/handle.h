@@ -208,6 +208,7 @@ struct nrb200_handle {
     uint32_t flags = 0;
     // tuning knobs (environment, read at create): NRB200_RPT iterations per thread of the rank count
     // kernel, NRB200_MINB its min CTAs/SM, NRB200_TABLE_MULT rank-table entries per range
+    bool tune_end_rank = true;         // NRB200_END_RANK=0: always radix-sort the ends (index build)
     int tune_rows_ipc = 4;             // NRB200_ROWS_IPC: iterations a CTA of the rows kernel loops over
     int tune_rpt = 1, tune_minb = 8, tune_minb_rows = 6;  // NRB200_RPT / NRB200_MINB / NRB200_MINB_ROWS (min CTAs per SM: 8 = 32 registers, all 64 warps resident)
     double tune_table_mult = 4.0;

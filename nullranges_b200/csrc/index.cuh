@@ -287,7 +287,15 @@ int build_rank_tables(nrb200_handle *h) {
         if (h->ends_alias_starts) return NRB200_OK;
         // ends in ascending order within each sequence: radix sort of (seqid << 32 | end)
         NRB_CUDA(h, h->rank_end.reserve(entries * sizeof(int32_t)));
-        if (y.n > 0) {
+        // ranges that are short against their spacing (expected ranges per widest-range window <= 4): the ends are
+        // nearly in order already and every range finds its rank with a short scan (end_rank_scatter_kernel);
+        // otherwise a radix sort of (seqid << 32 | end)
+        const bool by_rank = y.n > 0 && h->tune_end_rank && (double)y.wmax * (double)y.n <= 4.0 * (double)genome;
+        if (by_rank) {
+            end_rank_scatter_kernel<<<n_grid, threads, 0, h->stream>>>(y.seqid.as<int32_t>(), y.start.as<int32_t>(), y.end.as<int32_t>(),
+                                                                       h->seq_info_dev.as<int4>(), h->rank_start.as<uint32_t>(), shift, y.n,
+                                                                       y.wmax, h->end_sorted.as<int32_t>());
+        } else if (y.n > 0) {
             int seq_bits = 1;
             while ((1 << seq_bits) < C) ++seq_bits;
             pack_end_keys_kernel<<<n_grid, threads, 0, h->stream>>>(y.seqid.as<int32_t>(), y.end.as<int32_t>(), y.n,

@@ -372,6 +372,28 @@ __global__ void count_observed_kernel(const RangesView y, int64_t n, const int32
     if ((threadIdx.x & 31) == 0 && found) atomicAdd(total, (unsigned long long)found);
 }
 
+// Ends in ascending order inside each sequence WITHOUT a sort, for y in canonical (start) order whose widest range is
+// short against the spacing of the ranges: end_i = start_i + w_i - 1 is then nearly sorted already.  Rank of end_i =
+// #{start_j <= end_i - wmax} (all of those end before it) + the (end, index)-smaller ones among the few ranges that start
+// in (end_i - wmax, end_i] -- two probes of the start table and a short scan; every range writes its end to its rank.
+__global__ void end_rank_scatter_kernel(const int32_t *__restrict__ seqid, const int32_t *__restrict__ start,
+                                        const int32_t *__restrict__ end, const int4 *__restrict__ seq_info,
+                                        const uint32_t *__restrict__ rank_start, int rank_shift, int64_t n, int32_t wmax,
+                                        int32_t *__restrict__ end_sorted) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int4 si = __ldg(seq_info + seqid[i]);
+    const int32_t e = end[i];
+    const int32_t lo = first_ge_ranked(start, rank_start, rank_shift, si, e - wmax + 1);
+    const int32_t hi = first_ge_ranked(start, rank_start, rank_shift, si, e + 1);
+    int32_t rank = lo;
+    for (int32_t j = lo; j < hi; ++j) {
+        const int32_t ej = __ldg(end + j);
+        rank += (ej < e || (ej == e && j < (int32_t)i)) ? 1 : 0;
+    }
+    end_sorted[rank] = e;
+}
+
 // Per-feature moments over a batch of iterations: thread per feature, coalesced over g.
 __global__ void accumulate_moments_kernel(const int32_t *__restrict__ counts, int64_t n_iter, int64_t n_query,
                                           const int32_t *__restrict__ observed, long long *__restrict__ sum,
