@@ -290,7 +290,9 @@ int build_rank_tables(nrb200_handle *h) {
         // ranges that are short against their spacing (expected ranges per widest-range window <= 4): the ends are
         // nearly in order already and every range finds its rank with a short scan (end_rank_scatter_kernel);
         // otherwise a radix sort of (seqid << 32 | end)
-        const bool by_rank = y.n > 0 && h->tune_end_rank && (double)y.wmax * (double)y.n <= 4.0 * (double)genome;
+        bool by_rank = y.n > 0 && h->tune_end_rank;
+        for (int c = 0; c < C && by_rank; ++c)  // judged per sequence: a crowded one would make its ranges scan long windows
+            by_rank = (double)y.wmax * (double)(y.h_seq_off[c + 1] - y.h_seq_off[c]) <= 4.0 * (double)std::max<int64_t>(max_pos[c], 1);
         if (by_rank) {
             end_rank_scatter_kernel<<<n_grid, threads, 0, h->stream>>>(y.seqid.as<int32_t>(), y.start.as<int32_t>(), y.end.as<int32_t>(),
                                                                        h->seq_info_dev.as<int4>(), h->rank_start.as<uint32_t>(), shift, y.n,
