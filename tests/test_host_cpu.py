@@ -155,3 +155,22 @@ def test_expand_runs_matches_numpy_repeat():
         out = np.empty(int(offs[-1] - offs[0]), np.int32)
         lib.nrb200_expand_runs(_lib.ptr(offs, C.c_int64), n_runs, 1, _lib.ptr(out, C.c_int32))
         np.testing.assert_array_equal(out, np.repeat(np.arange(1, n_runs + 1, dtype=np.int32), lens))
+
+
+def test_side_arrays_maps_seqlevels_and_drops_foreign_ranges():
+    """Front-end helper: x is expressed in y's seqlevels; ranges on sequences y lacks are dropped (they can never be hit);
+    identical seqlevels pass the arrays through untouched."""
+    from nullranges_b200 import GRanges
+    from nullranges_b200 import bootranges as BR
+    y = GRanges(["chr1", "chr2"], [1, 5], width=[3, 3], seqlengths={"chr1": 100, "chr2": 50})
+    same = GRanges(["chr2", "chr1"], [7, 9], width=[2, 2], seqlengths={"chr1": 100, "chr2": 50})
+    sid, st, en, strand, keep = BR._side_arrays(same, y, "x")
+    assert sid is same.seqid and st is same.start and en is same.end and strand is None and keep is None
+    other = GRanges(["chr2", "chrX", "chr1"], [7, 1, 9], width=[2, 2, 2], strand=["+", "*", "-"],
+                    seqlengths={"chr2": 50, "chrX": 10, "chr1": 100})
+    sid, st, en, strand, keep = BR._side_arrays(other, y, "x")
+    assert sid.tolist() == [1, 0] and st.tolist() == [7, 9] and en.tolist() == [8, 10]
+    assert strand.tolist() == [1, 2] and keep.tolist() == [0, 2]
+    reordered = GRanges(["chr2", "chr1"], [7, 9], width=[2, 2], seqlengths={"chr2": 50, "chr1": 100})
+    sid, st, en, strand, keep = BR._side_arrays(reordered, y, "x")
+    assert sid.tolist() == [1, 0] and keep is None and st is reordered.start
