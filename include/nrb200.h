@@ -16,8 +16,8 @@
  *   - every function returns NRB200_OK (0) or a negative code; the text is in
  *     nrb200_last_error().  Nothing is thrown across the boundary, so an R shim can free
  *     its resources and only then call Rf_error();
- *   - a handle is bound to ONE GPU and is not thread-safe (R is single-threaded); use one
- *     handle per GPU / per process rank.
+ *   - a handle is bound to one GPU, or to a device group (nrb200_config.n_devices: the iterations of a run are
+ *     sharded over the GPUs of the box from ONE calling thread), and is not thread-safe (R is single-threaded).
  */
 #ifndef NRB200_H
 #define NRB200_H
@@ -46,12 +46,25 @@ typedef struct nrb200_handle nrb200_handle;
                                        and for measuring the streaming kernel */
 
 typedef struct nrb200_config {
-    int32_t device;     /* CUDA ordinal */
+    int32_t device;     /* CUDA ordinal (ignored when n_devices > 0) */
     uint32_t flags;     /* NRB200_FLAG_* */
-    void *stream;       /* cudaStream_t to launch on, or NULL = a private stream */
+    void *stream;       /* cudaStream_t to launch on, or NULL = a private stream (must be NULL for a device group) */
+    /* Device group: n_devices > 1 ordinals in `devices` (n_devices == 1: that one device; 0: `device`).  The handle
+     * then shards the bootstrap iterations of every run over those GPUs -- replicate(R, ...) of R/bootRanges.R:90 is
+     * R independent draws -- and delivers ONE result into the caller's arrays, as the reference does
+     * (R/bootRanges.R:120-122): inputs go to every GPU from the caller's single host copy, the window lists are built
+     * once, GPU k runs iterations [ceil(k R / W), ceil((k + 1) R / W)) and copies its rows of the count matrix
+     * straight into the caller's matrix.  Philox draws are keyed by the global iteration: results are bit-identical
+     * for every W.  Every entry point below works on a group handle except the *_resident pair (device pointers of
+     * several GPUs) -- NRB200_ERR_UNSUPPORTED; nrb200_run_materialize / nrb200_count_observed run on the first
+     * device. */
+    int32_t n_devices;
+    const int32_t *devices;
 } nrb200_config;
 
 int nrb200_create(const nrb200_config *cfg, nrb200_handle **out);
+/* Number of GPUs behind the handle (1 unless it is a device group). */
+int nrb200_n_devices(const nrb200_handle *h);
 void nrb200_destroy(nrb200_handle *h);
 /* h may be NULL: error of the last failed nrb200_create() on this thread. */
 const char *nrb200_last_error(const nrb200_handle *h);
@@ -244,6 +257,9 @@ int nrb200_run_materialize(nrb200_handle *h, const nrb200_draws *draws, int64_t 
  * (the reference's internal `block` column, R/bootRanges.R:126). Pointers may be NULL. */
 int nrb200_fetch_rows(nrb200_handle *h, int64_t row0, int64_t n, int32_t *seqid,
                       int32_t *start, int32_t *end, int32_t *src_idx, int32_t *block);
+/* Permute variants with device draws: the tile each block of iterations [r0, r0 + n) of the last run moved TO
+ * ([n x n_blocks], the dst_tile a host-mode caller would have passed in) -- what `blockStart` needs.  */
+int nrb200_fetch_dst_tiles(nrb200_handle *h, int64_t r0, int64_t n, int32_t *dst_tile);
 
 /* ---- base-R RNG for hosts that are not R ------------------------------------------- */
 /* In R the wrapper draws blocks with R's own sample()/runif().  A non-R host (the Python

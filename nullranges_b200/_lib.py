@@ -21,7 +21,8 @@ EXCLUDE_DROP, EXCLUDE_TRIM = 0, 1
 
 
 class Config(C.Structure):
-    _fields_ = [("device", C.c_int32), ("flags", C.c_uint32), ("stream", C.c_void_p)]
+    _fields_ = [("device", C.c_int32), ("flags", C.c_uint32), ("stream", C.c_void_p),
+                ("n_devices", C.c_int32), ("devices", C.POINTER(C.c_int32))]
 
 
 class PlanSpec(C.Structure):
@@ -46,6 +47,7 @@ class Stats(C.Structure):
 # every symbol include/nrb200.h declares: (name, restype, argtypes)
 SYMBOLS = [
     ("nrb200_create", C.c_int, [C.POINTER(Config), C.POINTER(vp)]),
+    ("nrb200_n_devices", C.c_int, [vp]),
     ("nrb200_destroy", None, [vp]),
     ("nrb200_last_error", C.c_char_p, [vp]),
     ("nrb200_version", C.c_char_p, []),
@@ -72,6 +74,7 @@ SYMBOLS = [
     ("nrb200_count_observed_ex", C.c_int, [vp, C.c_int32, i32p, i64p]),
     ("nrb200_run_materialize", C.c_int, [vp, C.POINTER(Draws), i64p, C.POINTER(Stats)]),
     ("nrb200_fetch_rows", C.c_int, [vp, C.c_int64, C.c_int64, i32p, i32p, i32p, i32p, i32p]),
+    ("nrb200_fetch_dst_tiles", C.c_int, [vp, C.c_int64, C.c_int64, i32p]),
     ("nrb200_rrng_create", vp, [C.c_uint32]),
     ("nrb200_rrng_destroy", None, [vp]),
     ("nrb200_rrng_unif_rand", C.c_double, [vp]),

@@ -86,10 +86,11 @@ def _draw_host(kind, rng: RRng, R: int, y: GRanges, L_b: int, seg, eng: Engine):
     return bait_seq, bait_start, dst
 
 
-def _setup(y: GRanges, blockLength, seg, exclude, excludeOption, proportionLength, type_, withinChrom, device, query=None):
+def _setup(eng: Engine, y: GRanges, blockLength, seg, exclude, excludeOption, proportionLength, type_, withinChrom, query=None):
     """Argument checks of R/bootRanges.R:80-88 and R/bootUnsegmented.R:8,31, inputs to the engine.  y goes first and
     asynchronously (nrb200_set_ranges_begin): exclude, plan and query are prepared while it is on the wire.
-    query: (x, maxgap, minoverlap) of bootCounts(); returns (engine, kind, L_b, seg arrays, positions of x kept)."""
+    query: (x, maxgap, minoverlap) of bootCounts(); returns (kind, L_b, seg arrays, positions of x kept).  The caller holds
+    eng.lock: the handle is stateful from here to the result."""
     chr_lens = y.seqlengths
     if np.any(chr_lens < 0):
         raise ValueError("all(!is.na(chr_lens)) is not TRUE")  # R/bootRanges.R:81
@@ -105,7 +106,6 @@ def _setup(y: GRanges, blockLength, seg, exclude, excludeOption, proportionLengt
     L_b = int(blockLength)
     kind = _plan_kind(seg, proportionLength, type_, withinChrom)
     segd = _seg_arrays(seg, y) if seg is not None else None
-    eng = get_engine(device)
     stranded = bool(np.any(y.strand))
     eng.set_ranges(chr_lens, y.seqid, y.start, y.end, y.strand if stranded else None, defer=True)
     qkeep = None
@@ -127,7 +127,7 @@ def _setup(y: GRanges, blockLength, seg, exclude, excludeOption, proportionLengt
         # engine's canonical-order test (made on the GPU while loading) is that check.
         if not (eng.ranges_info()["sorted"] if not stranded else y.is_sorted()):
             raise ValueError("all(y == GenomicRanges::sort(y)) is not TRUE")
-    return eng, kind, L_b, segd, qkeep
+    return kind, L_b, segd, qkeep
 
 
 def _make_draws(eng, kind, R, y, L_b, segd, rng, seed, iter0):
@@ -142,9 +142,18 @@ def _make_draws(eng, kind, R, y, L_b, segd, rng, seed, iter0):
 def bootRanges(y: GRanges, blockLength, R: int = 1, seg: GRanges | None = None, exclude: GRanges | None = None,
                excludeOption=("drop", "trim"), proportionLength: bool = True, type=("bootstrap", "permute"),
                withinChrom: bool = False, storeBlockLength: bool = False, *, rng="R", seed=None, iter0: int = 0,
-               storeBlockStart: bool = False, device: int = 0) -> BootRanges:
-    """Block bootstrap of genomic ranges; returns all iterations concatenated with an ``iter`` column."""
-    eng, kind, L_b, segd, _ = _setup(y, blockLength, seg, exclude, excludeOption, proportionLength, type, withinChrom, device)
+               storeBlockStart: bool = False, device=0, gpus=None) -> BootRanges:
+    """Block bootstrap of genomic ranges; returns all iterations concatenated with an ``iter`` column.
+    gpus: as in bootCounts(); the materialised table itself is produced by the first GPU."""
+    eng = get_engine(device, gpus)
+    with eng.lock:
+        return _boot_ranges(eng, y, blockLength, R, seg, exclude, excludeOption, proportionLength, type, withinChrom,
+                            storeBlockLength, rng, seed, iter0, storeBlockStart)
+
+
+def _boot_ranges(eng, y, blockLength, R, seg, exclude, excludeOption, proportionLength, type, withinChrom, storeBlockLength,
+                 rng, seed, iter0, storeBlockStart) -> BootRanges:
+    kind, L_b, segd, _ = _setup(eng, y, blockLength, seg, exclude, excludeOption, proportionLength, type, withinChrom)
     draws = _make_draws(eng, kind, int(R), y, L_b, segd, rng, seed, iter0)
     rows = eng.run_materialize(draws)
     lens = np.diff(rows["iter_offsets"])
@@ -170,7 +179,12 @@ def bootRanges(y: GRanges, blockLength, R: int = 1, seg: GRanges | None = None, 
         br.mcols["blockLength"] = np.full(src.size, L_b, dtype=np.int32)  # :123-125
     if storeBlockStart:
         _, tile_start, _ = eng.tiles()
-        dst = rows["block"] if draws.dst_tile is None else draws.dst_tile[br.mcols["iter"] - 1, rows["block"]]
+        # where the block LANDED: bootstrap kinds, block b -> tile b; permute kinds, the tile it was drawn for (host
+        # draws: the caller's dst_tile; Philox: the permutation the device made)
+        dst_tile = draws.dst_tile
+        if dst_tile is None and kind in (_lib.PERMUTE_WITHIN, _lib.PERMUTE_ACROSS):
+            dst_tile = eng.fetch_dst_tiles(0, int(R))
+        dst = rows["block"] if dst_tile is None else dst_tile[br.mcols["iter"] - 1, rows["block"]]
         br.mcols["blockStart"] = tile_start[dst]
     return br
 
@@ -189,13 +203,23 @@ class BootCounts:
 def bootCounts(y: GRanges, x: GRanges, blockLength, R: int = 1, seg: GRanges | None = None,
                exclude: GRanges | None = None, excludeOption=("drop", "trim"), proportionLength: bool = True,
                type=("bootstrap", "permute"), withinChrom: bool = False, *, rng="philox", seed=None, iter0: int = 0,
-               perFeature: bool = True, device: int = 0, out: dict | None = None, maxgap: int = -1,
-               minoverlap: int = 0, weights: str | None = None) -> BootCounts:
+               perFeature: bool = True, device=0, out: dict | None = None, maxgap: int = -1,
+               minoverlap: int = 0, weights: str | None = None, gpus=None) -> BootCounts:
     """countOverlaps(x, bootRanges(y, ...), maxgap = , minoverlap = ) per iteration, fused on the GPU.
     weights: name of a numeric metadata column of y; adds its sum over the overlapping bootstrapped ranges per
-    (iteration, feature) -- summarize(sum(signal)) of vignettes/bootRanges.Rmd:532-540."""
-    eng, kind, L_b, segd, qkeep = _setup(y, blockLength, seg, exclude, excludeOption, proportionLength, type, withinChrom, device,
-                                         query=(x, maxgap, minoverlap))
+    (iteration, feature) -- summarize(sum(signal)) of vignettes/bootRanges.Rmd:532-540.
+    gpus: N (the first N GPUs of the box) or a list of ordinals: the R iterations are sharded over them
+    (replicate() at R/bootRanges.R:90 is R independent draws) and land in ONE result, bit-identical for every N."""
+    eng = get_engine(device, gpus)
+    with eng.lock:
+        return _boot_counts(eng, y, x, blockLength, R, seg, exclude, excludeOption, proportionLength, type, withinChrom, rng, seed,
+                            iter0, perFeature, out, maxgap, minoverlap, weights)
+
+
+def _boot_counts(eng, y, x, blockLength, R, seg, exclude, excludeOption, proportionLength, type, withinChrom, rng, seed, iter0,
+                 perFeature, out, maxgap, minoverlap, weights) -> BootCounts:
+    kind, L_b, segd, qkeep = _setup(eng, y, blockLength, seg, exclude, excludeOption, proportionLength, type, withinChrom,
+                                    query=(x, maxgap, minoverlap))
     draws = _make_draws(eng, kind, int(R), y, L_b, segd, rng, seed, iter0)
     if out is not None and qkeep is not None:
         raise ValueError("out= needs every seqlevel of x to be a seqlevel of y")
@@ -239,15 +263,24 @@ class BootMoments:
 def bootMoments(y: GRanges, x: GRanges, blockLength, R: int = 1, seg: GRanges | None = None,
                 exclude: GRanges | None = None, excludeOption=("drop", "trim"), proportionLength: bool = True,
                 type=("bootstrap", "permute"), withinChrom: bool = False, *, rng="philox", seed=None, iter0: int = 0,
-                device: int = 0, maxgap: int = -1, minoverlap: int = 0, weights: str | None = None,
-                observed=None) -> BootMoments:
+                device=0, maxgap: int = -1, minoverlap: int = 0, weights: str | None = None,
+                observed=None, gpus=None) -> BootMoments:
     """Mean / sd / z-score / empirical p-value per feature of countOverlaps(x, boots) -- or, with ``weights``, of the
     sum of that metadata column over the overlapping bootstrapped ranges -- over R iterations, accumulated on the GPU
     (the summary the vignette computes from the per-iteration table, vignettes/bootRanges.Rmd:497-560; no R x G
     matrix, so R = 10^4 with 10^5 features is fine).  observed: the statistic on the original ranges; for counts it
-    defaults to countOverlaps(x, y), for weights it has to be given to get z and p."""
-    eng, kind, L_b, segd, qkeep = _setup(y, blockLength, seg, exclude, excludeOption, proportionLength, type, withinChrom, device,
-                                         query=(x, maxgap, minoverlap))
+    defaults to countOverlaps(x, y), for weights it has to be given to get z and p.
+    gpus: as in bootCounts(); every GPU reduces its shard of the iterations, the per-feature sums are added on the host."""
+    eng = get_engine(device, gpus)
+    with eng.lock:
+        return _boot_moments(eng, y, x, blockLength, R, seg, exclude, excludeOption, proportionLength, type, withinChrom, rng, seed,
+                             iter0, maxgap, minoverlap, weights, observed)
+
+
+def _boot_moments(eng, y, x, blockLength, R, seg, exclude, excludeOption, proportionLength, type, withinChrom, rng, seed, iter0,
+                  maxgap, minoverlap, weights, observed) -> BootMoments:
+    kind, L_b, segd, qkeep = _setup(eng, y, blockLength, seg, exclude, excludeOption, proportionLength, type, withinChrom,
+                                    query=(x, maxgap, minoverlap))
     if qkeep is not None:
         raise ValueError("bootMoments needs every seqlevel of x to be a seqlevel of y")
     draws = _make_draws(eng, kind, int(R), y, L_b, segd, rng, seed, iter0)

@@ -8,7 +8,10 @@ const char *nrb200_last_error(const nrb200_handle *h) { return h ? h->error.c_st
 int nrb200_create(const nrb200_config *cfg, nrb200_handle **out) {
     if (!out) return fail(nullptr, NRB200_ERR_INVALID, "nrb200_create: out is NULL");
     *out = nullptr;
-    const int dev = cfg ? cfg->device : 0;
+    if (cfg && cfg->n_devices > 1) return group_create(cfg, out);
+    if (cfg && cfg->n_devices < 0) return fail(nullptr, NRB200_ERR_INVALID, "nrb200_create: n_devices must be >= 0");
+    if (cfg && cfg->n_devices == 1 && !cfg->devices) return fail(nullptr, NRB200_ERR_INVALID, "nrb200_create: n_devices = 1 needs the device list");
+    const int dev = cfg ? (cfg->n_devices == 1 ? cfg->devices[0] : cfg->device) : 0;
     int count = 0;
     cudaError_t e = cudaGetDeviceCount(&count);
     if (e != cudaSuccess || count == 0)
@@ -19,16 +22,12 @@ int nrb200_create(const nrb200_config *cfg, nrb200_handle **out) {
     nrb200_handle *h = new nrb200_handle();
     h->device = dev;
     h->flags = cfg ? cfg->flags : 0;
-    if (const char *e = getenv("NRB200_RPT")) h->tune_rpt = atoi(e);
-    if (const char *e = getenv("NRB200_MINB")) h->tune_minb = atoi(e);
     if (const char *e = getenv("NRB200_END_RANK")) h->tune_end_rank = atoi(e) != 0;
     if (const char *e = getenv("NRB200_ROWS_IPC")) h->tune_rows_ipc = std::min(std::max(atoi(e), 1), 64);
-    if (const char *e = getenv("NRB200_MINB_ROWS")) h->tune_minb_rows = atoi(e);
     if (const char *e = getenv("NRB200_TABLE_MULT")) h->tune_table_mult = atof(e);
     if (const char *e = getenv("NRB200_TABLE_CAP")) h->tune_table_cap = atoll(e);
     if (const char *e = getenv("NRB200_CHUNKS")) h->tune_chunks = std::min(std::max(atoi(e), 1), 64);
     if (const char *e = getenv("NRB200_MAX_BATCH")) h->tune_max_batch = std::min<int64_t>(std::max<int64_t>(atoll(e), 8), 2048);
-    if (h->tune_rpt != 1 && h->tune_rpt != 2 && h->tune_rpt != 4 && h->tune_rpt != 8) h->tune_rpt = 1;
     if (cfg && cfg->stream) {
         h->stream = (cudaStream_t)cfg->stream;
     } else {
@@ -45,8 +44,11 @@ int nrb200_create(const nrb200_config *cfg, nrb200_handle **out) {
     return NRB200_OK;
 }
 
+int nrb200_n_devices(const nrb200_handle *h) { return !h ? 0 : (is_group(h) ? group_size(h) : 1); }
+
 void nrb200_destroy(nrb200_handle *h) {
     if (!h) return;
+    if (is_group(h)) return group_destroy(h);
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
     for (auto &ev : h->ev)
@@ -71,6 +73,7 @@ void nrb200_destroy(nrb200_handle *h) {
 int nrb200_set_ranges_begin(nrb200_handle *h, int64_t n, int32_t n_seq, const int64_t *seqlengths, const int32_t *seqid,
                             const int32_t *start, const int32_t *end, const int8_t *strand) {
     if (!h) return NRB200_ERR_INVALID;
+    if (is_group(h)) return group_set_ranges_begin(h, n, n_seq, seqlengths, seqid, start, end, strand);
     NRB_CUDA(h, cudaSetDevice(h->device));
     h->y_pending = false;
     if (n_seq <= 0 || !seqlengths) return fail(h, NRB200_ERR_INVALID, "seqlengths(y) must be known");
@@ -84,6 +87,7 @@ int nrb200_set_ranges_begin(nrb200_handle *h, int64_t n, int32_t n_seq, const in
     h->query_minoverlap = 0;
     h->query_widen = 0;
     h->have_weights = false;      // weights belong to the ranges they were set for
+    h->moments_ready = false;     // accumulated moments belong to the query they were taken against
     h->n_seq = n_seq;
     h->seqlen.assign(seqlengths, seqlengths + n_seq);
     int rc;
@@ -95,6 +99,7 @@ int nrb200_set_ranges_begin(nrb200_handle *h, int64_t n, int32_t n_seq, const in
 
 int nrb200_set_ranges_end(nrb200_handle *h) {
     if (!h) return NRB200_ERR_INVALID;
+    if (is_group(h)) return group_all(h, [](int, nrb200_handle *m) { return nrb200_set_ranges_end(m); });
     NRB_CUDA(h, cudaSetDevice(h->device));
     if (!h->y_pending) return fail(h, NRB200_ERR_STATE, "nrb200_set_ranges_begin() has not been called");
     h->y_pending = false;
@@ -128,6 +133,7 @@ int nrb200_set_ranges(nrb200_handle *h, int64_t n, int32_t n_seq, const int64_t 
 }
 
 int nrb200_ranges_info(const nrb200_handle *h, int32_t *is_sorted, int32_t *is_stranded, int32_t *max_width) {
+    if (is_group(h)) h = h->members[0];
     if (!h || !h->have_y) return NRB200_ERR_STATE;
     if (is_sorted) *is_sorted = h->y.sorted_input;
     if (is_stranded) *is_stranded = h->y.stranded;
@@ -141,6 +147,7 @@ static int set_side(nrb200_handle *h, RangeSet &rs, const char *what, int64_t n,
     NRB_CUDA(h, cudaSetDevice(h->device));
     if (!h->have_y && !h->y_pending) return fail(h, NRB200_ERR_STATE, "call nrb200_set_ranges() first (it defines the seqlevels)");
     h->slices_dirty = true;
+    if (&rs == &h->query) h->moments_ready = false;  // a new query: sums of the old one must not be mixed in (nor its G trusted)
     if (n == 0) {
         rs.n = 0;
         return NRB200_OK;
@@ -167,6 +174,7 @@ int nrb200_set_query_ex(nrb200_handle *h, int64_t n, const int32_t *seqid, const
     if (maxgap >= (1 << 29)) return fail(h, NRB200_ERR_UNSUPPORTED, "'maxgap' must be below 2^29");
     if (minoverlap < 0) return fail(h, NRB200_ERR_INVALID, "'minoverlap' must be >= 0");
     if (minoverlap > 0 && maxgap != -1) return fail(h, NRB200_ERR_INVALID, "'maxgap' and 'minoverlap' cannot both be set");
+    if (is_group(h)) return group_all(h, [&](int, nrb200_handle *m) { return nrb200_set_query_ex(m, n, seqid, start, end, strand, maxgap, minoverlap); });
     const int rc = set_side(h, h->query, "query", n, seqid, start, end, strand, maxgap + 1);
     if (rc == NRB200_OK) {
         h->query_widen = maxgap + 1;
@@ -177,11 +185,14 @@ int nrb200_set_query_ex(nrb200_handle *h, int64_t n, const int32_t *seqid, const
 
 int nrb200_set_exclude(nrb200_handle *h, int64_t n, const int32_t *seqid, const int32_t *start, const int32_t *end,
                        const int8_t *strand) {
+    if (is_group(h)) return group_all(h, [&](int, nrb200_handle *m) { return nrb200_set_exclude(m, n, seqid, start, end, strand); });
+    if (!h) return NRB200_ERR_INVALID;
     return set_side(h, h->excl, "exclude", n, seqid, start, end, strand);
 }
 
 int nrb200_set_exclude_option(nrb200_handle *h, int32_t option) {
     if (!h) return NRB200_ERR_INVALID;
+    if (is_group(h)) return group_all(h, [&](int, nrb200_handle *m) { return nrb200_set_exclude_option(m, option); });
     if (option != NRB200_EXCLUDE_DROP && option != NRB200_EXCLUDE_TRIM)
         return fail(h, NRB200_ERR_INVALID, "'excludeOption' should be one of 'drop', 'trim'");
     // stopifnot(all(strand(exclude) == "*"))                       R/bootRanges.R:84
@@ -194,6 +205,11 @@ int nrb200_set_exclude_option(nrb200_handle *h, int32_t option) {
 
 int nrb200_set_plan(nrb200_handle *h, const nrb200_plan_spec *spec, int64_t *n_blocks) {
     if (!h || !spec) return NRB200_ERR_INVALID;
+    if (is_group(h)) {
+        const int rc = group_all(h, [&](int, nrb200_handle *m) { return nrb200_set_plan(m, spec, nullptr); });
+        if (rc == NRB200_OK && n_blocks) *n_blocks = h->members[0]->plan.n_blocks();
+        return rc;
+    }
     NRB_CUDA(h, cudaSetDevice(h->device));
     if (!h->have_y && !h->y_pending) return fail(h, NRB200_ERR_STATE, "call nrb200_set_ranges() first (the plan needs seqlengths)");
     Plan p;
@@ -277,6 +293,7 @@ int nrb200_set_plan(nrb200_handle *h, const nrb200_plan_spec *spec, int64_t *n_b
 }
 
 int nrb200_get_tiles(const nrb200_handle *h, int32_t *tile_seqid, int32_t *tile_start, int32_t *bait_width) {
+    if (is_group(h)) h = h->members[0];
     if (!h || !h->have_plan) return NRB200_ERR_STATE;
     const size_t bytes = (size_t)h->plan.n_blocks() * sizeof(int32_t);
     if (tile_seqid) std::memcpy(tile_seqid, h->plan.tile_seq.data(), bytes);
@@ -288,13 +305,14 @@ int nrb200_get_tiles(const nrb200_handle *h, int32_t *tile_seqid, int32_t *tile_
 int nrb200_run_counts_resident(nrb200_handle *h, const nrb200_draws *draws, int32_t want_feature_counts,
                                nrb200_stats *stats) {
     if (!h) return NRB200_ERR_INVALID;
+    if (is_group(h)) return fail(h, NRB200_ERR_UNSUPPORTED, "device-resident results are per GPU: use one handle per device (or nrb200_run_counts)");
     NRB_CUDA(h, cudaSetDevice(h->device));
     return run_counts_core(h, draws, want_feature_counts != 0, nullptr, stats);
 }
 
 int nrb200_resident_pointers(const nrb200_handle *h, void **iter_nranges_dev, void **iter_totals_dev,
                              void **feature_counts_dev) {
-    if (!h) return NRB200_ERR_INVALID;
+    if (!h || is_group(h)) return NRB200_ERR_INVALID;
     if (iter_nranges_dev) *iter_nranges_dev = h->d_iter_nranges.p;
     if (iter_totals_dev) *iter_totals_dev = h->d_iter_totals.p;
     if (feature_counts_dev) *feature_counts_dev = h->res_has_counts ? h->d_counts.p : nullptr;
@@ -304,6 +322,7 @@ int nrb200_resident_pointers(const nrb200_handle *h, void **iter_nranges_dev, vo
 int nrb200_run_counts(nrb200_handle *h, const nrb200_draws *draws, int64_t *iter_nranges, int64_t *iter_totals,
                       int32_t *feature_counts, nrb200_stats *stats) {
     if (!h) return NRB200_ERR_INVALID;
+    if (is_group(h)) return group_run_counts(h, draws, iter_nranges, iter_totals, feature_counts, stats);
     NRB_CUDA(h, cudaSetDevice(h->device));
     int rc = run_counts_core(h, draws, feature_counts != nullptr, feature_counts, stats);
     if (rc) return rc;
@@ -320,6 +339,7 @@ int nrb200_run_counts(nrb200_handle *h, const nrb200_draws *draws, int64_t *iter
 
 int nrb200_moments_reset(nrb200_handle *h) {
     if (!h) return NRB200_ERR_INVALID;
+    if (is_group(h)) return group_all(h, [](int, nrb200_handle *m) { return nrb200_moments_reset(m); });
     NRB_CUDA(h, cudaSetDevice(h->device));
     const int64_t G = h->query.n;
     if (G == 0) return fail(h, NRB200_ERR_STATE, "moments need a query (nrb200_set_query)");
@@ -330,17 +350,19 @@ int nrb200_moments_reset(nrb200_handle *h) {
     NRB_CUDA(h, cudaMemsetAsync(h->m_sumsq.p, 0, G * 8, h->stream));
     NRB_CUDA(h, cudaMemsetAsync(h->m_nge.p, 0, G * 8, h->stream));
     h->moments_ready = true;
+    h->moments_G = G;
     return NRB200_OK;
 }
 
 int nrb200_run_moments(nrb200_handle *h, const nrb200_draws *draws, int64_t batch_iter, const int32_t *observed,
                        int64_t *iter_nranges, int64_t *iter_totals, nrb200_stats *stats) {
     if (!h || !draws) return NRB200_ERR_INVALID;
+    if (is_group(h)) return group_run_moments(h, draws, batch_iter, observed, iter_nranges, iter_totals, stats);
     NRB_CUDA(h, cudaSetDevice(h->device));
     const int64_t G = h->query.n;
     if (G == 0) return fail(h, NRB200_ERR_STATE, "moments need a query (nrb200_set_query)");
     int rc;
-    if (!h->moments_ready && (rc = nrb200_moments_reset(h))) return rc;
+    if ((!h->moments_ready || h->moments_G != G) && (rc = nrb200_moments_reset(h))) return rc;
     if (observed && (rc = upload(h, h->m_observed, observed, (size_t)G))) return rc;
     if (batch_iter <= 0) batch_iter = std::max<int64_t>(1, std::min<int64_t>(draws->n_iter, ((int64_t)1 << 28) / std::max<int64_t>(G, 1)));
     const int64_t B = h->plan.n_blocks();
@@ -378,9 +400,10 @@ int nrb200_run_moments(nrb200_handle *h, const nrb200_draws *draws, int64_t batc
 
 int nrb200_moments_fetch(nrb200_handle *h, int64_t *feat_sum, int64_t *feat_sumsq, int64_t *feat_n_ge_observed) {
     if (!h) return NRB200_ERR_INVALID;
-    if (!h->moments_ready) return fail(h, NRB200_ERR_STATE, "no moments accumulated");
+    if (is_group(h)) return group_moments_fetch(h, feat_sum, feat_sumsq, feat_n_ge_observed);
+    if (!h->moments_ready || h->moments_G != h->query.n) return fail(h, NRB200_ERR_STATE, "no moments accumulated for this query");
     NRB_CUDA(h, cudaSetDevice(h->device));
-    const size_t bytes = (size_t)h->query.n * 8;
+    const size_t bytes = (size_t)h->moments_G * 8;
     if (feat_sum) NRB_CUDA(h, cudaMemcpyAsync(feat_sum, h->m_sum.p, bytes, cudaMemcpyDeviceToHost, h->stream));
     if (feat_sumsq) NRB_CUDA(h, cudaMemcpyAsync(feat_sumsq, h->m_sumsq.p, bytes, cudaMemcpyDeviceToHost, h->stream));
     if (feat_n_ge_observed) NRB_CUDA(h, cudaMemcpyAsync(feat_n_ge_observed, h->m_nge.p, bytes, cudaMemcpyDeviceToHost, h->stream));
@@ -390,6 +413,7 @@ int nrb200_moments_fetch(nrb200_handle *h, int64_t *feat_sum, int64_t *feat_sums
 
 int nrb200_set_weights(nrb200_handle *h, const double *weights) {
     if (!h) return NRB200_ERR_INVALID;
+    if (is_group(h)) return group_all(h, [&](int, nrb200_handle *m) { return nrb200_set_weights(m, weights); });
     NRB_CUDA(h, cudaSetDevice(h->device));
     if (!h->have_y) return fail(h, NRB200_ERR_STATE, "call nrb200_set_ranges() first");
     if (!weights) {
@@ -497,11 +521,13 @@ static int run_weighted_core(nrb200_handle *h, const nrb200_draws *draws, double
 }
 
 int nrb200_run_weighted(nrb200_handle *h, const nrb200_draws *draws, double *iter_sums, double *feature_sums, nrb200_stats *stats) {
+    if (is_group(h)) return group_run_weighted(h, draws, iter_sums, feature_sums, stats);
     return run_weighted_core(h, draws, iter_sums, feature_sums, nullptr, stats);
 }
 
 int nrb200_run_weighted_moments(nrb200_handle *h, const nrb200_draws *draws, const double *observed, double *iter_sums,
                                 double *feat_sum, double *feat_sumsq, int64_t *feat_n_ge_observed, nrb200_stats *stats) {
+    if (is_group(h)) return group_run_weighted_moments(h, draws, observed, iter_sums, feat_sum, feat_sumsq, feat_n_ge_observed, stats);
     const WeightedMoments mom{observed, feat_sum, feat_sumsq, feat_n_ge_observed};
     return run_weighted_core(h, draws, iter_sums, nullptr, &mom, stats);
 }
@@ -512,6 +538,7 @@ int nrb200_count_observed(nrb200_handle *h, int32_t *feature_counts, int64_t *to
 
 int nrb200_count_observed_ex(nrb200_handle *h, int32_t minoverlap, int32_t *feature_counts, int64_t *total) {
     if (!h) return NRB200_ERR_INVALID;
+    if (is_group(h)) return group_lead(h, [&](nrb200_handle *m) { return nrb200_count_observed_ex(m, minoverlap, feature_counts, total); });
     NRB_CUDA(h, cudaSetDevice(h->device));
     if (minoverlap < 0) return fail(h, NRB200_ERR_INVALID, "'minoverlap' must be >= 0");
     if (minoverlap > 0 && h->query_widen > 0) return fail(h, NRB200_ERR_INVALID, "'maxgap' and 'minoverlap' cannot both be set");
@@ -555,6 +582,7 @@ int nrb200_count_observed_ex(nrb200_handle *h, int32_t minoverlap, int32_t *feat
 
 int nrb200_run_materialize(nrb200_handle *h, const nrb200_draws *draws, int64_t *iter_offsets, nrb200_stats *stats) {
     if (!h || !draws) return NRB200_ERR_INVALID;
+    if (is_group(h)) return group_lead(h, [&](nrb200_handle *m) { return nrb200_run_materialize(m, draws, iter_offsets, stats); });
     NRB_CUDA(h, cudaSetDevice(h->device));
     int rc;
     if ((rc = prepare(h))) return rc;
@@ -592,7 +620,11 @@ int nrb200_run_materialize(nrb200_handle *h, const nrb200_draws *draws, int64_t 
     std::vector<int64_t> per_iter(R), offs(R + 1, 0);
     if ((rc = fetch_u64_as_i64(h, h->d_iter_nranges, R, per_iter.data()))) return rc;
     if (int rc_sync = sync_stream(h)) return rc_sync;
-    for (int64_t r = 0; r < R; ++r) offs[r + 1] = offs[r] + per_iter[r];
+    for (int64_t r = 0; r < R; ++r) {
+        // positions inside an iteration are int32 (within_off): an iteration of 2^31 rows or more cannot be laid out
+        if (per_iter[r] > (int64_t)INT32_MAX) return fail(h, NRB200_ERR_UNSUPPORTED, "an iteration holds more than 2^31 - 1 rows");
+        offs[r + 1] = offs[r] + per_iter[r];
+    }
     const int64_t rows = offs[R];
     if ((rc = upload(h, h->iter_off_dev, offs.data(), (size_t)R + 1))) return rc;
     for (DevMem *m : {&h->row_seq, &h->row_start, &h->row_end, &h->row_src, &h->row_block})
@@ -642,6 +674,7 @@ int nrb200_run_materialize(nrb200_handle *h, const nrb200_draws *draws, int64_t 
 int nrb200_fetch_rows(nrb200_handle *h, int64_t row0, int64_t n, int32_t *seqid, int32_t *start, int32_t *end,
                       int32_t *src_idx, int32_t *block) {
     if (!h) return NRB200_ERR_INVALID;
+    if (is_group(h)) return group_lead(h, [&](nrb200_handle *m) { return nrb200_fetch_rows(m, row0, n, seqid, start, end, src_idx, block); });
     NRB_CUDA(h, cudaSetDevice(h->device));
     if (row0 < 0 || n < 0 || row0 + n > h->n_rows) return fail(h, NRB200_ERR_INVALID, "fetch_rows: range outside the materialised table");
     struct { int32_t *dst; DevMem *src; } cols[] = {{seqid, &h->row_seq}, {start, &h->row_start}, {end, &h->row_end},
@@ -651,6 +684,19 @@ int nrb200_fetch_rows(nrb200_handle *h, int64_t row0, int64_t n, int32_t *seqid,
         if (c.dst && n)
             if (int rc = download(h, c.dst, c.src->as<int32_t>() + row0, (size_t)n * 4)) return rc;
     return NRB200_OK;
+}
+
+int nrb200_fetch_dst_tiles(nrb200_handle *h, int64_t r0, int64_t n, int32_t *dst_tile) {
+    if (!h) return NRB200_ERR_INVALID;
+    if (is_group(h)) return group_lead(h, [&](nrb200_handle *m) { return nrb200_fetch_dst_tiles(m, r0, n, dst_tile); });
+    NRB_CUDA(h, cudaSetDevice(h->device));
+    if (!h->have_plan || !h->plan.permute()) return fail(h, NRB200_ERR_STATE, "fetch_dst_tiles: the last plan is not a permute variant");
+    const int64_t B = h->plan.n_blocks();
+    if (r0 < 0 || n < 0 || (size_t)(r0 + n) * B * 4 > h->d_dst_tile.cap || (size_t)(r0 + n) * B > (size_t)h->dst_tile_items)
+        return fail(h, NRB200_ERR_INVALID, "fetch_dst_tiles: iterations outside the last run");
+    if (n == 0 || !dst_tile) return NRB200_OK;
+    NRB_CUDA(h, cudaMemcpyAsync(dst_tile, h->d_dst_tile.as<int32_t>() + r0 * B, (size_t)n * B * 4, cudaMemcpyDeviceToHost, h->stream));
+    return sync_stream(h);
 }
 
 void nrb200_expand_runs(const int64_t *offsets, int64_t n_runs, int32_t first, int32_t *out) {

@@ -23,8 +23,8 @@ struct RangesView {            // canonical (seqname, start, end) order
     const int32_t *src;        // index in the caller's order; nullptr = identity (the input was already canonical)
     const int32_t *seq_off;    // [n_seq + 1]
     const int4 *seq_info;      // [n_seq] {seq_off[c], seq_off[c+1], max_pos[c], first table entry} in one 16-byte load
-    const uint32_t *rank_start;  // packed rank tables over start / pmax, see "direct-address rank tables" below
-    const uint32_t *rank_pmax;
+    const uint2 *rank_start;   // packed rank tables over start / pmax, see "direct-address rank tables" below
+    const uint2 *rank_pmax;
     int rank_shift;
     // Rank path.  When strand can matter the ranges are ALSO kept grouped by strand class inside each
     // sequence ("virtual sequence" v = seq * n_cls + class), so that a count can be taken per class; class =
@@ -36,7 +36,7 @@ struct RangesView {            // canonical (seqname, start, end) order
     int32_t end_shift;                       // all ranges equally wide (w): end order = start order, end_sorted aliases
                                              // rstart and #{end < b} = #{start < b - (w - 1)}; end_shift = w - 1, else 0
     const int4 *rseq_info;                   // [n_seq * n_cls]
-    const uint32_t *rrank_start, *rank_end;  // tables over rstart / end_sorted
+    const uint2 *rrank_start, *rank_end;     // tables over rstart / end_sorted
 };
 
 struct SliceView {             // query or exclude (or, for "trim", the gaps), canonical order, plus a per-tile window
@@ -106,35 +106,73 @@ __device__ __forceinline__ int32_t first_ge(const int32_t *__restrict__ v, int32
 
 // ---- direct-address rank tables --------------------------------------------------------
 // One table per ascending per-sequence array (start, running-max end, sorted end).  Entry u of a
-// sequence describes bucket u = [u << shift, (u + 1) << shift):
-//     entry = (first << 3) | min(count, 7)
+// sequence describes bucket u = [u << shift, (u + 1) << shift) in 8 bytes:
+//     .x = (first << 3) | min(count, 7)
+//     .y = the bucket's first values themselves, as offsets from the bucket's lower end
 // first = index, relative to the sequence's first range, of the first value >= u << shift;
-// count = values inside the bucket.  One 4-byte probe therefore yields both ends of the bucket
-// (count == 7 means "7 or more": the next entry holds the end).
+// count = values inside the bucket (7 means "7 or more": the next entry holds the end).
+// .y holds three 10-bit offsets when shift <= 10 (kInlineShift) and one 32-bit offset otherwise;
+// unused slots are all ones, which no key offset exceeds.  A rank query is therefore ONE 8-byte
+// load -- one 32-byte sector -- and touches the value array only when a bucket holds more values
+// than are inlined and the key lies beyond the last inlined one.
+typedef uint2 RankEntry;
 constexpr int kHitSlots = 64;  // the H statistic is tallied in this many places so that no single address takes every atomic
 constexpr int kRankCountBits = 3;
 constexpr int32_t kRankCountCap = (1 << kRankCountBits) - 1;
+constexpr int kInlineShift = 10;                 // up to this shift an entry inlines three values
+constexpr uint32_t kInlineMask = (1u << kInlineShift) - 1u;
 
 __device__ __forceinline__ int32_t rank_clamp_key(int32_t key, const int4 si) {
     return min(max(key, 0), si.z + 1);  // key <= 0 -> si.x and key > max_pos -> si.y fall out of the table
 }
 
-// First index of a sequence (si = seq_info[c]) whose value in `vals` is >= key.  Branch-free in the
-// common case: one table probe, then the first three values of the bucket read together.
-__device__ __forceinline__ int32_t first_ge_ranked(const int32_t *__restrict__ vals, const uint32_t *__restrict__ table,
+// Entry of a bucket from its values: vals[p .. q) are the values inside bucket `base`..; a = first index of the sequence.
+__device__ __forceinline__ RankEntry rank_entry_pack(const int32_t *__restrict__ vals, int32_t a, int32_t p, int32_t q, int64_t base,
+                                                     int shift) {
+    RankEntry e;
+    e.x = ((uint32_t)(p - a) << kRankCountBits) | (uint32_t)min(q - p, kRankCountCap);
+    if (shift <= kInlineShift) {
+        uint32_t o[3] = {kInlineMask, kInlineMask, kInlineMask};
+#pragma unroll
+        for (int k = 0; k < 3; ++k)
+            if (p + k < q) o[k] = (uint32_t)((int64_t)__ldg(vals + p + k) - base);
+        e.y = o[0] | (o[1] << kInlineShift) | (o[2] << (2 * kInlineShift));
+    } else {
+        e.y = p < q ? (uint32_t)((int64_t)__ldg(vals + p) - base) : 0xffffffffu;
+    }
+    return e;
+}
+
+// Rank from a loaded entry: first index of the sequence whose value is >= key (key already clamped, u its entry).
+__device__ __forceinline__ int32_t rank_from_entry(const int32_t *__restrict__ vals, const RankEntry *__restrict__ table, int rank_shift,
+                                                   const int4 si, int32_t key, int32_t u, const RankEntry e) {
+    const int32_t a = si.x + (int32_t)(e.x >> kRankCountBits), n = (int32_t)(e.x & kRankCountCap);
+    const uint32_t koff = (uint32_t)key & ((1u << rank_shift) - 1u);
+    int32_t below, inlined;
+    bool beyond;  // every inlined value is below the key
+    if (rank_shift <= kInlineShift) {
+        const uint32_t o0 = e.y & kInlineMask, o1 = (e.y >> kInlineShift) & kInlineMask, o2 = (e.y >> (2 * kInlineShift)) & kInlineMask;
+        below = (o0 < koff) + (o1 < koff) + (o2 < koff);
+        beyond = o2 < koff;
+        inlined = 3;
+    } else {
+        below = e.y < koff;
+        beyond = below;
+        inlined = 1;
+    }
+    if (n > inlined && beyond) {  // rare: the bucket holds more values than the entry inlines and the key lies beyond them
+        const int32_t b = n < kRankCountCap ? a + n : si.x + (int32_t)(__ldg(table + u + 1).x >> kRankCountBits);
+        return first_ge(vals, a + inlined, b, key);
+    }
+    return a + below;
+}
+
+// First index of a sequence (si = seq_info[c]) whose value in `vals` is >= key: one table probe.
+__device__ __forceinline__ int32_t first_ge_ranked(const int32_t *__restrict__ vals, const RankEntry *__restrict__ table,
                                                    int rank_shift, const int4 si, int32_t key) {
     key = rank_clamp_key(key, si);
     const int32_t u = si.w + (key >> rank_shift);
-    const uint32_t e = __ldg(table + u);
-    const int32_t a = si.x + (int32_t)(e >> kRankCountBits), n = (int32_t)(e & kRankCountCap);
-    const int32_t v0 = n > 0 ? __ldg(vals + a) : INT32_MAX;
-    const int32_t v1 = n > 1 ? __ldg(vals + a + 1) : INT32_MAX;
-    const int32_t v2 = n > 2 ? __ldg(vals + a + 2) : INT32_MAX;
-    if (v2 < key) {  // rare: more than three values in the bucket and the first three are below the key
-        const int32_t b = n < kRankCountCap ? a + n : si.x + (int32_t)(__ldg(table + u + 1) >> kRankCountBits);
-        return first_ge(vals, a + 3, b, key);
-    }
-    return a + (v0 < key) + (v1 < key) + (v2 < key);
+    return rank_from_entry(vals, table, rank_shift, si, key, u, __ldg(table + u));
 }
 
 // Hits of the bait block [s, e] on sequence c are a window [lo, hi) of the canonical order:

@@ -19,9 +19,11 @@
 //   index.cuh  loading y / query / exclude, canonical order, rank tables, weight running sums
 //   lists.cuh  per-tile slices, gaps(exclude), signed window lists of the rank path
 //   run.cuh    dispatch, block draws, launches, core of the counting entry points
+//   group.cuh  device groups: one handle sharding the iterations over several GPUs
 //   api.cuh    extern "C" entry points (include/nrb200.h)
 #include "handle.h"
 #include "index.cuh"
 #include "lists.cuh"
 #include "run.cuh"
+#include "group.cuh"
 #include "api.cuh"

@@ -1,0 +1,373 @@
+// libnrb200: device groups -- one handle that shards the bootstrap iterations over several GPUs of the box.
+// (textually included by engine.cu, before api.cuh)
+//
+// The reference's iterations are independent (replicate(R, ...), R/bootRanges.R:90) and its result is ONE table /
+// matrix for one caller (R/bootRanges.R:120-122).  A handle created with nrb200_config.n_devices > 1 keeps one
+// ordinary single-GPU handle per device ("members") and serves the same entry points:
+//   * inputs (y, query, exclude, plan, weights) go to every member from the caller's ONE host copy, in parallel
+//     (one host thread and one PCIe link per GPU); a pageable y is first copied into pinned memory once;
+//   * the window lists of the rank path are built once, by the leader (member 0), and uploaded by the others;
+//   * member k runs iterations [ceil(k R / W), ceil((k + 1) R / W)) -- Philox is keyed by the GLOBAL iteration, so the
+//     result does not depend on W -- and copies its rows of the count matrix straight into the caller's matrix
+//     (W device-to-host copies in parallel, no collective: the result lives on the host);
+//   * per-feature moments are summed over the members on the host (3 G words per member).
+// The caller's thread drives member 0 itself; members 1.. have a worker thread each.  R's API is single-threaded:
+// workers never touch anything but the plain C arrays the caller handed in.
+namespace nrb {
+
+struct GroupPool {
+    int n_workers = 0;                      // members 1 .. n_workers
+    std::vector<std::thread> threads;
+    std::mutex mu;
+    std::condition_variable cv;
+    std::atomic<uint64_t> generation{0};
+    std::atomic<int> pending{0};
+    std::atomic<bool> stop{false};
+    std::function<int(int)> task;           // task(member index) -> status
+    std::vector<int> rc;
+
+    static void spin_pause() {
+#if defined(__x86_64__) || defined(__i386__)
+        __builtin_ia32_pause();
+#endif
+    }
+
+    void worker(int k) {
+        uint64_t seen = 0;
+        for (;;) {
+            // calls of one front-end step follow each other within microseconds: spin briefly before sleeping
+            bool got = false;
+            const auto t0 = std::chrono::steady_clock::now();
+            for (int i = 0;; ++i) {
+                if (generation.load(std::memory_order_acquire) != seen || stop.load(std::memory_order_acquire)) {
+                    got = true;
+                    break;
+                }
+                spin_pause();
+                if ((i & 255) == 255 && std::chrono::steady_clock::now() - t0 > std::chrono::microseconds(300)) break;
+            }
+            if (!got) {
+                std::unique_lock<std::mutex> lk(mu);
+                cv.wait(lk, [&] { return generation.load(std::memory_order_acquire) != seen || stop.load(std::memory_order_acquire); });
+            }
+            if (stop.load(std::memory_order_acquire)) return;
+            seen = generation.load(std::memory_order_acquire);
+            rc[k] = task(k);
+            pending.fetch_sub(1, std::memory_order_acq_rel);
+        }
+    }
+
+    void start(int workers) {
+        n_workers = workers;
+        rc.assign((size_t)workers + 1, 0);
+        for (int k = 1; k <= workers; ++k) threads.emplace_back([this, k] { worker(k); });
+    }
+
+    // Runs fn(k) for k = 0 .. n_workers (k = 0 on the calling thread); returns when all are done.
+    void run(const std::function<int(int)> &fn) {
+        task = fn;
+        pending.store(n_workers, std::memory_order_release);
+        {
+            std::lock_guard<std::mutex> lk(mu);
+            generation.fetch_add(1, std::memory_order_acq_rel);
+        }
+        cv.notify_all();
+        rc[0] = fn(0);
+        for (int i = 0; pending.load(std::memory_order_acquire) > 0; ++i) {
+            spin_pause();
+            if ((i & 1023) == 1023) std::this_thread::yield();
+        }
+    }
+
+    ~GroupPool() {
+        {
+            std::lock_guard<std::mutex> lk(mu);
+            stop.store(true, std::memory_order_release);
+        }
+        cv.notify_all();
+        for (auto &t : threads) t.join();
+    }
+};
+
+}  // namespace nrb
+
+namespace {
+
+inline bool is_group(const nrb200_handle *h) { return h && !h->members.empty(); }
+inline int group_size(const nrb200_handle *h) { return (int)h->members.size(); }
+
+// [lo, hi) of member k: iterations {r : floor(r W / R) == k}  (the same split as nullranges_b200/sharding.py)
+inline void shard_iterations(int64_t R, int W, int k, int64_t &lo, int64_t &hi) {
+    lo = ((int64_t)k * R + W - 1) / W;
+    hi = ((int64_t)(k + 1) * R + W - 1) / W;
+}
+
+// fn(k, member) on every member in parallel; the first failure's status and message become the group's.
+int group_all(nrb200_handle *g, const std::function<int(int, nrb200_handle *)> &fn) {
+    g->pool->run([&](int k) { return fn(k, g->members[k]); });
+    for (int k = 0; k < group_size(g); ++k)
+        if (g->pool->rc[k] != NRB200_OK) {
+            g->error = "GPU " + std::to_string(g->members[k]->device) + ": " + g->members[k]->error;
+            return g->pool->rc[k];
+        }
+    return NRB200_OK;
+}
+
+// The draws of member k's shard.
+nrb200_draws shard_draws(const nrb200_handle *g, const nrb200_draws *d, int k, int64_t &lo, int64_t &n) {
+    int64_t hi;
+    shard_iterations(d->n_iter, group_size(g), k, lo, hi);
+    n = hi - lo;
+    nrb200_draws s = *d;
+    s.n_iter = n;
+    s.iter0 = d->iter0 + lo;
+    const int64_t B = g->members[0]->plan.n_blocks();
+    if (d->rng_mode == NRB200_RNG_HOST) {
+        if (d->bait_seqid) s.bait_seqid = d->bait_seqid + lo * B;
+        if (d->bait_start) s.bait_start = d->bait_start + lo * B;
+        if (d->dst_tile) s.dst_tile = d->dst_tile + lo * B;
+    }
+    return s;
+}
+
+void merge_stats(nrb200_stats *out, const std::vector<nrb200_stats> &st) {
+    if (!out) return;
+    std::memset(out, 0, sizeof *out);
+    for (const nrb200_stats &s : st) {  // times: the slowest member; volumes: all members
+        out->kernel_ms = std::max(out->kernel_ms, s.kernel_ms);
+        out->total_ms = std::max(out->total_ms, s.total_ms);
+        out->rows_kernel_ms = std::max(out->rows_kernel_ms, s.rows_kernel_ms);
+        out->count_kernel_ms = std::max(out->count_kernel_ms, s.count_kernel_ms);
+        out->n_launches += s.n_launches;
+        out->n_hits += s.n_hits;
+        out->h2d_bytes += s.h2d_bytes;
+        out->d2h_bytes += s.d2h_bytes;
+        out->n_windows = std::max(out->n_windows, s.n_windows);
+    }
+}
+
+// fn(leader) on the calling thread: entry points a group serves with its first device only.
+int group_lead(nrb200_handle *g, const std::function<int(nrb200_handle *)> &fn) {
+    nrb200_handle *lead = g->members[0];
+    const int rc = fn(lead);
+    if (rc) g->error = "GPU " + std::to_string(lead->device) + ": " + lead->error;
+    return rc;
+}
+
+
+// Before a run: the leader prepares first (it builds the window lists, with all host threads), the others then take
+// its lists.  Nothing happens when no input changed since the last run.
+int group_prepare(nrb200_handle *g) {
+    nrb200_handle *lead = g->members[0];
+    NRB_CUDA(g, cudaSetDevice(lead->device));
+    const int share = lead->omp_threads;
+    lead->omp_threads = 0;
+    const int rc = prepare(lead);
+    lead->omp_threads = share;
+    if (rc) {
+        g->error = "GPU " + std::to_string(lead->device) + ": " + lead->error;
+        return rc;
+    }
+    return NRB200_OK;
+}
+
+int group_create(const nrb200_config *cfg, nrb200_handle **out) {
+    const int W = cfg->n_devices;
+    if (!cfg->devices) return fail(nullptr, NRB200_ERR_INVALID, "nrb200_create: n_devices > 1 needs the device list");
+    if (cfg->stream) return fail(nullptr, NRB200_ERR_INVALID, "nrb200_create: a device group runs on private streams (stream must be NULL)");
+    // NRB200_ALLOW_DUP_DEVICES=1 (tests on a one-GPU box): members may share a GPU -- same code path, no speed-up
+    const bool dup_ok = getenv("NRB200_ALLOW_DUP_DEVICES") != nullptr;
+    for (int a = 0; a < W && !dup_ok; ++a)
+        for (int b = a + 1; b < W; ++b)
+            if (cfg->devices[a] == cfg->devices[b]) return fail(nullptr, NRB200_ERR_INVALID, "nrb200_create: a device is listed twice");
+    nrb200_handle *g = new nrb200_handle();
+    g->device = cfg->devices[0];
+    g->flags = cfg->flags;
+    const int cores = omp_get_max_threads();
+    for (int k = 0; k < W; ++k) {
+        nrb200_config one{};
+        one.device = cfg->devices[k];
+        one.flags = cfg->flags;
+        nrb200_handle *m = nullptr;
+        const int rc = nrb200_create(&one, &m);
+        if (rc) {
+            for (nrb200_handle *x : g->members) nrb200_destroy(x);
+            delete g;
+            return rc;  // the message is already in place
+        }
+        m->omp_threads = std::max(1, cores / W);
+        m->keep_lists = k == 0;
+        m->lists_from = k == 0 ? nullptr : g->members[0];
+        g->members.push_back(m);
+    }
+    g->pool = new GroupPool();
+    g->pool->start(W - 1);
+    *out = g;
+    return NRB200_OK;
+}
+
+void group_destroy(nrb200_handle *g) {
+    delete g->pool;  // joins the workers
+    for (nrb200_handle *m : g->members) nrb200_destroy(m);
+    if (g->g_stage) {
+        cudaSetDevice(g->device);
+        cudaFreeHost(g->g_stage);
+    }
+    delete g;
+}
+
+// y for every member.  A large pageable y is copied into pinned memory once (all host threads), so that each
+// member's upload is a plain DMA from the same pinned copy.
+int group_set_ranges_begin(nrb200_handle *g, int64_t n, int32_t n_seq, const int64_t *seqlengths, const int32_t *seqid,
+                           const int32_t *start, const int32_t *end, const int8_t *strand) {
+    NRB_CUDA(g, cudaSetDevice(g->device));
+    const size_t col = ((size_t)std::max<int64_t>(n, 0) * 4 + 4095) & ~(size_t)4095;
+    if (n > 0 && seqid && start && end && (size_t)n * 4 >= ((size_t)256 << 10) && (size_t)n * 4 <= ((size_t)1 << 30)) {
+        cudaPointerAttributes attr{};
+        const bool pageable = cudaPointerGetAttributes(&attr, start) != cudaSuccess || attr.type == cudaMemoryTypeUnregistered;
+        cudaGetLastError();
+        if (pageable) {
+            const size_t need = 4 * col;
+            if (g->g_stage_cap < need) {
+                if (g->g_stage) cudaFreeHost(g->g_stage);
+                g->g_stage = nullptr;
+                g->g_stage_cap = 0;
+                if (cudaMallocHost(&g->g_stage, need) == cudaSuccess) g->g_stage_cap = need;
+                else cudaGetLastError();
+            }
+            if (g->g_stage_cap >= need) {
+                char *base = static_cast<char *>(g->g_stage);
+                const void *src[4] = {seqid, start, end, strand};
+                const size_t bytes[4] = {(size_t)n * 4, (size_t)n * 4, (size_t)n * 4, strand ? (size_t)n : 0};
+                const size_t piece = (size_t)1 << 20;
+                for (int c = 0; c < 4; ++c) {
+                    const int64_t pieces = (int64_t)((bytes[c] + piece - 1) / piece);
+#pragma omp parallel for schedule(static)
+                    for (int64_t i = 0; i < pieces; ++i)
+                        std::memcpy(base + c * col + i * piece, static_cast<const char *>(src[c]) + i * piece,
+                                    std::min(piece, bytes[c] - (size_t)i * piece));
+                }
+                seqid = reinterpret_cast<const int32_t *>(base);
+                start = reinterpret_cast<const int32_t *>(base + col);
+                end = reinterpret_cast<const int32_t *>(base + 2 * col);
+                if (strand) strand = reinterpret_cast<const int8_t *>(base + 3 * col);
+            }
+        }
+    }
+    return group_all(g, [&](int, nrb200_handle *m) { return nrb200_set_ranges_begin(m, n, n_seq, seqlengths, seqid, start, end, strand); });
+}
+
+// ---- runs: member k takes its shard and writes straight into the caller's arrays ------------------------------
+
+int group_run_counts(nrb200_handle *g, const nrb200_draws *d, int64_t *iter_nranges, int64_t *iter_totals, int32_t *feature_counts,
+                     nrb200_stats *stats) {
+    if (!d || d->n_iter < 0) return fail(g, NRB200_ERR_INVALID, "draws: n_iter must be >= 0");
+    int rc;
+    if ((rc = group_prepare(g))) return rc;
+    const int64_t G = g->members[0]->query.n;
+    std::vector<nrb200_stats> st((size_t)group_size(g));
+    rc = group_all(g, [&](int k, nrb200_handle *m) {
+        int64_t lo, n;
+        const nrb200_draws s = shard_draws(g, d, k, lo, n);
+        return nrb200_run_counts(m, &s, iter_nranges ? iter_nranges + lo : nullptr, iter_totals ? iter_totals + lo : nullptr,
+                                 feature_counts ? feature_counts + lo * G : nullptr, stats ? &st[k] : nullptr);
+    });
+    if (rc) return rc;
+    merge_stats(stats, st);
+    return NRB200_OK;
+}
+
+int group_run_moments(nrb200_handle *g, const nrb200_draws *d, int64_t batch_iter, const int32_t *observed, int64_t *iter_nranges,
+                      int64_t *iter_totals, nrb200_stats *stats) {
+    if (!d || d->n_iter < 0) return fail(g, NRB200_ERR_INVALID, "draws: n_iter must be >= 0");
+    int rc;
+    if ((rc = group_prepare(g))) return rc;
+    std::vector<nrb200_stats> st((size_t)group_size(g));
+    rc = group_all(g, [&](int k, nrb200_handle *m) {
+        int64_t lo, n;
+        const nrb200_draws s = shard_draws(g, d, k, lo, n);
+        return nrb200_run_moments(m, &s, batch_iter, observed, iter_nranges ? iter_nranges + lo : nullptr,
+                                  iter_totals ? iter_totals + lo : nullptr, stats ? &st[k] : nullptr);
+    });
+    if (rc) return rc;
+    merge_stats(stats, st);
+    return NRB200_OK;
+}
+
+// Per-feature moment vectors of all members, summed on the host in member order.
+int group_moments_fetch(nrb200_handle *g, int64_t *feat_sum, int64_t *feat_sumsq, int64_t *feat_n_ge) {
+    const int W = group_size(g);
+    const size_t G = (size_t)g->members[0]->query.n;
+    std::vector<std::vector<int64_t>> part((size_t)W * 3);
+    const int rc = group_all(g, [&](int k, nrb200_handle *m) {
+        for (int j = 0; j < 3; ++j) part[(size_t)k * 3 + j].assign(G, 0);
+        return nrb200_moments_fetch(m, feat_sum ? part[(size_t)k * 3].data() : nullptr, feat_sumsq ? part[(size_t)k * 3 + 1].data() : nullptr,
+                                    feat_n_ge ? part[(size_t)k * 3 + 2].data() : nullptr);
+    });
+    if (rc) return rc;
+    int64_t *outs[3] = {feat_sum, feat_sumsq, feat_n_ge};
+    for (int j = 0; j < 3; ++j) {
+        if (!outs[j]) continue;
+        std::fill(outs[j], outs[j] + G, (int64_t)0);
+        for (int k = 0; k < W; ++k)
+            for (size_t i = 0; i < G; ++i) outs[j][i] += part[(size_t)k * 3 + j][i];
+    }
+    return NRB200_OK;
+}
+
+int group_run_weighted(nrb200_handle *g, const nrb200_draws *d, double *iter_sums, double *feature_sums, nrb200_stats *stats) {
+    if (!d || d->n_iter < 0) return fail(g, NRB200_ERR_INVALID, "draws: n_iter must be >= 0");
+    int rc;
+    if ((rc = group_prepare(g))) return rc;
+    const int64_t G = g->members[0]->query.n;
+    std::vector<nrb200_stats> st((size_t)group_size(g));
+    rc = group_all(g, [&](int k, nrb200_handle *m) {
+        int64_t lo, n;
+        const nrb200_draws s = shard_draws(g, d, k, lo, n);
+        return nrb200_run_weighted(m, &s, iter_sums ? iter_sums + lo : nullptr, feature_sums ? feature_sums + lo * G : nullptr,
+                                   stats ? &st[k] : nullptr);
+    });
+    if (rc) return rc;
+    merge_stats(stats, st);
+    return NRB200_OK;
+}
+
+// Moments of the weighted sums: every member reduces its shard, the host adds the W partial vectors in member order
+// (double sums: deterministic for a given W; across different W they agree to rounding, as a weighted sum does anyway).
+int group_run_weighted_moments(nrb200_handle *g, const nrb200_draws *d, const double *observed, double *iter_sums, double *feat_sum,
+                               double *feat_sumsq, int64_t *feat_n_ge, nrb200_stats *stats) {
+    if (!d || d->n_iter < 0) return fail(g, NRB200_ERR_INVALID, "draws: n_iter must be >= 0");
+    int rc;
+    if ((rc = group_prepare(g))) return rc;
+    const int W = group_size(g);
+    const size_t G = (size_t)g->members[0]->query.n;
+    std::vector<nrb200_stats> st((size_t)W);
+    std::vector<std::vector<double>> ps((size_t)W), pq((size_t)W);
+    std::vector<std::vector<int64_t>> pg((size_t)W);
+    rc = group_all(g, [&](int k, nrb200_handle *m) {
+        int64_t lo, n;
+        const nrb200_draws s = shard_draws(g, d, k, lo, n);
+        ps[k].assign(G, 0.0);
+        pq[k].assign(G, 0.0);
+        pg[k].assign(G, 0);
+        return nrb200_run_weighted_moments(m, &s, observed, iter_sums ? iter_sums + lo : nullptr, ps[k].data(), pq[k].data(), pg[k].data(),
+                                           stats ? &st[k] : nullptr);
+    });
+    if (rc) return rc;
+    for (size_t i = 0; i < G; ++i) {
+        double a = 0.0, b = 0.0;
+        int64_t c = 0;
+        for (int k = 0; k < W; ++k) {
+            a += ps[k][i];
+            b += pq[k][i];
+            c += pg[k][i];
+        }
+        if (feat_sum) feat_sum[i] = a;
+        if (feat_sumsq) feat_sumsq[i] = b;
+        if (feat_n_ge) feat_n_ge[i] = c;
+    }
+    merge_stats(stats, st);
+    return NRB200_OK;
+}
+
+}  // namespace

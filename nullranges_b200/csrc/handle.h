@@ -7,9 +7,16 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <atomic>
+#include <condition_variable>
+#include <functional>
+#include <mutex>
 #include <numeric>
 #include <string>
+#include <thread>
 #include <vector>
+
+#include <omp.h>
 
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
@@ -144,11 +151,34 @@ struct RangeSet {
     DevMem start, end, pmax, src, strand, seq_off, seqid;
 };
 
+// Window lists of the rank path as the host built them (lists.cuh): kept by the leader of a device group so that the
+// other members upload the same lists instead of building them again.
+struct HostLists {
+    bool valid = false;
+    int64_t n_pairs = 0;
+    std::vector<int32_t> f_src, f_off, x_off, x_rec;
+    std::vector<int32_t> recs;  // 4 words per record: the "a" halves of all records, then the "b" halves
+};
+
+struct GroupPool;
+
 }  // namespace nrb
 
 using namespace nrb;
 
 struct nrb200_handle {
+    // ---- device group (nrb200_config.n_devices > 1): this handle owns no GPU state, it shards the iterations over
+    // its members (one nrb200_handle per GPU, each driven by its own host thread) -- see group.cuh
+    std::vector<nrb200_handle *> members;
+    GroupPool *pool = nullptr;
+    void *g_stage = nullptr;  // pinned copy of a pageable y, so that it crosses the host memory once for all members
+    size_t g_stage_cap = 0;
+    // ---- member of a group
+    nrb200_handle *lists_from = nullptr;  // take the window lists this handle (the group's leader) built
+    bool keep_lists = false;              // leader: keep the host copy of the lists for the others
+    HostLists lists;
+    int omp_threads = 0;                  // host threads of this handle's parallel loops (0 = all)
+
     int device = 0;
     cudaStream_t stream = nullptr;
     bool own_stream = false;
@@ -206,11 +236,9 @@ struct nrb200_handle {
     DevMem r_start, r_end, r_pmax, r_order, r_idx, r_keys_a, r_keys_b, r_voff_dev, rseq_info_dev, rrank_off_dev, rrank_start;
     DevMem rank_off_dev, max_pos_dev, rank_start, rank_pmax, rank_end, end_sorted, sort_keys_a, sort_keys_b, sort_tmp;
     uint32_t flags = 0;
-    // tuning knobs (environment, read at create): NRB200_RPT iterations per thread of the rank count
-    // kernel, NRB200_MINB its min CTAs/SM, NRB200_TABLE_MULT rank-table entries per range
+    // tuning knobs (environment, read at create)
     bool tune_end_rank = true;         // NRB200_END_RANK=0: always radix-sort the ends (index build)
     int tune_rows_ipc = 4;             // NRB200_ROWS_IPC: iterations a CTA of the rows kernel loops over
-    int tune_rpt = 1, tune_minb = 8, tune_minb_rows = 6;  // NRB200_RPT / NRB200_MINB / NRB200_MINB_ROWS (min CTAs per SM: 8 = 32 registers, all 64 warps resident)
     double tune_table_mult = 4.0;
     int tune_chunks = 8;               // NRB200_CHUNKS: pipeline depth of nrb200_run_counts
     int64_t tune_max_batch = 2048;     // NRB200_MAX_BATCH: iterations per launch group
@@ -238,12 +266,16 @@ struct nrb200_handle {
     DevMem m_sum, m_sumsq, m_nge, m_observed;
     DevMem wm_sum, wm_sumsq, wm_nge, wm_observed;  // moments of the weighted sums (double; n_ge int64)
     bool moments_ready = false;
+    int64_t moments_G = 0;  // features the moment buffers were sized (and zeroed) for
     // rows
     DevMem item_rec, item_rows, within_off, iter_off_dev, row_seq, row_start, row_end, row_src, row_block;
     int64_t n_rows = 0;
+    int64_t dst_tile_items = 0;  // [iterations x blocks] the last run left in d_dst_tile (permute kinds)
 };
 
 namespace {
+
+inline int host_threads(const nrb200_handle *h) { return h && h->omp_threads > 0 ? h->omp_threads : omp_get_max_threads(); }
 
 int fail(nrb200_handle *h, int code, const std::string &msg) {
     if (h) h->error = msg; else g_create_error = msg;
@@ -344,7 +376,7 @@ inline int download(nrb200_handle *h, void *dst, const void *src_dev, size_t byt
         char *to = static_cast<char *>(dst) + off;
         const size_t piece = (size_t)1 << 20;
         const int64_t pieces = (int64_t)((len + piece - 1) / piece);
-#pragma omp parallel for schedule(static)
+#pragma omp parallel for schedule(static) num_threads(host_threads(h))
         for (int64_t i = 0; i < pieces; ++i) std::memcpy(to + i * piece, from + i * piece, std::min(piece, len - (size_t)i * piece));
     };
     const size_t chunks = (bytes + kChunk - 1) / kChunk;
@@ -391,7 +423,7 @@ int upload_direct(nrb200_handle *h, DevMem &dst, const T *src, size_t n, int slo
                 char *to = static_cast<char *>(h->stage_in) + (size_t)slot * region;
                 const size_t piece = (size_t)1 << 20;
                 const int64_t pieces = (int64_t)((bytes + piece - 1) / piece);
-#pragma omp parallel for schedule(static)
+#pragma omp parallel for schedule(static) num_threads(host_threads(h))
                 for (int64_t i = 0; i < pieces; ++i)
                     std::memcpy(to + i * piece, reinterpret_cast<const char *>(src) + i * piece, std::min(piece, bytes - (size_t)i * piece));
                 from = to;

@@ -258,15 +258,15 @@ int build_rank_tables(nrb200_handle *h) {
         seq_info[4 * c + 3] = (int32_t)h->rank_off[c];
     }
     if ((rc = upload(h, h->seq_info_dev, seq_info.data(), seq_info.size()))) return rc;
-    NRB_CUDA(h, h->rank_start.reserve(entries * sizeof(int32_t)));
-    NRB_CUDA(h, h->rank_pmax.reserve(entries * sizeof(int32_t)));
+    NRB_CUDA(h, h->rank_start.reserve(entries * sizeof(RankEntry)));
+    NRB_CUDA(h, h->rank_pmax.reserve(entries * sizeof(RankEntry)));
     NRB_CUDA(h, h->end_sorted.reserve(std::max<int64_t>(y.n, 1) * sizeof(int32_t)));
     const int threads = 256;
     const unsigned n_grid = (unsigned)((std::max<int64_t>(y.n, 1) + threads - 1) / threads);
     const unsigned t_grid = rank_table_grid(entries);
     // canonical start table: locate_block() of the streaming kernels, and the rank path of an unstranded y
     build_rank_table_kernel<<<t_grid, threads, 0, h->stream>>>(y.start.as<int32_t>(), y.seq_off.as<int32_t>(),
-                                                               h->rank_off_dev.as<int64_t>(), C, shift, h->rank_start.as<uint32_t>());
+                                                               h->rank_off_dev.as<int64_t>(), C, shift, h->rank_start.as<RankEntry>());
     h->have_pmax_table = false;  // only the streaming kernels need it: built on first use
     NRB_CUDA(h, h->sort_keys_a.reserve(std::max<int64_t>(y.n, 1) * 8));
     NRB_CUDA(h, h->sort_keys_b.reserve(std::max<int64_t>(y.n, 1) * 8));
@@ -286,7 +286,7 @@ int build_rank_tables(nrb200_handle *h) {
     if (h->n_cls == 1) {
         if (h->ends_alias_starts) return NRB200_OK;
         // ends in ascending order within each sequence: radix sort of (seqid << 32 | end)
-        NRB_CUDA(h, h->rank_end.reserve(entries * sizeof(int32_t)));
+        NRB_CUDA(h, h->rank_end.reserve(entries * sizeof(RankEntry)));
         // ranges that are short against their spacing (expected ranges per widest-range window <= 4): the ends are
         // nearly in order already and every range finds its rank with a short scan (end_rank_scatter_kernel);
         // otherwise a radix sort of (seqid << 32 | end)
@@ -295,7 +295,7 @@ int build_rank_tables(nrb200_handle *h) {
             by_rank = (double)y.wmax * (double)(y.h_seq_off[c + 1] - y.h_seq_off[c]) <= 4.0 * (double)std::max<int64_t>(max_pos[c], 1);
         if (by_rank) {
             end_rank_scatter_kernel<<<n_grid, threads, 0, h->stream>>>(y.seqid.as<int32_t>(), y.start.as<int32_t>(), y.end.as<int32_t>(),
-                                                                       h->seq_info_dev.as<int4>(), h->rank_start.as<uint32_t>(), shift, y.n,
+                                                                       h->seq_info_dev.as<int4>(), h->rank_start.as<RankEntry>(), shift, y.n,
                                                                        y.wmax, h->end_sorted.as<int32_t>());
         } else if (y.n > 0) {
             int seq_bits = 1;
@@ -306,7 +306,7 @@ int build_rank_tables(nrb200_handle *h) {
             unpack_end_keys_kernel<<<n_grid, threads, 0, h->stream>>>(h->sort_keys_b.as<unsigned long long>(), y.n, h->end_sorted.as<int32_t>());
         }
         build_rank_table_kernel<<<t_grid, threads, 0, h->stream>>>(h->end_sorted.as<int32_t>(), y.seq_off.as<int32_t>(),
-                                                                   h->rank_off_dev.as<int64_t>(), C, shift, h->rank_end.as<uint32_t>());
+                                                                   h->rank_off_dev.as<int64_t>(), C, shift, h->rank_end.as<RankEntry>());
         NRB_CUDA(h, cudaGetLastError());
         return NRB200_OK;
     }
@@ -320,8 +320,8 @@ int build_rank_tables(nrb200_handle *h) {
         NRB_CUDA(h, m->reserve(std::max<int64_t>(y.n, 1) * 4));
     NRB_CUDA(h, h->r_voff_dev.reserve(((size_t)V + 1) * 4));
     NRB_CUDA(h, h->rseq_info_dev.reserve((size_t)V * sizeof(int4)));
-    NRB_CUDA(h, h->rrank_start.reserve(r_entries * sizeof(int32_t)));
-    NRB_CUDA(h, h->rank_end.reserve(r_entries * sizeof(int32_t)));
+    NRB_CUDA(h, h->rrank_start.reserve(r_entries * sizeof(RankEntry)));
+    NRB_CUDA(h, h->rank_end.reserve(r_entries * sizeof(RankEntry)));
     int v_bits = 1;
     while ((1 << v_bits) < V) ++v_bits;
     if (y.n > 0) {
@@ -354,10 +354,10 @@ int build_rank_tables(nrb200_handle *h) {
         h->rseq_info_dev.as<int4>());
     const unsigned rt_grid = rank_table_grid(r_entries);
     build_rank_table_kernel<<<rt_grid, threads, 0, h->stream>>>(h->r_start.as<int32_t>(), h->r_voff_dev.as<int32_t>(),
-                                                                h->rrank_off_dev.as<int64_t>(), V, shift, h->rrank_start.as<uint32_t>());
+                                                                h->rrank_off_dev.as<int64_t>(), V, shift, h->rrank_start.as<RankEntry>());
     if (!h->ends_alias_starts)
         build_rank_table_kernel<<<rt_grid, threads, 0, h->stream>>>(h->end_sorted.as<int32_t>(), h->r_voff_dev.as<int32_t>(),
-                                                                    h->rrank_off_dev.as<int64_t>(), V, shift, h->rank_end.as<uint32_t>());
+                                                                    h->rrank_off_dev.as<int64_t>(), V, shift, h->rank_end.as<RankEntry>());
     NRB_CUDA(h, cudaGetLastError());
     return NRB200_OK;
 }
@@ -369,7 +369,7 @@ int ensure_pmax_table(nrb200_handle *h) {
     const int64_t entries = h->rank_off[h->n_seq];
     build_rank_table_kernel<<<rank_table_grid(entries), 256, 0, h->stream>>>(
         h->y.pmax.as<int32_t>(), h->y.seq_off.as<int32_t>(), h->rank_off_dev.as<int64_t>(), h->n_seq, h->rank_shift,
-        h->rank_pmax.as<uint32_t>());
+        h->rank_pmax.as<RankEntry>());
     NRB_CUDA(h, cudaGetLastError());
     h->have_pmax_table = true;
     return NRB200_OK;

@@ -294,12 +294,13 @@ __global__ void gather_i8_kernel(const int32_t *__restrict__ src, const int8_t *
 
 // Packed rank table (see "direct-address rank tables").  A thread fills kTableRun consecutive entries: one binary
 // search for the first, then it walks the values forward bucket by bucket (an entry's end is the next entry's
-// start); the CTA's entries go out through shared memory so that the stores are contiguous.
+// start) and packs the bucket's first values into the entry; the CTA's entries go out through shared memory so
+// that the stores are contiguous.
 constexpr int kTableRun = 8;
 __global__ void __launch_bounds__(256) build_rank_table_kernel(const int32_t *__restrict__ values, const int32_t *__restrict__ seq_off,
                                                                const int64_t *__restrict__ rank_off, int n_seq, int shift,
-                                                               uint32_t *__restrict__ table) {
-    __shared__ uint32_t buf[256 * kTableRun + 256 / 4];  // skewed: one pad word per four threads' runs
+                                                               RankEntry *__restrict__ table) {
+    __shared__ RankEntry buf[256 * kTableRun + 256 / 2];  // skewed: one pad entry per two threads' runs
     const int64_t total = rank_off[n_seq];
     const int64_t cta_first = (int64_t)blockIdx.x * (256 * kTableRun);
     const int64_t t0 = cta_first + (int64_t)threadIdx.x * kTableRun;
@@ -313,7 +314,7 @@ __global__ void __launch_bounds__(256) build_rank_table_kernel(const int32_t *__
         int32_t a = seq_off[c], b = seq_off[c + 1];
         int64_t bucket = t0 - rank_off[c];
         int32_t p = (bucket << shift) > INT32_MAX ? b : first_ge(values, a, b, (int32_t)(bucket << shift));
-        const int out0 = threadIdx.x * kTableRun + threadIdx.x / 4;
+        const int out0 = threadIdx.x * kTableRun + threadIdx.x / 2;
         for (int j = 0; j < kTableRun && t0 + j < total; ++j, ++bucket) {
             if (t0 + j >= seq_last) {  // the run crosses into the next sequence (every sequence has entries)
                 ++c;
@@ -337,13 +338,13 @@ __global__ void __launch_bounds__(256) build_rank_table_kernel(const int32_t *__
                     }
                 }
             }
-            buf[out0 + j] = ((uint32_t)(p - a) << kRankCountBits) | (uint32_t)min(q - p, kRankCountCap);
+            buf[out0 + j] = rank_entry_pack(values, a, p, q, bucket << shift, shift);
             p = q;
         }
     }
     __syncthreads();
     for (int i = threadIdx.x; i < 256 * kTableRun; i += 256)
-        if (cta_first + i < total) table[cta_first + i] = buf[i + (i / kTableRun) / 4];
+        if (cta_first + i < total) table[cta_first + i] = buf[i + (i / kTableRun) / 2];
 }
 inline unsigned rank_table_grid(int64_t entries) { return (unsigned)((entries + 256 * kTableRun - 1) / (256 * kTableRun)); }
 
@@ -378,7 +379,7 @@ __global__ void count_observed_kernel(const RangesView y, int64_t n, const int32
 // in (end_i - wmax, end_i] -- two probes of the start table and a short scan; every range writes its end to its rank.
 __global__ void end_rank_scatter_kernel(const int32_t *__restrict__ seqid, const int32_t *__restrict__ start,
                                         const int32_t *__restrict__ end, const int4 *__restrict__ seq_info,
-                                        const uint32_t *__restrict__ rank_start, int rank_shift, int64_t n, int32_t wmax,
+                                        const RankEntry *__restrict__ rank_start, int rank_shift, int64_t n, int32_t wmax,
                                         int32_t *__restrict__ end_sorted) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;

@@ -91,6 +91,21 @@ int build_pairs(nrb200_handle *h) {
     const RangeSet &q = h->query;
     const int C = h->n_seq;
     const int64_t B = p.n_blocks(), G = q.n;
+    if (h->lists_from) {  // member of a device group: same inputs as the leader, so the leader's lists are this handle's lists
+        const HostLists &L = h->lists_from->lists;
+        if (!L.valid) return fail(h, NRB200_ERR_STATE, "device group: the leader has no window lists");
+        int rc;
+        if (h->excl.n > 0) {
+            if ((rc = upload(h, h->tile_x_off, L.x_off.data(), L.x_off.size()))) return rc;
+            if ((rc = upload(h, h->tile_x_rec, L.x_rec.data(), L.x_rec.size()))) return rc;
+        }
+        if (G == 0) return NRB200_OK;
+        h->n_pairs = L.n_pairs;
+        if ((rc = upload(h, h->f_src, L.f_src.data(), L.f_src.size()))) return rc;
+        if ((rc = upload(h, h->pair_off, L.f_off.data(), L.f_off.size()))) return rc;
+        return upload(h, h->pair_rec, L.recs.data(), L.recs.size());
+    }
+    h->lists.valid = false;
     const int64_t reach = std::max<int32_t>(h->y.wmax, 1) - 1;
     const bool has_excl = h->excl.n > 0, trim = trim_mode(h);
     const int n_cls = h->n_cls;
@@ -141,7 +156,15 @@ int build_pairs(nrb200_handle *h) {
         if ((rc = upload(h, h->tile_x_off, x_off.data(), x_off.size()))) return rc;
         if ((rc = upload(h, h->tile_x_rec, x_rec.data(), x_rec.size()))) return rc;
     }
-    if (G == 0) return NRB200_OK;
+    if (G == 0) {
+        if (h->keep_lists) {
+            h->lists.x_off = std::move(x_off);
+            h->lists.x_rec = std::move(x_rec);
+            h->lists.n_pairs = 0;
+            h->lists.valid = true;
+        }
+        return NRB200_OK;
+    }
 
     // ---- per feature.  Tiles of each sequence in ascending start order with the running max of
     // their ends (tiles_by_seq, made with the plan); features come in canonical (start-sorted) order, so the
@@ -211,7 +234,7 @@ int build_pairs(nrb200_handle *h) {
     std::vector<int32_t> len(G, 0);
     std::vector<int64_t> hist((size_t)C * kBins, 0), long_sum(C, 0);
     auto bin = [&](int64_t k) { return std::min<int>(len[k], kBins - 1); };
-#pragma omp parallel for schedule(dynamic, 1) if (G >= 4096)
+#pragma omp parallel for schedule(dynamic, 1) num_threads(host_threads(h)) if (G >= 4096)
     for (int c = 0; c < C; ++c) {
         enumerate_seq(c, [](int32_t) {}, [&](int32_t k, int32_t, int64_t, int64_t, int, int) { ++len[k]; });
         for (int32_t k = q.h_seq_off[c]; k < q.h_seq_off[c + 1]; ++k) {
@@ -245,14 +268,14 @@ int build_pairs(nrb200_handle *h) {
     struct Rec4 {
         int32_t x, y, z, w;
     };
-    std::vector<Rec4> f_recs_vec;  // the "a" halves of all records, then the "b" halves (rank_kernels.cuh)
-    Rec4 *f_recs = static_cast<Rec4 *>(arena_alloc(h, (size_t)std::max<int64_t>(2 * total, 1) * sizeof(Rec4)));
+    std::vector<int32_t> f_recs_vec;  // the "a" halves of all records, then the "b" halves (rank_kernels.cuh)
+    Rec4 *f_recs = h->keep_lists ? nullptr : static_cast<Rec4 *>(arena_alloc(h, (size_t)std::max<int64_t>(2 * total, 1) * sizeof(Rec4)));
     const bool staged = f_recs != nullptr;
-    if (!staged) {
-        f_recs_vec.resize((size_t)(2 * total));
-        f_recs = f_recs_vec.data();
+    if (!staged) {  // (the leader of a device group keeps the host copy for the other members)
+        f_recs_vec.resize((size_t)(8 * total));
+        f_recs = reinterpret_cast<Rec4 *>(f_recs_vec.data());
     }
-#pragma omp parallel for schedule(dynamic, 1) if (G >= 4096)
+#pragma omp parallel for schedule(dynamic, 1) num_threads(host_threads(h)) if (G >= 4096)
     for (int c = 0; c < C; ++c) {
         int64_t cursor = 0, long_cursor = long_rec[c];
         int64_t *next_pos = &pos_start[(size_t)c * kBins];
@@ -280,6 +303,16 @@ int build_pairs(nrb200_handle *h) {
     if ((rc = upload(h, h->pair_off, f_off.data(), (size_t)G + 1))) return rc;
     if ((rc = staged ? upload_staged(h, h->pair_rec, f_recs, (size_t)(2 * total)) : upload(h, h->pair_rec, f_recs, (size_t)(2 * total)))) return rc;
     tr.lap("upload");
+    if (h->keep_lists) {
+        HostLists &L = h->lists;
+        L.n_pairs = total;
+        L.f_src = std::move(f_src);
+        L.f_off = std::move(f_off);
+        L.x_off = std::move(x_off);
+        L.x_rec = std::move(x_rec);
+        L.recs = std::move(f_recs_vec);
+        L.valid = true;
+    }
     return NRB200_OK;
 }
 

@@ -44,40 +44,20 @@ struct TileExcl {              // signed exclusion windows of each (tile, strand
     const int4 *rec;           // {ws, we, sign, 0}
 };
 
-// One (feature, tile, iteration) evaluation, split into stages so that the RPT evaluations a thread
-// owns can be issued stage by stage: all table probes first, then all value reads, so that the
-// dependent-load chain (draw -> sequence info -> table -> values) is paid once per thread, not per
-// evaluation.  All coordinates are below 2^30 and widths at most 2^30: every sum fits int32.
+// One (feature window, tile, iteration) evaluation.  All coordinates are below 2^30 and widths at most 2^30: every
+// sum fits int32.
 struct PairProbe {
     int4 si;                   // seq_info of the bait sequence
     int32_t A, Bv;             // count = #{start <= A and end >= Bv}
     int32_t bs;                // bait start (the permute variants also need start >= bs)
-    int32_t key_a, key_b;      // clamped search keys (A + 1 in starts, Bv in sorted ends)
-    int32_t a0, an, b0, bn;    // bucket start and (capped) size in start[] and end_sorted[]
 };
 
-__device__ __forceinline__ void pair_keys(PairProbe &q, int2 draw, int32_t width, int32_t ts, int32_t seq_len,
-                                          int32_t gs, int32_t ge, int rank_shift, int32_t end_shift, int32_t &ua, int32_t &ub) {
+__device__ __forceinline__ void pair_keys(PairProbe &q, int2 draw, int32_t width, int32_t ts, int32_t seq_len, int32_t gs, int32_t ge) {
     const int32_t bs = draw.y;
     const int32_t sh = ts - bs;
     q.bs = bs;
     q.A = min(bs + (width - 1), min(ge, seq_len) - sh);
     q.Bv = max(bs, gs - sh);
-    q.key_a = rank_clamp_key(q.A + 1, q.si);
-    q.key_b = rank_clamp_key(q.Bv - end_shift, q.si);
-    ua = q.si.w + (q.key_a >> rank_shift);
-    ub = q.si.w + (q.key_b >> rank_shift);
-}
-
-// rank inside one bucket: first index with vals >= key (first three values already read; rare search)
-__device__ __forceinline__ int32_t bucket_rank(const int32_t *__restrict__ vals, const uint32_t *__restrict__ table, int32_t u,
-                                               const int4 si, int32_t a, int32_t n, int32_t key, int32_t v0, int32_t v1,
-                                               int32_t v2) {
-    if (v2 < key) {
-        const int32_t b = n < kRankCountCap ? a + n : si.x + (int32_t)(__ldg(table + u + 1) >> kRankCountBits);
-        return first_ge(vals, a + 3, b, key);
-    }
-    return a + (v0 < key) + (v1 < key) + (v2 < key);
 }
 
 // #{start <= a and end >= b} for a < b: such ranges contain [a, b]; walk back from #{start <= a}
@@ -89,100 +69,63 @@ __device__ __forceinline__ int count_spanning(const RangesView &y, const int4 si
     return n;
 }
 
+// The count of one evaluation: both table entries are fetched together (two independent 8-byte loads, one sector
+// each), the ranks come out of the entries themselves.
 // PERMUTE: a range belongs to the ONE tile that holds its start (findOverlaps(select = "first"),
 // R/bootUnsegmented.R:95, :155), so the members are {bs <= start <= A and end >= Bv}: the bootstrap
 // count minus the ranges that start before the tile and reach Bv (they contain [bs - 1, Bv]).
 template <bool PERMUTE>
-__device__ __forceinline__ int pair_finish(const RangesView &y, const PairProbe &q, int32_t ia, int32_t ib) {
+__device__ __forceinline__ int count_pair(const RangesView &y, int2 d, int cls, int32_t width, int32_t ts, int32_t seq_len,
+                                          int32_t gs, int32_t ge) {
+    PairProbe q;
+    q.si = __ldg(y.rseq_info + d.x * y.n_cls + cls);
+    pair_keys(q, d, width, ts, seq_len, gs, ge);
+    const int32_t key_a = rank_clamp_key(q.A + 1, q.si), key_b = rank_clamp_key(q.Bv - y.end_shift, q.si);
+    const int32_t ua = q.si.w + (key_a >> y.rank_shift), ub = q.si.w + (key_b >> y.rank_shift);
+    const RankEntry ea = __ldg(y.rrank_start + ua), eb = __ldg(y.rank_end + ub);
     if (q.A < 1 || (PERMUTE && q.A < q.bs)) return 0;  // permute: no start can lie in [bs, A]
-    int n = q.Bv <= q.A ? ia - ib : count_spanning(y, q.si, ia, q.Bv);  // second form: the feature lies beside the tile
+    const int32_t ia = rank_from_entry(y.rstart, y.rrank_start, y.rank_shift, q.si, key_a, ua, ea);
+    int n;
+    if (q.Bv <= q.A) n = ia - rank_from_entry(y.end_sorted, y.rank_end, y.rank_shift, q.si, key_b, ub, eb);
+    else n = count_spanning(y, q.si, ia, q.Bv);  // the feature lies beside the tile
     if (PERMUTE && n > 0) n -= count_spanning(y, q.si, first_ge_ranked(y.rstart, y.rrank_start, y.rank_shift, q.si, q.bs), q.Bv);
     return n;
 }
 
-template <int RPT, bool PERMUTE = false>
-__device__ __forceinline__ void count_pairs(const RangesView &y, const int2 (&d)[RPT], int cls, int32_t width, int32_t ts,
-                                            int32_t seq_len, int32_t gs, int32_t ge, int (&cnt)[RPT]) {
-    PairProbe q[RPT];
-    int32_t ua[RPT], ub[RPT];
-#pragma unroll
-    for (int j = 0; j < RPT; ++j) q[j].si = __ldg(y.rseq_info + d[j].x * y.n_cls + cls);
-#pragma unroll
-    for (int j = 0; j < RPT; ++j) pair_keys(q[j], d[j], width, ts, seq_len, gs, ge, y.rank_shift, y.end_shift, ua[j], ub[j]);
-#pragma unroll
-    for (int j = 0; j < RPT; ++j) {
-        const uint32_t ea = __ldg(y.rrank_start + ua[j]), eb = __ldg(y.rank_end + ub[j]);
-        q[j].a0 = q[j].si.x + (int32_t)(ea >> kRankCountBits);
-        q[j].an = (int32_t)(ea & kRankCountCap);
-        q[j].b0 = q[j].si.x + (int32_t)(eb >> kRankCountBits);
-        q[j].bn = (int32_t)(eb & kRankCountCap);
-    }
-    int32_t va[RPT][3], vb[RPT][3];
-#pragma unroll
-    for (int j = 0; j < RPT; ++j) {
-#pragma unroll
-        for (int k = 0; k < 3; ++k) {
-            va[j][k] = k < q[j].an ? __ldg(y.rstart + q[j].a0 + k) : INT32_MAX;
-            vb[j][k] = k < q[j].bn ? __ldg(y.end_sorted + q[j].b0 + k) : INT32_MAX;
-        }
-    }
-#pragma unroll
-    for (int j = 0; j < RPT; ++j) {
-        const int32_t ia = bucket_rank(y.rstart, y.rrank_start, ua[j], q[j].si, q[j].a0, q[j].an, q[j].key_a, va[j][0], va[j][1], va[j][2]);
-        const int32_t ib = bucket_rank(y.end_sorted, y.rank_end, ub[j], q[j].si, q[j].b0, q[j].bn, q[j].key_b, vb[j][0], vb[j][1], vb[j][2]);
-        cnt[j] += pair_finish<PERMUTE>(y, q[j], ia, ib);
-    }
-}
-
-// Thread = (feature, RPT consecutive iterations); the block draws come from the table the
-// block-rows kernel wrote.  Features are visited in F's order (grouped by tile count, so a warp's
-// lanes loop the same number of times).  No atomics on the count matrix, no memset: every element
-// is written exactly once.
-constexpr int kCountThreads = 128;  // CTA size of the count kernel: 128 beat 64 / 256 / 512 (0.258 vs 0.297 / 0.271 / 0.294 ms at cfg 2)
-template <int RPT, int MINB>
-__global__ void __launch_bounds__(kCountThreads, (MINB * 256) / kCountThreads > 0 ? (MINB * 256) / kCountThreads : 1) boot_rank_count_kernel(const BootParams P, const FeatView F) {
-    __shared__ int warp_tot[kCountThreads / 32][RPT];
+// Thread = (feature, iteration); the block draws come from the table the block-rows kernel wrote.  Features are
+// visited in F's order (grouped by tile count, so a warp's lanes loop the same number of times; neighbours in a
+// group are neighbours on the genome, so they mostly share their tile and the draw is one broadcast load).  No
+// atomics on the count matrix, no memset: every element is written exactly once.
+// 128-thread CTAs, 16 per SM (32 registers): the kernel is a chain of dependent L2 hits -- record -> draw -> sequence
+// info -> table entries -- and resident warps are what hides it.
+constexpr int kCountThreads = 128;
+__global__ void __launch_bounds__(kCountThreads, 16) boot_rank_count_kernel(const BootParams P, const FeatView F) {
+    __shared__ int warp_tot[kCountThreads / 32];
     const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int64_t r0 = (int64_t)blockIdx.y * RPT;
-    const int n_live = (int)min((int64_t)RPT, P.n_iter - r0);
-    int cnt[RPT];
-#pragma unroll
-    for (int j = 0; j < RPT; ++j) cnt[j] = 0;
+    const int64_t r = blockIdx.y;
+    int cnt = 0;
     if (g < P.n_query) {
         const int32_t src = __ldg(F.src + g);
         const int32_t p1 = __ldg(F.pair_off + g + 1);
+        const int2 *__restrict__ tab = P.draw_tab + r * P.n_blocks;
         for (int32_t p = __ldg(F.pair_off + g); p < p1; ++p) {
             const int4 ra = __ldg(F.rec_a + p);  // tile, ws, we, sign
             const int4 rb = __ldg(F.rec_b + p);  // tile_start, width, seq_len, cls
-            const int2 *__restrict__ tab = P.draw_tab + r0 * P.n_blocks + ra.x;
-            int2 d[RPT];
-#pragma unroll
-            for (int j = 0; j < RPT; ++j) d[j] = __ldg(tab + (j < n_live ? j : 0) * P.n_blocks);  // tail: recount row 0, discarded
-            int c[RPT];
-#pragma unroll
-            for (int j = 0; j < RPT; ++j) c[j] = 0;
-            if (P.permute) count_pairs<RPT, true>(P.y, d, rb.w, rb.y, rb.x, rb.z, ra.y, ra.z, c);
-            else count_pairs<RPT, false>(P.y, d, rb.w, rb.y, rb.x, rb.z, ra.y, ra.z, c);
-#pragma unroll
-            for (int j = 0; j < RPT; ++j) cnt[j] += ra.w * c[j];
+            const int2 d = __ldg(tab + ra.x);
+            const int c = P.permute ? count_pair<true>(P.y, d, rb.w, rb.y, rb.x, rb.z, ra.y, ra.z)
+                                    : count_pair<false>(P.y, d, rb.w, rb.y, rb.x, rb.z, ra.y, ra.z);
+            cnt += ra.w * c;
         }
-        if (P.counts) {
-#pragma unroll
-            for (int j = 0; j < RPT; ++j)
-                if (j < n_live) __stcs(P.counts + (r0 + j) * P.n_query + src, cnt[j]);  // streaming store: written once, read back by the copy engine
-        }
+        if (P.counts) __stcs(P.counts + r * P.n_query + src, cnt);  // streaming store: written once, read back by the copy engine
     }
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-#pragma unroll
-    for (int j = 0; j < RPT; ++j) {
-        const int s = __reduce_add_sync(kFull, cnt[j]);
-        if (lane == 0) warp_tot[warp][j] = s;
-    }
+    const int s = __reduce_add_sync(kFull, cnt);
+    if (lane == 0) warp_tot[warp] = s;
     __syncthreads();
-    if (threadIdx.x < n_live) {
-        unsigned long long s = 0;
-        for (int w = 0; w < kCountThreads / 32; ++w) s += (unsigned)warp_tot[w][threadIdx.x];
-        if (s) atomicAdd(P.iter_totals + r0 + threadIdx.x, s);
+    if (threadIdx.x == 0) {
+        unsigned long long t = 0;
+        for (int w = 0; w < kCountThreads / 32; ++w) t += (unsigned)warp_tot[w];
+        if (t) atomicAdd(P.iter_totals + r, t);
     }
 }
 
@@ -212,9 +155,8 @@ template <bool PERMUTE>
 __device__ __forceinline__ double weighted_pair(const RangesView &y, const WeightView &W, int2 draw, int cls, int32_t width,
                                                 int32_t ts, int32_t seq_len, int32_t ws, int32_t we) {
     PairProbe q;
-    int32_t ua, ub;
     q.si = __ldg(y.rseq_info + draw.x * y.n_cls + cls);
-    pair_keys(q, draw, width, ts, seq_len, ws, we, y.rank_shift, y.end_shift, ua, ub);
+    pair_keys(q, draw, width, ts, seq_len, ws, we);
     if (q.A < 1 || (PERMUTE && q.A < q.bs)) return 0.0;
     const int32_t ia = first_ge_ranked(y.rstart, y.rrank_start, y.rank_shift, q.si, q.A + 1);
     double s;
@@ -290,13 +232,21 @@ struct AddF64 {
 // (checked on the host).
 // SIMPLE: one class of y, bootstrap kinds, no exclusion, no table wanted -- the common fused-counts call; the general
 // branches are compiled out.
+// Sum over the warp of non-negative per-lane counts (each below 2^31) without wrapping: a few blocks over very many
+// ranges can push 32 lanes past 2^32, so the halves are reduced separately.
+__device__ __forceinline__ unsigned long long warp_sum_u64(int v) {
+    const unsigned lo = __reduce_add_sync(kFull, (unsigned)v & 0xffffu), hi = __reduce_add_sync(kFull, (unsigned)v >> 16);
+    return ((unsigned long long)hi << 16) + lo;
+}
+
 constexpr int kRowsThreads = 256;  // 128 measured the same
-template <int RPT, int MINB, bool SIMPLE>
-__global__ void __launch_bounds__(kRowsThreads, (MINB * 256) / kRowsThreads) boot_block_rows_kernel(const BootParams P, const TileExcl X, int ipc) {
+template <bool SIMPLE>
+__global__ void __launch_bounds__(kRowsThreads, 6) boot_block_rows_kernel(const BootParams P, const TileExcl X, int ipc) {
     const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int lane = threadIdx.x & 31;
 #pragma unroll 1
-  for (int it = 0; it < ipc; ++it) {  // a CTA keeps its 256 blocks for `ipc` iteration groups (fewer, longer-lived CTAs)
+  constexpr int RPT = 1;
+  for (int it = 0; it < ipc; ++it) {  // a CTA keeps its 256 blocks for `ipc` iterations (fewer, longer-lived CTAs)
     const int64_t r0 = ((int64_t)blockIdx.y * ipc + it) * RPT;
     if (r0 >= P.n_iter) break;
     int rows[RPT];
@@ -341,11 +291,8 @@ __global__ void __launch_bounds__(kRowsThreads, (MINB * 256) / kRowsThreads) boo
                         const int32_t x1 = __ldg(X.off + t * n_cls + cls + 1);
                         for (int32_t k = __ldg(X.off + t * n_cls + cls); k < x1; ++k) {
                             const int4 w = __ldg(X.rec + k);
-                            const int2 dd[1] = {d};
-                            int c1[1] = {0};
-                            if (P.permute) count_pairs<1, true>(P.y, dd, cls, width, ts, seq_len, w.x, w.y, c1);
-                            else count_pairs<1, false>(P.y, dd, cls, width, ts, seq_len, w.x, w.y, c1);
-                            rows[j] += w.z * c1[0];
+                            rows[j] += w.z * (P.permute ? count_pair<true>(P.y, d, cls, width, ts, seq_len, w.x, w.y)
+                                                        : count_pair<false>(P.y, d, cls, width, ts, seq_len, w.x, w.y));
                         }
                     }
                 }
@@ -358,11 +305,11 @@ __global__ void __launch_bounds__(kRowsThreads, (MINB * 256) / kRowsThreads) boo
     // shared-memory stage, no barrier, a warp retires as soon as its 32 blocks are done
 #pragma unroll
     for (int j = 0; j < RPT; ++j) {
-        const int s = __reduce_add_sync(kFull, rows[j]);
-        if (lane == 0 && s && r0 + j < P.n_iter) atomicAdd(P.iter_nranges + r0 + j, (unsigned long long)(unsigned)s);
+        const unsigned long long s = warp_sum_u64(rows[j]);
+        if (lane == 0 && s && r0 + j < P.n_iter) atomicAdd(P.iter_nranges + r0 + j, s);
     }
-    hits_sum = __reduce_add_sync(kFull, hits_sum);
-    if (lane == 0 && P.n_hits && hits_sum) atomicAdd(P.n_hits + (r0 & (kHitSlots - 1)), (unsigned long long)hits_sum);
+    const unsigned long long hs = warp_sum_u64(hits_sum);
+    if (lane == 0 && P.n_hits && hs) atomicAdd(P.n_hits + (r0 & (kHitSlots - 1)), hs);
   }
 }
 

@@ -84,6 +84,7 @@ int stage_draws(nrb200_handle *h, const nrb200_draws *d) {
         if (h->n_seq > 4096) return fail(h, NRB200_ERR_UNSUPPORTED, "device permutations support at most 4096 sequences");
         const int64_t R = d->n_iter;
         NRB_CUDA(h, h->d_dst_tile.reserve((size_t)std::max<int64_t>(R * B, 1) * 4));
+        h->dst_tile_items = R * B;
         const int64_t kPermBatch = 4096;  // 12 bits of the sort key
         const int64_t cap = std::min(R, kPermBatch) * B;
         NRB_CUDA(h, h->sort_keys_a.reserve((size_t)std::max<int64_t>(cap, 1) * 8));
@@ -134,6 +135,7 @@ int stage_draws(nrb200_handle *h, const nrb200_draws *d) {
     if ((rc = upload(h, h->d_bait_seq, d->bait_seqid, (size_t)n))) return rc;
     if ((rc = upload(h, h->d_bait_start, d->bait_start, (size_t)n))) return rc;
     if (d->dst_tile && (rc = upload(h, h->d_dst_tile, d->dst_tile, (size_t)n))) return rc;
+    h->dst_tile_items = d->dst_tile ? n : 0;
     return NRB200_OK;
 }
 
@@ -148,12 +150,12 @@ BootParams make_params(nrb200_handle *h, const nrb200_draws *d) {
     Y.src = y.sorted_input ? nullptr : y.src.as<int32_t>();
     Y.seq_off = y.seq_off.as<int32_t>();
     Y.seq_info = h->seq_info_dev.as<int4>();
-    Y.rank_start = h->rank_start.as<uint32_t>();
-    Y.rank_pmax = h->rank_pmax.as<uint32_t>();
+    Y.rank_start = h->rank_start.as<RankEntry>();
+    Y.rank_pmax = h->rank_pmax.as<RankEntry>();
     Y.rank_shift = h->rank_shift;
     Y.n_cls = h->n_cls;
     Y.end_sorted = h->end_sorted.as<int32_t>();
-    Y.rank_end = h->rank_end.as<uint32_t>();
+    Y.rank_end = h->rank_end.as<RankEntry>();
     if (h->n_cls == 1) {  // unstranded: the rank path reads the canonical arrays
         Y.rstart = Y.start;
         Y.rend = Y.end;
@@ -165,7 +167,7 @@ BootParams make_params(nrb200_handle *h, const nrb200_draws *d) {
         Y.rend = h->r_end.as<int32_t>();
         Y.rpmax = h->r_pmax.as<int32_t>();
         Y.rseq_info = h->rseq_info_dev.as<int4>();
-        Y.rrank_start = h->rrank_start.as<uint32_t>();
+        Y.rrank_start = h->rrank_start.as<RankEntry>();
     }
     Y.end_shift = h->end_shift;
     if (h->ends_alias_starts) {
@@ -220,10 +222,6 @@ constexpr size_t kMaxStagingBytes = (size_t)2 << 30;  // pinned staging for page
 int launch_rank(nrb200_handle *h, const BootParams &P, bool has_query) {
     if (P.n_iter == 0) return 0;
     int launches = 0;
-    int rpt = h->tune_rpt;
-    const int variant = rpt * 10 + h->tune_minb;  // tuning variants kept from the sweep; anything else runs <1, 8>
-    if (variant != 11 && variant != 17 && variant != 21 && variant != 24 && variant != 41 && variant != 43 && variant != 44 && variant != 81) rpt = 1;
-    const unsigned gy = (unsigned)((P.n_iter + rpt - 1) / rpt);
     if (P.n_blocks > 0) {
         const TileExcl X{h->excl.n > 0 ? h->tile_x_off.as<int32_t>() : nullptr, h->tile_x_rec.as<int4>()};  // drop: minus, trim: plus
         // iterations a CTA loops over: up to NRB200_ROWS_IPC, as long as the grid still holds a few CTAs per resident slot
@@ -231,29 +229,15 @@ int launch_rank(nrb200_handle *h, const BootParams &P, bool has_query) {
         const int ipc = (int)std::max<int64_t>(1, std::min<int64_t>(h->tune_rows_ipc, P.n_iter * ctas_x / ((int64_t)h->sm_count * 12)));
         const dim3 rows_grid((unsigned)ctas_x, (unsigned)((P.n_iter + ipc - 1) / ipc));
         const bool simple = P.y.n_cls == 1 && !X.off && !P.item_rec && !P.item_rows && !P.permute && !P.dst_tile && !P.rows_windows_only;
-        if (simple && h->tune_minb_rows == 6) boot_block_rows_kernel<1, 6, true><<<rows_grid, kRowsThreads, 0, h->stream>>>(P, X, ipc);
-        else if (simple && h->tune_minb_rows == 8) boot_block_rows_kernel<1, 8, true><<<rows_grid, kRowsThreads, 0, h->stream>>>(P, X, ipc);
-        else if (h->tune_minb_rows >= 8) boot_block_rows_kernel<1, 8, false><<<rows_grid, kRowsThreads, 0, h->stream>>>(P, X, ipc);
-        else if (h->tune_minb_rows == 6) boot_block_rows_kernel<1, 6, false><<<rows_grid, kRowsThreads, 0, h->stream>>>(P, X, ipc);
-        else if (h->tune_minb_rows == 5) boot_block_rows_kernel<1, 5, false><<<rows_grid, kRowsThreads, 0, h->stream>>>(P, X, ipc);
-        else boot_block_rows_kernel<1, 1, false><<<rows_grid, kRowsThreads, 0, h->stream>>>(P, X, ipc);
+        if (simple) boot_block_rows_kernel<true><<<rows_grid, kRowsThreads, 0, h->stream>>>(P, X, ipc);
+        else boot_block_rows_kernel<false><<<rows_grid, kRowsThreads, 0, h->stream>>>(P, X, ipc);
         ++launches;
     }
     if (h->split_ev) cudaEventRecord(h->split_ev, h->stream);  // stats: end of the rows kernel
     if (has_query) {
         const FeatView F{h->f_src.as<int32_t>(), h->pair_off.as<int32_t>(), h->pair_rec.as<int4>(), h->pair_rec.as<int4>() + h->n_pairs};
-        const dim3 grid((unsigned)((P.n_query + kCountThreads - 1) / kCountThreads), gy);
-        switch (variant) {
-        case 11: boot_rank_count_kernel<1, 1><<<grid, kCountThreads, 0, h->stream>>>(P, F); break;
-        case 17: boot_rank_count_kernel<1, 7><<<grid, kCountThreads, 0, h->stream>>>(P, F); break;
-        case 21: boot_rank_count_kernel<2, 1><<<grid, kCountThreads, 0, h->stream>>>(P, F); break;
-        case 24: boot_rank_count_kernel<2, 4><<<grid, kCountThreads, 0, h->stream>>>(P, F); break;
-        case 41: boot_rank_count_kernel<4, 1><<<grid, kCountThreads, 0, h->stream>>>(P, F); break;
-        case 43: boot_rank_count_kernel<4, 3><<<grid, kCountThreads, 0, h->stream>>>(P, F); break;
-        case 44: boot_rank_count_kernel<4, 4><<<grid, kCountThreads, 0, h->stream>>>(P, F); break;
-        case 81: boot_rank_count_kernel<8, 1><<<grid, kCountThreads, 0, h->stream>>>(P, F); break;
-        default: boot_rank_count_kernel<1, 8><<<grid, kCountThreads, 0, h->stream>>>(P, F); break;
-        }
+        const dim3 grid((unsigned)((P.n_query + kCountThreads - 1) / kCountThreads), (unsigned)P.n_iter);
+        boot_rank_count_kernel<<<grid, kCountThreads, 0, h->stream>>>(P, F);
         ++launches;
     }
     return launches;
@@ -399,7 +383,7 @@ int run_counts_core(nrb200_handle *h, const nrb200_draws *d, bool want_counts, i
         char *dst = reinterpret_cast<char *>(host_counts + r0 * G);
         const size_t piece = (size_t)1 << 20;
         const int64_t pieces = (int64_t)((bytes + piece - 1) / piece);
-#pragma omp parallel for schedule(static)
+#pragma omp parallel for schedule(static) num_threads(host_threads(h))
         for (int64_t i = 0; i < pieces; ++i) std::memcpy(dst + i * piece, src + i * piece, std::min(piece, bytes - (size_t)i * piece));
     }
     h->res_has_counts = want_counts;

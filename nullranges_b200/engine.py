@@ -2,6 +2,7 @@
 from __future__ import annotations
 
 import ctypes as C
+import threading
 from dataclasses import dataclass
 
 import numpy as np
@@ -42,19 +43,36 @@ class Draws:
 
 
 class Engine:
-    def __init__(self, device: int = 0, stream: int | None = None, force_stream: bool = False):
+    """One nrb200_handle: a single GPU, or -- ``device`` a list of ordinals -- a device group that shards the
+    iterations of every run over those GPUs and delivers one result (include/nrb200.h, nrb200_config.n_devices)."""
+
+    def __init__(self, device=0, stream: int | None = None, force_stream: bool = False):
         """force_stream: always stream the sampled ranges instead of counting by ranks (tests, profiling)."""
         self._lib = _lib.load()
         self._h = C.c_void_p()
-        cfg = _lib.Config(int(device), _lib.FLAG_FORCE_STREAM if force_stream else 0, C.c_void_p(stream) if stream else None)
+        self.lock = threading.RLock()  # the handle is stateful: a front-end call holds it from set_ranges to the result
+        devices = [int(d) for d in device] if isinstance(device, (list, tuple)) else None
+        flags = _lib.FLAG_FORCE_STREAM if force_stream else 0
+        if devices is not None:
+            if not devices:
+                raise ValueError("Engine: empty device list")
+            arr = (C.c_int32 * len(devices))(*devices)
+            cfg = _lib.Config(devices[0], flags, C.c_void_p(stream) if stream else None, len(devices), arr)
+        else:
+            cfg = _lib.Config(int(device), flags, C.c_void_p(stream) if stream else None, 0, None)
         rc = self._lib.nrb200_create(C.byref(cfg), C.byref(self._h))
         if rc:
             raise EngineError(rc, self._lib.nrb200_last_error(None).decode())
-        self.device = device
+        self.device = devices[0] if devices is not None else int(device)
+        self.devices = devices if devices is not None else [int(device)]
         self.force_stream = bool(force_stream)
         self.n_blocks = 0
         self.n_query = 0
         self.n_seq = 0
+
+    @property
+    def n_devices(self) -> int:
+        return int(self._lib.nrb200_n_devices(self._h))
 
     def close(self):
         if getattr(self, "_h", None):
@@ -239,12 +257,35 @@ class Engine:
         return out
 
 
-_engines: dict[int, Engine] = {}
+    def fetch_dst_tiles(self, r0: int, n: int) -> np.ndarray:
+        """Permute variants: the tile every block of iterations [r0, r0 + n) of the last run moved to, [n, n_blocks]."""
+        out = np.empty((int(n), self.n_blocks), np.int32)
+        self._check(self._lib.nrb200_fetch_dst_tiles(self._h, int(r0), int(n), ptr(out, C.c_int32)))
+        return out
 
 
-def get_engine(device: int = 0) -> Engine:
-    """Process-wide engine per GPU (device buffers are reused across calls)."""
-    e = _engines.get(device)
-    if e is None or e._h is None:
-        e = _engines[device] = Engine(device)
+_engines: dict[tuple, Engine] = {}
+_engines_lock = threading.Lock()
+
+
+def resolve_devices(device=0, gpus=None):
+    """device: one ordinal or a list of them; gpus: N -> the first N GPUs, or a list of ordinals (overrides device)."""
+    if gpus is not None:
+        device = list(range(int(gpus))) if isinstance(gpus, (int, np.integer)) else [int(d) for d in gpus]
+    if isinstance(device, (list, tuple)):
+        device = [int(d) for d in device]
+        if not device:
+            raise ValueError("gpus: no device given")
+        return device if len(device) > 1 else device[0]
+    return int(device)
+
+
+def get_engine(device=0, gpus=None) -> Engine:
+    """Process-wide engine per GPU -- or per device group -- (device buffers are reused across calls)."""
+    dev = resolve_devices(device, gpus)
+    key = tuple(dev) if isinstance(dev, list) else (dev,)
+    with _engines_lock:
+        e = _engines.get(key)
+        if e is None or e._h is None:
+            e = _engines[key] = Engine(dev)
     return e

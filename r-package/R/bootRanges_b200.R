@@ -10,9 +10,17 @@
 # nullranges_b200/bootranges.py + samplers.py, which the test-suite runs against the oracle.
 
 .nrb_env <- new.env()
-.handle <- function(device = 0L) {
-  key <- paste0("h", device)
-  if (is.null(.nrb_env[[key]])) .nrb_env[[key]] <- .Call("nrb200_R_create", as.integer(device))
+# gpus: NULL (one GPU: `device`), N (the first N GPUs of the box) or a vector of CUDA ordinals.  With more than one
+# GPU the handle is a device group: every run shards its R iterations over the GPUs (replicate() at
+# R/bootRanges.R:90 is R independent draws) and returns ONE result, bit-identical for every number of GPUs.
+.devices <- function(device = 0L, gpus = NULL) {
+  if (is.null(gpus)) return(as.integer(device))
+  if (length(gpus) == 1L) seq_len(as.integer(gpus)) - 1L else as.integer(gpus)
+}
+.handle <- function(device = 0L, gpus = NULL) {
+  dev <- .devices(device, gpus)
+  key <- paste0("h", paste(dev, collapse = "_"))
+  if (is.null(.nrb_env[[key]])) .nrb_env[[key]] <- .Call("nrb200_R_create", dev)
   .nrb_env[[key]]
 }
 .strand_code <- function(x) {
@@ -73,12 +81,12 @@
   list(seqid = unlist(lapply(out, `[[`, 1)), start = as.integer(unlist(lapply(out, `[[`, 2))), dst = NULL)
 }
 
-.setup <- function(y, blockLength, seg, exclude, excludeOption, proportionLength, type, withinChrom, device) {
+.setup <- function(y, blockLength, seg, exclude, excludeOption, proportionLength, type, withinChrom, device, gpus = NULL) {
   chr_lens <- GenomeInfoDb::seqlengths(y)
   stopifnot(all(!is.na(chr_lens)))
   if (excludeOption == "trim") stopifnot(all(GenomicRanges::strand(exclude) == "*"))   # R/bootRanges.R:83-85
   lv <- GenomeInfoDb::seqlevels(y)
-  h <- .handle(device)
+  h <- .handle(device, gpus)
   kind <- .kind(seg, proportionLength, type, withinChrom)
   sorted <- .Call("nrb200_R_set_ranges", h, as.numeric(chr_lens), .seqid(y, lv), GenomicRanges::start(y),
                   GenomicRanges::end(y), .strand_code(y))
@@ -111,9 +119,10 @@
 
 bootRanges <- function(y, blockLength, R = 1, seg = NULL, exclude = NULL, excludeOption = c("drop", "trim"),
                        proportionLength = TRUE, type = c("bootstrap", "permute"), withinChrom = FALSE,
-                       storeBlockLength = FALSE, rng = c("R", "philox"), seed = 0, iter0 = 0, device = 0L) {
+                       storeBlockLength = FALSE, rng = c("R", "philox"), seed = 0, iter0 = 0, storeBlockStart = FALSE,
+                       device = 0L, gpus = NULL) {
   excludeOption <- match.arg(excludeOption); type <- match.arg(type); rng <- match.arg(rng)
-  s <- .setup(y, blockLength, seg, exclude, excludeOption, proportionLength, type, withinChrom, device)
+  s <- .setup(y, blockLength, seg, exclude, excludeOption, proportionLength, type, withinChrom, device, gpus)
   d <- .draws(s, R, blockLength, rng)
   res <- .Call("nrb200_R_run_materialize", s$h, as.numeric(R), as.numeric(iter0), as.numeric(seed), d[[1]], d[[2]], d[[3]])
   if (!s$sorted) {   # row order of the reference follows the order y was given in (see bootranges.py)
@@ -135,6 +144,18 @@ bootRanges <- function(y, blockLength, R = 1, seg = NULL, exclude = NULL, exclud
   # Rle(factor(rep(seq_len(R), lens))) of R/bootRanges.R:122, built from (values, run lengths): no per-row work
   S4Vectors::mcols(br)$iter <- S4Vectors::Rle(factor(seq_len(R), levels = seq_len(R)), res[[1]])
   if (storeBlockLength) S4Vectors::mcols(br)$blockLength <- S4Vectors::Rle(as.integer(blockLength), length(br))
+  if (storeBlockStart) {
+    # start of the tile the row's block LANDED on (the reference drops its `block` column, R/bootRanges.R:126; this
+    # column is the free extra SURVEY fact 5 describes).  Bootstrap kinds: block b lands on tile b.  Permute kinds:
+    # on the tile it was drawn for -- R's own draw (d[[3]], 0-based, iteration-major) or the device's permutation.
+    dst <- res[[6]]
+    if (s$kind %in% c(4L, 5L)) {
+      B <- length(s$tiles[[1]])
+      perm <- if (rng == "R") matrix(d[[3]] + 1L, nrow = B) else .Call("nrb200_R_fetch_dst_tiles", s$h, as.integer(R), as.integer(B))
+      dst <- perm[cbind(res[[6]], rep(seq_len(R), res[[1]]))]
+    }
+    S4Vectors::mcols(br)$blockStart <- s$tiles[[2]][dst]
+  }
   new("BootRanges", br)
 }
 
@@ -142,9 +163,10 @@ bootRanges <- function(y, blockLength, R = 1, seg = NULL, exclude = NULL, exclud
 # Returns list(iter_totals, iter_nranges, counts = integer matrix [length(x), R]).
 bootCounts <- function(y, x, blockLength, R = 1, seg = NULL, exclude = NULL, excludeOption = c("drop", "trim"),
                        proportionLength = TRUE, type = c("bootstrap", "permute"), withinChrom = FALSE,
-                       rng = c("philox", "R"), seed = 0, iter0 = 0, perFeature = TRUE, maxgap = -1L, minoverlap = 0L, weights = NULL, device = 0L) {
+                       rng = c("philox", "R"), seed = 0, iter0 = 0, perFeature = TRUE, maxgap = -1L, minoverlap = 0L, weights = NULL,
+                       device = 0L, gpus = NULL) {
   excludeOption <- match.arg(excludeOption); type <- match.arg(type); rng <- match.arg(rng)
-  s <- .setup(y, blockLength, seg, exclude, excludeOption, proportionLength, type, withinChrom, device)
+  s <- .setup(y, blockLength, seg, exclude, excludeOption, proportionLength, type, withinChrom, device, gpus)
   keep <- which(as.character(GenomicRanges::seqnames(x)) %in% s$lv)
   xk <- x[keep]
   .Call("nrb200_R_set_query", s$h, .seqid(xk, s$lv), GenomicRanges::start(xk), GenomicRanges::end(xk), .strand_code(xk),
@@ -176,9 +198,9 @@ bootCounts <- function(y, x, blockLength, R = 1, seg = NULL, exclude = NULL, exc
 bootWeightedMoments <- function(y, x, blockLength, weights, R = 1, observed = NULL, seg = NULL, exclude = NULL,
                                 excludeOption = c("drop", "trim"), proportionLength = TRUE, type = c("bootstrap", "permute"),
                                 withinChrom = FALSE, rng = c("philox", "R"), seed = 0, iter0 = 0, maxgap = -1L, minoverlap = 0L,
-                                device = 0L) {
+                                device = 0L, gpus = NULL) {
   excludeOption <- match.arg(excludeOption); type <- match.arg(type); rng <- match.arg(rng)
-  s <- .setup(y, blockLength, seg, exclude, excludeOption, proportionLength, type, withinChrom, device)
+  s <- .setup(y, blockLength, seg, exclude, excludeOption, proportionLength, type, withinChrom, device, gpus)
   stopifnot("every seqlevel of x must be a seqlevel of y" = all(as.character(GenomicRanges::seqnames(x)) %in% s$lv))
   .Call("nrb200_R_set_query", s$h, .seqid(x, s$lv), GenomicRanges::start(x), GenomicRanges::end(x), .strand_code(x),
         as.integer(maxgap), as.integer(minoverlap))
@@ -194,4 +216,25 @@ bootWeightedMoments <- function(y, x, blockLength, weights, R = 1, observed = NU
     out$p_ge <- (m[[4]] + 1) / (R + 1)
   }
   out
+}
+
+# Per-feature mean / sd / z / empirical p of countOverlaps(x, boots) over R iterations, reduced on the GPU(s): no
+# G x R matrix, so R = 10^4 against 2 * 10^5 features (BASELINE config 4) is fine.  observed defaults to
+# countOverlaps(x, y) on the original ranges (vignettes/bootRanges.Rmd:482-483).
+bootMoments <- function(y, x, blockLength, R = 1, observed = NULL, seg = NULL, exclude = NULL, excludeOption = c("drop", "trim"),
+                        proportionLength = TRUE, type = c("bootstrap", "permute"), withinChrom = FALSE, rng = c("philox", "R"),
+                        seed = 0, iter0 = 0, maxgap = -1L, minoverlap = 0L, device = 0L, gpus = NULL) {
+  excludeOption <- match.arg(excludeOption); type <- match.arg(type); rng <- match.arg(rng)
+  s <- .setup(y, blockLength, seg, exclude, excludeOption, proportionLength, type, withinChrom, device, gpus)
+  stopifnot("every seqlevel of x must be a seqlevel of y" = all(as.character(GenomicRanges::seqnames(x)) %in% s$lv))
+  .Call("nrb200_R_set_query", s$h, .seqid(x, s$lv), GenomicRanges::start(x), GenomicRanges::end(x), .strand_code(x),
+        as.integer(maxgap), as.integer(minoverlap))
+  if (is.null(observed)) observed <- .Call("nrb200_R_count_observed", s$h, as.numeric(length(x)), as.integer(minoverlap))
+  d <- .draws(s, R, blockLength, rng)
+  m <- .Call("nrb200_R_run_moments", s$h, as.integer(observed), as.numeric(R), as.numeric(iter0), as.numeric(seed), d[[1]], d[[2]],
+             d[[3]], as.numeric(length(x)))
+  mean <- m[[3]] / R
+  sd <- sqrt(pmax(m[[4]] - R * mean^2, 0) / max(R - 1, 1))
+  list(iter_nranges = m[[1]], iter_totals = m[[2]], mean = mean, sd = sd, observed = observed, z = (observed - mean) / sd,
+       p_ge = (m[[5]] + 1) / (R + 1))
 }

@@ -57,8 +57,13 @@ static int8_t *strand_codes(SEXP x) { /* integer 0/1/2 -> int8 (R_alloc: freed b
     return out;
 }
 
-SEXP nrb200_R_create(SEXP device) {
-    nrb200_config cfg = {Rf_asInteger(device), 0, NULL};
+/* devices: integer vector of CUDA ordinals; more than one = a device group (the iterations of every run are sharded
+ * over those GPUs from this one R thread, see nrb200_config in nrb200.h) */
+SEXP nrb200_R_create(SEXP devices) {
+    const R_xlen_t W = XLENGTH(devices);
+    if (W < 1) Rf_error("nrb200: no device given");
+    const int *dev = ints(devices, "devices");
+    nrb200_config cfg = {dev[0], 0, NULL, (int32_t)W, dev};
     nrb200_handle *h = NULL;
     check(NULL, nrb200_create(&cfg, &h));
     SEXP ptr = PROTECT(R_MakeExternalPtr(h, R_NilValue, R_NilValue));
@@ -112,6 +117,25 @@ SEXP nrb200_R_set_plan(SEXP ptr, SEXP kind, SEXP block_length, SEXP seg_seqid, S
     return out;
 }
 
+/* Long runs go to the engine in batches of iterations with R_CheckUserInterrupt() in between (it longjmps out on
+ * Ctrl-C: nothing but R-managed memory and the still-valid handle is live at that point).  Iterations are
+ * independent and Philox is keyed by the global iteration, so batching does not change any result. */
+#define NRB_R_BATCH 4096
+static nrb200_draws batch_of(const nrb200_draws *d, int64_t r0, int64_t n, int64_t n_blocks) {
+    nrb200_draws b = *d;
+    b.n_iter = n;
+    b.iter0 = d->iter0 + r0;
+    if (d->rng_mode == NRB200_RNG_HOST) {
+        b.bait_seqid = d->bait_seqid + r0 * n_blocks;
+        b.bait_start = d->bait_start + r0 * n_blocks;
+        b.dst_tile = d->dst_tile ? d->dst_tile + r0 * n_blocks : NULL;
+    }
+    return b;
+}
+static int64_t blocks_of(const nrb200_draws *d, SEXP bait_start) { /* n_blocks of host-mode draws (0 when unused) */
+    return (d->rng_mode == NRB200_RNG_HOST && d->n_iter > 0) ? (int64_t)(XLENGTH(bait_start) / d->n_iter) : 0;
+}
+
 static void fill_draws(nrb200_draws *d, SEXP n_iter, SEXP iter0, SEXP seed, SEXP bait_seqid, SEXP bait_start, SEXP dst_tile) {
     memset(d, 0, sizeof *d);
     d->n_iter = (int64_t)Rf_asReal(n_iter);
@@ -142,9 +166,16 @@ SEXP nrb200_R_run_counts(SEXP ptr, SEXP n_iter, SEXP iter0, SEXP seed, SEXP bait
         mat = Rf_allocMatrix(INTSXP, (int)G, (int)R);
         SET_VECTOR_ELT(out, 2, mat);
     }
-    check(H(ptr), nrb200_run_counts(H(ptr), &d, nr, tot, mat == R_NilValue ? NULL : INTEGER(mat), NULL));
-    SEXP a = Rf_allocVector(REALSXP, R), b = Rf_allocVector(REALSXP, R);
-    SET_VECTOR_ELT(out, 0, a);
+    const int64_t B = blocks_of(&d, bait_start);
+    for (int64_t r0 = 0; r0 < (int64_t)R || r0 == 0; r0 += NRB_R_BATCH) {
+        const int64_t n = (int64_t)R - r0 < NRB_R_BATCH ? (int64_t)R - r0 : NRB_R_BATCH;
+        const nrb200_draws b = batch_of(&d, r0, n, B);
+        check(H(ptr), nrb200_run_counts(H(ptr), &b, nr + r0, tot + r0, mat == R_NilValue ? NULL : INTEGER(mat) + r0 * (int64_t)G, NULL));
+        if (r0 + NRB_R_BATCH < (int64_t)R) R_CheckUserInterrupt();
+    }
+    SEXP a = Rf_allocVector(REALSXP, R);
+    SET_VECTOR_ELT(out, 0, a); /* reachable from `out` before the next allocation can trigger a collection */
+    SEXP b = Rf_allocVector(REALSXP, R);
     SET_VECTOR_ELT(out, 1, b);
     for (R_xlen_t r = 0; r < R; r++) {
         REAL(a)[r] = (double)nr[r];
@@ -172,7 +203,13 @@ SEXP nrb200_R_run_weighted(SEXP ptr, SEXP weights, SEXP n_iter, SEXP iter0, SEXP
         mat = Rf_allocMatrix(REALSXP, (int)G, (int)R);
         SET_VECTOR_ELT(out, 1, mat);
     }
-    check(H(ptr), nrb200_run_weighted(H(ptr), &d, REAL(it), mat == R_NilValue ? NULL : REAL(mat), NULL));
+    const int64_t B = blocks_of(&d, bait_start);
+    for (int64_t r0 = 0; r0 < (int64_t)R || r0 == 0; r0 += NRB_R_BATCH) {
+        const int64_t n = (int64_t)R - r0 < NRB_R_BATCH ? (int64_t)R - r0 : NRB_R_BATCH;
+        const nrb200_draws b = batch_of(&d, r0, n, B);
+        check(H(ptr), nrb200_run_weighted(H(ptr), &b, REAL(it) + r0, mat == R_NilValue ? NULL : REAL(mat) + r0 * (int64_t)G, NULL));
+        if (r0 + NRB_R_BATCH < (int64_t)R) R_CheckUserInterrupt();
+    }
     UNPROTECT(1);
     return out;
 }
@@ -227,6 +264,61 @@ SEXP nrb200_R_run_materialize(SEXP ptr, SEXP n_iter, SEXP iter0, SEXP seed, SEXP
     return out;
 }
 
+/* per-feature moments of the overlap counts, no [G x R] matrix (bootMoments): list(iter_nranges = double[R],
+ * iter_totals = double[R], sum = double[G], sumsq = double[G], n_ge = double[G]).  observed: integer[G] or NULL.
+ * Accumulates batch by batch on the device(s); R_CheckUserInterrupt() between batches. */
+SEXP nrb200_R_run_moments(SEXP ptr, SEXP observed, SEXP n_iter, SEXP iter0, SEXP seed, SEXP bait_seqid, SEXP bait_start, SEXP dst_tile,
+                          SEXP n_query) {
+    nrb200_draws d;
+    fill_draws(&d, n_iter, iter0, seed, bait_seqid, bait_start, dst_tile);
+    const R_xlen_t R = (R_xlen_t)d.n_iter, G = (R_xlen_t)Rf_asReal(n_query);
+    if (observed != R_NilValue && XLENGTH(observed) != G) Rf_error("observed must have one value per feature");
+    const int *obs = observed == R_NilValue ? NULL : ints(observed, "observed");
+    int64_t *nr = (int64_t *)R_alloc(R ? R : 1, 8), *tot = (int64_t *)R_alloc(R ? R : 1, 8);
+    int64_t *m = (int64_t *)R_alloc(G ? 3 * G : 1, 8);
+    check(H(ptr), nrb200_moments_reset(H(ptr)));
+    const int64_t B = blocks_of(&d, bait_start);
+    for (int64_t r0 = 0; r0 < (int64_t)R; r0 += NRB_R_BATCH) {
+        const int64_t n = (int64_t)R - r0 < NRB_R_BATCH ? (int64_t)R - r0 : NRB_R_BATCH;
+        const nrb200_draws b = batch_of(&d, r0, n, B);
+        check(H(ptr), nrb200_run_moments(H(ptr), &b, 0, obs, nr + r0, tot + r0, NULL));
+        if (r0 + NRB_R_BATCH < (int64_t)R) R_CheckUserInterrupt();
+    }
+    check(H(ptr), nrb200_moments_fetch(H(ptr), m, m + G, m + 2 * G));
+    SEXP out = PROTECT(Rf_allocVector(VECSXP, 5));
+    for (int k = 0; k < 5; k++) SET_VECTOR_ELT(out, k, Rf_allocVector(REALSXP, k < 2 ? R : G));
+    for (R_xlen_t r = 0; r < R; r++) {
+        REAL(VECTOR_ELT(out, 0))[r] = (double)nr[r];
+        REAL(VECTOR_ELT(out, 1))[r] = (double)tot[r];
+    }
+    for (int k = 0; k < 3; k++)
+        for (R_xlen_t g = 0; g < G; g++) REAL(VECTOR_ELT(out, 2 + k))[g] = (double)m[k * G + g];
+    UNPROTECT(1);
+    return out;
+}
+
+/* countOverlaps(x, y) on the original ranges (the observed statistic): integer[G] */
+SEXP nrb200_R_count_observed(SEXP ptr, SEXP n_query, SEXP minoverlap) {
+    const R_xlen_t G = (R_xlen_t)Rf_asReal(n_query);
+    SEXP out = PROTECT(Rf_allocVector(INTSXP, G));
+    int64_t total = 0;
+    check(H(ptr), nrb200_count_observed_ex(H(ptr), Rf_asInteger(minoverlap), INTEGER(out), &total));
+    UNPROTECT(1);
+    return out;
+}
+
+/* permute variants drawn on the device: the tile (1-based) every block of iterations 1..n_iter moved to, as an
+ * integer matrix [n_blocks x n_iter] -- what blockStart needs */
+SEXP nrb200_R_fetch_dst_tiles(SEXP ptr, SEXP n_iter, SEXP n_blocks) {
+    const int R = Rf_asInteger(n_iter), B = Rf_asInteger(n_blocks);
+    SEXP out = PROTECT(Rf_allocMatrix(INTSXP, B, R));
+    check(H(ptr), nrb200_fetch_dst_tiles(H(ptr), 0, R, INTEGER(out)));
+    int *p = INTEGER(out);
+    for (int64_t i = 0, n = (int64_t)R * B; i < n; i++) p[i] += 1;
+    UNPROTECT(1);
+    return out;
+}
+
 static const R_CallMethodDef call_methods[] = {
     {"nrb200_R_create", (DL_FUNC)&nrb200_R_create, 1},
     {"nrb200_R_set_ranges", (DL_FUNC)&nrb200_R_set_ranges, 6},
@@ -237,6 +329,9 @@ static const R_CallMethodDef call_methods[] = {
     {"nrb200_R_run_weighted", (DL_FUNC)&nrb200_R_run_weighted, 10},
     {"nrb200_R_run_weighted_moments", (DL_FUNC)&nrb200_R_run_weighted_moments, 10},
     {"nrb200_R_run_materialize", (DL_FUNC)&nrb200_R_run_materialize, 7},
+    {"nrb200_R_run_moments", (DL_FUNC)&nrb200_R_run_moments, 9},
+    {"nrb200_R_count_observed", (DL_FUNC)&nrb200_R_count_observed, 3},
+    {"nrb200_R_fetch_dst_tiles", (DL_FUNC)&nrb200_R_fetch_dst_tiles, 3},
     {NULL, NULL, 0}};
 
 void R_init_nullrangesB200(DllInfo *dll) {

@@ -37,4 +37,5 @@ SEXP R_MakeExternalPtr(void *, SEXP, SEXP);
 void *R_ExternalPtrAddr(SEXP);
 void R_ClearExternalPtr(SEXP);
 void R_RegisterCFinalizerEx(SEXP, R_CFinalizer_t, Rboolean);
+void R_CheckUserInterrupt(void);
 #endif

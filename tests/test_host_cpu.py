@@ -99,11 +99,11 @@ def test_granges_sort_semantics():
 def test_front_end_argument_checks():
     y = GRanges(["chr1"] * 3, [1, 20, 40], width=[5, 5, 5], seqlengths={"chr1": 100})
     with pytest.raises(ValueError, match="is.na"):
-        BR._setup(GRanges(["chr1"], [1], width=[2], seqlevels=["chr1"]), 10, None, None, "drop", True, "bootstrap", False, 0)
+        BR._setup(None, GRanges(["chr1"], [1], width=[2], seqlevels=["chr1"]), 10, None, None, "drop", True, "bootstrap", False)
     with pytest.raises(ValueError, match="should be one of"):
-        BR._setup(y, 10, None, None, "keep", True, "bootstrap", False, 0)
+        BR._setup(None, y, 10, None, None, "keep", True, "bootstrap", False)
     with pytest.raises(ValueError, match="should be one of"):
-        BR._setup(y, 10, None, None, "drop", True, "shuffle", False, 0)
+        BR._setup(None, y, 10, None, None, "drop", True, "shuffle", False)
     with pytest.raises(ValueError, match="state"):
         BR._seg_arrays(GRanges(["chr1"], [1], end=[100], seqlengths={"chr1": 100}), y)
     assert BR._plan_kind(None, True, "bootstrap", False) == _lib.UNSEG_ACROSS
