@@ -22,10 +22,12 @@ int nrb200_create(const nrb200_config *cfg, nrb200_handle **out) {
     nrb200_handle *h = new nrb200_handle();
     h->device = dev;
     h->flags = cfg ? cfg->flags : 0;
+    if (const char *e = getenv("NRB200_RPT")) h->tune_rpt = atoi(e) == 2 ? 2 : (atoi(e) == 4 ? 4 : 1);
     if (const char *e = getenv("NRB200_END_RANK")) h->tune_end_rank = atoi(e) != 0;
     if (const char *e = getenv("NRB200_ROWS_IPC")) h->tune_rows_ipc = std::min(std::max(atoi(e), 1), 64);
     if (const char *e = getenv("NRB200_TABLE_MULT")) h->tune_table_mult = atof(e);
     if (const char *e = getenv("NRB200_TABLE_CAP")) h->tune_table_cap = atoll(e);
+    if (const char *e = getenv("NRB200_WIRE16")) h->tune_wire16 = std::min(std::max(atoi(e), 0), 2);
     if (const char *e = getenv("NRB200_CHUNKS")) h->tune_chunks = std::min(std::max(atoi(e), 1), 64);
     if (const char *e = getenv("NRB200_MAX_BATCH")) h->tune_max_batch = std::min<int64_t>(std::max<int64_t>(atoll(e), 8), 2048);
     if (cfg && cfg->stream) {
@@ -60,6 +62,7 @@ void nrb200_destroy(nrb200_handle *h) {
     if (h->stage_buf) cudaFreeHost(h->stage_buf);
     if (h->stage_in) cudaFreeHost(h->stage_in);
     if (h->inspect_host) cudaFreeHost(h->inspect_host);
+    if (h->flags_host) cudaFreeHost(h->flags_host);
     for (auto &ev : h->batch_ev) cudaEventDestroy(ev);
     if (h->copy_stream) {
         cudaStreamSynchronize(h->copy_stream);
@@ -215,7 +218,7 @@ int nrb200_set_plan(nrb200_handle *h, const nrb200_plan_spec *spec, int64_t *n_b
     Plan p;
     const std::string msg = build_plan(*spec, h->seqlen, p);
     if (!msg.empty()) return fail(h, NRB200_ERR_INVALID, msg);
-    if (p.n_blocks() > (int64_t)INT32_MAX / 2) return fail(h, NRB200_ERR_UNSUPPORTED, "too many blocks per iteration");
+    if (p.n_blocks() >= ((int64_t)1 << (31 - kRecTileShift))) return fail(h, NRB200_ERR_UNSUPPORTED, "too many blocks per iteration");
     h->plan = std::move(p);
     const Plan &pl = h->plan;
     const size_t B = (size_t)pl.n_blocks();
@@ -223,6 +226,14 @@ int nrb200_set_plan(nrb200_handle *h, const nrb200_plan_spec *spec, int64_t *n_b
     if ((rc = upload(h, h->tile_seq, pl.tile_seq.data(), B))) return rc;
     if ((rc = upload(h, h->tile_start, pl.tile_start.data(), B))) return rc;
     if ((rc = upload(h, h->bait_width, pl.bait_width.data(), B))) return rc;
+    {
+        std::vector<int32_t> info(2 * B);  // {bait width, length of the tile's sequence} per tile, one 8-byte load
+        for (size_t t = 0; t < B; ++t) {
+            info[2 * t] = pl.bait_width[t];
+            info[2 * t + 1] = (int32_t)h->seqlen[pl.tile_seq[t]];
+        }
+        if ((rc = upload(h, h->tile_info, info.data(), info.size()))) return rc;
+    }
     // sampler tables packed into one int64 and one int32 buffer
     std::vector<int64_t> i64;
     std::vector<int32_t> i32;
@@ -333,7 +344,7 @@ int nrb200_run_counts(nrb200_handle *h, const nrb200_draws *draws, int64_t *iter
     if (h->copy_stream) NRB_CUDA(h, cudaStreamSynchronize(h->copy_stream));
     h->timeline.mark("run_counts returns", h->stream);
     h->timeline.dump();
-    if (stats) stats->d2h_bytes = (iter_nranges ? R * 8 : 0) + (iter_totals ? R * 8 : 0) + (feature_counts ? R * G * 4 : 0);
+    if (stats) stats->d2h_bytes = (iter_nranges ? R * 8 : 0) + (iter_totals ? R * 8 : 0) + (feature_counts ? R * G * (h->last_wire16 ? 2 : 4) : 0);
     return NRB200_OK;
 }
 
@@ -475,7 +486,7 @@ static int run_weighted_core(nrb200_handle *h, const nrb200_draws *draws, double
     P.iter_nranges = h->d_iter_nranges.as<unsigned long long>();
     P.n_hits = h->d_n_hits.as<unsigned long long>();
     P.draw_tab = h->draw_tab.as<int2>();
-    const FeatView F{h->f_src.as<int32_t>(), h->pair_off.as<int32_t>(), h->pair_rec.as<int4>(), h->pair_rec.as<int4>() + h->n_pairs};
+    const FeatView F{h->f_src.as<int32_t>(), h->pair_off.as<int32_t>(), h->pair_rec.as<int4>()};
     const WeightView W{h->n_cls > 1 ? h->w_r.as<double>() : h->w_c.as<double>(), h->w_ps.as<double>(),
                        h->ends_alias_starts ? h->w_ps.as<double>() : h->w_pe.as<double>()};
     NRB_CUDA(h, cudaEventRecord(h->ev[1], h->stream));

@@ -66,6 +66,7 @@ struct BootParams {
     // iteration-invariant block tables
     int64_t n_blocks;
     const int32_t *tile_seq, *tile_start, *bait_width;
+    const int2 *tile_info;    // [n_blocks] {bait width, length of the tile's sequence}
     const int64_t *seqlen;
     int permute, drop_zero;
     int rows_windows_only;    // rank path, excludeOption = "trim": rows = sum of the tile's gap windows
@@ -79,6 +80,8 @@ struct BootParams {
     int64_t n_iter, n_query;
     unsigned long long *iter_nranges, *iter_totals;  // [n_iter]
     int32_t *counts;          // [n_iter x n_query], caller's query order, or nullptr
+    unsigned short *counts16; // the same as uint16 (rank path; takes precedence), with one overflow flag for the launch
+    int *overflow16;
     int32_t *item_rows;       // [n_iter x n_blocks] surviving rows per item, or nullptr
     unsigned long long *n_hits;  // [kHitSlots] partial sums of the ranges sampled (byte-model H), slot = iteration % kHitSlots
     int2 *draw_tab;           // [n_iter x n_blocks] {bait seq, bait start}: rank path scratch

@@ -17,6 +17,9 @@
 #include <vector>
 
 #include <omp.h>
+#if defined(__SSE2__)
+#include <emmintrin.h>
+#endif
 
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
@@ -157,7 +160,7 @@ struct HostLists {
     bool valid = false;
     int64_t n_pairs = 0;
     std::vector<int32_t> f_src, f_off, x_off, x_rec;
-    std::vector<int32_t> recs;  // 4 words per record: the "a" halves of all records, then the "b" halves
+    std::vector<int32_t> recs;  // 4 words per record
 };
 
 struct GroupPool;
@@ -238,14 +241,16 @@ struct nrb200_handle {
     uint32_t flags = 0;
     // tuning knobs (environment, read at create)
     bool tune_end_rank = true;         // NRB200_END_RANK=0: always radix-sort the ends (index build)
+    int tune_rpt = 1;                  // NRB200_RPT: iterations per thread of the count kernel (1, 2 or 4)
     int tune_rows_ipc = 4;             // NRB200_ROWS_IPC: iterations a CTA of the rows kernel loops over
     double tune_table_mult = 4.0;
+    int tune_wire16 = 2;               // NRB200_WIRE16: uint16 wire format of a host-bound matrix (0 never, 1 always, 2 pageable destinations)
     int tune_chunks = 8;               // NRB200_CHUNKS: pipeline depth of nrb200_run_counts
     int64_t tune_max_batch = 2048;     // NRB200_MAX_BATCH: iterations per launch group
     int64_t tune_table_cap = 8 << 20;  // NRB200_TABLE_CAP: the multiplier applies up to this many entries
 
     Plan plan;
-    DevMem tile_seq, tile_start, bait_width, sampler_i64, sampler_i32;
+    DevMem tile_seq, tile_start, bait_width, tile_info, sampler_i64, sampler_i32;
     SamplerView sampler_view{};
     bool slices_dirty = true, have_pmax_table = false;
     DevMem q_tile_lo, q_tile_hi, x_tile_lo, x_tile_hi, pair_off, pair_rec, f_src, tile_x_off, tile_x_rec;
@@ -260,7 +265,9 @@ struct nrb200_handle {
 
     // run scratch / results
     DevMem d_bait_seq, d_bait_start, d_dst_tile, perm_vals_a, perm_vals_b, np_seg, np_start, np_state, np_list, np_cnt;
-    DevMem d_iter_nranges, d_iter_totals, d_counts, d_n_hits;
+    DevMem d_iter_nranges, d_iter_totals, d_counts, d_counts16, redo_scratch, d_n_hits;
+    int *flags_host = nullptr;         // pinned: per-chunk overflow flags of the uint16 wire format
+    bool last_wire16 = false;          // the last host-bound matrix travelled as uint16
     bool res_has_counts = false;
     // moments
     DevMem m_sum, m_sumsq, m_nge, m_observed;

@@ -268,11 +268,11 @@ int build_pairs(nrb200_handle *h) {
     struct Rec4 {
         int32_t x, y, z, w;
     };
-    std::vector<int32_t> f_recs_vec;  // the "a" halves of all records, then the "b" halves (rank_kernels.cuh)
-    Rec4 *f_recs = h->keep_lists ? nullptr : static_cast<Rec4 *>(arena_alloc(h, (size_t)std::max<int64_t>(2 * total, 1) * sizeof(Rec4)));
+    std::vector<int32_t> f_recs_vec;  // 16-byte window records (rank_kernels.cuh)
+    Rec4 *f_recs = h->keep_lists ? nullptr : static_cast<Rec4 *>(arena_alloc(h, (size_t)std::max<int64_t>(total, 1) * sizeof(Rec4)));
     const bool staged = f_recs != nullptr;
     if (!staged) {  // (the leader of a device group keeps the host copy for the other members)
-        f_recs_vec.resize((size_t)(8 * total));
+        f_recs_vec.resize((size_t)(4 * total));
         f_recs = reinterpret_cast<Rec4 *>(f_recs_vec.data());
     }
 #pragma omp parallel for schedule(dynamic, 1) num_threads(host_threads(h)) if (G >= 4096)
@@ -293,15 +293,15 @@ int build_pairs(nrb200_handle *h) {
                           f_off[at] = (int32_t)cursor;
                       },
                       [&](int32_t, int32_t t, int64_t ws, int64_t we, int sign, int cls) {
-                          f_recs[cursor] = Rec4{t, (int32_t)ws, (int32_t)std::min<int64_t>(we, INT32_MAX / 2), sign};
-                          f_recs[total + cursor] = Rec4{p.tile_start[t], p.bait_width[t], (int32_t)h->seqlen[p.tile_seq[t]], cls};
+                          f_recs[cursor] = Rec4{(t << kRecTileShift) | (cls << 1) | (sign < 0 ? 1 : 0), (int32_t)ws,
+                                                (int32_t)std::min<int64_t>(we, INT32_MAX / 2), p.tile_start[t]};
                           ++cursor;
                       });
     }
     tr.lap("lists");
     if ((rc = upload(h, h->f_src, f_src.data(), (size_t)G))) return rc;
     if ((rc = upload(h, h->pair_off, f_off.data(), (size_t)G + 1))) return rc;
-    if ((rc = staged ? upload_staged(h, h->pair_rec, f_recs, (size_t)(2 * total)) : upload(h, h->pair_rec, f_recs, (size_t)(2 * total)))) return rc;
+    if ((rc = staged ? upload_staged(h, h->pair_rec, f_recs, (size_t)total) : upload(h, h->pair_rec, f_recs, (size_t)total))) return rc;
     tr.lap("upload");
     if (h->keep_lists) {
         HostLists &L = h->lists;

@@ -26,17 +26,22 @@ namespace nrb {
 // (disjoint, sorted), so a range overlaps a run of consecutive regions and the union is
 // sum_k |S_k| - sum_k |S_k and S_k+1|.  A feature therefore owns a list of signed windows per tile.
 
-// One signed window to count for a feature on a tile: 32 bytes kept as two int4 in two parallel arrays, so that a
-// warp's 32 consecutive records are 4 full lines per load instead of 8 half-used ones.
-//   a = {tile (block index b, row of the draw table), ws, we (window on the tile's sequence: [gs, ge] or an exclusion
-//        pseudo-feature), sign (+1 / -1)}
-//   b = {tile_start, width, seq_len (copied from the block tables: saves three dependent loads), cls (strand class of
-//        y the window counts; 0 when y is unstranded)}
+// One signed window to count for a feature on a tile, 16 bytes (half a sector: the count kernel is bound by the
+// sectors it pulls through the L2, so the record carries only what is per window):
+//   {(tile << 4) | (cls << 1) | negative, ws, we, tile_start}
+// tile = block index b (row of the draw table), [ws, we] = window on the tile's sequence ([gs, ge] or an exclusion
+// pseudo-feature), cls = class of y the window counts (0 when y has one class), negative = the window is subtracted.
+// The tile's bait width and sequence length come from tile_info[tile] (8 bytes per tile, read beside the draw -- the
+// same tile for most lanes of a warp, so one broadcast).
+constexpr int kRecTileShift = 4;
+__device__ __forceinline__ int rec_tile(int32_t x) { return x >> kRecTileShift; }
+__device__ __forceinline__ int rec_cls(int32_t x) { return (x >> 1) & 7; }
+__device__ __forceinline__ int rec_sign(int32_t x) { return 1 - 2 * (x & 1); }
 
 struct FeatView {              // query features in visit order (grouped by list length)
     const int32_t *src;        // [n_query] index in the caller's order
     const int32_t *pair_off;   // [n_query + 1]
-    const int4 *rec_a, *rec_b;  // [n_pairs] each
+    const int4 *rec;           // [n_pairs]
 };
 
 struct TileExcl {              // signed exclusion windows of each (tile, strand class), for the rows kernel
@@ -69,63 +74,114 @@ __device__ __forceinline__ int count_spanning(const RangesView &y, const int4 si
     return n;
 }
 
-// The count of one evaluation: both table entries are fetched together (two independent 8-byte loads, one sector
-// each), the ranks come out of the entries themselves.
+// The counts of RPT evaluations that share a window (RPT consecutive iterations), stage by stage so that the
+// independent loads of a stage are in flight together: sequence infos, then both table entries of every evaluation
+// (two 8-byte loads, one sector each), then the ranks out of the entries themselves.
 // PERMUTE: a range belongs to the ONE tile that holds its start (findOverlaps(select = "first"),
 // R/bootUnsegmented.R:95, :155), so the members are {bs <= start <= A and end >= Bv}: the bootstrap
 // count minus the ranges that start before the tile and reach Bv (they contain [bs - 1, Bv]).
+template <int RPT, bool PERMUTE>
+__device__ __forceinline__ void count_pairs(const RangesView &y, const int2 (&d)[RPT], int cls, int32_t width, int32_t ts,
+                                            int32_t seq_len, int32_t gs, int32_t ge, int (&cnt)[RPT]) {
+    PairProbe q[RPT];
+    int32_t key_a[RPT], key_b[RPT], ua[RPT], ub[RPT];
+    RankEntry ea[RPT], eb[RPT];
+#pragma unroll
+    for (int j = 0; j < RPT; ++j) q[j].si = __ldg(y.rseq_info + d[j].x * y.n_cls + cls);
+#pragma unroll
+    for (int j = 0; j < RPT; ++j) {
+        pair_keys(q[j], d[j], width, ts, seq_len, gs, ge);
+        key_a[j] = rank_clamp_key(q[j].A + 1, q[j].si);
+        key_b[j] = rank_clamp_key(q[j].Bv - y.end_shift, q[j].si);
+        ua[j] = q[j].si.w + (key_a[j] >> y.rank_shift);
+        ub[j] = q[j].si.w + (key_b[j] >> y.rank_shift);
+        ea[j] = __ldg(y.rrank_start + ua[j]);
+        eb[j] = __ldg(y.rank_end + ub[j]);
+    }
+#pragma unroll
+    for (int j = 0; j < RPT; ++j) {
+        if (q[j].A < 1 || (PERMUTE && q[j].A < q[j].bs)) continue;  // permute: no start can lie in [bs, A]
+        const int32_t ia = rank_from_entry(y.rstart, y.rrank_start, y.rank_shift, q[j].si, key_a[j], ua[j], ea[j]);
+        int n;
+        if (q[j].Bv <= q[j].A) n = ia - rank_from_entry(y.end_sorted, y.rank_end, y.rank_shift, q[j].si, key_b[j], ub[j], eb[j]);
+        else n = count_spanning(y, q[j].si, ia, q[j].Bv);  // the feature lies beside the tile
+        if (PERMUTE && n > 0)
+            n -= count_spanning(y, q[j].si, first_ge_ranked(y.rstart, y.rrank_start, y.rank_shift, q[j].si, q[j].bs), q[j].Bv);
+        cnt[j] += n;
+    }
+}
+
 template <bool PERMUTE>
 __device__ __forceinline__ int count_pair(const RangesView &y, int2 d, int cls, int32_t width, int32_t ts, int32_t seq_len,
                                           int32_t gs, int32_t ge) {
-    PairProbe q;
-    q.si = __ldg(y.rseq_info + d.x * y.n_cls + cls);
-    pair_keys(q, d, width, ts, seq_len, gs, ge);
-    const int32_t key_a = rank_clamp_key(q.A + 1, q.si), key_b = rank_clamp_key(q.Bv - y.end_shift, q.si);
-    const int32_t ua = q.si.w + (key_a >> y.rank_shift), ub = q.si.w + (key_b >> y.rank_shift);
-    const RankEntry ea = __ldg(y.rrank_start + ua), eb = __ldg(y.rank_end + ub);
-    if (q.A < 1 || (PERMUTE && q.A < q.bs)) return 0;  // permute: no start can lie in [bs, A]
-    const int32_t ia = rank_from_entry(y.rstart, y.rrank_start, y.rank_shift, q.si, key_a, ua, ea);
-    int n;
-    if (q.Bv <= q.A) n = ia - rank_from_entry(y.end_sorted, y.rank_end, y.rank_shift, q.si, key_b, ub, eb);
-    else n = count_spanning(y, q.si, ia, q.Bv);  // the feature lies beside the tile
-    if (PERMUTE && n > 0) n -= count_spanning(y, q.si, first_ge_ranked(y.rstart, y.rrank_start, y.rank_shift, q.si, q.bs), q.Bv);
-    return n;
+    const int2 dd[1] = {d};
+    int c[1] = {0};
+    count_pairs<1, PERMUTE>(y, dd, cls, width, ts, seq_len, gs, ge, c);
+    return c[0];
 }
 
-// Thread = (feature, iteration); the block draws come from the table the block-rows kernel wrote.  Features are
-// visited in F's order (grouped by tile count, so a warp's lanes loop the same number of times; neighbours in a
-// group are neighbours on the genome, so they mostly share their tile and the draw is one broadcast load).  No
-// atomics on the count matrix, no memset: every element is written exactly once.
-// 128-thread CTAs, 16 per SM (32 registers): the kernel is a chain of dependent L2 hits -- record -> draw -> sequence
-// info -> table entries -- and resident warps are what hides it.
+// Thread = (feature, RPT consecutive iterations); the block draws come from the table the block-rows kernel wrote.
+// Features are visited in F's order (grouped by tile count, so a warp's lanes loop the same number of times;
+// neighbours in a group are neighbours on the genome, so they mostly share their tile and the draw is one broadcast
+// load).  No atomics on the count matrix, no memset: every element is written exactly once -- as int32, or as uint16
+// (the wire format of a host-bound matrix: half the bytes through the L2, HBM and PCIe; a count above 65535 raises
+// the chunk's overflow flag and the chunk is redone in int32).
+// The kernel is bound by the 32-byte sectors it pulls through the L2 (two table entries per evaluation, the 16-byte
+// record and the draw per RPT evaluations); resident warps hide the latency of the chain record -> draw -> sequence
+// info -> table entries.
 constexpr int kCountThreads = 128;
-__global__ void __launch_bounds__(kCountThreads, 16) boot_rank_count_kernel(const BootParams P, const FeatView F) {
-    __shared__ int warp_tot[kCountThreads / 32];
+template <int RPT, int MINB>
+__global__ void __launch_bounds__(kCountThreads, MINB) boot_rank_count_kernel(const BootParams P, const FeatView F) {
+    __shared__ int warp_tot[kCountThreads / 32][RPT];
     const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int64_t r = blockIdx.y;
-    int cnt = 0;
+    const int64_t r0 = (int64_t)blockIdx.y * RPT;
+    const int n_live = (int)min((int64_t)RPT, P.n_iter - r0);
+    int cnt[RPT];
+#pragma unroll
+    for (int j = 0; j < RPT; ++j) cnt[j] = 0;
     if (g < P.n_query) {
         const int32_t src = __ldg(F.src + g);
         const int32_t p1 = __ldg(F.pair_off + g + 1);
-        const int2 *__restrict__ tab = P.draw_tab + r * P.n_blocks;
+        const int2 *__restrict__ tab = P.draw_tab + r0 * P.n_blocks;
         for (int32_t p = __ldg(F.pair_off + g); p < p1; ++p) {
-            const int4 ra = __ldg(F.rec_a + p);  // tile, ws, we, sign
-            const int4 rb = __ldg(F.rec_b + p);  // tile_start, width, seq_len, cls
-            const int2 d = __ldg(tab + ra.x);
-            const int c = P.permute ? count_pair<true>(P.y, d, rb.w, rb.y, rb.x, rb.z, ra.y, ra.z)
-                                    : count_pair<false>(P.y, d, rb.w, rb.y, rb.x, rb.z, ra.y, ra.z);
-            cnt += ra.w * c;
+            const int4 rec = __ldg(F.rec + p);
+            const int tile = rec_tile(rec.x);
+            const int2 ti = __ldg(P.tile_info + tile);  // bait width, sequence length
+            int2 d[RPT];
+#pragma unroll
+            for (int j = 0; j < RPT; ++j) d[j] = __ldg(tab + (int64_t)(j < n_live ? j : 0) * P.n_blocks + tile);  // tail: recount row 0, discarded
+            int c[RPT];
+#pragma unroll
+            for (int j = 0; j < RPT; ++j) c[j] = 0;
+            if (P.permute) count_pairs<RPT, true>(P.y, d, rec_cls(rec.x), ti.x, rec.w, ti.y, rec.y, rec.z, c);
+            else count_pairs<RPT, false>(P.y, d, rec_cls(rec.x), ti.x, rec.w, ti.y, rec.y, rec.z, c);
+            const int sign = rec_sign(rec.x);
+#pragma unroll
+            for (int j = 0; j < RPT; ++j) cnt[j] += sign * c[j];
         }
-        if (P.counts) __stcs(P.counts + r * P.n_query + src, cnt);  // streaming store: written once, read back by the copy engine
+#pragma unroll
+        for (int j = 0; j < RPT; ++j) {
+            if (j >= n_live) continue;
+            // streaming stores: written once, read back by the copy engine
+            if (P.counts16) {
+                __stcs(P.counts16 + (r0 + j) * P.n_query + src, (unsigned short)min(cnt[j], 65535));
+                if (cnt[j] > 65535) atomicOr(P.overflow16, 1);
+            } else if (P.counts) {
+                __stcs(P.counts + (r0 + j) * P.n_query + src, cnt[j]);
+            }
+        }
     }
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int s = __reduce_add_sync(kFull, cnt);
-    if (lane == 0) warp_tot[warp] = s;
+#pragma unroll
+    for (int j = 0; j < RPT; ++j) {
+        const int s = __reduce_add_sync(kFull, cnt[j]);
+        if (lane == 0) warp_tot[warp][j] = s;
+    }
     __syncthreads();
-    if (threadIdx.x == 0) {
+    if (threadIdx.x < n_live) {
         unsigned long long t = 0;
-        for (int w = 0; w < kCountThreads / 32; ++w) t += (unsigned)warp_tot[w];
-        if (t) atomicAdd(P.iter_totals + r, t);
+        for (int w = 0; w < kCountThreads / 32; ++w) t += (unsigned)warp_tot[w][threadIdx.x];
+        if (t) atomicAdd(P.iter_totals + r0 + threadIdx.x, t);
     }
 }
 
@@ -181,12 +237,13 @@ __global__ void __launch_bounds__(256) boot_rank_wsum_kernel(const BootParams P,
         const int32_t src = __ldg(F.src + g);
         const int32_t p1 = __ldg(F.pair_off + g + 1);
         for (int32_t p = __ldg(F.pair_off + g); p < p1; ++p) {
-            const int4 ra = __ldg(F.rec_a + p);
-            const int4 rb = __ldg(F.rec_b + p);
-            const int2 d = __ldg(P.draw_tab + r * P.n_blocks + ra.x);
-            const double v = P.permute ? weighted_pair<true>(P.y, W, d, rb.w, rb.y, rb.x, rb.z, ra.y, ra.z)
-                                       : weighted_pair<false>(P.y, W, d, rb.w, rb.y, rb.x, rb.z, ra.y, ra.z);
-            acc += ra.w * v;
+            const int4 rec = __ldg(F.rec + p);
+            const int tile = rec_tile(rec.x);
+            const int2 ti = __ldg(P.tile_info + tile);
+            const int2 d = __ldg(P.draw_tab + r * P.n_blocks + tile);
+            const double v = P.permute ? weighted_pair<true>(P.y, W, d, rec_cls(rec.x), ti.x, rec.w, ti.y, rec.y, rec.z)
+                                       : weighted_pair<false>(P.y, W, d, rec_cls(rec.x), ti.x, rec.w, ti.y, rec.y, rec.z);
+            acc += rec_sign(rec.x) * v;
         }
         if (sums) sums[r * P.n_query + src] = acc;
     }

@@ -187,6 +187,7 @@ BootParams make_params(nrb200_handle *h, const nrb200_draws *d) {
     P.tile_seq = h->tile_seq.as<int32_t>();
     P.tile_start = h->tile_start.as<int32_t>();
     P.bait_width = h->bait_width.as<int32_t>();
+    P.tile_info = h->tile_info.as<int2>();
     P.seqlen = h->seqlen_dev.as<int64_t>();
     P.permute = h->plan.permute();
     P.drop_zero = h->plan.drop_zero_width();
@@ -235,9 +236,12 @@ int launch_rank(nrb200_handle *h, const BootParams &P, bool has_query) {
     }
     if (h->split_ev) cudaEventRecord(h->split_ev, h->stream);  // stats: end of the rows kernel
     if (has_query) {
-        const FeatView F{h->f_src.as<int32_t>(), h->pair_off.as<int32_t>(), h->pair_rec.as<int4>(), h->pair_rec.as<int4>() + h->n_pairs};
-        const dim3 grid((unsigned)((P.n_query + kCountThreads - 1) / kCountThreads), (unsigned)P.n_iter);
-        boot_rank_count_kernel<<<grid, kCountThreads, 0, h->stream>>>(P, F);
+        const FeatView F{h->f_src.as<int32_t>(), h->pair_off.as<int32_t>(), h->pair_rec.as<int4>()};
+        const int rpt = h->tune_rpt;
+        const dim3 grid((unsigned)((P.n_query + kCountThreads - 1) / kCountThreads), (unsigned)((P.n_iter + rpt - 1) / rpt));
+        if (rpt == 2) boot_rank_count_kernel<2, 12><<<grid, kCountThreads, 0, h->stream>>>(P, F);
+        else if (rpt == 4) boot_rank_count_kernel<4, 8><<<grid, kCountThreads, 0, h->stream>>>(P, F);
+        else boot_rank_count_kernel<1, 16><<<grid, kCountThreads, 0, h->stream>>>(P, F);
         ++launches;
     }
     return launches;
@@ -269,14 +273,40 @@ BootParams slice_params(const BootParams &P, int64_t r0, int64_t n) {
     if (P.iter_nranges) Q.iter_nranges = P.iter_nranges + r0;
     if (P.iter_totals) Q.iter_totals = P.iter_totals + r0;
     if (P.counts) Q.counts = P.counts + r0 * P.n_query;
+    if (P.counts16) Q.counts16 = P.counts16 + r0 * P.n_query;
     if (P.item_rows) Q.item_rows = P.item_rows + r0 * P.n_blocks;
     if (P.item_rec) Q.item_rec = P.item_rec + r0 * P.n_blocks;
     return Q;
 }
 
+// uint16 -> int32, written with streaming stores (the destination is not read again by this thread)
+inline void widen_u16_to_i32(const uint16_t *src, int32_t *dst, size_t n) {
+    size_t i = 0;
+#if defined(__SSE2__)
+    while (i < n && (reinterpret_cast<uintptr_t>(dst + i) & 15)) {
+        dst[i] = src[i];
+        ++i;
+    }
+    const __m128i zero = _mm_setzero_si128();
+    for (; i + 8 <= n; i += 8) {
+        const __m128i v = _mm_loadu_si128(reinterpret_cast<const __m128i *>(src + i));
+        _mm_stream_si128(reinterpret_cast<__m128i *>(dst + i), _mm_unpacklo_epi16(v, zero));
+        _mm_stream_si128(reinterpret_cast<__m128i *>(dst + i + 4), _mm_unpackhi_epi16(v, zero));
+    }
+    _mm_sfence();
+#endif
+    for (; i < n; ++i) dst[i] = src[i];
+}
+
 // Core of every counting entry point: results stay on the device.  With host_counts set, the
 // iterations run in chunks and each chunk of the [R x G] matrix starts its way to the host
 // (copy stream) while the next chunk computes.
+//
+// Wire format of a host-bound matrix (rank path): uint16.  Counts of overlaps per (feature, iteration) are small
+// (cfg 2: mean 15, max a few hundred), so the kernel stores them as uint16 -- half the bytes through L2, HBM and
+// PCIe -- into a pinned staging buffer, and the host widens every chunk into the caller's int32 matrix (R `integer`)
+// with all its threads while later chunks still compute / travel.  A count above 65535 raises the chunk's overflow
+// flag; such a chunk is computed again with int32 output.  NRB200_WIRE16=0 turns the format off.
 int run_counts_core(nrb200_handle *h, const nrb200_draws *d, bool want_counts, int32_t *host_counts,
                     nrb200_stats *stats) {
     int rc;
@@ -292,21 +322,51 @@ int run_counts_core(nrb200_handle *h, const nrb200_draws *d, bool want_counts, i
     NRB_CUDA(h, cudaMemsetAsync(h->d_iter_nranges.p, 0, R * 8, h->stream));
     NRB_CUDA(h, cudaMemsetAsync(h->d_iter_totals.p, 0, R * 8, h->stream));
     if ((rc = hits_reset(h))) return rc;
+    const bool pipelined = host_counts && want_counts && R > 0;
+    bool pageable = false;
+    if (pipelined) {
+        cudaPointerAttributes attr{};
+        pageable = cudaPointerGetAttributes(&attr, host_counts) != cudaSuccess || attr.type == cudaMemoryTypeUnregistered;
+        cudaGetLastError();  // an unregistered pointer may leave a sticky-free error behind on older drivers
+    }
+    const size_t cells = (size_t)R * (size_t)std::max<int64_t>(G, 0);
+    // tune_wire16: 0 never, 1 always, 2 (default) for pageable destinations only -- a pinned destination takes the
+    // int32 matrix by DMA without any host work
+    bool wire16 = pipelined && rank_path_ok(h) && cells * 2 <= kMaxStagingBytes && (h->tune_wire16 == 1 || (h->tune_wire16 == 2 && pageable));
+    if (wire16 && h->stage_cap < cells * 2) {
+        if (h->stage_buf) cudaFreeHost(h->stage_buf);
+        h->stage_buf = nullptr;
+        h->stage_cap = 0;
+        if (cudaMallocHost((void **)&h->stage_buf, cells * 2) == cudaSuccess) h->stage_cap = cells * 2;
+        else {
+            cudaGetLastError();
+            wire16 = false;
+        }
+    }
     int32_t *counts = nullptr;
-    if (want_counts) {
-        NRB_CUDA(h, h->d_counts.reserve((size_t)R * G * sizeof(int32_t)));
+    uint16_t *counts16 = nullptr;
+    int *flags_dev = nullptr;
+    if (wire16) {
+        NRB_CUDA(h, h->d_counts16.reserve(((cells * 2 + 15) & ~(size_t)15) + kChunkEvents * sizeof(int)));  // matrix, then the flags
+        counts16 = h->d_counts16.as<uint16_t>();
+        flags_dev = reinterpret_cast<int *>(h->d_counts16.as<char>() + ((cells * 2 + 15) & ~(size_t)15));
+        NRB_CUDA(h, cudaMemsetAsync(flags_dev, 0, kChunkEvents * sizeof(int), h->stream));
+        if (!h->flags_host) NRB_CUDA(h, cudaMallocHost((void **)&h->flags_host, kChunkEvents * sizeof(int)));
+        std::memset(h->flags_host, 0, kChunkEvents * sizeof(int));
+    } else if (want_counts) {
+        NRB_CUDA(h, h->d_counts.reserve(cells * sizeof(int32_t)));
         counts = h->d_counts.as<int32_t>();
         // the rank path writes every element; the streaming path accumulates with atomics
-        if (!rank_path_ok(h)) NRB_CUDA(h, cudaMemsetAsync(counts, 0, (size_t)R * G * sizeof(int32_t), h->stream));
+        if (!rank_path_ok(h)) NRB_CUDA(h, cudaMemsetAsync(counts, 0, cells * sizeof(int32_t), h->stream));
     }
     BootParams P = make_params(h, d);
     P.iter_nranges = h->d_iter_nranges.as<unsigned long long>();
     P.iter_totals = h->d_iter_totals.as<unsigned long long>();
     P.counts = counts;
+    P.counts16 = counts16;
     P.n_hits = stats ? h->d_n_hits.as<unsigned long long>() : nullptr;  // the H statistic is tallied only when it is asked for
     NRB_CUDA(h, cudaEventRecord(h->ev[1], h->stream));
     int launches = 0;
-    const bool pipelined = host_counts && counts && R > 0;
     // Iterations go in batches: bounded draw-table scratch on the rank path and, when the matrix
     // is wanted on the host, chunk k copies out (copy stream) while chunk k + 1 computes.
     int64_t chunk = h->tune_max_batch;
@@ -318,16 +378,13 @@ int run_counts_core(nrb200_handle *h, const nrb200_draws *d, bool want_counts, i
         NRB_CUDA(h, h->draw_tab.reserve((size_t)std::min(chunk, std::max<int64_t>(R, 1)) * h->plan.n_blocks() * sizeof(int2)));
         P.draw_tab = h->draw_tab.as<int2>();
     }
-    // A pageable destination (R's own vectors are): cudaMemcpyAsync would stage it synchronously at a few GB/s.
+    // A pageable int32 destination (R's own vectors are): cudaMemcpyAsync would stage it synchronously at a few GB/s.
     // Copy chunk by chunk into a pinned staging buffer of the handle instead and move each chunk on with a
     // parallel memcpy as soon as its copy event fires, while later chunks still compute / travel.
     int32_t *staging = nullptr;
     std::vector<std::pair<int64_t, int64_t>> staged;  // (first iteration, count) of every chunk, in order
-    if (pipelined) {
-        cudaPointerAttributes attr{};
-        const bool pageable = cudaPointerGetAttributes(&attr, host_counts) != cudaSuccess || attr.type == cudaMemoryTypeUnregistered;
-        cudaGetLastError();  // an unregistered pointer may leave a sticky-free error behind on older drivers
-        const size_t bytes = (size_t)R * G * sizeof(int32_t);
+    if (pipelined && !wire16) {
+        const size_t bytes = cells * sizeof(int32_t);
         if (pageable) advise_huge_pages(host_counts, bytes);
         if (pageable && bytes <= kMaxStagingBytes) {
             if (h->stage_cap < bytes) {
@@ -340,6 +397,8 @@ int run_counts_core(nrb200_handle *h, const nrb200_draws *d, bool want_counts, i
             if (h->stage_cap >= bytes) staging = static_cast<int32_t *>(h->stage_buf);
         }
     }
+    if (wire16 && pageable) advise_huge_pages(host_counts, cells * sizeof(int32_t));
+    uint16_t *staging16 = wire16 ? static_cast<uint16_t *>(h->stage_buf) : nullptr;
     int k = 0;
     const bool split = stats && rank_path_ok(h);
     for (int64_t r0 = 0; r0 < R; r0 += chunk, ++k) {
@@ -353,7 +412,9 @@ int run_counts_core(nrb200_handle *h, const nrb200_draws *d, bool want_counts, i
             NRB_CUDA(h, cudaEventRecord(h->batch_ev[3 * k], h->stream));
             h->split_ev = h->batch_ev[3 * k + 1];
         }
-        launches += launch_count(h, slice_params(P, r0, n), has_query);
+        BootParams Q = slice_params(P, r0, n);
+        if (wire16) Q.overflow16 = flags_dev + (k % kChunkEvents);
+        launches += launch_count(h, Q, has_query);
         h->split_ev = nullptr;
         if (split) NRB_CUDA(h, cudaEventRecord(h->batch_ev[3 * k + 2], h->stream));
         NRB_CUDA(h, cudaGetLastError());
@@ -363,10 +424,17 @@ int run_counts_core(nrb200_handle *h, const nrb200_draws *d, bool want_counts, i
             if (!ev) NRB_CUDA(h, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
             NRB_CUDA(h, cudaEventRecord(ev, h->stream));
             NRB_CUDA(h, cudaStreamWaitEvent(h->copy_stream, ev, 0));
-            NRB_CUDA(h, cudaMemcpyAsync((staging ? staging : host_counts) + r0 * G, counts + r0 * G, (size_t)n * G * sizeof(int32_t),
-                                        cudaMemcpyDeviceToHost, h->copy_stream));
+            if (wire16) {
+                NRB_CUDA(h, cudaMemcpyAsync(staging16 + r0 * G, counts16 + r0 * G, (size_t)n * G * sizeof(uint16_t), cudaMemcpyDeviceToHost,
+                                            h->copy_stream));
+                NRB_CUDA(h, cudaMemcpyAsync(h->flags_host + (k % kChunkEvents), flags_dev + (k % kChunkEvents), sizeof(int),
+                                            cudaMemcpyDeviceToHost, h->copy_stream));
+            } else {
+                NRB_CUDA(h, cudaMemcpyAsync((staging ? staging : host_counts) + r0 * G, counts + r0 * G, (size_t)n * G * sizeof(int32_t),
+                                            cudaMemcpyDeviceToHost, h->copy_stream));
+            }
             h->timeline.mark("chunk copied out", h->copy_stream);
-            if (staging) {
+            if (staging || wire16) {
                 cudaEvent_t &done = h->copied_ev[k % kChunkEvents];
                 if (!done) NRB_CUDA(h, cudaEventCreateWithFlags(&done, cudaEventDisableTiming));
                 NRB_CUDA(h, cudaEventRecord(done, h->copy_stream));
@@ -375,18 +443,54 @@ int run_counts_core(nrb200_handle *h, const nrb200_draws *d, bool want_counts, i
         }
     }
     NRB_CUDA(h, cudaEventRecord(h->ev[2], h->stream));
+    std::vector<size_t> redo;  // wire16: chunks whose overflow flag is up
     for (size_t c = 0; c < staged.size(); ++c) {  // chunk c has landed in pinned memory: hand it to the caller
         NRB_CUDA(h, cudaEventSynchronize(h->copied_ev[c % kChunkEvents]));
         const int64_t r0 = staged[c].first, n = staged[c].second;
-        const size_t bytes = (size_t)n * G * sizeof(int32_t);
-        const char *src = reinterpret_cast<const char *>(staging + r0 * G);
-        char *dst = reinterpret_cast<char *>(host_counts + r0 * G);
-        const size_t piece = (size_t)1 << 20;
-        const int64_t pieces = (int64_t)((bytes + piece - 1) / piece);
+        const size_t piece = (size_t)1 << 18;  // elements per task
+        const size_t elems = (size_t)n * G;
+        const int64_t pieces = (int64_t)((elems + piece - 1) / piece);
+        if (wire16) {
+            if (h->flags_host[c % kChunkEvents]) {
+                redo.push_back(c);
+                continue;
+            }
+            const uint16_t *src = staging16 + r0 * G;
+            int32_t *dst = host_counts + r0 * G;
 #pragma omp parallel for schedule(static) num_threads(host_threads(h))
-        for (int64_t i = 0; i < pieces; ++i) std::memcpy(dst + i * piece, src + i * piece, std::min(piece, bytes - (size_t)i * piece));
+            for (int64_t i = 0; i < pieces; ++i) widen_u16_to_i32(src + i * piece, dst + i * piece, std::min(piece, elems - (size_t)i * piece));
+        } else {
+            const int32_t *src = staging + r0 * G;
+            int32_t *dst = host_counts + r0 * G;
+#pragma omp parallel for schedule(static) num_threads(host_threads(h))
+            for (int64_t i = 0; i < pieces; ++i)
+                std::memcpy(dst + i * piece, src + i * piece, std::min(piece, elems - (size_t)i * piece) * sizeof(int32_t));
+        }
     }
-    h->res_has_counts = want_counts;
+    if (!redo.empty()) {
+        // some count exceeds 65535: those chunks again, with int32 output (the per-iteration vectors of the second pass go
+        // to scratch: the first pass already holds them)
+        int64_t n_max = 0;
+        for (size_t c : redo) n_max = std::max(n_max, staged[c].second);
+        NRB_CUDA(h, h->d_counts.reserve((size_t)n_max * G * sizeof(int32_t)));
+        NRB_CUDA(h, h->redo_scratch.reserve((size_t)n_max * 16));
+        for (size_t c : redo) {
+            const int64_t r0 = staged[c].first, n = staged[c].second;
+            NRB_CUDA(h, cudaMemsetAsync(h->redo_scratch.p, 0, (size_t)n * 16, h->stream));
+            BootParams Q = slice_params(P, r0, n);
+            Q.counts16 = nullptr;
+            Q.overflow16 = nullptr;
+            Q.counts = h->d_counts.as<int32_t>();
+            Q.iter_nranges = h->redo_scratch.as<unsigned long long>();
+            Q.iter_totals = h->redo_scratch.as<unsigned long long>() + n;
+            Q.n_hits = nullptr;
+            launches += launch_count(h, Q, has_query);
+            NRB_CUDA(h, cudaGetLastError());
+            if ((rc = download(h, host_counts + r0 * G, h->d_counts.p, (size_t)n * G * sizeof(int32_t)))) return rc;
+        }
+    }
+    h->res_has_counts = want_counts && !wire16;
+    h->last_wire16 = wire16;
     if (stats) {
         NRB_CUDA(h, cudaEventSynchronize(h->ev[2]));
         float k_ms = 0, t_ms = 0;

@@ -1,0 +1,111 @@
+"""Development probe of the end-to-end bootCounts() step and of the resident kernels (cfg 2), one script with modes
+(run on the GPU box; every line it prints is JSON):
+
+  python scripts/e2e_probe.py step [--gpus N] [--dest pinned|pageable|fresh] [--reps K]
+      wall clock of bootCounts(y, x, 5e5, R = 1000 * N) from host arrays: dest = pinned result buffers, pageable
+      buffers reused across calls, or freshly allocated pageable buffers every call (what an R caller has)
+  python scripts/e2e_probe.py kernels
+      rows / count kernel ms per 1000 iterations, device-resident
+  python scripts/e2e_probe.py sweep
+      both of the above under the tuning knobs (NRB200_RPT, NRB200_WIRE16, NRB200_CHUNKS), one child process each
+  python scripts/e2e_probe.py timeline
+      NRB200_TRACE_DEV timeline of one step (host queue time vs device arrival of every stage)
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+L_B, R1 = 500_000, 1000
+
+
+def inputs(pin: bool):
+    import numpy as np
+    from nullranges_b200 import synth
+    y, x = synth.atac_peaks(1_000_000, seed=3), synth.genes(20_000, seed=2)
+    keep = []
+    if pin:
+        import torch
+        for gr in (y, x):
+            for k in ("seqid", "start", "end"):
+                a = getattr(gr, k)
+                t = torch.empty(a.shape, dtype=torch.int32, pin_memory=True)
+                t.numpy()[...] = a
+                keep.append(t)
+                setattr(gr, k, t.numpy())
+    return y, x, keep
+
+
+def step(args):
+    import numpy as np
+    import torch
+    from nullranges_b200 import bootCounts
+    y, x, keep = inputs(pin=args.dest == "pinned")
+    R, G = R1 * args.gpus, len(x)
+    out = None
+    if args.dest == "pinned":
+        ts = {k: torch.empty(s, dtype=d, pin_memory=True) for k, s, d in (("iter_totals", (R,), torch.int64), ("iter_nranges", (R,), torch.int64),
+                                                                           ("feature_counts", (R, G), torch.int32))}
+        out = {k: t.numpy() for k, t in ts.items()}
+    elif args.dest == "pageable":
+        out = {"iter_totals": np.zeros(R, np.int64), "iter_nranges": np.zeros(R, np.int64), "feature_counts": np.zeros((R, G), np.int32)}
+    gpus = args.gpus if args.gpus > 1 else None
+    times, check = [], None
+    for rep in range(args.reps + 2):
+        t0 = time.perf_counter()
+        res = bootCounts(y, x, L_B, R=R, rng="philox", seed=2024, iter0=0, out=out, gpus=gpus)
+        times.append(time.perf_counter() - t0)
+        check = int(res.iter_totals.sum()), int(res.feature_counts[:: max(R // 7, 1)].sum())
+        del res
+    times = sorted(times[2:])
+    print(json.dumps({"mode": "step", "gpus": args.gpus, "dest": args.dest, "R": R, "ms_min": 1e3 * times[0], "ms_median": 1e3 * times[len(times) // 2],
+                      "iters_per_s_median": R / times[len(times) // 2], "checksum": check,
+                      "env": {k: v for k, v in os.environ.items() if k.startswith("NRB200_")}}), flush=True)
+
+
+def kernels(args):
+    from nullranges_b200 import Draws, Engine, _lib
+    y, x, _ = inputs(pin=False)
+    e = Engine(0)
+    e.set_ranges(y.seqlengths, y.seqid, y.start, y.end, None)
+    e.set_query(x.seqid, x.start, x.end, None)
+    e.set_plan(_lib.UNSEG_ACROSS, L_B)
+    best = None
+    for rep in range(8):
+        st = e.run_counts_resident(Draws(n_iter=R1, rng_mode=_lib.RNG_PHILOX, seed=2024, iter0=rep * R1), True, True)
+        if rep >= 2 and (best is None or st["kernel_ms"] < best["kernel_ms"]):
+            best = st
+    print(json.dumps({"mode": "kernels", "rows_ms": best["rows_kernel_ms"], "count_ms": best["count_kernel_ms"], "both_ms": best["kernel_ms"],
+                      "windows": best["n_windows"], "env": {k: v for k, v in os.environ.items() if k.startswith("NRB200_")}}), flush=True)
+
+
+def sweep(args):
+    def child(mode, env, *extra):
+        out = subprocess.run([sys.executable, __file__, mode, *extra], env=dict(os.environ, **env), capture_output=True, text=True)
+        print(out.stdout.strip() or json.dumps({"failed": mode, "env": env, "stderr": out.stderr[-400:]}), flush=True)
+    for rpt in ("1", "2", "4"):
+        child("kernels", {"NRB200_RPT": rpt})
+    for dest in ("pinned", "pageable", "fresh"):
+        for wire in ("0", "1"):
+            child("step", {"NRB200_WIRE16": wire}, "--dest", dest)
+    for chunks in ("4", "16"):
+        child("step", {"NRB200_CHUNKS": chunks}, "--dest", "fresh")
+
+
+def timeline(args):
+    os.environ["NRB200_TRACE_DEV"] = "1"
+    step(args)
+
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("mode", choices=["step", "kernels", "sweep", "timeline"])
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--dest", default="pinned", choices=["pinned", "pageable", "fresh"])
+    ap.add_argument("--reps", type=int, default=9)
+    a = ap.parse_args()
+    {"step": step, "kernels": kernels, "sweep": sweep, "timeline": timeline}[a.mode](a)

@@ -44,10 +44,11 @@ def groups():
 
 
 def _draws(plan, kind, R, philox, seed):
+    """(Draws for the engine, the oracle's keyword arguments for the same draws)"""
     if philox:
-        return Draws(n_iter=R, rng_mode=_lib.RNG_PHILOX, seed=seed, iter0=11)
+        return Draws(n_iter=R, rng_mode=_lib.RNG_PHILOX, seed=seed, iter0=11), {"seed": seed, "iter0": 11}
     d = H.draw_R(plan, seed, R)
-    return Draws(n_iter=R, rng_mode=_lib.RNG_HOST, bait_seqid=d[0], bait_start=d[1], dst_tile=d[2] if kind >= 4 else None)
+    return Draws(n_iter=R, rng_mode=_lib.RNG_HOST, bait_seqid=d[0], bait_start=d[1], dst_tile=d[2] if kind >= 4 else None), {"draws": d}
 
 
 @pytest.mark.parametrize("kind", [0, 1, 2, 3, 4, 5])
@@ -59,11 +60,8 @@ def test_group_counts_equal_single_gpu_and_oracle(groups, kind, philox, n_excl):
     plan, y, q, x = H.oracle_objects(case, kind)
     R = 13  # not a multiple of any group size: ragged shards
     try:
-        draws = _draws(plan, kind, R, philox, seed=5)
-        if philox:
-            ref = O.boot_counts(plan, y, q, R, exclude=x, seed=5, iter0=11)
-        else:
-            ref = O.boot_counts(plan, y, q, R, exclude=x, draws=(draws.bait_seqid, draws.bait_start, draws.dst_tile))
+        draws, how = _draws(plan, kind, R, philox, seed=5)
+        ref = O.boot_counts(plan, y, q, R, exclude=x, **how)
     except ValueError as e:
         assert "drew no segments" in str(e)
         pytest.skip("proportionLength = FALSE: a state drew no segments (fails in the reference too)")

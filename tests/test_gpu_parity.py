@@ -740,3 +740,62 @@ def test_boot_moments_front_end():
     bw = bootMoments(y, x, 5000, R=R, seed=9, weights="score", observed=target)
     assert np.allclose(bw.mean, fs.mean(0), rtol=1e-9) and np.allclose(bw.sd, fs.std(0, ddof=1), rtol=1e-6)
     assert np.allclose(bw.p_ge, ((fs >= target).sum(0) + 1) / (R + 1))
+
+
+# ---- wire format of a host-bound count matrix ----------------------------------------------------------------
+# Plain numpy result arrays are pageable, so every run_counts() above already travelled as uint16 and was widened
+# on the host (run.cuh).  Here: the int32 path with the format switched off, pinned destinations, and a count that
+# does not fit uint16 (the chunk is redone in int32).
+
+@pytest.mark.parametrize("wire", ["0", "1", "2"])
+@pytest.mark.parametrize("pinned", [False, True])
+def test_wire_format_variants(wire, pinned, monkeypatch):
+    import torch
+    from nullranges_b200 import Engine
+    monkeypatch.setenv("NRB200_WIRE16", wire)
+    monkeypatch.setenv("NRB200_CHUNKS", "3")
+    eng = Engine(0)
+    try:
+        case = H.random_case(seed=71, n=3000, n_seq=4, n_query=257, n_excl=15, n_seg=8)
+        plan, y, q, x = H.oracle_objects(case, 2)
+        H.load_engine(eng, case, 2)
+        R = 200  # several chunks (the pipeline makes at least 64 iterations per chunk)
+        out = None
+        if pinned:
+            keep = torch.empty((R, 257), dtype=torch.int32, pin_memory=True)
+            out = {"feature_counts": keep.numpy()}
+        got = eng.run_counts(Draws(n_iter=R, rng_mode=_lib.RNG_PHILOX, seed=12, iter0=40), out=out)
+        ref = O.boot_counts(plan, y, q, R, exclude=x, seed=12, iter0=40)
+        for k in ("iter_nranges", "iter_totals", "feature_counts"):
+            assert np.array_equal(got[k], ref[k]), k
+        expect16 = wire == "1" or (wire == "2" and not pinned)
+        assert got["stats"]["d2h_bytes"] == 2 * R * 8 + R * 257 * (2 if expect16 else 4)
+    finally:
+        eng.close()
+
+
+def test_wire_format_overflow_falls_back_to_int32():
+    """70,000 ranges inside one feature: the count exceeds 65535, the chunk's overflow flag goes up and the chunk is
+    computed again with int32 output; the other chunks stay uint16."""
+    from nullranges_b200 import Engine
+    n = 70_000
+    seqlen = np.array([5000, 4000], np.int64)
+    sid = np.concatenate([np.zeros(n, np.int32), np.ones(500, np.int32)])
+    rng = np.random.default_rng(2)
+    st = np.concatenate([np.full(n, 100), np.sort(rng.integers(1, 3500, 500))]).astype(np.int32)
+    en = (st + np.concatenate([np.full(n, 100), rng.integers(1, 300, 500)])).astype(np.int32)
+    o = np.lexsort((en, st, sid))
+    case = {"seqlen": seqlen, "y": (sid[o], st[o], en[o], None), "excl": None, "seg": None, "L_b": 1000,
+            "query": (np.array([0, 0, 1], np.int32), np.array([1, 900, 10], np.int32), np.array([1000, 1500, 3000], np.int32), None)}
+    plan, y, q, x = H.oracle_objects(case, 1)
+    eng = Engine(0)
+    try:
+        H.load_engine(eng, case, 1)
+        R = 150
+        got = eng.run_counts(Draws(n_iter=R, rng_mode=_lib.RNG_PHILOX, seed=3))
+        ref = O.boot_counts(plan, y, q, R, seed=3)
+        assert ref["feature_counts"].max() > 65535
+        for k in ("iter_nranges", "iter_totals", "feature_counts"):
+            assert np.array_equal(got[k], ref[k]), k
+    finally:
+        eng.close()
