@@ -261,6 +261,13 @@ int nrb200_fetch_rows(nrb200_handle *h, int64_t row0, int64_t n, int32_t *seqid,
  * ([n x n_blocks], the dst_tile a host-mode caller would have passed in) -- what `blockStart` needs.  */
 int nrb200_fetch_dst_tiles(nrb200_handle *h, int64_t r0, int64_t n, int32_t *dst_tile);
 
+/* ---- diagnostics ----------------------------------------------------------------------- */
+/* Measures, on the handle's GPU, the rate at which the L2 serves scattered 8-byte loads that each touch their own
+ * 32-byte sector of an L2-resident buffer of `buffer_bytes` (a power of two is used; 0 = 32 MiB): the ceiling of the
+ * rank-path count kernel, whose evaluations are two such loads each (kernels).  *gbytes_per_s = sectors
+ * per second x 32 bytes / 1e9.  bench.py reports the count kernel against this number. */
+int nrb200_measure_l2_sector_rate(nrb200_handle *h, int64_t buffer_bytes, double *gbytes_per_s);
+
 /* ---- base-R RNG for hosts that are not R ------------------------------------------- */
 /* In R the wrapper draws blocks with R's own sample()/runif().  A non-R host (the Python
  * mirror) needs the same stream under set.seed(): Mersenne-Twister / Inversion / Rejection,

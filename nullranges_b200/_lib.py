@@ -75,6 +75,7 @@ SYMBOLS = [
     ("nrb200_run_materialize", C.c_int, [vp, C.POINTER(Draws), i64p, C.POINTER(Stats)]),
     ("nrb200_fetch_rows", C.c_int, [vp, C.c_int64, C.c_int64, i32p, i32p, i32p, i32p, i32p]),
     ("nrb200_fetch_dst_tiles", C.c_int, [vp, C.c_int64, C.c_int64, i32p]),
+    ("nrb200_measure_l2_sector_rate", C.c_int, [vp, C.c_int64, dp]),
     ("nrb200_rrng_create", vp, [C.c_uint32]),
     ("nrb200_rrng_destroy", None, [vp]),
     ("nrb200_rrng_unif_rand", C.c_double, [vp]),

@@ -23,6 +23,8 @@ int nrb200_create(const nrb200_config *cfg, nrb200_handle **out) {
     h->device = dev;
     h->flags = cfg ? cfg->flags : 0;
     if (const char *e = getenv("NRB200_RPT")) h->tune_rpt = atoi(e) == 2 ? 2 : (atoi(e) == 4 ? 4 : 1);
+    if (const char *e = getenv("NRB200_IPT")) h->tune_ipt = std::min(std::max(atoi(e), 1), kLoopMaxIpt);
+    if (const char *e = getenv("NRB200_LOOP_MINB")) h->tune_loop_minb = atoi(e);
     if (const char *e = getenv("NRB200_END_RANK")) h->tune_end_rank = atoi(e) != 0;
     if (const char *e = getenv("NRB200_ROWS_IPC")) h->tune_rows_ipc = std::min(std::max(atoi(e), 1), 64);
     if (const char *e = getenv("NRB200_TABLE_MULT")) h->tune_table_mult = atof(e);
@@ -375,6 +377,63 @@ int nrb200_run_moments(nrb200_handle *h, const nrb200_draws *draws, int64_t batc
     int rc;
     if ((!h->moments_ready || h->moments_G != G) && (rc = nrb200_moments_reset(h))) return rc;
     if (observed && (rc = upload(h, h->m_observed, observed, (size_t)G))) return rc;
+    if ((rc = prepare(h))) return rc;
+    if (rank_path_ok(h)) {
+        // Fused: the count kernel keeps sum / sum of squares / #{>= observed} of every feature in registers over a run
+        // of iterations and never writes the [R x G] matrix; batches (bounded draw-table scratch) follow each other on
+        // the stream without a host synchronisation; one wait at the end.
+        const int64_t R = draws->n_iter, Bk = h->plan.n_blocks();
+        if (R < 0) return fail(h, NRB200_ERR_INVALID, "draws: n_iter must be >= 0");
+        NRB_CUDA(h, cudaEventRecord(h->ev[0], h->stream));
+        if ((rc = stage_draws(h, draws))) return rc;
+        const int64_t batch = std::max<int64_t>(1, std::min<int64_t>(batch_iter > 0 ? batch_iter : h->tune_max_batch, h->tune_max_batch));
+        NRB_CUDA(h, h->d_iter_nranges.reserve(std::max<int64_t>(R, 1) * 8));
+        NRB_CUDA(h, h->d_iter_totals.reserve(std::max<int64_t>(R, 1) * 8));
+        NRB_CUDA(h, cudaMemsetAsync(h->d_iter_nranges.p, 0, R * 8, h->stream));
+        NRB_CUDA(h, cudaMemsetAsync(h->d_iter_totals.p, 0, R * 8, h->stream));
+        if ((rc = hits_reset(h))) return rc;
+        NRB_CUDA(h, h->draw_tab.reserve((size_t)std::min(batch, std::max<int64_t>(R, 1)) * Bk * sizeof(int2)));
+        BootParams P = make_params(h, draws);
+        P.iter_nranges = h->d_iter_nranges.as<unsigned long long>();
+        P.iter_totals = h->d_iter_totals.as<unsigned long long>();
+        P.n_hits = stats ? h->d_n_hits.as<unsigned long long>() : nullptr;
+        P.draw_tab = h->draw_tab.as<int2>();
+        const FeatView F{h->f_src.as<int32_t>(), h->pair_off.as<int32_t>(), h->pair_rec.as<int4>()};
+        const MomentsOut M{observed ? h->m_observed.as<int32_t>() : nullptr, h->m_sum.as<long long>(), h->m_sumsq.as<long long>(),
+                           h->m_nge.as<long long>()};
+        NRB_CUDA(h, cudaEventRecord(h->ev[1], h->stream));
+        int launches = 0;
+        for (int64_t r0 = 0; r0 < R; r0 += batch) {
+            const BootParams Q = slice_params(P, r0, std::min(batch, R - r0));
+            launches += launch_rank(h, Q, false);  // draws + rows per iteration
+            const unsigned gx = (unsigned)((G + kCountThreads - 1) / kCountThreads);
+            const int ipt = (int)std::max<int64_t>(1, std::min<int64_t>(kLoopMaxIpt, (int64_t)gx * Q.n_iter / ((int64_t)h->sm_count * 16 * 3)));
+            boot_rank_loop_kernel<true, 12><<<dim3(gx, (unsigned)((Q.n_iter + ipt - 1) / ipt)), kCountThreads, 0, h->stream>>>(Q, F, ipt, M);
+            ++launches;
+            NRB_CUDA(h, cudaGetLastError());
+        }
+        NRB_CUDA(h, cudaEventRecord(h->ev[2], h->stream));
+        if ((rc = fetch_u64_as_i64(h, h->d_iter_nranges, R, iter_nranges))) return rc;
+        if ((rc = fetch_u64_as_i64(h, h->d_iter_totals, R, iter_totals))) return rc;
+        unsigned long long hit_words[kHitSlots + 1] = {};
+        if (stats && (rc = hits_fetch(h, hit_words))) return rc;
+        if (int rc_sync = sync_stream(h)) return rc_sync;
+        if (stats) {
+            float k_ms = 0, t_ms = 0;
+            cudaEventElapsedTime(&k_ms, h->ev[1], h->ev[2]);
+            cudaEventElapsedTime(&t_ms, h->ev[0], h->ev[2]);
+            std::memset(stats, 0, sizeof *stats);
+            stats->kernel_ms = k_ms;
+            stats->total_ms = t_ms;
+            stats->n_launches = launches;
+            stats->n_hits = (int64_t)hits_total(hit_words);
+            stats->n_windows = h->n_pairs;
+            stats->d2h_bytes = (iter_nranges ? R * 8 : 0) + (iter_totals ? R * 8 : 0);
+            stats->h2d_bytes = draws->rng_mode == NRB200_RNG_HOST ? R * Bk * (draws->dst_tile ? 12 : 8) : 0;
+        }
+        return NRB200_OK;
+    }
+    // streaming path: the matrix of a batch of iterations, then its reduction
     if (batch_iter <= 0) batch_iter = std::max<int64_t>(1, std::min<int64_t>(draws->n_iter, ((int64_t)1 << 28) / std::max<int64_t>(G, 1)));
     const int64_t B = h->plan.n_blocks();
     nrb200_stats acc{};
@@ -708,6 +767,44 @@ int nrb200_fetch_dst_tiles(nrb200_handle *h, int64_t r0, int64_t n, int32_t *dst
     if (n == 0 || !dst_tile) return NRB200_OK;
     NRB_CUDA(h, cudaMemcpyAsync(dst_tile, h->d_dst_tile.as<int32_t>() + r0 * B, (size_t)n * B * 4, cudaMemcpyDeviceToHost, h->stream));
     return sync_stream(h);
+}
+
+int nrb200_measure_l2_sector_rate(nrb200_handle *h, int64_t buffer_bytes, double *gbytes_per_s) {
+    if (!h || !gbytes_per_s) return NRB200_ERR_INVALID;
+    if (is_group(h)) h = h->members[0];
+    NRB_CUDA(h, cudaSetDevice(h->device));
+    size_t bytes = (size_t)32 << 20;
+    if (buffer_bytes > 0) {
+        bytes = 1 << 20;
+        while (bytes * 2 <= (size_t)buffer_bytes && bytes < ((size_t)1 << 30)) bytes *= 2;
+    }
+    DevMem buf, sink;
+    NRB_CUDA(h, buf.reserve(bytes));
+    NRB_CUDA(h, sink.reserve(8));
+    NRB_CUDA(h, cudaMemsetAsync(buf.p, 1, bytes, h->stream));
+    NRB_CUDA(h, cudaMemsetAsync(sink.p, 0, 8, h->stream));
+    const uint32_t n_mask = (uint32_t)(bytes / 32 - 1);
+    const int rounds = 64;
+    const unsigned grid = (unsigned)h->sm_count * 8 * 4;  // 8 resident CTAs of 256 threads per SM, four waves
+    cudaEvent_t a, b;
+    NRB_CUDA(h, cudaEventCreate(&a));
+    NRB_CUDA(h, cudaEventCreate(&b));
+    float best = 1e30f;
+    for (int rep = 0; rep < 4; ++rep) {  // the first pass also pulls the buffer into the L2
+        cudaEventRecord(a, h->stream);
+        l2_sector_rate_kernel<<<grid, 256, 0, h->stream>>>(buf.as<uint2>(), n_mask, rounds, sink.as<unsigned long long>());
+        cudaEventRecord(b, h->stream);
+        cudaEventSynchronize(b);
+        float ms = 0;
+        cudaEventElapsedTime(&ms, a, b);
+        if (rep > 0) best = std::min(best, ms);
+    }
+    cudaEventDestroy(a);
+    cudaEventDestroy(b);
+    NRB_CUDA(h, cudaGetLastError());
+    const double sectors = (double)grid * 256.0 * rounds * kCalibLoads;
+    *gbytes_per_s = sectors * 32.0 / (best * 1e-3) / 1e9;
+    return NRB200_OK;
 }
 
 void nrb200_expand_runs(const int64_t *offsets, int64_t n_runs, int32_t first, int32_t *out) {

@@ -242,6 +242,8 @@ struct nrb200_handle {
     // tuning knobs (environment, read at create)
     bool tune_end_rank = true;         // NRB200_END_RANK=0: always radix-sort the ends (index build)
     int tune_rpt = 1;                  // NRB200_RPT: iterations per thread of the count kernel (1, 2 or 4)
+    int tune_ipt = 1;                  // NRB200_IPT: iterations a thread of the count kernel stays on its feature (<= 64; 1 = one thread per (feature, iteration))
+    int tune_loop_minb = 12;           // NRB200_LOOP_MINB: its min CTAs per SM (16 = 32 registers, 12 = 40)
     int tune_rows_ipc = 4;             // NRB200_ROWS_IPC: iterations a CTA of the rows kernel loops over
     double tune_table_mult = 4.0;
     int tune_wire16 = 2;               // NRB200_WIRE16: uint16 wire format of a host-bound matrix (0 never, 1 always, 2 pageable destinations)

@@ -395,6 +395,29 @@ __global__ void end_rank_scatter_kernel(const int32_t *__restrict__ seqid, const
     end_sorted[rank] = e;
 }
 
+// ---- calibration: what the L2 delivers to scattered 8-byte loads ------------------------------------------------
+// The rank-path count kernel is bound by 32-byte sectors pulled through the L2 at random addresses (two table entries
+// per evaluation).  This kernel measures that ceiling on the device at hand: every thread issues kCalibLoads
+// independent 8-byte loads per round at hashed, sector-distinct positions of an L2-resident buffer.
+constexpr int kCalibLoads = 8;
+__global__ void __launch_bounds__(256) l2_sector_rate_kernel(const uint2 *__restrict__ buf, uint32_t n_mask, int rounds,
+                                                             unsigned long long *__restrict__ sink) {
+    uint32_t x = (blockIdx.x * blockDim.x + threadIdx.x) * 2654435761u + 12345u;
+    uint32_t acc = 0;
+    for (int r = 0; r < rounds; ++r) {
+        uint2 v[kCalibLoads];
+#pragma unroll
+        for (int j = 0; j < kCalibLoads; ++j) {
+            x = x * 1664525u + 1013904223u;
+            v[j] = __ldg(buf + (((x >> 4) & n_mask) << 2));  // one 8-byte word per 32-byte sector
+        }
+#pragma unroll
+        for (int j = 0; j < kCalibLoads; ++j) acc += v[j].x ^ v[j].y;
+        x ^= acc & 1u;  // the next round's addresses depend on this round's data: rounds do not overlap freely
+    }
+    if (acc == 0x9e3779b9u) atomicAdd(sink, 1ull);
+}
+
 // Per-feature moments over a batch of iterations: thread per feature, coalesced over g.
 __global__ void accumulate_moments_kernel(const int32_t *__restrict__ counts, int64_t n_iter, int64_t n_query,
                                           const int32_t *__restrict__ observed, long long *__restrict__ sum,

@@ -185,6 +185,89 @@ __global__ void __launch_bounds__(kCountThreads, MINB) boot_rank_count_kernel(co
     }
 }
 
+// The same count with the thread staying on its feature for `ipt` consecutive iterations: the window record, the
+// tile's bait width / sequence length and the list bounds are read once per thread instead of once per iteration,
+// and the next iteration's draw is requested while the current one is evaluated, so that per iteration the chain
+// is draw (prefetched) -> sequence info (an L1 hit) -> the two table entries.  Per-iteration totals are summed in
+// shared memory and leave the CTA once.  With MOMENTS the counts are not stored at all: every thread keeps
+// sum, sum of squares and #{count >= observed} of its feature in registers and adds them to the per-feature
+// vectors when its iterations are done -- the [R x G] matrix never exists (BASELINE config 4: R = 10^4, G = 2 * 10^5).
+struct MomentsOut {
+    const int32_t *observed;       // [n_query] caller's order, or nullptr
+    long long *sum, *sumsq, *n_ge; // [n_query] caller's order
+};
+constexpr int kLoopMaxIpt = 64;
+template <bool MOMENTS, int MINB>
+__global__ void __launch_bounds__(kCountThreads, MINB) boot_rank_loop_kernel(const BootParams P, const FeatView F, int ipt, const MomentsOut M) {
+    __shared__ int s_tot[kLoopMaxIpt];
+    const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t r0 = (int64_t)blockIdx.y * ipt;
+    const int n_it = (int)min((int64_t)ipt, P.n_iter - r0);
+    for (int k = threadIdx.x; k < n_it; k += kCountThreads) s_tot[k] = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    int32_t src = 0, p0 = 0, p1 = 0;
+    if (g < P.n_query) {
+        src = __ldg(F.src + g);
+        p0 = __ldg(F.pair_off + g);
+        p1 = __ldg(F.pair_off + g + 1);
+    }
+    const bool live = g < P.n_query, any = p1 > p0;
+    int4 rec0 = make_int4(0, 0, 0, 0);
+    int2 ti0 = make_int2(0, 0), d_next = make_int2(0, 0);
+    const int2 *__restrict__ tab = P.draw_tab + r0 * P.n_blocks;
+    if (any) {
+        rec0 = __ldg(F.rec + p0);
+        ti0 = __ldg(P.tile_info + rec_tile(rec0.x));
+        d_next = __ldg(tab + rec_tile(rec0.x));
+    }
+    long long m_sum = 0, m_sq = 0;
+    int m_ge = 0;
+    const int32_t obs = (MOMENTS && live && M.observed) ? __ldg(M.observed + src) : 0;
+#pragma unroll 1
+    for (int k = 0; k < n_it; ++k) {
+        int cnt = 0;
+        if (any) {
+            const int2 d = d_next;
+            if (k + 1 < n_it) d_next = __ldg(tab + (int64_t)(k + 1) * P.n_blocks + rec_tile(rec0.x));
+            const int c0 = P.permute ? count_pair<true>(P.y, d, rec_cls(rec0.x), ti0.x, rec0.w, ti0.y, rec0.y, rec0.z)
+                                     : count_pair<false>(P.y, d, rec_cls(rec0.x), ti0.x, rec0.w, ti0.y, rec0.y, rec0.z);
+            cnt = rec_sign(rec0.x) * c0;
+            for (int32_t p = p0 + 1; p < p1; ++p) {  // further windows of the feature (other tiles, exclusion windows): L1 hits after the first iteration
+                const int4 rec = __ldg(F.rec + p);
+                const int tile = rec_tile(rec.x);
+                const int2 ti = __ldg(P.tile_info + tile);
+                const int2 dd = __ldg(tab + (int64_t)k * P.n_blocks + tile);
+                const int c = P.permute ? count_pair<true>(P.y, dd, rec_cls(rec.x), ti.x, rec.w, ti.y, rec.y, rec.z)
+                                        : count_pair<false>(P.y, dd, rec_cls(rec.x), ti.x, rec.w, ti.y, rec.y, rec.z);
+                cnt += rec_sign(rec.x) * c;
+            }
+        }
+        if (live) {
+            if (MOMENTS) {
+                m_sum += cnt;
+                m_sq += (long long)cnt * cnt;
+                m_ge += (M.observed && cnt >= obs) ? 1 : 0;
+            } else if (P.counts16) {
+                __stcs(P.counts16 + (r0 + k) * P.n_query + src, (unsigned short)min(cnt, 65535));
+                if (cnt > 65535) atomicOr(P.overflow16, 1);
+            } else if (P.counts) {
+                __stcs(P.counts + (r0 + k) * P.n_query + src, cnt);
+            }
+        }
+        const int s = __reduce_add_sync(kFull, cnt);
+        if (lane == 0 && s) atomicAdd(&s_tot[k], s);
+    }
+    __syncthreads();
+    for (int k = threadIdx.x; k < n_it; k += kCountThreads)
+        if (s_tot[k]) atomicAdd(P.iter_totals + r0 + k, (unsigned long long)(unsigned)s_tot[k]);
+    if (MOMENTS && live) {
+        if (m_sum) atomicAdd(reinterpret_cast<unsigned long long *>(M.sum + src), (unsigned long long)m_sum);
+        if (m_sq) atomicAdd(reinterpret_cast<unsigned long long *>(M.sumsq + src), (unsigned long long)m_sq);
+        if (m_ge) atomicAdd(reinterpret_cast<unsigned long long *>(M.n_ge + src), (unsigned long long)m_ge);
+    }
+}
+
 // ---- weighted sums on the rank path -----------------------------------------------------------
 // sum of a numeric column of y over the ranges that land on a feature (vignettes/bootRanges.Rmd:532-540:
 // summarize(sum(signal)) per (feature, iter)).  Same windows and ranks as the counts; instead of

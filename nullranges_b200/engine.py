@@ -257,6 +257,12 @@ class Engine:
         return out
 
 
+    def measure_l2_sector_rate(self, buffer_bytes: int = 0) -> float:
+        """GB/s (sectors x 32 B) the L2 serves to scattered 8-byte loads on this GPU: the count kernel's ceiling."""
+        v = C.c_double()
+        self._check(self._lib.nrb200_measure_l2_sector_rate(self._h, int(buffer_bytes), C.byref(v)))
+        return v.value
+
     def fetch_dst_tiles(self, r0: int, n: int) -> np.ndarray:
         """Permute variants: the tile every block of iterations [r0, r0 + n) of the last run moved to, [n, n_blocks]."""
         out = np.empty((int(n), self.n_blocks), np.int32)

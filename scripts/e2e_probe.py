@@ -98,14 +98,23 @@ def sweep(args):
 
 def timeline(args):
     os.environ["NRB200_TRACE_DEV"] = "1"
+    os.environ["NRB200_TRACE"] = "1"
+    args.reps = 1
     step(args)
+
+
+def calib(args):
+    from nullranges_b200 import Engine
+    e = Engine(0)
+    print(json.dumps({"mode": "calib", "thp": open("/sys/kernel/mm/transparent_hugepage/enabled").read().strip(),
+                      "l2_sector_rate_GBps": {f"{mb}MiB": e.measure_l2_sector_rate(mb << 20) for mb in (8, 32, 64, 256, 1024)}}), flush=True)
 
 
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
-    ap.add_argument("mode", choices=["step", "kernels", "sweep", "timeline"])
+    ap.add_argument("mode", choices=["step", "kernels", "sweep", "timeline", "calib"])
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--dest", default="pinned", choices=["pinned", "pageable", "fresh"])
     ap.add_argument("--reps", type=int, default=9)
     a = ap.parse_args()
-    {"step": step, "kernels": kernels, "sweep": sweep, "timeline": timeline}[a.mode](a)
+    {"step": step, "kernels": kernels, "sweep": sweep, "timeline": timeline, "calib": calib}[a.mode](a)
