@@ -4,23 +4,27 @@
 Workload (BASELINE.json configs[1], SURVEY 8d cfg 2): unsegmented across-chromosome block
 bootstrap of 1M synthetic ATAC-like peaks on hg38 chr1-22, blockLength = 5e5, against 20k
 synthetic genes; per-iteration totals AND the [R x 20k] per-gene count matrix.
-One "step" = R = 1000 bootstrap iterations (one nrb200_run_counts* call).
+One "step" = R = 1000 bootstrap iterations per GPU.
 
   value   iterations/s, device-resident (ranges, query and plan already in HBM; block draws are
-          Philox on the device, so a step has no input copy), CUDA events, max over ranks
-  e2e     iterations/s through the public API bootCounts(y, x, ...) from HOST arrays: every
-          step uploads y and x, builds the indexes, runs, and copies totals + the count matrix
-          back to pinned host memory
-  roofline  algorithmic bytes (8*H + 16*B + 4*G + 16 per iteration) / kernel time
+          Philox on the device, so a step has no input copy), CUDA events, max over ranks; one process per GPU
+  e2e     iterations/s through the public API bootCounts(y, x, ..., gpus=N) from PAGEABLE host arrays into a freshly
+          allocated pageable int32 matrix (what an R caller has: R's vectors are pageable and every call allocates
+          its result): every step uploads y and x, builds the indexes, runs R * N iterations sharded over the N GPUs
+          and delivers ONE [R * N x G] host matrix.  e2e_pinned: the same from / into pinned buffers.  Under
+          torchrun rank 0 drives the N devices through one device-group handle (the product's multi-GPU path); the
+          other ranks wait on the host.
+  roofline  the dominant kernel (boot_rank_count_kernel) against the minimal DRAM bytes of the rank path;
+          roofline_l2: the same kernel against what bounds it -- 32-byte sectors through the L2 -- with the ceiling
+          measured on the device in this run; roofline_model_8d: SURVEY 8d's byte model (which the rank path does
+          not follow: it never reads the sampled ranges); roofline_stream: the streaming kernel that does
+  checks  N-GPU result == 1-GPU result (per-iteration totals of the same global iterations; count matrix of the
+          device group against one GPU)
   cpu_baseline  the CPU oracle (plain-C port of the reference algorithm) on this box's cores
 
 --impl reference: the reference's CPU implementation of the same path.  The reference is pure
 R and R is not installed, so this arm times the oracle port (oracle/nr_oracle.c) with all host
 threads on a bounded sample (iterations per step reduced; same ranges, query and block length).
-
-Multi-GPU (torchrun): iterations shard across ranks with no data-path collective; the small
-per-iteration vectors are all-gathered over NCCL at the end of each step (weak scaling: every
-rank runs R iterations per step).
 """
 from __future__ import annotations
 
@@ -83,6 +87,13 @@ def cpu_sample(O, plan, yi, qi, n_iter, threads, iter0=0):
     return time.perf_counter() - t0
 
 
+def config_dict():
+    """The workload description, identical in both arms (the driver compares the two `config` objects)."""
+    return {"workload": WORKLOAD, "iters_per_step_per_gpu": R_STEP, "ranges": 1_000_000, "features": 20_000, "block_length": L_B,
+            "rng": "philox4x32-10, counter = (global iteration, block), seed 2024",
+            "l2": "flushed between timed steps (256 MiB fill, outside the step events); inside a step the index is re-read by design"}
+
+
 def run_reference(args):
     """The reference arm: oracle port of the R algorithm, all host threads, bounded sample."""
     rank = int(os.environ.get("RANK", "0"))
@@ -106,8 +117,8 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": "iter/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "iters_per_step": per_step,
-                   "note": "reference is pure R (not installable here: no R); this is the plain-C oracle port of its algorithm, faster than real R"},
+        "config": config_dict(),
+        "note": "the reference is pure R (not installable here: no R); this is the plain-C oracle port of its algorithm, faster than real R",
         "cpu_baseline": {"value": value, "unit": "iter/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "iter/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -181,12 +192,20 @@ def pinned(shape, dtype):
     return t, t.numpy()
 
 
+def checksum(a) -> int:
+    """Order-sensitive 61-bit checksum of an integer array (sum of value * (position + 1) mod 2^61 - 1)."""
+    v = np.asarray(a, dtype=np.int64).ravel()
+    m = (1 << 61) - 1
+    w = (np.arange(1, v.size + 1, dtype=np.int64) % 1_000_003)
+    return int((int((v % 1_000_003 * w).sum()) + int(v.sum())) % m)
+
+
 def run_gpu(args):
     import torch
     import torch.distributed as dist
 
     from nullranges_b200 import Draws, Engine, _lib, bootCounts
-    from nullranges_b200.sharding import resident_tensors
+    from nullranges_b200.sharding import resident_tensors, shard_iterations
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -199,8 +218,14 @@ def run_gpu(args):
     sys.stdout.flush()
     saved_stdout = os.dup(1)
     os.dup2(2, 1)
+    host_pg = None
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        host_pg = dist.new_group(backend="gloo")  # host-side waits: a rank parked here does not spin a kernel on its GPU
+
+    def host_barrier():
+        if world > 1:
+            dist.barrier(group=host_pg)
 
     y, x = make_inputs()
     G, R = len(x), R_STEP
@@ -276,8 +301,30 @@ def run_gpu(args):
         clk = clocks.stop()
         clk["window"] = "warm-up + timed region + accounting pass (the timed region alone lasts a few ms)"
 
+        # ---- result check 1: the world's GPUs together reproduce what one GPU computes.  Global iterations [0, R) are
+        # split over the ranks exactly as the product splits them (shard_iterations); the gathered per-iteration
+        # totals must equal rank 0's own run of all R iterations.
+        lo, n_mine = shard_iterations(R, world, rank)
+        eng.run_counts_resident(Draws(n_iter=n_mine, rng_mode=_lib.RNG_PHILOX, seed=2024, iter0=lo), want_counts=True, want_stats=False)
+        mine = resident_tensors(eng, n_mine, 0)["iter_totals"].clone()
+        n_max = max(shard_iterations(R, world, k)[1] for k in range(world))
+        pad = torch.zeros(n_max, dtype=torch.int64, device="cuda")
+        pad[:n_mine] = mine
+        if world > 1:
+            allv = torch.empty(world * n_max, dtype=torch.int64, device="cuda")
+            dist.all_gather_into_tensor(allv, pad)
+            allv = allv.cpu().numpy().reshape(world, n_max)
+            sharded = np.concatenate([allv[k, : shard_iterations(R, world, k)[1]] for k in range(world)])
+        else:
+            sharded = pad.cpu().numpy()[:n_mine]
+        eng.run_counts_resident(Draws(n_iter=R, rng_mode=_lib.RNG_PHILOX, seed=2024, iter0=0), want_counts=True, want_stats=False)
+        alone = resident_tensors(eng, R, 0)["iter_totals"].cpu().numpy()
+        checks = {"iter_totals_checksum_N_gpus": checksum(sharded), "iter_totals_checksum_1_gpu": checksum(alone),
+                  "n_gpu_equals_1_gpu": bool(np.array_equal(sharded, alone))}
+
     # ---- the streaming kernel on the same workload (the path that really reads the 8*H bytes)
     stream_ms, stream_hits, stream_steps = 0.0, 0, 3
+    l2_peak = None
     if rank == 0:
         eng_s = Engine(local, stream=stream.cuda_stream, force_stream=True)
         eng_s.set_ranges(y.seqlengths, y.seqid, y.start, y.end, None)
@@ -290,44 +337,71 @@ def run_gpu(args):
                     stream_ms += st["kernel_ms"]
                     stream_hits += st["n_hits"]
         eng_s.close()
+        l2_peak = eng.measure_l2_sector_rate(64 << 20)  # the count kernel's ceiling, measured on this GPU now
+    torch.cuda.synchronize()
+    host_barrier()
 
-    # ---- end-to-end through the public API: pinned host arrays in, pinned host arrays out
-    from nullranges_b200 import GRanges
+    # ---- end to end through the public API, all N GPUs driven by rank 0 through ONE device-group handle; the other
+    # ranks wait on the host (gloo), their GPUs idle.  Weak scaling: R iterations per GPU per step, one [R * N x G] result.
+    e2e = {}
+    if rank == 0:
+        gpus = list(range(world)) if world > 1 else None
+        Rt = R * world
+        e2e_steps = max(2, min(args.steps, 5))
+        y_pg, x_pg = make_inputs()  # plain numpy arrays: pageable, like R's vectors
 
-    def pinned_copy(a):
-        keep, view = pinned(a.shape, {np.dtype(np.int32): torch.int32, np.dtype(np.int8): torch.int8}[a.dtype])
-        view[...] = a
-        pinned_keep.append(keep)
-        return view
+        def timed(fn):
+            fn(0)
+            fn(1)
+            t0 = time.perf_counter()
+            for s_ in range(e2e_steps):
+                res = fn(2 + s_)
+            return (time.perf_counter() - t0) / e2e_steps, res
 
-    pinned_keep = []
-    for gr in (y, x):
-        gr.seqid, gr.start, gr.end = pinned_copy(gr.seqid), pinned_copy(gr.start), pinned_copy(gr.end)
-    keep_t, out_tot = pinned((R,), torch.int64)
-    keep_n, out_nr = pinned((R,), torch.int64)
-    keep_c, out_cnt = pinned((R, G), torch.int32)
-    e2e_steps = max(1, min(args.steps, 5))
+        # (a) pageable in, freshly allocated pageable out -- the R-realistic call
+        t_pg, res_pg = timed(lambda s_: bootCounts(y_pg, x_pg, L_B, R=Rt, rng="philox", seed=2024, iter0=s_ * Rt, gpus=gpus))
+        # (b) pinned in, pinned out
+        keep = []
 
-    def step_e2e(step):
-        return bootCounts(y, x, L_B, R=R, rng="philox", seed=2024, iter0=(step * world + rank) * R, device=local,
-                          out={"iter_totals": out_tot, "iter_nranges": out_nr, "feature_counts": out_cnt})
+        def pinned_copy(a):
+            t = torch.empty(a.shape, dtype={np.dtype(np.int32): torch.int32, np.dtype(np.int8): torch.int8}[a.dtype], pin_memory=True)
+            t.numpy()[...] = a
+            keep.append(t)
+            return t.numpy()
 
-    step_e2e(0)
-    barrier()
-    t0 = time.perf_counter()
-    for s in range(e2e_steps):
-        res = step_e2e(1 + s)
-    barrier()
-    e2e_s = time.perf_counter() - t0
-    h2d = int(y.seqid.nbytes + y.start.nbytes + y.end.nbytes + x.seqid.nbytes + x.start.nbytes + x.end.nbytes)
-    d2h = int(out_tot.nbytes + out_nr.nbytes + out_cnt.nbytes)
-    assert int(res.feature_counts.sum()) == int(res.iter_totals.sum())
+        y_pin, x_pin = make_inputs()
+        for gr in (y_pin, x_pin):
+            gr.seqid, gr.start, gr.end = pinned_copy(gr.seqid), pinned_copy(gr.start), pinned_copy(gr.end)
+        outs = {"iter_totals": torch.empty((Rt,), dtype=torch.int64, pin_memory=True), "iter_nranges": torch.empty((Rt,), dtype=torch.int64, pin_memory=True),
+                "feature_counts": torch.empty((Rt, G), dtype=torch.int32, pin_memory=True)}
+        out_np = {k: v.numpy() for k, v in outs.items()}
+        t_pin, res_pin = timed(lambda s_: bootCounts(y_pin, x_pin, L_B, R=Rt, rng="philox", seed=2024, iter0=s_ * Rt, gpus=gpus, out=out_np))
+        last = 2 + e2e_steps - 1
+        assert int(res_pg.feature_counts.sum()) == int(res_pg.iter_totals.sum())
+        # result check 2: the device group's matrix == one GPU's matrix, for the first R iterations of the last step
+        one = bootCounts(y_pin, x_pin, L_B, R=R, rng="philox", seed=2024, iter0=last * Rt, device=0)
+        checks["e2e_matrix_checksum_group"] = checksum(res_pg.feature_counts[:R])
+        checks["e2e_matrix_checksum_1_gpu"] = checksum(one.feature_counts)
+        checks["e2e_group_equals_1_gpu"] = bool(np.array_equal(res_pg.feature_counts[:R], one.feature_counts) and
+                                                np.array_equal(res_pin.feature_counts[:R], one.feature_counts) and
+                                                np.array_equal(res_pg.iter_totals[:R], one.iter_totals))
+        h2d = int(sum(a.nbytes for gr in (y_pg, x_pg) for a in (gr.seqid, gr.start, gr.end)))
+        api = ("nullranges_b200.bootCounts(y, x, blockLength, R = 1000 * N, gpus = N): upload + index build + run + D2H every step, "
+               "one [R x G] int32 host matrix; rank 0 drives the N GPUs through one device-group handle")
+        e2e = {"e2e": {"value": Rt / t_pg, "unit": "iter/s", "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": int(res_pg.stats["d2h_bytes"]),
+                       "steps": e2e_steps, "ms_per_step": 1e3 * t_pg, "api": api,
+                       "buffers": "pageable numpy inputs; the [R x G] int32 result is allocated inside every call (fresh pages), as an R caller's is; "
+                                  "the matrix crosses PCIe as uint16 and is widened by the host"},
+               "e2e_pinned": {"value": Rt / t_pin, "unit": "iter/s", "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": int(res_pin.stats["d2h_bytes"]),
+                              "steps": e2e_steps, "ms_per_step": 1e3 * t_pin, "buffers": "pinned inputs and pinned preallocated outputs (int32 on the wire)"}}
+        del res_pg, res_pin, one
+    host_barrier()
 
     # ---- max over ranks
-    t = torch.tensor([dev_ms, e2e_s, kernel_ms], dtype=torch.float64, device="cuda")
+    t = torch.tensor([dev_ms, kernel_ms], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    dev_ms, e2e_s, kernel_ms_max = (float(v) for v in t.tolist())
+    dev_ms, kernel_ms_max = (float(v) for v in t.tolist())
 
     if rank == 0:
         peaks = {}
@@ -337,15 +411,24 @@ def run_gpu(args):
             pass
         peak = float(peaks.get("hbm_gbs", 6650.0))
         peak_src = "MEASURED_PEAKS.json hbm_gbs (of measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (of fallback)"
-        alg_bytes = 8.0 * hits + (16.0 * B + 4.0 * G + 16.0) * R * args.steps  # this rank, whole timed region
         groups = max(launches // 2, 1)  # one launch group = rows kernel + count kernel over <= 2048 iterations
-        per_launch = alg_bytes / groups
-        achieved = alg_bytes / (kernel_ms * 1e-3) / 1e9
+        count_s = count_ms / groups * 1e-3
+        W = int(n_windows)
+        # the rank path per launch (R iterations): what MUST cross HBM -- the count matrix out, the draw table in (the rows
+        # kernel left it in the L2 / HBM), the index (tables + records) once
+        table_entries = int(np.sum(y.seqlengths)) >> 10  # one bucket per 2^10 positions at this size (index.cuh, build_rank_tables)
+        index_bytes = 2 * 8 * table_entries + 16 * W + 8 * G
+        min_dram = (4.0 * G + 8.0 * B) * R + index_bytes
+        # what must cross the L2 -> SM crossbar, in 32-byte sectors: two table entries and half a record sector per
+        # evaluation, 12 bytes per feature (list bounds, caller's position, count out), the tile's draw
+        sectors = R * (2.5 * W + 0.375 * G + 0.25 * B)
+        alg8d = 8.0 * hits + (16.0 * B + 4.0 * G + 16.0) * R * args.steps
         stream_alg = 8.0 * stream_hits + (16.0 * B + 4.0 * G + 16.0) * R * stream_steps
         stream_achieved = stream_alg / (stream_ms * 1e-3) / 1e9
-        traffic = None
+        traffic, traffic_src = None, None
         try:
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get("rank_launch_group_dram_bytes_per_launch")
+            tj = json.load(open(os.path.join(ROOT, "profiles", "r02_traffic.json")))
+            traffic, traffic_src = tj.get("boot_rank_count_kernel", {}).get("dram_bytes_per_launch"), tj.get("source")
         except Exception:
             pass
         # CPU baseline: bounded sample on this box's cores
@@ -361,29 +444,34 @@ def run_gpu(args):
             "metric": METRIC, "value": R * world * args.steps / (dev_ms * 1e-3), "unit": "iter/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "iters_per_step_per_gpu": R, "n_blocks": int(B), "rng": "philox4x32-10 on device",
-                       "l2": "flushed between timed steps (256 MiB fill, outside the step events); inside a step the 12 MB range table is re-read by design",
-                       "sharding": "iterations, rank-major; [2 x R] int64 per-iteration vectors all-gathered over NCCL each step" if world > 1 else "single GPU",
-                       "host_threads_per_rank": int(os.environ.get("OMP_NUM_THREADS", "0") or 0) or host_cores(),
-                       "wall_s_timed_region": t_wall},
-            "e2e": {"value": R * world * e2e_steps / e2e_s, "unit": "iter/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "steps": e2e_steps, "api": "nullranges_b200.bootCounts(y, x, blockLength, R) from host arrays (upload + index build + run + D2H every step)"},
+            "config": config_dict(),
+            "run": {"n_blocks": int(B), "windows_per_iteration": W,
+                    "sharding": "iterations, rank-major; [2 x R] int64 per-iteration vectors all-gathered over NCCL each step" if world > 1 else "single GPU",
+                    "host_threads": host_cores(), "wall_s_timed_region": t_wall},
+            **e2e,
             "gpu_launches": int(launches),
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                         "kernel": "boot_rank_count_kernel (dominant) + boot_block_rows_kernel: one launch of each per step",
-                         "kernel_ms_per_launch": {"boot_rank_count_kernel": count_ms / groups, "boot_block_rows_kernel": rows_ms / groups,
-                                                  "both": kernel_ms / groups},
-                         "algorithmic_bytes_per_launch": per_launch, "peak_source": peak_src,
-                         "kernel_share_of_step": kernel_ms / dev_ms if world == 1 else kernel_ms_max / dev_ms,
-                         "timing": "kernel times: CUDA events inside libnrb200 around each kernel, accounting pass over the same steps right after the timed region",
-                         "note": "bytes = SURVEY 8d model (8*H + 16*B + 4*G + 16 per iteration, H = sampled ranges). The rank path counts by "
-                                 "rank differences and never reads the H ranges, so it legitimately exceeds 1.0 on this scale (SURVEY 8d); "
-                                 "its own limit is L1TEX wavefronts of scattered table probes, see DESIGN.md 4a. roofline_stream is the kernel that does read them."},
-            "roofline_own": {"bound": "l1tex wavefronts (scattered 128-byte-line accesses), not HBM",
-                             "evaluations_per_launch": n_windows * R, "windows_per_iteration": n_windows,
-                             "sm_cycles_per_evaluation": (count_ms / groups) * 1e-3 * 148 * (clk.get("sm_mhz") or 1965) * 1e6 / max(n_windows * R, 1),
-                             "floor": "2 rank-table probes per evaluation = 2 line accesses at ~1 line/cycle/SM; measured ~3.4 accesses per evaluation (ncu l1tex sectors), see DESIGN.md 4a"},
-            "roofline_stream": {"bound": "hbm", "kernel": "boot_count_kernel<0,1,0> (NRB200_FLAG_FORCE_STREAM, same workload)",
+            "checks": checks,
+            "roofline": {"bound": "hbm", "kernel": "boot_rank_loop_kernel (the rank path's count kernel, dominant)",
+                         "achieved": min_dram / count_s / 1e9, "peak": peak, "unit": "GB/s", "frac": min_dram / count_s / 1e9 / peak,
+                         "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": min_dram,
+                         "bytes_model": "per launch of R iterations: (4*G + 8*B)*R (count matrix out, draw table in) + the index once (rank tables, window records)",
+                         "kernel_ms_per_launch": {"count": count_ms / groups, "rows": rows_ms / groups, "both": kernel_ms / groups},
+                         "kernel_share_of_step": (count_ms / args.steps) / (dev_ms / args.steps),
+                         "timing": "CUDA events inside libnrb200 around each kernel, accounting pass over the same steps right after the timed region",
+                         "note": "this kernel is not HBM-bound: it counts by rank differences in L2-resident tables (two scattered 8-byte probes per "
+                                 "(feature, tile, iteration) evaluation); what bounds it is in roofline_l2"},
+            "roofline_l2": {"bound": "32-byte sectors through the L2 (scattered 8-byte loads)", "achieved": sectors * 32.0 / count_s / 1e9,
+                            "peak": l2_peak, "unit": "GB/s", "frac": sectors * 32.0 / count_s / 1e9 / l2_peak if l2_peak else None,
+                            "peak_source": "nrb200_measure_l2_sector_rate (64 MiB buffer) on this GPU, this run",
+                            "sectors_model": "R * (2.5 * windows + 0.375 * G + 0.25 * B): two table entries + a 16-byte record per evaluation, 12 bytes per feature, 8 bytes per tile",
+                            "sectors_per_launch": sectors, "evaluations_per_launch": W * R,
+                            "sm_cycles_per_evaluation": count_s * 148 * (clk.get("sm_mhz") or 1965) * 1e6 / max(W * R, 1)},
+            "roofline_model_8d": {"bound": "hbm", "achieved": alg8d / (kernel_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                                  "frac": alg8d / (kernel_ms * 1e-3) / 1e9 / peak,
+                                  "note": "SURVEY 8d bytes (8*H + 16*B + 4*G + 16 per iteration) over rows + count kernel time; above 1 because the "
+                                          "rank path never reads the H sampled ranges -- kept for comparison, not a bound"},
+            "roofline_stream": {"bound": "hbm", "kernel": "boot_count_kernel (NRB200_FLAG_FORCE_STREAM, same workload): streams the sampled ranges, the 8d model's kernel",
                                 "achieved": stream_achieved, "peak": peak, "unit": "GB/s", "frac": stream_achieved / peak,
                                 "kernel_ms_per_launch": stream_ms / stream_steps, "iters_per_s": R * stream_steps / (stream_ms * 1e-3)},
             "cpu_baseline": {"value": n_cpu / cpu_t, "unit": "iter/s", "cores": cores, "kind": "port",
@@ -395,8 +483,8 @@ def run_gpu(args):
         os.dup2(saved_stdout, 1)
         print(json.dumps(line), flush=True)
         os.dup2(2, 1)
+    host_barrier()
     if world > 1:
-        dist.barrier()
         dist.destroy_process_group()
     eng.close()
     return 0

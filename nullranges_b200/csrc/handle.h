@@ -30,6 +30,14 @@
 
 namespace nrb {
 
+struct GroupSpin {
+    static void pause() {
+#if defined(__x86_64__) || defined(__i386__)
+        __builtin_ia32_pause();
+#endif
+    }
+};
+
 // NRB200_TRACE=1: host-side stage timings on stderr (development aid)
 struct Trace {
     static bool on() {
@@ -242,7 +250,7 @@ struct nrb200_handle {
     // tuning knobs (environment, read at create)
     bool tune_end_rank = true;         // NRB200_END_RANK=0: always radix-sort the ends (index build)
     int tune_rpt = 1;                  // NRB200_RPT: iterations per thread of the count kernel (1, 2 or 4)
-    int tune_ipt = 1;                  // NRB200_IPT: iterations a thread of the count kernel stays on its feature (<= 64; 1 = one thread per (feature, iteration))
+    int tune_ipt = 4;                  // NRB200_IPT: iterations a thread of the count kernel stays on its feature (<= 64; 1 = one thread per (feature, iteration))
     int tune_loop_minb = 12;           // NRB200_LOOP_MINB: its min CTAs per SM (16 = 32 registers, 12 = 40)
     int tune_rows_ipc = 4;             // NRB200_ROWS_IPC: iterations a CTA of the rows kernel loops over
     double tune_table_mult = 4.0;

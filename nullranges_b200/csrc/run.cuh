@@ -449,29 +449,39 @@ int run_counts_core(nrb200_handle *h, const nrb200_draws *d, bool want_counts, i
         }
     }
     NRB_CUDA(h, cudaEventRecord(h->ev[2], h->stream));
+    // Chunks that landed in pinned staging memory are handed to the caller by ONE team of host threads that stays up
+    // for the whole drain: thread 0 waits for chunk c's copy event and publishes it, every thread then converts
+    // (uint16 -> int32) or copies its slice of the chunk and moves on to the next -- no fork / join per chunk.
     std::vector<size_t> redo;  // wire16: chunks whose overflow flag is up
-    for (size_t c = 0; c < staged.size(); ++c) {  // chunk c has landed in pinned memory: hand it to the caller
-        NRB_CUDA(h, cudaEventSynchronize(h->copied_ev[c % kChunkEvents]));
-        const int64_t r0 = staged[c].first, n = staged[c].second;
-        const size_t piece = (size_t)1 << 18;  // elements per task
-        const size_t elems = (size_t)n * G;
-        const int64_t pieces = (int64_t)((elems + piece - 1) / piece);
-        if (wire16) {
-            if (h->flags_host[c % kChunkEvents]) {
-                redo.push_back(c);
-                continue;
+    if (!staged.empty()) {
+        std::atomic<int64_t> landed{-1};
+        std::atomic<int> drain_err{0};
+        const int64_t n_chunks = (int64_t)staged.size();
+#pragma omp parallel num_threads(host_threads(h))
+        {
+            const int tid = omp_get_thread_num(), nth = omp_get_num_threads();
+            for (int64_t c = 0; c < n_chunks; ++c) {
+                if (tid == 0) {
+                    if (cudaEventSynchronize(h->copied_ev[c % kChunkEvents]) != cudaSuccess) drain_err.store(1);
+                    landed.store(c, std::memory_order_release);
+                } else {
+                    while (landed.load(std::memory_order_acquire) < c) GroupSpin::pause();
+                }
+                if (drain_err.load()) continue;
+                const int64_t r0 = staged[c].first, n = staged[c].second;
+                if (wire16 && h->flags_host[c % kChunkEvents]) continue;  // redone in int32 below
+                const size_t elems = (size_t)n * G;
+                const size_t per = ((elems + nth - 1) / nth + 15) & ~(size_t)15;
+                const size_t lo = std::min(elems, (size_t)tid * per), hi = std::min(elems, lo + per);
+                if (hi <= lo) continue;
+                if (wire16) widen_u16_to_i32(staging16 + r0 * G + lo, host_counts + r0 * G + lo, hi - lo);
+                else std::memcpy(host_counts + r0 * G + lo, staging + r0 * G + lo, (hi - lo) * sizeof(int32_t));
             }
-            const uint16_t *src = staging16 + r0 * G;
-            int32_t *dst = host_counts + r0 * G;
-#pragma omp parallel for schedule(static) num_threads(host_threads(h))
-            for (int64_t i = 0; i < pieces; ++i) widen_u16_to_i32(src + i * piece, dst + i * piece, std::min(piece, elems - (size_t)i * piece));
-        } else {
-            const int32_t *src = staging + r0 * G;
-            int32_t *dst = host_counts + r0 * G;
-#pragma omp parallel for schedule(static) num_threads(host_threads(h))
-            for (int64_t i = 0; i < pieces; ++i)
-                std::memcpy(dst + i * piece, src + i * piece, std::min(piece, elems - (size_t)i * piece) * sizeof(int32_t));
         }
+        if (drain_err.load()) return fail(h, NRB200_ERR_CUDA, "cudaEventSynchronize failed while draining the count matrix");
+        if (wire16)
+            for (int64_t c = 0; c < n_chunks; ++c)
+                if (h->flags_host[c % kChunkEvents]) redo.push_back((size_t)c);
     }
     if (!redo.empty()) {
         // some count exceeds 65535: those chunks again, with int32 output (the per-iteration vectors of the second pass go
