@@ -45,7 +45,9 @@ if _lws > 1 and os.environ.get("OMP_NUM_THREADS") == "1":
         _cores = len(os.sched_getaffinity(0))
     except AttributeError:
         _cores = os.cpu_count() or 1
-    os.environ["OMP_NUM_THREADS"] = str(max(1, _cores // _lws))
+    # every rank may use all cores: the device-resident leg has next to no host work, and in the end-to-end leg only
+    # rank 0 works (it drives all N GPUs through one device-group handle; the other ranks sleep in a host barrier)
+    os.environ["OMP_NUM_THREADS"] = str(max(1, _cores))
 
 import numpy as np
 

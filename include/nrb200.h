@@ -69,6 +69,11 @@ void nrb200_destroy(nrb200_handle *h);
 /* h may be NULL: error of the last failed nrb200_create() on this thread. */
 const char *nrb200_last_error(const nrb200_handle *h);
 const char *nrb200_version(void);
+/* How this build treats the zero-width ranges the within-chromosome variants keep at [L + 1, L] (no width filter at
+ * R/bootUnsegmented.R:73, :107) when they meet exclude / query ranges: 0 = they overlap nothing, 1 = IRanges' plain
+ * overlap test (a hit of every range strictly containing the position).  A compile-time constant
+ * (NRB_ZERO_WIDTH_RULE, csrc/device_views.cuh); INTEGRATION.md lists the R one-liner that settles it. */
+int nrb200_zero_width_rule(void);
 
 /* ---- inputs ------------------------------------------------------------------------ */
 

@@ -51,6 +51,7 @@ SYMBOLS = [
     ("nrb200_destroy", None, [vp]),
     ("nrb200_last_error", C.c_char_p, [vp]),
     ("nrb200_version", C.c_char_p, []),
+    ("nrb200_zero_width_rule", C.c_int, []),
     ("nrb200_set_ranges", C.c_int, [vp, C.c_int64, C.c_int32, i64p, i32p, i32p, i32p, i8p]),
     ("nrb200_set_ranges_begin", C.c_int, [vp, C.c_int64, C.c_int32, i64p, i32p, i32p, i32p, i8p]),
     ("nrb200_set_ranges_end", C.c_int, [vp]),

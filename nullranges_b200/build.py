@@ -43,7 +43,8 @@ def stale() -> bool:
 def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not stale():
         return SO
-    cmd = [nvcc(), *NVCC_FLAGS, *(["-Xptxas", "-v"] if verbose else []), "-o", SO,
+    rule = os.environ.get("NRB200_ZERO_WIDTH_RULE")  # development: flip THE ZERO-WIDTH RULE (csrc/device_views.cuh)
+    cmd = [nvcc(), *NVCC_FLAGS, *([f"-DNRB_ZERO_WIDTH_RULE={int(rule)}"] if rule else []), *(["-Xptxas", "-v"] if verbose else []), "-o", SO,
            *[os.path.join(CSRC, f) for f in SOURCES]]
     env = dict(os.environ)
     # nvcc's host compiler: the system g++ (the image also exports CC/CXX wrappers)

@@ -1,7 +1,9 @@
 // libnrb200: the extern "C" entry points of include/nrb200.h.  (textually included by engine.cu)
 extern "C" {
 
-const char *nrb200_version(void) { return "nrb200 0.1.0 (sm_100a)"; }
+const char *nrb200_version(void) { return "nrb200 0.2.0 (sm_100a)"; }
+
+int nrb200_zero_width_rule(void) { return kZeroWidthStrictlyInside ? 1 : 0; }
 
 const char *nrb200_last_error(const nrb200_handle *h) { return h ? h->error.c_str() : g_create_error.c_str(); }
 

@@ -13,6 +13,21 @@ namespace nrb {
 constexpr int kWarp = 32;
 constexpr unsigned kFull = 0xffffffffu;
 
+// ---- THE ZERO-WIDTH RULE (one named constant; the oracle carries the same one, oracle/nr_oracle.c) -------------
+// The within-chromosome variants keep ranges that trim() shrank to width 0 at [L + 1, L] (no width filter at
+// R/bootUnsegmented.R:73, :107).  Whether such a range overlaps an exclude / query range is decided inside IRanges,
+// which is neither in the reference tree nor runnable here ("R-check items"):
+//   0  a zero-width range overlaps nothing                                              (what this build ships)
+//   1  the plain test start_q <= end_s && end_q >= start_s also at width 0: a hit of every range that strictly
+//      contains its position.  Only exclude / query ranges that reach past their sequence end can tell the two apart.
+// Flip with -DNRB_ZERO_WIDTH_RULE=1 (NRB200_ZERO_WIDTH_RULE=1 python nullranges_b200/build.py --force).  Under rule 1
+// the streaming kernels apply the test per range; the rank path, whose windows encode rule 0 (start' <= L), steps
+// aside for exactly the inputs where the rules differ (rank_path_ok(), run.cuh).
+#ifndef NRB_ZERO_WIDTH_RULE
+#define NRB_ZERO_WIDTH_RULE 0
+#endif
+constexpr bool kZeroWidthStrictlyInside = NRB_ZERO_WIDTH_RULE != 0;
+
 // ---- device views ---------------------------------------------------------------------
 
 struct RangesView {            // canonical (seqname, start, end) order

@@ -155,15 +155,13 @@ int group_lead(nrb200_handle *g, const std::function<int(nrb200_handle *)> &fn) 
 }
 
 
-// Before a run: the leader prepares first (it builds the window lists, with all host threads), the others then take
-// its lists.  Nothing happens when no input changed since the last run.
+// Before a run: the leader prepares first (it builds the window lists), the others then take its lists.  Nothing happens when no input changed since the last run.
 int group_prepare(nrb200_handle *g) {
     nrb200_handle *lead = g->members[0];
     NRB_CUDA(g, cudaSetDevice(lead->device));
-    const int share = lead->omp_threads;
-    lead->omp_threads = 0;
+    // (with the leader's own share of the host threads: a larger team's idle threads would spin on the cores the other
+    // members' driver threads need right after)
     const int rc = prepare(lead);
-    lead->omp_threads = share;
     if (rc) {
         g->error = "GPU " + std::to_string(lead->device) + ": " + lead->error;
         return rc;
@@ -236,17 +234,24 @@ int group_set_ranges_begin(nrb200_handle *g, int64_t n, int32_t n_seq, const int
                 else cudaGetLastError();
             }
             if (g->g_stage_cap >= need) {
+                // every member copies its 1/W-th of each column with its own host threads (all cores busy, no team larger
+                // than a member's share), then all of them upload from the one pinned copy
                 char *base = static_cast<char *>(g->g_stage);
                 const void *src[4] = {seqid, start, end, strand};
                 const size_t bytes[4] = {(size_t)n * 4, (size_t)n * 4, (size_t)n * 4, strand ? (size_t)n : 0};
-                const size_t piece = (size_t)1 << 20;
-                for (int c = 0; c < 4; ++c) {
-                    const int64_t pieces = (int64_t)((bytes[c] + piece - 1) / piece);
-#pragma omp parallel for schedule(static)
-                    for (int64_t i = 0; i < pieces; ++i)
-                        std::memcpy(base + c * col + i * piece, static_cast<const char *>(src[c]) + i * piece,
-                                    std::min(piece, bytes[c] - (size_t)i * piece));
-                }
+                const int W = group_size(g);
+                group_all(g, [&](int k, nrb200_handle *m) {
+                    const size_t piece = (size_t)256 << 10;
+                    for (int c = 0; c < 4; ++c) {
+                        const int64_t pieces = (int64_t)((bytes[c] + piece - 1) / piece);
+                        const int64_t p0 = pieces * k / W, p1 = pieces * (k + 1) / W;
+#pragma omp parallel for schedule(static) num_threads(host_threads(m))
+                        for (int64_t i = p0; i < p1; ++i)
+                            std::memcpy(base + c * col + i * piece, static_cast<const char *>(src[c]) + i * piece,
+                                        std::min(piece, bytes[c] - (size_t)i * piece));
+                    }
+                    return NRB200_OK;
+                });
                 seqid = reinterpret_cast<const int32_t *>(base);
                 start = reinterpret_cast<const int32_t *>(base + col);
                 end = reinterpret_cast<const int32_t *>(base + 2 * col);

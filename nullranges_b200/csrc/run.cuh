@@ -6,6 +6,13 @@ namespace {
 // only a segmentation reaching beyond its sequence falls back to streaming the hits (boot_count_kernel).
 bool rank_path_ok(const nrb200_handle *h) {
     if (h->flags & NRB200_FLAG_FORCE_STREAM) return false;
+    if (kZeroWidthStrictlyInside && h->have_plan && !h->plan.drop_zero_width()) {
+        // zero-width rule 1 (device_views.cuh): the window lists encode rule 0; the rules differ only when an exclude or
+        // query range reaches past the end of its sequence -- those inputs take the streaming kernels
+        for (const RangeSet *rs : {&h->query, &h->excl})
+            for (int c = 0; rs->n > 0 && c < h->n_seq; ++c)
+                if ((int64_t)rs->max_end[c] > h->seqlen[c]) return false;
+    }
     return h->tiles_in_bounds;
 }
 
@@ -460,6 +467,19 @@ int run_counts_core(nrb200_handle *h, const nrb200_draws *d, bool want_counts, i
 #pragma omp parallel num_threads(host_threads(h))
         {
             const int tid = omp_get_thread_num(), nth = omp_get_num_threads();
+            if (pageable) {
+                // A freshly allocated destination (every R call's result is) faults its pages in on first touch.  Each
+                // thread touches the pages of the slices it will fill NOW, while the first chunks still compute and
+                // travel, instead of inside the conversion loop.  (Thread 0 goes straight to the copy events.)
+                for (int64_t c = 0; c < n_chunks && tid > 0; ++c) {
+                    const size_t elems = (size_t)staged[c].second * G;
+                    const size_t per = ((elems + nth - 1) / nth + 15) & ~(size_t)15;
+                    const size_t lo = std::min(elems, (size_t)tid * per), hi = std::min(elems, lo + per);
+                    volatile int32_t *dst = host_counts + staged[c].first * G;
+                    for (size_t i = lo; i < hi; i += 1024) dst[i] = 0;  // one store per 4 KB page
+                    if (hi > lo) dst[hi - 1] = 0;
+                }
+            }
             for (int64_t c = 0; c < n_chunks; ++c) {
                 if (tid == 0) {
                     if (cudaEventSynchronize(h->copied_ev[c % kChunkEvents]) != cudaSuccess) drain_err.store(1);

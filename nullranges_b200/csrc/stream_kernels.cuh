@@ -77,7 +77,7 @@ __device__ __forceinline__ bool transform(const BootParams &P, const Item &it, i
 
 template <bool STRANDED>
 __device__ __forceinline__ bool excluded(const SliceView &X, int tile, int32_t s2, int32_t e2, int strand) {
-    if (e2 < s2) return false;
+    if (e2 < s2 && !kZeroWidthStrictlyInside) return false;  // THE ZERO-WIDTH RULE (device_views.cuh)
     const int32_t a = __ldg(X.tile_lo + tile), b = __ldg(X.tile_hi + tile);
     for (int32_t k = a; k < b; ++k) {
         if (s2 <= __ldg(X.end + k) && e2 >= __ldg(X.start + k)) {
@@ -149,7 +149,7 @@ __global__ void __launch_bounds__(256) boot_count_kernel(const BootParams P) {
             }
             if (EXCL == kExclDrop && excluded<STRANDED>(P.excl, it.tile, s2, e2, strand)) continue;
             ++rows;
-            if (HAS_QUERY && e2 >= s2) overlaps += count_piece<STRANDED>(P, r, q_lo, q_hi, s2, e2, strand);
+            if (HAS_QUERY && (e2 >= s2 || kZeroWidthStrictlyInside)) overlaps += count_piece<STRANDED>(P, r, q_lo, q_hi, s2, e2, strand);
         }
         rows = __reduce_add_sync(kFull, rows);
         hits = __reduce_add_sync(kFull, hits);

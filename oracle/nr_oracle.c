@@ -877,11 +877,26 @@ static int64_t upper_start(const orc_index *ix, int64_t lo, int64_t hi, int64_t 
 
 static inline int strand_compatible(int a, int b) { return a == 0 || b == 0 || a == b; }
 
+/* ---- THE ZERO-WIDTH RULE (one named constant; the kernels carry the same one, device_views.cuh) --------------
+ * The within-chromosome variants keep ranges that trim() shrank to width 0 at [L + 1, L] (no width filter at
+ * R/bootUnsegmented.R:73, :107).  Whether such a range overlaps an exclude / query range is decided inside IRanges,
+ * which is not in the reference tree and cannot run here (INTEGRATION.md "R-check items"):
+ *   0  a zero-width range overlaps nothing                                        (what this build ships)
+ *   1  the plain overlap test start_q <= end_s && end_q >= start_s also for width 0, i.e. a zero-width range is a
+ *      hit of every range that strictly contains its position (IRanges' documented behaviour for maxgap = -1,
+ *      minoverlap = 0); only ranges reaching past the sequence end can tell the two apart.
+ * Build with -DORC_ZERO_WIDTH_RULE=1 (and the engine with -DNRB_ZERO_WIDTH_RULE=1) to flip it. */
+#ifndef ORC_ZERO_WIDTH_RULE
+#define ORC_ZERO_WIDTH_RULE 0
+#endif
+ORC_API int orc_zero_width_rule(void) { return ORC_ZERO_WIDTH_RULE; }
+static inline int zero_width_skips(int64_t s, int64_t e) { return e < s && !ORC_ZERO_WIDTH_RULE; }
+
 /* overlapsAny(range, index) with findOverlaps(type="any") semantics on positive-width
  * ranges: same seqname, start_q <= end_s, end_q >= start_s, compatible strands.
  * A zero-width query range overlaps nothing that lies inside the sequence bounds. */
 static int overlaps_any(const orc_index *ix, int c, int64_t s, int64_t e, int strand) {
-    if (!ix || e < s) return 0;
+    if (!ix || zero_width_skips(s, e)) return 0;
     int64_t lo = ix->off[c], hi = upper_start(ix, ix->off[c], ix->off[c + 1], e);
     for (int64_t k = hi - 1; k >= lo; k--) {
         if ((int64_t)ix->pmax[k] < s) break;
@@ -898,7 +913,8 @@ static int overlaps_any(const orc_index *ix, int c, int64_t s, int64_t e, int st
  * Returns the number of overlapped features. */
 static int64_t count_into(const orc_index *q, int c, int64_t s, int64_t e, int strand,
                           int32_t *counts) {
-    if (!q || e < s) return 0;
+    if (!q || zero_width_skips(s, e)) return 0;
+    if (e < s && q->minoverlap > 0) return 0; /* an empty intersection is never minoverlap wide */
     int64_t n = 0;
     const int64_t m1 = q->slack;
     int64_t lo = q->off[c], hi = upper_start(q, q->off[c], q->off[c + 1], e + m1);
@@ -990,8 +1006,8 @@ static int64_t one_iteration(const orc_plan *p, const orc_index *y, const orc_in
                  * gaps(exclude, end = seqlengths(y)) restricted to strand "*"; the range is replaced by
                  * its intersections with the gaps it overlaps (join_overlap_intersect: one row per
                  * (range, gap) hit, gaps ascending).  Gaps are disjoint and sorted, so the overlapped
-                 * ones are consecutive.  A zero-width range overlaps no gap. */
-                if (e2 < s2) continue;
+                 * ones are consecutive.  A zero-width range: see THE ZERO-WIDTH RULE. */
+                if (zero_width_skips(s2, e2)) continue;
                 int64_t glo = excl->off[tc], ghi = upper_start(excl, glo, excl->off[tc + 1], e2);
                 int64_t k0 = ghi;
                 while (k0 > glo && (int64_t)excl->end[excl->ord[k0 - 1]] >= s2) k0--;

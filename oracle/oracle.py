@@ -22,7 +22,8 @@ UNSEG_ACROSS, UNSEG_WITHIN, SEG_PROP, SEG_NOPROP, PERMUTE_WITHIN, PERMUTE_ACROSS
 def build(force: bool = False) -> str:
     src = os.path.join(_HERE, "nr_oracle.c")
     if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < os.path.getmtime(src):
-        subprocess.check_call(["make", "-C", _HERE, "-s"] + (["-B"] if force else []))
+        rule = os.environ.get("NRB200_ZERO_WIDTH_RULE")  # development: flip the zero-width rule together with the engine's
+        subprocess.check_call(["make", "-C", _HERE, "-s"] + (["-B"] if force else []) + ([f"EXTRA=-DORC_ZERO_WIDTH_RULE={int(rule)}"] if rule else []))
     return _SO
 
 
@@ -38,6 +39,7 @@ def lib():
     vp, i32p, i64p, i8p, dp = C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_int64), C.POINTER(C.c_int8), C.POINTER(C.c_double)
     u32p = C.POINTER(C.c_uint32)
     L.orc_last_error.restype = C.c_char_p
+    L.orc_zero_width_rule.restype = C.c_int
     L.orc_rng_new.restype = vp
     L.orc_rng_new.argtypes = [C.c_uint32]
     L.orc_rng_free.argtypes = [vp]
@@ -316,3 +318,8 @@ def boot_weighted(plan: Plan, y: Index, query: Index, weights, R: int, *, exclud
                 hit &= ov >= minoverlap
             sums[r, hit] += w[src]
     return {"feature_sums": sums, "iter_sums": sums.sum(axis=1)}
+
+
+def zero_width_rule() -> int:
+    """0: a zero-width bootstrapped range overlaps nothing; 1: IRanges' plain overlap test (nr_oracle.c, THE ZERO-WIDTH RULE)."""
+    return int(lib().orc_zero_width_rule())

@@ -182,6 +182,30 @@ def test_cfg2_full_size(engine):
     assert abs(big["iter_totals"].mean() / tot - 1.0) < 0.05
 
 
+@pytest.mark.parametrize("L_b", [100_000, 200_000, 1_000_000])
+def test_cfg5_block_length_sweep_full_size(engine, L_b):
+    """BASELINE configs[4] (the vignette's variance-vs-L_b diagnostic, vignettes/bootRanges.Rmd:195-199) at full size:
+    the 1M-range workload at the other three block lengths (5e5 is test_cfg2_full_size), 8 Philox iterations each
+    against the oracle -- whole count matrix, per-iteration totals and rows; B = 28,760 / 14,385 / 2,887 blocks."""
+    from nullranges_b200 import synth
+    y, x = synth.atac_peaks(1_000_000, seed=3), synth.genes(20_000, seed=2)
+    case = _synth_case(y, x)
+    case["L_b"] = L_b
+    plan, yi, qi, _ = H.oracle_objects(case, 0)
+    assert H.load_engine(engine, case, 0) == plan.B == {100_000: 28_760, 200_000: 14_385, 1_000_000: 2_887}[L_b]
+    R = 8
+    got = engine.run_counts(Draws(n_iter=R, rng_mode=_lib.RNG_PHILOX, seed=77, iter0=123))
+    ref = O.boot_counts(plan, yi, qi, R, seed=77, iter0=123, nthreads=O.max_threads())
+    for k in ("iter_nranges", "iter_totals", "feature_counts"):
+        assert np.array_equal(got[k], ref[k]), k
+    # R = 400 through size-independent properties: a later shard reproduces its rows; row sums are the totals
+    big = engine.run_counts(Draws(n_iter=400, rng_mode=_lib.RNG_PHILOX, seed=77, iter0=123))
+    assert np.array_equal(big["feature_counts"][:R], got["feature_counts"])
+    assert np.array_equal(big["feature_counts"].sum(axis=1), big["iter_totals"])
+    part = engine.run_counts(Draws(n_iter=50, rng_mode=_lib.RNG_PHILOX, seed=77, iter0=123 + 350))
+    assert np.array_equal(part["feature_counts"], big["feature_counts"][350:])
+
+
 @pytest.mark.parametrize("kind", BOOT_KINDS)
 def test_dense_exclusion(engine, kind):
     """Many small, close exclude regions and ranges long enough to span several of them: the rank

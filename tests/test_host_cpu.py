@@ -174,3 +174,13 @@ def test_side_arrays_maps_seqlevels_and_drops_foreign_ranges():
     reordered = GRanges(["chr2", "chr1"], [7, 9], width=[2, 2], seqlengths={"chr2": 50, "chr1": 100})
     sid, st, en, strand, keep = BR._side_arrays(reordered, y, "x")
     assert sid.tolist() == [1, 0] and keep is None and st is reordered.start
+
+
+def test_zero_width_rule_is_one_constant_on_both_sides():
+    """The engine and the oracle are built with the same zero-width rule (include/nrb200.h: nrb200_zero_width_rule);
+    flipping it is one define on each side (NRB200_ZERO_WIDTH_RULE=1 at build time sets both)."""
+    from nullranges_b200 import _lib
+    from oracle import oracle as O
+    lib = _lib.load()
+    assert lib.nrb200_zero_width_rule() == O.zero_width_rule()
+    assert lib.nrb200_zero_width_rule() == int(os.environ.get("NRB200_ZERO_WIDTH_RULE", "0"))
