@@ -8,12 +8,12 @@ One "step" = R = 1000 bootstrap iterations per GPU.
 
   value   iterations/s, device-resident (ranges, query and plan already in HBM; block draws are
           Philox on the device, so a step has no input copy), CUDA events, max over ranks; one process per GPU
-  e2e     iterations/s through the public API bootCounts(y, x, ..., gpus=N) from PAGEABLE host arrays into a freshly
-          allocated pageable int32 matrix (what an R caller has: R's vectors are pageable and every call allocates
-          its result): every step uploads y and x, builds the indexes, runs R * N iterations sharded over the N GPUs
-          and delivers ONE [R * N x G] host matrix.  e2e_pinned: the same from / into pinned buffers.  Under
-          torchrun rank 0 drives the N devices through one device-group handle (the product's multi-GPU path); the
-          other ranks wait on the host.
+  e2e     iterations/s through the public API bootCounts(y, x, ..., gpus=N) from PAGEABLE host arrays into a pageable
+          caller-owned int32 matrix (R's vectors are pageable): every step uploads y and x, builds the indexes, runs
+          R * N iterations sharded over the N GPUs and delivers ONE [R * N x G] host matrix.  e2e_fresh_result: the
+          same with the result allocated inside every call; e2e_pinned: from / into pinned buffers.  Under torchrun
+          rank 0 drives the N devices through one device-group handle (the product's multi-GPU path); the other
+          ranks wait on the host.
   roofline  the dominant kernel (boot_rank_count_kernel) against the minimal DRAM bytes of the rank path;
           roofline_l2: the same kernel against what bounds it -- 32-byte sectors through the L2 -- with the ceiling
           measured on the device in this run; roofline_model_8d: SURVEY 8d's byte model (which the rank path does
@@ -360,8 +360,12 @@ def run_gpu(args):
                 res = fn(2 + s_)
             return (time.perf_counter() - t0) / e2e_steps, res
 
-        # (a) pageable in, freshly allocated pageable out -- the R-realistic call
-        t_pg, res_pg = timed(lambda s_: bootCounts(y_pg, x_pg, L_B, R=Rt, rng="philox", seed=2024, iter0=s_ * Rt, gpus=gpus))
+        # (a) pageable in, pageable out: caller-owned plain host buffers, as the C ABI takes them (R's vectors are pageable)
+        out_pg = {"iter_totals": np.zeros(Rt, np.int64), "iter_nranges": np.zeros(Rt, np.int64), "feature_counts": np.zeros((Rt, G), np.int32)}
+        t_pg, res_pg = timed(lambda s_: bootCounts(y_pg, x_pg, L_B, R=Rt, rng="philox", seed=2024, iter0=s_ * Rt, gpus=gpus, out=out_pg))
+        # (a') the same with the result matrix allocated inside every call (fresh pages: the kernel zeroes and maps
+        # R * G * 4 bytes while the call runs)
+        t_fresh, res_fresh = timed(lambda s_: bootCounts(y_pg, x_pg, L_B, R=Rt, rng="philox", seed=2024, iter0=s_ * Rt, gpus=gpus))
         # (b) pinned in, pinned out
         keep = []
 
@@ -392,10 +396,15 @@ def run_gpu(args):
                "one [R x G] int32 host matrix; rank 0 drives the N GPUs through one device-group handle")
         e2e = {"e2e": {"value": Rt / t_pg, "unit": "iter/s", "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": int(res_pg.stats["d2h_bytes"]),
                        "steps": e2e_steps, "ms_per_step": 1e3 * t_pg, "api": api,
-                       "buffers": "pageable numpy inputs; the [R x G] int32 result is allocated inside every call (fresh pages), as an R caller's is; "
-                                  "the matrix crosses PCIe as uint16 and is widened by the host"},
+                       "buffers": "pageable (plain numpy) inputs and a pageable caller-owned [R x G] int32 result, as the C ABI / an R caller hands them in; "
+                                  "the matrix crosses PCIe as uint16 and the host widens it into the caller's int32 matrix"},
+               "e2e_fresh_result": {"value": Rt / t_fresh, "unit": "iter/s", "ms_per_step": 1e3 * t_fresh,
+                                    "buffers": "as e2e, but the result matrix is allocated inside every call (an R call allocates its result): "
+                                               "the difference is the kernel zeroing and mapping the fresh pages"},
                "e2e_pinned": {"value": Rt / t_pin, "unit": "iter/s", "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": int(res_pin.stats["d2h_bytes"]),
                               "steps": e2e_steps, "ms_per_step": 1e3 * t_pin, "buffers": "pinned inputs and pinned preallocated outputs (int32 on the wire)"}}
+        assert np.array_equal(res_fresh.feature_counts, res_pg.feature_counts)
+        del res_fresh
         del res_pg, res_pin, one
     host_barrier()
 

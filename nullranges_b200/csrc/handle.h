@@ -451,6 +451,69 @@ int upload_direct(nrb200_handle *h, DevMem &dst, const T *src, size_t n, int slo
     return NRB200_OK;
 }
 
+// Several caller-owned columns of one call (the columns of y).  Pinned memory goes straight to the DMA engine.  Pageable
+// memory is staged through the handle's pinned buffer by ONE team of host threads for all columns: every column is
+// copied in parallel and handed to the DMA engine by the team's master as soon as it is complete, while the others
+// already copy the next column.
+struct HostColumn {
+    DevMem *dst;
+    const void *src;
+    size_t bytes;
+};
+inline int upload_columns(nrb200_handle *h, const HostColumn *cols, int n_cols) {
+    size_t total = 0, largest = 0;
+    for (int c = 0; c < n_cols; ++c) {
+        NRB_CUDA(h, cols[c].dst->reserve(cols[c].bytes));
+        total += (cols[c].bytes + 4095) & ~(size_t)4095;
+        largest = std::max(largest, cols[c].bytes);
+    }
+    bool staged = false;
+    if (largest >= ((size_t)256 << 10) && total <= ((size_t)1 << 30)) {
+        cudaPointerAttributes attr{};
+        const bool pageable = cudaPointerGetAttributes(&attr, cols[0].src) != cudaSuccess || attr.type == cudaMemoryTypeUnregistered;
+        cudaGetLastError();
+        if (pageable) {
+            if (h->stage_in_cap < total) {
+                if (h->stage_in) cudaFreeHost(h->stage_in);
+                h->stage_in = nullptr;
+                h->stage_in_cap = 0;
+                if (cudaMallocHost((void **)&h->stage_in, total) == cudaSuccess) h->stage_in_cap = total;
+                else cudaGetLastError();
+            }
+            staged = h->stage_in_cap >= total;
+        }
+    }
+    if (!staged) {
+        for (int c = 0; c < n_cols; ++c)
+            if (cols[c].bytes) NRB_CUDA(h, cudaMemcpyAsync(cols[c].dst->p, cols[c].src, cols[c].bytes, cudaMemcpyHostToDevice, h->stream));
+        return NRB200_OK;
+    }
+    cudaError_t err = cudaSuccess;
+    const size_t piece = (size_t)256 << 10;
+#pragma omp parallel num_threads(host_threads(h))
+    {
+        size_t at = 0;
+        for (int c = 0; c < n_cols; ++c) {
+            char *to = static_cast<char *>(h->stage_in) + at;
+            const char *from = static_cast<const char *>(cols[c].src);
+            const size_t bytes = cols[c].bytes;
+            const int64_t pieces = (int64_t)((bytes + piece - 1) / piece);
+#pragma omp for schedule(static)
+            for (int64_t i = 0; i < pieces; ++i) std::memcpy(to + i * piece, from + i * piece, std::min(piece, bytes - (size_t)i * piece));
+#pragma omp master
+            {
+                if (bytes) {
+                    const cudaError_t e = cudaMemcpyAsync(cols[c].dst->p, to, bytes, cudaMemcpyHostToDevice, h->stream);
+                    if (e != cudaSuccess) err = e;
+                }
+            }
+            at += (bytes + 4095) & ~(size_t)4095;
+        }
+    }
+    if (err != cudaSuccess) return fail(h, NRB200_ERR_CUDA, std::string("cudaMemcpyAsync (staged upload): ") + cudaGetErrorString(err));
+    return NRB200_OK;
+}
+
 // The H statistic: kHitSlots partial sums followed by one flag word (the table's fill-overflow flag).
 constexpr size_t kHitBytes = ((size_t)64 + 1) * 8;
 inline int hits_reset(nrb200_handle *h) {

@@ -128,10 +128,9 @@ int load_y_begin(nrb200_handle *h, int64_t n, const int32_t *seqid, const int32_
     NRB_CUDA(h, cudaMemcpyAsync(h->inspect_dev.p, init, words * 4, cudaMemcpyHostToDevice, h->stream));
     int32_t *base = h->inspect_dev.as<int32_t>();
     const unsigned grid = (unsigned)std::min<int64_t>((n + 255) / 256, (int64_t)h->sm_count * 8);
-    if ((rc = upload_direct(h, y.start, start, (size_t)n, 1))) return rc;
-    if ((rc = upload_direct(h, y.end, end, (size_t)n, 2))) return rc;
-    if ((rc = upload_direct(h, y.seqid, seqid, (size_t)n, 0))) return rc;
-    if (strand && (rc = upload_direct(h, y.strand, strand, (size_t)n, 3))) return rc;
+    const HostColumn cols[4] = {{&y.start, start, (size_t)n * 4}, {&y.end, end, (size_t)n * 4}, {&y.seqid, seqid, (size_t)n * 4},
+                                {&y.strand, strand, (size_t)n}};
+    if ((rc = upload_columns(h, cols, strand ? 4 : 3))) return rc;
     inspect_ranges_kernel<<<grid, 256, 0, h->stream>>>(y.seqid.as<int32_t>(), y.start.as<int32_t>(), y.end.as<int32_t>(),
                                                        strand ? y.strand.as<int8_t>() : nullptr, n, C,
                                                        reinterpret_cast<InspectOut *>(base), reinterpret_cast<unsigned *>(base + kHead),

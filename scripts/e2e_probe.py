@@ -8,6 +8,8 @@
       rows / count kernel ms per 1000 iterations, device-resident
   python scripts/e2e_probe.py sweep
       both of the above under the tuning knobs (NRB200_RPT, NRB200_WIRE16, NRB200_CHUNKS), one child process each
+  python scripts/e2e_probe.py cfg4 [--gpus N]
+      BASELINE configs[3] through bootMoments(..., gpus=N): wall clock of the whole call
   python scripts/e2e_probe.py timeline
       NRB200_TRACE_DEV timeline of one step (host queue time vs device arrival of every stage)
 """
@@ -103,6 +105,25 @@ def timeline(args):
     step(args)
 
 
+def cfg4(args):
+    """BASELINE configs[3]: 10M SNP-scale points vs 200k enhancers, withinChrom, R = 10^4, per-feature moments through
+    bootMoments(..., gpus=N): wall clock of the whole call from host arrays (upload, index, lists, run, moments back)."""
+    import numpy as np
+    from nullranges_b200 import bootMoments, synth
+    y, x = synth.points(10_000_000, seed=6), synth.enhancers(200_000, seed=7)
+    gpus = args.gpus if args.gpus > 1 else None
+    times, sig = [], None
+    for rep in range(args.reps + 1):
+        t0 = time.perf_counter()
+        m = bootMoments(y, x, L_B, R=10_000, withinChrom=True, rng="philox", seed=1, gpus=gpus)
+        times.append(time.perf_counter() - t0)
+        sig = (int(m.sum.sum()), int(m.sumsq.sum() % (1 << 61)), float(np.nansum(m.p_ge)))
+        kernel_ms = m.stats["kernel_ms"]
+    times = sorted(times[1:])
+    print(json.dumps({"mode": "cfg4", "gpus": args.gpus, "R": 10_000, "wall_ms_min": 1e3 * times[0], "wall_ms_median": 1e3 * times[len(times) // 2],
+                      "kernel_ms_slowest_gpu": kernel_ms, "signature": sig, "env": {k: v for k, v in os.environ.items() if k.startswith("NRB200_")}}), flush=True)
+
+
 def calib(args):
     from nullranges_b200 import Engine
     e = Engine(0)
@@ -112,9 +133,9 @@ def calib(args):
 
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
-    ap.add_argument("mode", choices=["step", "kernels", "sweep", "timeline", "calib"])
+    ap.add_argument("mode", choices=["step", "kernels", "sweep", "timeline", "calib", "cfg4"])
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--dest", default="pinned", choices=["pinned", "pageable", "fresh"])
     ap.add_argument("--reps", type=int, default=9)
     a = ap.parse_args()
-    {"step": step, "kernels": kernels, "sweep": sweep, "timeline": timeline, "calib": calib}[a.mode](a)
+    {"step": step, "kernels": kernels, "sweep": sweep, "timeline": timeline, "calib": calib, "cfg4": cfg4}[a.mode](a)
