@@ -252,6 +252,7 @@ struct nrb200_handle {
     int tune_rpt = 1;                  // NRB200_RPT: iterations per thread of the count kernel (1, 2 or 4)
     int tune_ipt = 4;                  // NRB200_IPT: iterations a thread of the count kernel stays on its feature (<= 64; 1 = one thread per (feature, iteration))
     int tune_loop_minb = 12;           // NRB200_LOOP_MINB: its min CTAs per SM (16 = 32 registers, 12 = 40)
+    bool tune_stream_old = false;      // NRB200_STREAM_OLD=1: streaming path through boot_count_kernel only (A/B)
     int tune_rows_ipc = 4;             // NRB200_ROWS_IPC: iterations a CTA of the rows kernel loops over
     double tune_table_mult = 4.0;
     int tune_wire16 = 2;               // NRB200_WIRE16: uint16 wire format of a host-bound matrix (0 never, 1 always, 2 pageable destinations)
@@ -264,6 +265,12 @@ struct nrb200_handle {
     SamplerView sampler_view{};
     bool slices_dirty = true, have_pmax_table = false;
     DevMem q_tile_lo, q_tile_hi, x_tile_lo, x_tile_hi, pair_off, pair_rec, f_src, tile_x_off, tile_x_rec;
+    // streaming path, tile-group form (boot_stream_kernel): y interleaved, tiles in genome order, groups of tiles
+    DevMem y_se, tiles_sorted_dev, groups_dev;
+    bool have_se = false, groups_ok = false;
+    int64_t n_groups = 0;
+    int group_slice_cap = 0;
+    std::vector<int32_t> q_lo_host, q_hi_host;
     int64_t n_pairs = 0;
     // tiles of each sequence in ascending start order, with the running max of their ends (made by nrb200_set_plan
     // for build_pairs)

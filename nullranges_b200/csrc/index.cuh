@@ -7,6 +7,9 @@ int range_set_to_device(nrb200_handle *h, RangeSet &rs) {
     if (rs.on_device) return NRB200_OK;
     int rc;
     const size_t n = (size_t)rs.n;
+    // 16 elements of slack behind every column: boot_stream_kernel copies 16-element-aligned slices of them
+    for (DevMem *m : {&rs.start, &rs.end, &rs.pmax, &rs.src}) NRB_CUDA(h, m->reserve((n + 16) * 4));
+    if (rs.stranded) NRB_CUDA(h, rs.strand.reserve(n + 16));
     if ((rc = upload(h, rs.start, rs.h_start.data(), n))) return rc;
     if ((rc = upload(h, rs.end, rs.h_end.data(), n))) return rc;
     if ((rc = upload(h, rs.pmax, rs.h_pmax.data(), n))) return rc;
@@ -267,6 +270,7 @@ int build_rank_tables(nrb200_handle *h) {
     build_rank_table_kernel<<<t_grid, threads, 0, h->stream>>>(y.start.as<int32_t>(), y.seq_off.as<int32_t>(),
                                                                h->rank_off_dev.as<int64_t>(), C, shift, h->rank_start.as<RankEntry>());
     h->have_pmax_table = false;  // only the streaming kernels need it: built on first use
+    h->have_se = false;          // (the same for the interleaved copy of y)
     NRB_CUDA(h, h->sort_keys_a.reserve(std::max<int64_t>(y.n, 1) * 8));
     NRB_CUDA(h, h->sort_keys_b.reserve(std::max<int64_t>(y.n, 1) * 8));
     auto sort_u64 = [&](int bits) -> int {  // sort_keys_a -> sort_keys_b
@@ -361,6 +365,18 @@ int build_rank_tables(nrb200_handle *h) {
     return NRB200_OK;
 }
 
+
+// y as interleaved {start, end} pairs: what boot_stream_kernel streams
+int ensure_interleaved(nrb200_handle *h) {
+    if (h->have_se) return NRB200_OK;
+    const int64_t n = h->y.n;
+    NRB_CUDA(h, h->y_se.reserve((size_t)(n + 2) * sizeof(int2)));
+    interleave_ranges_kernel<<<(unsigned)((n + 1 + 255) / 256), 256, 0, h->stream>>>(h->y.start.as<int32_t>(), h->y.end.as<int32_t>(), n,
+                                                                                     h->y_se.as<int2>());
+    NRB_CUDA(h, cudaGetLastError());
+    h->have_se = true;
+    return NRB200_OK;
+}
 
 // rank table over the running max of end: locate_block() of the streaming kernels
 int ensure_pmax_table(nrb200_handle *h) {

@@ -25,6 +25,54 @@ int build_slices(nrb200_handle *h, const RangeSet &rs, DevMem &lo_dev, DevMem &h
     int rc;
     if ((rc = upload(h, lo_dev, lo.data(), (size_t)B))) return rc;
     if ((rc = upload(h, hi_dev, hi.data(), (size_t)B))) return rc;
+    if (&rs == &h->query) {  // the tile groups of the streaming kernel are cut from these
+        h->q_lo_host = std::move(lo);
+        h->q_hi_host = std::move(hi);
+    }
+    return NRB200_OK;
+}
+
+// Tile groups of boot_stream_kernel: the tiles of every sequence in ascending start order, cut into runs of at most
+// kGroupTiles whose query slices (the union of the tiles' candidate windows: contiguous, because both orders follow the
+// genome) fit the shared-memory arrays.  A single tile with a larger slice makes the plan fall back to boot_count_kernel.
+int build_tile_groups(nrb200_handle *h) {
+    h->groups_ok = false;
+    if (h->plan.permute()) return NRB200_OK;  // block b lands on tile dst_tile[b]: block-centric kernel
+    const bool has_query = h->query.n > 0;
+    std::vector<int32_t> sorted;
+    std::vector<int32_t> groups;  // 4 words per group
+    int cap = 16;
+    for (int c = 0; c < h->n_seq; ++c) {
+        const auto &ids = h->tiles_by_seq.id[c];
+        size_t at = 0;
+        while (at < ids.size()) {
+            size_t n = std::min<size_t>(kGroupTiles, ids.size() - at);
+            int32_t lo = 0, hi = 0;
+            for (;;) {
+                lo = INT32_MAX, hi = 0;
+                for (size_t k = 0; has_query && k < n; ++k) {
+                    lo = std::min(lo, h->q_lo_host[ids[at + k]]);
+                    hi = std::max(hi, h->q_hi_host[ids[at + k]]);
+                }
+                if (!has_query || hi <= lo) { lo = hi = 0; break; }
+                lo &= ~15;
+                hi = (hi + 15) & ~15;
+                if (hi - lo <= kMaxSlice) break;
+                if (n == 1) return NRB200_OK;  // does not fit: the block-centric kernel takes this plan
+                n = (n + 1) / 2;
+            }
+            groups.insert(groups.end(), {(int32_t)sorted.size(), (int32_t)n, lo, hi});
+            cap = std::max(cap, hi - lo);
+            for (size_t k = 0; k < n; ++k) sorted.push_back(ids[at + k]);
+            at += n;
+        }
+    }
+    int rc;
+    if ((rc = upload(h, h->tiles_sorted_dev, sorted.data(), sorted.size()))) return rc;
+    if ((rc = upload(h, h->groups_dev, groups.data(), groups.size()))) return rc;
+    h->n_groups = (int64_t)groups.size() / 4;
+    h->group_slice_cap = cap;
+    h->groups_ok = h->n_groups > 0 && h->n_groups <= INT32_MAX;
     return NRB200_OK;
 }
 

@@ -384,8 +384,8 @@ template <bool SIMPLE>
 __global__ void __launch_bounds__(kRowsThreads, 6) boot_block_rows_kernel(const BootParams P, const TileExcl X, int ipc) {
     const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int lane = threadIdx.x & 31;
-#pragma unroll 1
   constexpr int RPT = 1;
+#pragma unroll 1
   for (int it = 0; it < ipc; ++it) {  // a CTA keeps its 256 blocks for `ipc` iterations (fewer, longer-lived CTAs)
     const int64_t r0 = ((int64_t)blockIdx.y * ipc + it) * RPT;
     if (r0 >= P.n_iter) break;

@@ -36,6 +36,7 @@ int prepare_lists(nrb200_handle *h) {
     if (!rank) {
         if (h->query.n && (rc = range_set_to_device(h, h->query))) return rc;
         if (h->query.n && (rc = build_slices(h, h->query, h->q_tile_lo, h->q_tile_hi))) return rc;
+        if ((rc = build_tile_groups(h))) return rc;
     }
     return NRB200_OK;
 }
@@ -49,7 +50,10 @@ int prepare(nrb200_handle *h) {
         if ((rc = prepare_lists(h))) return rc;
         h->slices_dirty = false;
     }
-    if (!rank_path_ok(h)) return ensure_pmax_table(h);
+    if (!rank_path_ok(h)) {
+        if (int rc = ensure_interleaved(h)) return rc;
+        return ensure_pmax_table(h);
+    }
     return NRB200_OK;
 }
 
@@ -216,6 +220,16 @@ BootParams make_params(nrb200_handle *h, const nrb200_draws *d) {
 }
 
 template <bool ST, bool HQ>
+void launch_stream_t(nrb200_handle *h, const BootParams &P, int excl) {
+    const GroupView V{h->groups_dev.as<TileGroup>(), h->tiles_sorted_dev.as<int32_t>(), h->y_se.as<int2>(), h->group_slice_cap};
+    const dim3 grid((unsigned)h->n_groups, (unsigned)P.n_iter);
+    const size_t smem = ((size_t)h->group_slice_cap * 21 + 15) & ~(size_t)15;
+    if (excl == kExclNone) boot_stream_kernel<ST, HQ, kExclNone><<<grid, 256, smem, h->stream>>>(P, V);
+    else if (excl == kExclDrop) boot_stream_kernel<ST, HQ, kExclDrop><<<grid, 256, smem, h->stream>>>(P, V);
+    else boot_stream_kernel<ST, HQ, kExclTrim><<<grid, 256, smem, h->stream>>>(P, V);
+}
+
+template <bool ST, bool HQ>
 void launch_count_t(nrb200_handle *h, const BootParams &P, unsigned grid, int excl) {
     if (excl == kExclNone) boot_count_kernel<ST, HQ, kExclNone><<<grid, 256, 0, h->stream>>>(P);
     else if (excl == kExclDrop) boot_count_kernel<ST, HQ, kExclDrop><<<grid, 256, 0, h->stream>>>(P);
@@ -268,6 +282,13 @@ int launch_count(nrb200_handle *h, const BootParams &P, bool has_query) {
     const unsigned grid = (unsigned)std::min<int64_t>(ctas, (int64_t)h->sm_count * 64);
     const bool st = h->y.stranded && ((has_query && h->query.stranded) || (h->excl.n && active_excl(h).stranded));
     const int excl = excl_kind(h);
+    if (h->groups_ok && !P.permute && !P.dst_tile && !(h->tune_stream_old)) {  // tile-group form (bootstrap kinds)
+        if (st && has_query) launch_stream_t<true, true>(h, P, excl);
+        else if (st) launch_stream_t<true, false>(h, P, excl);
+        else if (has_query) launch_stream_t<false, true>(h, P, excl);
+        else launch_stream_t<false, false>(h, P, excl);
+        return 1;
+    }
     if (st && has_query) launch_count_t<true, true>(h, P, grid, excl);
     else if (st) launch_count_t<true, false>(h, P, grid, excl);
     else if (has_query) launch_count_t<false, true>(h, P, grid, excl);

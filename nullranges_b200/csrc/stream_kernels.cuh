@@ -163,6 +163,228 @@ __global__ void __launch_bounds__(256) boot_count_kernel(const BootParams P) {
     }
 }
 
+// ---- the fused streaming kernel, tile-group form -------------------------------------------
+//
+// CTA = (iteration, group of up to kGroupTiles tiles that follow each other on one sequence).  The query features
+// within reach of those tiles are ONE contiguous slice of the canonical query arrays; an elected thread brings the
+// slice (start, end, running-max end, caller's position[, strand]) into shared memory with 1-D bulk asynchronous
+// copies (cp.async.bulk + mbarrier: the copy engine works while the CTA draws its blocks and locates their hit
+// windows), and the overlaps are tallied in a shared-memory histogram that leaves the CTA once, one atomic per
+// feature hit instead of one per overlap.  A warp takes a tile at a time and streams its hit window of y from the
+// interleaved {start, end} array: 16 bytes per lane, 64 ranges per load instruction; shift / trim / drop / exclude
+// per range as in the reference (R/bootUnsegmented.R:175-191, R/bootRanges.R:106-116).  The 64 ranges of a load
+// are neighbours on the genome, so the features they can reach are narrowed once per warp (two searches of the
+// shared slice for the warp's smallest start and largest end) and every lane tests only those.
+// Bootstrap kinds only (block b lands on tile b); the permute variants and slices that do not fit keep
+// boot_count_kernel.
+constexpr int kGroupTiles = 16;    // tiles per CTA at most
+constexpr int kMaxSlice = 2048;    // features of a group's slice at most (shared memory: 21 bytes per feature)
+
+struct TileGroup {
+    int32_t first, count;   // tiles_sorted[first .. first + count): tile indices, ascending start on one sequence
+    int32_t q_lo, q_hi;     // the group's slice of the canonical query, both multiples of 16 (16-byte aligned copies of every column)
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_copy_g2s(void *dst, const void *src, uint32_t bytes, unsigned long long *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)), "l"(src),
+                 "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, uint32_t parity) {
+    uint32_t done = 0;
+    while (!done)
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n"
+            : "=r"(done)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+}
+
+struct GroupView {
+    const TileGroup *groups;
+    const int32_t *tiles_sorted;
+    const int2 *se;            // y as interleaved {start, end}, canonical order
+    int slice_cap;             // features the shared-memory arrays hold (a multiple of 4)
+};
+
+template <bool STRANDED, bool HAS_QUERY, int EXCL>
+__global__ void __launch_bounds__(256) boot_stream_kernel(const BootParams P, const GroupView V) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ __align__(8) unsigned long long bar;
+    const int cap = V.slice_cap;
+    int32_t *s_start = reinterpret_cast<int32_t *>(smem_raw);
+    int32_t *s_end = s_start + cap, *s_pmax = s_end + cap, *s_src = s_pmax + cap;
+    int *s_hist = s_src + cap;
+    int8_t *s_strand = reinterpret_cast<int8_t *>(s_hist + cap);
+    const int lane = threadIdx.x & (kWarp - 1), warp = threadIdx.x / kWarp;
+    const TileGroup grp = V.groups[blockIdx.x];
+    const int64_t r = blockIdx.y;
+    const int n_slice = grp.q_hi - grp.q_lo;             // a multiple of 16 (the arrays carry that much slack at their ends)
+    const bool stage = HAS_QUERY && n_slice > 0;
+    if (stage) {
+        if (threadIdx.x == 0) mbar_init(&bar, 1);
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const uint32_t bytes = (uint32_t)n_slice * 4u;
+            const bool with_strand = STRANDED && P.query.strand;
+            mbar_expect_tx(&bar, 4u * bytes + (with_strand ? (uint32_t)n_slice : 0u));
+            bulk_copy_g2s(s_start, P.query.start + grp.q_lo, bytes, &bar);
+            bulk_copy_g2s(s_end, P.query.end + grp.q_lo, bytes, &bar);
+            bulk_copy_g2s(s_pmax, P.query.pmax + grp.q_lo, bytes, &bar);
+            bulk_copy_g2s(s_src, P.query.src + grp.q_lo, bytes, &bar);
+            if (with_strand) bulk_copy_g2s(s_strand, P.query.strand + grp.q_lo, (uint32_t)n_slice, &bar);
+        }
+        for (int k = threadIdx.x; k < n_slice; k += blockDim.x) s_hist[k] = 0;  // generic-proxy writes to a region the copies do not touch
+    }
+    unsigned long long overlaps_warp = 0;
+    // every warp draws its first block and locates its hit window while the copies are in flight
+    const int warps = blockDim.x / kWarp;
+    int j = warp;
+    int32_t t = 0;
+    Item it{};
+    if (j < grp.count) {
+        t = __ldg(V.tiles_sorted + grp.first + j);
+        it = load_item(P, r, t);
+    }
+    if (stage) mbar_wait(&bar, 0);  // the slice has landed (every thread observes the phase itself)
+    __syncthreads();                // ... and the histogram is zeroed
+    for (; j < grp.count; j += warps) {
+        if (j != warp) {
+            t = __ldg(V.tiles_sorted + grp.first + j);
+            it = load_item(P, r, t);
+        }
+        int32_t q_lo = 0, q_hi = 0, x_lo = 0, x_hi = 0;
+        if (HAS_QUERY) {
+            q_lo = __ldg(P.query.tile_lo + t) - grp.q_lo;
+            q_hi = __ldg(P.query.tile_hi + t) - grp.q_lo;
+        }
+        if (EXCL == kExclTrim) {
+            x_lo = __ldg(P.excl.tile_lo + t);
+            x_hi = __ldg(P.excl.tile_hi + t);
+        }
+        int rows = 0, hits = 0, overlaps = 0;
+        for (int32_t base = it.lo & ~1; base < it.hi; base += 2 * kWarp) {
+            const int32_t i0 = base + 2 * lane;
+            int4 v = make_int4(0, 0, 0, 0);
+            if (i0 < it.hi) v = __ldg(reinterpret_cast<const int4 *>(V.se + i0));  // ranges i0 and i0 + 1 (the array is padded to an even length)
+            int32_t s2[2], e2[2];
+            bool keep[2];
+            int strand[2] = {0, 0};
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                const int32_t i = i0 + u;
+                const int32_t st = u ? v.z : v.x, en = u ? v.w : v.y;
+                const bool in = i >= it.lo && i < it.hi;
+                const bool hit = in && (P.permute ? (st >= it.bait_start) : (en >= it.bait_start));
+                hits += hit ? 1 : 0;
+                keep[u] = in && transform(P, it, st, en, s2[u], e2[u]);
+                if (keep[u] && STRANDED && P.y.strand) strand[u] = __ldg(P.y.strand + i);
+                if (EXCL == kExclDrop && keep[u] && excluded<STRANDED>(P.excl, it.tile, s2[u], e2[u], strand[u])) keep[u] = false;
+                if (EXCL == kExclTrim && keep[u] && e2[u] < s2[u]) keep[u] = false;  // a zero-width survivor overlaps no gap
+            }
+            if (EXCL == kExclTrim) {
+                // each range is cut to the gaps it overlaps: one row (and one piece to count) per overlap
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                    if (!keep[u]) continue;
+                    for (int32_t k = x_lo; k < x_hi; ++k) {
+                        const int32_t gs = __ldg(P.excl.start + k), ge = __ldg(P.excl.end + k);
+                        if (s2[u] > ge || e2[u] < gs) continue;
+                        ++rows;
+                        if (HAS_QUERY) {
+                            const int32_t ps = max(s2[u], gs), pe = min(e2[u], ge);
+                            for (int32_t q = q_lo; q < q_hi; ++q) {
+                                const int32_t qs = s_start[q], qe = s_end[q];
+                                if (ps > qe || pe < qs) continue;
+                                if (STRANDED && P.query.strand && !strands_match(strand[u], s_strand[q])) continue;
+                                if (P.minoverlap > 0 && min(pe, qe) - max(ps, qs) + 1 < P.minoverlap) continue;
+                                ++overlaps;
+                                atomicAdd(&s_hist[q], 1);
+                            }
+                        }
+                    }
+                }
+                continue;
+            }
+            rows += (keep[0] ? 1 : 0) + (keep[1] ? 1 : 0);
+            if (HAS_QUERY && q_hi > q_lo) {
+                // features the warp's ranges can reach: start <= the largest end, running-max end >= the smallest start
+                const bool cnt0 = keep[0] && (e2[0] >= s2[0] || kZeroWidthStrictlyInside), cnt1 = keep[1] && (e2[1] >= s2[1] || kZeroWidthStrictlyInside);
+                const int32_t my_min = min(cnt0 ? s2[0] : INT32_MAX, cnt1 ? s2[1] : INT32_MAX);
+                const int32_t my_max = max(cnt0 ? e2[0] : INT32_MIN, cnt1 ? e2[1] : INT32_MIN);
+                const int32_t w_min = __reduce_min_sync(kFull, my_min), w_max = __reduce_max_sync(kFull, my_max);
+                if (w_max >= w_min || (kZeroWidthStrictlyInside && w_max != INT32_MIN)) {
+                    int32_t a = q_lo, b = q_hi;       // first feature with start > w_max
+                    while (a < b) {
+                        const int32_t m = (a + b) >> 1;
+                        if (s_start[m] <= w_max) a = m + 1; else b = m;
+                    }
+                    const int32_t hi_w = a;
+                    a = q_lo, b = hi_w;               // first feature whose running-max end reaches w_min
+                    while (a < b) {
+                        const int32_t m = (a + b) >> 1;
+                        if (s_pmax[m] < w_min) a = m + 1; else b = m;
+                    }
+                    for (int32_t q = a; q < hi_w; ++q) {
+                        const int32_t qs = s_start[q], qe = s_end[q];  // broadcast reads
+                        bool h0 = cnt0 && s2[0] <= qe && e2[0] >= qs, h1 = cnt1 && s2[1] <= qe && e2[1] >= qs;
+                        if (STRANDED && P.query.strand) {
+                            const int qst = s_strand[q];
+                            h0 = h0 && strands_match(strand[0], qst);
+                            h1 = h1 && strands_match(strand[1], qst);
+                        }
+                        if (P.minoverlap > 0) {
+                            h0 = h0 && min(e2[0], qe) - max(s2[0], qs) + 1 >= P.minoverlap;
+                            h1 = h1 && min(e2[1], qe) - max(s2[1], qs) + 1 >= P.minoverlap;
+                        }
+                        const int n = __popc(__ballot_sync(kFull, h0)) + __popc(__ballot_sync(kFull, h1));
+                        if (n && lane == 0) atomicAdd(&s_hist[q], n);
+                        overlaps += (lane == 0) ? n : 0;
+                    }
+                }
+            }
+        }
+        rows = __reduce_add_sync(kFull, rows);
+        hits = __reduce_add_sync(kFull, hits);
+        if (EXCL == kExclTrim) overlaps = __reduce_add_sync(kFull, overlaps);
+        else overlaps = __shfl_sync(kFull, overlaps, 0);
+        overlaps_warp += (unsigned)overlaps;
+        if (lane == 0) {
+            if (rows) atomicAdd(P.iter_nranges + r, (unsigned long long)rows);
+            if (P.item_rows) P.item_rows[r * P.n_blocks + t] = rows;
+            if (P.n_hits && hits) atomicAdd(P.n_hits + (r & (kHitSlots - 1)), (unsigned long long)hits);
+        }
+    }
+    if (HAS_QUERY) {
+        if (lane == 0 && overlaps_warp) atomicAdd(P.iter_totals + r, overlaps_warp);
+        if (stage) {
+            __syncthreads();
+            if (P.counts)
+                for (int k = threadIdx.x; k < n_slice; k += blockDim.x)
+                    if (s_hist[k]) atomicAdd(P.counts + r * P.n_query + s_src[k], s_hist[k]);
+        }
+    }
+}
+
+// y as interleaved {start, end} pairs (one 16-byte load = two ranges); one pad element at the end
+__global__ void interleave_ranges_kernel(const int32_t *__restrict__ start, const int32_t *__restrict__ end, int64_t n, int2 *__restrict__ se) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) se[i] = make_int2(start[i], end[i]);
+    else if (i == n) se[i] = make_int2(INT32_MAX, INT32_MIN);
+}
+
 // ---- materialising path ---------------------------------------------------------------
 
 // One CTA per iteration: exclusive scan of the rows-per-block of that iteration.
