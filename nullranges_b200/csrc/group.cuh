@@ -16,7 +16,9 @@
 namespace nrb {
 
 struct GroupPool {
-    int n_workers = 0;                      // members 1 .. n_workers
+    int n_workers = 0;                      // worker threads
+    int first = 1;                          // member driven by worker 0's thread (1: the caller drives member 0 itself; 0: workers drive all)
+    std::vector<std::vector<int>> cpus;     // per member: CPUs to bind its driver thread (and so its host team) to; empty = unbound
     std::vector<std::thread> threads;
     std::mutex mu;
     std::condition_variable cv;
@@ -33,6 +35,12 @@ struct GroupPool {
     }
 
     void worker(int k) {
+        if (k < (int)cpus.size() && !cpus[k].empty()) {  // before the thread's first parallel region: its host team inherits the mask
+            cpu_set_t set;
+            CPU_ZERO(&set);
+            for (int c : cpus[k]) CPU_SET(c, &set);
+            sched_setaffinity(0, sizeof set, &set);
+        }
         uint64_t seen = 0;
         for (;;) {
             // calls of one front-end step follow each other within microseconds: spin briefly before sleeping
@@ -57,13 +65,15 @@ struct GroupPool {
         }
     }
 
-    void start(int workers) {
-        n_workers = workers;
-        rc.assign((size_t)workers + 1, 0);
-        for (int k = 1; k <= workers; ++k) threads.emplace_back([this, k] { worker(k); });
+    // members: group size; caller_drives_first: member 0 runs on the calling thread (else every member has a worker)
+    void start(int members, bool caller_drives_first) {
+        first = caller_drives_first ? 1 : 0;
+        n_workers = members - first;
+        rc.assign((size_t)members, 0);
+        for (int k = first; k < members; ++k) threads.emplace_back([this, k] { worker(k); });
     }
 
-    // Runs fn(k) for k = 0 .. n_workers (k = 0 on the calling thread); returns when all are done.
+    // Runs fn(k) for every member k; returns when all are done.
     void run(const std::function<int(int)> &fn) {
         task = fn;
         pending.store(n_workers, std::memory_order_release);
@@ -72,7 +82,7 @@ struct GroupPool {
             generation.fetch_add(1, std::memory_order_acq_rel);
         }
         cv.notify_all();
-        rc[0] = fn(0);
+        if (first == 1) rc[0] = fn(0);
         for (int i = 0; pending.load(std::memory_order_acquire) > 0; ++i) {
             spin_pause();
             if ((i & 1023) == 1023) std::this_thread::yield();
@@ -157,16 +167,9 @@ int group_lead(nrb200_handle *g, const std::function<int(nrb200_handle *)> &fn) 
 
 // Before a run: the leader prepares first (it builds the window lists), the others then take its lists.  Nothing happens when no input changed since the last run.
 int group_prepare(nrb200_handle *g) {
-    nrb200_handle *lead = g->members[0];
-    NRB_CUDA(g, cudaSetDevice(lead->device));
-    // (with the leader's own share of the host threads: a larger team's idle threads would spin on the cores the other
-    // members' driver threads need right after)
-    const int rc = prepare(lead);
-    if (rc) {
-        g->error = "GPU " + std::to_string(lead->device) + ": " + lead->error;
-        return rc;
-    }
-    return NRB200_OK;
+    // (on the leader's own driver thread, with the leader's own share of the host threads: a larger team's idle threads
+    // would spin on the cores the other members' driver threads need right after)
+    return group_all(g, [](int k, nrb200_handle *m) { return k == 0 ? prepare(m) : NRB200_OK; });
 }
 
 int group_create(const nrb200_config *cfg, nrb200_handle **out) {
@@ -199,7 +202,62 @@ int group_create(const nrb200_config *cfg, nrb200_handle **out) {
         g->members.push_back(m);
     }
     g->pool = new GroupPool();
-    g->pool->start(W - 1);
+    // NUMA placement (NRB200_NUMA=0 turns it off): when the GPUs hang off different NUMA nodes, every member gets its own
+    // driver thread bound to the CPUs of its GPU's node, so that its host team, its pinned staging buffers and the pages
+    // it touches first sit next to the PCIe root its GPU uses.
+    const char *numa_env = getenv("NRB200_NUMA");
+    if (!numa_env || atoi(numa_env) != 0) {
+        std::vector<int> node((size_t)W, -1);
+        std::vector<std::vector<int>> cpus((size_t)W);
+        cpu_set_t allowed;
+        CPU_ZERO(&allowed);
+        sched_getaffinity(0, sizeof allowed, &allowed);
+        bool known = true;
+        for (int k = 0; k < W && known; ++k) {
+            char bus[32] = {0};
+            if (cudaDeviceGetPCIBusId(bus, sizeof bus, cfg->devices[k]) != cudaSuccess) { known = false; break; }
+            for (char *c = bus; *c; ++c) *c = (char)tolower(*c);
+            FILE *f = fopen((std::string("/sys/bus/pci/devices/") + bus + "/numa_node").c_str(), "r");
+            if (!f || fscanf(f, "%d", &node[k]) != 1 || node[k] < 0) known = false;
+            if (f) fclose(f);
+            if (!known) break;
+            f = fopen(("/sys/devices/system/node/node" + std::to_string(node[k]) + "/cpulist").c_str(), "r");
+            if (!f) { known = false; break; }
+            int a = 0, b = 0;
+            while (fscanf(f, "%d", &a) == 1) {  // "0-15,32-47"
+                b = a;
+                int ch = fgetc(f);
+                if (ch == '-') {
+                    if (fscanf(f, "%d", &b) != 1) break;
+                    ch = fgetc(f);
+                }
+                for (int c = a; c <= b && c < CPU_SETSIZE; ++c)
+                    if (CPU_ISSET(c, &allowed)) cpus[k].push_back(c);
+                if (ch != ',') break;
+            }
+            fclose(f);
+            if (cpus[k].empty()) known = false;
+        }
+        cudaGetLastError();
+        bool several = false;
+        for (int k = 1; k < W && known; ++k) several |= node[k] != node[0];
+        if (known && several) {
+            for (int k = 0; k < W; ++k) {
+                int sharing = 0;
+                for (int j = 0; j < W; ++j) sharing += node[j] == node[k];
+                // the members of one node split its CPUs among them
+                int rank_on_node = 0;
+                for (int j = 0; j < k; ++j) rank_on_node += node[j] == node[k];
+                const size_t per = std::max<size_t>(1, cpus[k].size() / (size_t)sharing);
+                std::vector<int> mine(cpus[k].begin() + std::min(cpus[k].size(), per * rank_on_node),
+                                      cpus[k].begin() + std::min(cpus[k].size(), per * (rank_on_node + 1)));
+                if (mine.empty()) mine = cpus[k];
+                g->members[k]->omp_threads = (int)mine.size();
+                g->pool->cpus.push_back(std::move(mine));
+            }
+        }
+    }
+    g->pool->start(W, g->pool->cpus.empty());
     *out = g;
     return NRB200_OK;
 }

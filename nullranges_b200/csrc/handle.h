@@ -4,6 +4,8 @@
 #include <algorithm>
 #include <chrono>
 #include <sys/mman.h>
+#include <sched.h>
+#include <cctype>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>

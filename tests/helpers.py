@@ -113,7 +113,7 @@ def brute_counts(case, rows):
     qs = q[3] if q[3] is not None else np.zeros(q[0].size, np.int8)
     counts = np.zeros(q[0].size, np.int64)
     for c, s, e, st in zip(*rows):
-        if e < s:
+        if e < s and not O.zero_width_rule():   # THE ZERO-WIDTH RULE (oracle/nr_oracle.c)
             continue
         m = (q[0] == c) & (q[1] <= e) & (q[2] >= s) & ((qs == 0) | (st == 0) | (qs == st))
         counts += m

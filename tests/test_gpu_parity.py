@@ -555,7 +555,14 @@ def test_weighted_sums(engine, kind, variant):
             engine.run_weighted(draws)
         return
     engine.set_weights(w)
-    got = engine.run_weighted(draws)
+    try:
+        got = engine.run_weighted(draws)
+    except EngineError as e:
+        # zero-width rule 1 (a development build, device_views.cuh): the rank path steps aside where the two rules differ,
+        # and the weighted statistic exists on the rank path only
+        if O.zero_width_rule() == 1 and kind in (1, 4) and "rank path" in str(e):
+            pytest.skip("zero-width rule 1: this input takes the streaming kernels, which have no weighted statistic")
+        raise
     ref = O.boot_weighted(plan, y, q, w, R, exclude=x, exclude_mode=H.excl_mode(case), draws=d, maxgap=case.get("maxgap", -1),
                           minoverlap=case.get("minoverlap", 0))
     scale = np.abs(w).sum()

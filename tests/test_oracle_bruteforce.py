@@ -10,6 +10,8 @@ import pytest
 from oracle import oracle as O
 from tests import helpers as H
 
+ZERO_WIDTH_RULE = O.zero_width_rule()
+
 
 def _compat(a, b):
     return (a == 0) | (b == 0) | (a == b)
@@ -62,12 +64,12 @@ def brute_iteration(case, kind, plan, bc, bs, dt):
                             end += 1
                         pieces.append((pos, end))
                         pos = end + 1
-            elif x is not None and e2 >= s2:
+            elif x is not None and (e2 >= s2 or ZERO_WIDTH_RULE):   # THE ZERO-WIDTH RULE (oracle/nr_oracle.c): 1 = plain test at width 0 too
                 if np.any((xc == tc) & (xs <= e2) & (xe >= s2) & _compat(ysd[i], xsd)):
                     continue
             for ps, pe in pieces:
                 rows.append((tc, ps, pe, i, b))
-                if pe >= ps:
+                if pe >= ps or (ZERO_WIDTH_RULE and mo == 0):
                     ov = np.minimum(pe, q[2]) - np.maximum(ps, q[1]) + 1
                     counts += (q[0] == tc) & (q[1] - m1 <= pe) & (q[2] + m1 >= ps) & _compat(ysd[i], qsd) & ((mo == 0) | (ov >= mo))
     return np.array(rows, np.int64).reshape(-1, 5), counts
