@@ -439,7 +439,7 @@ def run_gpu(args):
         traffic, traffic_src = None, None
         try:
             tj = json.load(open(os.path.join(ROOT, "profiles", "r02_traffic.json")))
-            traffic, traffic_src = tj.get("boot_rank_count_kernel", {}).get("dram_bytes_per_launch"), tj.get("source")
+            traffic, traffic_src = tj.get("boot_rank_loop_kernel", {}).get("dram_bytes_per_launch"), tj.get("source")
         except Exception:
             pass
         # CPU baseline: bounded sample on this box's cores

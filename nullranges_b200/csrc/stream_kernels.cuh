@@ -223,6 +223,8 @@ template <bool STRANDED, bool HAS_QUERY, int EXCL>
 __global__ void __launch_bounds__(256) boot_stream_kernel(const BootParams P, const GroupView V) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ __align__(8) unsigned long long bar;
+    __shared__ unsigned long long s_tally[3];  // rows, hits, overlaps of the CTA's tiles
+    if (threadIdx.x < 3) s_tally[threadIdx.x] = 0;
     const int cap = V.slice_cap;
     int32_t *s_start = reinterpret_cast<int32_t *>(smem_raw);
     int32_t *s_end = s_start + cap, *s_pmax = s_end + cap, *s_src = s_pmax + cap;
@@ -248,7 +250,7 @@ __global__ void __launch_bounds__(256) boot_stream_kernel(const BootParams P, co
         }
         for (int k = threadIdx.x; k < n_slice; k += blockDim.x) s_hist[k] = 0;  // generic-proxy writes to a region the copies do not touch
     }
-    unsigned long long overlaps_warp = 0;
+    unsigned long long overlaps_warp = 0, rows_warp = 0, hits_warp = 0;
     // every warp draws its first block and locates its hit window while the copies are in flight
     const int warps = blockDim.x / kWarp;
     int j = warp;
@@ -361,21 +363,26 @@ __global__ void __launch_bounds__(256) boot_stream_kernel(const BootParams P, co
         if (EXCL == kExclTrim) overlaps = __reduce_add_sync(kFull, overlaps);
         else overlaps = __shfl_sync(kFull, overlaps, 0);
         overlaps_warp += (unsigned)overlaps;
-        if (lane == 0) {
-            if (rows) atomicAdd(P.iter_nranges + r, (unsigned long long)rows);
-            if (P.item_rows) P.item_rows[r * P.n_blocks + t] = rows;
-            if (P.n_hits && hits) atomicAdd(P.n_hits + (r & (kHitSlots - 1)), (unsigned long long)hits);
-        }
+        rows_warp += (unsigned)rows;
+        hits_warp += (unsigned)hits;
+        if (lane == 0 && P.item_rows) P.item_rows[r * P.n_blocks + t] = rows;
     }
-    if (HAS_QUERY) {
-        if (lane == 0 && overlaps_warp) atomicAdd(P.iter_totals + r, overlaps_warp);
-        if (stage) {
-            __syncthreads();
-            if (P.counts)
-                for (int k = threadIdx.x; k < n_slice; k += blockDim.x)
-                    if (s_hist[k]) atomicAdd(P.counts + r * P.n_query + s_src[k], s_hist[k]);
-        }
+    // The per-iteration tallies leave the CTA once: all CTAs of an iteration add to the same three words, and atomics on
+    // one address serialise in the L2 (one per tile -- 5.76M per 1000 iterations at cfg 2 -- was what bounded this path).
+    if (lane == 0) {
+        if (rows_warp) atomicAdd(&s_tally[0], rows_warp);
+        if (hits_warp) atomicAdd(&s_tally[1], hits_warp);
+        if (overlaps_warp) atomicAdd(&s_tally[2], overlaps_warp);
     }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        if (s_tally[0]) atomicAdd(P.iter_nranges + r, s_tally[0]);
+        if (P.n_hits && s_tally[1]) atomicAdd(P.n_hits + (r & (kHitSlots - 1)), s_tally[1]);
+        if (HAS_QUERY && s_tally[2]) atomicAdd(P.iter_totals + r, s_tally[2]);
+    }
+    if (HAS_QUERY && stage && P.counts)
+        for (int k = threadIdx.x; k < n_slice; k += blockDim.x)
+            if (s_hist[k]) atomicAdd(P.counts + r * P.n_query + s_src[k], s_hist[k]);
 }
 
 // y as interleaved {start, end} pairs (one 16-byte load = two ranges); one pad element at the end

@@ -7,8 +7,8 @@ from nullranges_b200 import synth, Engine, Draws, _lib
 
 PEAK = json.load(open(os.path.join(os.path.dirname(__file__), "..", "MEASURED_PEAKS.json"))).get("hbm_gbs", 6650.0) if os.path.exists(
     os.path.join(os.path.dirname(__file__), "..", "MEASURED_PEAKS.json")) else 6650.0
-only = set(sys.argv[1:])
-force_stream = bool(int(os.environ.get("FORCE_STREAM", "0")))
+force_stream = bool(int(os.environ.get("FORCE_STREAM", "0"))) or "--stream" in sys.argv
+only = set(a for a in sys.argv[1:] if not a.startswith("--"))
 eng = Engine(0, force_stream=force_stream)
 
 
