@@ -83,6 +83,7 @@ int nrb200_set_ranges_begin(nrb200_handle *h, int64_t n, int32_t n_seq, const in
     if (!h) return NRB200_ERR_INVALID;
     if (is_group(h)) return group_set_ranges_begin(h, n, n_seq, seqlengths, seqid, start, end, strand);
     NRB_CUDA(h, cudaSetDevice(h->device));
+    NvtxRange nvtx("nrb200: upload y + inspect");
     h->y_pending = false;
     if (n_seq <= 0 || !seqlengths) return fail(h, NRB200_ERR_INVALID, "seqlengths(y) must be known");
     for (int c = 0; c < n_seq; ++c) {
@@ -110,6 +111,7 @@ int nrb200_set_ranges_end(nrb200_handle *h) {
     if (is_group(h)) return group_all(h, [](int, nrb200_handle *m) { return nrb200_set_ranges_end(m); });
     NRB_CUDA(h, cudaSetDevice(h->device));
     if (!h->y_pending) return fail(h, NRB200_ERR_STATE, "nrb200_set_ranges_begin() has not been called");
+    NvtxRange nvtx("nrb200: verdict + index build");
     h->y_pending = false;
     Trace tr("set_ranges_end");
     h->slices_dirty = true;
@@ -220,6 +222,7 @@ int nrb200_set_plan(nrb200_handle *h, const nrb200_plan_spec *spec, int64_t *n_b
     }
     NRB_CUDA(h, cudaSetDevice(h->device));
     if (!h->have_y && !h->y_pending) return fail(h, NRB200_ERR_STATE, "call nrb200_set_ranges() first (the plan needs seqlengths)");
+    NvtxRange nvtx("nrb200: plan");
     Plan p;
     const std::string msg = build_plan(*spec, h->seqlen, p);
     if (!msg.empty()) return fail(h, NRB200_ERR_INVALID, msg);

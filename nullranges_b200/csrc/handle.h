@@ -19,6 +19,7 @@
 #include <vector>
 
 #include <omp.h>
+#include <nvtx3/nvToolsExt.h>
 #if defined(__SSE2__)
 #include <emmintrin.h>
 #endif
@@ -31,6 +32,15 @@
 #include "plan.h"
 
 namespace nrb {
+
+// NVTX ranges around the stages of a call (upload, index build, window lists, chunks, drain): visible in Nsight
+// Systems / Compute timelines, no-ops when no tool is attached (NVTX3 is header-only).
+struct NvtxRange {
+    explicit NvtxRange(const char *name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+    NvtxRange(const NvtxRange &) = delete;
+    NvtxRange &operator=(const NvtxRange &) = delete;
+};
 
 struct GroupSpin {
     static void pause() {

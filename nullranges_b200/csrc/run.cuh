@@ -20,6 +20,7 @@ bool rank_path_ok(const nrb200_handle *h) {
 // its classes: the window lists of the rank path, the per-tile slices of the streaming kernels.
 int prepare_lists(nrb200_handle *h) {
     int rc;
+    NvtxRange nvtx("nrb200: window lists");
     Trace tr("prepare");
     h->tiles_in_bounds = true;
     for (int64_t t = 0; t < h->plan.n_blocks(); ++t)
@@ -345,6 +346,7 @@ int run_counts_core(nrb200_handle *h, const nrb200_draws *d, bool want_counts, i
                     nrb200_stats *stats) {
     int rc;
     if ((rc = prepare(h))) return rc;
+    NvtxRange nvtx("nrb200: run (chunks)");
     h->timeline.mark("lists ready", h->stream);
     NRB_CUDA(h, cudaEventRecord(h->ev[0], h->stream));
     if ((rc = stage_draws(h, d))) return rc;
@@ -482,6 +484,7 @@ int run_counts_core(nrb200_handle *h, const nrb200_draws *d, bool want_counts, i
     // (uint16 -> int32) or copies its slice of the chunk and moves on to the next -- no fork / join per chunk.
     std::vector<size_t> redo;  // wire16: chunks whose overflow flag is up
     if (!staged.empty()) {
+        NvtxRange nvtx_drain("nrb200: drain staged chunks");
         std::atomic<int64_t> landed{-1};
         std::atomic<int> drain_err{0};
         const int64_t n_chunks = (int64_t)staged.size();

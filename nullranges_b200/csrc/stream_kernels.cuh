@@ -177,7 +177,7 @@ __global__ void __launch_bounds__(256) boot_count_kernel(const BootParams P) {
 // shared slice for the warp's smallest start and largest end) and every lane tests only those.
 // Bootstrap kinds only (block b lands on tile b); the permute variants and slices that do not fit keep
 // boot_count_kernel.
-constexpr int kGroupTiles = 16;    // tiles per CTA at most
+constexpr int kGroupTiles = 32;    // tiles per CTA at most (one lane of a warp draws each: <= 32)
 constexpr int kMaxSlice = 2048;    // features of a group's slice at most (shared memory: 21 bytes per feature)
 
 struct TileGroup {
@@ -224,6 +224,7 @@ __global__ void __launch_bounds__(256) boot_stream_kernel(const BootParams P, co
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ __align__(8) unsigned long long bar;
     __shared__ unsigned long long s_tally[3];  // rows, hits, overlaps of the CTA's tiles
+    __shared__ Item s_item[kGroupTiles];       // the group's blocks: drawn and located once, by one lane each
     if (threadIdx.x < 3) s_tally[threadIdx.x] = 0;
     const int cap = V.slice_cap;
     int32_t *s_start = reinterpret_cast<int32_t *>(smem_raw);
@@ -250,23 +251,16 @@ __global__ void __launch_bounds__(256) boot_stream_kernel(const BootParams P, co
         }
         for (int k = threadIdx.x; k < n_slice; k += blockDim.x) s_hist[k] = 0;  // generic-proxy writes to a region the copies do not touch
     }
-    unsigned long long overlaps_warp = 0, rows_warp = 0, hits_warp = 0;
-    // every warp draws its first block and locates its hit window while the copies are in flight
-    const int warps = blockDim.x / kWarp;
-    int j = warp;
-    int32_t t = 0;
-    Item it{};
-    if (j < grp.count) {
-        t = __ldg(V.tiles_sorted + grp.first + j);
-        it = load_item(P, r, t);
-    }
+    // While the copy engine works: lane j of the last warp draws block j of the group and locates its hit window
+    // (Philox + pick + two rank probes: ~275 instructions that 32 lanes would otherwise repeat for every tile).
+    if (warp == blockDim.x / kWarp - 1 && lane < grp.count) s_item[lane] = load_item(P, r, __ldg(V.tiles_sorted + grp.first + lane));
     if (stage) mbar_wait(&bar, 0);  // the slice has landed (every thread observes the phase itself)
-    __syncthreads();                // ... and the histogram is zeroed
-    for (; j < grp.count; j += warps) {
-        if (j != warp) {
-            t = __ldg(V.tiles_sorted + grp.first + j);
-            it = load_item(P, r, t);
-        }
+    __syncthreads();                // ... the histogram is zeroed and the items are in place
+    unsigned long long overlaps_warp = 0, rows_warp = 0, hits_warp = 0;
+    const bool want_hits = P.n_hits != nullptr;
+    for (int j = warp; j < grp.count; j += blockDim.x / kWarp) {
+        const Item it = s_item[j];
+        const int32_t t = it.tile;
         int32_t q_lo = 0, q_hi = 0, x_lo = 0, x_hi = 0;
         if (HAS_QUERY) {
             q_lo = __ldg(P.query.tile_lo + t) - grp.q_lo;
@@ -276,6 +270,9 @@ __global__ void __launch_bounds__(256) boot_stream_kernel(const BootParams P, co
             x_lo = __ldg(P.excl.tile_lo + t);
             x_hi = __ldg(P.excl.tile_hi + t);
         }
+        // the features the warp's current ranges can reach, [w_lo, w_hi) of the shared slice: the ranges come in ascending
+        // start order, so both ends only move forward (w_hi may run ahead: every lane tests exactly)
+        int32_t w_lo = q_lo, w_hi = q_lo;
         int rows = 0, hits = 0, overlaps = 0;
         for (int32_t base = it.lo & ~1; base < it.hi; base += 2 * kWarp) {
             const int32_t i0 = base + 2 * lane;
@@ -288,11 +285,21 @@ __global__ void __launch_bounds__(256) boot_stream_kernel(const BootParams P, co
             for (int u = 0; u < 2; ++u) {
                 const int32_t i = i0 + u;
                 const int32_t st = u ? v.z : v.x, en = u ? v.w : v.y;
-                const bool in = i >= it.lo && i < it.hi;
-                const bool hit = in && (P.permute ? (st >= it.bait_start) : (en >= it.bait_start));
-                hits += hit ? 1 : 0;
-                keep[u] = in && transform(P, it, st, en, s2[u], e2[u]);
-                if (keep[u] && STRANDED && P.y.strand) strand[u] = __ldg(P.y.strand + i);
+                // bootstrap kinds: every range of the window starts at or before the block's end; a hit also ends at or after its start
+                const bool hit = i >= it.lo && i < it.hi && en >= it.bait_start;
+                if (want_hits) hits += hit ? 1 : 0;
+                s2[u] = st + it.shift;
+                e2[u] = en + it.shift;
+                keep[u] = hit;
+                if (s2[u] > it.seq_len) {       // wholly beyond the sequence end -> [L + 1, L]
+                    if (P.drop_zero) keep[u] = false;
+                    s2[u] = it.seq_len + 1;
+                    e2[u] = it.seq_len;
+                } else {
+                    s2[u] = max(s2[u], 1);
+                    e2[u] = min(e2[u], it.seq_len);
+                }
+                if (STRANDED && keep[u] && P.y.strand) strand[u] = __ldg(P.y.strand + i);
                 if (EXCL == kExclDrop && keep[u] && excluded<STRANDED>(P.excl, it.tile, s2[u], e2[u], strand[u])) keep[u] = false;
                 if (EXCL == kExclTrim && keep[u] && e2[u] < s2[u]) keep[u] = false;  // a zero-width survivor overlaps no gap
             }
@@ -322,24 +329,14 @@ __global__ void __launch_bounds__(256) boot_stream_kernel(const BootParams P, co
             }
             rows += (keep[0] ? 1 : 0) + (keep[1] ? 1 : 0);
             if (HAS_QUERY && q_hi > q_lo) {
-                // features the warp's ranges can reach: start <= the largest end, running-max end >= the smallest start
                 const bool cnt0 = keep[0] && (e2[0] >= s2[0] || kZeroWidthStrictlyInside), cnt1 = keep[1] && (e2[1] >= s2[1] || kZeroWidthStrictlyInside);
                 const int32_t my_min = min(cnt0 ? s2[0] : INT32_MAX, cnt1 ? s2[1] : INT32_MAX);
                 const int32_t my_max = max(cnt0 ? e2[0] : INT32_MIN, cnt1 ? e2[1] : INT32_MIN);
                 const int32_t w_min = __reduce_min_sync(kFull, my_min), w_max = __reduce_max_sync(kFull, my_max);
-                if (w_max >= w_min || (kZeroWidthStrictlyInside && w_max != INT32_MIN)) {
-                    int32_t a = q_lo, b = q_hi;       // first feature with start > w_max
-                    while (a < b) {
-                        const int32_t m = (a + b) >> 1;
-                        if (s_start[m] <= w_max) a = m + 1; else b = m;
-                    }
-                    const int32_t hi_w = a;
-                    a = q_lo, b = hi_w;               // first feature whose running-max end reaches w_min
-                    while (a < b) {
-                        const int32_t m = (a + b) >> 1;
-                        if (s_pmax[m] < w_min) a = m + 1; else b = m;
-                    }
-                    for (int32_t q = a; q < hi_w; ++q) {
+                if (w_max != INT32_MIN) {
+                    while (w_hi < q_hi && s_start[w_hi] <= w_max) ++w_hi;                  // features starting at or before the largest end
+                    while (w_lo < w_hi && s_pmax[w_lo] < w_min) ++w_lo;                    // ... whose running-max end reaches the smallest start
+                    for (int32_t q = w_lo; q < w_hi; ++q) {
                         const int32_t qs = s_start[q], qe = s_end[q];  // broadcast reads
                         bool h0 = cnt0 && s2[0] <= qe && e2[0] >= qs, h1 = cnt1 && s2[1] <= qe && e2[1] >= qs;
                         if (STRANDED && P.query.strand) {
@@ -359,7 +356,7 @@ __global__ void __launch_bounds__(256) boot_stream_kernel(const BootParams P, co
             }
         }
         rows = __reduce_add_sync(kFull, rows);
-        hits = __reduce_add_sync(kFull, hits);
+        if (want_hits) hits = __reduce_add_sync(kFull, hits);
         if (EXCL == kExclTrim) overlaps = __reduce_add_sync(kFull, overlaps);
         else overlaps = __shfl_sync(kFull, overlaps, 0);
         overlaps_warp += (unsigned)overlaps;
@@ -367,8 +364,7 @@ __global__ void __launch_bounds__(256) boot_stream_kernel(const BootParams P, co
         hits_warp += (unsigned)hits;
         if (lane == 0 && P.item_rows) P.item_rows[r * P.n_blocks + t] = rows;
     }
-    // The per-iteration tallies leave the CTA once: all CTAs of an iteration add to the same three words, and atomics on
-    // one address serialise in the L2 (one per tile -- 5.76M per 1000 iterations at cfg 2 -- was what bounded this path).
+    // The per-iteration tallies leave the CTA once: all CTAs of an iteration add to the same three words.
     if (lane == 0) {
         if (rows_warp) atomicAdd(&s_tally[0], rows_warp);
         if (hits_warp) atomicAdd(&s_tally[1], hits_warp);
