@@ -65,6 +65,8 @@ SYMBOLS = [
     ("nrb200_run_counts", C.c_int, [vp, C.POINTER(Draws), i64p, i64p, i32p, C.POINTER(Stats)]),
     ("nrb200_run_counts_resident", C.c_int, [vp, C.POINTER(Draws), C.c_int32, C.POINTER(Stats)]),
     ("nrb200_resident_pointers", C.c_int, [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]),
+    ("nrb200_run_counts_gathered", C.c_int, [vp, C.POINTER(Draws), C.POINTER(Stats)]),
+    ("nrb200_gathered_pointers", C.c_int, [vp, C.c_int32, i32p, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]),
     ("nrb200_moments_reset", C.c_int, [vp]),
     ("nrb200_run_moments", C.c_int, [vp, C.POINTER(Draws), C.c_int64, i32p, i64p, i64p, C.POINTER(Stats)]),
     ("nrb200_moments_fetch", C.c_int, [vp, i64p, i64p, i64p]),

@@ -338,6 +338,29 @@ int nrb200_resident_pointers(const nrb200_handle *h, void **iter_nranges_dev, vo
     return NRB200_OK;
 }
 
+int nrb200_run_counts_gathered(nrb200_handle *h, const nrb200_draws *draws, nrb200_stats *stats) {
+    if (!h) return NRB200_ERR_INVALID;
+    if (is_group(h)) return group_run_counts_gathered(h, draws, stats);
+    return nrb200_run_counts_resident(h, draws, 1, stats);  // one GPU: gathered is resident
+}
+
+int nrb200_gathered_pointers(const nrb200_handle *h, int32_t member, int32_t *device, void **iter_nranges_dev, void **iter_totals_dev,
+                             void **feature_counts_dev) {
+    if (!h) return NRB200_ERR_INVALID;
+    if (!is_group(h)) {
+        if (member != 0) return NRB200_ERR_INVALID;
+        if (device) *device = h->device;
+        return nrb200_resident_pointers(h, iter_nranges_dev, iter_totals_dev, feature_counts_dev);
+    }
+    if (member < 0 || member >= group_size(h)) return NRB200_ERR_INVALID;
+    const nrb200_handle *m = h->members[member];
+    if (device) *device = m->device;
+    if (iter_nranges_dev) *iter_nranges_dev = m->gat_nranges.p;
+    if (iter_totals_dev) *iter_totals_dev = m->gat_totals.p;
+    if (feature_counts_dev) *feature_counts_dev = m->gat_counts.p;
+    return NRB200_OK;
+}
+
 int nrb200_run_counts(nrb200_handle *h, const nrb200_draws *draws, int64_t *iter_nranges, int64_t *iter_totals,
                       int32_t *feature_counts, nrb200_stats *stats) {
     if (!h) return NRB200_ERR_INVALID;

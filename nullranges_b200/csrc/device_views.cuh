@@ -11,6 +11,7 @@ namespace nrb {
 
 
 constexpr int kWarp = 32;
+constexpr int kMaxPeers = 16;  // GPUs of a device group whose count kernels store into each other's memory
 constexpr unsigned kFull = 0xffffffffu;
 
 // ---- THE ZERO-WIDTH RULE (one named constant; the oracle carries the same one, oracle/nr_oracle.c) -------------
@@ -97,6 +98,10 @@ struct BootParams {
     int32_t *counts;          // [n_iter x n_query], caller's query order, or nullptr
     unsigned short *counts16; // the same as uint16 (rank path; takes precedence), with one overflow flag for the launch
     int *overflow16;
+    // device group, gathered result: the rows of this GPU's iterations are stored into the [R x n_query] matrix of EVERY
+    // member (peer-mapped pointers over NVLink, this GPU's own included), already offset to this launch's first row
+    int n_peers;
+    int32_t *peer_counts[kMaxPeers];
     int32_t *item_rows;       // [n_iter x n_blocks] surviving rows per item, or nullptr
     unsigned long long *n_hits;  // [kHitSlots] partial sums of the ranges sampled (byte-model H), slot = iteration % kHitSlots
     int2 *draw_tab;           // [n_iter x n_blocks] {bait seq, bait start}: rank path scratch

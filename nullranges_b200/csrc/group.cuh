@@ -433,4 +433,75 @@ int group_run_weighted_moments(nrb200_handle *g, const nrb200_draws *d, const do
     return NRB200_OK;
 }
 
+// ---- gathered result: every member ends up with the whole [R x G] matrix in ITS memory ---------------------------
+// SURVEY 8e's "ncclAllGather of the [R/W x G] tiles", without a collective after the kernels: the count kernel of GPU k
+// stores every count of its iterations into the matrices of all W members (peer-mapped pointers, NVLink 5 through the
+// NVSwitch), so the transfer happens tile by tile under the computation; a last small kernel spreads the
+// per-iteration vectors.  The call returns when every member's stream has drained: all matrices are complete.
+int group_enable_peers(nrb200_handle *g) {
+    if (g->peers_enabled) return NRB200_OK;
+    const int W = group_size(g);
+    if (W > kMaxPeers) return fail(g, NRB200_ERR_UNSUPPORTED, "a gathered result supports at most 16 GPUs");
+    for (int a = 0; a < W; ++a) {
+        NRB_CUDA(g, cudaSetDevice(g->members[a]->device));
+        for (int b = 0; b < W; ++b) {
+            if (a == b || g->members[a]->device == g->members[b]->device) continue;
+            int can = 0;
+            NRB_CUDA(g, cudaDeviceCanAccessPeer(&can, g->members[a]->device, g->members[b]->device));
+            if (!can) return fail(g, NRB200_ERR_UNSUPPORTED, "the GPUs of this group cannot address each other's memory (no peer access)");
+            const cudaError_t e = cudaDeviceEnablePeerAccess(g->members[b]->device, 0);
+            if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) NRB_CUDA(g, e);
+            cudaGetLastError();
+        }
+    }
+    g->peers_enabled = true;
+    return NRB200_OK;
+}
+
+int group_run_counts_gathered(nrb200_handle *g, const nrb200_draws *d, nrb200_stats *stats) {
+    if (!d || d->n_iter < 0) return fail(g, NRB200_ERR_INVALID, "draws: n_iter must be >= 0");
+    int rc;
+    if ((rc = group_enable_peers(g))) return rc;
+    if ((rc = group_prepare(g))) return rc;
+    const int W = group_size(g);
+    const int64_t R = d->n_iter, G = g->members[0]->query.n;
+    if (G == 0) return fail(g, NRB200_ERR_STATE, "a gathered result needs a query (nrb200_set_query)");
+    rc = group_all(g, [&](int, nrb200_handle *m) {  // every member makes room for the whole result
+        NRB_CUDA(m, cudaSetDevice(m->device));
+        NRB_CUDA(m, m->gat_counts.reserve((size_t)std::max<int64_t>(R * G, 1) * 4));
+        NRB_CUDA(m, m->gat_nranges.reserve((size_t)std::max<int64_t>(R, 1) * 8));
+        NRB_CUDA(m, m->gat_totals.reserve((size_t)std::max<int64_t>(R, 1) * 8));
+        m->gat_R = R;
+        m->gat_G = G;
+        return NRB200_OK;
+    });
+    if (rc) return rc;
+    std::vector<nrb200_stats> st((size_t)W);
+    rc = group_all(g, [&](int k, nrb200_handle *m) {
+        int64_t lo, n;
+        const nrb200_draws s = shard_draws(g, d, k, lo, n);
+        m->peer_out.n = W;
+        PeerVectors V{};
+        V.n = W;
+        for (int w = 0; w < W; ++w) {
+            m->peer_out.counts[w] = g->members[w]->gat_counts.as<int32_t>() + lo * G;
+            V.nranges[w] = g->members[w]->gat_nranges.as<unsigned long long>() + lo;
+            V.totals[w] = g->members[w]->gat_totals.as<unsigned long long>() + lo;
+        }
+        NRB_CUDA(m, cudaSetDevice(m->device));
+        int rc2 = run_counts_core(m, &s, true, nullptr, stats ? &st[k] : nullptr);
+        m->peer_out.n = 0;
+        if (rc2) return rc2;
+        if (n > 0) {
+            broadcast_iteration_vectors_kernel<<<(unsigned)std::min<int64_t>((n + 255) / 256, 64), 256, 0, m->stream>>>(
+                m->d_iter_nranges.as<unsigned long long>(), m->d_iter_totals.as<unsigned long long>(), n, V);
+            NRB_CUDA(m, cudaGetLastError());
+        }
+        return sync_stream(m);
+    });
+    if (rc) return rc;
+    merge_stats(stats, st);
+    return NRB200_OK;
+}
+
 }  // namespace

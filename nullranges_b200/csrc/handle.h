@@ -305,6 +305,14 @@ struct nrb200_handle {
     int64_t moments_G = 0;  // features the moment buffers were sized (and zeroed) for
     // rows
     DevMem item_rec, item_rows, within_off, iter_off_dev, row_seq, row_start, row_end, row_src, row_block;
+    // device group, gathered result (group.cuh): every member holds the full [R x G] matrix and [R] vectors
+    DevMem gat_counts, gat_nranges, gat_totals;
+    int64_t gat_R = 0, gat_G = 0;
+    struct PeerOut {
+        int n = 0;
+        int32_t *counts[kMaxPeers] = {};
+    } peer_out;                       // set by the group around a gathered run of this member
+    bool peers_enabled = false;       // group handle: every pair of members can store into each other's memory
     int64_t n_rows = 0;
     int64_t dst_tile_items = 0;  // [iterations x blocks] the last run left in d_dst_tile (permute kinds)
 };

@@ -251,6 +251,9 @@ __global__ void __launch_bounds__(kCountThreads, MINB) boot_rank_loop_kernel(con
             } else if (P.counts16) {
                 __stcs(P.counts16 + (r0 + k) * P.n_query + src, (unsigned short)min(cnt, 65535));
                 if (cnt > 65535) atomicOr(P.overflow16, 1);
+            } else if (P.n_peers > 0) {  // the tile goes straight into every member's matrix: the all-gather IS the kernel's store
+                const int64_t at = (r0 + k) * P.n_query + src;
+                for (int w = 0; w < P.n_peers; ++w) __stcs(P.peer_counts[w] + at, cnt);
             } else if (P.counts) {
                 __stcs(P.counts + (r0 + k) * P.n_query + src, cnt);
             }
@@ -265,6 +268,22 @@ __global__ void __launch_bounds__(kCountThreads, MINB) boot_rank_loop_kernel(con
         if (m_sum) atomicAdd(reinterpret_cast<unsigned long long *>(M.sum + src), (unsigned long long)m_sum);
         if (m_sq) atomicAdd(reinterpret_cast<unsigned long long *>(M.sumsq + src), (unsigned long long)m_sq);
         if (m_ge) atomicAdd(reinterpret_cast<unsigned long long *>(M.n_ge + src), (unsigned long long)m_ge);
+    }
+}
+
+// Device group, gathered result: this GPU's slices of the per-iteration vectors into every member's vectors.
+struct PeerVectors {
+    int n;
+    unsigned long long *nranges[kMaxPeers], *totals[kMaxPeers];  // already offset to this GPU's first iteration
+};
+__global__ void broadcast_iteration_vectors_kernel(const unsigned long long *__restrict__ nranges, const unsigned long long *__restrict__ totals,
+                                                   int64_t n, const PeerVectors V) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const unsigned long long a = nranges[i], b = totals[i];
+        for (int w = 0; w < V.n; ++w) {
+            V.nranges[w][i] = a;
+            V.totals[w][i] = b;
+        }
     }
 }
 

@@ -261,7 +261,7 @@ int launch_rank(nrb200_handle *h, const BootParams &P, bool has_query) {
         const FeatView F{h->f_src.as<int32_t>(), h->pair_off.as<int32_t>(), h->pair_rec.as<int4>()};
         const int rpt = h->tune_rpt;
         const dim3 grid((unsigned)((P.n_query + kCountThreads - 1) / kCountThreads), (unsigned)((P.n_iter + rpt - 1) / rpt));
-        if (h->tune_ipt > 1) {  // a thread stays on its feature for several iterations
+        if (h->tune_ipt > 1 || P.n_peers > 0) {  // a thread stays on its feature for several iterations
             // as many iterations per thread as leave a few CTAs per resident slot
             const int ipt = (int)std::max<int64_t>(1, std::min<int64_t>(h->tune_ipt, (int64_t)grid.x * P.n_iter / ((int64_t)h->sm_count * 16 * 3)));
             const dim3 lgrid(grid.x, (unsigned)((P.n_iter + ipt - 1) / ipt));
@@ -309,6 +309,7 @@ BootParams slice_params(const BootParams &P, int64_t r0, int64_t n) {
     if (P.iter_totals) Q.iter_totals = P.iter_totals + r0;
     if (P.counts) Q.counts = P.counts + r0 * P.n_query;
     if (P.counts16) Q.counts16 = P.counts16 + r0 * P.n_query;
+    for (int w = 0; w < P.n_peers; ++w) Q.peer_counts[w] = P.peer_counts[w] + r0 * P.n_query;
     if (P.item_rows) Q.item_rows = P.item_rows + r0 * P.n_blocks;
     if (P.item_rec) Q.item_rec = P.item_rec + r0 * P.n_blocks;
     return Q;
@@ -389,6 +390,9 @@ int run_counts_core(nrb200_handle *h, const nrb200_draws *d, bool want_counts, i
         NRB_CUDA(h, cudaMemsetAsync(flags_dev, 0, kChunkEvents * sizeof(int), h->stream));
         if (!h->flags_host) NRB_CUDA(h, cudaMallocHost((void **)&h->flags_host, kChunkEvents * sizeof(int)));
         std::memset(h->flags_host, 0, kChunkEvents * sizeof(int));
+    } else if (want_counts && !host_counts && h->peer_out.n > 0) {
+        if (!rank_path_ok(h)) return fail(h, NRB200_ERR_UNSUPPORTED, "the gathered result of a device group needs the rank path");
+        // gathered run of a device group: the kernel stores into every member's matrix, nothing local
     } else if (want_counts) {
         NRB_CUDA(h, h->d_counts.reserve(cells * sizeof(int32_t)));
         counts = h->d_counts.as<int32_t>();
@@ -400,6 +404,10 @@ int run_counts_core(nrb200_handle *h, const nrb200_draws *d, bool want_counts, i
     P.iter_totals = h->d_iter_totals.as<unsigned long long>();
     P.counts = counts;
     P.counts16 = counts16;
+    if (want_counts && !host_counts && !counts && !counts16) {
+        P.n_peers = h->peer_out.n;
+        for (int w = 0; w < P.n_peers; ++w) P.peer_counts[w] = h->peer_out.counts[w];
+    }
     P.n_hits = stats ? h->d_n_hits.as<unsigned long long>() : nullptr;  // the H statistic is tallied only when it is asked for
     NRB_CUDA(h, cudaEventRecord(h->ev[1], h->stream));
     int launches = 0;

@@ -15,6 +15,7 @@ struct Item {
     int32_t shift;             // tile_start - bait_start       (block_shift, :179)
     int32_t seq_len;           // seqlengths[tile_seq]
     int32_t lo, hi;            // hit window in canonical y
+    int32_t q_lo, q_hi, x_lo, x_hi;  // boot_stream_kernel only: the tile's query / exclude candidates
 };
 
 __device__ __forceinline__ Item load_item(const BootParams &P, int64_t r, int64_t b) {
@@ -178,6 +179,7 @@ __global__ void __launch_bounds__(256) boot_count_kernel(const BootParams P) {
 // Bootstrap kinds only (block b lands on tile b); the permute variants and slices that do not fit keep
 // boot_count_kernel.
 constexpr int kGroupTiles = 32;    // tiles per CTA at most (one lane of a warp draws each: <= 32)
+constexpr int kStreamMinBlocks = 5; // resident CTAs per SM the stream kernel is compiled for (<= 51 registers: no spills)
 constexpr int kMaxSlice = 2048;    // features of a group's slice at most (shared memory: 21 bytes per feature)
 
 struct TileGroup {
@@ -220,7 +222,7 @@ struct GroupView {
 };
 
 template <bool STRANDED, bool HAS_QUERY, int EXCL>
-__global__ void __launch_bounds__(256) boot_stream_kernel(const BootParams P, const GroupView V) {
+__global__ void __launch_bounds__(256, kStreamMinBlocks) boot_stream_kernel(const BootParams P, const GroupView V) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ __align__(8) unsigned long long bar;
     __shared__ unsigned long long s_tally[3];  // rows, hits, overlaps of the CTA's tiles
@@ -253,7 +255,19 @@ __global__ void __launch_bounds__(256) boot_stream_kernel(const BootParams P, co
     }
     // While the copy engine works: lane j of the last warp draws block j of the group and locates its hit window
     // (Philox + pick + two rank probes: ~275 instructions that 32 lanes would otherwise repeat for every tile).
-    if (warp == blockDim.x / kWarp - 1 && lane < grp.count) s_item[lane] = load_item(P, r, __ldg(V.tiles_sorted + grp.first + lane));
+    if (warp == blockDim.x / kWarp - 1 && lane < grp.count) {
+        Item it = load_item(P, r, __ldg(V.tiles_sorted + grp.first + lane));
+        it.q_lo = it.q_hi = it.x_lo = it.x_hi = 0;
+        if (HAS_QUERY) {
+            it.q_lo = __ldg(P.query.tile_lo + it.tile) - grp.q_lo;
+            it.q_hi = __ldg(P.query.tile_hi + it.tile) - grp.q_lo;
+        }
+        if (EXCL == kExclTrim) {
+            it.x_lo = __ldg(P.excl.tile_lo + it.tile);
+            it.x_hi = __ldg(P.excl.tile_hi + it.tile);
+        }
+        s_item[lane] = it;
+    }
     if (stage) mbar_wait(&bar, 0);  // the slice has landed (every thread observes the phase itself)
     __syncthreads();                // ... the histogram is zeroed and the items are in place
     unsigned long long overlaps_warp = 0, rows_warp = 0, hits_warp = 0;
@@ -261,23 +275,19 @@ __global__ void __launch_bounds__(256) boot_stream_kernel(const BootParams P, co
     for (int j = warp; j < grp.count; j += blockDim.x / kWarp) {
         const Item it = s_item[j];
         const int32_t t = it.tile;
-        int32_t q_lo = 0, q_hi = 0, x_lo = 0, x_hi = 0;
-        if (HAS_QUERY) {
-            q_lo = __ldg(P.query.tile_lo + t) - grp.q_lo;
-            q_hi = __ldg(P.query.tile_hi + t) - grp.q_lo;
-        }
-        if (EXCL == kExclTrim) {
-            x_lo = __ldg(P.excl.tile_lo + t);
-            x_hi = __ldg(P.excl.tile_hi + t);
-        }
+        const int32_t q_lo = it.q_lo, q_hi = it.q_hi, x_lo = it.x_lo, x_hi = it.x_hi;
         // the features the warp's current ranges can reach, [w_lo, w_hi) of the shared slice: the ranges come in ascending
         // start order, so both ends only move forward (w_hi may run ahead: every lane tests exactly)
         int32_t w_lo = q_lo, w_hi = q_lo;
         int rows = 0, hits = 0, overlaps = 0;
+        // ranges i0 and i0 + 1 per lane and trip (the array is padded to an even length); the next trip's load is issued
+        // before this trip's ranges are worked on
+        int4 v_next = make_int4(0, 0, 0, 0);
+        if ((it.lo & ~1) + 2 * lane < it.hi) v_next = __ldg(reinterpret_cast<const int4 *>(V.se + (it.lo & ~1) + 2 * lane));
         for (int32_t base = it.lo & ~1; base < it.hi; base += 2 * kWarp) {
             const int32_t i0 = base + 2 * lane;
-            int4 v = make_int4(0, 0, 0, 0);
-            if (i0 < it.hi) v = __ldg(reinterpret_cast<const int4 *>(V.se + i0));  // ranges i0 and i0 + 1 (the array is padded to an even length)
+            const int4 v = v_next;
+            if (i0 + 2 * kWarp < it.hi) v_next = __ldg(reinterpret_cast<const int4 *>(V.se + i0 + 2 * kWarp));
             int32_t s2[2], e2[2];
             bool keep[2];
             int strand[2] = {0, 0};

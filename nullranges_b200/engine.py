@@ -181,6 +181,20 @@ class Engine:
         self._check(self._lib.nrb200_run_counts_resident(self._h, C.byref(d), int(want_counts), C.byref(st) if want_stats else None))
         return st.as_dict() if want_stats else None
 
+    def run_counts_gathered(self, draws: Draws, want_stats: bool = True) -> dict | None:
+        """Device group: every GPU ends up with the whole [R, G] matrix and [R] vectors in its own memory (the count
+        kernels store into each other's memory over NVLink); see gathered_pointers()."""
+        st = _lib.Stats()
+        d = draws.to_c()
+        self._check(self._lib.nrb200_run_counts_gathered(self._h, C.byref(d), C.byref(st) if want_stats else None))
+        return st.as_dict() if want_stats else None
+
+    def gathered_pointers(self, member: int):
+        """(device ordinal, iter_nranges ptr, iter_totals ptr, feature_counts ptr) of a member's copy of the gathered result."""
+        dev, a, b, c = C.c_int32(), C.c_void_p(), C.c_void_p(), C.c_void_p()
+        self._check(self._lib.nrb200_gathered_pointers(self._h, int(member), C.byref(dev), C.byref(a), C.byref(b), C.byref(c)))
+        return dev.value, a.value, b.value, c.value
+
     def resident_pointers(self):
         a, b, c = C.c_void_p(), C.c_void_p(), C.c_void_p()
         self._check(self._lib.nrb200_resident_pointers(self._h, C.byref(a), C.byref(b), C.byref(c)))

@@ -21,7 +21,40 @@ from nullranges_b200.sharding import allreduce_moments, gather_count_matrix, gat
 ap = argparse.ArgumentParser()
 ap.add_argument("--config", type=int, default=4)
 ap.add_argument("--iters", type=int, default=0)
+ap.add_argument("--group", type=int, default=0, help="cfg 2 in ONE process through a device-group handle of this many GPUs: "
+                "nrb200_run_counts_gathered, the count kernels store their tiles into every member's matrix over NVLink")
 args = ap.parse_args()
+if args.group:
+    # ---- cfg 2, strong scaling, device-resident consumers: R = 1000 iterations sharded over the group, every GPU ends
+    # up with the whole [R x 20k] matrix.  No collective: the all-gather is the count kernel's store (peer pointers).
+    from nullranges_b200.sharding import DeviceView
+    R = args.iters or 1000
+    y, x = synth.atac_peaks(1_000_000, seed=3), synth.genes(20_000, seed=2)
+    G = len(x)
+    eng = Engine(list(range(args.group)) if args.group > 1 else 0)
+    eng.set_ranges(y.seqlengths, y.seqid, y.start, y.end)
+    eng.set_query(x.seqid, x.start, x.end)
+    eng.set_plan(_lib.UNSEG_ACROSS, 500_000)
+    for s_ in range(3):
+        eng.run_counts_gathered(Draws(n_iter=R, seed=100 + s_), want_stats=False)
+    times, kernel_ms = [], []
+    for s_ in range(10):
+        t0 = time.perf_counter()
+        st = eng.run_counts_gathered(Draws(n_iter=R, seed=s_), want_stats=True)   # returns when every member's stream has drained
+        times.append(time.perf_counter() - t0)
+        kernel_ms.append(st["kernel_ms"])
+    chks = []
+    for k in range(max(args.group, 1)):
+        d, _, _, cnt_p = eng.gathered_pointers(k)
+        full = torch.as_tensor(DeviceView(cnt_p, (R, G), "<i4"), device=f"cuda:{d}")
+        chks.append([int(full.sum()), int((full.to(torch.int64) * torch.arange(1, G + 1, device=full.device)).sum() % (1 << 61))])
+    ms = 1e3 * sorted(times)[len(times) // 2]
+    print(json.dumps({"config": "cfg2 R=1000 sharded over a device group, [R x 20k] matrix on every GPU (stored by the count kernels over NVLink)",
+                      "n_gpus": max(args.group, 1), "iters": R, "ms_per_1000_iterations_wall_median": ms, "ms_wall_min": 1e3 * min(times),
+                      "iters_per_s": R / ms * 1e3, "slowest_gpu_kernel_ms_median": sorted(kernel_ms)[len(kernel_ms) // 2],
+                      "matrix_bytes": R * G * 4, "checksum": chks[0], "members_agree": all(c == chks[0] for c in chks)}))
+    eng.close()
+    sys.exit(0)
 world, rank, local = int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0))
 torch.cuda.set_device(local)
 if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
