@@ -437,7 +437,7 @@ int nrb200_run_moments(nrb200_handle *h, const nrb200_draws *draws, int64_t batc
             launches += launch_rank(h, Q, false);  // draws + rows per iteration
             const unsigned gx = (unsigned)((G + kCountThreads - 1) / kCountThreads);
             const int ipt = (int)std::max<int64_t>(1, std::min<int64_t>(kLoopMaxIpt, (int64_t)gx * Q.n_iter / ((int64_t)h->sm_count * 16 * 3)));
-            boot_rank_loop_kernel<true, 12><<<dim3(gx, (unsigned)((Q.n_iter + ipt - 1) / ipt)), kCountThreads, 0, h->stream>>>(Q, F, ipt, M);
+            boot_rank_loop_kernel<true, 10><<<dim3(gx, (unsigned)((Q.n_iter + ipt - 1) / ipt)), kCountThreads, 0, h->stream>>>(Q, F, ipt, M);
             ++launches;
             NRB_CUDA(h, cudaGetLastError());
         }

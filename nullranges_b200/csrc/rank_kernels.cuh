@@ -199,13 +199,13 @@ struct MomentsOut {
 constexpr int kLoopMaxIpt = 64;
 template <bool MOMENTS, int MINB>
 __global__ void __launch_bounds__(kCountThreads, MINB) boot_rank_loop_kernel(const BootParams P, const FeatView F, int ipt, const MomentsOut M) {
-    __shared__ int s_tot[kLoopMaxIpt];
+    __shared__ int s_tot[kCountThreads / 32][kLoopMaxIpt];  // per-iteration totals, one row per warp (plain adds by lane 0)
     const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t r0 = (int64_t)blockIdx.y * ipt;
     const int n_it = (int)min((int64_t)ipt, P.n_iter - r0);
-    for (int k = threadIdx.x; k < n_it; k += kCountThreads) s_tot[k] = 0;
-    __syncthreads();
-    const int lane = threadIdx.x & 31;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int k = lane; k < n_it; k += 32) s_tot[warp][k] = 0;
+    __syncwarp();
     int32_t src = 0, p0 = 0, p1 = 0;
     if (g < P.n_query) {
         src = __ldg(F.src + g);
@@ -216,10 +216,12 @@ __global__ void __launch_bounds__(kCountThreads, MINB) boot_rank_loop_kernel(con
     int4 rec0 = make_int4(0, 0, 0, 0);
     int2 ti0 = make_int2(0, 0), d_next = make_int2(0, 0);
     const int2 *__restrict__ tab = P.draw_tab + r0 * P.n_blocks;
+    const int2 *__restrict__ dp = tab;  // the first window's draw of the current iteration; advances by one row per iteration
     if (any) {
         rec0 = __ldg(F.rec + p0);
         ti0 = __ldg(P.tile_info + rec_tile(rec0.x));
-        d_next = __ldg(tab + rec_tile(rec0.x));
+        dp += rec_tile(rec0.x);
+        d_next = __ldg(dp);
     }
     long long m_sum = 0, m_sq = 0;
     int m_ge = 0;
@@ -229,7 +231,8 @@ __global__ void __launch_bounds__(kCountThreads, MINB) boot_rank_loop_kernel(con
         int cnt = 0;
         if (any) {
             const int2 d = d_next;
-            if (k + 1 < n_it) d_next = __ldg(tab + (int64_t)(k + 1) * P.n_blocks + rec_tile(rec0.x));
+            dp += P.n_blocks;
+            if (k + 1 < n_it) d_next = __ldg(dp);
             const int c0 = P.permute ? count_pair<true>(P.y, d, rec_cls(rec0.x), ti0.x, rec0.w, ti0.y, rec0.y, rec0.z)
                                      : count_pair<false>(P.y, d, rec_cls(rec0.x), ti0.x, rec0.w, ti0.y, rec0.y, rec0.z);
             cnt = rec_sign(rec0.x) * c0;
@@ -259,11 +262,15 @@ __global__ void __launch_bounds__(kCountThreads, MINB) boot_rank_loop_kernel(con
             }
         }
         const int s = __reduce_add_sync(kFull, cnt);
-        if (lane == 0 && s) atomicAdd(&s_tot[k], s);
+        if (lane == 0) s_tot[warp][k] += s;
     }
     __syncthreads();
-    for (int k = threadIdx.x; k < n_it; k += kCountThreads)
-        if (s_tot[k]) atomicAdd(P.iter_totals + r0 + k, (unsigned long long)(unsigned)s_tot[k]);
+    for (int k = threadIdx.x; k < n_it; k += kCountThreads) {
+        unsigned long long t = 0;
+#pragma unroll
+        for (int w = 0; w < kCountThreads / 32; ++w) t += (unsigned)s_tot[w][k];
+        if (t) atomicAdd(P.iter_totals + r0 + k, t);
+    }
     if (MOMENTS && live) {
         if (m_sum) atomicAdd(reinterpret_cast<unsigned long long *>(M.sum + src), (unsigned long long)m_sum);
         if (m_sq) atomicAdd(reinterpret_cast<unsigned long long *>(M.sumsq + src), (unsigned long long)m_sq);
