@@ -382,6 +382,12 @@ def run_gpu(args):
                 "feature_counts": torch.empty((Rt, G), dtype=torch.int32, pin_memory=True)}
         out_np = {k: v.numpy() for k, v in outs.items()}
         t_pin, res_pin = timed(lambda s_: bootCounts(y_pin, x_pin, L_B, R=Rt, rng="philox", seed=2024, iter0=s_ * Rt, gpus=gpus, out=out_np))
+        # (c) the same into a pinned uint16 matrix (nrb200_run_counts_u16): for callers that can take the counts as uint16
+        out16 = dict(out_np)
+        keep16 = torch.empty((Rt, G), dtype=torch.uint16, pin_memory=True)
+        out16["feature_counts"] = keep16.numpy()
+        t_u16, res_u16 = timed(lambda s_: bootCounts(y_pin, x_pin, L_B, R=Rt, rng="philox", seed=2024, iter0=s_ * Rt, gpus=gpus, out=out16,
+                                                     counts_dtype=np.uint16))
         last = 2 + e2e_steps - 1
         assert int(res_pg.feature_counts.sum()) == int(res_pg.iter_totals.sum())
         # result check 2: the device group's matrix == one GPU's matrix, for the first R iterations of the last step
@@ -403,8 +409,13 @@ def run_gpu(args):
                                                "the difference is the kernel zeroing and mapping the fresh pages"},
                "e2e_pinned": {"value": Rt / t_pin, "unit": "iter/s", "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": int(res_pin.stats["d2h_bytes"]),
                               "steps": e2e_steps, "ms_per_step": 1e3 * t_pin, "buffers": "pinned inputs and pinned preallocated outputs (int32 on the wire)"}}
+        e2e["e2e_pinned_uint16"] = {"value": Rt / t_u16, "unit": "iter/s", "d2h_bytes_per_step": int(res_u16.stats["d2h_bytes"]), "ms_per_step": 1e3 * t_u16,
+                                    "buffers": "pinned inputs, pinned uint16 result (bootCounts(..., counts_dtype = uint16)): half the bytes into host memory; "
+                                               "not what an R caller gets (R's integer is 32-bit) -- reported beside the headline, not as it",
+                                    "overflow": bool(res_u16.stats.get("overflow", False))}
         assert np.array_equal(res_fresh.feature_counts, res_pg.feature_counts)
-        del res_fresh
+        assert np.array_equal(res_u16.feature_counts, res_pg.feature_counts)
+        del res_fresh, res_u16
         del res_pg, res_pin, one
     host_barrier()
 

@@ -206,6 +206,13 @@ typedef struct nrb200_stats {
 int nrb200_run_counts(nrb200_handle *h, const nrb200_draws *draws, int64_t *iter_nranges,
                       int64_t *iter_totals, int32_t *feature_counts, nrb200_stats *stats);
 
+/* The same with the count matrix delivered as uint16 -- half the bytes over PCIe and into host memory, for callers
+ * whose counts fit (overlaps per feature and iteration: cfg 2's mean is 15).  A count above 65535 is stored as 65535
+ * and *overflow is set: call nrb200_run_counts() then.  Rank path only (NRB200_ERR_UNSUPPORTED otherwise).  An R
+ * caller keeps nrb200_run_counts(): R's integer is 32-bit. */
+int nrb200_run_counts_u16(nrb200_handle *h, const nrb200_draws *draws, int64_t *iter_nranges, int64_t *iter_totals,
+                          uint16_t *feature_counts, int32_t *overflow, nrb200_stats *stats);
+
 /* Same computation, results left in device memory owned by the handle (valid until the next
  * run or destroy).  want_feature_counts = 0 skips the [n_iter x n_query] matrix. */
 int nrb200_run_counts_resident(nrb200_handle *h, const nrb200_draws *draws,

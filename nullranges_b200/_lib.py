@@ -63,6 +63,7 @@ SYMBOLS = [
     ("nrb200_set_plan", C.c_int, [vp, C.POINTER(PlanSpec), i64p]),
     ("nrb200_get_tiles", C.c_int, [vp, i32p, i32p, i32p]),
     ("nrb200_run_counts", C.c_int, [vp, C.POINTER(Draws), i64p, i64p, i32p, C.POINTER(Stats)]),
+    ("nrb200_run_counts_u16", C.c_int, [vp, C.POINTER(Draws), i64p, i64p, C.POINTER(C.c_uint16), i32p, C.POINTER(Stats)]),
     ("nrb200_run_counts_resident", C.c_int, [vp, C.POINTER(Draws), C.c_int32, C.POINTER(Stats)]),
     ("nrb200_resident_pointers", C.c_int, [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]),
     ("nrb200_run_counts_gathered", C.c_int, [vp, C.POINTER(Draws), C.POINTER(Stats)]),

@@ -204,31 +204,35 @@ def bootCounts(y: GRanges, x: GRanges, blockLength, R: int = 1, seg: GRanges | N
                exclude: GRanges | None = None, excludeOption=("drop", "trim"), proportionLength: bool = True,
                type=("bootstrap", "permute"), withinChrom: bool = False, *, rng="philox", seed=None, iter0: int = 0,
                perFeature: bool = True, device=0, out: dict | None = None, maxgap: int = -1,
-               minoverlap: int = 0, weights: str | None = None, gpus=None) -> BootCounts:
+               minoverlap: int = 0, weights: str | None = None, gpus=None, counts_dtype=np.int32) -> BootCounts:
     """countOverlaps(x, bootRanges(y, ...), maxgap = , minoverlap = ) per iteration, fused on the GPU.
     weights: name of a numeric metadata column of y; adds its sum over the overlapping bootstrapped ranges per
     (iteration, feature) -- summarize(sum(signal)) of vignettes/bootRanges.Rmd:532-540.
     gpus: N (the first N GPUs of the box) or a list of ordinals: the R iterations are sharded over them
-    (replicate() at R/bootRanges.R:90 is R independent draws) and land in ONE result, bit-identical for every N."""
+    (replicate() at R/bootRanges.R:90 is R independent draws) and land in ONE result, bit-identical for every N.
+    counts_dtype: np.int32 (R's integer, the default) or np.uint16 -- half the bytes over PCIe and into host memory;
+    counts above 65535 are saturated and flagged in ``stats['overflow']``."""
     eng = get_engine(device, gpus)
     with eng.lock:
         return _boot_counts(eng, y, x, blockLength, R, seg, exclude, excludeOption, proportionLength, type, withinChrom, rng, seed,
-                            iter0, perFeature, out, maxgap, minoverlap, weights)
+                            iter0, perFeature, out, maxgap, minoverlap, weights, counts_dtype)
 
 
 def _boot_counts(eng, y, x, blockLength, R, seg, exclude, excludeOption, proportionLength, type, withinChrom, rng, seed, iter0,
-                 perFeature, out, maxgap, minoverlap, weights) -> BootCounts:
+                 perFeature, out, maxgap, minoverlap, weights, counts_dtype=np.int32) -> BootCounts:
     kind, L_b, segd, qkeep = _setup(eng, y, blockLength, seg, exclude, excludeOption, proportionLength, type, withinChrom,
                                     query=(x, maxgap, minoverlap))
     draws = _make_draws(eng, kind, int(R), y, L_b, segd, rng, seed, iter0)
     if out is not None and qkeep is not None:
         raise ValueError("out= needs every seqlevel of x to be a seqlevel of y")
-    res = eng.run_counts(draws, want_counts=perFeature, out=out)
+    res = eng.run_counts(draws, want_counts=perFeature, out=out, counts_dtype=counts_dtype)
+    if "overflow" in res:
+        res["stats"]["overflow"] = res["overflow"]
     fc = res["feature_counts"]
     if fc is None and perFeature:  # no feature lies on a sequence of y
-        fc = np.zeros((int(R), len(x)), np.int32)
+        fc = np.zeros((int(R), len(x)), counts_dtype)
     elif fc is not None and qkeep is not None:  # features on sequences y lacks count 0
-        full = np.zeros((int(R), len(x)), np.int32)
+        full = np.zeros((int(R), len(x)), fc.dtype)
         full[:, qkeep] = fc
         fc = full
     bc = BootCounts(res["iter_totals"], res["iter_nranges"], fc, res["stats"])

@@ -379,6 +379,26 @@ int nrb200_run_counts(nrb200_handle *h, const nrb200_draws *draws, int64_t *iter
     return NRB200_OK;
 }
 
+int nrb200_run_counts_u16(nrb200_handle *h, const nrb200_draws *draws, int64_t *iter_nranges, int64_t *iter_totals,
+                          uint16_t *feature_counts, int32_t *overflow, nrb200_stats *stats) {
+    if (!h || !feature_counts) return NRB200_ERR_INVALID;
+    if (is_group(h)) return group_run_counts_u16(h, draws, iter_nranges, iter_totals, feature_counts, overflow, stats);
+    NRB_CUDA(h, cudaSetDevice(h->device));
+    if (h->query.n == 0) return fail(h, NRB200_ERR_STATE, "nrb200_set_query() has not been called");
+    h->out16 = feature_counts;
+    int rc = run_counts_core(h, draws, true, nullptr, stats);
+    h->out16 = nullptr;
+    if (rc) return rc;
+    const int64_t R = draws->n_iter, G = h->query.n;
+    if ((rc = fetch_u64_as_i64(h, h->d_iter_nranges, R, iter_nranges))) return rc;
+    if ((rc = fetch_u64_as_i64(h, h->d_iter_totals, R, iter_totals))) return rc;
+    if (int rc_sync = sync_stream(h)) return rc_sync;
+    if (h->copy_stream) NRB_CUDA(h, cudaStreamSynchronize(h->copy_stream));
+    if (overflow) *overflow = h->out16_overflow;
+    if (stats) stats->d2h_bytes = (iter_nranges ? R * 8 : 0) + (iter_totals ? R * 8 : 0) + R * G * 2;
+    return NRB200_OK;
+}
+
 int nrb200_moments_reset(nrb200_handle *h) {
     if (!h) return NRB200_ERR_INVALID;
     if (is_group(h)) return group_all(h, [](int, nrb200_handle *m) { return nrb200_moments_reset(m); });

@@ -340,6 +340,29 @@ int group_run_counts(nrb200_handle *g, const nrb200_draws *d, int64_t *iter_nran
     return NRB200_OK;
 }
 
+int group_run_counts_u16(nrb200_handle *g, const nrb200_draws *d, int64_t *iter_nranges, int64_t *iter_totals, uint16_t *feature_counts,
+                         int32_t *overflow, nrb200_stats *stats) {
+    if (!d || d->n_iter < 0) return fail(g, NRB200_ERR_INVALID, "draws: n_iter must be >= 0");
+    int rc;
+    if ((rc = group_prepare(g))) return rc;
+    const int64_t G = g->members[0]->query.n;
+    std::vector<nrb200_stats> st((size_t)group_size(g));
+    std::vector<int32_t> ov((size_t)group_size(g), 0);
+    rc = group_all(g, [&](int k, nrb200_handle *m) {
+        int64_t lo, n;
+        const nrb200_draws s = shard_draws(g, d, k, lo, n);
+        return nrb200_run_counts_u16(m, &s, iter_nranges ? iter_nranges + lo : nullptr, iter_totals ? iter_totals + lo : nullptr,
+                                     feature_counts + lo * G, &ov[k], stats ? &st[k] : nullptr);
+    });
+    if (rc) return rc;
+    if (overflow) {
+        *overflow = 0;
+        for (int32_t v : ov) *overflow |= v;
+    }
+    merge_stats(stats, st);
+    return NRB200_OK;
+}
+
 int group_run_moments(nrb200_handle *g, const nrb200_draws *d, int64_t batch_iter, const int32_t *observed, int64_t *iter_nranges,
                       int64_t *iter_totals, nrb200_stats *stats) {
     if (!d || d->n_iter < 0) return fail(g, NRB200_ERR_INVALID, "draws: n_iter must be >= 0");

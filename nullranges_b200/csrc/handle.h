@@ -296,6 +296,8 @@ struct nrb200_handle {
     DevMem d_bait_seq, d_bait_start, d_dst_tile, perm_vals_a, perm_vals_b, np_seg, np_start, np_state, np_list, np_cnt;
     DevMem d_iter_nranges, d_iter_totals, d_counts, d_counts16, redo_scratch, d_n_hits;
     int *flags_host = nullptr;         // pinned: per-chunk overflow flags of the uint16 wire format
+    uint16_t *out16 = nullptr;         // set by nrb200_run_counts_u16 around its run: the caller's uint16 matrix
+    int out16_overflow = 0;            // ... some count did not fit (it was stored as 65535)
     bool last_wire16 = false;          // the last host-bound matrix travelled as uint16
     bool res_has_counts = false;
     // moments

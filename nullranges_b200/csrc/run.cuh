@@ -359,24 +359,32 @@ int run_counts_core(nrb200_handle *h, const nrb200_draws *d, bool want_counts, i
     NRB_CUDA(h, cudaMemsetAsync(h->d_iter_nranges.p, 0, R * 8, h->stream));
     NRB_CUDA(h, cudaMemsetAsync(h->d_iter_totals.p, 0, R * 8, h->stream));
     if ((rc = hits_reset(h))) return rc;
-    const bool pipelined = host_counts && want_counts && R > 0;
+    uint16_t *host16 = h->out16;  // nrb200_run_counts_u16: the caller takes the matrix as uint16 (saturating), no widening
+    h->out16 = nullptr;
+    h->out16_overflow = 0;
+    if (host16 && !rank_path_ok(h)) return fail(h, NRB200_ERR_UNSUPPORTED, "uint16 counts need the rank path (segmentation within seqlengths, no NRB200_FLAG_FORCE_STREAM)");
+    const bool pipelined = (host_counts || host16) && want_counts && R > 0;
     bool pageable = false;
     if (pipelined) {
         cudaPointerAttributes attr{};
-        pageable = cudaPointerGetAttributes(&attr, host_counts) != cudaSuccess || attr.type == cudaMemoryTypeUnregistered;
+        pageable = cudaPointerGetAttributes(&attr, host16 ? (const void *)host16 : (const void *)host_counts) != cudaSuccess || attr.type == cudaMemoryTypeUnregistered;
         cudaGetLastError();  // an unregistered pointer may leave a sticky-free error behind on older drivers
     }
     const size_t cells = (size_t)R * (size_t)std::max<int64_t>(G, 0);
     // tune_wire16: 0 never, 1 always, 2 (default) for pageable destinations only -- a pinned destination takes the
     // int32 matrix by DMA without any host work
     bool wire16 = pipelined && rank_path_ok(h) && cells * 2 <= kMaxStagingBytes && (h->tune_wire16 == 1 || (h->tune_wire16 == 2 && pageable));
-    if (wire16 && h->stage_cap < cells * 2) {
+    if (host16) wire16 = pipelined;
+    const bool stage16 = wire16 && !(host16 && !pageable);  // a pinned uint16 destination takes the chunks by DMA as they are
+    if (host16 && pageable && cells * 2 > kMaxStagingBytes) return fail(h, NRB200_ERR_UNSUPPORTED, "uint16 counts into pageable memory: the matrix exceeds the staging limit; use a pinned buffer or fewer iterations per call");
+    if (stage16 && h->stage_cap < cells * 2) {
         if (h->stage_buf) cudaFreeHost(h->stage_buf);
         h->stage_buf = nullptr;
         h->stage_cap = 0;
         if (cudaMallocHost((void **)&h->stage_buf, cells * 2) == cudaSuccess) h->stage_cap = cells * 2;
         else {
             cudaGetLastError();
+            if (host16) return fail(h, NRB200_ERR_NOMEM, "no pinned staging memory for the uint16 matrix");
             wire16 = false;
         }
     }
@@ -441,8 +449,8 @@ int run_counts_core(nrb200_handle *h, const nrb200_draws *d, bool want_counts, i
             if (h->stage_cap >= bytes) staging = static_cast<int32_t *>(h->stage_buf);
         }
     }
-    if (wire16 && pageable) advise_huge_pages(host_counts, cells * sizeof(int32_t));
-    uint16_t *staging16 = wire16 ? static_cast<uint16_t *>(h->stage_buf) : nullptr;
+    if (wire16 && pageable) advise_huge_pages(host16 ? (void *)host16 : (void *)host_counts, cells * (host16 ? 2 : 4));
+    uint16_t *staging16 = stage16 ? static_cast<uint16_t *>(h->stage_buf) : (wire16 ? host16 : nullptr);
     int k = 0;
     const bool split = stats && rank_path_ok(h);
     for (int64_t r0 = 0; r0 < R; r0 += chunk, ++k) {
@@ -478,7 +486,7 @@ int run_counts_core(nrb200_handle *h, const nrb200_draws *d, bool want_counts, i
                                             cudaMemcpyDeviceToHost, h->copy_stream));
             }
             h->timeline.mark("chunk copied out", h->copy_stream);
-            if (staging || wire16) {
+            if (staging || stage16) {
                 cudaEvent_t &done = h->copied_ev[k % kChunkEvents];
                 if (!done) NRB_CUDA(h, cudaEventCreateWithFlags(&done, cudaEventDisableTiming));
                 NRB_CUDA(h, cudaEventRecord(done, h->copy_stream));
@@ -507,9 +515,15 @@ int run_counts_core(nrb200_handle *h, const nrb200_draws *d, bool want_counts, i
                     const size_t elems = (size_t)staged[c].second * G;
                     const size_t per = ((elems + nth - 1) / nth + 15) & ~(size_t)15;
                     const size_t lo = std::min(elems, (size_t)tid * per), hi = std::min(elems, lo + per);
-                    volatile int32_t *dst = host_counts + staged[c].first * G;
-                    for (size_t i = lo; i < hi; i += 1024) dst[i] = 0;  // one store per 4 KB page
-                    if (hi > lo) dst[hi - 1] = 0;
+                    if (host16) {
+                        volatile uint16_t *dst = host16 + staged[c].first * G;
+                        for (size_t i = lo; i < hi; i += 2048) dst[i] = 0;  // one store per 4 KB page
+                        if (hi > lo) dst[hi - 1] = 0;
+                    } else {
+                        volatile int32_t *dst = host_counts + staged[c].first * G;
+                        for (size_t i = lo; i < hi; i += 1024) dst[i] = 0;
+                        if (hi > lo) dst[hi - 1] = 0;
+                    }
                 }
             }
             for (int64_t c = 0; c < n_chunks; ++c) {
@@ -521,19 +535,24 @@ int run_counts_core(nrb200_handle *h, const nrb200_draws *d, bool want_counts, i
                 }
                 if (drain_err.load()) continue;
                 const int64_t r0 = staged[c].first, n = staged[c].second;
-                if (wire16 && h->flags_host[c % kChunkEvents]) continue;  // redone in int32 below
+                if (wire16 && !host16 && h->flags_host[c % kChunkEvents]) continue;  // redone in int32 below
                 const size_t elems = (size_t)n * G;
                 const size_t per = ((elems + nth - 1) / nth + 15) & ~(size_t)15;
                 const size_t lo = std::min(elems, (size_t)tid * per), hi = std::min(elems, lo + per);
                 if (hi <= lo) continue;
-                if (wire16) widen_u16_to_i32(staging16 + r0 * G + lo, host_counts + r0 * G + lo, hi - lo);
+                if (host16) std::memcpy(host16 + r0 * G + lo, staging16 + r0 * G + lo, (hi - lo) * sizeof(uint16_t));
+                else if (wire16) widen_u16_to_i32(staging16 + r0 * G + lo, host_counts + r0 * G + lo, hi - lo);
                 else std::memcpy(host_counts + r0 * G + lo, staging + r0 * G + lo, (hi - lo) * sizeof(int32_t));
             }
         }
         if (drain_err.load()) return fail(h, NRB200_ERR_CUDA, "cudaEventSynchronize failed while draining the count matrix");
-        if (wire16)
+        if (wire16 && !host16)
             for (int64_t c = 0; c < n_chunks; ++c)
                 if (h->flags_host[c % kChunkEvents]) redo.push_back((size_t)c);
+    }
+    if (host16) {  // saturated counts are reported, not recomputed: the caller asked for uint16
+        NRB_CUDA(h, cudaStreamSynchronize(h->copy_stream));
+        for (int c = 0; c < kChunkEvents; ++c) h->out16_overflow |= h->flags_host[c];
     }
     if (!redo.empty()) {
         // some count exceeds 65535: those chunks again, with int32 output (the per-iteration vectors of the second pass go

@@ -152,11 +152,25 @@ class Engine:
         return ts, tt, bw
 
     # ---- fused counting
-    def run_counts(self, draws: Draws, want_counts: bool = True, out: dict | None = None) -> dict:
+    def run_counts(self, draws: Draws, want_counts: bool = True, out: dict | None = None, counts_dtype=np.int32) -> dict:
         """out: optional preallocated (e.g. pinned) C-contiguous result arrays keyed iter_nranges /
-        iter_totals [R] int64 and feature_counts [R, G] int32; every element is overwritten."""
+        iter_totals [R] int64 and feature_counts [R, G] int32; every element is overwritten.
+        counts_dtype=np.uint16: the matrix comes back as uint16 (nrb200_run_counts_u16: half the bytes over PCIe and into
+        host memory); result['overflow'] tells whether some count was saturated at 65535."""
         R, G = int(draws.n_iter), self.n_query
         out = out or {}
+        if np.dtype(counts_dtype) == np.uint16 and want_counts and G:
+            nr = out.get("iter_nranges", np.empty(R, np.int64))
+            tot = out.get("iter_totals", np.empty(R, np.int64))
+            cnt = out.get("feature_counts")
+            if cnt is None:
+                cnt = np.empty((R, G), np.uint16)
+            if cnt.shape != (R, G) or cnt.dtype != np.uint16 or not cnt.flags.c_contiguous:
+                raise ValueError("out['feature_counts'] must be C-contiguous uint16[R, G]")
+            st, ov, d = _lib.Stats(), C.c_int32(0), draws.to_c()
+            self._check(self._lib.nrb200_run_counts_u16(self._h, C.byref(d), ptr(nr, C.c_int64), ptr(tot, C.c_int64), ptr(cnt, C.c_uint16),
+                                                        C.byref(ov), C.byref(st)))
+            return {"iter_nranges": nr, "iter_totals": tot, "feature_counts": cnt, "overflow": bool(ov.value), "stats": st.as_dict()}
 
         def buf(key, shape, dtype):
             a = out.get(key)

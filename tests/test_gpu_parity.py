@@ -830,3 +830,37 @@ def test_wire_format_overflow_falls_back_to_int32():
             assert np.array_equal(got[k], ref[k]), k
     finally:
         eng.close()
+
+
+@pytest.mark.parametrize("pinned", [False, True])
+def test_uint16_result(pinned):
+    """nrb200_run_counts_u16: the matrix delivered as uint16 (pinned: DMA straight into the caller's buffer; pageable:
+    staged and copied by the drain team); saturation is flagged, not hidden."""
+    import torch
+    from nullranges_b200 import Engine
+    eng = Engine(0)
+    try:
+        case = H.random_case(seed=72, n=3000, n_seq=4, n_query=130, n_excl=10, n_seg=8)
+        plan, y, q, x = H.oracle_objects(case, 0)
+        H.load_engine(eng, case, 0)
+        R = 150
+        out = None
+        if pinned:
+            keep = torch.empty((R, 130), dtype=torch.uint16, pin_memory=True)
+            out = {"feature_counts": keep.numpy()}
+        got = eng.run_counts(Draws(n_iter=R, rng_mode=_lib.RNG_PHILOX, seed=12, iter0=40), out=out, counts_dtype=np.uint16)
+        ref = O.boot_counts(plan, y, q, R, exclude=x, seed=12, iter0=40)
+        assert got["feature_counts"].dtype == np.uint16 and not got["overflow"]
+        assert np.array_equal(got["feature_counts"], ref["feature_counts"]) and np.array_equal(got["iter_totals"], ref["iter_totals"])
+        assert got["stats"]["d2h_bytes"] == 2 * R * 8 + R * 130 * 2
+        # 70,000 ranges inside one feature: saturated and flagged; the totals stay exact
+        n = 70_000
+        sid = np.zeros(n, np.int32)
+        st = np.full(n, 100, np.int32)
+        big = {"seqlen": np.array([5000], np.int64), "y": (sid, st, st + 50, None), "excl": None, "seg": None, "L_b": 5000,
+               "query": (np.array([0, 0], np.int32), np.array([1, 2000], np.int32), np.array([1000, 3000], np.int32), None)}
+        H.load_engine(eng, big, 1)
+        got = eng.run_counts(Draws(n_iter=4, rng_mode=_lib.RNG_PHILOX, seed=1), counts_dtype=np.uint16)
+        assert got["overflow"] and got["feature_counts"].max() == 65535 and int(got["iter_totals"][0]) == n
+    finally:
+        eng.close()
