@@ -457,10 +457,11 @@ int group_run_weighted_moments(nrb200_handle *g, const nrb200_draws *d, const do
 }
 
 // ---- gathered result: every member ends up with the whole [R x G] matrix in ITS memory ---------------------------
-// SURVEY 8e's "ncclAllGather of the [R/W x G] tiles", without a collective after the kernels: the count kernel of GPU k
-// stores every count of its iterations into the matrices of all W members (peer-mapped pointers, NVLink 5 through the
-// NVSwitch), so the transfer happens tile by tile under the computation; a last small kernel spreads the
-// per-iteration vectors.  The call returns when every member's stream has drained: all matrices are complete.
+// SURVEY 8e's "ncclAllGather of the [R/W x G] tiles" without NCCL and without a second process: the count kernel of
+// GPU k writes the rows of its iterations into its own copy of the matrix, and a push kernel on the same stream
+// stores them into the copies of the other W - 1 members through peer-mapped pointers (NVLink 5 through the NVSwitch,
+// 16-byte coalesced stores); a last small kernel spreads the per-iteration vectors.  Every GPU pushes while the others
+// compute and push.  The call returns when every member's stream has drained: all matrices are complete.
 int group_enable_peers(nrb200_handle *g) {
     if (g->peers_enabled) return NRB200_OK;
     const int W = group_size(g);
@@ -503,19 +504,24 @@ int group_run_counts_gathered(nrb200_handle *g, const nrb200_draws *d, nrb200_st
     rc = group_all(g, [&](int k, nrb200_handle *m) {
         int64_t lo, n;
         const nrb200_draws s = shard_draws(g, d, k, lo, n);
-        m->peer_out.n = W;
+        // the count kernel writes this GPU's rows into its OWN copy of the matrix ...
+        m->peer_out.n = 1;
+        m->peer_out.counts[0] = m->gat_counts.as<int32_t>() + lo * G;
         PeerVectors V{};
-        V.n = W;
+        PeerTiles T{};
         for (int w = 0; w < W; ++w) {
-            m->peer_out.counts[w] = g->members[w]->gat_counts.as<int32_t>() + lo * G;
-            V.nranges[w] = g->members[w]->gat_nranges.as<unsigned long long>() + lo;
-            V.totals[w] = g->members[w]->gat_totals.as<unsigned long long>() + lo;
+            V.nranges[V.n] = g->members[w]->gat_nranges.as<unsigned long long>() + lo;
+            V.totals[V.n++] = g->members[w]->gat_totals.as<unsigned long long>() + lo;
+            if (w != k) T.dst[T.n++] = g->members[w]->gat_counts.as<int32_t>() + lo * G;
         }
         NRB_CUDA(m, cudaSetDevice(m->device));
         int rc2 = run_counts_core(m, &s, true, nullptr, stats ? &st[k] : nullptr);
         m->peer_out.n = 0;
         if (rc2) return rc2;
         if (n > 0) {
+            // ... and two small kernels spread the rows and the per-iteration vectors to the other members
+            if (T.n > 0)
+                push_tile_kernel<<<(unsigned)m->sm_count * 4, 256, 0, m->stream>>>(m->gat_counts.as<int32_t>() + lo * G, n * G, T);
             broadcast_iteration_vectors_kernel<<<(unsigned)std::min<int64_t>((n + 255) / 256, 64), 256, 0, m->stream>>>(
                 m->d_iter_nranges.as<unsigned long long>(), m->d_iter_totals.as<unsigned long long>(), n, V);
             NRB_CUDA(m, cudaGetLastError());

@@ -14,14 +14,8 @@ MB = 80  # per GPU per round, as one 1000-iteration shard of the cfg 2 count mat
 
 
 def numa_of_gpu(i):
-    try:
-        bus = torch.cuda.get_device_properties(i).pci_bus_id if hasattr(torch.cuda.get_device_properties(i), "pci_bus_id") else None
-    except Exception:
-        bus = None
-    if bus is None:
-        out = subprocess.run(["nvidia-smi", f"--id={i}", "--query-gpu=pci.bus_id", "--format=csv,noheader"], capture_output=True, text=True).stdout.strip()
-        bus = out
-    bus = bus.lower()
+    out = subprocess.run(["nvidia-smi", f"--id={i}", "--query-gpu=pci.bus_id", "--format=csv,noheader"], capture_output=True, text=True).stdout.strip()
+    bus = out.lower()
     if len(bus.split(":")[0]) == 8:
         bus = bus[4:]
     try:
