@@ -222,10 +222,10 @@ int nrb200_resident_pointers(const nrb200_handle *h, void **iter_nranges_dev,
 
 /* Device group, device-resident consumers: the same computation, and EVERY GPU of the group ends up with the whole
  * result in its own memory -- iter_nranges / iter_totals [n_iter] (uint64) and feature_counts [n_iter x n_query] (int32)
- * -- for work that continues on the GPUs.  This is SURVEY 8e's all-gather of the [R/W x G] tiles, fused into the count
- * kernel: GPU k stores the counts of its iterations straight into the matrices of all members over NVLink (peer
- * access is required), so the exchange runs under the computation instead of after it.  On a single-GPU handle it is
- * nrb200_run_counts_resident().  nrb200_gathered_pointers: member = 0 .. nrb200_n_devices(h) - 1; the pointers live on
+ * -- for work that continues on the GPUs.  This is SURVEY 8e's all-gather of the [R/W x G] tiles without a collective
+ * library or a second process: GPU k computes the rows of its iterations into its own copy of the matrix and pushes
+ * them into the copies of the other members with coalesced 16-byte stores over peer-mapped pointers (NVLink; peer
+ * access is required), all GPUs at once.  On a single-GPU handle it is nrb200_run_counts_resident().  nrb200_gathered_pointers: member = 0 .. nrb200_n_devices(h) - 1; the pointers live on
  * *device and stay valid until the group's next gathered run. */
 int nrb200_run_counts_gathered(nrb200_handle *h, const nrb200_draws *draws, nrb200_stats *stats);
 int nrb200_gathered_pointers(const nrb200_handle *h, int32_t member, int32_t *device, void **iter_nranges_dev,

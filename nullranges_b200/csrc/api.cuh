@@ -668,7 +668,7 @@ int nrb200_count_observed_ex(nrb200_handle *h, int32_t minoverlap, int32_t *feat
         if (rc0) return rc0;
     }
     const RangeSet &q = h->query;
-    DevMem counts, tot;
+    DevMem &counts = h->obs_counts, &tot = h->obs_total;  // handle-owned: no cudaMalloc / cudaFree per call
     NRB_CUDA(h, counts.reserve(q.n * 4));
     NRB_CUDA(h, tot.reserve(8));
     NRB_CUDA(h, cudaMemsetAsync(counts.p, 0, q.n * 4, h->stream));

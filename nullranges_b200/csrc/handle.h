@@ -301,7 +301,7 @@ struct nrb200_handle {
     bool last_wire16 = false;          // the last host-bound matrix travelled as uint16
     bool res_has_counts = false;
     // moments
-    DevMem m_sum, m_sumsq, m_nge, m_observed;
+    DevMem m_sum, m_sumsq, m_nge, m_observed, obs_counts, obs_total;
     DevMem wm_sum, wm_sumsq, wm_nge, wm_observed;  // moments of the weighted sums (double; n_ge int64)
     bool moments_ready = false;
     int64_t moments_G = 0;  // features the moment buffers were sized (and zeroed) for
