@@ -45,9 +45,9 @@ if _lws > 1 and os.environ.get("OMP_NUM_THREADS") == "1":
         _cores = len(os.sched_getaffinity(0))
     except AttributeError:
         _cores = os.cpu_count() or 1
-    # every rank may use all cores: the device-resident leg has next to no host work, and in the end-to-end leg only
-    # rank 0 works (it drives all N GPUs through one device-group handle; the other ranks sleep in a host barrier)
-    os.environ["OMP_NUM_THREADS"] = str(max(1, _cores))
+    # rank 0 may use all cores: in the end-to-end leg it alone works (it drives all N GPUs through one device-group handle
+    # while the other ranks sleep in a host barrier); the others keep to their share
+    os.environ["OMP_NUM_THREADS"] = str(max(1, _cores if os.environ.get("RANK", "0") == "0" else _cores // _lws))
 
 import numpy as np
 
@@ -388,6 +388,10 @@ def run_gpu(args):
         out16["feature_counts"] = keep16.numpy()
         t_u16, res_u16 = timed(lambda s_: bootCounts(y_pin, x_pin, L_B, R=Rt, rng="philox", seed=2024, iter0=s_ * Rt, gpus=gpus, out=out16,
                                                      counts_dtype=np.uint16))
+        # (d) the matrix-free statistic: per-feature mean / sd / empirical p of the same counts over the same R * N iterations,
+        # reduced on the GPUs (bootMoments: 3 * G * 8 bytes come back instead of R * G * 4) -- where the host does not bound the step
+        from nullranges_b200 import bootMoments
+        t_mom, res_mom = timed(lambda s_: bootMoments(y_pg, x_pg, L_B, R=Rt, rng="philox", seed=2024, iter0=s_ * Rt, gpus=gpus))
         last = 2 + e2e_steps - 1
         assert int(res_pg.feature_counts.sum()) == int(res_pg.iter_totals.sum())
         # result check 2: the device group's matrix == one GPU's matrix, for the first R iterations of the last step
@@ -413,9 +417,13 @@ def run_gpu(args):
                                     "buffers": "pinned inputs, pinned uint16 result (bootCounts(..., counts_dtype = uint16)): half the bytes into host memory; "
                                                "not what an R caller gets (R's integer is 32-bit) -- reported beside the headline, not as it",
                                     "overflow": bool(res_u16.stats.get("overflow", False))}
+        e2e["e2e_moments"] = {"value": Rt / t_mom, "unit": "iter/s", "ms_per_step": 1e3 * t_mom, "d2h_bytes_per_step": int(3 * G * 8 + 2 * Rt * 8),
+                              "api": "nullranges_b200.bootMoments(y, x, blockLength, R = 1000 * N, gpus = N): the same bootstrap and counts, reduced to per-feature "
+                                     "mean / sd / z / empirical p on the GPUs (no [R x G] matrix crosses PCIe)"}
+        assert np.array_equal(res_mom.sum, res_pg.feature_counts.sum(axis=0))  # the same counts, summed over the iterations
         assert np.array_equal(res_fresh.feature_counts, res_pg.feature_counts)
         assert np.array_equal(res_u16.feature_counts, res_pg.feature_counts)
-        del res_fresh, res_u16
+        del res_fresh, res_u16, res_mom
         del res_pg, res_pin, one
     host_barrier()
 

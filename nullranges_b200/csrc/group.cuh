@@ -169,6 +169,8 @@ int group_lead(nrb200_handle *g, const std::function<int(nrb200_handle *)> &fn) 
 int group_prepare(nrb200_handle *g) {
     // (on the leader's own driver thread, with the leader's own share of the host threads: a larger team's idle threads
     // would spin on the cores the other members' driver threads need right after)
+    const nrb200_handle *lead = g->members[0];
+    if (lead->have_y && lead->have_plan && !lead->slices_dirty) return NRB200_OK;  // nothing changed since the last run: no dispatch
     return group_all(g, [](int k, nrb200_handle *m) { return k == 0 ? prepare(m) : NRB200_OK; });
 }
 
@@ -490,7 +492,9 @@ int group_run_counts_gathered(nrb200_handle *g, const nrb200_draws *d, nrb200_st
     const int W = group_size(g);
     const int64_t R = d->n_iter, G = g->members[0]->query.n;
     if (G == 0) return fail(g, NRB200_ERR_STATE, "a gathered result needs a query (nrb200_set_query)");
-    rc = group_all(g, [&](int, nrb200_handle *m) {  // every member makes room for the whole result
+    bool sized = true;
+    for (int k = 0; k < W; ++k) sized = sized && g->members[k]->gat_R == R && g->members[k]->gat_G == G;
+    if (!sized) rc = group_all(g, [&](int, nrb200_handle *m) {  // every member makes room for the whole result
         NRB_CUDA(m, cudaSetDevice(m->device));
         NRB_CUDA(m, m->gat_counts.reserve((size_t)std::max<int64_t>(R * G, 1) * 4));
         NRB_CUDA(m, m->gat_nranges.reserve((size_t)std::max<int64_t>(R, 1) * 8));
@@ -526,7 +530,14 @@ int group_run_counts_gathered(nrb200_handle *g, const nrb200_draws *d, nrb200_st
                 m->d_iter_nranges.as<unsigned long long>(), m->d_iter_totals.as<unsigned long long>(), n, V);
             NRB_CUDA(m, cudaGetLastError());
         }
-        return sync_stream(m);
+        if (stats) NRB_CUDA(m, cudaEventRecord(m->ev[3], m->stream));
+        if (int rc3 = sync_stream(m)) return rc3;
+        if (stats) {  // device time of this member's whole step: draws, counts, push to the peers
+            float ms = 0;
+            cudaEventElapsedTime(&ms, m->ev[0], m->ev[3]);
+            st[k].total_ms = ms;
+        }
+        return NRB200_OK;
     });
     if (rc) return rc;
     merge_stats(stats, st);
