@@ -9,7 +9,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 SO = os.path.join(HERE, "libnrb200.so")
-SOURCES = ["engine.cu", "plan.cpp", "rrng.cpp"]
+SOURCES = ["engine.cu", "plan.cpp", "rrng.cpp", "host_simd.cpp"]
 HEADERS = ["kernels.cuh", "device_views.cuh", "stream_kernels.cuh", "rank_kernels.cuh", "index_kernels.cuh", "philox.cuh", "plan.h", "handle.h", "index.cuh", "lists.cuh", "run.cuh", "group.cuh", "api.cuh",
            os.path.join("..", "..", "include", "nrb200.h")]
 

@@ -33,6 +33,9 @@
 
 namespace nrb {
 
+void widen_u16_to_i32(const uint16_t *src, int32_t *dst, size_t n);  // host_simd.cpp
+const char *widen_variant();
+
 // NVTX ranges around the stages of a call (upload, index build, window lists, chunks, drain): visible in Nsight
 // Systems / Compute timelines, no-ops when no tool is attached (NVTX3 is header-only).
 struct NvtxRange {

@@ -315,25 +315,7 @@ BootParams slice_params(const BootParams &P, int64_t r0, int64_t n) {
     return Q;
 }
 
-// uint16 -> int32, written with streaming stores (the destination is not read again by this thread)
-inline void widen_u16_to_i32(const uint16_t *src, int32_t *dst, size_t n) {
-    size_t i = 0;
-#if defined(__SSE2__)
-    while (i < n && (reinterpret_cast<uintptr_t>(dst + i) & 15)) {
-        dst[i] = src[i];
-        ++i;
-    }
-    const __m128i zero = _mm_setzero_si128();
-    for (; i + 8 <= n; i += 8) {
-        const __m128i v = _mm_loadu_si128(reinterpret_cast<const __m128i *>(src + i));
-        _mm_stream_si128(reinterpret_cast<__m128i *>(dst + i), _mm_unpacklo_epi16(v, zero));
-        _mm_stream_si128(reinterpret_cast<__m128i *>(dst + i + 4), _mm_unpackhi_epi16(v, zero));
-    }
-    _mm_sfence();
-#endif
-    for (; i < n; ++i) dst[i] = src[i];
-}
-
+// uint16 -> int32 with streaming stores, AVX-512 / AVX2 / SSE2 chosen at run time: host_simd.cpp
 // Core of every counting entry point: results stay on the device.  With host_counts set, the
 // iterations run in chunks and each chunk of the [R x G] matrix starts its way to the host
 // (copy stream) while the next chunk computes.
