@@ -341,7 +341,8 @@ int nrb200_resident_pointers(const nrb200_handle *h, void **iter_nranges_dev, vo
 int nrb200_run_counts_gathered(nrb200_handle *h, const nrb200_draws *draws, nrb200_stats *stats) {
     if (!h) return NRB200_ERR_INVALID;
     if (is_group(h)) return group_run_counts_gathered(h, draws, stats);
-    return nrb200_run_counts_resident(h, draws, 1, stats);  // one GPU: gathered is resident
+    if (int rc = nrb200_run_counts_resident(h, draws, 1, stats)) return rc;  // one GPU: gathered is resident ...
+    return sync_stream(h);                                                    // ... and complete on return, as for a group
 }
 
 int nrb200_gathered_pointers(const nrb200_handle *h, int32_t member, int32_t *device, void **iter_nranges_dev, void **iter_totals_dev,

@@ -524,8 +524,15 @@ int group_run_counts_gathered(nrb200_handle *g, const nrb200_draws *d, nrb200_st
         if (rc2) return rc2;
         if (n > 0) {
             // ... and two small kernels spread the rows and the per-iteration vectors to the other members
-            if (T.n > 0)
+            static const bool push_by_copy_engine = getenv("NRB200_PUSH_MEMCPY") != nullptr;  // A/B: cudaMemcpyPeerAsync per peer
+            if (T.n > 0 && push_by_copy_engine) {
+                for (int w = 0; w < W; ++w)
+                    if (w != k)
+                        NRB_CUDA(m, cudaMemcpyPeerAsync(g->members[w]->gat_counts.as<int32_t>() + lo * G, g->members[w]->device,
+                                                        m->gat_counts.as<int32_t>() + lo * G, m->device, (size_t)n * G * 4, m->stream));
+            } else if (T.n > 0) {
                 push_tile_kernel<<<(unsigned)m->sm_count * 4, 256, 0, m->stream>>>(m->gat_counts.as<int32_t>() + lo * G, n * G, T);
+            }
             broadcast_iteration_vectors_kernel<<<(unsigned)std::min<int64_t>((n + 255) / 256, 64), 256, 0, m->stream>>>(
                 m->d_iter_nranges.as<unsigned long long>(), m->d_iter_totals.as<unsigned long long>(), n, V);
             NRB_CUDA(m, cudaGetLastError());

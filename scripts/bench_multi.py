@@ -42,8 +42,11 @@ if args.group:
         t0 = time.perf_counter()
         eng.run_counts_gathered(Draws(n_iter=R, seed=s_), want_stats=False)   # returns when every member's stream has drained
         times.append(time.perf_counter() - t0)
+    compute_ms = []
     for s_ in range(5):   # device time of the slowest member (its kernels + push), from a separate pass with event timing on
-        kernel_ms.append(eng.run_counts_gathered(Draws(n_iter=R, seed=s_), want_stats=True)["total_ms"])
+        st = eng.run_counts_gathered(Draws(n_iter=R, seed=s_), want_stats=True)
+        kernel_ms.append(st["total_ms"])
+        compute_ms.append(st["kernel_ms"])
     chks = []
     for k in range(max(args.group, 1)):
         d, _, _, cnt_p = eng.gathered_pointers(k)
@@ -52,7 +55,8 @@ if args.group:
     ms = 1e3 * sorted(times)[len(times) // 2]
     print(json.dumps({"config": "cfg2 R=1000 sharded over a device group, [R x 20k] matrix on every GPU (stored by the count kernels over NVLink)",
                       "n_gpus": max(args.group, 1), "iters": R, "ms_per_1000_iterations_wall_median": ms, "ms_wall_min": 1e3 * min(times),
-                      "iters_per_s": R / ms * 1e3, "slowest_gpu_device_ms_median": sorted(kernel_ms)[len(kernel_ms) // 2],
+                      "iters_per_s": R / ms * 1e3, "slowest_gpu_device_ms_median": sorted(kernel_ms)[len(kernel_ms) // 2], "of_it_compute_ms": sorted(compute_ms)[len(compute_ms) // 2],
+                      "push": "cudaMemcpyPeerAsync" if os.environ.get("NRB200_PUSH_MEMCPY") else "push_tile_kernel (16-byte peer stores)",
                       "matrix_bytes": R * G * 4, "checksum": chks[0], "members_agree": all(c == chks[0] for c in chks)}))
     eng.close()
     sys.exit(0)

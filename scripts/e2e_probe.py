@@ -10,6 +10,8 @@
       both of the above under the tuning knobs (NRB200_RPT, NRB200_WIRE16, NRB200_CHUNKS), one child process each
   python scripts/e2e_probe.py cfg4 [--gpus N]
       BASELINE configs[3] through bootMoments(..., gpus=N): wall clock of the whole call
+  python scripts/e2e_probe.py cfg1
+      BASELINE configs[0] end to end: the materialised bootRanges() table and the fused bootCounts(), R's RNG
   python scripts/e2e_probe.py timeline
       NRB200_TRACE_DEV timeline of one step (host queue time vs device arrival of every stage)
 """
@@ -124,6 +126,28 @@ def cfg4(args):
                       "kernel_ms_slowest_gpu": kernel_ms, "signature": sig, "env": {k: v for k, v in os.environ.items() if k.startswith("NRB200_")}}), flush=True)
 
 
+def cfg1(args):
+    """BASELINE configs[0] end to end: bootRanges(y, 5e5, R = 50) on 10k ranges -- the literal drop-in call, materialised
+    BootRanges table with its iter column -- and the fused bootCounts() against 20k genes, under R's RNG (set.seed(1))."""
+    from nullranges_b200 import bootCounts, bootRanges, synth
+    y, x = synth.uniform_ranges(10_000, seed=1), synth.genes(20_000, seed=2)
+    t_tab, t_cnt, rows = [], [], 0
+    for rep in range(args.reps + 2):
+        t0 = time.perf_counter()
+        br = bootRanges(y, L_B, R=50, rng="R", seed=1)
+        t1 = time.perf_counter()
+        bc = bootCounts(y, x, L_B, R=50, rng="R", seed=1)
+        t2 = time.perf_counter()
+        t_tab.append(t1 - t0)
+        t_cnt.append(t2 - t1)
+        rows = len(br.start)
+    t_tab, t_cnt = sorted(t_tab[2:]), sorted(t_cnt[2:])
+    print(json.dumps({"mode": "cfg1", "rows": rows, "bootRanges_ms_median": 1e3 * t_tab[len(t_tab) // 2], "bootCounts_ms_median": 1e3 * t_cnt[len(t_cnt) // 2],
+                      "iters_per_s_table": 50 / t_tab[len(t_tab) // 2], "iters_per_s_counts": 50 / t_cnt[len(t_cnt) // 2],
+                      "note": "rng = 'R': the 50 x 5,760 block draws are made on the host by the R-compatible RNG inside the timed call",
+                      "totals_checksum": int(bc.iter_totals.sum())}), flush=True)
+
+
 def calib(args):
     from nullranges_b200 import Engine
     e = Engine(0)
@@ -133,9 +157,9 @@ def calib(args):
 
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
-    ap.add_argument("mode", choices=["step", "kernels", "sweep", "timeline", "calib", "cfg4"])
+    ap.add_argument("mode", choices=["step", "kernels", "sweep", "timeline", "calib", "cfg4", "cfg1"])
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--dest", default="pinned", choices=["pinned", "pageable", "fresh"])
     ap.add_argument("--reps", type=int, default=9)
     a = ap.parse_args()
-    {"step": step, "kernels": kernels, "sweep": sweep, "timeline": timeline, "calib": calib, "cfg4": cfg4}[a.mode](a)
+    {"step": step, "kernels": kernels, "sweep": sweep, "timeline": timeline, "calib": calib, "cfg4": cfg4, "cfg1": cfg1}[a.mode](a)
