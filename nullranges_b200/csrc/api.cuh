@@ -24,7 +24,6 @@ int nrb200_create(const nrb200_config *cfg, nrb200_handle **out) {
     nrb200_handle *h = new nrb200_handle();
     h->device = dev;
     h->flags = cfg ? cfg->flags : 0;
-    if (const char *e = getenv("NRB200_RPT")) h->tune_rpt = atoi(e) == 2 ? 2 : (atoi(e) == 4 ? 4 : 1);
     if (const char *e = getenv("NRB200_IPT")) h->tune_ipt = std::min(std::max(atoi(e), 1), kLoopMaxIpt);
     if (const char *e = getenv("NRB200_LOOP_MINB")) h->tune_loop_minb = atoi(e);
     if (const char *e = getenv("NRB200_STREAM_OLD")) h->tune_stream_old = atoi(e) != 0;

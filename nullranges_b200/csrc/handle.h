@@ -264,8 +264,7 @@ struct nrb200_handle {
     uint32_t flags = 0;
     // tuning knobs (environment, read at create)
     bool tune_end_rank = true;         // NRB200_END_RANK=0: always radix-sort the ends (index build)
-    int tune_rpt = 1;                  // NRB200_RPT: iterations per thread of the count kernel (1, 2 or 4)
-    int tune_ipt = 4;                  // NRB200_IPT: iterations a thread of the count kernel stays on its feature (<= 64; 1 = one thread per (feature, iteration))
+    int tune_ipt = 4;                  // NRB200_IPT: iterations a thread of the count kernel stays on its feature (<= 64)
     int tune_loop_minb = 12;           // NRB200_LOOP_MINB: its min CTAs per SM (16 = 32 registers, 12 = 40)
     bool tune_stream_old = false;      // NRB200_STREAM_OLD=1: streaming path through boot_count_kernel only (A/B)
     int tune_rows_ipc = 4;             // NRB200_ROWS_IPC: iterations a CTA of the rows kernel loops over

@@ -120,72 +120,9 @@ __device__ __forceinline__ int count_pair(const RangesView &y, int2 d, int cls, 
     return c[0];
 }
 
-// Thread = (feature, RPT consecutive iterations); the block draws come from the table the block-rows kernel wrote.
-// Features are visited in F's order (grouped by tile count, so a warp's lanes loop the same number of times;
-// neighbours in a group are neighbours on the genome, so they mostly share their tile and the draw is one broadcast
-// load).  No atomics on the count matrix, no memset: every element is written exactly once -- as int32, or as uint16
-// (the wire format of a host-bound matrix: half the bytes through the L2, HBM and PCIe; a count above 65535 raises
-// the chunk's overflow flag and the chunk is redone in int32).
-// The kernel is bound by the 32-byte sectors it pulls through the L2 (two table entries per evaluation, the 16-byte
-// record and the draw per RPT evaluations); resident warps hide the latency of the chain record -> draw -> sequence
-// info -> table entries.
-constexpr int kCountThreads = 128;
-template <int RPT, int MINB>
-__global__ void __launch_bounds__(kCountThreads, MINB) boot_rank_count_kernel(const BootParams P, const FeatView F) {
-    __shared__ int warp_tot[kCountThreads / 32][RPT];
-    const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int64_t r0 = (int64_t)blockIdx.y * RPT;
-    const int n_live = (int)min((int64_t)RPT, P.n_iter - r0);
-    int cnt[RPT];
-#pragma unroll
-    for (int j = 0; j < RPT; ++j) cnt[j] = 0;
-    if (g < P.n_query) {
-        const int32_t src = __ldg(F.src + g);
-        const int32_t p1 = __ldg(F.pair_off + g + 1);
-        const int2 *__restrict__ tab = P.draw_tab + r0 * P.n_blocks;
-        for (int32_t p = __ldg(F.pair_off + g); p < p1; ++p) {
-            const int4 rec = __ldg(F.rec + p);
-            const int tile = rec_tile(rec.x);
-            const int2 ti = __ldg(P.tile_info + tile);  // bait width, sequence length
-            int2 d[RPT];
-#pragma unroll
-            for (int j = 0; j < RPT; ++j) d[j] = __ldg(tab + (int64_t)(j < n_live ? j : 0) * P.n_blocks + tile);  // tail: recount row 0, discarded
-            int c[RPT];
-#pragma unroll
-            for (int j = 0; j < RPT; ++j) c[j] = 0;
-            if (P.permute) count_pairs<RPT, true>(P.y, d, rec_cls(rec.x), ti.x, rec.w, ti.y, rec.y, rec.z, c);
-            else count_pairs<RPT, false>(P.y, d, rec_cls(rec.x), ti.x, rec.w, ti.y, rec.y, rec.z, c);
-            const int sign = rec_sign(rec.x);
-#pragma unroll
-            for (int j = 0; j < RPT; ++j) cnt[j] += sign * c[j];
-        }
-#pragma unroll
-        for (int j = 0; j < RPT; ++j) {
-            if (j >= n_live) continue;
-            // streaming stores: written once, read back by the copy engine
-            if (P.counts16) {
-                __stcs(P.counts16 + (r0 + j) * P.n_query + src, (unsigned short)min(cnt[j], 65535));
-                if (cnt[j] > 65535) atomicOr(P.overflow16, 1);
-            } else if (P.counts) {
-                __stcs(P.counts + (r0 + j) * P.n_query + src, cnt[j]);
-            }
-        }
-    }
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-#pragma unroll
-    for (int j = 0; j < RPT; ++j) {
-        const int s = __reduce_add_sync(kFull, cnt[j]);
-        if (lane == 0) warp_tot[warp][j] = s;
-    }
-    __syncthreads();
-    if (threadIdx.x < n_live) {
-        unsigned long long t = 0;
-        for (int w = 0; w < kCountThreads / 32; ++w) t += (unsigned)warp_tot[w][threadIdx.x];
-        if (t) atomicAdd(P.iter_totals + r0 + threadIdx.x, t);
-    }
-}
+constexpr int kCountThreads = 128;  // CTA size of the count kernels: 128 beat 64 / 256 / 512 in round 1's sweep
 
-// The same count with the thread staying on its feature for `ipt` consecutive iterations: the window record, the
+// The count kernel.  Thread = feature, staying on it for `ipt` consecutive iterations: the window record, the
 // tile's bait width / sequence length and the list bounds are read once per thread instead of once per iteration,
 // and the next iteration's draw is requested while the current one is evaluated, so that per iteration the chain
 // is draw (prefetched) -> sequence info (an L1 hit) -> the two table entries.  Per-iteration totals are summed in
@@ -359,7 +296,7 @@ __device__ __forceinline__ double weighted_pair(const RangesView &y, const Weigh
     return s;
 }
 
-// Thread = (feature, iteration), like boot_rank_count_kernel<1>; sums[r, g] written once, iter_sums by atomics.
+// Thread = (feature, iteration); sums[r, g] written once, iter_sums by atomics.
 __global__ void __launch_bounds__(256) boot_rank_wsum_kernel(const BootParams P, const FeatView F, const WeightView W,
                                                              double *__restrict__ sums, double *__restrict__ iter_sums) {
     __shared__ double warp_tot[8];

@@ -259,17 +259,13 @@ int launch_rank(nrb200_handle *h, const BootParams &P, bool has_query) {
     if (h->split_ev) cudaEventRecord(h->split_ev, h->stream);  // stats: end of the rows kernel
     if (has_query) {
         const FeatView F{h->f_src.as<int32_t>(), h->pair_off.as<int32_t>(), h->pair_rec.as<int4>()};
-        const int rpt = h->tune_rpt;
-        const dim3 grid((unsigned)((P.n_query + kCountThreads - 1) / kCountThreads), (unsigned)((P.n_iter + rpt - 1) / rpt));
-        if (h->tune_ipt > 1 || P.n_peers > 0) {  // a thread stays on its feature for several iterations
-            // as many iterations per thread as leave a few CTAs per resident slot
-            const int ipt = (int)std::max<int64_t>(1, std::min<int64_t>(h->tune_ipt, (int64_t)grid.x * P.n_iter / ((int64_t)h->sm_count * 16 * 3)));
-            const dim3 lgrid(grid.x, (unsigned)((P.n_iter + ipt - 1) / ipt));
-            if (h->tune_loop_minb >= 16) boot_rank_loop_kernel<false, 16><<<lgrid, kCountThreads, 0, h->stream>>>(P, F, ipt, MomentsOut{});
-            else boot_rank_loop_kernel<false, 12><<<lgrid, kCountThreads, 0, h->stream>>>(P, F, ipt, MomentsOut{});
-        } else if (rpt == 2) boot_rank_count_kernel<2, 12><<<grid, kCountThreads, 0, h->stream>>>(P, F);
-        else if (rpt == 4) boot_rank_count_kernel<4, 8><<<grid, kCountThreads, 0, h->stream>>>(P, F);
-        else boot_rank_count_kernel<1, 16><<<grid, kCountThreads, 0, h->stream>>>(P, F);
+        // a thread stays on its feature for up to NRB200_IPT iterations, as long as the grid still holds a few CTAs per
+        // resident slot (small runs: one iteration per thread)
+        const unsigned gx = (unsigned)((P.n_query + kCountThreads - 1) / kCountThreads);
+        const int ipt = (int)std::max<int64_t>(1, std::min<int64_t>(h->tune_ipt, (int64_t)gx * P.n_iter / ((int64_t)h->sm_count * 16 * 3)));
+        const dim3 lgrid(gx, (unsigned)((P.n_iter + ipt - 1) / ipt));
+        if (h->tune_loop_minb >= 16) boot_rank_loop_kernel<false, 16><<<lgrid, kCountThreads, 0, h->stream>>>(P, F, ipt, MomentsOut{});
+        else boot_rank_loop_kernel<false, 12><<<lgrid, kCountThreads, 0, h->stream>>>(P, F, ipt, MomentsOut{});
         ++launches;
     }
     return launches;

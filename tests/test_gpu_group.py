@@ -177,3 +177,22 @@ def test_group_full_size_cfg2_across_real_gpus():
     b = bootCounts(y, x, 500_000, R=1000, rng="philox", seed=2024, gpus=_n_gpus())
     assert np.array_equal(a.feature_counts, b.feature_counts)
     assert np.array_equal(a.iter_totals, b.iter_totals) and np.array_equal(a.iter_nranges, b.iter_nranges)
+
+
+def test_front_end_boot_ranges_on_a_group(groups):
+    """bootRanges(..., gpus=): the materialised table is produced by the group's first GPU -- same rows as one GPU,
+    including blockStart for a device-drawn permutation (nrb200_fetch_dst_tiles through the group handle)."""
+    from nullranges_b200 import bootRanges
+    rng = np.random.default_rng(4)
+    sl = {"chr1": 30000, "chr2": 20000}
+    y = GRanges(np.array(["chr1", "chr2"])[rng.integers(0, 2, 900)], rng.integers(1, 19000, 900), width=rng.integers(1, 150, 900), seqlengths=sl).sort()
+    devs = [0, 0] if _n_gpus() < 2 else [0, 1]
+    for kw in (dict(type="bootstrap"), dict(type="permute", withinChrom=True, storeBlockStart=True)):
+        a = bootRanges(y, 2000, R=6, rng="philox", seed=11, **kw)
+        b = bootRanges(y, 2000, R=6, rng="philox", seed=11, gpus=devs, **kw)
+        for k in ("seqid", "start", "end"):
+            assert np.array_equal(getattr(a, k), getattr(b, k)), k
+        assert np.array_equal(a.mcols["iter"], b.mcols["iter"])
+        if "storeBlockStart" in kw:
+            assert np.array_equal(a.mcols["blockStart"], b.mcols["blockStart"])
+            assert np.all((a.start >= a.mcols["blockStart"]) | (a.start == 1))  # a row lies on the tile its block landed on
