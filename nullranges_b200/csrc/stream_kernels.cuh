@@ -178,7 +178,9 @@ __global__ void __launch_bounds__(256) boot_count_kernel(const BootParams P) {
 // shared slice for the warp's smallest start and largest end) and every lane tests only those.
 // Bootstrap kinds only (block b lands on tile b); the permute variants and slices that do not fit keep
 // boot_count_kernel.
-constexpr int kGroupTiles = 32;    // tiles per CTA at most (one lane of a warp draws each: <= 32)
+constexpr int kGroupTiles = 256;   // tiles per CTA at most (one thread draws each: <= the CTA's 256 threads).  The draw + hit-window
+                                   // search is a ~4,000-cycle dependent chain before any range can be streamed: 16 tiles per warp
+                                   // make that prologue a fifth of a CTA's life (32 tiles per CTA: nearly half, measured as barrier stalls)
 constexpr int kStreamMinBlocks = 5; // resident CTAs per SM the stream kernel is compiled for (<= 51 registers: no spills)
 constexpr int kMaxSlice = 2048;    // features of a group's slice at most (shared memory: 21 bytes per feature)
 
@@ -253,10 +255,10 @@ __global__ void __launch_bounds__(256, kStreamMinBlocks) boot_stream_kernel(cons
         }
         for (int k = threadIdx.x; k < n_slice; k += blockDim.x) s_hist[k] = 0;  // generic-proxy writes to a region the copies do not touch
     }
-    // While the copy engine works: lane j of the last warp draws block j of the group and locates its hit window
+    // While the copy engine works: thread j draws block j of the group and locates its hit window
     // (Philox + pick + two rank probes: ~275 instructions that 32 lanes would otherwise repeat for every tile).
-    if (warp == blockDim.x / kWarp - 1 && lane < grp.count) {
-        Item it = load_item(P, r, __ldg(V.tiles_sorted + grp.first + lane));
+    if (threadIdx.x < grp.count) {
+        Item it = load_item(P, r, __ldg(V.tiles_sorted + grp.first + threadIdx.x));
         it.q_lo = it.q_hi = it.x_lo = it.x_hi = 0;
         if (HAS_QUERY) {
             it.q_lo = __ldg(P.query.tile_lo + it.tile) - grp.q_lo;
@@ -266,7 +268,7 @@ __global__ void __launch_bounds__(256, kStreamMinBlocks) boot_stream_kernel(cons
             it.x_lo = __ldg(P.excl.tile_lo + it.tile);
             it.x_hi = __ldg(P.excl.tile_hi + it.tile);
         }
-        s_item[lane] = it;
+        s_item[threadIdx.x] = it;
     }
     if (stage) mbar_wait(&bar, 0);  // the slice has landed (every thread observes the phase itself)
     __syncthreads();                // ... the histogram is zeroed and the items are in place
