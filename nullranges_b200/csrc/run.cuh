@@ -225,9 +225,14 @@ void launch_stream_t(nrb200_handle *h, const BootParams &P, int excl) {
     const GroupView V{h->groups_dev.as<TileGroup>(), h->tiles_sorted_dev.as<int32_t>(), h->y_se.as<int2>(), h->group_slice_cap};
     const dim3 grid((unsigned)h->n_groups, (unsigned)P.n_iter);
     const size_t smem = ((size_t)h->group_slice_cap * 21 + 15) & ~(size_t)15;
-    if (excl == kExclNone) boot_stream_kernel<ST, HQ, kExclNone><<<grid, 256, smem, h->stream>>>(P, V);
-    else if (excl == kExclDrop) boot_stream_kernel<ST, HQ, kExclDrop><<<grid, 256, smem, h->stream>>>(P, V);
-    else boot_stream_kernel<ST, HQ, kExclTrim><<<grid, 256, smem, h->stream>>>(P, V);
+    // dynamic slice (up to 43 KB) + the static item table (14 KB) can pass the 48 KB a kernel gets without asking
+    auto launch = [&](auto kernel) {
+        if (smem > ((size_t)32 << 10)) cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        kernel<<<grid, 256, smem, h->stream>>>(P, V);
+    };
+    if (excl == kExclNone) launch(boot_stream_kernel<ST, HQ, kExclNone>);
+    else if (excl == kExclDrop) launch(boot_stream_kernel<ST, HQ, kExclDrop>);
+    else launch(boot_stream_kernel<ST, HQ, kExclTrim>);
 }
 
 template <bool ST, bool HQ>

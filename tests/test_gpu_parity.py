@@ -864,3 +864,23 @@ def test_uint16_result(pinned):
         assert got["overflow"] and got["feature_counts"].max() == 65535 and int(got["iter_totals"][0]) == n
     finally:
         eng.close()
+
+
+@pytest.mark.parametrize("n_query,L_b", [(1500, 2000), (6000, 2000), (30000, 20000)])
+def test_stream_kernel_large_query_slices(n_query, L_b):
+    """The tile-group streaming kernel with query slices near and beyond its shared-memory capacity (2048 features):
+    groups are cut down until their slice fits (more than 48 KB of shared memory needs the opt-in), and a single tile
+    with a larger slice sends the plan to the block-centric kernel.  All three against the oracle."""
+    from nullranges_b200 import Engine
+    eng = Engine(0, force_stream=True)
+    try:
+        case = H.random_case(seed=333, n=4000, n_seq=3, max_len=60000, n_query=n_query, wmax=200, L_b=L_b, n_excl=12)
+        plan, y, q, x = H.oracle_objects(case, 0)
+        H.load_engine(eng, case, 0)
+        R = 5
+        got = eng.run_counts(Draws(n_iter=R, rng_mode=_lib.RNG_PHILOX, seed=6, iter0=2))
+        ref = O.boot_counts(plan, y, q, R, exclude=x, seed=6, iter0=2)
+        for k in ("iter_nranges", "iter_totals", "feature_counts"):
+            assert np.array_equal(got[k], ref[k]), k
+    finally:
+        eng.close()
