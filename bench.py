@@ -501,7 +501,7 @@ def run_gpu(args):
                                   "frac": alg8d / (kernel_ms * 1e-3) / 1e9 / peak,
                                   "note": "SURVEY 8d bytes (8*H + 16*B + 4*G + 16 per iteration) over rows + count kernel time; above 1 because the "
                                           "rank path never reads the H sampled ranges -- kept for comparison, not a bound"},
-            "roofline_stream": {"bound": "hbm", "kernel": "boot_count_kernel (NRB200_FLAG_FORCE_STREAM, same workload): streams the sampled ranges, the 8d model's kernel",
+            "roofline_stream": {"bound": "hbm", "kernel": "boot_stream_kernel (NRB200_FLAG_FORCE_STREAM, same workload): streams the sampled ranges, the 8d model's kernel",
                                 "achieved": stream_achieved, "peak": peak, "unit": "GB/s", "frac": stream_achieved / peak,
                                 "kernel_ms_per_launch": stream_ms / stream_steps, "iters_per_s": R * stream_steps / (stream_ms * 1e-3)},
             "cpu_baseline": {"value": n_cpu / cpu_t, "unit": "iter/s", "cores": cores, "kind": "port",

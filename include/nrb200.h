@@ -41,7 +41,7 @@ extern "C" {
 typedef struct nrb200_handle nrb200_handle;
 
 /* config flags */
-#define NRB200_FLAG_FORCE_STREAM 1u /* always stream the sampled ranges (boot_count_kernel), even where
+#define NRB200_FLAG_FORCE_STREAM 1u /* always stream the sampled ranges (boot_stream_kernel), even where
                                        the rank path (counting by rank differences) applies; for tests
                                        and for measuring the streaming kernel */
 
@@ -189,7 +189,7 @@ typedef struct nrb200_stats {
     int64_t h2d_bytes;
     int64_t d2h_bytes;
     double rows_kernel_ms;  /* rank path: boot_block_rows_kernel (draws + rows per block) */
-    double count_kernel_ms; /* rank path: boot_rank_count_kernel; streaming path: boot_count_kernel */
+    double count_kernel_ms; /* rank path: boot_rank_loop_kernel; streaming path: boot_stream_kernel (boot_count_kernel for permute) */
     int64_t n_windows;      /* rank path: signed windows evaluated per iteration (0 on the streaming path) */
 } nrb200_stats;
 

@@ -3,7 +3,7 @@
 namespace {
 
 // The rank path covers every sampler (bootstrap and permute, with or without exclusion, any strands);
-// only a segmentation reaching beyond its sequence falls back to streaming the hits (boot_count_kernel).
+// only a segmentation reaching beyond its sequence falls back to streaming the hits (boot_stream_kernel; boot_count_kernel for permute).
 bool rank_path_ok(const nrb200_handle *h) {
     if (h->flags & NRB200_FLAG_FORCE_STREAM) return false;
     if (kZeroWidthStrictlyInside && h->have_plan && !h->plan.drop_zero_width()) {
