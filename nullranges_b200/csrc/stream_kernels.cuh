@@ -216,6 +216,15 @@ __device__ __forceinline__ void mbar_wait(unsigned long long *bar, uint32_t pari
             : "memory");
 }
 
+// Shared-memory accesses of the hot loop by 32-bit shared address: the base stays in one register instead of being rebuilt
+// from the CTA's rank in its cluster at every use (what the compiler does under the register cap when it sees the pointers).
+__device__ __forceinline__ int32_t lds_s32(uint32_t addr) {
+    int32_t v;
+    asm("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void red_shared_add(uint32_t addr, int v) { asm volatile("red.shared.add.s32 [%0], %1;" ::"r"(addr), "r"(v) : "memory"); }
+
 struct GroupView {
     const TileGroup *groups;
     const int32_t *tiles_sorted;
@@ -235,6 +244,9 @@ __global__ void __launch_bounds__(256, kStreamMinBlocks) boot_stream_kernel(cons
     int32_t *s_end = s_start + cap, *s_pmax = s_end + cap, *s_src = s_pmax + cap;
     int *s_hist = s_src + cap;
     int8_t *s_strand = reinterpret_cast<int8_t *>(s_hist + cap);
+    uint32_t a_start = smem_u32(smem_raw);     // shared address of s_start; s_end, s_pmax, s_hist follow at 1, 2, 4 times cap4
+    asm volatile("" : "+r"(a_start));           // opaque to the compiler: kept, not rematerialised
+    const uint32_t cap4 = 4u * (uint32_t)cap;
     const int lane = threadIdx.x & (kWarp - 1), warp = threadIdx.x / kWarp;
     const TileGroup grp = V.groups[blockIdx.x];
     const int64_t r = blockIdx.y;
@@ -272,24 +284,22 @@ __global__ void __launch_bounds__(256, kStreamMinBlocks) boot_stream_kernel(cons
     }
     if (stage) mbar_wait(&bar, 0);  // the slice has landed (every thread observes the phase itself)
     __syncthreads();                // ... the histogram is zeroed and the items are in place
-    unsigned long long overlaps_warp = 0, rows_warp = 0, hits_warp = 0;
-    const bool want_hits = P.n_hits != nullptr;
+    // rows and hits are tallied per lane over all the warp's tiles (a lane sees at most 1/32 of every hit window, so 32 bits hold
+    // them) and leave the warp once; the overlaps are read off the histogram when it leaves the CTA.
+    unsigned rows_lane = 0, hits_lane = 0;
     for (int j = warp; j < grp.count; j += blockDim.x / kWarp) {
         const Item it = s_item[j];
-        const int32_t t = it.tile;
         const int32_t q_lo = it.q_lo, q_hi = it.q_hi, x_lo = it.x_lo, x_hi = it.x_hi;
         // the features the warp's current ranges can reach, [w_lo, w_hi) of the shared slice: the ranges come in ascending
         // start order, so both ends only move forward (w_hi may run ahead: every lane tests exactly)
         int32_t w_lo = q_lo, w_hi = q_lo;
-        int rows = 0, hits = 0, overlaps = 0;
+        unsigned rows = 0;
         // ranges i0 and i0 + 1 per lane and trip (the array is padded to an even length); the next trip's load is issued
         // before this trip's ranges are worked on
-        int4 v_next = make_int4(0, 0, 0, 0);
-        if ((it.lo & ~1) + 2 * lane < it.hi) v_next = __ldg(reinterpret_cast<const int4 *>(V.se + (it.lo & ~1) + 2 * lane));
+        int4 v = make_int4(0, 0, 0, 0);
+        if ((it.lo & ~1) + 2 * lane < it.hi) v = __ldg(reinterpret_cast<const int4 *>(V.se + (it.lo & ~1) + 2 * lane));
         for (int32_t base = it.lo & ~1; base < it.hi; base += 2 * kWarp) {
             const int32_t i0 = base + 2 * lane;
-            const int4 v = v_next;
-            if (i0 + 2 * kWarp < it.hi) v_next = __ldg(reinterpret_cast<const int4 *>(V.se + i0 + 2 * kWarp));
             int32_t s2[2], e2[2];
             bool keep[2];
             int strand[2] = {0, 0};
@@ -299,7 +309,7 @@ __global__ void __launch_bounds__(256, kStreamMinBlocks) boot_stream_kernel(cons
                 const int32_t st = u ? v.z : v.x, en = u ? v.w : v.y;
                 // bootstrap kinds: every range of the window starts at or before the block's end; a hit also ends at or after its start
                 const bool hit = i >= it.lo && i < it.hi && en >= it.bait_start;
-                if (want_hits) hits += hit ? 1 : 0;
+                if (hit) ++hits_lane;
                 s2[u] = st + it.shift;
                 e2[u] = en + it.shift;
                 keep[u] = hit;
@@ -315,6 +325,8 @@ __global__ void __launch_bounds__(256, kStreamMinBlocks) boot_stream_kernel(cons
                 if (EXCL == kExclDrop && keep[u] && excluded<STRANDED>(P.excl, it.tile, s2[u], e2[u], strand[u])) keep[u] = false;
                 if (EXCL == kExclTrim && keep[u] && e2[u] < s2[u]) keep[u] = false;  // a zero-width survivor overlaps no gap
             }
+            // the pair is consumed: the next trip's load goes out now and has the rest of this trip to arrive
+            if (i0 + 2 * kWarp < it.hi) v = __ldg(reinterpret_cast<const int4 *>(V.se + i0 + 2 * kWarp));
             if (EXCL == kExclTrim) {
                 // each range is cut to the gaps it overlaps: one row (and one piece to count) per overlap
 #pragma unroll
@@ -331,7 +343,6 @@ __global__ void __launch_bounds__(256, kStreamMinBlocks) boot_stream_kernel(cons
                                 if (ps > qe || pe < qs) continue;
                                 if (STRANDED && P.query.strand && !strands_match(strand[u], s_strand[q])) continue;
                                 if (P.minoverlap > 0 && min(pe, qe) - max(ps, qs) + 1 < P.minoverlap) continue;
-                                ++overlaps;
                                 atomicAdd(&s_hist[q], 1);
                             }
                         }
@@ -339,20 +350,35 @@ __global__ void __launch_bounds__(256, kStreamMinBlocks) boot_stream_kernel(cons
                 }
                 continue;
             }
-            rows += (keep[0] ? 1 : 0) + (keep[1] ? 1 : 0);
+            if (keep[0]) ++rows;
+            if (keep[1]) ++rows;
             if (HAS_QUERY && q_hi > q_lo) {
-                const bool cnt0 = keep[0] && (e2[0] >= s2[0] || kZeroWidthStrictlyInside), cnt1 = keep[1] && (e2[1] >= s2[1] || kZeroWidthStrictlyInside);
-                const int32_t my_min = min(cnt0 ? s2[0] : INT32_MAX, cnt1 ? s2[1] : INT32_MAX);
-                const int32_t my_max = max(cnt0 ? e2[0] : INT32_MIN, cnt1 ? e2[1] : INT32_MIN);
-                const int32_t w_min = __reduce_min_sync(kFull, my_min), w_max = __reduce_max_sync(kFull, my_max);
+                // a range that is not counted becomes the empty [INT32_MAX, INT32_MIN]: it fails every overlap test below
+                if (!(keep[0] && (e2[0] >= s2[0] || kZeroWidthStrictlyInside))) { s2[0] = INT32_MAX; e2[0] = INT32_MIN; }
+                if (!(keep[1] && (e2[1] >= s2[1] || kZeroWidthStrictlyInside))) { s2[1] = INT32_MAX; e2[1] = INT32_MIN; }
+                const int32_t w_min = __reduce_min_sync(kFull, min(s2[0], s2[1])), w_max = __reduce_max_sync(kFull, max(e2[0], e2[1]));
                 if (w_max != INT32_MIN) {
-                    while (w_hi < q_hi && s_start[w_hi] <= w_max) ++w_hi;                  // features starting at or before the largest end
-                    while (w_lo < w_hi && s_pmax[w_lo] < w_min) ++w_lo;                    // ... whose running-max end reaches the smallest start
-                    for (int32_t q = w_lo; q < w_hi; ++q) {
-                        const int32_t qs = s_start[q], qe = s_end[q];  // broadcast reads
-                        bool h0 = cnt0 && s2[0] <= qe && e2[0] >= qs, h1 = cnt1 && s2[1] <= qe && e2[1] >= qs;
+                    // both ends of the window advance 32 candidates at a time: starts and running-max ends ascend along the slice,
+                    // so the lanes that pass are a prefix and their number is the step
+                    for (;;) {  // features starting at or before the largest end
+                        const int32_t q = w_hi + lane;
+                        const unsigned m = __ballot_sync(kFull, q < q_hi && lds_s32(a_start + 4u * (uint32_t)q) <= w_max);
+                        w_hi += __popc(m);
+                        if (m != kFull) break;
+                    }
+                    for (;;) {  // ... whose running-max end reaches the smallest start
+                        const int32_t q = w_lo + lane;
+                        const unsigned m = __ballot_sync(kFull, q < w_hi && lds_s32(a_start + 2u * cap4 + 4u * (uint32_t)q) < w_min);
+                        w_lo += __popc(m);
+                        if (m != kFull) break;
+                    }
+                    const uint32_t a_stop = a_start + 4u * (uint32_t)w_hi;
+#pragma unroll 1
+                    for (uint32_t a = a_start + 4u * (uint32_t)w_lo; a < a_stop; a += 4u) {
+                        const int32_t qs = lds_s32(a), qe = lds_s32(a + cap4);  // broadcast reads
+                        bool h0 = s2[0] <= qe && e2[0] >= qs, h1 = s2[1] <= qe && e2[1] >= qs;
                         if (STRANDED && P.query.strand) {
-                            const int qst = s_strand[q];
+                            const int qst = s_strand[(a - a_start) >> 2];
                             h0 = h0 && strands_match(strand[0], qst);
                             h1 = h1 && strands_match(strand[1], qst);
                         }
@@ -361,36 +387,51 @@ __global__ void __launch_bounds__(256, kStreamMinBlocks) boot_stream_kernel(cons
                             h1 = h1 && min(e2[1], qe) - max(s2[1], qs) + 1 >= P.minoverlap;
                         }
                         const int n = __popc(__ballot_sync(kFull, h0)) + __popc(__ballot_sync(kFull, h1));
-                        if (n && lane == 0) atomicAdd(&s_hist[q], n);
-                        overlaps += (lane == 0) ? n : 0;
+                        if (n && lane == 0) red_shared_add(a + 4u * cap4, n);
                     }
                 }
             }
         }
-        rows = __reduce_add_sync(kFull, rows);
-        if (want_hits) hits = __reduce_add_sync(kFull, hits);
-        if (EXCL == kExclTrim) overlaps = __reduce_add_sync(kFull, overlaps);
-        else overlaps = __shfl_sync(kFull, overlaps, 0);
-        overlaps_warp += (unsigned)overlaps;
-        rows_warp += (unsigned)rows;
-        hits_warp += (unsigned)hits;
-        if (lane == 0 && P.item_rows) P.item_rows[r * P.n_blocks + t] = rows;
+        rows_lane += rows;
+        if (P.item_rows) {
+            const unsigned rows_tile = __reduce_add_sync(kFull, rows);
+            if (lane == 0) P.item_rows[r * P.n_blocks + it.tile] = (int32_t)rows_tile;
+        }
     }
     // The per-iteration tallies leave the CTA once: all CTAs of an iteration add to the same three words.
-    if (lane == 0) {
-        if (rows_warp) atomicAdd(&s_tally[0], rows_warp);
-        if (hits_warp) atomicAdd(&s_tally[1], hits_warp);
-        if (overlaps_warp) atomicAdd(&s_tally[2], overlaps_warp);
+    {
+        unsigned long long rows_warp = rows_lane, hits_warp = hits_lane;
+#pragma unroll
+        for (int d = kWarp / 2; d > 0; d >>= 1) {
+            rows_warp += __shfl_xor_sync(kFull, rows_warp, d);
+            hits_warp += __shfl_xor_sync(kFull, hits_warp, d);
+        }
+        if (lane == 0) {
+            if (rows_warp) atomicAdd(&s_tally[0], rows_warp);
+            if (hits_warp) atomicAdd(&s_tally[1], hits_warp);
+        }
     }
-    __syncthreads();
+    __syncthreads();  // ... and the histogram is complete
+    if (HAS_QUERY && stage) {
+        unsigned long long overlaps = 0;
+        const bool store = P.counts != nullptr;
+        for (int k = threadIdx.x; k < n_slice; k += blockDim.x) {
+            const int n = s_hist[k];
+            if (n) {
+                overlaps += (unsigned)n;
+                if (store) atomicAdd(P.counts + r * P.n_query + s_src[k], n);
+            }
+        }
+#pragma unroll
+        for (int d = kWarp / 2; d > 0; d >>= 1) overlaps += __shfl_xor_sync(kFull, overlaps, d);
+        if (lane == 0 && overlaps) atomicAdd(&s_tally[2], overlaps);
+        __syncthreads();
+    }
     if (threadIdx.x == 0) {
         if (s_tally[0]) atomicAdd(P.iter_nranges + r, s_tally[0]);
         if (P.n_hits && s_tally[1]) atomicAdd(P.n_hits + (r & (kHitSlots - 1)), s_tally[1]);
         if (HAS_QUERY && s_tally[2]) atomicAdd(P.iter_totals + r, s_tally[2]);
     }
-    if (HAS_QUERY && stage && P.counts)
-        for (int k = threadIdx.x; k < n_slice; k += blockDim.x)
-            if (s_hist[k]) atomicAdd(P.counts + r * P.n_query + s_src[k], s_hist[k]);
 }
 
 // y as interleaved {start, end} pairs (one 16-byte load = two ranges); one pad element at the end
