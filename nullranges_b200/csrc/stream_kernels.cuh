@@ -16,6 +16,7 @@ struct Item {
     int32_t seq_len;           // seqlengths[tile_seq]
     int32_t lo, hi;            // hit window in canonical y
     int32_t q_lo, q_hi, x_lo, x_hi;  // boot_stream_kernel only: the tile's query / exclude candidates
+    int32_t interior;          // boot_stream_kernel only: no range of the hit window can leave [1, seq_len) after the shift
 };
 
 __device__ __forceinline__ Item load_item(const BootParams &P, int64_t r, int64_t b) {
@@ -224,6 +225,17 @@ __device__ __forceinline__ int32_t lds_s32(uint32_t addr) {
     return v;
 }
 __device__ __forceinline__ void red_shared_add(uint32_t addr, int v) { asm volatile("red.shared.add.s32 [%0], %1;" ::"r"(addr), "r"(v) : "memory"); }
+// adds 1 where `on` holds, as ONE predicated instruction (no branch around it)
+__device__ __forceinline__ void red_shared_inc_if(bool on, uint32_t addr) {
+    asm volatile(
+        "{\n"
+        ".reg .pred q;\n"
+        "setp.ne.s32 q, %1, 0;\n"
+        "@q red.shared.add.s32 [%0], 1;\n"
+        "}\n" ::"r"(addr),
+        "r"((int)on)
+        : "memory");
+}
 
 struct GroupView {
     const TileGroup *groups;
@@ -231,6 +243,133 @@ struct GroupView {
     const int2 *se;            // y as interleaved {start, end}, canonical order
     int slice_cap;             // features the shared-memory arrays hold (a multiple of 4)
 };
+
+// One tile of a group, worked by one warp: streams the tile's hit window of y, 64 ranges per trip, and tallies the overlaps
+// with the features of the shared slice.  INTERIOR: the tile's window stays inside [1, seq_len) after the shift (Item::interior),
+// so trim() and the fall-off-the-end rule cannot apply and every hit is a row.
+template <bool STRANDED, bool HAS_QUERY, int EXCL, bool INTERIOR>
+__device__ __forceinline__ void stream_tile(const BootParams &P, const GroupView &V, const Item &it, const int lane, const uint32_t a_start,
+                                            const uint32_t cap4, const int32_t *s_start, const int32_t *s_end, int *s_hist,
+                                            const int8_t *s_strand, unsigned &rows_out, unsigned &hits_lane) {
+    const int32_t q_lo = it.q_lo, q_hi = it.q_hi, x_lo = it.x_lo, x_hi = it.x_hi;
+    // the features the warp's current ranges can reach, [w_lo, w_hi) of the shared slice: the ranges come in ascending
+    // start order, so both ends only move forward (w_hi may run ahead: every lane tests exactly)
+    int32_t w_lo = q_lo, w_hi = q_lo;
+    unsigned rows = 0, hits = 0;
+    // ranges i0 and i0 + 1 per lane and trip (the array is padded to an even length)
+    int4 v = make_int4(0, 0, 0, 0);
+    if ((it.lo & ~1) + 2 * lane < it.hi) v = __ldg(reinterpret_cast<const int4 *>(V.se + (it.lo & ~1) + 2 * lane));
+    for (int32_t base = it.lo & ~1; base < it.hi; base += 2 * kWarp) {
+        const int32_t i0 = base + 2 * lane;
+        int32_t s2[2], e2[2];
+        bool keep[2];
+        int strand[2] = {0, 0};
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const int32_t i = i0 + u;
+            const int32_t st = u ? v.z : v.x, en = u ? v.w : v.y;
+            // bootstrap kinds: every range of the window starts at or before the block's end; a hit also ends at or after its start.
+            // Only the even-aligned first slot of the first trip can lie before the window.
+            const bool hit = (u ? true : i >= it.lo) && i < it.hi && en >= it.bait_start;
+            if (hit) ++hits;
+            s2[u] = st + it.shift;
+            e2[u] = en + it.shift;
+            keep[u] = hit;
+            if (!INTERIOR) {
+                if (s2[u] > it.seq_len) {       // wholly beyond the sequence end -> [L + 1, L]
+                    if (P.drop_zero) keep[u] = false;
+                    s2[u] = it.seq_len + 1;
+                    e2[u] = it.seq_len;
+                } else {
+                    s2[u] = max(s2[u], 1);
+                    e2[u] = min(e2[u], it.seq_len);
+                }
+            }
+            if (STRANDED && keep[u] && P.y.strand) strand[u] = __ldg(P.y.strand + i);
+            if (EXCL == kExclDrop && keep[u] && x_hi > x_lo && (e2[u] >= s2[u] || kZeroWidthStrictlyInside)) {  // THE ZERO-WIDTH RULE (device_views.cuh)
+                for (int32_t k = x_lo; k < x_hi; ++k) {  // the tile's exclude candidates (few tiles have any)
+                    if (s2[u] <= __ldg(P.excl.end + k) && e2[u] >= __ldg(P.excl.start + k) &&
+                        (!STRANDED || !P.excl.strand || strands_match(strand[u], __ldg(P.excl.strand + k)))) {
+                        keep[u] = false;
+                        break;
+                    }
+                }
+            }
+            if (EXCL == kExclTrim && keep[u] && e2[u] < s2[u]) keep[u] = false;  // a zero-width survivor overlaps no gap
+        }
+        // the pair is consumed: the next trip's load goes out now and has the rest of this trip to arrive
+        if (i0 + 2 * kWarp < it.hi) v = __ldg(reinterpret_cast<const int4 *>(V.se + i0 + 2 * kWarp));
+        if (EXCL == kExclTrim) {
+            // each range is cut to the gaps it overlaps: one row (and one piece to count) per overlap
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                if (!keep[u]) continue;
+                for (int32_t k = x_lo; k < x_hi; ++k) {
+                    const int32_t gs = __ldg(P.excl.start + k), ge = __ldg(P.excl.end + k);
+                    if (s2[u] > ge || e2[u] < gs) continue;
+                    ++rows;
+                    if (HAS_QUERY) {
+                        const int32_t ps = max(s2[u], gs), pe = min(e2[u], ge);
+                        for (int32_t q = q_lo; q < q_hi; ++q) {
+                            const int32_t qs = s_start[q], qe = s_end[q];
+                            if (ps > qe || pe < qs) continue;
+                            if (STRANDED && P.query.strand && !strands_match(strand[u], s_strand[q])) continue;
+                            if (P.minoverlap > 0 && min(pe, qe) - max(ps, qs) + 1 < P.minoverlap) continue;
+                            atomicAdd(&s_hist[q], 1);
+                        }
+                    }
+                }
+            }
+            continue;
+        }
+        if (!INTERIOR) {  // (interior tiles: every hit is a row)
+            if (keep[0]) ++rows;
+            if (keep[1]) ++rows;
+        }
+        if (HAS_QUERY && q_hi > q_lo) {
+            const bool cnt0 = keep[0] && (e2[0] >= s2[0] || kZeroWidthStrictlyInside), cnt1 = keep[1] && (e2[1] >= s2[1] || kZeroWidthStrictlyInside);
+            const int32_t my_min = min(cnt0 ? s2[0] : INT32_MAX, cnt1 ? s2[1] : INT32_MAX);
+            const int32_t my_max = max(cnt0 ? e2[0] : INT32_MIN, cnt1 ? e2[1] : INT32_MIN);
+            const int32_t w_min = __reduce_min_sync(kFull, my_min), w_max = __reduce_max_sync(kFull, my_max);
+            if (w_max != INT32_MIN) {
+                // both ends of the window advance 32 candidates at a time: starts and running-max ends ascend along the slice,
+                // so the lanes that pass are a prefix and their number is the step
+                for (;;) {  // features starting at or before the largest end
+                    const int32_t q = w_hi + lane;
+                    const unsigned m = __ballot_sync(kFull, q < q_hi && lds_s32(a_start + 4u * (uint32_t)q) <= w_max);
+                    w_hi += __popc(m);
+                    if (m != kFull) break;
+                }
+                for (;;) {  // ... whose running-max end reaches the smallest start
+                    const int32_t q = w_lo + lane;
+                    const unsigned m = __ballot_sync(kFull, q < w_hi && lds_s32(a_start + 2u * cap4 + 4u * (uint32_t)q) < w_min);
+                    w_lo += __popc(m);
+                    if (m != kFull) break;
+                }
+                const uint32_t a_stop = a_start + 4u * (uint32_t)w_hi;
+#pragma unroll 1
+                for (uint32_t a = a_start + 4u * (uint32_t)w_lo; a < a_stop; a += 4u) {
+                    const int32_t qs = lds_s32(a), qe = lds_s32(a + cap4);  // broadcast reads
+                    bool h0 = cnt0 && s2[0] <= qe && e2[0] >= qs, h1 = cnt1 && s2[1] <= qe && e2[1] >= qs;
+                    if (STRANDED && P.query.strand) {
+                        const int qst = s_strand[(a - a_start) >> 2];
+                        h0 = h0 && strands_match(strand[0], qst);
+                        h1 = h1 && strands_match(strand[1], qst);
+                    }
+                    if (P.minoverlap > 0) {
+                        h0 = h0 && min(e2[0], qe) - max(s2[0], qs) + 1 >= P.minoverlap;
+                        h1 = h1 && min(e2[1], qe) - max(s2[1], qs) + 1 >= P.minoverlap;
+                    }
+                    // few ranges of a trip meet one feature (a handful at most): the lanes that do add for themselves
+                    red_shared_inc_if(h0, a + 4u * cap4);
+                    red_shared_inc_if(h1, a + 4u * cap4);
+                }
+            }
+        }
+    }
+    hits_lane += hits;
+    rows_out = INTERIOR ? hits : rows;
+}
 
 template <bool STRANDED, bool HAS_QUERY, int EXCL>
 __global__ void __launch_bounds__(256, kStreamMinBlocks) boot_stream_kernel(const BootParams P, const GroupView V) {
@@ -276,9 +415,16 @@ __global__ void __launch_bounds__(256, kStreamMinBlocks) boot_stream_kernel(cons
             it.q_lo = __ldg(P.query.tile_lo + it.tile) - grp.q_lo;
             it.q_hi = __ldg(P.query.tile_hi + it.tile) - grp.q_lo;
         }
-        if (EXCL == kExclTrim) {
+        if (EXCL != kExclNone) {
             it.x_lo = __ldg(P.excl.tile_lo + it.tile);
             it.x_hi = __ldg(P.excl.tile_hi + it.tile);
+        }
+        // Most tiles sit well inside their sequence: when the window's smallest start and (a bound on) its largest end stay inside
+        // after the shift, trim() is the identity for every range of the tile and nothing can fall off the sequence end.
+        it.interior = 0;
+        if (EXCL == kExclNone && it.hi > it.lo) {
+            const int64_t s_min = (int64_t)__ldg(&V.se[it.lo].x) + it.shift, e_max = (int64_t)__ldg(P.y.pmax + it.hi - 1) + it.shift;
+            it.interior = (s_min >= 1 && e_max < it.seq_len) ? 1 : 0;
         }
         s_item[threadIdx.x] = it;
     }
@@ -289,109 +435,15 @@ __global__ void __launch_bounds__(256, kStreamMinBlocks) boot_stream_kernel(cons
     unsigned rows_lane = 0, hits_lane = 0;
     for (int j = warp; j < grp.count; j += blockDim.x / kWarp) {
         const Item it = s_item[j];
-        const int32_t q_lo = it.q_lo, q_hi = it.q_hi, x_lo = it.x_lo, x_hi = it.x_hi;
-        // the features the warp's current ranges can reach, [w_lo, w_hi) of the shared slice: the ranges come in ascending
-        // start order, so both ends only move forward (w_hi may run ahead: every lane tests exactly)
-        int32_t w_lo = q_lo, w_hi = q_lo;
         unsigned rows = 0;
-        // ranges i0 and i0 + 1 per lane and trip (the array is padded to an even length); the next trip's load is issued
-        // before this trip's ranges are worked on
-        int4 v = make_int4(0, 0, 0, 0);
-        if ((it.lo & ~1) + 2 * lane < it.hi) v = __ldg(reinterpret_cast<const int4 *>(V.se + (it.lo & ~1) + 2 * lane));
-        for (int32_t base = it.lo & ~1; base < it.hi; base += 2 * kWarp) {
-            const int32_t i0 = base + 2 * lane;
-            int32_t s2[2], e2[2];
-            bool keep[2];
-            int strand[2] = {0, 0};
-#pragma unroll
-            for (int u = 0; u < 2; ++u) {
-                const int32_t i = i0 + u;
-                const int32_t st = u ? v.z : v.x, en = u ? v.w : v.y;
-                // bootstrap kinds: every range of the window starts at or before the block's end; a hit also ends at or after its start
-                const bool hit = i >= it.lo && i < it.hi && en >= it.bait_start;
-                if (hit) ++hits_lane;
-                s2[u] = st + it.shift;
-                e2[u] = en + it.shift;
-                keep[u] = hit;
-                if (s2[u] > it.seq_len) {       // wholly beyond the sequence end -> [L + 1, L]
-                    if (P.drop_zero) keep[u] = false;
-                    s2[u] = it.seq_len + 1;
-                    e2[u] = it.seq_len;
-                } else {
-                    s2[u] = max(s2[u], 1);
-                    e2[u] = min(e2[u], it.seq_len);
-                }
-                if (STRANDED && keep[u] && P.y.strand) strand[u] = __ldg(P.y.strand + i);
-                if (EXCL == kExclDrop && keep[u] && excluded<STRANDED>(P.excl, it.tile, s2[u], e2[u], strand[u])) keep[u] = false;
-                if (EXCL == kExclTrim && keep[u] && e2[u] < s2[u]) keep[u] = false;  // a zero-width survivor overlaps no gap
-            }
-            // the pair is consumed: the next trip's load goes out now and has the rest of this trip to arrive
-            if (i0 + 2 * kWarp < it.hi) v = __ldg(reinterpret_cast<const int4 *>(V.se + i0 + 2 * kWarp));
-            if (EXCL == kExclTrim) {
-                // each range is cut to the gaps it overlaps: one row (and one piece to count) per overlap
-#pragma unroll
-                for (int u = 0; u < 2; ++u) {
-                    if (!keep[u]) continue;
-                    for (int32_t k = x_lo; k < x_hi; ++k) {
-                        const int32_t gs = __ldg(P.excl.start + k), ge = __ldg(P.excl.end + k);
-                        if (s2[u] > ge || e2[u] < gs) continue;
-                        ++rows;
-                        if (HAS_QUERY) {
-                            const int32_t ps = max(s2[u], gs), pe = min(e2[u], ge);
-                            for (int32_t q = q_lo; q < q_hi; ++q) {
-                                const int32_t qs = s_start[q], qe = s_end[q];
-                                if (ps > qe || pe < qs) continue;
-                                if (STRANDED && P.query.strand && !strands_match(strand[u], s_strand[q])) continue;
-                                if (P.minoverlap > 0 && min(pe, qe) - max(ps, qs) + 1 < P.minoverlap) continue;
-                                atomicAdd(&s_hist[q], 1);
-                            }
-                        }
-                    }
-                }
-                continue;
-            }
-            if (keep[0]) ++rows;
-            if (keep[1]) ++rows;
-            if (HAS_QUERY && q_hi > q_lo) {
-                // a range that is not counted becomes the empty [INT32_MAX, INT32_MIN]: it fails every overlap test below
-                if (!(keep[0] && (e2[0] >= s2[0] || kZeroWidthStrictlyInside))) { s2[0] = INT32_MAX; e2[0] = INT32_MIN; }
-                if (!(keep[1] && (e2[1] >= s2[1] || kZeroWidthStrictlyInside))) { s2[1] = INT32_MAX; e2[1] = INT32_MIN; }
-                const int32_t w_min = __reduce_min_sync(kFull, min(s2[0], s2[1])), w_max = __reduce_max_sync(kFull, max(e2[0], e2[1]));
-                if (w_max != INT32_MIN) {
-                    // both ends of the window advance 32 candidates at a time: starts and running-max ends ascend along the slice,
-                    // so the lanes that pass are a prefix and their number is the step
-                    for (;;) {  // features starting at or before the largest end
-                        const int32_t q = w_hi + lane;
-                        const unsigned m = __ballot_sync(kFull, q < q_hi && lds_s32(a_start + 4u * (uint32_t)q) <= w_max);
-                        w_hi += __popc(m);
-                        if (m != kFull) break;
-                    }
-                    for (;;) {  // ... whose running-max end reaches the smallest start
-                        const int32_t q = w_lo + lane;
-                        const unsigned m = __ballot_sync(kFull, q < w_hi && lds_s32(a_start + 2u * cap4 + 4u * (uint32_t)q) < w_min);
-                        w_lo += __popc(m);
-                        if (m != kFull) break;
-                    }
-                    const uint32_t a_stop = a_start + 4u * (uint32_t)w_hi;
-#pragma unroll 1
-                    for (uint32_t a = a_start + 4u * (uint32_t)w_lo; a < a_stop; a += 4u) {
-                        const int32_t qs = lds_s32(a), qe = lds_s32(a + cap4);  // broadcast reads
-                        bool h0 = s2[0] <= qe && e2[0] >= qs, h1 = s2[1] <= qe && e2[1] >= qs;
-                        if (STRANDED && P.query.strand) {
-                            const int qst = s_strand[(a - a_start) >> 2];
-                            h0 = h0 && strands_match(strand[0], qst);
-                            h1 = h1 && strands_match(strand[1], qst);
-                        }
-                        if (P.minoverlap > 0) {
-                            h0 = h0 && min(e2[0], qe) - max(s2[0], qs) + 1 >= P.minoverlap;
-                            h1 = h1 && min(e2[1], qe) - max(s2[1], qs) + 1 >= P.minoverlap;
-                        }
-                        const int n = __popc(__ballot_sync(kFull, h0)) + __popc(__ballot_sync(kFull, h1));
-                        if (n && lane == 0) red_shared_add(a + 4u * cap4, n);
-                    }
-                }
+        bool done = false;
+        if constexpr (EXCL == kExclNone) {
+            if (it.interior) {
+                stream_tile<STRANDED, HAS_QUERY, EXCL, true>(P, V, it, lane, a_start, cap4, s_start, s_end, s_hist, s_strand, rows, hits_lane);
+                done = true;
             }
         }
+        if (!done) stream_tile<STRANDED, HAS_QUERY, EXCL, false>(P, V, it, lane, a_start, cap4, s_start, s_end, s_hist, s_strand, rows, hits_lane);
         rows_lane += rows;
         if (P.item_rows) {
             const unsigned rows_tile = __reduce_add_sync(kFull, rows);
