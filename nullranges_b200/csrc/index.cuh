@@ -370,8 +370,8 @@ int build_rank_tables(nrb200_handle *h) {
 int ensure_interleaved(nrb200_handle *h) {
     if (h->have_se) return NRB200_OK;
     const int64_t n = h->y.n;
-    NRB_CUDA(h, h->y_se.reserve((size_t)(n + 2) * sizeof(int2)));
-    interleave_ranges_kernel<<<(unsigned)((n + 1 + 255) / 256), 256, 0, h->stream>>>(h->y.start.as<int32_t>(), h->y.end.as<int32_t>(), n,
+    NRB_CUDA(h, h->y_se.reserve((size_t)(n + kSePad) * sizeof(int2)));
+    interleave_ranges_kernel<<<(unsigned)((n + kSePad + 255) / 256), 256, 0, h->stream>>>(h->y.start.as<int32_t>(), h->y.end.as<int32_t>(), n,
                                                                                      h->y_se.as<int2>());
     NRB_CUDA(h, cudaGetLastError());
     h->have_se = true;

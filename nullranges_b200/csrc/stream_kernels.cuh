@@ -171,18 +171,24 @@ __global__ void __launch_bounds__(256) boot_count_kernel(const BootParams P) {
 // within reach of those tiles are ONE contiguous slice of the canonical query arrays; an elected thread brings the
 // slice (start, end, running-max end, caller's position[, strand]) into shared memory with 1-D bulk asynchronous
 // copies (cp.async.bulk + mbarrier: the copy engine works while the CTA draws its blocks and locates their hit
-// windows), and the overlaps are tallied in a shared-memory histogram that leaves the CTA once, one atomic per
+// windows), and the overlaps are tallied in a shared-memory histogram that leaves the CTA once, one global atomic per
 // feature hit instead of one per overlap.  A warp takes a tile at a time and streams its hit window of y from the
-// interleaved {start, end} array: 16 bytes per lane, 64 ranges per load instruction; shift / trim / drop / exclude
-// per range as in the reference (R/bootUnsegmented.R:175-191, R/bootRanges.R:106-116).  The 64 ranges of a load
-// are neighbours on the genome, so the features they can reach are narrowed once per warp (two searches of the
-// shared slice for the warp's smallest start and largest end) and every lane tests only those.
+// interleaved {start, end} array: 16 bytes per lane, 64 ranges per load instruction, the next trip's (or the next
+// tile's first) load in flight while a trip is worked on; shift / trim / drop / exclude per range as in the
+// reference (R/bootUnsegmented.R:175-191, R/bootRanges.R:106-116).  The 64 ranges of a load are neighbours on the
+// genome, so the features they can reach are narrowed once per warp -- the window's two ends step forward over the
+// sorted slice by one ballot each, from the warp's largest end and smallest start -- and every lane tests only those.
+// The kernel is bound by instruction issue (profiles/README.md), so the loop is written for few instructions: tiles
+// that provably stay inside their sequence skip trim() and count rows as hits (Item::interior), the shared arrays are
+// addressed from one register, rows / hits leave a warp once, the total of overlaps is read off the histogram.
 // Bootstrap kinds only (block b lands on tile b); the permute variants and slices that do not fit keep
 // boot_count_kernel.
 constexpr int kGroupTiles = 256;   // tiles per CTA at most (one thread draws each: <= the CTA's 256 threads).  The draw + hit-window
                                    // search is a ~4,000-cycle dependent chain before any range can be streamed: 16 tiles per warp
                                    // make that prologue a fifth of a CTA's life (32 tiles per CTA: nearly half, measured as barrier stalls)
-constexpr int kStreamMinBlocks = 5; // resident CTAs per SM the stream kernel is compiled for (<= 51 registers: no spills)
+constexpr int kStreamMinBlocks = 5; // resident CTAs per SM the stream kernel is compiled for (<= 51 registers: no spills); the plain variant
+                                    // (no strands, no exclusion) fits 40 registers and takes 6
+constexpr int kSePad = 2 * kWarp + 2; // sentinel elements after y's interleaved copy (a whole trip may be loaded from an even index <= n)
 constexpr int kMaxSlice = 2048;    // features of a group's slice at most (shared memory: 21 bytes per feature)
 
 struct TileGroup {
@@ -225,6 +231,16 @@ __device__ __forceinline__ int32_t lds_s32(uint32_t addr) {
     return v;
 }
 __device__ __forceinline__ void red_shared_add(uint32_t addr, int v) { asm volatile("red.shared.add.s32 [%0], %1;" ::"r"(addr), "r"(v) : "memory"); }
+// n += on, as one predicated add (the compiler's own pattern is an add and a predicated move)
+__device__ __forceinline__ void inc_if(unsigned &n, bool on) {
+    asm("{\n"
+        ".reg .pred q;\n"
+        "setp.ne.s32 q, %1, 0;\n"
+        "@q add.u32 %0, %0, 1;\n"
+        "}\n"
+        : "+r"(n)
+        : "r"((int)on));
+}
 // adds 1 where `on` holds, as ONE predicated instruction (no branch around it)
 __device__ __forceinline__ void red_shared_inc_if(bool on, uint32_t addr) {
     asm volatile(
@@ -250,15 +266,20 @@ struct GroupView {
 template <bool STRANDED, bool HAS_QUERY, int EXCL, bool INTERIOR>
 __device__ __forceinline__ void stream_tile(const BootParams &P, const GroupView &V, const Item &it, const int lane, const uint32_t a_start,
                                             const uint32_t cap4, const int32_t *s_start, const int32_t *s_end, int *s_hist,
-                                            const int8_t *s_strand, unsigned &rows_out, unsigned &hits_lane) {
+                                            const int8_t *s_strand, unsigned &rows_out, unsigned &hits_lane, int4 &v, const int32_t next_base) {
     const int32_t q_lo = it.q_lo, q_hi = it.q_hi, x_lo = it.x_lo, x_hi = it.x_hi;
     // the features the warp's current ranges can reach, [w_lo, w_hi) of the shared slice: the ranges come in ascending
     // start order, so both ends only move forward (w_hi may run ahead: every lane tests exactly)
     int32_t w_lo = q_lo, w_hi = q_lo;
     unsigned rows = 0, hits = 0;
-    // ranges i0 and i0 + 1 per lane and trip (the array is padded to an even length)
-    int4 v = make_int4(0, 0, 0, 0);
-    if ((it.lo & ~1) + 2 * lane < it.hi) v = __ldg(reinterpret_cast<const int4 *>(V.se + (it.lo & ~1) + 2 * lane));
+    // Ranges i0 and i0 + 1 per lane and trip.  v holds the lane's pair of the tile's first trip on entry (loaded while the warp
+    // still worked on its previous tile) and the pair of the NEXT tile's first trip on exit; every load is unconditional: the
+    // array carries kSePad sentinel elements at its end and the index tests below discard what lies outside the window.
+    if ((it.lo & ~1) >= it.hi) {  // empty window
+        v = __ldg(reinterpret_cast<const int4 *>(V.se + next_base + 2 * lane));
+        rows_out = 0;
+        return;
+    }
     for (int32_t base = it.lo & ~1; base < it.hi; base += 2 * kWarp) {
         const int32_t i0 = base + 2 * lane;
         int32_t s2[2], e2[2];
@@ -271,7 +292,7 @@ __device__ __forceinline__ void stream_tile(const BootParams &P, const GroupView
             // bootstrap kinds: every range of the window starts at or before the block's end; a hit also ends at or after its start.
             // Only the even-aligned first slot of the first trip can lie before the window.
             const bool hit = (u ? true : i >= it.lo) && i < it.hi && en >= it.bait_start;
-            if (hit) ++hits;
+            inc_if(hits, hit);
             s2[u] = st + it.shift;
             e2[u] = en + it.shift;
             keep[u] = hit;
@@ -297,8 +318,9 @@ __device__ __forceinline__ void stream_tile(const BootParams &P, const GroupView
             }
             if (EXCL == kExclTrim && keep[u] && e2[u] < s2[u]) keep[u] = false;  // a zero-width survivor overlaps no gap
         }
-        // the pair is consumed: the next trip's load goes out now and has the rest of this trip to arrive
-        if (i0 + 2 * kWarp < it.hi) v = __ldg(reinterpret_cast<const int4 *>(V.se + i0 + 2 * kWarp));
+        // the pair is consumed: the next trip's load (the next tile's first, after the last trip) goes out now and has the rest
+        // of this trip to arrive
+        v = __ldg(reinterpret_cast<const int4 *>(V.se + (base + 2 * kWarp < it.hi ? i0 + 2 * kWarp : next_base + 2 * lane)));
         if (EXCL == kExclTrim) {
             // each range is cut to the gaps it overlaps: one row (and one piece to count) per overlap
 #pragma unroll
@@ -323,8 +345,8 @@ __device__ __forceinline__ void stream_tile(const BootParams &P, const GroupView
             continue;
         }
         if (!INTERIOR) {  // (interior tiles: every hit is a row)
-            if (keep[0]) ++rows;
-            if (keep[1]) ++rows;
+            inc_if(rows, keep[0]);
+            inc_if(rows, keep[1]);
         }
         if (HAS_QUERY && q_hi > q_lo) {
             const bool cnt0 = keep[0] && (e2[0] >= s2[0] || kZeroWidthStrictlyInside), cnt1 = keep[1] && (e2[1] >= s2[1] || kZeroWidthStrictlyInside);
@@ -372,7 +394,7 @@ __device__ __forceinline__ void stream_tile(const BootParams &P, const GroupView
 }
 
 template <bool STRANDED, bool HAS_QUERY, int EXCL>
-__global__ void __launch_bounds__(256, kStreamMinBlocks) boot_stream_kernel(const BootParams P, const GroupView V) {
+__global__ void __launch_bounds__(256, (!STRANDED && EXCL == kExclNone) ? kStreamMinBlocks + 1 : kStreamMinBlocks) boot_stream_kernel(const BootParams P, const GroupView V) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ __align__(8) unsigned long long bar;
     __shared__ unsigned long long s_tally[3];  // rows, hits, overlaps of the CTA's tiles
@@ -433,17 +455,21 @@ __global__ void __launch_bounds__(256, kStreamMinBlocks) boot_stream_kernel(cons
     // rows and hits are tallied per lane over all the warp's tiles (a lane sees at most 1/32 of every hit window, so 32 bits hold
     // them) and leave the warp once; the overlaps are read off the histogram when it leaves the CTA.
     unsigned rows_lane = 0, hits_lane = 0;
+    int4 v = make_int4(0, 0, 0, 0);
+    if (warp < grp.count) v = __ldg(reinterpret_cast<const int4 *>(V.se + (s_item[warp].lo & ~1) + 2 * lane));
     for (int j = warp; j < grp.count; j += blockDim.x / kWarp) {
         const Item it = s_item[j];
+        const int j_next = j + blockDim.x / kWarp;
+        const int32_t next_base = (j_next < grp.count ? s_item[j_next].lo : it.lo) & ~1;  // (after the warp's last tile: a load nobody reads)
         unsigned rows = 0;
         bool done = false;
         if constexpr (EXCL == kExclNone) {
             if (it.interior) {
-                stream_tile<STRANDED, HAS_QUERY, EXCL, true>(P, V, it, lane, a_start, cap4, s_start, s_end, s_hist, s_strand, rows, hits_lane);
+                stream_tile<STRANDED, HAS_QUERY, EXCL, true>(P, V, it, lane, a_start, cap4, s_start, s_end, s_hist, s_strand, rows, hits_lane, v, next_base);
                 done = true;
             }
         }
-        if (!done) stream_tile<STRANDED, HAS_QUERY, EXCL, false>(P, V, it, lane, a_start, cap4, s_start, s_end, s_hist, s_strand, rows, hits_lane);
+        if (!done) stream_tile<STRANDED, HAS_QUERY, EXCL, false>(P, V, it, lane, a_start, cap4, s_start, s_end, s_hist, s_strand, rows, hits_lane, v, next_base);
         rows_lane += rows;
         if (P.item_rows) {
             const unsigned rows_tile = __reduce_add_sync(kFull, rows);
@@ -486,11 +512,12 @@ __global__ void __launch_bounds__(256, kStreamMinBlocks) boot_stream_kernel(cons
     }
 }
 
-// y as interleaved {start, end} pairs (one 16-byte load = two ranges); one pad element at the end
+// y as interleaved {start, end} pairs (one 16-byte load = two ranges) followed by kSePad sentinel elements: boot_stream_kernel
+// loads whole trips (2 * kWarp ranges from an even index) without looking at the window's end first
 __global__ void interleave_ranges_kernel(const int32_t *__restrict__ start, const int32_t *__restrict__ end, int64_t n, int2 *__restrict__ se) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) se[i] = make_int2(start[i], end[i]);
-    else if (i == n) se[i] = make_int2(INT32_MAX, INT32_MIN);
+    else if (i < n + kSePad) se[i] = make_int2(INT32_MAX, INT32_MIN);
 }
 
 // ---- materialising path ---------------------------------------------------------------
