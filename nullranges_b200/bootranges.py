@@ -298,13 +298,19 @@ def _boot_moments(eng, y, x, blockLength, R, seg, exclude, excludeOption, propor
         obs = None if observed is None else np.asarray(observed, dtype=np.float64)
         m = eng.run_weighted_moments(draws, observed=obs)
     n = int(R)
-    s, q = m["sum"].astype(np.float64), m["sumsq"].astype(np.float64)
-    mean = s / max(n, 1)
-    var = np.maximum(q - n * mean * mean, 0.0) / max(n - 1, 1)
-    sd = np.sqrt(var)
+    # (in place: with 10^5..10^6 features every temporary is megabytes of fresh pages)
+    mean = np.divide(m["sum"], float(max(n, 1)))                   # exact int64 -> float64 below 2^53
+    sd = np.multiply(mean, mean)
+    sd *= n
+    np.subtract(m["sumsq"], sd, out=sd)                           # q - n * mean^2
+    np.maximum(sd, 0.0, out=sd)
+    sd /= max(n - 1, 1)
+    np.sqrt(sd, out=sd)
     z = p = None
     if obs is not None:
         with np.errstate(divide="ignore", invalid="ignore"):
-            z = (obs - mean) / sd
-        p = (m["n_ge_observed"] + 1.0) / (n + 1.0)
+            z = np.subtract(obs, mean)
+            z /= sd
+        p = np.add(m["n_ge_observed"], 1.0)
+        p /= n + 1.0
     return BootMoments(n, mean, sd, obs, z, p, m["sum"], m["sumsq"], m["stats"])

@@ -65,6 +65,8 @@ void nrb200_destroy(nrb200_handle *h) {
         if (ev) cudaEventDestroy(ev);
     if (h->stage_buf) cudaFreeHost(h->stage_buf);
     if (h->stage_in) cudaFreeHost(h->stage_in);
+    if (h->m_stage) cudaFreeHost(h->m_stage);
+    if (h->y_ev) cudaEventDestroy(h->y_ev);
     if (h->inspect_host) cudaFreeHost(h->inspect_host);
     if (h->flags_host) cudaFreeHost(h->flags_host);
     for (auto &ev : h->batch_ev) cudaEventDestroy(ev);

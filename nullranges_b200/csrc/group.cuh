@@ -274,8 +274,72 @@ void group_destroy(nrb200_handle *g) {
     delete g;
 }
 
-// y for every member.  A large pageable y is copied into pinned memory once (all host threads), so that each
-// member's upload is a plain DMA from the same pinned copy.
+int group_enable_peers(nrb200_handle *g);  // (below, with the gathered result)
+
+// Peer access between all members, probed once and without raising an error (the callers have a path without it).
+bool group_peers_quiet(nrb200_handle *g) {
+    if (g->peers_state == 0) {
+        const std::string keep = g->error;
+        g->peers_state = group_enable_peers(g) == NRB200_OK ? 1 : -1;
+        g->error = keep;
+        cudaGetLastError();
+    }
+    return g->peers_state > 0;
+}
+
+// A large y crosses PCIe ONCE for the whole group: member k uploads the k-th slice of every column to its own GPU and
+// passes it on to the other W - 1 members with peer copies queued behind it on the same stream (NVLink through the
+// NVSwitch: W x faster than W full uploads through the host); a member's stream takes up the inspection of y when all
+// W slices have arrived.  (start, end, seqid[, strand]) are pinned host arrays of n elements.
+int group_scatter_y(nrb200_handle *g, int64_t n, const int32_t *seqid, const int32_t *start, const int32_t *end, const int8_t *strand) {
+    const int W = group_size(g);
+    int rc = group_all(g, [&](int, nrb200_handle *m) {
+        NRB_CUDA(m, cudaSetDevice(m->device));
+        if (int rs = sync_stream(m)) return rs;  // nothing of an earlier call reads the columns any more
+        NRB_CUDA(m, m->y.start.reserve((size_t)n * 4));
+        NRB_CUDA(m, m->y.end.reserve((size_t)n * 4));
+        NRB_CUDA(m, m->y.seqid.reserve((size_t)n * 4));
+        if (strand) NRB_CUDA(m, m->y.strand.reserve((size_t)n));
+        if (!m->y_ev) NRB_CUDA(m, cudaEventCreateWithFlags(&m->y_ev, cudaEventDisableTiming));
+        return NRB200_OK;
+    });
+    if (rc) return rc;
+    auto cut = [&](int k) { return k >= W ? n : (n * k / W) & ~(int64_t)63; };  // slice bounds: multiples of 64 elements
+    rc = group_all(g, [&](int k, nrb200_handle *m) {
+        NRB_CUDA(m, cudaSetDevice(m->device));
+        const int64_t lo = cut(k), cnt = cut(k + 1) - lo;
+        struct Col {
+            DevMem RangeSet::*dst;
+            const void *src;
+            size_t elem;
+        };
+        const Col cols[4] = {{&RangeSet::start, start, 4}, {&RangeSet::end, end, 4}, {&RangeSet::seqid, seqid, 4}, {&RangeSet::strand, strand, 1}};
+        for (const Col &c : cols) {
+            if (!c.src || cnt <= 0) continue;
+            const size_t off = (size_t)lo * c.elem, bytes = (size_t)cnt * c.elem;
+            char *own = static_cast<char *>((m->y.*(c.dst)).p) + off;
+            NRB_CUDA(m, cudaMemcpyAsync(own, static_cast<const char *>(c.src) + off, bytes, cudaMemcpyHostToDevice, m->stream));
+            for (int j = 0; j < W; ++j) {
+                nrb200_handle *peer = g->members[j];
+                if (j == k) continue;
+                NRB_CUDA(m, cudaMemcpyPeerAsync(static_cast<char *>((peer->y.*(c.dst)).p) + off, peer->device, own, m->device, bytes, m->stream));
+            }
+        }
+        NRB_CUDA(m, cudaEventRecord(m->y_ev, m->stream));
+        return NRB200_OK;
+    });
+    if (rc) return rc;
+    return group_all(g, [&](int k, nrb200_handle *m) {
+        NRB_CUDA(m, cudaSetDevice(m->device));
+        for (int j = 0; j < W; ++j)
+            if (j != k) NRB_CUDA(m, cudaStreamWaitEvent(m->stream, g->members[j]->y_ev, 0));
+        return NRB200_OK;
+    });
+}
+
+// y for every member.  A large pageable y is copied into pinned memory once (all host threads); from pinned memory
+// (that copy, or the caller's own) a large y is scattered over the members and exchanged between the GPUs
+// (group_scatter_y), a small one or one without peer access is uploaded by every member from the same pinned copy.
 int group_set_ranges_begin(nrb200_handle *g, int64_t n, int32_t n_seq, const int64_t *seqlengths, const int32_t *seqid,
                            const int32_t *start, const int32_t *end, const int8_t *strand) {
     NRB_CUDA(g, cudaSetDevice(g->device));
@@ -319,7 +383,25 @@ int group_set_ranges_begin(nrb200_handle *g, int64_t n, int32_t n_seq, const int
             }
         }
     }
-    return group_all(g, [&](int, nrb200_handle *m) { return nrb200_set_ranges_begin(m, n, n_seq, seqlengths, seqid, start, end, strand); });
+    // NRB200_SCATTER_MIN (ranges; default 2^20, 0 = never): from this size on y is scattered and exchanged between the GPUs
+    const char *scatter_env = getenv("NRB200_SCATTER_MIN");
+    const int64_t scatter_min = scatter_env ? atoll(scatter_env) : ((int64_t)1 << 20);
+    bool scattered = false;
+    if (scatter_min > 0 && n >= scatter_min && n <= (int64_t)INT32_MAX - 64 && seqid && start && end) {
+        cudaPointerAttributes attr{};
+        const bool pinned = cudaPointerGetAttributes(&attr, start) == cudaSuccess && attr.type == cudaMemoryTypeHost;
+        cudaGetLastError();
+        if (pinned && group_peers_quiet(g)) {
+            if (int rc = group_scatter_y(g, n, seqid, start, end, strand)) return rc;
+            scattered = true;
+        }
+    }
+    return group_all(g, [&](int, nrb200_handle *m) {
+        m->y_preloaded = scattered;
+        const int rc = nrb200_set_ranges_begin(m, n, n_seq, seqlengths, seqid, start, end, strand);
+        m->y_preloaded = false;
+        return rc;
+    });
 }
 
 // ---- runs: member k takes its shard and writes straight into the caller's arrays ------------------------------
@@ -382,25 +464,56 @@ int group_run_moments(nrb200_handle *g, const nrb200_draws *d, int64_t batch_ite
     return NRB200_OK;
 }
 
-// Per-feature moment vectors of all members, summed on the host in member order.
-int group_moments_fetch(nrb200_handle *g, int64_t *feat_sum, int64_t *feat_sumsq, int64_t *feat_n_ge) {
+// Pinned landing place of a member's three per-feature vectors (3 x G x 8 bytes), kept between calls.
+int member_moment_stage(nrb200_handle *m, size_t G) {
+    const size_t need = std::max<size_t>(G, 1) * 24;
+    if (m->m_stage_cap >= need) return NRB200_OK;
+    NRB_CUDA(m, cudaSetDevice(m->device));
+    if (m->m_stage) cudaFreeHost(m->m_stage);
+    m->m_stage = nullptr;
+    m->m_stage_cap = 0;
+    NRB_CUDA(m, cudaMallocHost(&m->m_stage, need));
+    m->m_stage_cap = need;
+    return NRB200_OK;
+}
+
+// out[j][i] = sum over the members, in member order, of vector j of their staging buffers; every member's driver thread adds
+// its share of the features with its own host team (all cores at work, no oversized team left spinning).
+template <class T0, class T1, class T2>
+int group_add_staged(nrb200_handle *g, size_t G, T0 *out0, T1 *out1, T2 *out2) {
     const int W = group_size(g);
+    return group_all(g, [&](int k, nrb200_handle *m) {
+        const int64_t lo = (int64_t)(G * (size_t)k / (size_t)W), hi = (int64_t)(G * (size_t)(k + 1) / (size_t)W);
+#pragma omp parallel for schedule(static) num_threads(host_threads(m))
+        for (int64_t i = lo; i < hi; ++i) {
+            T0 a = 0;
+            T1 b = 0;
+            T2 c = 0;
+            for (int w = 0; w < W; ++w) {
+                const char *base = static_cast<const char *>(g->members[w]->m_stage);
+                a += reinterpret_cast<const T0 *>(base)[i];
+                b += reinterpret_cast<const T1 *>(base + G * 8)[i];
+                c += reinterpret_cast<const T2 *>(base + G * 16)[i];
+            }
+            if (out0) out0[i] = a;
+            if (out1) out1[i] = b;
+            if (out2) out2[i] = c;
+        }
+        return NRB200_OK;
+    });
+}
+
+// Per-feature moment vectors of all members, summed on the host in member order: the W x 3 device-to-host copies land in
+// pinned staging and are in flight together, then the members' threads add them.
+int group_moments_fetch(nrb200_handle *g, int64_t *feat_sum, int64_t *feat_sumsq, int64_t *feat_n_ge) {
     const size_t G = (size_t)g->members[0]->query.n;
-    std::vector<std::vector<int64_t>> part((size_t)W * 3);
-    const int rc = group_all(g, [&](int k, nrb200_handle *m) {
-        for (int j = 0; j < 3; ++j) part[(size_t)k * 3 + j].assign(G, 0);
-        return nrb200_moments_fetch(m, feat_sum ? part[(size_t)k * 3].data() : nullptr, feat_sumsq ? part[(size_t)k * 3 + 1].data() : nullptr,
-                                    feat_n_ge ? part[(size_t)k * 3 + 2].data() : nullptr);
+    const int rc = group_all(g, [&](int, nrb200_handle *m) {
+        if (int rs = member_moment_stage(m, G)) return rs;
+        int64_t *st = static_cast<int64_t *>(m->m_stage);
+        return nrb200_moments_fetch(m, st, st + G, st + 2 * G);
     });
     if (rc) return rc;
-    int64_t *outs[3] = {feat_sum, feat_sumsq, feat_n_ge};
-    for (int j = 0; j < 3; ++j) {
-        if (!outs[j]) continue;
-        std::fill(outs[j], outs[j] + G, (int64_t)0);
-        for (int k = 0; k < W; ++k)
-            for (size_t i = 0; i < G; ++i) outs[j][i] += part[(size_t)k * 3 + j][i];
-    }
-    return NRB200_OK;
+    return group_add_staged<int64_t, int64_t, int64_t>(g, G, feat_sum, feat_sumsq, feat_n_ge);
 }
 
 int group_run_weighted(nrb200_handle *g, const nrb200_draws *d, double *iter_sums, double *feature_sums, nrb200_stats *stats) {
@@ -430,30 +543,17 @@ int group_run_weighted_moments(nrb200_handle *g, const nrb200_draws *d, const do
     const int W = group_size(g);
     const size_t G = (size_t)g->members[0]->query.n;
     std::vector<nrb200_stats> st((size_t)W);
-    std::vector<std::vector<double>> ps((size_t)W), pq((size_t)W);
-    std::vector<std::vector<int64_t>> pg((size_t)W);
     rc = group_all(g, [&](int k, nrb200_handle *m) {
         int64_t lo, n;
         const nrb200_draws s = shard_draws(g, d, k, lo, n);
-        ps[k].assign(G, 0.0);
-        pq[k].assign(G, 0.0);
-        pg[k].assign(G, 0);
-        return nrb200_run_weighted_moments(m, &s, observed, iter_sums ? iter_sums + lo : nullptr, ps[k].data(), pq[k].data(), pg[k].data(),
+        if (int rs = member_moment_stage(m, G)) return rs;
+        char *base = static_cast<char *>(m->m_stage);
+        return nrb200_run_weighted_moments(m, &s, observed, iter_sums ? iter_sums + lo : nullptr, reinterpret_cast<double *>(base),
+                                           reinterpret_cast<double *>(base + G * 8), reinterpret_cast<int64_t *>(base + G * 16),
                                            stats ? &st[k] : nullptr);
     });
     if (rc) return rc;
-    for (size_t i = 0; i < G; ++i) {
-        double a = 0.0, b = 0.0;
-        int64_t c = 0;
-        for (int k = 0; k < W; ++k) {
-            a += ps[k][i];
-            b += pq[k][i];
-            c += pg[k][i];
-        }
-        if (feat_sum) feat_sum[i] = a;
-        if (feat_sumsq) feat_sumsq[i] = b;
-        if (feat_n_ge) feat_n_ge[i] = c;
-    }
+    if ((rc = group_add_staged<double, double, int64_t>(g, G, feat_sum, feat_sumsq, feat_n_ge))) return rc;
     merge_stats(stats, st);
     return NRB200_OK;
 }

@@ -224,6 +224,10 @@ struct nrb200_handle {
     size_t stage_cap = 0;
     void *stage_in = nullptr;         // pinned staging for large pageable INPUT columns (4 regions)
     size_t stage_in_cap = 0;
+    bool y_preloaded = false;         // device groups: the group has already put y's columns on this GPU (group_scatter_y)
+    cudaEvent_t y_ev = nullptr;       // device groups: this member's slice of y has reached every member
+    void *m_stage = nullptr;          // device groups: pinned landing place of this member's three per-feature moment vectors
+    size_t m_stage_cap = 0;
     std::string error;
     int sm_count = 148;
 
@@ -317,6 +321,7 @@ struct nrb200_handle {
         int32_t *counts[kMaxPeers] = {};
     } peer_out;                       // set by the group around a gathered run of this member
     bool peers_enabled = false;       // group handle: every pair of members can store into each other's memory
+    int peers_state = 0;              // group handle: 0 = not probed, 1 = peer access is on, -1 = not available
     int64_t n_rows = 0;
     int64_t dst_tile_items = 0;  // [iterations x blocks] the last run left in d_dst_tile (permute kinds)
 };

@@ -133,7 +133,11 @@ int load_y_begin(nrb200_handle *h, int64_t n, const int32_t *seqid, const int32_
     const unsigned grid = (unsigned)std::min<int64_t>((n + 255) / 256, (int64_t)h->sm_count * 8);
     const HostColumn cols[4] = {{&y.start, start, (size_t)n * 4}, {&y.end, end, (size_t)n * 4}, {&y.seqid, seqid, (size_t)n * 4},
                                 {&y.strand, strand, (size_t)n}};
-    if ((rc = upload_columns(h, cols, strand ? 4 : 3))) return rc;
+    if (h->y_preloaded) {  // member of a device group: the columns are already here (group_scatter_y; this stream waits for them)
+        for (int c = 0; c < (strand ? 4 : 3); ++c) NRB_CUDA(h, cols[c].dst->reserve(cols[c].bytes));
+    } else if ((rc = upload_columns(h, cols, strand ? 4 : 3))) {
+        return rc;
+    }
     inspect_ranges_kernel<<<grid, 256, 0, h->stream>>>(y.seqid.as<int32_t>(), y.start.as<int32_t>(), y.end.as<int32_t>(),
                                                        strand ? y.strand.as<int8_t>() : nullptr, n, C,
                                                        reinterpret_cast<InspectOut *>(base), reinterpret_cast<unsigned *>(base + kHead),

@@ -115,15 +115,31 @@ def cfg4(args):
     y, x = synth.points(10_000_000, seed=6), synth.enhancers(200_000, seed=7)
     gpus = args.gpus if args.gpus > 1 else None
     times, sig = [], None
+    laps = []
+    if args.detail:  # wall clock of every engine call the front end makes (the calls are synchronous unless noted in engine.py)
+        from nullranges_b200 import engine as _e
+        for name in ("set_ranges", "set_exclude", "clear_exclude", "set_plan", "set_query", "finish_ranges", "ranges_info", "count_observed", "run_moments"):
+            def wrap(f, name=name):
+                def g(*a, **k):
+                    t = time.perf_counter()
+                    try:
+                        return f(*a, **k)
+                    finally:
+                        laps.append((name, round(1e3 * (time.perf_counter() - t), 3)))
+                return g
+            setattr(_e.Engine, name, wrap(getattr(_e.Engine, name)))
     for rep in range(args.reps + 1):
+        laps.clear()
         t0 = time.perf_counter()
         m = bootMoments(y, x, L_B, R=10_000, withinChrom=True, rng="philox", seed=1, gpus=gpus)
-        times.append(time.perf_counter() - t0)
+        last = time.perf_counter() - t0
+        times.append(last)
         sig = (int(m.sum.sum()), int(m.sumsq.sum() % (1 << 61)), float(np.nansum(m.p_ge)))
         kernel_ms = m.stats["kernel_ms"]
     times = sorted(times[1:])
     print(json.dumps({"mode": "cfg4", "gpus": args.gpus, "R": 10_000, "wall_ms_min": 1e3 * times[0], "wall_ms_median": 1e3 * times[len(times) // 2],
-                      "kernel_ms_slowest_gpu": kernel_ms, "signature": sig, "env": {k: v for k, v in os.environ.items() if k.startswith("NRB200_")}}), flush=True)
+                      "kernel_ms_slowest_gpu": kernel_ms, "signature": sig, "env": {k: v for k, v in os.environ.items() if k.startswith("NRB200_")},
+                      **({"last_call_laps_ms": list(laps), "last_call_ms": round(1e3 * last, 3)} if args.detail else {})}), flush=True)
 
 
 def cfg1(args):
@@ -162,6 +178,7 @@ def calib(args):
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("mode", choices=["step", "kernels", "sweep", "timeline", "calib", "cfg4", "cfg1"])
+    ap.add_argument("--detail", action="store_true", help="cfg4: wall clock of every engine call of the last repetition")
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--dest", default="pinned", choices=["pinned", "pageable", "fresh"])
     ap.add_argument("--reps", type=int, default=9)

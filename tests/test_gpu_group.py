@@ -127,6 +127,36 @@ def test_group_weighted_sums(groups):
         assert np.array_equal(got_m["n_ge_observed"], one_m["n_ge_observed"])
 
 
+@pytest.mark.parametrize("how", ["pageable", "pinned", "pinned_unsorted_stranded"])
+def test_group_scattered_upload(groups, how, monkeypatch):
+    """A large y crosses PCIe once for the whole group: every member uploads one slice and hands it to the others with peer copies
+    (group_scatter_y; here forced for a small y with NRB200_SCATTER_MIN).  Same index, same counts as one GPU -- from a pageable y
+    (goes through the group's pinned copy; needs columns of 256 KB or more), from pinned arrays, and for an unsorted, stranded y
+    (sorted on every GPU after the exchange)."""
+    import torch
+    single, made = groups
+    n = 70_000 if how == "pageable" else 3_001   # 3001: the slices' ragged ends
+    case = H.random_case(seed=91, n=n, n_seq=5, max_len=400_000, n_query=300, L_b=20_000, stranded=how.endswith("stranded"),
+                         sort=not how.endswith("unsorted_stranded"))
+    if how != "pageable":
+        case["y"] = tuple(None if a is None else torch.from_numpy(a).pin_memory().numpy() for a in case["y"])
+    d = Draws(n_iter=7, rng_mode=_lib.RNG_PHILOX, seed=12)
+    kind = 1 if how == "pinned_unsorted_stranded" else 0  # (the across-chromosome sampler insists on a sorted y)
+    H.load_engine(single, case, kind)
+    one = single.run_counts(d)
+    for devs, eng in made.items():
+        monkeypatch.setenv("NRB200_SCATTER_MIN", "0")  # (0: never)
+        H.load_engine(eng, case, kind)
+        plain = eng.run_counts(d)
+        monkeypatch.setenv("NRB200_SCATTER_MIN", "1")
+        H.load_engine(eng, case, kind)
+        got = eng.run_counts(d)
+        for k in ("iter_nranges", "iter_totals", "feature_counts"):
+            assert np.array_equal(got[k], one[k]), (devs, k)
+            assert np.array_equal(plain[k], one[k]), (devs, k)
+        assert eng.ranges_info() == single.ranges_info()
+
+
 def test_group_errors_and_unsupported(groups):
     single, made = groups
     from nullranges_b200 import EngineError
