@@ -167,11 +167,29 @@ int group_lead(nrb200_handle *g, const std::function<int(nrb200_handle *)> &fn) 
 
 // Before a run: the leader prepares first (it builds the window lists), the others then take its lists.  Nothing happens when no input changed since the last run.
 int group_prepare(nrb200_handle *g) {
-    // (on the leader's own driver thread, with the leader's own share of the host threads: a larger team's idle threads
-    // would spin on the cores the other members' driver threads need right after)
-    const nrb200_handle *lead = g->members[0];
+    nrb200_handle *lead = g->members[0];
     if (lead->have_y && lead->have_plan && !lead->slices_dirty) return NRB200_OK;  // nothing changed since the last run: no dispatch
-    return group_all(g, [](int k, nrb200_handle *m) { return k == 0 ? prepare(m) : NRB200_OK; });
+    // The leader prepares on the calling thread; the per-sequence passes of its list building are handed to the driver
+    // threads of all members, each with its own share of the host threads: every core builds, and no team is larger than a
+    // member's share (a larger team's idle threads would spin on the cores the members' driver threads need right after).
+    NRB_CUDA(g, cudaSetDevice(lead->device));
+    std::atomic<int> next{0};
+    lead->seq_runner = [&](int n, const std::function<void(int)> &body) {
+        next.store(0);
+        group_all(g, [&](int, nrb200_handle *m) {
+#pragma omp parallel num_threads(host_threads(m))
+            for (;;) {
+                const int i = next.fetch_add(1);
+                if (i >= n) break;
+                body(i);
+            }
+            return NRB200_OK;
+        });
+    };
+    const int rc = prepare(lead);
+    lead->seq_runner = nullptr;
+    if (rc) g->error = "GPU " + std::to_string(lead->device) + ": " + lead->error;
+    return rc;
 }
 
 int group_create(const nrb200_config *cfg, nrb200_handle **out) {

@@ -224,6 +224,9 @@ struct nrb200_handle {
     size_t stage_cap = 0;
     void *stage_in = nullptr;         // pinned staging for large pageable INPUT columns (4 regions)
     size_t stage_in_cap = 0;
+    // device groups, leader only, set around prepare(): runs body(0..n-1) on the driver threads of ALL members, each with its own
+    // host team (the window lists are built once, by every core of the box, without a team larger than a member's share)
+    std::function<void(int, const std::function<void(int)> &)> seq_runner;
     bool y_preloaded = false;         // device groups: the group has already put y's columns on this GPU (group_scatter_y)
     cudaEvent_t y_ev = nullptr;       // device groups: this member's slice of y has reached every member
     void *m_stage = nullptr;          // device groups: pinned landing place of this member's three per-feature moment vectors

@@ -282,14 +282,22 @@ int build_pairs(nrb200_handle *h) {
     std::vector<int32_t> len(G, 0);
     std::vector<int64_t> hist((size_t)C * kBins, 0), long_sum(C, 0);
     auto bin = [&](int64_t k) { return std::min<int>(len[k], kBins - 1); };
+    // body(c) for every sequence, in parallel: this handle's host team, or -- the leader of a device group -- all members' teams
+    auto for_each_sequence = [&](const std::function<void(int)> &body) {
+        if (h->seq_runner && G >= 4096) {
+            h->seq_runner(C, body);
+            return;
+        }
 #pragma omp parallel for schedule(dynamic, 1) num_threads(host_threads(h)) if (G >= 4096)
-    for (int c = 0; c < C; ++c) {
+        for (int c = 0; c < C; ++c) body(c);
+    };
+    for_each_sequence([&](int c) {
         enumerate_seq(c, [](int32_t) {}, [&](int32_t k, int32_t, int64_t, int64_t, int, int) { ++len[k]; });
         for (int32_t k = q.h_seq_off[c]; k < q.h_seq_off[c + 1]; ++k) {
             hist[(size_t)c * kBins + bin(k)]++;
             if (len[k] >= kBins - 1) long_sum[c] += len[k];
         }
-    }
+    });
     tr.lap("pass1");
     std::vector<int64_t> pos_start((size_t)C * kBins);  // first position of the (sequence, bin) group
     int64_t bin_first[kBins], rec_first[kBins];
@@ -323,8 +331,7 @@ int build_pairs(nrb200_handle *h) {
         f_recs_vec.resize((size_t)(4 * total));
         f_recs = reinterpret_cast<Rec4 *>(f_recs_vec.data());
     }
-#pragma omp parallel for schedule(dynamic, 1) num_threads(host_threads(h)) if (G >= 4096)
-    for (int c = 0; c < C; ++c) {
+    for_each_sequence([&](int c) {
         int64_t cursor = 0, long_cursor = long_rec[c];
         int64_t *next_pos = &pos_start[(size_t)c * kBins];
         enumerate_seq(c,
@@ -345,7 +352,7 @@ int build_pairs(nrb200_handle *h) {
                                                 (int32_t)std::min<int64_t>(we, INT32_MAX / 2), p.tile_start[t]};
                           ++cursor;
                       });
-    }
+    });
     tr.lap("lists");
     if ((rc = upload(h, h->f_src, f_src.data(), (size_t)G))) return rc;
     if ((rc = upload(h, h->pair_off, f_off.data(), (size_t)G + 1))) return rc;

@@ -157,6 +157,22 @@ def test_group_scattered_upload(groups, how, monkeypatch):
         assert eng.ranges_info() == single.ranges_info()
 
 
+@pytest.mark.parametrize("kind,n_excl", [(0, 0), (2, 40)])
+def test_group_window_lists_built_by_all_members(groups, kind, n_excl):
+    """From 4096 features on, the leader's two per-sequence passes of the window-list building run on the driver threads of
+    all members (group_prepare / seq_runner): same lists, same counts as one GPU."""
+    single, made = groups
+    case = H.random_case(seed=640 + kind, n=30_000, n_seq=7, max_len=300_000, n_query=5_000, n_excl=n_excl, n_seg=21, L_b=9_000)
+    d = Draws(n_iter=5, rng_mode=_lib.RNG_PHILOX, seed=21)
+    H.load_engine(single, case, kind)
+    one = single.run_counts(d)
+    for devs, eng in made.items():
+        H.load_engine(eng, case, kind)
+        got = eng.run_counts(d)
+        for k in ("iter_nranges", "iter_totals", "feature_counts"):
+            assert np.array_equal(got[k], one[k]), (devs, k)
+
+
 def test_group_errors_and_unsupported(groups):
     single, made = groups
     from nullranges_b200 import EngineError
