@@ -389,8 +389,8 @@ int group_set_ranges_begin(nrb200_handle *g, int64_t n, int32_t n_seq, const int
                         const int64_t p0 = pieces * k / W, p1 = pieces * (k + 1) / W;
 #pragma omp parallel for schedule(static) num_threads(host_threads(m))
                         for (int64_t i = p0; i < p1; ++i)
-                            std::memcpy(base + c * col + i * piece, static_cast<const char *>(src[c]) + i * piece,
-                                        std::min(piece, bytes[c] - (size_t)i * piece));
+                            copy_streaming(static_cast<const char *>(src[c]) + i * piece, base + c * col + i * piece,
+                                           std::min(piece, bytes[c] - (size_t)i * piece));
                     }
                     return NRB200_OK;
                 });

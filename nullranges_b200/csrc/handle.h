@@ -35,6 +35,7 @@ namespace nrb {
 
 void widen_u16_to_i32(const uint16_t *src, int32_t *dst, size_t n);  // host_simd.cpp
 const char *widen_variant();
+void copy_streaming(const void *src, void *dst, size_t bytes);  // host_simd.cpp: memcpy with non-temporal stores (staging for DMA)
 
 // NVTX ranges around the stages of a call (upload, index build, window lists, chunks, drain): visible in Nsight
 // Systems / Compute timelines, no-ops when no tool is attached (NVTX3 is header-only).
@@ -368,7 +369,8 @@ int upload(nrb200_handle *h, DevMem &dst, const T *src, size_t n) {
     if (!h->arena && cudaMallocHost((void **)&h->arena, kArenaBytes) == cudaSuccess) h->arena_cap = kArenaBytes;
     const size_t at = (h->arena_used + 255) & ~(size_t)255;
     if (h->arena && at + bytes <= h->arena_cap) {
-        std::memcpy(h->arena + at, src, bytes);
+        if (bytes >= ((size_t)64 << 10)) copy_streaming(src, h->arena + at, bytes);  // (a DMA engine reads it next: keep it out of the caches)
+        else std::memcpy(h->arena + at, src, bytes);
         h->arena_used = at + bytes;
         NRB_CUDA(h, cudaMemcpyAsync(dst.p, h->arena + at, bytes, cudaMemcpyHostToDevice, h->stream));
     } else {
@@ -481,7 +483,7 @@ int upload_direct(nrb200_handle *h, DevMem &dst, const T *src, size_t n, int slo
                 const int64_t pieces = (int64_t)((bytes + piece - 1) / piece);
 #pragma omp parallel for schedule(static) num_threads(host_threads(h))
                 for (int64_t i = 0; i < pieces; ++i)
-                    std::memcpy(to + i * piece, reinterpret_cast<const char *>(src) + i * piece, std::min(piece, bytes - (size_t)i * piece));
+                    copy_streaming(reinterpret_cast<const char *>(src) + i * piece, to + i * piece, std::min(piece, bytes - (size_t)i * piece));
                 from = to;
             }
         }
@@ -538,12 +540,13 @@ inline int upload_columns(nrb200_handle *h, const HostColumn *cols, int n_cols) 
             const size_t bytes = cols[c].bytes;
             const int64_t pieces = (int64_t)((bytes + piece - 1) / piece);
 #pragma omp for schedule(static)
-            for (int64_t i = 0; i < pieces; ++i) std::memcpy(to + i * piece, from + i * piece, std::min(piece, bytes - (size_t)i * piece));
+            for (int64_t i = 0; i < pieces; ++i) copy_streaming(from + i * piece, to + i * piece, std::min(piece, bytes - (size_t)i * piece));
 #pragma omp master
             {
                 if (bytes) {
                     const cudaError_t e = cudaMemcpyAsync(cols[c].dst->p, to, bytes, cudaMemcpyHostToDevice, h->stream);
                     if (e != cudaSuccess) err = e;
+                    h->timeline.mark("column uploaded", h->stream);
                 }
             }
             at += (bytes + 4095) & ~(size_t)4095;

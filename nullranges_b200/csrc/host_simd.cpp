@@ -83,6 +83,59 @@ void widen_u16_to_i32(const uint16_t *src, int32_t *dst, size_t n) {
     fn(src, dst, n);
 }
 
+// Copy with streaming (non-temporal) stores: staging of host data that a DMA engine reads next.  Lines written with
+// ordinary stores sit dirty in the writing cores' caches and every PCIe read of them has to be snooped out (measured:
+// a 4 MB column staged by memcpy uploads at 30 GB/s instead of the link's 50+); streamed lines are in DRAM.
+#ifdef NRB_X86
+__attribute__((target("avx2"))) static void copy_stream_avx2(const char *src, char *dst, size_t n) {
+    size_t i = 0;
+    while (i < n && (reinterpret_cast<uintptr_t>(dst + i) & 31)) {
+        dst[i] = src[i];
+        ++i;
+    }
+    for (; i + 128 <= n; i += 128) {
+        const __m256i a = _mm256_loadu_si256(reinterpret_cast<const __m256i *>(src + i));
+        const __m256i b = _mm256_loadu_si256(reinterpret_cast<const __m256i *>(src + i + 32));
+        const __m256i c = _mm256_loadu_si256(reinterpret_cast<const __m256i *>(src + i + 64));
+        const __m256i d = _mm256_loadu_si256(reinterpret_cast<const __m256i *>(src + i + 96));
+        _mm256_stream_si256(reinterpret_cast<__m256i *>(dst + i), a);
+        _mm256_stream_si256(reinterpret_cast<__m256i *>(dst + i + 32), b);
+        _mm256_stream_si256(reinterpret_cast<__m256i *>(dst + i + 64), c);
+        _mm256_stream_si256(reinterpret_cast<__m256i *>(dst + i + 96), d);
+    }
+    _mm_sfence();
+    for (; i < n; ++i) dst[i] = src[i];
+}
+static void copy_stream_sse2(const char *src, char *dst, size_t n) {
+    size_t i = 0;
+    while (i < n && (reinterpret_cast<uintptr_t>(dst + i) & 15)) {
+        dst[i] = src[i];
+        ++i;
+    }
+    for (; i + 32 <= n; i += 32) {
+        const __m128i a = _mm_loadu_si128(reinterpret_cast<const __m128i *>(src + i));
+        const __m128i b = _mm_loadu_si128(reinterpret_cast<const __m128i *>(src + i + 16));
+        _mm_stream_si128(reinterpret_cast<__m128i *>(dst + i), a);
+        _mm_stream_si128(reinterpret_cast<__m128i *>(dst + i + 16), b);
+    }
+    _mm_sfence();
+    for (; i < n; ++i) dst[i] = src[i];
+}
+#endif
+
+void copy_streaming(const void *src, void *dst, size_t bytes) {
+#ifdef NRB_X86
+    using Fn = void (*)(const char *, char *, size_t);
+    static const Fn fn = [] {
+        __builtin_cpu_init();
+        return __builtin_cpu_supports("avx2") ? (Fn)copy_stream_avx2 : (Fn)copy_stream_sse2;
+    }();
+    fn(static_cast<const char *>(src), static_cast<char *>(dst), bytes);
+#else
+    __builtin_memcpy(dst, src, bytes);
+#endif
+}
+
 const char *widen_variant() {
 #ifdef NRB_X86
     __builtin_cpu_init();

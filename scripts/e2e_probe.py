@@ -44,6 +44,27 @@ def inputs(pin: bool):
     return y, x, keep
 
 
+def engine_laps():
+    """--detail: wraps every engine call the front ends make; returns the list that collects (call, start ms, duration ms),
+    start relative to the first call since the list was last cleared."""
+    from nullranges_b200 import engine as _e
+    laps = []
+    for name in ("set_ranges", "set_exclude", "clear_exclude", "set_plan", "set_query", "finish_ranges", "ranges_info", "count_observed",
+                 "run_moments", "run_counts"):
+        def wrap(f, name=name):
+            def g(*a, **k):
+                t = time.perf_counter()
+                if not laps:
+                    laps.append(("t0", t, 0.0))
+                try:
+                    return f(*a, **k)
+                finally:
+                    laps.append((name, round(1e3 * (t - laps[0][1]), 3), round(1e3 * (time.perf_counter() - t), 3)))
+            return g
+        setattr(_e.Engine, name, wrap(getattr(_e.Engine, name)))
+    return laps
+
+
 def step(args):
     import numpy as np
     import torch
@@ -59,16 +80,21 @@ def step(args):
         out = {"iter_totals": np.zeros(R, np.int64), "iter_nranges": np.zeros(R, np.int64), "feature_counts": np.zeros((R, G), np.int32)}
     gpus = args.gpus if args.gpus > 1 else None
     times, check = [], None
+    laps = engine_laps() if args.detail else []
     for rep in range(args.reps + 2):
+        laps.clear()
         t0 = time.perf_counter()
         res = bootCounts(y, x, L_B, R=R, rng="philox", seed=2024, iter0=0, out=out, gpus=gpus)
         times.append(time.perf_counter() - t0)
+        last = (t0, times[-1])
         check = int(res.iter_totals.sum()), int(res.feature_counts[:: max(R // 7, 1)].sum())
         del res
     times = sorted(times[2:])
     print(json.dumps({"mode": "step", "gpus": args.gpus, "dest": args.dest, "R": R, "ms_min": 1e3 * times[0], "ms_median": 1e3 * times[len(times) // 2],
                       "iters_per_s_median": R / times[len(times) // 2], "checksum": check,
-                      "env": {k: v for k, v in os.environ.items() if k.startswith("NRB200_")}}), flush=True)
+                      "env": {k: v for k, v in os.environ.items() if k.startswith("NRB200_")},
+                      **({"last_call_ms": round(1e3 * last[1], 3), "first_engine_call_at_ms": round(1e3 * (laps[0][1] - last[0]), 3),
+                          "last_call_laps_ms": laps[1:]} if args.detail else {})}), flush=True)
 
 
 def kernels(args):
@@ -115,19 +141,7 @@ def cfg4(args):
     y, x = synth.points(10_000_000, seed=6), synth.enhancers(200_000, seed=7)
     gpus = args.gpus if args.gpus > 1 else None
     times, sig = [], None
-    laps = []
-    if args.detail:  # wall clock of every engine call the front end makes (the calls are synchronous unless noted in engine.py)
-        from nullranges_b200 import engine as _e
-        for name in ("set_ranges", "set_exclude", "clear_exclude", "set_plan", "set_query", "finish_ranges", "ranges_info", "count_observed", "run_moments"):
-            def wrap(f, name=name):
-                def g(*a, **k):
-                    t = time.perf_counter()
-                    try:
-                        return f(*a, **k)
-                    finally:
-                        laps.append((name, round(1e3 * (time.perf_counter() - t), 3)))
-                return g
-            setattr(_e.Engine, name, wrap(getattr(_e.Engine, name)))
+    laps = engine_laps() if args.detail else []
     for rep in range(args.reps + 1):
         laps.clear()
         t0 = time.perf_counter()
@@ -139,7 +153,7 @@ def cfg4(args):
     times = sorted(times[1:])
     print(json.dumps({"mode": "cfg4", "gpus": args.gpus, "R": 10_000, "wall_ms_min": 1e3 * times[0], "wall_ms_median": 1e3 * times[len(times) // 2],
                       "kernel_ms_slowest_gpu": kernel_ms, "signature": sig, "env": {k: v for k, v in os.environ.items() if k.startswith("NRB200_")},
-                      **({"last_call_laps_ms": list(laps), "last_call_ms": round(1e3 * last, 3)} if args.detail else {})}), flush=True)
+                      **({"last_call_laps_ms": laps[1:], "last_call_ms": round(1e3 * last, 3)} if args.detail else {})}), flush=True)
 
 
 def cfg1(args):
@@ -178,7 +192,7 @@ def calib(args):
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("mode", choices=["step", "kernels", "sweep", "timeline", "calib", "cfg4", "cfg1"])
-    ap.add_argument("--detail", action="store_true", help="cfg4: wall clock of every engine call of the last repetition")
+    ap.add_argument("--detail", action="store_true", help="step / cfg4: start and duration of every engine call of the last repetition")
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--dest", default="pinned", choices=["pinned", "pageable", "fresh"])
     ap.add_argument("--reps", type=int, default=9)
