@@ -412,7 +412,10 @@ def run_gpu(args):
                                     "buffers": "as e2e, but the result matrix is allocated inside every call (an R call allocates its result): "
                                                "the difference is the kernel zeroing and mapping the fresh pages"},
                "e2e_pinned": {"value": Rt / t_pin, "unit": "iter/s", "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": int(res_pin.stats["d2h_bytes"]),
-                              "steps": e2e_steps, "ms_per_step": 1e3 * t_pin, "buffers": "pinned inputs and pinned preallocated outputs (int32 on the wire)"}}
+                              "steps": e2e_steps, "ms_per_step": 1e3 * t_pin, "buffers": "pinned inputs and pinned preallocated outputs ("
+                                         + ("int32 on the wire: plain DMA into the caller's matrix, what the engine chooses from 4 GPUs on, where the host's memory is the bottleneck)"
+                                            if int(res_pin.stats["d2h_bytes"]) >= 4 * Rt * G else
+                                            "uint16 on the wire, widened into the caller's int32 matrix by the host threads: faster than DMA of the int32 matrix up to 2 GPUs)")}}
         e2e["e2e_pinned_uint16"] = {"value": Rt / t_u16, "unit": "iter/s", "d2h_bytes_per_step": int(res_u16.stats["d2h_bytes"]), "ms_per_step": 1e3 * t_u16,
                                     "buffers": "pinned inputs, pinned uint16 result (bootCounts(..., counts_dtype = uint16)): half the bytes into host memory; "
                                                "not what an R caller gets (R's integer is 32-bit) -- reported beside the headline, not as it",

@@ -217,6 +217,7 @@ int group_create(const nrb200_config *cfg, nrb200_handle **out) {
             return rc;  // the message is already in place
         }
         m->omp_threads = std::max(1, cores / W);
+        m->group_w = W;
         m->keep_lists = k == 0;
         m->lists_from = k == 0 ? nullptr : g->members[0];
         g->members.push_back(m);

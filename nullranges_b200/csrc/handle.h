@@ -277,7 +277,8 @@ struct nrb200_handle {
     bool tune_stream_old = false;      // NRB200_STREAM_OLD=1: streaming path through boot_count_kernel only (A/B)
     int tune_rows_ipc = 4;             // NRB200_ROWS_IPC: iterations a CTA of the rows kernel loops over
     double tune_table_mult = 4.0;
-    int tune_wire16 = 2;               // NRB200_WIRE16: uint16 wire format of a host-bound matrix (0 never, 1 always, 2 pageable destinations)
+    int tune_wire16 = 2;               // NRB200_WIRE16: uint16 wire format of a host-bound matrix (0 never, 1 always, 2 = where it pays: run.cuh)
+    int group_w = 1;                   // members of the device group this handle belongs to (1: a handle of its own)
     int tune_chunks = 8;               // NRB200_CHUNKS: pipeline depth of nrb200_run_counts
     int64_t tune_max_batch = 2048;     // NRB200_MAX_BATCH: iterations per launch group
     int64_t tune_table_cap = 8 << 20;  // NRB200_TABLE_CAP: the multiplier applies up to this many entries

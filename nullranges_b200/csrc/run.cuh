@@ -354,9 +354,13 @@ int run_counts_core(nrb200_handle *h, const nrb200_draws *d, bool want_counts, i
         cudaGetLastError();  // an unregistered pointer may leave a sticky-free error behind on older drivers
     }
     const size_t cells = (size_t)R * (size_t)std::max<int64_t>(G, 0);
-    // tune_wire16: 0 never, 1 always, 2 (default) for pageable destinations only -- a pinned destination takes the
-    // int32 matrix by DMA without any host work
-    bool wire16 = pipelined && rank_path_ok(h) && cells * 2 <= kMaxStagingBytes && (h->tune_wire16 == 1 || (h->tune_wire16 == 2 && pageable));
+    // tune_wire16: 0 never, 1 always, 2 (default) where it pays.  A pageable destination always does (the matrix has to be
+    // moved by the host anyway).  A pinned one could take the int32 matrix by DMA without any host work, but half the bytes
+    // on the wire and a widening pass by the host threads is faster as long as the host has the bandwidth to spare: 1.65
+    // against 2.14 ms per 1000 iterations on one GPU, 1.96 against 2.25 ms per 2000 on two; from four GPUs on the host's
+    // memory is the bottleneck (device groups) and plain DMA wins (8 GPUs: 7.8 against 10 ms per 8000).
+    bool wire16 = pipelined && rank_path_ok(h) && cells * 2 <= kMaxStagingBytes &&
+                  (h->tune_wire16 == 1 || (h->tune_wire16 == 2 && (pageable || h->group_w <= 2)));
     if (host16) wire16 = pipelined;
     const bool stage16 = wire16 && !(host16 && !pageable);  // a pinned uint16 destination takes the chunks by DMA as they are
     if (host16 && pageable && cells * 2 > kMaxStagingBytes) return fail(h, NRB200_ERR_UNSUPPORTED, "uint16 counts into pageable memory: the matrix exceeds the staging limit; use a pinned buffer or fewer iterations per call");

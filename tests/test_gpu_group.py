@@ -173,6 +173,24 @@ def test_group_window_lists_built_by_all_members(groups, kind, n_excl):
             assert np.array_equal(got[k], one[k]), (devs, k)
 
 
+def test_group_wire_format_policy(groups):
+    """A pinned [R x G] int32 destination: up to 2 GPUs the matrix crosses PCIe as uint16 and the host widens it (faster while the
+    host has bandwidth to spare); from 3 members on every GPU copies its int32 rows by DMA (run.cuh, tune_wire16).  Same matrix."""
+    import torch
+    single, made = groups
+    case = H.random_case(seed=19, n=2500, n_seq=3, n_query=130)
+    R, G = 390, 130
+    d = Draws(n_iter=R, rng_mode=_lib.RNG_PHILOX, seed=6)
+    H.load_engine(single, case, 0)
+    one = single.run_counts(d)
+    for devs, eng in made.items():
+        keep = torch.empty((R, G), dtype=torch.int32, pin_memory=True)
+        H.load_engine(eng, case, 0)
+        got = eng.run_counts(d, out={"feature_counts": keep.numpy()})
+        assert np.array_equal(got["feature_counts"], one["feature_counts"]), devs
+        assert got["stats"]["d2h_bytes"] == 2 * R * 8 + R * G * (2 if len(devs) <= 2 else 4), devs
+
+
 def test_group_errors_and_unsupported(groups):
     single, made = groups
     from nullranges_b200 import EngineError
