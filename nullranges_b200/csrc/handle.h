@@ -398,9 +398,22 @@ int upload_staged(nrb200_handle *h, DevMem &dst, const T *arena_src, size_t n) {
 // A large pageable destination is usually freshly allocated: ask for huge pages before the first touch, so that the
 // staging copies below fault in 2 MB at a time instead of 4 KB (no effect when the system does not allow it).
 inline void advise_huge_pages(void *dst, size_t bytes) {
+    static const bool off = getenv("NRB200_HUGEPAGES") && atoi(getenv("NRB200_HUGEPAGES")) == 0;  // NRB200_HUGEPAGES=0: leave the pages as they are (A/B)
+    if (off) return;
     constexpr uintptr_t kHuge = (uintptr_t)2 << 20;
     const uintptr_t lo = ((uintptr_t)dst + kHuge - 1) & ~(kHuge - 1), hi = ((uintptr_t)dst + bytes) & ~(kHuge - 1);
     if (hi > lo) madvise((void *)lo, hi - lo, MADV_HUGEPAGE);
+}
+
+// Fault in the pages of [p, p + bytes) for writing with ONE call (MADV_POPULATE_WRITE, Linux 5.14+): the kernel maps and
+// zeroes them without a trap per page.  Returns false where the call is not available; the caller then touches the pages.
+inline bool populate_pages(void *p, size_t bytes) {
+#ifndef MADV_POPULATE_WRITE
+#define MADV_POPULATE_WRITE 23
+#endif
+    if (!bytes) return true;
+    const uintptr_t lo = (uintptr_t)p & ~(uintptr_t)4095, hi = ((uintptr_t)p + bytes + 4095) & ~(uintptr_t)4095;
+    return madvise((void *)lo, hi - lo, MADV_POPULATE_WRITE) == 0;
 }
 
 // Device -> host copy into a caller-owned buffer, complete on return.  Pinned destinations take one DMA; large

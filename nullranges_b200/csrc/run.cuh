@@ -494,23 +494,21 @@ int run_counts_core(nrb200_handle *h, const nrb200_draws *d, bool want_counts, i
 #pragma omp parallel num_threads(host_threads(h))
         {
             const int tid = omp_get_thread_num(), nth = omp_get_num_threads();
-            if (pageable) {
-                // A freshly allocated destination (every R call's result is) faults its pages in on first touch.  Each
-                // thread touches the pages of the slices it will fill NOW, while the first chunks still compute and
+            if (pageable && nth > 1 && tid > 0) {
+                // A freshly allocated destination (every R call's result is) faults its pages in on first touch, and with
+                // transparent huge pages (numpy and glibc ask for them for a matrix this size) one fault zeroes 2 MB: ~0.15 ms
+                // during which every other thread that needs the same 2 MB waits.  So the threads take whole 2 MB blocks of the
+                // destination in turn, lowest addresses (first chunks) first, NOW, while the first chunks still compute and
                 // travel, instead of inside the conversion loop.  (Thread 0 goes straight to the copy events.)
-                for (int64_t c = 0; c < n_chunks && tid > 0; ++c) {
-                    const size_t elems = (size_t)staged[c].second * G;
-                    const size_t per = ((elems + nth - 1) / nth + 15) & ~(size_t)15;
-                    const size_t lo = std::min(elems, (size_t)tid * per), hi = std::min(elems, lo + per);
-                    if (host16) {
-                        volatile uint16_t *dst = host16 + staged[c].first * G;
-                        for (size_t i = lo; i < hi; i += 2048) dst[i] = 0;  // one store per 4 KB page
-                        if (hi > lo) dst[hi - 1] = 0;
-                    } else {
-                        volatile int32_t *dst = host_counts + staged[c].first * G;
-                        for (size_t i = lo; i < hi; i += 1024) dst[i] = 0;
-                        if (hi > lo) dst[hi - 1] = 0;
-                    }
+                char *base = host16 ? reinterpret_cast<char *>(host16) : reinterpret_cast<char *>(host_counts);
+                const size_t total = cells * (host16 ? 2 : 4);
+                constexpr uintptr_t kBlock = (uintptr_t)2 << 20;
+                const uintptr_t first = (uintptr_t)base & ~(kBlock - 1), end = (uintptr_t)base + total;
+                for (uintptr_t blk = first + (uintptr_t)(tid - 1) * kBlock; blk < end; blk += (uintptr_t)(nth - 1) * kBlock) {
+                    char *lo = reinterpret_cast<char *>(std::max(blk, (uintptr_t)base)), *hi = reinterpret_cast<char *>(std::min(blk + kBlock, end));
+                    if (populate_pages(lo, (size_t)(hi - lo))) continue;  // one call, no trap per page
+                    for (volatile char *q = lo; q < hi; q += 4096) *q = 0;  // (older kernels: one store per 4 KB page)
+                    *(volatile char *)(hi - 1) = 0;
                 }
             }
             for (int64_t c = 0; c < n_chunks; ++c) {
