@@ -223,7 +223,11 @@ BootParams make_params(nrb200_handle *h, const nrb200_draws *d) {
 template <bool ST, bool HQ>
 void launch_stream_t(nrb200_handle *h, const BootParams &P, int excl) {
     const GroupView V{h->groups_dev.as<TileGroup>(), h->tiles_sorted_dev.as<int32_t>(), h->y_se.as<int2>(), h->group_slice_cap};
-    const dim3 grid((unsigned)h->n_groups, (unsigned)P.n_iter);
+    // Few iterations (or few groups) would leave most SMs without a CTA: a group is then worked by `split` CTAs, CTA z taking
+    // the group's tiles z, z + split, ... (each stages the group's query slice for itself and flushes its own histogram).
+    const int64_t ctas = (int64_t)h->n_groups * P.n_iter, want = (int64_t)h->sm_count * kStreamMinBlocks * 2;
+    const unsigned split = (unsigned)std::max<int64_t>(1, std::min<int64_t>(kGroupTiles / 32, (want + ctas - 1) / std::max<int64_t>(ctas, 1)));
+    const dim3 grid((unsigned)h->n_groups, (unsigned)P.n_iter, split);
     const size_t smem = ((size_t)h->group_slice_cap * 21 + 15) & ~(size_t)15;
     // dynamic slice (up to 43 KB) + the static item table (14 KB) can pass the 48 KB a kernel gets without asking
     auto launch = [&](auto kernel) {

@@ -382,9 +382,11 @@ __device__ __forceinline__ void stream_tile(const BootParams &P, const GroupView
                         h0 = h0 && min(e2[0], qe) - max(s2[0], qs) + 1 >= P.minoverlap;
                         h1 = h1 && min(e2[1], qe) - max(s2[1], qs) + 1 >= P.minoverlap;
                     }
-                    // few ranges of a trip meet one feature (a handful at most): the lanes that do add for themselves
-                    red_shared_inc_if(h0, a + 4u * cap4);
-                    red_shared_inc_if(h1, a + 4u * cap4);
+                    // one add per warp and feature, whatever the density of y (with every lane adding for itself a dense y --
+                    // thousands of ranges per feature -- turned each trip into 64 serialised same-address atomics: 4x slower
+                    // at 5e7 ranges)
+                    const int n = __reduce_add_sync(kFull, (h0 ? 1 : 0) + (h1 ? 1 : 0));
+                    if (n && lane == 0) red_shared_add(a + 4u * cap4, n);
                 }
             }
         }
@@ -430,8 +432,10 @@ __global__ void __launch_bounds__(256, (!STRANDED && EXCL == kExclNone) ? kStrea
     }
     // While the copy engine works: thread j draws block j of the group and locates its hit window
     // (Philox + pick + two rank probes: ~275 instructions that 32 lanes would otherwise repeat for every tile).
-    if (threadIdx.x < grp.count) {
-        Item it = load_item(P, r, __ldg(V.tiles_sorted + grp.first + threadIdx.x));
+    // (gridDim.z > 1, small launches: this CTA works the group's tiles z, z + gridDim.z, ...: n_tiles of them)
+    const int n_tiles = (grp.count - (int)blockIdx.z + (int)gridDim.z - 1) / (int)gridDim.z;
+    if ((int)threadIdx.x < n_tiles) {
+        Item it = load_item(P, r, __ldg(V.tiles_sorted + grp.first + blockIdx.z + threadIdx.x * gridDim.z));
         it.q_lo = it.q_hi = it.x_lo = it.x_hi = 0;
         if (HAS_QUERY) {
             it.q_lo = __ldg(P.query.tile_lo + it.tile) - grp.q_lo;
@@ -456,11 +460,11 @@ __global__ void __launch_bounds__(256, (!STRANDED && EXCL == kExclNone) ? kStrea
     // them) and leave the warp once; the overlaps are read off the histogram when it leaves the CTA.
     unsigned rows_lane = 0, hits_lane = 0;
     int4 v = make_int4(0, 0, 0, 0);
-    if (warp < grp.count) v = __ldg(reinterpret_cast<const int4 *>(V.se + (s_item[warp].lo & ~1) + 2 * lane));
-    for (int j = warp; j < grp.count; j += blockDim.x / kWarp) {
+    if (warp < n_tiles) v = __ldg(reinterpret_cast<const int4 *>(V.se + (s_item[warp].lo & ~1) + 2 * lane));
+    for (int j = warp; j < n_tiles; j += blockDim.x / kWarp) {
         const Item it = s_item[j];
         const int j_next = j + blockDim.x / kWarp;
-        const int32_t next_base = (j_next < grp.count ? s_item[j_next].lo : it.lo) & ~1;  // (after the warp's last tile: a load nobody reads)
+        const int32_t next_base = (j_next < n_tiles ? s_item[j_next].lo : it.lo) & ~1;  // (after the warp's last tile: a load nobody reads)
         unsigned rows = 0;
         bool done = false;
         if constexpr (EXCL == kExclNone) {
