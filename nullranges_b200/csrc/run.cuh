@@ -507,6 +507,7 @@ int run_counts_core(nrb200_handle *h, const nrb200_draws *d, bool want_counts, i
                 char *base = host16 ? reinterpret_cast<char *>(host16) : reinterpret_cast<char *>(host_counts);
                 const size_t total = cells * (host16 ? 2 : 4);
                 constexpr uintptr_t kBlock = (uintptr_t)2 << 20;
+                const auto t_pop = std::chrono::steady_clock::now();
                 const uintptr_t first = (uintptr_t)base & ~(kBlock - 1), end = (uintptr_t)base + total;
                 for (uintptr_t blk = first + (uintptr_t)(tid - 1) * kBlock; blk < end; blk += (uintptr_t)(nth - 1) * kBlock) {
                     char *lo = reinterpret_cast<char *>(std::max(blk, (uintptr_t)base)), *hi = reinterpret_cast<char *>(std::min(blk + kBlock, end));
@@ -514,6 +515,9 @@ int run_counts_core(nrb200_handle *h, const nrb200_draws *d, bool want_counts, i
                     for (volatile char *q = lo; q < hi; q += 4096) *q = 0;  // (older kernels: one store per 4 KB page)
                     *(volatile char *)(hi - 1) = 0;
                 }
+                if (Trace::on() && tid == 1)
+                    fprintf(stderr, "[nrb200] drain/populate (thread 1 of %d) %.3f ms\n", nth,
+                            std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_pop).count());
             }
             for (int64_t c = 0; c < n_chunks; ++c) {
                 if (tid == 0) {
