@@ -181,6 +181,7 @@ __global__ void __launch_bounds__(256) boot_count_kernel(const BootParams P) {
 // The kernel is bound by instruction issue (profiles/README.md), so the loop is written for few instructions: tiles
 // that provably stay inside their sequence skip trim() and count rows as hits (Item::interior), the shared arrays are
 // addressed from one register, rows / hits leave a warp once, the total of overlaps is read off the histogram.
+// A launch with few (group, iteration) pairs gives every group to gridDim.z CTAs that take its tiles in turn (run.cuh).
 // Bootstrap kinds only (block b lands on tile b); the permute variants and slices that do not fit keep
 // boot_count_kernel.
 constexpr int kGroupTiles = 256;   // tiles per CTA at most (one thread draws each: <= the CTA's 256 threads).  The draw + hit-window
@@ -241,18 +242,6 @@ __device__ __forceinline__ void inc_if(unsigned &n, bool on) {
         : "+r"(n)
         : "r"((int)on));
 }
-// adds 1 where `on` holds, as ONE predicated instruction (no branch around it)
-__device__ __forceinline__ void red_shared_inc_if(bool on, uint32_t addr) {
-    asm volatile(
-        "{\n"
-        ".reg .pred q;\n"
-        "setp.ne.s32 q, %1, 0;\n"
-        "@q red.shared.add.s32 [%0], 1;\n"
-        "}\n" ::"r"(addr),
-        "r"((int)on)
-        : "memory");
-}
-
 struct GroupView {
     const TileGroup *groups;
     const int32_t *tiles_sorted;
