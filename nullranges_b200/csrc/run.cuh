@@ -417,6 +417,7 @@ int run_counts_core(nrb200_handle *h, const nrb200_draws *d, bool want_counts, i
         if (!h->copy_stream) NRB_CUDA(h, cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
         chunk = std::min<int64_t>(h->tune_max_batch, std::max<int64_t>(((R + h->tune_chunks - 1) / h->tune_chunks + 7) / 8 * 8, 64));
     }
+    if (pipelined) chunk = std::max(chunk, (R + kChunkEvents - 1) / kChunkEvents);  // one event / flag slot per chunk in flight
     if (rank_path_ok(h) && has_query) {
         NRB_CUDA(h, h->draw_tab.reserve((size_t)std::min(chunk, std::max<int64_t>(R, 1)) * h->plan.n_blocks() * sizeof(int2)));
         P.draw_tab = h->draw_tab.as<int2>();

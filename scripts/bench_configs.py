@@ -18,6 +18,9 @@ def report(name, R, B, G, st, extra=None):
     line = {"config": name, "path": "stream" if force_stream else "default", "iters": R, "kernel_ms": round(ms, 3),
             "iters_per_s": round(R / ms * 1e3, 1), "launches": st["n_launches"], "hits_per_iter": st["n_hits"] / max(R, 1),
             "algorithmic_GBps": round(alg / ms / 1e6, 1), "frac_of_measured_hbm": round(alg / ms / 1e6 / PEAK, 3)}
+    if not force_stream and st.get("rows_kernel_ms"):
+        line.update({"rows_kernel_ms": round(st["rows_kernel_ms"], 3), "count_kernel_ms": round(st["count_kernel_ms"], 3),
+                     "windows_per_iter": st.get("n_windows")})
     line.update(extra or {})
     print(json.dumps(line), flush=True)
 

@@ -778,6 +778,25 @@ def test_boot_moments_front_end():
 # on the host (run.cuh).  Here: the int32 path with the format switched off, pinned destinations, and a count that
 # does not fit uint16 (the chunk is redone in int32).
 
+def test_host_matrix_in_more_batches_than_chunk_slots(monkeypatch):
+    """A host-bound matrix leaves in at most 64 chunks (one copy event and one overflow-flag slot per chunk in flight): with
+    small launch batches (NRB200_MAX_BATCH) and many iterations the chunk grows instead of the slots being reused."""
+    from nullranges_b200 import Engine
+    monkeypatch.setenv("NRB200_MAX_BATCH", "8")
+    eng = Engine(0)
+    try:
+        case = H.random_case(seed=88, n=400, n_seq=3, n_query=9)
+        plan, y, q, x = H.oracle_objects(case, 0)
+        H.load_engine(eng, case, 0)
+        R = 2000  # 250 batches of 8 iterations if the chunk did not grow
+        got = eng.run_counts(Draws(n_iter=R, rng_mode=_lib.RNG_PHILOX, seed=3))
+        ref = O.boot_counts(plan, y, q, R, seed=3, iter0=0)
+        for k in ("iter_nranges", "iter_totals", "feature_counts"):
+            assert np.array_equal(got[k], ref[k]), k
+    finally:
+        eng.close()
+
+
 @pytest.mark.parametrize("wire", ["0", "1", "2"])
 @pytest.mark.parametrize("pinned", [False, True])
 def test_wire_format_variants(wire, pinned, monkeypatch):
